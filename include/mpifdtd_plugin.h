@@ -1,0 +1,200 @@
+/* mpifdtd_plugin.h -- the host-side plugin surface libmpifdtd_b200.so exports.
+ *
+ * Every symbol below keeps the name, argument meaning and error behaviour
+ * (printf + exit(2)) of the reference interface it replaces, so the reference's
+ * own driver (main.c) and viewer (drawer.c) link against this library instead of
+ * the reference's simulator/field/models/solver objects.  Citations are
+ * file:line into rennone/mpiFDTD.  Host code is C99; the time-stepping itself
+ * runs on the GPU behind include/b200fdtd.h.
+ *
+ * A translation unit may include either this header or the reference's own
+ * headers (simulator.h, field.h, models.h, ...): the declarations are ABI
+ * identical.
+ */
+#ifndef MPIFDTD_PLUGIN_H
+#define MPIFDTD_PLUGIN_H
+
+#include <complex.h>
+#include <stdio.h>
+
+#ifdef __cplusplus
+#error "C99 host interface (uses double complex); bind the engine through b200fdtd.h from C++"
+#endif
+
+#ifndef bool                 /* bool.h:1-18 of the reference: bool is int */
+#define bool int
+#define true 1
+#define false 0
+#endif
+
+typedef double complex dcomplex;          /* myComplex.h:6 */
+
+/* ---- units and constants (field.h:70-75) ------------------------------- */
+#define C_0_S 0.7071                      /* deliberately not 1/sqrt(2) */
+static const double LIGHT_SPEED_S = 0.7071;
+static const double EPSILON_0_S = 1.0;
+static const double MU_0_S = 1.0 / C_0_S / C_0_S;
+static const double Z_0_S = 1.41422712488;
+
+/* ---- grid / wave / far-field descriptors (field.h:20-68) ---------------- */
+typedef struct FieldInfo {
+  int width_nm, height_nm;   /* physical size of the region            */
+  int h_u_nm;                /* cell edge                               */
+  int pml;                   /* PML thickness in cells                  */
+  int lambda_nm;             /* wavelength                              */
+  int angle_deg;             /* incidence angle                         */
+  int stepNum;               /* number of time steps                    */
+} FieldInfo;
+
+typedef struct FieldInfo_S {
+  int N_X, N_Y;              /* cells without PML */
+  int N_PX, N_PY;            /* cells with PML    */
+  int N_CELL;
+  int N_PML;
+  int DX, DY;                /* index strides: DX = N_PY, DY = 1 */
+} FieldInfo_S;
+
+typedef struct SubFieldInfo_S {
+  int OFFSET_X, OFFSET_Y;
+  int SUB_N_X, SUB_N_Y;
+  int SUB_N_PX, SUB_N_PY;
+  int SUB_N_CELL;
+  int Rank;
+  int RtRank, LtRank, TpRank, BmRank;
+} SubFieldInfo_S;
+
+typedef struct WaveInfo_S {
+  double Lambda_s, T_s, Omega_s, K_s, K_0_s, Angle_deg;
+} WaveInfo_S;
+
+typedef struct NFFInfo {
+  int top, bottom, left, right;
+  int cx, cy;
+  double RFperC;
+  int arraySize;
+} NTFFInfo;
+
+/* globals kept for source compatibility (field.h:77-82) */
+extern int N_X, N_Y, N_CELL, N_PML, N_PX, N_PY;
+
+/* ---- grid / time services (field.h:102-163) ----------------------------- */
+extern void field_init(FieldInfo field_info);                 /* field.c:89  */
+extern void field_reset(void);                                /* field.c:83  */
+extern void field_nextStep(void);                             /* field.c:312 */
+extern bool field_isFinish(void);                             /* field.c:317 */
+extern void field_setWaveAngle(int deg);                      /* field.c:39  */
+extern double field_sigmaX(double x, double y);               /* field.c:259 */
+extern double field_sigmaY(double x, double y);               /* field.c:272 */
+extern double field_pmlCoef(double ep_mu, double sig);        /* field.c:288 */
+extern double field_pmlCoef_LXY(double ep_mu, double sig);    /* field.c:292 */
+extern double field_ns_beta(double alpha, double alpha_aster);        /* field.c:298 */
+extern double field_ns_beta_aster(double alpha, double alpha_aster);  /* field.c:304 */
+extern double field_toCellUnit(const double);                 /* field.c:76  */
+extern double field_toPhisycalUnit(const double);             /* field.c:79  */
+extern double field_getT(void);
+extern double field_getK(void);
+extern double field_getRayCoef(void);
+extern double field_getOmega(void);
+extern double field_getLambda(void);
+extern double field_getWaveAngle(void);
+extern double field_getTime(void);
+extern double field_getMaxTime(void);
+extern NTFFInfo field_getNTFFInfo(void);
+extern WaveInfo_S field_getWaveInfo_S(void);
+extern SubFieldInfo_S field_getSubFieldInfo_S(void);
+extern FieldInfo_S field_getFieldInfo_S(void);
+extern FieldInfo field_getFieldInfo(void);
+extern int field_getOffsetX(void), field_getOffsetY(void);
+extern int field_getSubNx(void), field_getSubNy(void);
+extern int field_getSubNpx(void), field_getSubNpy(void), field_getSubNcell(void);
+extern int ind(const int, const int);                         /* field.c:74 */
+extern int field_index(int i, int j);                         /* field.c:70 */
+extern int field_subIndex(int i, int j);                      /* field.c:66 */
+extern dcomplex field_pointLight(void);                       /* field.c:145 */
+extern void field_outputElliptic(const char *fileName, double complex *data);      /* field.c:322 */
+extern void field_outputAllDataComplex(const char *fileName, double complex *data);/* field.c:346 */
+extern void field_outputAllDataDouble(const char *fileName, double *data);         /* field.c:368 */
+/* field_scattered*(), the host-array source injectors of field.h:143-149, are NOT
+ * exported: source injection is fused into the GPU E-phase kernel. */
+
+/* ---- material models (models.h:5-31) ------------------------------------ */
+enum MODEL { NO_MODEL, MIE_CYLINDER, LAYER, MORPHO_SCALE, CONCENTRIC_CIRCLE, ZIGZAG, TRACE_IMAGE };
+enum MODE { D_X, D_Y, D_XY };
+extern void models_setModel(enum MODEL model);                /* models.c:105 */
+extern double models_eps(double x, double y, enum MODE mode); /* models.c:132 */
+extern bool models_isFinish(void);                            /* models.c:92  */
+extern void models_moveDirectory(void);                       /* models.c:98  */
+extern void models_needSize(int *x_nm, int *y_nm);            /* models.c:152 */
+extern void models_initModel(void);                           /* models.c:157 */
+
+/* ---- the solver table (simulator.h:8-31, simulator.c:19-27) ------------- */
+enum SOLVER { TM_2D, TE_2D, TM_UPML_2D, TE_UPML_2D, MPI_TM_UPML_2D, MPI_TE_UPML_2D,
+              NS_TM_2D, NS_TE_2D };
+extern void simulator_setSolver(enum SOLVER solverType);      /* simulator.c:221 */
+extern void simulator_init(FieldInfo field_info);             /* simulator.c:226 */
+extern void simulator_calc(void);                             /* simulator.c:215 */
+extern bool simulator_isFinish(void);                         /* simulator.c:270 */
+extern void simulator_finish(void);                           /* simulator.c:257 */
+extern void simulator_reset(void);                            /* simulator.c:243 */
+extern void simulator_solverInit(void);                       /* simulator.c:236 */
+extern void simulator_changeModelAndRestart(void);            /* simulator.c:252 */
+extern double complex *simulator_getDrawingData(void);        /* simulator.c:266 */
+extern double *simulator_getEps(void);                        /* simulator.c:276 */
+extern void simulator_moveDirectory(void);                    /* simulator.c:209 */
+
+/* per-solver entry points the table is filled from (fdtdTM_upml.h:5-14 etc.).
+ * Getters return borrowed host pointers, index k = i*N_PY + j, valid from init
+ * until finish; each call refreshes the host mirror from device memory. */
+#define MPIFDTD_DECLARE_SOLVER(P, A, B, Cc)                   \
+  extern void (*P##_getUpdate(void))(void);                  \
+  extern void (*P##_getFinish(void))(void);                  \
+  extern void (*P##_getReset(void))(void);                   \
+  extern void (*P##_getInit(void))(void);                    \
+  extern double complex *P##_get##A(void);                   \
+  extern double complex *P##_get##B(void);                   \
+  extern double complex *P##_get##Cc(void);                  \
+  extern double *P##_getEps(void);
+MPIFDTD_DECLARE_SOLVER(fdtdTM_upml, Hx, Hy, Ez)               /* fdtdTM_upml.h:5-14 */
+MPIFDTD_DECLARE_SOLVER(fdtdTE_upml, Ex, Ey, Hz)               /* fdtdTE_upml.h:5-14 */
+MPIFDTD_DECLARE_SOLVER(mpi_fdtdTM_upml, Hx, Hy, Ez)           /* mpiTM_UPML.h:5-12  */
+MPIFDTD_DECLARE_SOLVER(mpi_fdtdTE_upml, Ex, Ey, Hz)           /* mpiTE_UPML.h       */
+MPIFDTD_DECLARE_SOLVER(fdtdTM, Hx, Hy, Ez)                    /* fdtdTM.h:5-17      */
+MPIFDTD_DECLARE_SOLVER(fdtdTE, Ex, Ey, Hz)                    /* fdtdTE.h:5-17      */
+MPIFDTD_DECLARE_SOLVER(nsFdtdTM, Hx, Hy, Ez)                  /* nsFdtdTM.h:5-19    */
+MPIFDTD_DECLARE_SOLVER(nsFdtdTE, Ex, Ey, Hz)                  /* nsFdtdTE.h:5-19    */
+
+/* ---- far-field output format (ntff.h:4-9) ------------------------------- */
+#define LAMBDA_ST_NM 380
+#define LAMBDA_EN_NM 700
+#define NTFF_NUM 8192
+extern void ntff_outputEnormTxt(double **e_norm, const char *file_name);  /* ntff.c:6  */
+extern void ntff_outputEnormBin(double **e_norm, const char *file_name);  /* ntff.c:21 */
+
+/* ---- config.txt (parser.h:5, configSample.txt:6-22, main.c:319-366) ------ */
+extern bool parser_nextLine(FILE *fp, char buf[]);            /* parser.c:3 */
+typedef struct MpifdtdConfig {
+  FieldInfo field_info;
+  int startAngle, endAngle, deltaAngle;
+  int ModelType, SolverType;
+} MpifdtdConfig;
+/* Reads the 11 values of configSample.txt in order (width, height, h_u, pml,
+ * lambda, step, start/end/delta angle, model id, solver id).  Returns 0 on
+ * success; on a missing file or a short file prints and exit(2)s like the
+ * reference's readConfig (main.c:319-366, commented out upstream). */
+extern int mpifdtd_readConfig(const char *path, MpifdtdConfig *out);
+
+/* ---- small utilities main.c / drawer.c pull in (function.h, myComplex.h) -- */
+extern double *newDouble(int size);
+extern void freeDouble(double *array);
+extern dcomplex *newDComplex(int size);
+extern void freeDComplex(dcomplex *array);
+extern double cnorm(dcomplex c);                              /* squared magnitude */
+extern double complex cbilinear(dcomplex *p, double x, double y, int width, int height);
+extern double dbilinear(double *p, double x, double y, int width, int height);
+extern FILE *openFile(const char *file_name);
+extern FILE *FileOpen(const char *file_name, const char *mode);
+extern bool makeDirectory(const char *);
+extern void moveDirectory(const char *);
+extern void makeAndMoveDirectory(const char *);
+
+#endif /* MPIFDTD_PLUGIN_H */
