@@ -1,0 +1,223 @@
+/* b200fdtd.h -- C ABI of the B200 (sm_100a) FDTD time-stepping engine.
+ *
+ * This is the drop-in boundary for the hot path of rennone/mpiFDTD: everything
+ * the reference does per time step inside a solver's update() -- the UPML E/H
+ * leapfrog with its J/D and M/B recurrences, source injection, and the NTFF
+ * surface accumulation -- plus the once-per-run far-field post-processing.
+ * Plain pointers and sizes only; no CUDA or torch types.  The host-side C shims
+ * in mpifdtd_b200/csrc/host (symbols fdtdTM_upml_getUpdate etc., see
+ * mpifdtd_plugin.h) call these functions; other hosts (ctypes, cgo, JNI) can
+ * bind them directly.
+ *
+ * All functions return B200FDTD_OK (0) or a B200FDTD_ERR_* code;
+ * b200fdtd_last_error() returns a message for the calling thread's last
+ * failure.  There is no CPU fallback: without a CUDA device every entry point
+ * that would compute returns B200FDTD_ERR_NODEVICE.
+ *
+ * Index convention: host arrays are the reference's, k = i*N_PY + j (x slow, y
+ * fast; field.c:70-72).  Complex values are interleaved (re, im) doubles, the
+ * memory layout of C99 double complex.
+ */
+#ifndef B200FDTD_H
+#define B200FDTD_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200FDTD_ABI_VERSION 1
+
+enum {
+  B200FDTD_OK = 0,
+  B200FDTD_ERR_ARG = 1,       /* bad argument / unsupported combination       */
+  B200FDTD_ERR_CUDA = 2,      /* a CUDA runtime call failed                    */
+  B200FDTD_ERR_NOMEM = 3,     /* host or device allocation failed              */
+  B200FDTD_ERR_STATE = 4,     /* call order violated (e.g. step before tables) */
+  B200FDTD_ERR_NODEVICE = 5   /* no usable CUDA device                         */
+};
+
+/* Solver kinds; numeric values are enum SOLVER of simulator.h:8-18. */
+enum {
+  B200FDTD_TM = 0, B200FDTD_TE = 1,
+  B200FDTD_TM_UPML = 2, B200FDTD_TE_UPML = 3,
+  B200FDTD_MPI_TM_UPML = 4, B200FDTD_MPI_TE_UPML = 5,
+  B200FDTD_NS_TM = 6, B200FDTD_NS_TE = 7
+};
+
+/* Field slots.  UPML kinds keep 9 complex arrays (fdtdTM_upml.c:15-25,
+ * fdtdTE_upml.c:15-25): */
+enum { B200FDTD_TM_EZ = 0, B200FDTD_TM_JZ, B200FDTD_TM_DZ, B200FDTD_TM_HX, B200FDTD_TM_MX,
+       B200FDTD_TM_BX, B200FDTD_TM_HY, B200FDTD_TM_MY, B200FDTD_TM_BY };
+enum { B200FDTD_TE_EX = 0, B200FDTD_TE_JX, B200FDTD_TE_DX, B200FDTD_TE_EY, B200FDTD_TE_JY,
+       B200FDTD_TE_DY, B200FDTD_TE_HZ, B200FDTD_TE_MZ, B200FDTD_TE_BZ };
+#define B200FDTD_MAX_FIELDS 9
+
+/* 1-D coefficient tables of the UPML kinds.  The reference stores 15 dense
+ * N_CELL arrays per solver (fdtdTM_upml.c:30-35); because every one of them is
+ * built with eps = EPSILON_0_S (fdtdTM_upml.c:253, fdtdTE_upml.c:390) each is a
+ * function of i only, of j only, exactly 1, or a j-term divided by an i-term.
+ * The host passes the i-terms as tab_i[slot*n_px + i] and the j-terms as
+ * tab_j[slot*n_py + j], computed with the reference's own expressions. */
+enum { /* TM, by i */ B200FDTD_TMI_C_JZ = 0, B200FDTD_TMI_C_JZHXHY, B200FDTD_TMI_C_BXMX1,
+       B200FDTD_TMI_C_BXMX0, B200FDTD_TMI_C_BY, B200FDTD_TMI_DEN_BYMY,   /* 2eps + sig_hy_x */
+       /* TM, by j */ B200FDTD_TMJ_C_DZ = 0, B200FDTD_TMJ_C_DZJZ, B200FDTD_TMJ_C_MX,
+       B200FDTD_TMJ_C_MXEZ, B200FDTD_TMJ_NUM_BYMY1 /* 2eps + sig_hy_y */,
+       B200FDTD_TMJ_NUM_BYMY0 /* 2eps - sig_hy_y */ };
+enum { /* TE, by i */ B200FDTD_TEI_C_DXJX1 = 0, B200FDTD_TEI_C_DXJX0, B200FDTD_TEI_C_DY,
+       B200FDTD_TEI_DEN_DYJY /* 2eps + sig_ey_x */, B200FDTD_TEI_C_MZ, B200FDTD_TEI_C_MZEXEY,
+       /* TE, by j */ B200FDTD_TEJ_C_JX = 0, B200FDTD_TEJ_C_JXHZ, B200FDTD_TEJ_NUM_DYJY1,
+       B200FDTD_TEJ_NUM_DYJY0, B200FDTD_TEJ_C_BZ, B200FDTD_TEJ_C_BZMZ };
+#define B200FDTD_UPML_TABS 6
+
+typedef struct b200fdtd_engine b200fdtd_engine;   /* opaque */
+
+/* Geometry of one engine = one y-slab of the global grid on one GPU.
+ * Replaces field_init's FieldInfo_S (field.c:94-121) plus, for multi-GPU runs,
+ * the MPI sub-domain of mpiTM_UPML.c:718-748 (here a 1-D split along y). */
+typedef struct b200fdtd_grid {
+  int32_t kind;             /* B200FDTD_* solver kind                              */
+  int32_t n_px, n_py;       /* global cells incl. PML                              */
+  int32_t n_pml;
+  int32_t j0, nj;           /* this engine owns global columns j in [j0, j0+nj)    */
+  int32_t i_lo, i_hi;       /* updated cells, inclusive, global; the serial solvers */
+  int32_t j_lo, j_hi;       /*   use 1 .. N-2 (fdtdTM_upml.c:158-159)              */
+  int32_t device;           /* CUDA device ordinal, or -1 for the current device   */
+  int32_t reserved;
+  double mu0;               /* MU_0_S, passed so the divisor is the host's value   */
+} b200fdtd_grid;
+
+/* Scattered-field Gaussian pulse, field_scatteredPulse (field.c:224-256):
+ * p[k] += dot*exp(-(r/beam_width)^2)*(eps0/eps[k]-1)*cexp(i*r*omega) on cells with
+ * eps != eps0, r = (i+gap_x)*cos_per_c + (j+gap_y)*sin_per_c - time_minus_t0. */
+typedef struct b200fdtd_pulse {
+  int32_t enabled, reserved;
+  double gap_x, gap_y, dot;
+  double cos_per_c, sin_per_c;     /* cos(rad)/C_0_S, sin(rad)/C_0_S from host libm  */
+  double time_minus_t0;            /* (time - t0), t0 = -center_peak + 500            */
+  double omega, beam_width;
+} b200fdtd_pulse;
+
+/* Opt-in soft-started point source for the NoModel configuration:
+ * value field_pointLight() (field.c:145-152) added to E-slot 0 at (i, j). */
+typedef struct b200fdtd_point_source {
+  int32_t enabled, i, j, reserved;
+  double re, im;
+} b200fdtd_point_source;
+
+/* Everything one update() call depends on that the host owns (field.c:44-51). */
+typedef struct b200fdtd_step_args {
+  double time;                     /* field_getTime() BEFORE field_nextStep()         */
+  double ray_coef;                 /* field_getRayCoef()                              */
+  b200fdtd_pulse pulse[2];         /* TM: [0] on Ez.  TE: [0] on Ex, [1] on Ey        */
+  b200fdtd_point_source point;
+} b200fdtd_step_args;
+
+/* Closed NTFF surface (NTFFInfo, field.h:62-68) and its sampling plan.
+ * Perimeter points are ordered bottom (i = left..right-1), right (j =
+ * bottom..top-1), top (i = left..right-1), left (j = bottom..top-1), the loop
+ * order of ntffTM_TimeCalc (ntffTM.c:326-369).  time_shift[a*n_points + p] is the
+ * reference's running timeShift for angle a at point p, built on the host by the
+ * same repeated subtraction (ntffTM.c:329-334). */
+typedef struct b200fdtd_ntff_plan {
+  int32_t top, bottom, left, right;
+  int32_t n_points;                /* 2(right-left) + 2(top-bottom)                  */
+  int32_t max_time;                /* steps sampled = length of each point's history  */
+  int32_t n_bins;                  /* bins kept per angle in U/W (>= max_time to      */
+                                   /*   mirror arraySize; max_time suffices for the   */
+                                   /*   far field, ntffTM.c:181)                      */
+  int32_t n_angles;                /* 360                                             */
+  int32_t array_size;              /* NTFFInfo.arraySize: the reference keeps U/W as  */
+                                   /* one [360][arraySize] block, and its last-step   */
+                                   /* taps at index == arraySize land in the NEXT     */
+                                   /* direction's bin 0 (ntffTM.c:285-287 has no      */
+                                   /* bound check).  The projection reproduces that   */
+                                   /* spill; 0 disables it.                           */
+  int32_t reserved;
+  const double *time_shift;        /* host, [n_angles][n_points]                      */
+} b200fdtd_ntff_plan;
+
+/* Far-field post-processing, ntffT?_TimeTranslate + TimeOutput
+ * (ntffTM.c:161-232, ntffTE.c:20-55,160-195). */
+typedef struct b200fdtd_spectrum_args {
+  double coef_re, coef_im;         /* 1/(4 pi C) * csqrt(2 pi C/(i omega))            */
+  double z0;                       /* Z_0_S                                           */
+  const double *cos_phi, *sin_phi; /* host [n_angles], cos/sin(ang*pi/180)            */
+  int32_t n_fft;                   /* NTFF_NUM = 8192                                 */
+  int32_t lambda_first_nm, lambda_last_nm;   /* 380, 700                             */
+  int32_t reserved;
+  double c_hu_nfft;                /* C_0_S * h_u_nm * NTFF_NUM                       */
+  const double *twiddle;           /* host, interleaved complex, stage-major: for     */
+                                   /* half = n/2, n/4, .. 1: cexp(i*pi/half*k), k<half */
+} b200fdtd_spectrum_args;
+
+/* ---- lifetime ----------------------------------------------------------- */
+int b200fdtd_device_count(int *count);
+const char *b200fdtd_last_error(void);
+int b200fdtd_abi_version(void);
+
+int b200fdtd_create(const b200fdtd_grid *grid, b200fdtd_engine **out);   /* allocateMemories */
+int b200fdtd_destroy(b200fdtd_engine *e);                                /* freeMemories     */
+
+/* Pinned host memory for mirrors the getters hand out (cudaHostAlloc). */
+int b200fdtd_host_alloc(void **ptr, uint64_t bytes);
+int b200fdtd_host_free(void *ptr);
+
+/* ---- init-time uploads --------------------------------------------------- */
+/* setCoefficient (fdtdTM_upml.c:224-274, fdtdTE_upml.c:361-412) */
+int b200fdtd_set_upml_tables(b200fdtd_engine *e, const double *tab_i, const double *tab_j);
+/* eps_slot: TM 0 = EPS_EZ; TE 0 = EPS_EX, 1 = EPS_EY.  host_eps is the full
+ * [n_px][n_py] map; the engine takes its slab. */
+int b200fdtd_set_eps(b200fdtd_engine *e, int32_t eps_slot, const double *host_eps);
+int b200fdtd_set_ntff_plan(b200fdtd_engine *e, const b200fdtd_ntff_plan *plan);   /* ntffTM_init */
+
+/* ---- the hot path -------------------------------------------------------- */
+/* One update() (fdtdTM_upml.c:54-66 / fdtdTE_upml.c:168-192): H phase, E phase
+ * with source, NTFF surface sample.  Asynchronous on the engine's stream. */
+int b200fdtd_step(b200fdtd_engine *e, const b200fdtd_step_args *args);
+/* The same, split so a multi-GPU driver can exchange halos between phases. */
+int b200fdtd_phase_h(b200fdtd_engine *e, const b200fdtd_step_args *args);
+int b200fdtd_phase_e(b200fdtd_engine *e, const b200fdtd_step_args *args);
+int b200fdtd_phase_sample(b200fdtd_engine *e, const b200fdtd_step_args *args);
+int b200fdtd_sync(b200fdtd_engine *e);
+
+/* Halo columns for the y-slab split (replaces Connection_ISend_IRecvH/E,
+ * mpiTM_UPML.c:252-296).  which: 0 = after the H phase (TM Hx / TE Hz, my last
+ * owned column -> upper neighbour's low ghost), 1 = after the E phase (TM Ez / TE
+ * Ex, my first owned column -> lower neighbour's high ghost).  dev_buf is a
+ * device pointer to n_px complex values. */
+int b200fdtd_halo_pack(b200fdtd_engine *e, int32_t which, void *dev_buf);
+int b200fdtd_halo_unpack(b200fdtd_engine *e, int32_t which, const void *dev_buf);
+/* Launch everything on this CUDA stream (a cudaStream_t) from now on. */
+int b200fdtd_set_stream(b200fdtd_engine *e, void *cuda_stream);
+
+/* ---- state access (synchronous) ------------------------------------------ */
+/* getters: device slab -> host [n_px][n_py] complex array, columns [j0, j0+nj) */
+int b200fdtd_get_field(b200fdtd_engine *e, int32_t slot, double *host_complex);
+int b200fdtd_set_field(b200fdtd_engine *e, int32_t slot, const double *host_complex);
+int b200fdtd_zero_state(b200fdtd_engine *e);        /* the memsets of reset(), fdtdTM_upml.c:98-113 */
+
+/* ---- NTFF ---------------------------------------------------------------- */
+/* Turn the recorded surface history into U/W[3][n_angles][n_bins]
+ * (ntffTM_TimeCalc's accumulation, ntffTM.c:279-371, deferred).  Slots: TM
+ * Ux,Uy,Wz; TE Wx,Wy,Uz. */
+int b200fdtd_ntff_project(b200fdtd_engine *e);
+int b200fdtd_ntff_get_uw(b200fdtd_engine *e, int32_t slot, double *host_complex);
+/* device pointer + element count of the whole U/W block, for an NCCL reduce */
+int b200fdtd_ntff_uw_device(b200fdtd_engine *e, void **dev_ptr, uint64_t *n_doubles);
+/* out[(lambda-lambda_first)*n_angles + ang], the table ntff_outputEnormBin writes */
+int b200fdtd_ntff_spectrum(b200fdtd_engine *e, const b200fdtd_spectrum_args *args, double *out);
+
+/* ---- introspection -------------------------------------------------------- */
+/* kernels launched by this engine since creation (bench.py's gpu_launches) */
+int b200fdtd_launch_count(b200fdtd_engine *e, uint64_t *count);
+int b200fdtd_device_bytes(b200fdtd_engine *e, uint64_t *bytes);
+/* CUDA-event timing on the engine's stream: elapsed ms between the two marks */
+int b200fdtd_timer_start(b200fdtd_engine *e);
+int b200fdtd_timer_stop(b200fdtd_engine *e, float *elapsed_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200FDTD_H */

@@ -1,0 +1,392 @@
+"""ctypes view of libmpifdtd_b200.so for the Python harness (tests, bench.py).
+
+Python is plumbing here, not the product: the product is the C plugin surface
+(include/mpifdtd_plugin.h) over the CUDA engine (include/b200fdtd.h).  This
+module only declares argument types and wraps the two layers the way the
+reference's own driver uses them (main.c:150-213):
+
+    Plugin  -- models_setModel / simulator_setSolver / simulator_init / _calc /
+               _reset / _finish and the borrowed-pointer getters
+    Engine  -- the engine C ABI, for slab (multi-GPU) runs and kernel-level tests
+
+There is no fallback: if the shared library is missing the import fails loudly.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmpifdtd_b200.so")
+
+MODELS = dict(NO_MODEL=0, MIE_CYLINDER=1, LAYER=2, MORPHO_SCALE=3,
+              CONCENTRIC_CIRCLE=4, ZIGZAG=5, TRACE_IMAGE=6)
+SOLVERS = dict(TM_2D=0, TE_2D=1, TM_UPML_2D=2, TE_UPML_2D=3,
+               MPI_TM_UPML_2D=4, MPI_TE_UPML_2D=5, NS_TM_2D=6, NS_TE_2D=7)
+D_X, D_Y, D_XY = 0, 1, 2
+UPML_TABS = 6
+
+
+class FieldInfo(C.Structure):
+    _fields_ = [("width_nm", C.c_int), ("height_nm", C.c_int), ("h_u_nm", C.c_int),
+                ("pml", C.c_int), ("lambda_nm", C.c_int), ("angle_deg", C.c_int),
+                ("stepNum", C.c_int)]
+
+
+class FieldInfoS(C.Structure):
+    _fields_ = [("N_X", C.c_int), ("N_Y", C.c_int), ("N_PX", C.c_int), ("N_PY", C.c_int),
+                ("N_CELL", C.c_int), ("N_PML", C.c_int), ("DX", C.c_int), ("DY", C.c_int)]
+
+
+class NTFFInfo(C.Structure):
+    _fields_ = [("top", C.c_int), ("bottom", C.c_int), ("left", C.c_int), ("right", C.c_int),
+                ("cx", C.c_int), ("cy", C.c_int), ("RFperC", C.c_double), ("arraySize", C.c_int)]
+
+
+class Grid(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("n_px", C.c_int32), ("n_py", C.c_int32), ("n_pml", C.c_int32),
+                ("j0", C.c_int32), ("nj", C.c_int32), ("i_lo", C.c_int32), ("i_hi", C.c_int32),
+                ("j_lo", C.c_int32), ("j_hi", C.c_int32), ("device", C.c_int32),
+                ("reserved", C.c_int32), ("mu0", C.c_double)]
+
+
+class Pulse(C.Structure):
+    _fields_ = [("enabled", C.c_int32), ("reserved", C.c_int32), ("gap_x", C.c_double),
+                ("gap_y", C.c_double), ("dot", C.c_double), ("cos_per_c", C.c_double),
+                ("sin_per_c", C.c_double), ("time_minus_t0", C.c_double), ("omega", C.c_double),
+                ("beam_width", C.c_double)]
+
+
+class PointSource(C.Structure):
+    _fields_ = [("enabled", C.c_int32), ("i", C.c_int32), ("j", C.c_int32), ("reserved", C.c_int32),
+                ("re", C.c_double), ("im", C.c_double)]
+
+
+class StepArgs(C.Structure):
+    _fields_ = [("time", C.c_double), ("ray_coef", C.c_double), ("pulse", Pulse * 2),
+                ("point", PointSource)]
+
+
+class NtffPlan(C.Structure):
+    _fields_ = [("top", C.c_int32), ("bottom", C.c_int32), ("left", C.c_int32), ("right", C.c_int32),
+                ("n_points", C.c_int32), ("max_time", C.c_int32), ("n_bins", C.c_int32),
+                ("n_angles", C.c_int32), ("array_size", C.c_int32), ("reserved", C.c_int32),
+                ("time_shift", C.c_void_p)]
+
+
+class SpectrumArgs(C.Structure):
+    _fields_ = [("coef_re", C.c_double), ("coef_im", C.c_double), ("z0", C.c_double),
+                ("cos_phi", C.c_void_p), ("sin_phi", C.c_void_p), ("n_fft", C.c_int32),
+                ("lambda_first_nm", C.c_int32), ("lambda_last_nm", C.c_int32),
+                ("reserved", C.c_int32), ("c_hu_nfft", C.c_double), ("twiddle", C.c_void_p)]
+
+
+C_0_S = 0.7071
+MU_0_S = 1.0 / C_0_S / C_0_S
+Z_0_S = 1.41422712488
+
+_lib = None
+
+
+def lib():
+    """The shared library, loaded once.  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(there is no CPU fallback)" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp, i32, dbl = C.c_void_p, C.c_int32, C.c_double
+    L.b200fdtd_last_error.restype = C.c_char_p
+    L.b200fdtd_create.argtypes = [C.POINTER(Grid), C.POINTER(vp)]
+    L.b200fdtd_destroy.argtypes = [vp]
+    L.b200fdtd_device_count.argtypes = [C.POINTER(C.c_int)]
+    L.b200fdtd_host_alloc.argtypes = [C.POINTER(vp), C.c_uint64]
+    L.b200fdtd_host_free.argtypes = [vp]
+    L.b200fdtd_set_upml_tables.argtypes = [vp, vp, vp]
+    L.b200fdtd_set_eps.argtypes = [vp, i32, vp]
+    L.b200fdtd_set_ntff_plan.argtypes = [vp, C.POINTER(NtffPlan)]
+    for fn in ("b200fdtd_step", "b200fdtd_phase_h", "b200fdtd_phase_e", "b200fdtd_phase_sample"):
+        getattr(L, fn).argtypes = [vp, C.POINTER(StepArgs)]
+    L.b200fdtd_sync.argtypes = [vp]
+    L.b200fdtd_halo_pack.argtypes = [vp, i32, vp]
+    L.b200fdtd_halo_unpack.argtypes = [vp, i32, vp]
+    L.b200fdtd_set_stream.argtypes = [vp, vp]
+    L.b200fdtd_get_field.argtypes = [vp, i32, vp]
+    L.b200fdtd_set_field.argtypes = [vp, i32, vp]
+    L.b200fdtd_zero_state.argtypes = [vp]
+    L.b200fdtd_ntff_project.argtypes = [vp]
+    L.b200fdtd_ntff_get_uw.argtypes = [vp, i32, vp]
+    L.b200fdtd_ntff_uw_device.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_uint64)]
+    L.b200fdtd_ntff_spectrum.argtypes = [vp, C.POINTER(SpectrumArgs), vp]
+    L.b200fdtd_launch_count.argtypes = [vp, C.POINTER(C.c_uint64)]
+    L.b200fdtd_device_bytes.argtypes = [vp, C.POINTER(C.c_uint64)]
+    L.b200fdtd_timer_start.argtypes = [vp]
+    L.b200fdtd_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
+    # plugin surface
+    L.field_init.argtypes = [FieldInfo]
+    L.simulator_init.argtypes = [FieldInfo]
+    L.models_setModel.argtypes = [C.c_int]
+    L.simulator_setSolver.argtypes = [C.c_int]
+    L.simulator_isFinish.restype = C.c_int
+    L.simulator_getEps.restype = vp
+    L.simulator_getDrawingData.restype = vp
+    L.models_eps.argtypes = [dbl, dbl, C.c_int]
+    L.models_eps.restype = dbl
+    L.field_sigmaX.argtypes = [dbl, dbl]
+    L.field_sigmaX.restype = dbl
+    L.field_sigmaY.argtypes = [dbl, dbl]
+    L.field_sigmaY.restype = dbl
+    L.field_getNTFFInfo.restype = NTFFInfo
+    L.field_getFieldInfo_S.restype = FieldInfoS
+    for fn in ("field_getTime", "field_getMaxTime", "field_getOmega", "field_getK",
+               "field_getRayCoef", "field_getWaveAngle", "field_getLambda", "field_getT"):
+        getattr(L, fn).restype = dbl
+    L.field_setWaveAngle.argtypes = [C.c_int]
+    L.mpifdtd_fill_eps.argtypes = [vp, dbl, dbl, C.c_int]
+    L.mpifdtd_upml_dense_coefficient.argtypes = [C.c_int, C.c_char_p, vp]
+    L.mpifdtd_ntff_time_shift.argtypes = [C.POINTER(NTFFInfo), C.c_int, dbl]
+    L.mpifdtd_ntff_time_shift.restype = vp
+    L.mpifdtd_ntff_point_count.argtypes = [C.POINTER(NTFFInfo)]
+    L.mpifdtd_fft_twiddles.argtypes = [C.c_int]
+    L.mpifdtd_fft_twiddles.restype = vp
+    L.mpifdtd_ntff_direction_cosines.argtypes = [C.c_int, C.c_int, vp, vp]
+    L.mpifdtd_upml_engine.argtypes = [C.c_int]
+    L.mpifdtd_upml_engine.restype = vp
+    L.mpifdtd_enablePointSource.argtypes = [C.c_int]
+    L.mpifdtd_readConfig.argtypes = [C.c_char_p, vp]
+    for name in ("fdtdTM_upml_getHx", "fdtdTM_upml_getHy", "fdtdTM_upml_getEz",
+                 "fdtdTE_upml_getEx", "fdtdTE_upml_getEy", "fdtdTE_upml_getHz",
+                 "fdtdTM_upml_getEps", "fdtdTE_upml_getEps"):
+        getattr(L, name).restype = vp
+    L.free.argtypes = [vp]
+    _lib = L
+    return L
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+def check(rc, what=""):
+    if rc != 0:
+        raise EngineError("%s failed (%d): %s" % (what, rc, lib().b200fdtd_last_error().decode()))
+
+
+def device_count():
+    n = C.c_int(0)
+    lib().b200fdtd_device_count(C.byref(n))
+    return n.value
+
+
+def _as_complex(ptr, n_px, n_py):
+    buf = (C.c_double * (2 * n_px * n_py)).from_address(ptr)
+    return np.frombuffer(buf, dtype=np.complex128).reshape(n_px, n_py)
+
+
+class Plugin:
+    """The reference's driver sequence against the plugin surface."""
+
+    GETTERS = {2: dict(Hx="fdtdTM_upml_getHx", Hy="fdtdTM_upml_getHy", Ez="fdtdTM_upml_getEz"),
+               3: dict(Ex="fdtdTE_upml_getEx", Ey="fdtdTE_upml_getEy", Hz="fdtdTE_upml_getHz")}
+
+    def __init__(self, model, solver, n_px, n_py=None, steps=100, h_u_nm=10, pml=10,
+                 lambda_nm=500, angle_deg=0, point_source=False):
+        self.L = lib()
+        self.model = MODELS[model] if isinstance(model, str) else int(model)
+        self.solver = SOLVERS[solver] if isinstance(solver, str) else int(solver)
+        n_py = n_px if n_py is None else n_py
+        self.n_px, self.n_py, self.steps = n_px, n_py, steps
+        self.info = FieldInfo(n_px * h_u_nm, n_py * h_u_nm, h_u_nm, pml, lambda_nm, angle_deg, steps)
+        self.L.mpifdtd_enablePointSource(1 if point_source else 0)
+        self.L.models_setModel(self.model)
+        self.L.simulator_setSolver(self.solver)
+        self.L.simulator_init(self.info)
+        self.finished = False
+
+    def engine_handle(self):
+        return self.L.mpifdtd_upml_engine(self.solver)
+
+    def step(self, n=1):
+        for _ in range(n):
+            self.L.simulator_calc()
+
+    def run(self):
+        while not self.L.simulator_isFinish():
+            self.L.simulator_calc()
+
+    def sync(self):
+        check(self.L.b200fdtd_sync(self.engine_handle()), "sync")
+
+    def field(self, name):
+        ptr = getattr(self.L, self.GETTERS[self.solver][name])()
+        return _as_complex(ptr, self.n_px, self.n_py).copy()
+
+    def any_field(self, slot):
+        out = np.zeros((self.n_px, self.n_py), dtype=np.complex128)
+        check(self.L.b200fdtd_get_field(self.engine_handle(), slot, out.ctypes.data), "get_field")
+        return out
+
+    def eps(self):
+        ptr = self.L.simulator_getEps()
+        buf = (C.c_double * (self.n_px * self.n_py)).from_address(ptr)
+        return np.frombuffer(buf, dtype=np.float64).reshape(self.n_px, self.n_py).copy()
+
+    def ntff_uw(self, slot, project=True):
+        h = self.engine_handle()
+        if project:
+            check(self.L.b200fdtd_ntff_project(h), "ntff_project")
+        n_bins = self.ntff_bins()
+        out = np.zeros((360, n_bins), dtype=np.complex128)
+        check(self.L.b200fdtd_ntff_get_uw(h, slot, out.ctypes.data), "ntff_get_uw")
+        return out
+
+    def ntff_bins(self):
+        if os.environ.get("MPIFDTD_NTFF_FULL_BINS"):
+            return self.L.field_getNTFFInfo().arraySize
+        return self.steps
+
+    def launches(self):
+        n = C.c_uint64(0)
+        self.L.b200fdtd_launch_count(self.engine_handle(), C.byref(n))
+        return n.value
+
+    def finish(self, workdir=None):
+        """simulator_finish(); returns the 321 x 360 table written to cwd."""
+        if self.finished:
+            return None
+        cwd = os.getcwd()
+        if workdir is not None:
+            os.chdir(workdir)
+        try:
+            self.L.simulator_finish()
+            fn = "%d[deg]_380nm_700nm_b.dat" % self.info.angle_deg
+            out = np.fromfile(fn, dtype=np.float64).reshape(321, 360) if os.path.exists(fn) else None
+        finally:
+            os.chdir(cwd)
+        self.finished = True
+        return out
+
+
+def upml_tables(kind, n_px, n_py):
+    """1-D coefficient tables for the current field_init() state, rebuilt from the
+    dense-coefficient probe (tests) -- production code builds them in upml_shim.c."""
+    raise NotImplementedError
+
+
+class Engine:
+    """Engine-level access (one y-slab).  Host-side preparation (eps maps,
+    coefficient tables, NTFF plan) comes from the plugin's own C helpers after
+    field_init(), so a slab engine sees exactly what the serial shim would."""
+
+    def __init__(self, kind, n_px, n_py, n_pml, j0=0, nj=None, device=-1, extents=None):
+        self.L = lib()
+        nj = n_py - j0 if nj is None else nj
+        i_lo, i_hi, j_lo, j_hi = extents if extents else (1, n_px - 2, 1, n_py - 2)
+        self.grid = Grid(kind, n_px, n_py, n_pml, j0, nj, i_lo, i_hi, j_lo, j_hi, device, 0, MU_0_S)
+        self.h = C.c_void_p()
+        check(self.L.b200fdtd_create(C.byref(self.grid), C.byref(self.h)), "create")
+        self.kind, self.n_px, self.n_py, self.j0, self.nj = kind, n_px, n_py, j0, nj
+        self.n_bins = 0
+
+    def close(self):
+        if self.h:
+            self.L.b200fdtd_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def set_tables(self, tab_i, tab_j):
+        ti = np.ascontiguousarray(tab_i, dtype=np.float64)
+        tj = np.ascontiguousarray(tab_j, dtype=np.float64)
+        assert ti.shape == (UPML_TABS, self.n_px) and tj.shape == (UPML_TABS, self.n_py)
+        check(self.L.b200fdtd_set_upml_tables(self.h, ti.ctypes.data, tj.ctypes.data), "set_tables")
+
+    def set_eps(self, slot, eps):
+        e = np.ascontiguousarray(eps, dtype=np.float64)
+        assert e.shape == (self.n_px, self.n_py)
+        check(self.L.b200fdtd_set_eps(self.h, slot, e.ctypes.data), "set_eps")
+
+    def set_ntff(self, box, time_shift, max_time, n_bins=None, n_angles=360, array_size=None):
+        ts = np.ascontiguousarray(time_shift, dtype=np.float64)
+        n_points = 2 * (box.right - box.left) + 2 * (box.top - box.bottom)
+        assert ts.shape == (n_angles, n_points)
+        self.n_bins = max_time if n_bins is None else n_bins
+        array_size = box.arraySize if array_size is None else array_size
+        plan = NtffPlan(box.top, box.bottom, box.left, box.right, n_points, max_time, self.n_bins,
+                        n_angles, array_size, 0, ts.ctypes.data)
+        check(self.L.b200fdtd_set_ntff_plan(self.h, C.byref(plan)), "set_ntff_plan")
+
+    def step(self, args):
+        check(self.L.b200fdtd_step(self.h, C.byref(args)), "step")
+
+    def phase_h(self, args):
+        check(self.L.b200fdtd_phase_h(self.h, C.byref(args)), "phase_h")
+
+    def phase_e(self, args):
+        check(self.L.b200fdtd_phase_e(self.h, C.byref(args)), "phase_e")
+
+    def phase_sample(self, args):
+        check(self.L.b200fdtd_phase_sample(self.h, C.byref(args)), "phase_sample")
+
+    def sync(self):
+        check(self.L.b200fdtd_sync(self.h), "sync")
+
+    def set_stream(self, stream_handle):
+        check(self.L.b200fdtd_set_stream(self.h, C.c_void_p(stream_handle)), "set_stream")
+
+    def halo_pack(self, which, dev_ptr):
+        check(self.L.b200fdtd_halo_pack(self.h, which, C.c_void_p(dev_ptr)), "halo_pack")
+
+    def halo_unpack(self, which, dev_ptr):
+        check(self.L.b200fdtd_halo_unpack(self.h, which, C.c_void_p(dev_ptr)), "halo_unpack")
+
+    def get_field(self, slot, out=None):
+        if out is None:
+            out = np.zeros((self.n_px, self.n_py), dtype=np.complex128)
+        check(self.L.b200fdtd_get_field(self.h, slot, out.ctypes.data), "get_field")
+        return out
+
+    def set_field(self, slot, values):
+        v = np.ascontiguousarray(values, dtype=np.complex128)
+        assert v.shape == (self.n_px, self.n_py)
+        check(self.L.b200fdtd_set_field(self.h, slot, v.ctypes.data), "set_field")
+
+    def zero(self):
+        check(self.L.b200fdtd_zero_state(self.h), "zero_state")
+
+    def project(self):
+        check(self.L.b200fdtd_ntff_project(self.h), "ntff_project")
+
+    def uw(self, slot, n_angles=360):
+        out = np.zeros((n_angles, self.n_bins), dtype=np.complex128)
+        check(self.L.b200fdtd_ntff_get_uw(self.h, slot, out.ctypes.data), "ntff_get_uw")
+        return out
+
+    def uw_device(self):
+        p, n = C.c_void_p(), C.c_uint64()
+        check(self.L.b200fdtd_ntff_uw_device(self.h, C.byref(p), C.byref(n)), "uw_device")
+        return p.value, n.value
+
+    def spectrum(self, args):
+        n_lam = args.lambda_last_nm - args.lambda_first_nm + 1
+        out = np.zeros((n_lam, 360))
+        check(self.L.b200fdtd_ntff_spectrum(self.h, C.byref(args), out.ctypes.data), "ntff_spectrum")
+        return out
+
+    def launches(self):
+        n = C.c_uint64(0)
+        self.L.b200fdtd_launch_count(self.h, C.byref(n))
+        return n.value
+
+    def device_bytes(self):
+        n = C.c_uint64(0)
+        self.L.b200fdtd_device_bytes(self.h, C.byref(n))
+        return n.value
+
+    def timer_start(self):
+        check(self.L.b200fdtd_timer_start(self.h), "timer_start")
+
+    def timer_stop(self):
+        ms = C.c_float(0)
+        check(self.L.b200fdtd_timer_stop(self.h, C.byref(ms)), "timer_stop")
+        return ms.value

@@ -1,0 +1,448 @@
+// engine.cu -- lifetime, uploads, state access and the C ABI of include/b200fdtd.h.
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+#include "engine.h"
+
+static thread_local char g_last_error[512] = "";
+
+int b200_fail(int code, const char *fmt, ...)
+{
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_last_error, sizeof g_last_error, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+namespace {
+
+bool kind_is_upml(int kind)
+{
+  return kind == B200FDTD_TM_UPML || kind == B200FDTD_TE_UPML || kind == B200FDTD_MPI_TM_UPML ||
+         kind == B200FDTD_MPI_TE_UPML;
+}
+
+int select_device(b200fdtd_engine *e)
+{
+  B200_CUDA(cudaSetDevice(e->device));
+  return B200FDTD_OK;
+}
+
+int dev_alloc_zero(b200fdtd_engine *e, void **ptr, size_t bytes)
+{
+  cudaError_t err = cudaMalloc(ptr, bytes ? bytes : 16);
+  if (err != cudaSuccess)
+    return b200_fail(B200FDTD_ERR_NOMEM, "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(err));
+  B200_CUDA(cudaMemsetAsync(*ptr, 0, bytes ? bytes : 16, e->stream));
+  e->dev_bytes += bytes;
+  return B200FDTD_OK;
+}
+
+__global__ void fill_double_kernel(double *dst, size_t n, double value)
+{
+  for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x)
+    dst[k] = value;
+}
+
+void free_ntff(b200fdtd_engine *e)
+{
+  NtffState &n = e->ntff;
+  cudaFree(n.pts); cudaFree(n.ts); cudaFree(n.hist_e); cudaFree(n.hist_h); cudaFree(n.uw);
+  memset(&n, 0, sizeof n);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *b200fdtd_last_error(void) { return g_last_error; }
+int b200fdtd_abi_version(void) { return B200FDTD_ABI_VERSION; }
+
+int b200fdtd_device_count(int *count)
+{
+  if (!count) return b200_fail(B200FDTD_ERR_ARG, "count is NULL");
+  int n = 0;
+  cudaError_t err = cudaGetDeviceCount(&n);
+  if (err != cudaSuccess) {
+    *count = 0;
+    return b200_fail(B200FDTD_ERR_NODEVICE, "cudaGetDeviceCount: %s", cudaGetErrorString(err));
+  }
+  *count = n;
+  return B200FDTD_OK;
+}
+
+int b200fdtd_host_alloc(void **ptr, uint64_t bytes)
+{
+  if (!ptr) return b200_fail(B200FDTD_ERR_ARG, "ptr is NULL");
+  cudaError_t err = cudaHostAlloc(ptr, bytes ? bytes : 16, cudaHostAllocDefault);
+  if (err != cudaSuccess)
+    return b200_fail(err == cudaErrorMemoryAllocation ? B200FDTD_ERR_NOMEM : B200FDTD_ERR_NODEVICE,
+                     "cudaHostAlloc(%llu): %s", (unsigned long long)bytes, cudaGetErrorString(err));
+  memset(*ptr, 0, bytes);
+  return B200FDTD_OK;
+}
+
+int b200fdtd_host_free(void *ptr)
+{
+  if (ptr) B200_CUDA(cudaFreeHost(ptr));
+  return B200FDTD_OK;
+}
+
+int b200fdtd_create(const b200fdtd_grid *grid, b200fdtd_engine **out)
+{
+  if (!grid || !out) return b200_fail(B200FDTD_ERR_ARG, "NULL argument");
+  *out = nullptr;
+  if (!kind_is_upml(grid->kind))
+    return b200_fail(B200FDTD_ERR_ARG, "solver kind %d is not served by this engine build", grid->kind);
+  if (grid->n_px < 3 || grid->n_py < 3 || grid->nj < 1 || grid->j0 < 0 ||
+      grid->j0 + grid->nj > grid->n_py || grid->n_pml < 0)
+    return b200_fail(B200FDTD_ERR_ARG, "bad grid %dx%d slab [%d,+%d)", grid->n_px, grid->n_py,
+                     grid->j0, grid->nj);
+  if (grid->i_lo < 0 || grid->i_hi >= grid->n_px || grid->j_lo < 0 || grid->j_hi >= grid->n_py)
+    return b200_fail(B200FDTD_ERR_ARG, "update extents outside the grid");
+
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return b200_fail(B200FDTD_ERR_NODEVICE, "no CUDA device: the FDTD engine has no CPU path");
+
+  b200fdtd_engine *e = new (std::nothrow) b200fdtd_engine();
+  if (!e) return b200_fail(B200FDTD_ERR_NOMEM, "host allocation failed");
+  memset(e, 0, sizeof *e);
+  e->g = *grid;
+  if (grid->device >= 0) e->device = grid->device;
+  else if (cudaGetDevice(&e->device) != cudaSuccess) e->device = 0;
+  int rc = select_device(e);
+  if (rc) { delete e; return rc; }
+
+  cudaError_t err = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
+  if (err != cudaSuccess) { delete e; return b200_fail(B200FDTD_ERR_CUDA, "stream: %s", cudaGetErrorString(err)); }
+  e->own_stream = true;
+  cudaEventCreate(&e->ev0);
+  cudaEventCreate(&e->ev1);
+
+  e->rows = grid->n_px + 2;
+  e->pitch = ((B200_JOFF + grid->nj + 1) + 7) / 8 * 8;
+  e->plane = (size_t)e->rows * e->pitch;
+  e->n_fields = 9;
+
+  // update extents clipped to this slab, in layout coordinates
+  const int jl = grid->j_lo > grid->j0 ? grid->j_lo : grid->j0;
+  const int jh = grid->j_hi < grid->j0 + grid->nj - 1 ? grid->j_hi : grid->j0 + grid->nj - 1;
+  e->r_lo = grid->i_lo + 1;
+  e->r_hi = grid->i_hi + 1;
+  e->c_lo = jl - grid->j0 + B200_JOFF;
+  e->c_hi = jh - grid->j0 + B200_JOFF;
+
+  for (int s = 0; s < e->n_fields && !rc; s++)
+    rc = dev_alloc_zero(e, (void **)&e->field[s], e->plane * sizeof(double2));
+  const int n_eps = (grid->kind == B200FDTD_TM_UPML || grid->kind == B200FDTD_MPI_TM_UPML) ? 1 : 2;
+  for (int s = 0; s < n_eps && !rc; s++)
+    rc = dev_alloc_zero(e, (void **)&e->eps[s], e->plane * sizeof(double));
+  if (!rc) rc = dev_alloc_zero(e, (void **)&e->tab_i, sizeof(double) * B200FDTD_UPML_TABS * e->rows);
+  if (!rc) rc = dev_alloc_zero(e, (void **)&e->tab_j, sizeof(double) * B200FDTD_UPML_TABS * e->pitch);
+  if (rc) { b200fdtd_destroy(e); return rc; }
+  if (cudaStreamSynchronize(e->stream) != cudaSuccess) {
+    b200fdtd_destroy(e);
+    return b200_fail(B200FDTD_ERR_CUDA, "initial memset failed");
+  }
+  *out = e;
+  return B200FDTD_OK;
+}
+
+int b200fdtd_destroy(b200fdtd_engine *e)
+{
+  if (!e) return B200FDTD_OK;
+  cudaSetDevice(e->device);
+  if (e->stream) cudaStreamSynchronize(e->stream);
+  for (int s = 0; s < B200FDTD_MAX_FIELDS; s++) cudaFree(e->field[s]);
+  cudaFree(e->eps[0]); cudaFree(e->eps[1]);
+  cudaFree(e->tab_i); cudaFree(e->tab_j);
+  free_ntff(e);
+  if (e->ev0) cudaEventDestroy(e->ev0);
+  if (e->ev1) cudaEventDestroy(e->ev1);
+  if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
+  delete e;
+  return B200FDTD_OK;
+}
+
+int b200fdtd_set_stream(b200fdtd_engine *e, void *cuda_stream)
+{
+  if (!e) return b200_fail(B200FDTD_ERR_ARG, "NULL engine");
+  int rc = select_device(e); if (rc) return rc;
+  B200_CUDA(cudaStreamSynchronize(e->stream));
+  if (e->own_stream) { cudaStreamDestroy(e->stream); e->own_stream = false; }
+  e->stream = (cudaStream_t)cuda_stream;
+  return B200FDTD_OK;
+}
+
+int b200fdtd_set_upml_tables(b200fdtd_engine *e, const double *tab_i, const double *tab_j)
+{
+  if (!e || !tab_i || !tab_j) return b200_fail(B200FDTD_ERR_ARG, "NULL argument");
+  int rc = select_device(e); if (rc) return rc;
+  const b200fdtd_grid &g = e->g;
+  // ghost rows/columns get the neutral coefficient 1 (never used by an update)
+  std::vector<double> hi((size_t)B200FDTD_UPML_TABS * e->rows, 1.0);
+  std::vector<double> hj((size_t)B200FDTD_UPML_TABS * e->pitch, 1.0);
+  for (int s = 0; s < B200FDTD_UPML_TABS; s++) {
+    for (int i = 0; i < g.n_px; i++) hi[(size_t)s * e->rows + i + 1] = tab_i[(size_t)s * g.n_px + i];
+    for (int c = 0; c < g.nj; c++)
+      hj[(size_t)s * e->pitch + B200_JOFF + c] = tab_j[(size_t)s * g.n_py + g.j0 + c];
+  }
+  B200_CUDA(cudaMemcpyAsync(e->tab_i, hi.data(), hi.size() * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+  B200_CUDA(cudaMemcpyAsync(e->tab_j, hj.data(), hj.size() * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+  B200_CUDA(cudaStreamSynchronize(e->stream));
+  e->have_tabs = true;
+  return B200FDTD_OK;
+}
+
+int b200fdtd_set_eps(b200fdtd_engine *e, int32_t slot, const double *host_eps)
+{
+  if (!e || !host_eps || slot < 0 || slot > 1 || !e->eps[slot])
+    return b200_fail(B200FDTD_ERR_ARG, "bad eps slot %d", slot);
+  int rc = select_device(e); if (rc) return rc;
+  const b200fdtd_grid &g = e->g;
+  // ghosts and row padding hold vacuum (1.0) so no kernel can ever divide by zero there
+  fill_double_kernel<<<1184, 256, 0, e->stream>>>(e->eps[slot], e->plane, 1.0);
+  e->launches++;
+  B200_CUDA(cudaGetLastError());
+  B200_CUDA(cudaMemcpy2DAsync(e->eps[slot] + (size_t)e->pitch + B200_JOFF, sizeof(double) * e->pitch,
+                              host_eps + g.j0, sizeof(double) * g.n_py, sizeof(double) * g.nj, g.n_px,
+                              cudaMemcpyHostToDevice, e->stream));
+  B200_CUDA(cudaStreamSynchronize(e->stream));
+  e->have_eps[slot] = true;
+  return B200FDTD_OK;
+}
+
+int b200fdtd_set_ntff_plan(b200fdtd_engine *e, const b200fdtd_ntff_plan *p)
+{
+  if (!e || !p || !p->time_shift) return b200_fail(B200FDTD_ERR_ARG, "NULL argument");
+  int rc = select_device(e); if (rc) return rc;
+  const b200fdtd_grid &g = e->g;
+  const int nx = p->right - p->left, ny = p->top - p->bottom;
+  if (nx <= 0 || ny <= 0 || p->n_points != 2 * nx + 2 * ny || p->max_time < 1 ||
+      p->n_bins < 1 || p->n_angles < 1 || p->left < 1 || p->bottom < 1 ||
+      p->right >= g.n_px || p->top >= g.n_py)
+    return b200_fail(B200FDTD_ERR_ARG, "inconsistent NTFF plan (box %d..%d x %d..%d, %d points)",
+                     p->left, p->right, p->bottom, p->top, p->n_points);
+  B200_CUDA(cudaStreamSynchronize(e->stream));
+  free_ntff(e);
+  NtffState &n = e->ntff;
+  n.top = p->top; n.bottom = p->bottom; n.left = p->left; n.right = p->right;
+  n.n_points_global = p->n_points;
+  n.max_time = p->max_time; n.n_bins = p->n_bins; n.n_angles = p->n_angles;
+  n.array_size = p->array_size;
+
+  // perimeter in the reference's loop order, keeping the points this slab owns
+  std::vector<NtffPoint> pts;
+  auto push = [&](int i, int j, int edge, int pg) {
+    if (j < g.j0 || j >= g.j0 + g.nj) return;
+    NtffPoint q;
+    q.k = (long long)(i + 1) * e->pitch + (j - g.j0) + B200_JOFF;
+    q.edge = edge;
+    q.p_global = pg;
+    pts.push_back(q);
+  };
+  int pg = 0;
+  for (int i = p->left; i < p->right; i++) push(i, p->bottom, 0, pg++);
+  for (int j = p->bottom; j < p->top; j++) push(p->right, j, 1, pg++);
+  for (int i = p->left; i < p->right; i++) push(i, p->top, 2, pg++);
+  for (int j = p->bottom; j < p->top; j++) push(p->left, j, 3, pg++);
+  n.n_local = (int)pts.size();
+
+  std::vector<double> ts((size_t)n.n_angles * (n.n_local ? n.n_local : 1));
+  for (int a = 0; a < n.n_angles; a++)
+    for (int q = 0; q < n.n_local; q++)
+      ts[(size_t)a * n.n_local + q] = p->time_shift[(size_t)a * p->n_points + pts[q].p_global];
+
+  rc = dev_alloc_zero(e, (void **)&n.pts, sizeof(NtffPoint) * (size_t)(n.n_local ? n.n_local : 1));
+  if (!rc) rc = dev_alloc_zero(e, (void **)&n.ts, sizeof(double) * ts.size());
+  if (!rc) rc = dev_alloc_zero(e, (void **)&n.hist_e, sizeof(double2) * (size_t)n.n_local * n.max_time);
+  if (!rc) rc = dev_alloc_zero(e, (void **)&n.hist_h, sizeof(double2) * (size_t)n.n_local * n.max_time);
+  if (!rc) rc = dev_alloc_zero(e, (void **)&n.uw, sizeof(double2) * 3 * (size_t)n.n_angles * n.n_bins);
+  if (rc) { free_ntff(e); return rc; }
+  if (n.n_local) {
+    B200_CUDA(cudaMemcpyAsync(n.pts, pts.data(), sizeof(NtffPoint) * pts.size(), cudaMemcpyHostToDevice, e->stream));
+    B200_CUDA(cudaMemcpyAsync(n.ts, ts.data(), sizeof(double) * ts.size(), cudaMemcpyHostToDevice, e->stream));
+  }
+  B200_CUDA(cudaStreamSynchronize(e->stream));
+  n.ready = true;
+  n.steps_recorded = 0;
+  return B200FDTD_OK;
+}
+
+static int check_ready(b200fdtd_engine *e, const b200fdtd_step_args *a)
+{
+  if (!e || !a) return b200_fail(B200FDTD_ERR_ARG, "NULL argument");
+  if (!e->have_tabs) return b200_fail(B200FDTD_ERR_STATE, "step before set_upml_tables");
+  if (!e->have_eps[0] || (e->eps[1] && !e->have_eps[1]))
+    return b200_fail(B200FDTD_ERR_STATE, "step before set_eps");
+  return select_device(e);
+}
+
+int b200fdtd_phase_h(b200fdtd_engine *e, const b200fdtd_step_args *a)
+{
+  int rc = check_ready(e, a); if (rc) return rc;
+  return b200_launch_upml_h(e, a);
+}
+
+int b200fdtd_phase_e(b200fdtd_engine *e, const b200fdtd_step_args *a)
+{
+  int rc = check_ready(e, a); if (rc) return rc;
+  return b200_launch_upml_e(e, a);
+}
+
+int b200fdtd_phase_sample(b200fdtd_engine *e, const b200fdtd_step_args *a)
+{
+  int rc = check_ready(e, a); if (rc) return rc;
+  return b200_launch_ntff_sample(e, a);
+}
+
+int b200fdtd_step(b200fdtd_engine *e, const b200fdtd_step_args *a)
+{
+  int rc = check_ready(e, a); if (rc) return rc;
+  const bool e_first = (e->g.kind == B200FDTD_MPI_TM_UPML || e->g.kind == B200FDTD_MPI_TE_UPML);
+  if (e_first) {              // mpiTM_UPML.c:196-217: E, source, H, NTFF
+    rc = b200_launch_upml_e(e, a);
+    if (!rc) rc = b200_launch_upml_h(e, a);
+  } else {                    // fdtdTM_upml.c:54-66: H, E, source, NTFF
+    rc = b200_launch_upml_h(e, a);
+    if (!rc) rc = b200_launch_upml_e(e, a);
+  }
+  if (!rc) rc = b200_launch_ntff_sample(e, a);
+  return rc;
+}
+
+int b200fdtd_sync(b200fdtd_engine *e)
+{
+  if (!e) return b200_fail(B200FDTD_ERR_ARG, "NULL engine");
+  int rc = select_device(e); if (rc) return rc;
+  B200_CUDA(cudaStreamSynchronize(e->stream));
+  return B200FDTD_OK;
+}
+
+int b200fdtd_halo_pack(b200fdtd_engine *e, int32_t which, void *dev_buf)
+{
+  if (!e || !dev_buf || which < 0 || which > 1) return b200_fail(B200FDTD_ERR_ARG, "bad halo argument");
+  int rc = select_device(e); if (rc) return rc;
+  return b200_launch_halo(e, which, dev_buf, true);
+}
+
+int b200fdtd_halo_unpack(b200fdtd_engine *e, int32_t which, const void *dev_buf)
+{
+  if (!e || !dev_buf || which < 0 || which > 1) return b200_fail(B200FDTD_ERR_ARG, "bad halo argument");
+  int rc = select_device(e); if (rc) return rc;
+  return b200_launch_halo(e, which, const_cast<void *>(dev_buf), false);
+}
+
+int b200fdtd_get_field(b200fdtd_engine *e, int32_t slot, double *host)
+{
+  if (!e || !host || slot < 0 || slot >= e->n_fields) return b200_fail(B200FDTD_ERR_ARG, "bad field slot %d", slot);
+  int rc = select_device(e); if (rc) return rc;
+  const b200fdtd_grid &g = e->g;
+  B200_CUDA(cudaMemcpy2DAsync(host + 2 * (size_t)g.j0, sizeof(double2) * g.n_py,
+                              e->field[slot] + (size_t)e->pitch + B200_JOFF, sizeof(double2) * e->pitch,
+                              sizeof(double2) * g.nj, g.n_px, cudaMemcpyDeviceToHost, e->stream));
+  B200_CUDA(cudaStreamSynchronize(e->stream));
+  return B200FDTD_OK;
+}
+
+int b200fdtd_set_field(b200fdtd_engine *e, int32_t slot, const double *host)
+{
+  if (!e || !host || slot < 0 || slot >= e->n_fields) return b200_fail(B200FDTD_ERR_ARG, "bad field slot %d", slot);
+  int rc = select_device(e); if (rc) return rc;
+  const b200fdtd_grid &g = e->g;
+  B200_CUDA(cudaMemcpy2DAsync(e->field[slot] + (size_t)e->pitch + B200_JOFF, sizeof(double2) * e->pitch,
+                              host + 2 * (size_t)g.j0, sizeof(double2) * g.n_py,
+                              sizeof(double2) * g.nj, g.n_px, cudaMemcpyHostToDevice, e->stream));
+  B200_CUDA(cudaStreamSynchronize(e->stream));
+  return B200FDTD_OK;
+}
+
+int b200fdtd_zero_state(b200fdtd_engine *e)
+{
+  if (!e) return b200_fail(B200FDTD_ERR_ARG, "NULL engine");
+  int rc = select_device(e); if (rc) return rc;
+  for (int s = 0; s < e->n_fields; s++)
+    B200_CUDA(cudaMemsetAsync(e->field[s], 0, e->plane * sizeof(double2), e->stream));
+  NtffState &n = e->ntff;
+  if (n.ready) {
+    B200_CUDA(cudaMemsetAsync(n.hist_e, 0, sizeof(double2) * (size_t)n.n_local * n.max_time, e->stream));
+    B200_CUDA(cudaMemsetAsync(n.hist_h, 0, sizeof(double2) * (size_t)n.n_local * n.max_time, e->stream));
+    B200_CUDA(cudaMemsetAsync(n.uw, 0, sizeof(double2) * 3 * (size_t)n.n_angles * n.n_bins, e->stream));
+    n.steps_recorded = 0;
+  }
+  B200_CUDA(cudaStreamSynchronize(e->stream));
+  return B200FDTD_OK;
+}
+
+int b200fdtd_ntff_project(b200fdtd_engine *e)
+{
+  if (!e) return b200_fail(B200FDTD_ERR_ARG, "NULL engine");
+  int rc = select_device(e); if (rc) return rc;
+  return b200_launch_ntff_project(e);
+}
+
+int b200fdtd_ntff_get_uw(b200fdtd_engine *e, int32_t slot, double *host)
+{
+  if (!e || !host || slot < 0 || slot > 2 || !e->ntff.ready) return b200_fail(B200FDTD_ERR_ARG, "bad U/W request");
+  int rc = select_device(e); if (rc) return rc;
+  const NtffState &n = e->ntff;
+  const size_t count = (size_t)n.n_angles * n.n_bins;
+  B200_CUDA(cudaMemcpyAsync(host, n.uw + (size_t)slot * count, sizeof(double2) * count, cudaMemcpyDeviceToHost, e->stream));
+  B200_CUDA(cudaStreamSynchronize(e->stream));
+  return B200FDTD_OK;
+}
+
+int b200fdtd_ntff_uw_device(b200fdtd_engine *e, void **dev_ptr, uint64_t *n_doubles)
+{
+  if (!e || !dev_ptr || !n_doubles || !e->ntff.ready) return b200_fail(B200FDTD_ERR_ARG, "bad U/W request");
+  *dev_ptr = e->ntff.uw;
+  *n_doubles = 2ull * 3ull * (uint64_t)e->ntff.n_angles * (uint64_t)e->ntff.n_bins;
+  return B200FDTD_OK;
+}
+
+int b200fdtd_ntff_spectrum(b200fdtd_engine *e, const b200fdtd_spectrum_args *args, double *out)
+{
+  if (!e || !args || !out || !args->cos_phi || !args->sin_phi || !args->twiddle)
+    return b200_fail(B200FDTD_ERR_ARG, "NULL argument");
+  int rc = select_device(e); if (rc) return rc;
+  return b200_run_ntff_spectrum(e, args, out);
+}
+
+int b200fdtd_launch_count(b200fdtd_engine *e, uint64_t *count)
+{
+  if (!e || !count) return b200_fail(B200FDTD_ERR_ARG, "NULL argument");
+  *count = e->launches;
+  return B200FDTD_OK;
+}
+
+int b200fdtd_device_bytes(b200fdtd_engine *e, uint64_t *bytes)
+{
+  if (!e || !bytes) return b200_fail(B200FDTD_ERR_ARG, "NULL argument");
+  *bytes = e->dev_bytes;
+  return B200FDTD_OK;
+}
+
+int b200fdtd_timer_start(b200fdtd_engine *e)
+{
+  if (!e) return b200_fail(B200FDTD_ERR_ARG, "NULL engine");
+  int rc = select_device(e); if (rc) return rc;
+  B200_CUDA(cudaEventRecord(e->ev0, e->stream));
+  return B200FDTD_OK;
+}
+
+int b200fdtd_timer_stop(b200fdtd_engine *e, float *ms)
+{
+  if (!e || !ms) return b200_fail(B200FDTD_ERR_ARG, "NULL argument");
+  int rc = select_device(e); if (rc) return rc;
+  B200_CUDA(cudaEventRecord(e->ev1, e->stream));
+  B200_CUDA(cudaEventSynchronize(e->ev1));
+  B200_CUDA(cudaEventElapsedTime(ms, e->ev0, e->ev1));
+  return B200FDTD_OK;
+}
+
+}  // extern "C"

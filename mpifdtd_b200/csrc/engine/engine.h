@@ -1,0 +1,80 @@
+// engine.h -- internal state of one b200fdtd engine (one y-slab on one GPU).
+//
+// Device layout.  Every complex field is a pitched 2-D array of double2 with the
+// reference's orientation (x = i slow, y = j fast; field.c:70-72) so host
+// mirrors need no transpose:
+//
+//   element(i, j) = base[(i + 1) * pitch + (j - j0) + JOFF]
+//
+// Row -1 and row n_px are ghost rows (always zero for the serial solvers; the
+// "MPI" solver kinds update all N x N cells against them, mpiTM_UPML.c:737-743).
+// Column offset JOFF = 8 puts the first owned column on a 128-byte boundary and
+// leaves the low ghost column at JOFF-1; the high ghost column is JOFF + nj.
+// pitch is a multiple of 8 elements (128 B).  eps arrays share the layout with
+// double elements.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "b200fdtd.h"
+
+#define B200_JOFF 8
+
+struct NtffPoint {          // one perimeter sample owned by this slab
+  long long k;              // element offset of (i, j) in the pitched layout
+  int edge;                 // 0 bottom, 1 right, 2 top, 3 left
+  int p_global;             // index into the reference's perimeter order
+};
+
+struct NtffState {
+  bool ready;
+  int top, bottom, left, right;
+  int n_points_global;
+  int n_local;              // perimeter points whose column lies in this slab
+  int max_time, n_bins, n_angles, array_size;
+  NtffPoint *pts;           // device [n_local]
+  double *ts;               // device [n_angles][n_local]
+  double2 *hist_e, *hist_h; // device [n_local][max_time]
+  double2 *uw;              // device [3][n_angles][n_bins]
+  int steps_recorded;
+};
+
+struct b200fdtd_engine {
+  b200fdtd_grid g;
+  int device;
+  cudaStream_t stream;
+  bool own_stream;
+  int pitch, rows;
+  size_t plane;             // rows * pitch elements
+  int n_fields;
+  double2 *field[B200FDTD_MAX_FIELDS];
+  double *eps[2];
+  double *tab_i;            // device [B200FDTD_UPML_TABS][rows], indexed by row = i + 1
+  double *tab_j;            // device [B200FDTD_UPML_TABS][pitch], indexed by in-row offset
+  bool have_tabs, have_eps[2];
+  NtffState ntff;
+  uint64_t launches;
+  uint64_t dev_bytes;
+  cudaEvent_t ev0, ev1;
+  // update extents in layout coordinates (row r = i + 1, column c = j - j0 + JOFF), inclusive
+  int r_lo, r_hi, c_lo, c_hi;
+};
+
+// error plumbing (engine.cu)
+int b200_fail(int code, const char *fmt, ...);
+#define B200_CUDA(call)                                                              \
+  do {                                                                               \
+    cudaError_t err__ = (call);                                                      \
+    if (err__ != cudaSuccess)                                                        \
+      return b200_fail(B200FDTD_ERR_CUDA, "%s failed: %s (%s:%d)", #call,            \
+                       cudaGetErrorString(err__), __FILE__, __LINE__);               \
+  } while (0)
+
+// launchers (upml_kernels.cu)
+int b200_launch_upml_h(b200fdtd_engine *e, const b200fdtd_step_args *a);
+int b200_launch_upml_e(b200fdtd_engine *e, const b200fdtd_step_args *a);
+int b200_launch_halo(b200fdtd_engine *e, int which, void *buf, bool pack);
+
+// launchers (ntff_kernels.cu)
+int b200_launch_ntff_sample(b200fdtd_engine *e, const b200fdtd_step_args *a);
+int b200_launch_ntff_project(b200fdtd_engine *e);
+int b200_run_ntff_spectrum(b200fdtd_engine *e, const b200fdtd_spectrum_args *s, double *out);

@@ -1,0 +1,297 @@
+// ntff_kernels.cu -- near-to-far-field transform on the GPU.
+//
+// The reference accumulates the time-domain far field every step:
+// ntffTM_TimeCalc / ntffTE_TimeCalc (ntffTM.c:293-371, ntffTE.c:68-157) walk the
+// closed surface for each of 360 directions and scatter every tangential sample
+// into three retarded-time bins (calc(), ntffTM.c:279-288).  That is 360 x P x 6
+// colliding read-modify-writes per step and ~85 % of the CPU step.
+//
+// Here the per-step work is only a surface SAMPLE (P points, two complex values
+// each) appended to a history buffer; the 360-direction binning is deferred to
+// one PROJECTION kernel that, for every (direction, bin), gathers the samples
+// that the reference would have scattered there.  For a point with time shift
+// ts a sample taken at step t lands in bins m-1, m, m+1 with
+//   T = (t - 1) + ts  (E)  or  (t - 1/2) + ts  (H),  m = floor(T + 1/2),
+//   a = 1/2 + T - m,  b = 1 - a,  weights (+b, a-b, -a),
+// and m, a, b are recomputed here per (direction, point, step) with exactly those
+// double-precision expressions, so only the order of the additions differs from
+// the CPU.  Collision-free, deterministic, no atomics.
+//
+// Post-processing (ntffT?_TimeTranslate, the 8192-point cfft and the wavelength
+// interpolation, ntffTM.c:161-232, cfft.c:104-179) also runs here, once per run.
+#include "engine.h"
+
+namespace {
+
+__device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ double2 rmul(double r, double2 z) { return make_double2(r * z.x, r * z.y); }
+__device__ __forceinline__ double2 cneg(double2 a) { return make_double2(-a.x, -a.y); }
+// gcc's complex x complex product without -ffast-math: (ac - bd) + i(ad + bc)
+__device__ __forceinline__ double2 cmul(double2 a, double2 b)
+{
+  return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+
+// ---- per-step surface sample --------------------------------------------------
+// TM (ntffTM.c:326-369): bottom/top sample Ez and the j-averaged Hx, right/left
+// sample Ez and the i-averaged Hy; top and left are negated.
+// TE (ntffTE.c:100-155): bottom/top sample Ex and j-averaged Hz, right/left Ey and
+// i-averaged Hz; here bottom and right are the negated ones.
+__global__ void ntff_sample_kernel(const NtffPoint *__restrict__ pts, int n_local, int is_tm,
+                                   const double2 *__restrict__ e_a,   // TM Ez   | TE Ex
+                                   const double2 *__restrict__ e_b,   // TM Ez   | TE Ey
+                                   const double2 *__restrict__ h_a,   // TM Hx   | TE Hz
+                                   const double2 *__restrict__ h_b,   // TM Hy   | TE Hz
+                                   int pitch, double2 *hist_e, double2 *hist_h, int max_time, int t)
+{
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_local) return;
+  const NtffPoint pt = pts[p];
+  const bool along_x = (pt.edge == 0 || pt.edge == 2);      // bottom / top edges
+  double2 ev = along_x ? e_a[pt.k] : e_b[pt.k];
+  double2 hv = along_x ? cadd(h_a[pt.k], h_a[pt.k - 1]) : cadd(h_b[pt.k], h_b[pt.k - pitch]);
+  hv = rmul(0.5, hv);
+  const bool negate = is_tm ? (pt.edge >= 2) : (pt.edge < 2);
+  if (negate) { ev = cneg(ev); hv = cneg(hv); }
+  hist_e[(size_t)p * max_time + t] = ev;
+  hist_h[(size_t)p * max_time + t] = hv;
+}
+
+// ---- deferred projection --------------------------------------------------------
+// One thread owns one (direction, bin); the block walks the surface points.  For
+// every point the three steps whose taps can reach this bin are t0-1, t0, t0+1
+// around the nominal centre; when the shift sits within 1e-9 of a rounding
+// knife-edge (frac(ts + 1/2) or frac(ts) ~ 0) five steps are examined so that no
+// tap the reference would have written is missed.
+constexpr int kProjBlock = 128;
+constexpr int kSpillBins = 8;
+
+__device__ __forceinline__ void gather(double2 &acc, const double2 *__restrict__ series, int max_time,
+                                       int q, double ts, double lag, int t_center, int reach)
+{
+  for (int dt = -reach; dt <= reach; dt++) {
+    const int t = t_center + dt;
+    if (t < 0 || t >= max_time) continue;
+    const double T = ((double)t - lag) + ts;           // timeE / timeH + timeShift
+    const int m = (int)floor(T + 0.5);
+    const int tap = q - m;
+    if (tap < -1 || tap > 1) continue;
+    const double a = (0.5 + T) - m;
+    const double b = 1.0 - a;
+    const double w = tap < 0 ? b : (tap == 0 ? a - b : -a);
+    acc = cadd(acc, rmul(w, series[t]));
+  }
+}
+
+__global__ void __launch_bounds__(kProjBlock)
+ntff_project_kernel(const NtffPoint *__restrict__ pts, const double *__restrict__ ts_tab, int n_local,
+                    const double2 *__restrict__ hist_e, const double2 *__restrict__ hist_h,
+                    int max_time, int steps, int n_bins, int n_angles, int is_tm, int array_size,
+                    double2 *uw)
+{
+  const int ang = blockIdx.y;
+  const int q_block = blockIdx.x * kProjBlock;
+  const int q = q_block + (int)threadIdx.x;
+  double2 acc[3] = { make_double2(0, 0), make_double2(0, 0), make_double2(0, 0) };
+  const int t_limit = steps < max_time ? steps : max_time;
+
+  for (int p = 0; p < n_local; p++) {
+    const double ts = ts_tab[(size_t)ang * n_local + p];
+    const double fl_e = floor(ts + 0.5), fl_h = floor(ts);
+    // nominal centres: E has m = (t-1) + floor(ts+1/2), H has m = t + floor(ts)
+    const int shift_e = (int)fl_e - 1, shift_h = (int)fl_h;
+    // whole block out of range for this point?  (bins q_block .. q_block+127)
+    const int t_hi = q_block + kProjBlock - 1 - (shift_e < shift_h ? shift_e : shift_h) + 2;
+    const int t_lo = q_block - (shift_e > shift_h ? shift_e : shift_h) - 2;
+    if (t_hi < 0 || t_lo >= t_limit) continue;
+
+    const double fe = (ts + 0.5) - fl_e, fh = ts - fl_h;
+    const int reach_e = (fe < 1e-9 || fe > 1.0 - 1e-9) ? 2 : 1;
+    const int reach_h = (fh < 1e-9 || fh > 1.0 - 1e-9) ? 2 : 1;
+
+    const int edge = pts[p].edge;
+    const bool along_x = (edge == 0 || edge == 2);
+    // TM: E -> Ux (0) on bottom/top, Uy (1) on right/left; H -> Wz (2)
+    // TE: E -> Uz (2);  H -> Wx (0) on bottom/top, Wy (1) on right/left
+    const int slot_e = is_tm ? (along_x ? 0 : 1) : 2;
+    const int slot_h = is_tm ? 2 : (along_x ? 0 : 1);
+    if (q < n_bins) {
+      gather(acc[slot_e], hist_e + (size_t)p * max_time, t_limit, q, ts, 1.0, q - shift_e, reach_e);
+      gather(acc[slot_h], hist_h + (size_t)p * max_time, t_limit, q, ts, 0.5, q - shift_h, reach_h);
+    }
+  }
+  // Row spill of the reference's flat [360][arraySize] storage: a tap at index
+  // arraySize + q' of direction ang-1 is physically bin q' of direction ang
+  // (calc() has no bound check, ntffTM.c:285-287).  Only the last steps of the
+  // points with the largest shift get there, so this touches a few low bins.
+  if (array_size > 0 && ang > 0 && q_block == 0 && q < kSpillBins && q < n_bins) {
+    const int qv = q + array_size;
+    for (int p = 0; p < n_local; p++) {
+      const double ts = ts_tab[(size_t)(ang - 1) * n_local + p];
+      if (ts + (double)t_limit + 2.0 < (double)array_size) continue;
+      const double fl_e = floor(ts + 0.5), fl_h = floor(ts);
+      const int edge = pts[p].edge;
+      const bool along_x = (edge == 0 || edge == 2);
+      const int slot_e = is_tm ? (along_x ? 0 : 1) : 2;
+      const int slot_h = is_tm ? 2 : (along_x ? 0 : 1);
+      gather(acc[slot_e], hist_e + (size_t)p * max_time, t_limit, qv, ts, 1.0, qv - ((int)fl_e - 1), 2);
+      gather(acc[slot_h], hist_h + (size_t)p * max_time, t_limit, qv, ts, 0.5, qv - (int)fl_h, 2);
+    }
+  }
+  if (q < n_bins)
+    for (int s = 0; s < 3; s++)
+      uw[((size_t)s * n_angles + ang) * n_bins + q] = acc[s];
+}
+
+// ---- translate + FFT + wavelength interpolation ---------------------------------
+// One block per direction; the 8192-point series lives in shared memory (128 KB).
+// Radix-2 decimation in frequency with the positive-exponent twiddles of
+// cfft.c:139-150, then bit reversal, then the two-point interpolation of
+// ntffTM.c:224-231.  Twiddles come from the host (glibc cexp), so every butterfly
+// is the same arithmetic as the reference's.
+__global__ void ntff_spectrum_kernel(const double2 *__restrict__ uw, int n_bins, int n_angles,
+                                     int max_time, int is_tm, double2 coef, double z0,
+                                     const double *__restrict__ cos_phi,
+                                     const double *__restrict__ sin_phi,
+                                     const double2 *__restrict__ twiddle, int n_fft, int log2n,
+                                     int lam0, int lam1, double c_hu_nfft, double *out)
+{
+  extern __shared__ double2 series[];
+  const int ang = blockIdx.x;
+  const double2 *A0 = uw + ((size_t)0 * n_angles + ang) * n_bins;
+  const double2 *A1 = uw + ((size_t)1 * n_angles + ang) * n_bins;
+  const double2 *A2 = uw + ((size_t)2 * n_angles + ang) * n_bins;
+  // theta = 0: sx = cos(phi), sy = sin(phi), sz = -1, px = -sin(phi), py = cos(phi)
+  const double cp = cos_phi[ang], sp = sin_phi[ang];
+  const double cth = 1.0;                                    // cos(theta), theta = 0
+  const double sx = cth * cp, sy = cth * sp, sz = -cth, px = -sp, py = cp;
+
+  for (int n = threadIdx.x; n < n_fft; n += blockDim.x) {
+    double2 val = make_double2(0, 0);
+    if (n < max_time) {
+      if (is_tm) {
+        // ntffTM.c:183-187: Eth = coef * (-Z0*(Wz*sz) - (Ux*px + Uy*py))
+        const double2 wth = rmul(sz, A2[n]);
+        const double2 uph = cadd(rmul(px, A0[n]), rmul(py, A1[n]));
+        val = cmul(coef, csub(rmul(-z0, wth), uph));
+      } else {
+        // ntffTE.c:45-49: Eph = coef * (-Z0*(Wx*px + Wy*py) + Uz*sz)
+        const double2 wph = cadd(rmul(px, A0[n]), rmul(py, A1[n]));
+        const double2 uth = rmul(sz, A2[n]);
+        val = cmul(coef, cadd(rmul(-z0, wph), uth));
+      }
+    }
+    series[n] = val;
+  }
+  (void)sx; (void)sy;
+  __syncthreads();
+
+  // stages: half = n/2, n/4, ..., 1 ; butterfly (p, q = p + half), twiddle index k = p mod span
+  const double2 *tw = twiddle;
+  for (int half = n_fft >> 1; half >= 1; half >>= 1) {
+    for (int b = threadIdx.x; b < (n_fft >> 1); b += blockDim.x) {
+      const int k = b % half;
+      const int base = (b / half) * (half << 1) + k;
+      const double2 lo = series[base], hi = series[base + half];
+      const double2 diff = csub(lo, hi);
+      series[base] = cadd(lo, hi);
+      series[base + half] = cmul(diff, tw[k]);
+    }
+    tw += half;
+    __syncthreads();
+  }
+
+  // interpolation reads X[index], X[index+1] in natural order = bit-reversed positions
+  for (int lam = lam0 + (int)threadIdx.x; lam <= lam1; lam += blockDim.x) {
+    double pos = c_hu_nfft / lam;
+    const int index = (int)floor(pos);
+    pos = pos - index;
+    const unsigned r0 = __brev((unsigned)index) >> (32 - log2n);
+    const unsigned r1 = __brev((unsigned)(index + 1)) >> (32 - log2n);
+    const double2 x0 = series[r0], x1 = series[r1];
+    const double n0 = x0.x * x0.x + x0.y * x0.y;
+    const double n1 = x1.x * x1.x + x1.y * x1.y;
+    out[(size_t)(lam - lam0) * n_angles + ang] = ((1 - pos) * n0 + pos * n1) / n_fft;
+  }
+}
+
+bool is_tm(int kind)
+{
+  return kind == B200FDTD_TM_UPML || kind == B200FDTD_MPI_TM_UPML || kind == B200FDTD_TM ||
+         kind == B200FDTD_NS_TM;
+}
+
+}  // namespace
+
+int b200_launch_ntff_sample(b200fdtd_engine *e, const b200fdtd_step_args *a)
+{
+  NtffState &n = e->ntff;
+  if (!n.ready) return B200FDTD_OK;
+  const int t = (int)a->time;
+  if (t < 0 || t >= n.max_time)
+    return b200_fail(B200FDTD_ERR_ARG, "NTFF sample at step %d outside [0, %d)", t, n.max_time);
+  if (n.n_local > 0) {
+    const bool tm = is_tm(e->g.kind);
+    const double2 *ea = e->field[tm ? (int)B200FDTD_TM_EZ : (int)B200FDTD_TE_EX];
+    const double2 *eb = e->field[tm ? (int)B200FDTD_TM_EZ : (int)B200FDTD_TE_EY];
+    const double2 *ha = e->field[tm ? (int)B200FDTD_TM_HX : (int)B200FDTD_TE_HZ];
+    const double2 *hb = e->field[tm ? (int)B200FDTD_TM_HY : (int)B200FDTD_TE_HZ];
+    ntff_sample_kernel<<<(n.n_local + 127) / 128, 128, 0, e->stream>>>(
+        n.pts, n.n_local, tm ? 1 : 0, ea, eb, ha, hb, e->pitch, n.hist_e, n.hist_h, n.max_time, t);
+    e->launches++;
+    B200_CUDA(cudaGetLastError());
+  }
+  if (t + 1 > n.steps_recorded) n.steps_recorded = t + 1;
+  return B200FDTD_OK;
+}
+
+int b200_launch_ntff_project(b200fdtd_engine *e)
+{
+  NtffState &n = e->ntff;
+  if (!n.ready) return b200_fail(B200FDTD_ERR_STATE, "ntff_project before set_ntff_plan");
+  dim3 grid((n.n_bins + kProjBlock - 1) / kProjBlock, n.n_angles);
+  ntff_project_kernel<<<grid, kProjBlock, 0, e->stream>>>(
+      n.pts, n.ts, n.n_local, n.hist_e, n.hist_h, n.max_time, n.steps_recorded, n.n_bins,
+      n.n_angles, is_tm(e->g.kind) ? 1 : 0, n.array_size, n.uw);
+  e->launches++;
+  B200_CUDA(cudaGetLastError());
+  return B200FDTD_OK;
+}
+
+int b200_run_ntff_spectrum(b200fdtd_engine *e, const b200fdtd_spectrum_args *s, double *out)
+{
+  NtffState &n = e->ntff;
+  if (!n.ready) return b200_fail(B200FDTD_ERR_STATE, "ntff_spectrum before set_ntff_plan");
+  int log2n = 0;
+  while ((1 << log2n) < s->n_fft) log2n++;
+  if ((1 << log2n) != s->n_fft || s->n_fft < 2 || n.max_time > s->n_fft)
+    return b200_fail(B200FDTD_ERR_ARG, "n_fft=%d must be a power of two >= max_time=%d", s->n_fft,
+                     n.max_time);
+  const int n_lam = s->lambda_last_nm - s->lambda_first_nm + 1;
+  if (n_lam <= 0) return b200_fail(B200FDTD_ERR_ARG, "empty wavelength range");
+
+  double *d_cos = nullptr, *d_sin = nullptr, *d_out = nullptr;
+  double2 *d_tw = nullptr;
+  const size_t tw_count = (size_t)s->n_fft - 1;
+  B200_CUDA(cudaMalloc(&d_cos, sizeof(double) * n.n_angles));
+  B200_CUDA(cudaMalloc(&d_sin, sizeof(double) * n.n_angles));
+  B200_CUDA(cudaMalloc(&d_tw, sizeof(double2) * tw_count));
+  B200_CUDA(cudaMalloc(&d_out, sizeof(double) * (size_t)n_lam * n.n_angles));
+  B200_CUDA(cudaMemcpyAsync(d_cos, s->cos_phi, sizeof(double) * n.n_angles, cudaMemcpyHostToDevice, e->stream));
+  B200_CUDA(cudaMemcpyAsync(d_sin, s->sin_phi, sizeof(double) * n.n_angles, cudaMemcpyHostToDevice, e->stream));
+  B200_CUDA(cudaMemcpyAsync(d_tw, s->twiddle, sizeof(double2) * tw_count, cudaMemcpyHostToDevice, e->stream));
+
+  const size_t smem = sizeof(double2) * (size_t)s->n_fft;
+  B200_CUDA(cudaFuncSetAttribute(ntff_spectrum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ntff_spectrum_kernel<<<n.n_angles, 1024, smem, e->stream>>>(
+      n.uw, n.n_bins, n.n_angles, n.max_time, is_tm(e->g.kind) ? 1 : 0,
+      make_double2(s->coef_re, s->coef_im), s->z0, d_cos, d_sin, d_tw, s->n_fft, log2n,
+      s->lambda_first_nm, s->lambda_last_nm, s->c_hu_nfft, d_out);
+  e->launches++;
+  B200_CUDA(cudaGetLastError());
+  B200_CUDA(cudaMemcpyAsync(out, d_out, sizeof(double) * (size_t)n_lam * n.n_angles, cudaMemcpyDeviceToHost, e->stream));
+  B200_CUDA(cudaStreamSynchronize(e->stream));
+  cudaFree(d_cos); cudaFree(d_sin); cudaFree(d_tw); cudaFree(d_out);
+  return B200FDTD_OK;
+}

@@ -1,0 +1,307 @@
+// upml_kernels.cu -- UPML leapfrog kernels for sm_100a (TM and TE).
+//
+// What they replace (rennone/mpiFDTD):
+//   H phase  = calcMB + calcH   fdtdTM_upml.c:181-219 / fdtdTE_upml.c:293-314
+//   E phase  = calcJD + calcE   fdtdTM_upml.c:155-178 / fdtdTE_upml.c:252-291
+//              + field_scatteredPulse                     field.c:224-256
+// The reference makes 7 separate sweeps per step over 9 complex fields and 15
+// dense coefficient arrays (416 B/cell); here a step is two streaming kernels
+// that touch each field once and read coefficients from 1-D tables (296 B/cell
+// for TM: H phase reads Ez,Mx,Bx,My,By and writes Mx,Bx,My,By,Hx,Hy; E phase reads
+// Hx,Hy,Jz,Dz,eps and writes Jz,Dz,Ez).
+//
+// Arithmetic contract: every expression keeps the reference's operand order and
+// is compiled with -fmad=false, so each add/mul/div is the same IEEE-754 double
+// operation gcc emits for the C99 source (real x complex is component-wise, as
+// gcc lowers it).  One thread updates one cell; a warp covers 32 consecutive j
+// = 512 contiguous bytes per field, every access a 128-bit LDG/STG.
+#include "engine.h"
+
+namespace {
+
+constexpr int kBlock = 256;
+
+struct UpmlView {
+  double2 *f[B200FDTD_MAX_FIELDS];
+  const double *eps0, *eps1;
+  const double *ti, *tj;
+  int pitch, rows;
+  int r_lo, c_lo, c_hi;
+  int nbx;                      // thread blocks per row
+  double mu0;
+  b200fdtd_pulse pulse[2];
+  // point source (opt-in): layout offset or -1
+  long long point_k;
+  double point_re, point_im;
+};
+
+__device__ __forceinline__ double2 operator+(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 operator-(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ double2 operator-(double2 a) { return make_double2(-a.x, -a.y); }
+__device__ __forceinline__ double2 operator*(double r, double2 z) { return make_double2(r * z.x, r * z.y); }
+__device__ __forceinline__ double2 operator/(double2 z, double r) { return make_double2(z.x / r, z.y / r); }
+
+// Cell owned by this thread, or false when past the row end.
+__device__ __forceinline__ bool locate(const UpmlView &v, int &r, int &c, size_t &k)
+{
+  const long long b = blockIdx.x;
+  const int rb = (int)(b / v.nbx);
+  const int cb = (int)(b - (long long)rb * v.nbx);
+  r = v.r_lo + rb;
+  c = v.c_lo + cb * kBlock + (int)threadIdx.x;
+  k = (size_t)r * (size_t)v.pitch + (size_t)c;
+  return c <= v.c_hi;
+}
+
+// field_scatteredPulse (field.c:243-254) for one cell; i, j are GLOBAL indices.
+__device__ __forceinline__ double2 pulse_term(const b200fdtd_pulse &s, int i, int j, double eps)
+{
+  const double r = ((i + s.gap_x) * s.cos_per_c + (j + s.gap_y) * s.sin_per_c) - s.time_minus_t0;
+  const double q = r / s.beam_width;
+  const double gauss = exp(-(q * q));
+  const double amp = s.dot * gauss * (1.0 / eps - 1);
+  double sn, cs;
+  sincos(r * s.omega, &sn, &cs);
+  return make_double2(amp * cs, amp * sn);
+}
+
+// ------------------------------------------------------------------ TM -----
+// slots: 0 Ez 1 Jz 2 Dz 3 Hx 4 Mx 5 Bx 6 Hy 7 My 8 By
+__global__ void __launch_bounds__(kBlock) tm_upml_h_kernel(const UpmlView v)
+{
+  int r, c; size_t k;
+  if (!locate(v, r, c, k)) return;
+  const double2 *__restrict__ Ez = v.f[B200FDTD_TM_EZ];
+
+  const double2 ez = Ez[k];
+  const double2 ez_j1 = Ez[k + 1];            // Ez(i, j+1)
+  const double2 ez_i1 = Ez[k + v.pitch];      // Ez(i+1, j)
+  const double2 mx_old = v.f[B200FDTD_TM_MX][k];
+  const double2 bx_old = v.f[B200FDTD_TM_BX][k];
+  const double2 my_old = v.f[B200FDTD_TM_MY][k];
+  const double2 by_old = v.f[B200FDTD_TM_BY][k];
+
+  const double c_mx   = v.tj[B200FDTD_TMJ_C_MX * v.pitch + c];
+  const double c_mxez = v.tj[B200FDTD_TMJ_C_MXEZ * v.pitch + c];
+  const double num1   = v.tj[B200FDTD_TMJ_NUM_BYMY1 * v.pitch + c];
+  const double num0   = v.tj[B200FDTD_TMJ_NUM_BYMY0 * v.pitch + c];
+  const double c_bx1  = v.ti[B200FDTD_TMI_C_BXMX1 * v.rows + r];
+  const double c_bx0  = v.ti[B200FDTD_TMI_C_BXMX0 * v.rows + r];
+  const double c_by   = v.ti[B200FDTD_TMI_C_BY * v.rows + r];
+  const double den    = v.ti[B200FDTD_TMI_DEN_BYMY * v.rows + r];
+
+  // fdtdTM_upml.c:187-189 (C_BX == 1 exactly)
+  const double2 mx = c_mx * mx_old - c_mxez * (ez_j1 - ez);
+  const double2 bx = (bx_old + c_bx1 * mx) - c_bx0 * mx_old;
+  // fdtdTM_upml.c:196-198 (C_MY == C_MYEZ == 1 exactly)
+  const double2 my = my_old - ((-ez_i1) + ez);
+  const double c_by1 = num1 / den, c_by0 = num0 / den;      // fdtdTM_upml.c:270-271
+  const double2 by = (c_by * by_old + c_by1 * my) - c_by0 * my_old;
+
+  v.f[B200FDTD_TM_MX][k] = mx;
+  v.f[B200FDTD_TM_BX][k] = bx;
+  v.f[B200FDTD_TM_MY][k] = my;
+  v.f[B200FDTD_TM_BY][k] = by;
+  v.f[B200FDTD_TM_HX][k] = bx / v.mu0;        // fdtdTM_upml.c:209
+  v.f[B200FDTD_TM_HY][k] = by / v.mu0;        // fdtdTM_upml.c:216
+}
+
+__global__ void __launch_bounds__(kBlock) tm_upml_e_kernel(const UpmlView v, const int j_base)
+{
+  int r, c; size_t k;
+  if (!locate(v, r, c, k)) return;
+  const double2 *__restrict__ Hx = v.f[B200FDTD_TM_HX];
+  const double2 *__restrict__ Hy = v.f[B200FDTD_TM_HY];
+
+  const double2 hy = Hy[k];
+  const double2 hy_i0 = Hy[k - v.pitch];      // Hy(i-1, j)
+  const double2 hx = Hx[k];
+  const double2 hx_j0 = Hx[k - 1];            // Hx(i, j-1)
+  const double2 jz_old = v.f[B200FDTD_TM_JZ][k];
+  const double2 dz_old = v.f[B200FDTD_TM_DZ][k];
+  const double eps = v.eps0[k];
+
+  const double c_jz   = v.ti[B200FDTD_TMI_C_JZ * v.rows + r];
+  const double c_jzh  = v.ti[B200FDTD_TMI_C_JZHXHY * v.rows + r];
+  const double c_dz   = v.tj[B200FDTD_TMJ_C_DZ * v.pitch + c];
+  const double c_dzjz = v.tj[B200FDTD_TMJ_C_DZJZ * v.pitch + c];
+
+  // fdtdTM_upml.c:161-163 (C_DZJZ1 == C_DZJZ0 because sigma_z = 0)
+  const double2 jz = c_jz * jz_old + c_jzh * (((hy - hy_i0) - hx) + hx_j0);
+  const double2 dz = (c_dz * dz_old + c_dzjz * jz) - c_dzjz * jz_old;
+  double2 ez = dz / eps;                      // fdtdTM_upml.c:175
+
+  if (v.pulse[0].enabled && eps != 1.0)       // field.c:248
+    ez = ez + pulse_term(v.pulse[0], r - 1, j_base + c, eps);
+  if ((long long)k == v.point_k)
+    ez = ez + make_double2(v.point_re, v.point_im);
+
+  v.f[B200FDTD_TM_JZ][k] = jz;
+  v.f[B200FDTD_TM_DZ][k] = dz;
+  v.f[B200FDTD_TM_EZ][k] = ez;
+}
+
+// ------------------------------------------------------------------ TE -----
+// slots: 0 Ex 1 Jx 2 Dx 3 Ey 4 Jy 5 Dy 6 Hz 7 Mz 8 Bz
+__global__ void __launch_bounds__(kBlock) te_upml_h_kernel(const UpmlView v)
+{
+  int r, c; size_t k;
+  if (!locate(v, r, c, k)) return;
+  const double2 *__restrict__ Ex = v.f[B200FDTD_TE_EX];
+  const double2 *__restrict__ Ey = v.f[B200FDTD_TE_EY];
+
+  const double2 ey_i1 = Ey[k + v.pitch];
+  const double2 ey = Ey[k];
+  const double2 ex_j1 = Ex[k + 1];
+  const double2 ex = Ex[k];
+  const double2 mz_old = v.f[B200FDTD_TE_MZ][k];
+  const double2 bz_old = v.f[B200FDTD_TE_BZ][k];
+
+  const double c_mz   = v.ti[B200FDTD_TEI_C_MZ * v.rows + r];
+  const double c_mze  = v.ti[B200FDTD_TEI_C_MZEXEY * v.rows + r];
+  const double c_bz   = v.tj[B200FDTD_TEJ_C_BZ * v.pitch + c];
+  const double c_bzmz = v.tj[B200FDTD_TEJ_C_BZMZ * v.pitch + c];
+
+  // fdtdTE_upml.c:299-301 (C_BZMZ1 == C_BZMZ0 because sigma_z = 0)
+  const double2 mz = c_mz * mz_old - c_mze * (((ey_i1 - ey) - ex_j1) + ex);
+  const double2 bz = (c_bz * bz_old + c_bzmz * mz) - c_bzmz * mz_old;
+
+  v.f[B200FDTD_TE_MZ][k] = mz;
+  v.f[B200FDTD_TE_BZ][k] = bz;
+  v.f[B200FDTD_TE_HZ][k] = bz / v.mu0;        // fdtdTE_upml.c:312
+}
+
+__global__ void __launch_bounds__(kBlock) te_upml_e_kernel(const UpmlView v, const int j_base)
+{
+  int r, c; size_t k;
+  if (!locate(v, r, c, k)) return;
+  const double2 *__restrict__ Hz = v.f[B200FDTD_TE_HZ];
+
+  const double2 hz = Hz[k];
+  const double2 hz_j0 = Hz[k - 1];
+  const double2 hz_i0 = Hz[k - v.pitch];
+  const double2 jx_old = v.f[B200FDTD_TE_JX][k];
+  const double2 dx_old = v.f[B200FDTD_TE_DX][k];
+  const double2 jy_old = v.f[B200FDTD_TE_JY][k];
+  const double2 dy_old = v.f[B200FDTD_TE_DY][k];
+  const double eps_x = v.eps0[k], eps_y = v.eps1[k];
+
+  const double c_jx   = v.tj[B200FDTD_TEJ_C_JX * v.pitch + c];
+  const double c_jxhz = v.tj[B200FDTD_TEJ_C_JXHZ * v.pitch + c];
+  const double num1   = v.tj[B200FDTD_TEJ_NUM_DYJY1 * v.pitch + c];
+  const double num0   = v.tj[B200FDTD_TEJ_NUM_DYJY0 * v.pitch + c];
+  const double c_dx1  = v.ti[B200FDTD_TEI_C_DXJX1 * v.rows + r];
+  const double c_dx0  = v.ti[B200FDTD_TEI_C_DXJX0 * v.rows + r];
+  const double c_dy   = v.ti[B200FDTD_TEI_C_DY * v.rows + r];
+  const double den    = v.ti[B200FDTD_TEI_DEN_DYJY * v.rows + r];
+
+  // fdtdTE_upml.c:259-262 (C_DX == 1)
+  const double2 jx = c_jx * jx_old + c_jxhz * (hz - hz_j0);
+  const double2 dx = (dx_old + c_dx1 * jx) - c_dx0 * jx_old;
+  // fdtdTE_upml.c:269-271 (C_JY == C_JYHZ == 1)
+  const double2 jy = jy_old + ((-hz) + hz_i0);
+  const double c_dy1 = num1 / den, c_dy0 = num0 / den;      // fdtdTE_upml.c:402-403
+  const double2 dy = (c_dy * dy_old + c_dy1 * jy) - c_dy0 * jy_old;
+
+  double2 ex = dx / eps_x;                    // fdtdTE_upml.c:283
+  double2 ey = dy / eps_y;                    // fdtdTE_upml.c:289
+  const int i = r - 1, j = j_base + c;
+  if (v.pulse[0].enabled && eps_x != 1.0)     // fdtdTE_upml.c:186-187
+    ex = ex + pulse_term(v.pulse[0], i, j, eps_x);
+  if (v.pulse[1].enabled && eps_y != 1.0)     // fdtdTE_upml.c:188-189
+    ey = ey + pulse_term(v.pulse[1], i, j, eps_y);
+  if ((long long)k == v.point_k)
+    ex = ex + make_double2(v.point_re, v.point_im);
+
+  v.f[B200FDTD_TE_JX][k] = jx;
+  v.f[B200FDTD_TE_DX][k] = dx;
+  v.f[B200FDTD_TE_JY][k] = jy;
+  v.f[B200FDTD_TE_DY][k] = dy;
+  v.f[B200FDTD_TE_EX][k] = ex;
+  v.f[B200FDTD_TE_EY][k] = ey;
+}
+
+// One halo column <-> a contiguous buffer of n_px complex values.
+__global__ void halo_column_kernel(double2 *field, double2 *buf, int pitch, int col, int n_px, int pack)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_px) return;
+  const size_t k = (size_t)(i + 1) * pitch + col;
+  if (pack) buf[i] = field[k];
+  else      field[k] = buf[i];
+}
+
+UpmlView make_view(const b200fdtd_engine *e, const b200fdtd_step_args *a)
+{
+  UpmlView v;
+  for (int s = 0; s < B200FDTD_MAX_FIELDS; s++) v.f[s] = e->field[s];
+  v.eps0 = e->eps[0];
+  v.eps1 = e->eps[1];
+  v.ti = e->tab_i;
+  v.tj = e->tab_j;
+  v.pitch = e->pitch;
+  v.rows = e->rows;
+  v.r_lo = e->r_lo;
+  v.c_lo = e->c_lo;
+  v.c_hi = e->c_hi;
+  v.nbx = (e->c_hi - e->c_lo + 1 + kBlock - 1) / kBlock;
+  v.mu0 = e->g.mu0;
+  v.pulse[0] = a->pulse[0];
+  v.pulse[1] = a->pulse[1];
+  v.point_k = -1;
+  v.point_re = a->point.re;
+  v.point_im = a->point.im;
+  if (a->point.enabled) {
+    const int pj = a->point.j - e->g.j0;
+    if (pj >= 0 && pj < e->g.nj && a->point.i >= 0 && a->point.i < e->g.n_px)
+      v.point_k = (long long)(a->point.i + 1) * e->pitch + pj + B200_JOFF;
+  }
+  return v;
+}
+
+bool is_tm(int kind) { return kind == B200FDTD_TM_UPML || kind == B200FDTD_MPI_TM_UPML; }
+
+}  // namespace
+
+int b200_launch_upml_h(b200fdtd_engine *e, const b200fdtd_step_args *a)
+{
+  if (e->r_hi < e->r_lo || e->c_hi < e->c_lo) return B200FDTD_OK;   // slab owns no updated cell
+  const UpmlView v = make_view(e, a);
+  const long long nblk = (long long)v.nbx * (e->r_hi - e->r_lo + 1);
+  if (is_tm(e->g.kind)) tm_upml_h_kernel<<<(unsigned)nblk, kBlock, 0, e->stream>>>(v);
+  else                  te_upml_h_kernel<<<(unsigned)nblk, kBlock, 0, e->stream>>>(v);
+  e->launches++;
+  B200_CUDA(cudaGetLastError());
+  return B200FDTD_OK;
+}
+
+int b200_launch_upml_e(b200fdtd_engine *e, const b200fdtd_step_args *a)
+{
+  if (e->r_hi < e->r_lo || e->c_hi < e->c_lo) return B200FDTD_OK;
+  const UpmlView v = make_view(e, a);
+  const long long nblk = (long long)v.nbx * (e->r_hi - e->r_lo + 1);
+  const int j_base = e->g.j0 - B200_JOFF;     // global j = j_base + c
+  if (is_tm(e->g.kind)) tm_upml_e_kernel<<<(unsigned)nblk, kBlock, 0, e->stream>>>(v, j_base);
+  else                  te_upml_e_kernel<<<(unsigned)nblk, kBlock, 0, e->stream>>>(v, j_base);
+  e->launches++;
+  B200_CUDA(cudaGetLastError());
+  return B200FDTD_OK;
+}
+
+int b200_launch_halo(b200fdtd_engine *e, int which, void *buf, bool pack)
+{
+  int slot, col;
+  if (which == 0) {           // after the H phase: Hx (TM) / Hz (TE), last owned -> low ghost
+    slot = is_tm(e->g.kind) ? (int)B200FDTD_TM_HX : (int)B200FDTD_TE_HZ;
+    col = pack ? B200_JOFF + e->g.nj - 1 : B200_JOFF - 1;
+  } else {                    // after the E phase: Ez (TM) / Ex (TE), first owned -> high ghost
+    slot = is_tm(e->g.kind) ? (int)B200FDTD_TM_EZ : (int)B200FDTD_TE_EX;
+    col = pack ? B200_JOFF : B200_JOFF + e->g.nj;
+  }
+  const int n = e->g.n_px;
+  halo_column_kernel<<<(n + 255) / 256, 256, 0, e->stream>>>(e->field[slot], (double2 *)buf,
+                                                             e->pitch, col, n, pack ? 1 : 0);
+  e->launches++;
+  B200_CUDA(cudaGetLastError());
+  return B200FDTD_OK;
+}

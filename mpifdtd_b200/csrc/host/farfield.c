@@ -1,0 +1,131 @@
+/* farfield.c -- host side of the NTFF path: the sampling plan handed to the GPU
+ * engine, the constants of the far-field post-processing, and the on-disk
+ * formats.
+ *
+ * What it restates (rennone/mpiFDTD): the per-direction time-shift recurrence of
+ * ntffTM_TimeCalc / ntffTE_TimeCalc (ntffTM.c:316-369, ntffTE.c:90-155), the
+ * translate coefficient and direction cosines of ntffT?_TimeTranslate
+ * (ntffTM.c:161-179, ntffTE.c:20-40), the twiddle factors of the radix-2 FFT
+ * (cfft.c:131-141) and the writers of ntff.c:6-33.  Everything here is evaluated
+ * with the host libm so the constants match the reference bit for bit; all
+ * summation over the surface history runs on the GPU.
+ */
+#define _USE_MATH_DEFINES
+#include <complex.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include "host_internal.h"
+
+#ifndef M_PI
+#define M_PI 3.1415926535897932384626433832795
+#endif
+
+int mpifdtd_ntff_point_count(const NTFFInfo *box)
+{
+  return 2 * (box->right - box->left) + 2 * (box->top - box->bottom);
+}
+
+/* table[a*P + p] = the value `timeShift` holds when the reference visits point p
+ * for direction a.  Points are ordered bottom, right, top, left.  Each edge
+ * starts from -(r1 . r2) + RFperC at its first cell and is then decremented once
+ * per cell, exactly like the running variable in the reference loops (so the
+ * accumulated rounding is the same).  stagger = 0 for TM, 0.5 for TE, where the
+ * E samples sit half a cell along the edge (ntffTE.c:102,116,130,145). */
+double *mpifdtd_ntff_time_shift(const NTFFInfo *box, int n_angles, double stagger)
+{
+  const int nx = box->right - box->left, ny = box->top - box->bottom;
+  const int P = 2 * nx + 2 * ny;
+  double *table = (double *)malloc(sizeof(double) * (size_t)n_angles * (size_t)P);
+  if (table == NULL) { printf("cannot allocate NTFF time-shift table\n"); exit(2); }
+
+  const double lt_cx = box->left - box->cx,   rt_cx = box->right - box->cx;
+  const double bm_cy = box->bottom - box->cy, tp_cy = box->top - box->cy;
+  const double to_rad = M_PI / 180.0;
+
+  for (int a = 0; a < n_angles; a++) {
+    double rad = a * to_rad;
+    double r1x = cos(rad) / C_0_S, r1y = sin(rad) / C_0_S;
+    double *row = table + (size_t)a * P;
+    /* edge start vectors r2 = first cell - centre */
+    const double start[4][2] = { { lt_cx + stagger, bm_cy },      /* bottom: (l,b) -> (r,b) */
+                                 { rt_cx, bm_cy + stagger },      /* right:  (r,b) -> (r,t) */
+                                 { lt_cx + stagger, tp_cy },      /* top:    (l,t) -> (r,t) */
+                                 { lt_cx, bm_cy + stagger } };    /* left:   (l,b) -> (l,t) */
+    int p = 0;
+    for (int edge = 0; edge < 4; edge++) {
+      const int along_x = (edge == 0 || edge == 2);
+      const int len = along_x ? nx : ny;
+      const double step = along_x ? r1x : r1y;
+      double shift = -(r1x * start[edge][0] + r1y * start[edge][1]) + box->RFperC;
+      for (int n = 0; n < len; n++) {
+        row[p++] = shift;
+        shift -= step;
+      }
+    }
+  }
+  return table;
+}
+
+/* 1/(4 pi C) * csqrt(2 pi C / (i omega))  (ntffTM.c:165, ntffTE.c:25) */
+double complex mpifdtd_ntff_translate_coef(double omega)
+{
+  return 1.0 / (4 * M_PI * C_0_S) * csqrt(2 * M_PI * C_0_S / (I * omega));
+}
+
+/* cos(phi), sin(phi) per direction.  TM forms phi as ang*(pi/180) (ntffTM.c:169,173),
+ * TE as ang*pi/180 (ntffTE.c:33): different roundings, both kept. */
+void mpifdtd_ntff_direction_cosines(int n_angles, int is_tm, double *cos_phi, double *sin_phi)
+{
+  const double to_rad = M_PI / 180.0;
+  for (int a = 0; a < n_angles; a++) {
+    double phi = is_tm ? a * to_rad : a * M_PI / 180.0;
+    cos_phi[a] = cos(phi);
+    sin_phi[a] = sin(phi);
+  }
+}
+
+/* Twiddles of the n-point decimation-in-frequency FFT, stage by stage (span
+ * halves n/2, n/4, ..., 1): cexp(I*sign*w*k) with sign = -1, w = -pi/half
+ * (cfft.c:131-141), i.e. the positive-exponent transform.  n-1 complex values. */
+double complex *mpifdtd_fft_twiddles(int n)
+{
+  double complex *tw = (double complex *)malloc(sizeof(double complex) * (size_t)(n > 1 ? n - 1 : 1));
+  if (tw == NULL) { printf("cannot allocate FFT twiddles\n"); exit(2); }
+  const double sign = -1.;
+  size_t at = 0;
+  for (int half = n / 2; half >= 1; half /= 2) {
+    double w = -M_PI / half;
+    for (int k = 0; k < half; k++)
+      tw[at++] = cexp(I * sign * w * k);
+  }
+  return tw;
+}
+
+/* ---- on-disk formats (ntff.c:6-33) ----------------------------------------
+ * text: one line per wavelength, "<nm> " then 360 values printed with "%lf.20 "
+ * (upstream's format string: six decimals followed by the literal ".20");
+ * binary: 321 rows of 360 float64, row = wavelength 380..700 nm. */
+void ntff_outputEnormTxt(double **e_norm, const char *file_name)
+{
+  FILE *fp = FileOpen(file_name, "w");
+  for (int nm = LAMBDA_ST_NM; nm <= LAMBDA_EN_NM; nm++) {
+    fprintf(fp, "%d ", nm);
+    for (int ang = 0; ang < 360; ang++)
+      fprintf(fp, "%lf.20 ", e_norm[nm - LAMBDA_ST_NM][ang]);
+    fprintf(fp, "\n");
+  }
+  fclose(fp);
+}
+
+void ntff_outputEnormBin(double **e_norm, const char *file_name)
+{
+  FILE *fp = FileOpen(file_name, "wb");
+  for (int row = 0; row <= LAMBDA_EN_NM - LAMBDA_ST_NM; row++) {
+    if (fwrite(e_norm[row], sizeof(double), 360, fp) < 360) {
+      printf("error in write binary %s\n", file_name);
+      exit(2);
+    }
+  }
+  fclose(fp);
+}

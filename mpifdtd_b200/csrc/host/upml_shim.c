@@ -1,0 +1,380 @@
+/* upml_shim.c -- the serial UPML solvers' entry points (fdtdTM_upml_get*,
+ * fdtdTE_upml_get*) implemented over the GPU engine of include/b200fdtd.h.
+ *
+ * Lifecycle contract kept from rennone/mpiFDTD (fdtdTM_upml.c:54-135,
+ * fdtdTE_upml.c:60-192):
+ *   init()   after field_init + models_initModel: allocate, build eps maps and
+ *            coefficients, prepare the NTFF          (allocateMemories,
+ *            setCoefficient, ntffT?_init)
+ *   update() one time step; the host advances time afterwards (simulator_calc)
+ *   reset()  write "<angle>[deg].txt" and "<angle>[deg]_380nm_700nm_b.dat" into
+ *            cwd, then zero all state
+ *   finish() reset() + free
+ *   getters  borrowed host pointers, k = i*N_PY + j, valid from init to finish
+ *
+ * What moved: the nine complex fields live in GPU memory; the 15 dense
+ * coefficient arrays of the reference are twelve 1-D tables; update() is an
+ * asynchronous launch; getters refresh a pinned host mirror on demand.
+ */
+#define _USE_MATH_DEFINES
+#include <complex.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <unistd.h>
+#include "b200fdtd.h"
+#include "host_internal.h"
+
+#ifndef M_PI
+#define M_PI 3.1415926535897932384626433832795
+#endif
+
+#define N_ANGLES 360
+
+typedef struct UpmlSolver {
+  int kind;                       /* B200FDTD_TM_UPML or B200FDTD_TE_UPML          */
+  b200fdtd_engine *engine;
+  double *eps[3];                 /* host maps: TM EZ,HX,HY (HX/HY lazily) | TE EX,EY,HZ */
+  dcomplex *mirror[3];            /* pinned mirrors for the X, Y, Z getters        */
+  int n_cell;
+  int point_source;               /* opt-in, see mpifdtd_enablePointSource         */
+} UpmlSolver;
+
+static UpmlSolver tm_solver = { .kind = B200FDTD_TM_UPML };
+static UpmlSolver te_solver = { .kind = B200FDTD_TE_UPML };
+static int point_source_requested;
+
+static void die_on(int rc, const char *what)
+{
+  if (rc == B200FDTD_OK) return;
+  printf("b200fdtd: %s failed (%d): %s\n", what, rc, b200fdtd_last_error());
+  exit(2);
+}
+
+/* Opt-in CW point source at the domain centre (the reference's field_pointLight,
+ * field.c:145-152, has no caller).  Exists so the NoModel configuration, whose
+ * scattered-field sources are identically zero, has something to propagate. */
+void mpifdtd_enablePointSource(int on) { point_source_requested = on; }
+
+/* ---- coefficient tables ------------------------------------------------------
+ * Same expressions as setCoefficient (fdtdTM_upml.c:230-271, fdtdTE_upml.c:367-409)
+ * evaluated once per row / column instead of once per cell.  sigma_z = 0 and
+ * eps = EPSILON_0_S in every coefficient, which is what makes them separable. */
+static void build_tables(const UpmlSolver *s, double *ti, double *tj)
+{
+  FieldInfo_S g = field_getFieldInfo_S();
+  const double R = 1.0e-8, M = 2.0;
+  const double eps = EPSILON_0_S, sig_z = 0;
+  if (s->kind == B200FDTD_TM_UPML) {
+    const double sig_max = -(M + 1.0) * EPSILON_0_S * C_0_S / 2.0 / N_PML / cos(M_PI / 3) * log(R);
+    for (int i = 0; i < g.N_PX; i++) {
+      double sig_ez_x = sig_max * field_sigmaX(i, 0);
+      double sig_hx_x = sig_max * field_sigmaX(i, 0.5);
+      double sig_hy_x = sig_max * field_sigmaX(i + 0.5, 0);
+      ti[B200FDTD_TMI_C_JZ * g.N_PX + i]     = (2 * eps - sig_ez_x) / (2 * eps + sig_ez_x);
+      ti[B200FDTD_TMI_C_JZHXHY * g.N_PX + i] = (2 * eps) / (2 * eps + sig_ez_x);
+      ti[B200FDTD_TMI_C_BXMX1 * g.N_PX + i]  = (2 * eps + sig_hx_x) / (2 * eps + sig_z);
+      ti[B200FDTD_TMI_C_BXMX0 * g.N_PX + i]  = (2 * eps - sig_hx_x) / (2 * eps + sig_z);
+      ti[B200FDTD_TMI_C_BY * g.N_PX + i]     = (2 * eps - sig_hy_x) / (2 * eps + sig_hy_x);
+      ti[B200FDTD_TMI_DEN_BYMY * g.N_PX + i] = (2 * eps + sig_hy_x);
+    }
+    for (int j = 0; j < g.N_PY; j++) {
+      double sig_ez_y = sig_max * field_sigmaY(0, j);
+      double sig_hx_y = sig_max * field_sigmaY(0, j + 0.5);
+      double sig_hy_y = sig_max * field_sigmaY(0.5, j);
+      tj[B200FDTD_TMJ_C_DZ * g.N_PY + j]      = (2 * eps - sig_ez_y) / (2 * eps + sig_ez_y);
+      tj[B200FDTD_TMJ_C_DZJZ * g.N_PY + j]    = (2 * eps + sig_z) / (2 * eps + sig_ez_y);
+      tj[B200FDTD_TMJ_C_MX * g.N_PY + j]      = (2 * eps - sig_hx_y) / (2 * eps + sig_hx_y);
+      tj[B200FDTD_TMJ_C_MXEZ * g.N_PY + j]    = (2 * eps) / (2 * eps + sig_hx_y);
+      tj[B200FDTD_TMJ_NUM_BYMY1 * g.N_PY + j] = (2 * eps + sig_hy_y);
+      tj[B200FDTD_TMJ_NUM_BYMY0 * g.N_PY + j] = (2 * eps - sig_hy_y);
+    }
+  } else {
+    /* no cos(pi/3) factor for TE (fdtdTE_upml.c:369) */
+    const double sig_max = -(M + 1.0) * EPSILON_0_S * LIGHT_SPEED_S / 2.0 / N_PML * log(R);
+    for (int i = 0; i < g.N_PX; i++) {
+      double sig_ex_x = sig_max * field_sigmaX(i + 0.5, 0);
+      double sig_ey_x = sig_max * field_sigmaX(i, 0.5);
+      double sig_hz_x = sig_max * field_sigmaX(i + 0.5, 0.5);
+      ti[B200FDTD_TEI_C_DXJX1 * g.N_PX + i]  = (2 * eps + sig_ex_x) / (2 * eps + sig_z);
+      ti[B200FDTD_TEI_C_DXJX0 * g.N_PX + i]  = (2 * eps - sig_ex_x) / (2 * eps + sig_z);
+      ti[B200FDTD_TEI_C_DY * g.N_PX + i]     = (2 * eps - sig_ey_x) / (2 * eps + sig_ey_x);
+      ti[B200FDTD_TEI_DEN_DYJY * g.N_PX + i] = (2 * eps + sig_ey_x);
+      ti[B200FDTD_TEI_C_MZ * g.N_PX + i]     = (2 * eps - sig_hz_x) / (2 * eps + sig_hz_x);
+      ti[B200FDTD_TEI_C_MZEXEY * g.N_PX + i] = (2 * eps) / (2 * eps + sig_hz_x);
+    }
+    for (int j = 0; j < g.N_PY; j++) {
+      double sig_ex_y = sig_max * field_sigmaY(0.5, j);
+      double sig_ey_y = sig_max * field_sigmaY(0, j + 0.5);
+      double sig_hz_y = sig_max * field_sigmaY(0.5, j + 0.5);
+      tj[B200FDTD_TEJ_C_JX * g.N_PY + j]      = (2 * eps - sig_ex_y) / (2 * eps + sig_ex_y);
+      tj[B200FDTD_TEJ_C_JXHZ * g.N_PY + j]    = (2 * eps) / (2 * eps + sig_ex_y);
+      tj[B200FDTD_TEJ_NUM_DYJY1 * g.N_PY + j] = (2 * eps + sig_ey_y);
+      tj[B200FDTD_TEJ_NUM_DYJY0 * g.N_PY + j] = (2 * eps - sig_ey_y);
+      tj[B200FDTD_TEJ_C_BZ * g.N_PY + j]      = (2 * eps - sig_hz_y) / (2 * eps + sig_hz_y);
+      tj[B200FDTD_TEJ_C_BZMZ * g.N_PY + j]    = (2 * eps + sig_z) / (2 * eps + sig_hz_y);
+    }
+  }
+}
+
+/* Exposed for the parity tests: the 1-D tables expanded back to the reference's
+ * dense coefficient (name as in fdtdTM_upml.c:30-35 / fdtdTE_upml.c:27-32). */
+int mpifdtd_upml_dense_coefficient(int kind, const char *name, double *dst)
+{
+  FieldInfo_S g = field_getFieldInfo_S();
+  UpmlSolver probe = { .kind = kind };
+  double *ti = (double *)malloc(sizeof(double) * B200FDTD_UPML_TABS * g.N_PX);
+  double *tj = (double *)malloc(sizeof(double) * B200FDTD_UPML_TABS * g.N_PY);
+  build_tables(&probe, ti, tj);
+  /* each dense array = I[i] (by-i), J[j] (by-j), constant 1, or J[j] / I[i] */
+  struct { const char *name; int kind, by_i, by_j; } map[] = {
+    { "C_JZ", B200FDTD_TM_UPML, B200FDTD_TMI_C_JZ, -1 },
+    { "C_JZHXHY", B200FDTD_TM_UPML, B200FDTD_TMI_C_JZHXHY, -1 },
+    { "C_BXMX1", B200FDTD_TM_UPML, B200FDTD_TMI_C_BXMX1, -1 },
+    { "C_BXMX0", B200FDTD_TM_UPML, B200FDTD_TMI_C_BXMX0, -1 },
+    { "C_BY", B200FDTD_TM_UPML, B200FDTD_TMI_C_BY, -1 },
+    { "C_DZ", B200FDTD_TM_UPML, -1, B200FDTD_TMJ_C_DZ },
+    { "C_DZJZ1", B200FDTD_TM_UPML, -1, B200FDTD_TMJ_C_DZJZ },
+    { "C_DZJZ0", B200FDTD_TM_UPML, -1, B200FDTD_TMJ_C_DZJZ },
+    { "C_MX", B200FDTD_TM_UPML, -1, B200FDTD_TMJ_C_MX },
+    { "C_MXEZ", B200FDTD_TM_UPML, -1, B200FDTD_TMJ_C_MXEZ },
+    { "C_BYMY1", B200FDTD_TM_UPML, B200FDTD_TMI_DEN_BYMY, B200FDTD_TMJ_NUM_BYMY1 },
+    { "C_BYMY0", B200FDTD_TM_UPML, B200FDTD_TMI_DEN_BYMY, B200FDTD_TMJ_NUM_BYMY0 },
+    { "C_BX", B200FDTD_TM_UPML, -1, -1 }, { "C_MY", B200FDTD_TM_UPML, -1, -1 },
+    { "C_MYEZ", B200FDTD_TM_UPML, -1, -1 },
+    { "C_DXJX1", B200FDTD_TE_UPML, B200FDTD_TEI_C_DXJX1, -1 },
+    { "C_DXJX0", B200FDTD_TE_UPML, B200FDTD_TEI_C_DXJX0, -1 },
+    { "C_DY", B200FDTD_TE_UPML, B200FDTD_TEI_C_DY, -1 },
+    { "C_MZ", B200FDTD_TE_UPML, B200FDTD_TEI_C_MZ, -1 },
+    { "C_MZEXEY", B200FDTD_TE_UPML, B200FDTD_TEI_C_MZEXEY, -1 },
+    { "C_JX", B200FDTD_TE_UPML, -1, B200FDTD_TEJ_C_JX },
+    { "C_JXHZ", B200FDTD_TE_UPML, -1, B200FDTD_TEJ_C_JXHZ },
+    { "C_BZ", B200FDTD_TE_UPML, -1, B200FDTD_TEJ_C_BZ },
+    { "C_BZMZ1", B200FDTD_TE_UPML, -1, B200FDTD_TEJ_C_BZMZ },
+    { "C_BZMZ0", B200FDTD_TE_UPML, -1, B200FDTD_TEJ_C_BZMZ },
+    { "C_DYJY1", B200FDTD_TE_UPML, B200FDTD_TEI_DEN_DYJY, B200FDTD_TEJ_NUM_DYJY1 },
+    { "C_DYJY0", B200FDTD_TE_UPML, B200FDTD_TEI_DEN_DYJY, B200FDTD_TEJ_NUM_DYJY0 },
+    { "C_DX", B200FDTD_TE_UPML, -1, -1 }, { "C_JY", B200FDTD_TE_UPML, -1, -1 },
+    { "C_JYHZ", B200FDTD_TE_UPML, -1, -1 },
+  };
+  int found = 0;
+  for (size_t m = 0; m < sizeof map / sizeof map[0] && !found; m++) {
+    if (map[m].kind != kind || strcmp(map[m].name, name) != 0) continue;
+    found = 1;
+    for (int i = 0; i < g.N_PX; i++)
+      for (int j = 0; j < g.N_PY; j++) {
+        double v = 1.0;
+        if (map[m].by_i >= 0 && map[m].by_j >= 0)
+          v = tj[map[m].by_j * g.N_PY + j] / ti[map[m].by_i * g.N_PX + i];
+        else if (map[m].by_i >= 0) v = ti[map[m].by_i * g.N_PX + i];
+        else if (map[m].by_j >= 0) v = tj[map[m].by_j * g.N_PY + j];
+        dst[(size_t)i * g.N_PY + j] = v;
+      }
+  }
+  free(ti); free(tj);
+  return found ? 0 : -1;
+}
+
+/* ---- init -------------------------------------------------------------------- */
+static void solver_init(UpmlSolver *s)
+{
+  FieldInfo_S g = field_getFieldInfo_S();
+  NTFFInfo box = field_getNTFFInfo();
+  const int tm = (s->kind == B200FDTD_TM_UPML);
+  s->n_cell = g.N_CELL;
+  s->point_source = point_source_requested;
+
+  b200fdtd_grid grid;
+  memset(&grid, 0, sizeof grid);
+  grid.kind = s->kind;
+  grid.n_px = g.N_PX;  grid.n_py = g.N_PY;  grid.n_pml = g.N_PML;
+  grid.j0 = 0;         grid.nj = g.N_PY;
+  grid.i_lo = 1;       grid.i_hi = g.N_PX - 2;      /* fdtdTM_upml.c:158-159 */
+  grid.j_lo = 1;       grid.j_hi = g.N_PY - 2;
+  grid.device = -1;
+  grid.mu0 = MU_0_S;
+  die_on(b200fdtd_create(&grid, &s->engine), "b200fdtd_create");
+
+  /* permittivity maps.  TM: EPS_EZ at (i,j) area-averaged; EPS_HX/EPS_HY are
+   * computed upstream but never read (fdtdTM_upml.c:237-239), so they are not
+   * built.  TE: EPS_EX at (i+1/2, j) averaged along y, EPS_EY at (i, j+1/2)
+   * along x (fdtdTE_upml.c:374-375); EPS_HZ likewise unused. */
+  const int n_eps = tm ? 1 : 2;
+  for (int m = 0; m < n_eps; m++)
+    die_on(b200fdtd_host_alloc((void **)&s->eps[m], sizeof(double) * (size_t)g.N_CELL), "host_alloc(eps)");
+  if (tm) {
+    mpifdtd_fill_eps(s->eps[0], 0, 0, D_XY);
+  } else {
+    mpifdtd_fill_eps(s->eps[0], 0.5, 0, D_Y);
+    mpifdtd_fill_eps(s->eps[1], 0, 0.5, D_X);
+  }
+  for (int m = 0; m < n_eps; m++)
+    die_on(b200fdtd_set_eps(s->engine, m, s->eps[m]), "b200fdtd_set_eps");
+
+  double *ti = (double *)malloc(sizeof(double) * B200FDTD_UPML_TABS * g.N_PX);
+  double *tj = (double *)malloc(sizeof(double) * B200FDTD_UPML_TABS * g.N_PY);
+  build_tables(s, ti, tj);
+  die_on(b200fdtd_set_upml_tables(s->engine, ti, tj), "b200fdtd_set_upml_tables");
+  free(ti); free(tj);
+
+  for (int m = 0; m < 3; m++)
+    die_on(b200fdtd_host_alloc((void **)&s->mirror[m], sizeof(dcomplex) * (size_t)g.N_CELL), "host_alloc(mirror)");
+
+  /* ntffT?_init: surface, history length = stepNum, bins kept = the part of
+   * arraySize the far field reads (ntffTM.c:181: i < maxTime) */
+  b200fdtd_ntff_plan plan;
+  memset(&plan, 0, sizeof plan);
+  plan.top = box.top; plan.bottom = box.bottom; plan.left = box.left; plan.right = box.right;
+  plan.n_points = mpifdtd_ntff_point_count(&box);
+  plan.max_time = (int)field_getMaxTime();
+  plan.n_bins = getenv("MPIFDTD_NTFF_FULL_BINS") ? box.arraySize : plan.max_time;
+  plan.n_angles = N_ANGLES;
+  plan.array_size = box.arraySize;
+  double *shift = mpifdtd_ntff_time_shift(&box, N_ANGLES, tm ? 0.0 : 0.5);
+  plan.time_shift = shift;
+  if (plan.n_points > 0 && plan.max_time > 0)
+    die_on(b200fdtd_set_ntff_plan(s->engine, &plan), "b200fdtd_set_ntff_plan");
+  free(shift);
+}
+
+/* ---- update ------------------------------------------------------------------ */
+static void fill_pulse(b200fdtd_pulse *p, double gap_x, double gap_y, double dot)
+{
+  FieldInfo_S g = field_getFieldInfo_S();
+  double rad = field_getWaveAngle() * M_PI / 180.0;           /* field.c:228-241 */
+  double cos_per_c = cos(rad) / C_0_S, sin_per_c = sin(rad) / C_0_S;
+  const double center_peak = (g.N_PX / 2.0 + gap_x) * cos_per_c + (g.N_PY / 2 + gap_y) * sin_per_c;
+  const double t0 = -center_peak + 500;
+  p->enabled = 1;
+  p->gap_x = gap_x;  p->gap_y = gap_y;  p->dot = dot;
+  p->cos_per_c = cos_per_c;  p->sin_per_c = sin_per_c;
+  p->time_minus_t0 = field_getTime() - t0;
+  p->omega = field_getOmega();
+  p->beam_width = 50;
+}
+
+static void solver_update(UpmlSolver *s)
+{
+  b200fdtd_step_args a;
+  memset(&a, 0, sizeof a);
+  a.time = field_getTime();
+  a.ray_coef = field_getRayCoef();
+  if (s->kind == B200FDTD_TM_UPML) {
+    fill_pulse(&a.pulse[0], 0, 0, 1.0);                       /* fdtdTM_upml.c:63 */
+  } else {
+    /* polarisation 90 degrees from the wave vector (fdtdTE_upml.c:182-189); both
+     * components fire at 0 degrees because cos(90 deg) != 0 in floating point */
+    WaveInfo_S w = field_getWaveInfo_S();
+    double co = cos((w.Angle_deg + 90) * M_PI / 180.0);
+    double si = sin((w.Angle_deg + 90) * M_PI / 180.0);
+    if (co != 0.0) fill_pulse(&a.pulse[0], 0.5, 0.0, co);
+    if (si != 0.0) fill_pulse(&a.pulse[1], 0.0, 0.5, si);
+  }
+  if (s->point_source) {
+    dcomplex v = field_pointLight();
+    a.point.enabled = 1;
+    a.point.i = N_PX / 2;  a.point.j = N_PY / 2;
+    a.point.re = creal(v); a.point.im = cimag(v);
+  }
+  die_on(b200fdtd_step(s->engine, &a), "b200fdtd_step");
+}
+
+/* ---- reset / finish ------------------------------------------------------------ */
+/* ntffT?_TimeOutput (ntffTM.c:197-275, ntffTE.c:160-238) */
+static void write_far_field(UpmlSolver *s)
+{
+  if (field_getMaxTime() < 1) return;
+  const int tm = (s->kind == B200FDTD_TM_UPML);
+  const int rows = LAMBDA_EN_NM - LAMBDA_ST_NM + 1;
+  double *table = (double *)malloc(sizeof(double) * (size_t)rows * N_ANGLES);
+  double **by_row = (double **)malloc(sizeof(double *) * (size_t)rows);
+  double cos_phi[N_ANGLES], sin_phi[N_ANGLES];
+  mpifdtd_ntff_direction_cosines(N_ANGLES, tm, cos_phi, sin_phi);
+  double complex coef = mpifdtd_ntff_translate_coef(field_getOmega());
+  double complex *tw = mpifdtd_fft_twiddles(NTFF_NUM);
+  FieldInfo phys = field_getFieldInfo();
+
+  b200fdtd_spectrum_args sa;
+  memset(&sa, 0, sizeof sa);
+  sa.coef_re = creal(coef);  sa.coef_im = cimag(coef);
+  sa.z0 = Z_0_S;
+  sa.cos_phi = cos_phi;  sa.sin_phi = sin_phi;
+  sa.n_fft = NTFF_NUM;
+  sa.lambda_first_nm = LAMBDA_ST_NM;  sa.lambda_last_nm = LAMBDA_EN_NM;
+  sa.c_hu_nfft = C_0_S * phys.h_u_nm * NTFF_NUM;              /* ntffTM.c:227 */
+  sa.twiddle = (const double *)tw;
+  die_on(b200fdtd_ntff_project(s->engine), "b200fdtd_ntff_project");
+  die_on(b200fdtd_ntff_spectrum(s->engine, &sa, table), "b200fdtd_ntff_spectrum");
+  for (int r = 0; r < rows; r++) by_row[r] = table + (size_t)r * N_ANGLES;
+
+  char name[256], cwd[512];
+  if (getcwd(cwd, sizeof cwd) == NULL) cwd[0] = '\0';
+  sprintf(name, "%d[deg].txt", (int)field_getWaveAngle());
+  ntff_outputEnormTxt(by_row, name);
+  printf("saved %s/%s\n", cwd, name);
+  sprintf(name, "%d[deg]_%dnm_%dnm_b.dat", (int)field_getWaveAngle(), LAMBDA_ST_NM, LAMBDA_EN_NM);
+  ntff_outputEnormBin(by_row, name);
+  printf("saved %s/%s\n", cwd, name);
+  free(tw); free(by_row); free(table);
+}
+
+static void solver_reset(UpmlSolver *s)
+{
+  if (s->engine == NULL) return;
+  write_far_field(s);
+  die_on(b200fdtd_zero_state(s->engine), "b200fdtd_zero_state");
+}
+
+static void solver_finish(UpmlSolver *s)
+{
+  if (s->engine == NULL) return;
+  solver_reset(s);
+  die_on(b200fdtd_destroy(s->engine), "b200fdtd_destroy");
+  s->engine = NULL;
+  for (int m = 0; m < 3; m++) {
+    b200fdtd_host_free(s->eps[m]);    s->eps[m] = NULL;
+    b200fdtd_host_free(s->mirror[m]); s->mirror[m] = NULL;
+  }
+}
+
+static dcomplex *solver_field(UpmlSolver *s, int mirror, int slot)
+{
+  if (s->engine == NULL) return NULL;                         /* upstream returns its NULL static */
+  die_on(b200fdtd_get_field(s->engine, slot, (double *)s->mirror[mirror]), "b200fdtd_get_field");
+  return s->mirror[mirror];
+}
+
+/* ---- the exported entry points -------------------------------------------------- */
+static void tm_update(void) { solver_update(&tm_solver); }
+static void tm_init(void)   { solver_init(&tm_solver); }
+static void tm_reset(void)  { solver_reset(&tm_solver); }
+static void tm_finish(void) { solver_finish(&tm_solver); }
+void (*fdtdTM_upml_getUpdate(void))(void) { return tm_update; }
+void (*fdtdTM_upml_getInit(void))(void)   { return tm_init; }
+void (*fdtdTM_upml_getReset(void))(void)  { return tm_reset; }
+void (*fdtdTM_upml_getFinish(void))(void) { return tm_finish; }
+double complex *fdtdTM_upml_getHx(void) { return solver_field(&tm_solver, 0, B200FDTD_TM_HX); }
+double complex *fdtdTM_upml_getHy(void) { return solver_field(&tm_solver, 1, B200FDTD_TM_HY); }
+double complex *fdtdTM_upml_getEz(void) { return solver_field(&tm_solver, 2, B200FDTD_TM_EZ); }
+double *fdtdTM_upml_getEps(void) { return tm_solver.eps[0]; }              /* EPS_EZ */
+
+static void te_update(void) { solver_update(&te_solver); }
+static void te_init(void)   { solver_init(&te_solver); }
+static void te_reset(void)  { solver_reset(&te_solver); }
+static void te_finish(void) { solver_finish(&te_solver); }
+void (*fdtdTE_upml_getUpdate(void))(void) { return te_update; }
+void (*fdtdTE_upml_getInit(void))(void)   { return te_init; }
+void (*fdtdTE_upml_getReset(void))(void)  { return te_reset; }
+void (*fdtdTE_upml_getFinish(void))(void) { return te_finish; }
+double complex *fdtdTE_upml_getEx(void) { return solver_field(&te_solver, 0, B200FDTD_TE_EX); }
+double complex *fdtdTE_upml_getEy(void) { return solver_field(&te_solver, 1, B200FDTD_TE_EY); }
+double complex *fdtdTE_upml_getHz(void) { return solver_field(&te_solver, 2, B200FDTD_TE_HZ); }
+double *fdtdTE_upml_getEps(void) { return te_solver.eps[0]; }              /* EPS_EX, fdtdTE_upml.c:93-96 */
+
+/* engine handle of the active serial UPML solver, for harnesses that want device
+ * timers or the U/W arrays (not part of the reference surface) */
+b200fdtd_engine *mpifdtd_upml_engine(int kind)
+{
+  return kind == B200FDTD_TM_UPML ? tm_solver.engine : te_solver.engine;
+}
