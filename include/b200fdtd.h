@@ -122,7 +122,9 @@ typedef struct b200fdtd_step_args {
  * same repeated subtraction (ntffTM.c:329-334). */
 typedef struct b200fdtd_ntff_plan {
   int32_t top, bottom, left, right;
-  int32_t n_points;                /* 2(right-left) + 2(top-bottom)                  */
+  int32_t n_points;                /* 2(right-left) + 2(top-bottom), whole surface   */
+  int32_t n_local;                 /* points whose column j lies in this engine's     */
+                                   /* slab, in the same order (= n_points for 1 slab) */
   int32_t max_time;                /* steps sampled = length of each point's history  */
   int32_t n_bins;                  /* bins kept per angle in U/W (>= max_time to      */
                                    /*   mirror arraySize; max_time suffices for the   */
@@ -134,8 +136,7 @@ typedef struct b200fdtd_ntff_plan {
                                    /* direction's bin 0 (ntffTM.c:285-287 has no      */
                                    /* bound check).  The projection reproduces that   */
                                    /* spill; 0 disables it.                           */
-  int32_t reserved;
-  const double *time_shift;        /* host, [n_angles][n_points]                      */
+  const double *time_shift;        /* host, [n_angles][n_local]                       */
 } b200fdtd_ntff_plan;
 
 /* Far-field post-processing, ntffT?_TimeTranslate + TimeOutput
@@ -170,6 +171,8 @@ int b200fdtd_set_upml_tables(b200fdtd_engine *e, const double *tab_i, const doub
 /* eps_slot: TM 0 = EPS_EZ; TE 0 = EPS_EX, 1 = EPS_EY.  host_eps is the full
  * [n_px][n_py] map; the engine takes its slab. */
 int b200fdtd_set_eps(b200fdtd_engine *e, int32_t eps_slot, const double *host_eps);
+/* the same from a slab-shaped map [n_px][nj] (what a rank of a multi-GPU run builds) */
+int b200fdtd_set_eps_slab(b200fdtd_engine *e, int32_t eps_slot, const double *slab_eps);
 int b200fdtd_set_ntff_plan(b200fdtd_engine *e, const b200fdtd_ntff_plan *plan);   /* ntffTM_init */
 
 /* ---- the hot path -------------------------------------------------------- */
@@ -196,6 +199,8 @@ int b200fdtd_set_stream(b200fdtd_engine *e, void *cuda_stream);
 /* getters: device slab -> host [n_px][n_py] complex array, columns [j0, j0+nj) */
 int b200fdtd_get_field(b200fdtd_engine *e, int32_t slot, double *host_complex);
 int b200fdtd_set_field(b200fdtd_engine *e, int32_t slot, const double *host_complex);
+/* slab-shaped variant: host array is [n_px][nj] complex (what one rank mirrors) */
+int b200fdtd_get_field_slab(b200fdtd_engine *e, int32_t slot, double *slab_complex);
 int b200fdtd_zero_state(b200fdtd_engine *e);        /* the memsets of reset(), fdtdTM_upml.c:98-113 */
 
 /* ---- NTFF ---------------------------------------------------------------- */

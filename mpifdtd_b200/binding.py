@@ -69,8 +69,8 @@ class StepArgs(C.Structure):
 
 class NtffPlan(C.Structure):
     _fields_ = [("top", C.c_int32), ("bottom", C.c_int32), ("left", C.c_int32), ("right", C.c_int32),
-                ("n_points", C.c_int32), ("max_time", C.c_int32), ("n_bins", C.c_int32),
-                ("n_angles", C.c_int32), ("array_size", C.c_int32), ("reserved", C.c_int32),
+                ("n_points", C.c_int32), ("n_local", C.c_int32), ("max_time", C.c_int32),
+                ("n_bins", C.c_int32), ("n_angles", C.c_int32), ("array_size", C.c_int32),
                 ("time_shift", C.c_void_p)]
 
 
@@ -115,6 +115,7 @@ def lib():
     L.b200fdtd_set_stream.argtypes = [vp, vp]
     L.b200fdtd_get_field.argtypes = [vp, i32, vp]
     L.b200fdtd_set_field.argtypes = [vp, i32, vp]
+    L.b200fdtd_get_field_slab.argtypes = [vp, i32, vp]
     L.b200fdtd_zero_state.argtypes = [vp]
     L.b200fdtd_ntff_project.argtypes = [vp]
     L.b200fdtd_ntff_get_uw.argtypes = [vp, i32, vp]
@@ -146,7 +147,13 @@ def lib():
     L.field_setWaveAngle.argtypes = [C.c_int]
     L.mpifdtd_fill_eps.argtypes = [vp, dbl, dbl, C.c_int]
     L.mpifdtd_upml_dense_coefficient.argtypes = [C.c_int, C.c_char_p, vp]
-    L.mpifdtd_ntff_time_shift.argtypes = [C.POINTER(NTFFInfo), C.c_int, dbl]
+    L.mpifdtd_ntff_time_shift.argtypes = [C.POINTER(NTFFInfo), C.c_int, dbl, C.c_int, C.c_int]
+    L.mpifdtd_ntff_local_count.argtypes = [C.POINTER(NTFFInfo), C.c_int, C.c_int]
+    L.mpifdtd_fill_eps_slab.argtypes = [vp, dbl, dbl, C.c_int, C.c_int, C.c_int]
+    L.mpifdtd_upml_tables.argtypes = [C.c_int, vp, vp]
+    L.b200fdtd_set_eps_slab.argtypes = [vp, i32, vp]
+    L.mpifdtd_upml_step_args.argtypes = [C.c_int, C.c_int, C.POINTER(StepArgs)]
+    L.mpifdtd_upml_far_field.argtypes = [vp, C.c_int, C.c_int, vp]
     L.mpifdtd_ntff_time_shift.restype = vp
     L.mpifdtd_ntff_point_count.argtypes = [C.POINTER(NTFFInfo)]
     L.mpifdtd_fft_twiddles.argtypes = [C.c_int]
@@ -344,6 +351,11 @@ class Engine:
         if out is None:
             out = np.zeros((self.n_px, self.n_py), dtype=np.complex128)
         check(self.L.b200fdtd_get_field(self.h, slot, out.ctypes.data), "get_field")
+        return out
+
+    def get_field_slab(self, slot):
+        out = np.zeros((self.n_px, self.nj), dtype=np.complex128)
+        check(self.L.b200fdtd_get_field_slab(self.h, slot, out.ctypes.data), "get_field_slab")
         return out
 
     def set_field(self, slot, values):

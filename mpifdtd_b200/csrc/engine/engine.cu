@@ -199,9 +199,24 @@ int b200fdtd_set_upml_tables(b200fdtd_engine *e, const double *tab_i, const doub
   return B200FDTD_OK;
 }
 
+static int upload_eps(b200fdtd_engine *e, int32_t slot, const double *host_eps, size_t ld);
+
 int b200fdtd_set_eps(b200fdtd_engine *e, int32_t slot, const double *host_eps)
 {
-  if (!e || !host_eps || slot < 0 || slot > 1 || !e->eps[slot])
+  if (!e || !host_eps) return b200_fail(B200FDTD_ERR_ARG, "NULL argument");
+  return upload_eps(e, slot, host_eps + e->g.j0, (size_t)e->g.n_py);
+}
+
+int b200fdtd_set_eps_slab(b200fdtd_engine *e, int32_t slot, const double *slab_eps)
+{
+  if (!e || !slab_eps) return b200_fail(B200FDTD_ERR_ARG, "NULL argument");
+  return upload_eps(e, slot, slab_eps, (size_t)e->g.nj);
+}
+
+// src points at (i = 0, first owned column); ld = host row stride in doubles
+static int upload_eps(b200fdtd_engine *e, int32_t slot, const double *src, size_t ld)
+{
+  if (slot < 0 || slot > 1 || !e->eps[slot])
     return b200_fail(B200FDTD_ERR_ARG, "bad eps slot %d", slot);
   int rc = select_device(e); if (rc) return rc;
   const b200fdtd_grid &g = e->g;
@@ -210,7 +225,7 @@ int b200fdtd_set_eps(b200fdtd_engine *e, int32_t slot, const double *host_eps)
   e->launches++;
   B200_CUDA(cudaGetLastError());
   B200_CUDA(cudaMemcpy2DAsync(e->eps[slot] + (size_t)e->pitch + B200_JOFF, sizeof(double) * e->pitch,
-                              host_eps + g.j0, sizeof(double) * g.n_py, sizeof(double) * g.nj, g.n_px,
+                              src, sizeof(double) * ld, sizeof(double) * g.nj, g.n_px,
                               cudaMemcpyHostToDevice, e->stream));
   B200_CUDA(cudaStreamSynchronize(e->stream));
   e->have_eps[slot] = true;
@@ -219,7 +234,7 @@ int b200fdtd_set_eps(b200fdtd_engine *e, int32_t slot, const double *host_eps)
 
 int b200fdtd_set_ntff_plan(b200fdtd_engine *e, const b200fdtd_ntff_plan *p)
 {
-  if (!e || !p || !p->time_shift) return b200_fail(B200FDTD_ERR_ARG, "NULL argument");
+  if (!e || !p || (!p->time_shift && p->n_local > 0)) return b200_fail(B200FDTD_ERR_ARG, "NULL argument");
   int rc = select_device(e); if (rc) return rc;
   const b200fdtd_grid &g = e->g;
   const int nx = p->right - p->left, ny = p->top - p->bottom;
@@ -253,20 +268,24 @@ int b200fdtd_set_ntff_plan(b200fdtd_engine *e, const b200fdtd_ntff_plan *p)
   for (int j = p->bottom; j < p->top; j++) push(p->left, j, 3, pg++);
   n.n_local = (int)pts.size();
 
-  std::vector<double> ts((size_t)n.n_angles * (n.n_local ? n.n_local : 1));
-  for (int a = 0; a < n.n_angles; a++)
-    for (int q = 0; q < n.n_local; q++)
-      ts[(size_t)a * n.n_local + q] = p->time_shift[(size_t)a * p->n_points + pts[q].p_global];
+  if (n.n_local != p->n_local) {
+    const int have = n.n_local;
+    memset(&n, 0, sizeof n);
+    return b200_fail(B200FDTD_ERR_ARG, "NTFF plan lists %d local points, slab [%d,+%d) owns %d",
+                     p->n_local, g.j0, g.nj, have);
+  }
 
   rc = dev_alloc_zero(e, (void **)&n.pts, sizeof(NtffPoint) * (size_t)(n.n_local ? n.n_local : 1));
-  if (!rc) rc = dev_alloc_zero(e, (void **)&n.ts, sizeof(double) * ts.size());
+  const size_t ts_count = (size_t)n.n_angles * (size_t)(n.n_local ? n.n_local : 1);
+  if (!rc) rc = dev_alloc_zero(e, (void **)&n.ts, sizeof(double) * ts_count);
   if (!rc) rc = dev_alloc_zero(e, (void **)&n.hist_e, sizeof(double2) * (size_t)n.n_local * n.max_time);
   if (!rc) rc = dev_alloc_zero(e, (void **)&n.hist_h, sizeof(double2) * (size_t)n.n_local * n.max_time);
   if (!rc) rc = dev_alloc_zero(e, (void **)&n.uw, sizeof(double2) * 3 * (size_t)n.n_angles * n.n_bins);
   if (rc) { free_ntff(e); return rc; }
   if (n.n_local) {
     B200_CUDA(cudaMemcpyAsync(n.pts, pts.data(), sizeof(NtffPoint) * pts.size(), cudaMemcpyHostToDevice, e->stream));
-    B200_CUDA(cudaMemcpyAsync(n.ts, ts.data(), sizeof(double) * ts.size(), cudaMemcpyHostToDevice, e->stream));
+    B200_CUDA(cudaMemcpyAsync(n.ts, p->time_shift, sizeof(double) * (size_t)n.n_angles * n.n_local,
+                              cudaMemcpyHostToDevice, e->stream));
   }
   B200_CUDA(cudaStreamSynchronize(e->stream));
   n.ready = true;
@@ -344,6 +363,18 @@ int b200fdtd_get_field(b200fdtd_engine *e, int32_t slot, double *host)
   int rc = select_device(e); if (rc) return rc;
   const b200fdtd_grid &g = e->g;
   B200_CUDA(cudaMemcpy2DAsync(host + 2 * (size_t)g.j0, sizeof(double2) * g.n_py,
+                              e->field[slot] + (size_t)e->pitch + B200_JOFF, sizeof(double2) * e->pitch,
+                              sizeof(double2) * g.nj, g.n_px, cudaMemcpyDeviceToHost, e->stream));
+  B200_CUDA(cudaStreamSynchronize(e->stream));
+  return B200FDTD_OK;
+}
+
+int b200fdtd_get_field_slab(b200fdtd_engine *e, int32_t slot, double *host)
+{
+  if (!e || !host || slot < 0 || slot >= e->n_fields) return b200_fail(B200FDTD_ERR_ARG, "bad field slot %d", slot);
+  int rc = select_device(e); if (rc) return rc;
+  const b200fdtd_grid &g = e->g;
+  B200_CUDA(cudaMemcpy2DAsync(host, sizeof(double2) * g.nj,
                               e->field[slot] + (size_t)e->pitch + B200_JOFF, sizeof(double2) * e->pitch,
                               sizeof(double2) * g.nj, g.n_px, cudaMemcpyDeviceToHost, e->stream));
   B200_CUDA(cudaStreamSynchronize(e->stream));

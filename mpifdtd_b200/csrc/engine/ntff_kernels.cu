@@ -90,53 +90,95 @@ ntff_project_kernel(const NtffPoint *__restrict__ pts, const double *__restrict_
                     int max_time, int steps, int n_bins, int n_angles, int is_tm, int array_size,
                     double2 *uw)
 {
+  __shared__ double s_ts[kProjBlock];
+  __shared__ int s_edge[kProjBlock];
   const int ang = blockIdx.y;
   const int q_block = blockIdx.x * kProjBlock;
   const int q = q_block + (int)threadIdx.x;
   double2 acc[3] = { make_double2(0, 0), make_double2(0, 0), make_double2(0, 0) };
   const int t_limit = steps < max_time ? steps : max_time;
 
-  for (int p = 0; p < n_local; p++) {
-    const double ts = ts_tab[(size_t)ang * n_local + p];
-    const double fl_e = floor(ts + 0.5), fl_h = floor(ts);
-    // nominal centres: E has m = (t-1) + floor(ts+1/2), H has m = t + floor(ts)
-    const int shift_e = (int)fl_e - 1, shift_h = (int)fl_h;
-    // whole block out of range for this point?  (bins q_block .. q_block+127)
-    const int t_hi = q_block + kProjBlock - 1 - (shift_e < shift_h ? shift_e : shift_h) + 2;
-    const int t_lo = q_block - (shift_e > shift_h ? shift_e : shift_h) - 2;
-    if (t_hi < 0 || t_lo >= t_limit) continue;
-
-    const double fe = (ts + 0.5) - fl_e, fh = ts - fl_h;
-    const int reach_e = (fe < 1e-9 || fe > 1.0 - 1e-9) ? 2 : 1;
-    const int reach_h = (fh < 1e-9 || fh > 1.0 - 1e-9) ? 2 : 1;
-
-    const int edge = pts[p].edge;
-    const bool along_x = (edge == 0 || edge == 2);
-    // TM: E -> Ux (0) on bottom/top, Uy (1) on right/left; H -> Wz (2)
-    // TE: E -> Uz (2);  H -> Wx (0) on bottom/top, Wy (1) on right/left
-    const int slot_e = is_tm ? (along_x ? 0 : 1) : 2;
-    const int slot_h = is_tm ? 2 : (along_x ? 0 : 1);
-    if (q < n_bins) {
-      gather(acc[slot_e], hist_e + (size_t)p * max_time, t_limit, q, ts, 1.0, q - shift_e, reach_e);
-      gather(acc[slot_h], hist_h + (size_t)p * max_time, t_limit, q, ts, 0.5, q - shift_h, reach_h);
+  // The surface is walked in chunks of kProjBlock points: every thread tests one
+  // point of the chunk against this block's bin window, so the (common) case of a
+  // point whose retarded time falls outside the recorded steps costs one load per
+  // 128 points instead of one loop trip each.
+  for (int p0 = 0; p0 < n_local; p0 += kProjBlock) {
+    const int pm = p0 + (int)threadIdx.x;
+    double my_ts = 0.0;
+    int my_edge = -1;                                  // -1: nothing to gather from this point
+    if (pm < n_local) {
+      my_ts = ts_tab[(size_t)ang * n_local + pm];
+      const int se = (int)floor(my_ts + 0.5) - 1, sh = (int)floor(my_ts);
+      // steps that can reach bins q_block .. q_block+127 (two extra each side for knife-edges)
+      const int t_hi = q_block + kProjBlock - 1 - (se < sh ? se : sh) + 2;
+      const int t_lo = q_block - (se > sh ? se : sh) - 2;
+      if (t_hi >= 0 && t_lo < t_limit) my_edge = pts[pm].edge;
     }
+    const int any = __syncthreads_or(my_edge >= 0);
+    if (!any) continue;
+    s_ts[threadIdx.x] = my_ts;
+    s_edge[threadIdx.x] = my_edge;
+    __syncthreads();
+    const int chunk = (n_local - p0) < kProjBlock ? (n_local - p0) : kProjBlock;
+    for (int c = 0; c < chunk; c++) {
+      const int edge = s_edge[c];
+      if (edge < 0) continue;
+      const int p = p0 + c;
+      const double ts = s_ts[c];
+      const double fl_e = floor(ts + 0.5), fl_h = floor(ts);
+      // nominal centres: E has m = (t-1) + floor(ts+1/2), H has m = t + floor(ts)
+      const int shift_e = (int)fl_e - 1, shift_h = (int)fl_h;
+      const double fe = (ts + 0.5) - fl_e, fh = ts - fl_h;
+      const int reach_e = (fe < 1e-9 || fe > 1.0 - 1e-9) ? 2 : 1;
+      const int reach_h = (fh < 1e-9 || fh > 1.0 - 1e-9) ? 2 : 1;
+      const bool along_x = (edge == 0 || edge == 2);
+      // TM: E -> Ux (0) on bottom/top, Uy (1) on right/left; H -> Wz (2)
+      // TE: E -> Uz (2);  H -> Wx (0) on bottom/top, Wy (1) on right/left
+      const int slot_e = is_tm ? (along_x ? 0 : 1) : 2;
+      const int slot_h = is_tm ? 2 : (along_x ? 0 : 1);
+      if (q < n_bins) {
+        gather(acc[slot_e], hist_e + (size_t)p * max_time, t_limit, q, ts, 1.0, q - shift_e, reach_e);
+        gather(acc[slot_h], hist_h + (size_t)p * max_time, t_limit, q, ts, 0.5, q - shift_h, reach_h);
+      }
+    }
+    __syncthreads();
   }
   // Row spill of the reference's flat [360][arraySize] storage: a tap at index
   // arraySize + q' of direction ang-1 is physically bin q' of direction ang
   // (calc() has no bound check, ntffTM.c:285-287).  Only the last steps of the
   // points with the largest shift get there, so this touches a few low bins.
-  if (array_size > 0 && ang > 0 && q_block == 0 && q < kSpillBins && q < n_bins) {
+  if (array_size > 0 && ang > 0 && q_block == 0) {          // uniform per block
     const int qv = q + array_size;
-    for (int p = 0; p < n_local; p++) {
-      const double ts = ts_tab[(size_t)(ang - 1) * n_local + p];
-      if (ts + (double)t_limit + 2.0 < (double)array_size) continue;
-      const double fl_e = floor(ts + 0.5), fl_h = floor(ts);
-      const int edge = pts[p].edge;
-      const bool along_x = (edge == 0 || edge == 2);
-      const int slot_e = is_tm ? (along_x ? 0 : 1) : 2;
-      const int slot_h = is_tm ? 2 : (along_x ? 0 : 1);
-      gather(acc[slot_e], hist_e + (size_t)p * max_time, t_limit, qv, ts, 1.0, qv - ((int)fl_e - 1), 2);
-      gather(acc[slot_h], hist_h + (size_t)p * max_time, t_limit, qv, ts, 0.5, qv - (int)fl_h, 2);
+    for (int p0 = 0; p0 < n_local; p0 += kProjBlock) {
+      const int pm = p0 + (int)threadIdx.x;
+      double my_ts = 0.0;
+      int my_edge = -1;
+      if (pm < n_local) {
+        my_ts = ts_tab[(size_t)(ang - 1) * n_local + pm];
+        if (my_ts + (double)t_limit + 2.0 >= (double)array_size) my_edge = pts[pm].edge;
+      }
+      const int any = __syncthreads_or(my_edge >= 0);
+      if (!any) continue;
+      s_ts[threadIdx.x] = my_ts;
+      s_edge[threadIdx.x] = my_edge;
+      __syncthreads();
+      const int chunk = (n_local - p0) < kProjBlock ? (n_local - p0) : kProjBlock;
+      if (q < kSpillBins && q < n_bins) {
+        for (int c = 0; c < chunk; c++) {
+          const int edge = s_edge[c];
+          if (edge < 0) continue;
+          const int p = p0 + c;
+          const double ts = s_ts[c];
+          const bool along_x = (edge == 0 || edge == 2);
+          const int slot_e = is_tm ? (along_x ? 0 : 1) : 2;
+          const int slot_h = is_tm ? 2 : (along_x ? 0 : 1);
+          gather(acc[slot_e], hist_e + (size_t)p * max_time, t_limit, qv, ts, 1.0,
+                 qv - ((int)floor(ts + 0.5) - 1), 2);
+          gather(acc[slot_h], hist_h + (size_t)p * max_time, t_limit, qv, ts, 0.5,
+                 qv - (int)floor(ts), 2);
+        }
+      }
+      __syncthreads();
     }
   }
   if (q < n_bins)

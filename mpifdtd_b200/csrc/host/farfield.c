@@ -26,40 +26,57 @@ int mpifdtd_ntff_point_count(const NTFFInfo *box)
   return 2 * (box->right - box->left) + 2 * (box->top - box->bottom);
 }
 
-/* table[a*P + p] = the value `timeShift` holds when the reference visits point p
- * for direction a.  Points are ordered bottom, right, top, left.  Each edge
- * starts from -(r1 . r2) + RFperC at its first cell and is then decremented once
- * per cell, exactly like the running variable in the reference loops (so the
- * accumulated rounding is the same).  stagger = 0 for TM, 0.5 for TE, where the
- * E samples sit half a cell along the edge (ntffTE.c:102,116,130,145). */
-double *mpifdtd_ntff_time_shift(const NTFFInfo *box, int n_angles, double stagger)
+/* Number of surface points whose column j lies in [j0, j0+nj). */
+int mpifdtd_ntff_local_count(const NTFFInfo *box, int j0, int nj)
+{
+  const int j1 = j0 + nj;
+  int n = 0;
+  if (box->bottom >= j0 && box->bottom < j1) n += box->right - box->left;
+  if (box->top >= j0 && box->top < j1) n += box->right - box->left;
+  int lo = box->bottom > j0 ? box->bottom : j0, hi = box->top < j1 ? box->top : j1;
+  if (hi > lo) n += 2 * (hi - lo);
+  return n;
+}
+
+/* table[a*L + q] = the value `timeShift` holds when the reference visits the
+ * q-th surface point owned by the slab j in [j0, j0+nj), for direction a.  Points
+ * are ordered bottom, right, top, left.  Each edge starts from -(r1 . r2) + RFperC
+ * at its first cell and is then decremented once per cell, exactly like the
+ * running variable in the reference loops (so the accumulated rounding is the
+ * same); cells outside the slab are walked but not stored.  stagger = 0 for TM,
+ * 0.5 for TE, where the E samples sit half a cell along the edge
+ * (ntffTE.c:102,116,130,145). */
+double *mpifdtd_ntff_time_shift(const NTFFInfo *box, int n_angles, double stagger, int j0, int nj)
 {
   const int nx = box->right - box->left, ny = box->top - box->bottom;
-  const int P = 2 * nx + 2 * ny;
-  double *table = (double *)malloc(sizeof(double) * (size_t)n_angles * (size_t)P);
+  const int L = mpifdtd_ntff_local_count(box, j0, nj);
+  double *table = (double *)malloc(sizeof(double) * (size_t)n_angles * (size_t)(L > 0 ? L : 1));
   if (table == NULL) { printf("cannot allocate NTFF time-shift table\n"); exit(2); }
 
   const double lt_cx = box->left - box->cx,   rt_cx = box->right - box->cx;
   const double bm_cy = box->bottom - box->cy, tp_cy = box->top - box->cy;
   const double to_rad = M_PI / 180.0;
+  const int edge_j[4] = { box->bottom, -1, box->top, -1 };     /* fixed j of the x-edges */
 
   for (int a = 0; a < n_angles; a++) {
     double rad = a * to_rad;
     double r1x = cos(rad) / C_0_S, r1y = sin(rad) / C_0_S;
-    double *row = table + (size_t)a * P;
+    double *row = table + (size_t)a * L;
     /* edge start vectors r2 = first cell - centre */
     const double start[4][2] = { { lt_cx + stagger, bm_cy },      /* bottom: (l,b) -> (r,b) */
                                  { rt_cx, bm_cy + stagger },      /* right:  (r,b) -> (r,t) */
                                  { lt_cx + stagger, tp_cy },      /* top:    (l,t) -> (r,t) */
                                  { lt_cx, bm_cy + stagger } };    /* left:   (l,b) -> (l,t) */
-    int p = 0;
+    int q = 0;
     for (int edge = 0; edge < 4; edge++) {
       const int along_x = (edge == 0 || edge == 2);
       const int len = along_x ? nx : ny;
       const double step = along_x ? r1x : r1y;
       double shift = -(r1x * start[edge][0] + r1y * start[edge][1]) + box->RFperC;
       for (int n = 0; n < len; n++) {
-        row[p++] = shift;
+        const int j = along_x ? edge_j[edge] : box->bottom + n;
+        if (j >= j0 && j < j0 + nj)
+          row[q++] = shift;
         shift -= step;
       }
     }

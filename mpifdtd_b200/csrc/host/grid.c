@@ -46,7 +46,8 @@ void field_init(FieldInfo req)
   G.cells.N_PML = G.phys.pml;
   G.cells.N_X   = G.cells.N_PX - 2 * G.cells.N_PML;
   G.cells.N_Y   = G.cells.N_PY - 2 * G.cells.N_PML;
-  G.cells.N_CELL = G.cells.N_PY * G.cells.N_PX;
+  /* wraps for grids beyond 2^31 cells (slab runs never index with it) */
+  G.cells.N_CELL = (int)((unsigned)G.cells.N_PY * (unsigned)G.cells.N_PX);
   G.cells.DX = G.cells.N_PY;
   G.cells.DY = 1;
 

@@ -7,17 +7,25 @@
 
 /* dst[i*N_PY+j] = models_eps(i+xoff, j+yoff, mode) over the whole grid, threaded */
 extern void mpifdtd_fill_eps(double *dst, double xoff, double yoff, enum MODE mode);
+/* slab form: dst[i*nj + (j-j0)] for j in [j0, j0+nj) */
+extern void mpifdtd_fill_eps_slab(double *dst, double xoff, double yoff, enum MODE mode, int j0, int nj);
 
 
 /* farfield.c: NTFF sampling plan and post-processing constants (host libm) */
 extern int mpifdtd_ntff_point_count(const NTFFInfo *box);
-extern double *mpifdtd_ntff_time_shift(const NTFFInfo *box, int n_angles, double stagger);
+extern int mpifdtd_ntff_local_count(const NTFFInfo *box, int j0, int nj);
+extern double *mpifdtd_ntff_time_shift(const NTFFInfo *box, int n_angles, double stagger, int j0, int nj);
 extern double complex mpifdtd_ntff_translate_coef(double omega);
 extern void mpifdtd_ntff_direction_cosines(int n_angles, int is_tm, double *cos_phi, double *sin_phi);
 extern double complex *mpifdtd_fft_twiddles(int n);
 
 /* upml_shim.c */
+#include "b200fdtd.h"
+extern void mpifdtd_upml_step_args(int kind, int point_source, b200fdtd_step_args *a);
+extern void mpifdtd_upml_far_field(b200fdtd_engine *engine, int kind, int project, double *table);
 extern void mpifdtd_enablePointSource(int on);
 extern int mpifdtd_upml_dense_coefficient(int kind, const char *name, double *dst);
+/* the twelve 1-D tables of include/b200fdtd.h for the current field_init() state */
+extern void mpifdtd_upml_tables(int kind, double *tab_i, double *tab_j);
 
 #endif

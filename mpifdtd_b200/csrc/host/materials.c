@@ -65,20 +65,25 @@ void models_moveDirectory(void)
  * dst[i*N_PY + j] = models_eps(i + xoff, j + yoff, mode) for i in [i0, i1).
  * Rows are independent and every callback is a pure function of static model
  * parameters after models_initModel(), so rows are spread over host threads. */
-typedef struct { double *dst; double xoff, yoff; enum MODE mode; int i0, i1, n_py; } EpsJob;
+typedef struct { double *dst; double xoff, yoff; enum MODE mode; int i0, i1, j0, nj; } EpsJob;
 
 static void *eps_rows(void *arg)
 {
   const EpsJob *job = (const EpsJob *)arg;
   for (int i = job->i0; i < job->i1; i++) {
-    double *row = job->dst + (size_t)i * job->n_py;
-    for (int j = 0; j < job->n_py; j++)
-      row[j] = models_eps(i + job->xoff, j + job->yoff, job->mode);
+    double *row = job->dst + (size_t)i * job->nj;
+    for (int j = 0; j < job->nj; j++)
+      row[j] = models_eps(i + job->xoff, (job->j0 + j) + job->yoff, job->mode);
   }
   return NULL;
 }
 
 void mpifdtd_fill_eps(double *dst, double xoff, double yoff, enum MODE mode)
+{
+  mpifdtd_fill_eps_slab(dst, xoff, yoff, mode, 0, field_getFieldInfo_S().N_PY);
+}
+
+void mpifdtd_fill_eps_slab(double *dst, double xoff, double yoff, enum MODE mode, int j0, int nj)
 {
   FieldInfo_S g = field_getFieldInfo_S();
   long ncpu = sysconf(_SC_NPROCESSORS_ONLN);
@@ -91,7 +96,7 @@ void mpifdtd_fill_eps(double *dst, double xoff, double yoff, enum MODE mode)
   for (int t = 0; t < nthr; t++) {
     job[t] = (EpsJob){ dst, xoff, yoff, mode,
                        (int)((long long)g.N_PX * t / nthr),
-                       (int)((long long)g.N_PX * (t + 1) / nthr), g.N_PY };
+                       (int)((long long)g.N_PX * (t + 1) / nthr), j0, nj };
     if (t == nthr - 1 || pthread_create(&tid[t], NULL, eps_rows, &job[t]) != 0) {
       /* last chunk (or a failed spawn) runs on the calling thread */
       eps_rows(&job[t]);

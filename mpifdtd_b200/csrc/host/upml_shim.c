@@ -118,6 +118,12 @@ static void build_tables(const UpmlSolver *s, double *ti, double *tj)
   }
 }
 
+void mpifdtd_upml_tables(int kind, double *tab_i, double *tab_j)
+{
+  UpmlSolver probe = { .kind = kind };
+  build_tables(&probe, tab_i, tab_j);
+}
+
 /* Exposed for the parity tests: the 1-D tables expanded back to the reference's
  * dense coefficient (name as in fdtdTM_upml.c:30-35 / fdtdTE_upml.c:27-32). */
 int mpifdtd_upml_dense_coefficient(int kind, const char *name, double *dst)
@@ -227,11 +233,12 @@ static void solver_init(UpmlSolver *s)
   memset(&plan, 0, sizeof plan);
   plan.top = box.top; plan.bottom = box.bottom; plan.left = box.left; plan.right = box.right;
   plan.n_points = mpifdtd_ntff_point_count(&box);
+  plan.n_local = plan.n_points;
   plan.max_time = (int)field_getMaxTime();
   plan.n_bins = getenv("MPIFDTD_NTFF_FULL_BINS") ? box.arraySize : plan.max_time;
   plan.n_angles = N_ANGLES;
   plan.array_size = box.arraySize;
-  double *shift = mpifdtd_ntff_time_shift(&box, N_ANGLES, tm ? 0.0 : 0.5);
+  double *shift = mpifdtd_ntff_time_shift(&box, N_ANGLES, tm ? 0.0 : 0.5, 0, g.N_PY);
   plan.time_shift = shift;
   if (plan.n_points > 0 && plan.max_time > 0)
     die_on(b200fdtd_set_ntff_plan(s->engine, &plan), "b200fdtd_set_ntff_plan");
@@ -254,41 +261,47 @@ static void fill_pulse(b200fdtd_pulse *p, double gap_x, double gap_y, double dot
   p->beam_width = 50;
 }
 
-static void solver_update(UpmlSolver *s)
+/* Everything update() reads from the host's grid/time state, packed for the
+ * engine.  Also used by slab (multi-GPU) drivers, which call the engine phases
+ * themselves and then field_nextStep(). */
+void mpifdtd_upml_step_args(int kind, int point_source, b200fdtd_step_args *a)
 {
-  b200fdtd_step_args a;
-  memset(&a, 0, sizeof a);
-  a.time = field_getTime();
-  a.ray_coef = field_getRayCoef();
-  if (s->kind == B200FDTD_TM_UPML) {
-    fill_pulse(&a.pulse[0], 0, 0, 1.0);                       /* fdtdTM_upml.c:63 */
+  memset(a, 0, sizeof *a);
+  a->time = field_getTime();
+  a->ray_coef = field_getRayCoef();
+  if (kind == B200FDTD_TM_UPML) {
+    fill_pulse(&a->pulse[0], 0, 0, 1.0);                      /* fdtdTM_upml.c:63 */
   } else {
     /* polarisation 90 degrees from the wave vector (fdtdTE_upml.c:182-189); both
      * components fire at 0 degrees because cos(90 deg) != 0 in floating point */
     WaveInfo_S w = field_getWaveInfo_S();
     double co = cos((w.Angle_deg + 90) * M_PI / 180.0);
     double si = sin((w.Angle_deg + 90) * M_PI / 180.0);
-    if (co != 0.0) fill_pulse(&a.pulse[0], 0.5, 0.0, co);
-    if (si != 0.0) fill_pulse(&a.pulse[1], 0.0, 0.5, si);
+    if (co != 0.0) fill_pulse(&a->pulse[0], 0.5, 0.0, co);
+    if (si != 0.0) fill_pulse(&a->pulse[1], 0.0, 0.5, si);
   }
-  if (s->point_source) {
+  if (point_source) {
     dcomplex v = field_pointLight();
-    a.point.enabled = 1;
-    a.point.i = N_PX / 2;  a.point.j = N_PY / 2;
-    a.point.re = creal(v); a.point.im = cimag(v);
+    a->point.enabled = 1;
+    a->point.i = N_PX / 2;  a->point.j = N_PY / 2;
+    a->point.re = creal(v); a->point.im = cimag(v);
   }
+}
+
+static void solver_update(UpmlSolver *s)
+{
+  b200fdtd_step_args a;
+  mpifdtd_upml_step_args(s->kind, s->point_source, &a);
   die_on(b200fdtd_step(s->engine, &a), "b200fdtd_step");
 }
 
 /* ---- reset / finish ------------------------------------------------------------ */
-/* ntffT?_TimeOutput (ntffTM.c:197-275, ntffTE.c:160-238) */
-static void write_far_field(UpmlSolver *s)
+/* ntffT?_TimeOutput (ntffTM.c:197-275, ntffTE.c:160-238): project the recorded
+ * surface history, translate + FFT + interpolate on the GPU, return the
+ * 321 x 360 table.  Exposed so slab drivers can call it on the reduced U/W. */
+void mpifdtd_upml_far_field(b200fdtd_engine *engine, int kind, int project, double *table)
 {
-  if (field_getMaxTime() < 1) return;
-  const int tm = (s->kind == B200FDTD_TM_UPML);
-  const int rows = LAMBDA_EN_NM - LAMBDA_ST_NM + 1;
-  double *table = (double *)malloc(sizeof(double) * (size_t)rows * N_ANGLES);
-  double **by_row = (double **)malloc(sizeof(double *) * (size_t)rows);
+  const int tm = (kind == B200FDTD_TM_UPML);
   double cos_phi[N_ANGLES], sin_phi[N_ANGLES];
   mpifdtd_ntff_direction_cosines(N_ANGLES, tm, cos_phi, sin_phi);
   double complex coef = mpifdtd_ntff_translate_coef(field_getOmega());
@@ -304,8 +317,19 @@ static void write_far_field(UpmlSolver *s)
   sa.lambda_first_nm = LAMBDA_ST_NM;  sa.lambda_last_nm = LAMBDA_EN_NM;
   sa.c_hu_nfft = C_0_S * phys.h_u_nm * NTFF_NUM;              /* ntffTM.c:227 */
   sa.twiddle = (const double *)tw;
-  die_on(b200fdtd_ntff_project(s->engine), "b200fdtd_ntff_project");
-  die_on(b200fdtd_ntff_spectrum(s->engine, &sa, table), "b200fdtd_ntff_spectrum");
+  if (project)
+    die_on(b200fdtd_ntff_project(engine), "b200fdtd_ntff_project");
+  die_on(b200fdtd_ntff_spectrum(engine, &sa, table), "b200fdtd_ntff_spectrum");
+  free(tw);
+}
+
+static void write_far_field(UpmlSolver *s)
+{
+  if (field_getMaxTime() < 1) return;
+  const int rows = LAMBDA_EN_NM - LAMBDA_ST_NM + 1;
+  double *table = (double *)malloc(sizeof(double) * (size_t)rows * N_ANGLES);
+  double **by_row = (double **)malloc(sizeof(double *) * (size_t)rows);
+  mpifdtd_upml_far_field(s->engine, s->kind, 1, table);
   for (int r = 0; r < rows; r++) by_row[r] = table + (size_t)r * N_ANGLES;
 
   char name[256], cwd[512];
@@ -316,7 +340,7 @@ static void write_far_field(UpmlSolver *s)
   sprintf(name, "%d[deg]_%dnm_%dnm_b.dat", (int)field_getWaveAngle(), LAMBDA_ST_NM, LAMBDA_EN_NM);
   ntff_outputEnormBin(by_row, name);
   printf("saved %s/%s\n", cwd, name);
-  free(tw); free(by_row); free(table);
+  free(by_row); free(table);
 }
 
 static void solver_reset(UpmlSolver *s)
