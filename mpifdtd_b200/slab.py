@@ -30,6 +30,26 @@ def split_columns(n_py, world, rank):
     return j0, base + (1 if rank < extra else 0)
 
 
+def halo_peers(which, rank, world):
+    """(send_to, recv_from) for one halo phase; None at the ends of the stack.
+    which = 0: the H-phase column (TM Hx / TE Hz) goes UP, the ghost comes from below;
+    which = 1: the E-phase column (TM Ez / TE Ex) goes DOWN, the ghost comes from above."""
+    up = rank + 1 if rank + 1 < world else None
+    down = rank - 1 if rank - 1 >= 0 else None
+    return (up, down) if which == 0 else (down, up)
+
+
+def exchange_halo(engine, comm, which, rank, world, n_px, halo):
+    """pack -> send/recv -> unpack for one phase (engine: halo_pack/halo_unpack)."""
+    send_ptr, recv_ptr = halo
+    send_to, recv_from = halo_peers(which, rank, world)
+    if send_to is not None:
+        engine.halo_pack(which, send_ptr)
+    comm.exchange(send_ptr, recv_ptr, n_px, send_to, recv_from)
+    if recv_from is not None:
+        engine.halo_unpack(which, recv_ptr)
+
+
 class SlabRun:
     """One rank's slab.  `comm` is None for a single slab, else an object with
     exchange(which, send_ptr, recv_ptr, n_complex, send_to, recv_from) and
@@ -89,19 +109,7 @@ class SlabRun:
     def _exchange(self, which):
         if self.comm is None or self.world == 1:
             return
-        send_ptr, recv_ptr = self.halo
-        up, down = self.rank + 1, self.rank - 1
-        if which == 0:      # H-phase result goes up; ghost comes from below
-            send_to = up if up < self.world else None
-            recv_from = down if down >= 0 else None
-        else:               # E-phase result goes down; ghost comes from above
-            send_to = down if down >= 0 else None
-            recv_from = up if up < self.world else None
-        if send_to is not None:
-            self.engine.halo_pack(which, send_ptr)
-        self.comm.exchange(send_ptr, recv_ptr, self.n_px, send_to, recv_from)
-        if recv_from is not None:
-            self.engine.halo_unpack(which, recv_ptr)
+        exchange_halo(self.engine, self.comm, which, self.rank, self.world, self.n_px, self.halo)
 
     def step(self):
         """One update() of the serial solver, slab-wise: H, [halo], E + source,
@@ -171,10 +179,14 @@ class TorchHaloComm:
     def reduce_sum_to_root(self, dev_ptr, n_doubles):
         torch, dist = self.torch, self.dist
         # wrap the engine's U/W block without copying
-        class _Raw:
-            pass
-        raw = _Raw()
-        raw.__cuda_array_interface__ = {"shape": (int(n_doubles),), "typestr": "<f8",
-                                        "data": (int(dev_ptr), False), "version": 3}
-        t = torch.as_tensor(raw, device=self.device)
+        if str(self.device).startswith("cuda"):
+            class _Raw:
+                pass
+            raw = _Raw()
+            raw.__cuda_array_interface__ = {"shape": (int(n_doubles),), "typestr": "<f8",
+                                            "data": (int(dev_ptr), False), "version": 3}
+            t = torch.as_tensor(raw, device=self.device)
+        else:       # host pointer (CPU protocol tests over gloo)
+            buf = (C.c_double * int(n_doubles)).from_address(int(dev_ptr))
+            t = torch.frombuffer(buf, dtype=torch.float64)
         dist.reduce(t, dst=0, op=dist.ReduceOp.SUM)

@@ -101,7 +101,7 @@ class RefSim:
         os.makedirs("MPI_TE_UPML", exist_ok=True)
         if self.model == MODELS["TRACE_IMAGE"]:
             # traceImageModel.c:8,82 opens "traceImage1.txt"; the shipped file is traceImage.txt
-            src = "/root/reference/traceImage.txt"
+            src = os.environ.get("REFLIB_TRACE_IMAGE", "/root/reference/traceImage.txt")
             if os.path.exists(src) and not os.path.exists("traceImage1.txt"):
                 shutil.copy(src, "traceImage1.txt")
         self.L.models_setModel(self.model)
@@ -189,7 +189,8 @@ def eps_map(model, n_px, n_py, x_off, y_off, mode, h_u_nm=10, pml=10):
     try:
         mid = MODELS[model] if isinstance(model, str) else int(model)
         if mid == MODELS["TRACE_IMAGE"]:
-            shutil.copy("/root/reference/traceImage.txt", "traceImage1.txt")
+            shutil.copy(os.environ.get("REFLIB_TRACE_IMAGE", "/root/reference/traceImage.txt"),
+                        "traceImage1.txt")
         L.models_setModel(mid)
         L.field_init(FieldInfo(n_px * h_u_nm, n_py * h_u_nm, h_u_nm, pml, 500, 0, 10))
         L.models_initModel()

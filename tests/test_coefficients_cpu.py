@@ -1,0 +1,42 @@
+"""The twelve 1-D UPML tables the plugin hands to the GPU engine, expanded back to
+the reference's dense N_CELL coefficient arrays and compared bit-exactly with
+arrays recorded from the reference (fdtdTM_upml.c:224-274, fdtdTE_upml.c:361-412)."""
+import numpy as np
+import pytest
+
+from helpers import bit_equal, golden
+from mpifdtd_b200 import binding as B
+
+TM = ["C_JZ", "C_JZHXHY", "C_DZ", "C_DZJZ1", "C_DZJZ0", "C_MX", "C_MXEZ", "C_BX", "C_BXMX1", "C_BXMX0",
+      "C_MY", "C_MYEZ", "C_BY", "C_BYMY1", "C_BYMY0"]
+TE = ["C_JX", "C_JXHZ", "C_DX", "C_DXJX1", "C_DXJX0", "C_JY", "C_JYHZ", "C_DY", "C_DYJY1", "C_DYJY0",
+      "C_MZ", "C_MZEXEY", "C_BZ", "C_BZMZ1", "C_BZMZ0"]
+
+
+@pytest.mark.parametrize("fixture,kind,names", [("mie_tm_upml_88x96", 2, TM), ("mie_te_upml_88x96", 3, TE)])
+def test_dense_coefficients_bit_exact(plugin_lib, fixture, kind, names):
+    g = golden(fixture + ".npz")
+    npx, npy, hu, steps = (int(v) for v in g["meta"][:4])
+    L = plugin_lib
+    L.models_setModel(B.MODELS["MIE_CYLINDER"])
+    L.field_init(B.FieldInfo(npx * hu, npy * hu, hu, 10, 500, 0, steps))
+    for name in names:
+        dense = np.empty((npx, npy))
+        assert L.mpifdtd_upml_dense_coefficient(kind, name.encode(), dense.ctypes.data) == 0, name
+        assert bit_equal(dense, g[name]), name
+
+
+def test_interior_coefficients_are_exactly_one(plugin_lib):
+    """Outside the PML every sigma is 0, so all recurrences reduce to J += curl etc."""
+    L = plugin_lib
+    L.field_init(B.FieldInfo(640, 700, 10, 10, 500, 0, 10))
+    ti, tj = np.empty((6, 64)), np.empty((6, 70))
+    for kind in (2, 3):
+        L.mpifdtd_upml_tables(kind, ti.ctypes.data, tj.ctypes.data)
+        num_den = {2: ([4, 5], [5]), 3: ([2, 3], [3])}[kind]     # NUM_* (by j) and DEN_* (by i) slots
+        for s in range(6):
+            want_i = 2.0 if s in num_den[1] else 1.0
+            want_j = 2.0 if s in num_den[0] else 1.0
+            assert np.all(ti[s, 10:53] == want_i), (kind, "i", s)
+            assert np.all(tj[s, 10:59] == want_j), (kind, "j", s)
+        assert np.any(ti[:, :10] != ti[:, 20:30]) and np.any(tj[:, 60:] != tj[:, 20:30])
