@@ -226,9 +226,17 @@ class Plugin:
     def sync(self):
         check(self.L.b200fdtd_sync(self.engine_handle()), "sync")
 
+    SLOTS = {2: ["Ez", "Jz", "Dz", "Hx", "Mx", "Bx", "Hy", "My", "By"],
+             3: ["Ex", "Jx", "Dx", "Ey", "Jy", "Dy", "Hz", "Mz", "Bz"]}
+
     def field(self, name):
-        ptr = getattr(self.L, self.GETTERS[self.solver][name])()
-        return _as_complex(ptr, self.n_px, self.n_py).copy()
+        """The three public fields come through the reference's getters (borrowed host
+        mirror); the auxiliary J/D/M/B arrays, which the reference keeps file-static,
+        through the engine's slot accessor."""
+        if name in self.GETTERS[self.solver]:
+            ptr = getattr(self.L, self.GETTERS[self.solver][name])()
+            return _as_complex(ptr, self.n_px, self.n_py).copy()
+        return self.any_field(self.SLOTS[self.solver].index(name))
 
     def any_field(self, slot):
         out = np.zeros((self.n_px, self.n_py), dtype=np.complex128)
