@@ -214,6 +214,17 @@ int b200fdtd_ntff_uw_device(b200fdtd_engine *e, void **dev_ptr, uint64_t *n_doub
 /* out[(lambda-lambda_first)*n_angles + ang], the table ntff_outputEnormBin writes */
 int b200fdtd_ntff_spectrum(b200fdtd_engine *e, const b200fdtd_spectrum_args *args, double *out);
 
+/* ---- tuning switches ------------------------------------------------------ */
+enum {
+  B200FDTD_OPT_FUSED = 1,     /* 1: b200fdtd_step uses the one-pass H+E kernel (default for the
+                                 serial TM kind), 0: the two-kernel form                        */
+  B200FDTD_OPT_STORE_H = 2,   /* 1: the fused kernel also writes Hx/Hy every step (264 B/cell);
+                                 0 (default): H is derived from B on demand (getters, NTFF,
+                                 halo) -- Hx == Bx/mu0 holds after every H phase (232 B/cell)    */
+  B200FDTD_OPT_BAND_ROWS = 3  /* rows a warp marches per band in the fused kernel (default 256)  */
+};
+int b200fdtd_set_option(b200fdtd_engine *e, int32_t option, int32_t value);
+
 /* ---- introspection -------------------------------------------------------- */
 /* kernels launched by this engine since creation (bench.py's gpu_launches) */
 int b200fdtd_launch_count(b200fdtd_engine *e, uint64_t *count);

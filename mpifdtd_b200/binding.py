@@ -25,6 +25,7 @@ SOLVERS = dict(TM_2D=0, TE_2D=1, TM_UPML_2D=2, TE_UPML_2D=3,
                MPI_TM_UPML_2D=4, MPI_TE_UPML_2D=5, NS_TM_2D=6, NS_TE_2D=7)
 D_X, D_Y, D_XY = 0, 1, 2
 UPML_TABS = 6
+OPT_FUSED, OPT_STORE_H, OPT_BAND_ROWS = 1, 2, 3
 
 
 class FieldInfo(C.Structure):
@@ -116,6 +117,7 @@ def lib():
     L.b200fdtd_get_field.argtypes = [vp, i32, vp]
     L.b200fdtd_set_field.argtypes = [vp, i32, vp]
     L.b200fdtd_get_field_slab.argtypes = [vp, i32, vp]
+    L.b200fdtd_set_option.argtypes = [vp, i32, i32]
     L.b200fdtd_zero_state.argtypes = [vp]
     L.b200fdtd_ntff_project.argtypes = [vp]
     L.b200fdtd_ntff_get_uw.argtypes = [vp, i32, vp]
@@ -373,6 +375,9 @@ class Engine:
 
     def zero(self):
         check(self.L.b200fdtd_zero_state(self.h), "zero_state")
+
+    def set_option(self, option, value):
+        check(self.L.b200fdtd_set_option(self.h, option, value), "set_option")
 
     def project(self):
         check(self.L.b200fdtd_ntff_project(self.h), "ntff_project")

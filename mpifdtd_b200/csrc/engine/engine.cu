@@ -128,6 +128,9 @@ int b200fdtd_create(const b200fdtd_grid *grid, b200fdtd_engine **out)
   e->pitch = ((B200_JOFF + grid->nj + 1) + 7) / 8 * 8;
   e->plane = (size_t)e->rows * e->pitch;
   e->n_fields = 9;
+  e->use_fused = (grid->kind == B200FDTD_TM_UPML);
+  e->store_h = false;
+  e->h_stale = false;
 
   // update extents clipped to this slab, in layout coordinates
   const int jl = grid->j_lo > grid->j0 ? grid->j_lo : grid->j0;
@@ -162,6 +165,7 @@ int b200fdtd_destroy(b200fdtd_engine *e)
   cudaFree(e->eps[0]); cudaFree(e->eps[1]);
   cudaFree(e->tab_i); cudaFree(e->tab_j);
   free_ntff(e);
+  b200_fused_release(e);
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
   if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
@@ -305,13 +309,40 @@ static int check_ready(b200fdtd_engine *e, const b200fdtd_step_args *a)
 int b200fdtd_phase_h(b200fdtd_engine *e, const b200fdtd_step_args *a)
 {
   int rc = check_ready(e, a); if (rc) return rc;
+  e->h_stale = false;                           // the H phase rewrites every updated H cell
   return b200_launch_upml_h(e, a);
 }
 
 int b200fdtd_phase_e(b200fdtd_engine *e, const b200fdtd_step_args *a)
 {
   int rc = check_ready(e, a); if (rc) return rc;
+  rc = b200_refresh_h(e); if (rc) return rc;
   return b200_launch_upml_e(e, a);
+}
+
+int b200fdtd_set_option(b200fdtd_engine *e, int32_t option, int32_t value)
+{
+  if (!e) return b200_fail(B200FDTD_ERR_ARG, "NULL engine");
+  int rc = select_device(e); if (rc) return rc;
+  switch (option) {
+  case B200FDTD_OPT_FUSED:
+    if (value && e->g.kind != B200FDTD_TM_UPML)
+      return b200_fail(B200FDTD_ERR_ARG, "the fused step serves the serial TM kind only");
+    e->use_fused = value != 0;
+    return B200FDTD_OK;
+  case B200FDTD_OPT_STORE_H:
+    rc = b200_refresh_h(e); if (rc) return rc;
+    e->store_h = value != 0;
+    return B200FDTD_OK;
+  case B200FDTD_OPT_BAND_ROWS:
+    if (value < 1) return b200_fail(B200FDTD_ERR_ARG, "band rows must be >= 1");
+    B200_CUDA(cudaStreamSynchronize(e->stream));
+    b200_fused_release(e);
+    e->fused.band_h = value;
+    return B200FDTD_OK;
+  default:
+    return b200_fail(B200FDTD_ERR_ARG, "unknown option %d", option);
+  }
 }
 
 int b200fdtd_phase_sample(b200fdtd_engine *e, const b200fdtd_step_args *a)
@@ -324,10 +355,13 @@ int b200fdtd_step(b200fdtd_engine *e, const b200fdtd_step_args *a)
 {
   int rc = check_ready(e, a); if (rc) return rc;
   const bool e_first = (e->g.kind == B200FDTD_MPI_TM_UPML || e->g.kind == B200FDTD_MPI_TE_UPML);
-  if (e_first) {              // mpiTM_UPML.c:196-217: E, source, H, NTFF
+  if (e->use_fused && e->g.kind == B200FDTD_TM_UPML) {
+    rc = b200_launch_upml_fused(e, a);          // H and E in one pass
+  } else if (e_first) {              // mpiTM_UPML.c:196-217: E, source, H, NTFF
     rc = b200_launch_upml_e(e, a);
     if (!rc) rc = b200_launch_upml_h(e, a);
   } else {                    // fdtdTM_upml.c:54-66: H, E, source, NTFF
+    e->h_stale = false;
     rc = b200_launch_upml_h(e, a);
     if (!rc) rc = b200_launch_upml_e(e, a);
   }
@@ -347,6 +381,7 @@ int b200fdtd_halo_pack(b200fdtd_engine *e, int32_t which, void *dev_buf)
 {
   if (!e || !dev_buf || which < 0 || which > 1) return b200_fail(B200FDTD_ERR_ARG, "bad halo argument");
   int rc = select_device(e); if (rc) return rc;
+  rc = b200_refresh_h(e); if (rc) return rc;
   return b200_launch_halo(e, which, dev_buf, true);
 }
 
@@ -361,6 +396,7 @@ int b200fdtd_get_field(b200fdtd_engine *e, int32_t slot, double *host)
 {
   if (!e || !host || slot < 0 || slot >= e->n_fields) return b200_fail(B200FDTD_ERR_ARG, "bad field slot %d", slot);
   int rc = select_device(e); if (rc) return rc;
+  rc = b200_refresh_h(e); if (rc) return rc;
   const b200fdtd_grid &g = e->g;
   B200_CUDA(cudaMemcpy2DAsync(host + 2 * (size_t)g.j0, sizeof(double2) * g.n_py,
                               e->field[slot] + (size_t)e->pitch + B200_JOFF, sizeof(double2) * e->pitch,
@@ -373,6 +409,7 @@ int b200fdtd_get_field_slab(b200fdtd_engine *e, int32_t slot, double *host)
 {
   if (!e || !host || slot < 0 || slot >= e->n_fields) return b200_fail(B200FDTD_ERR_ARG, "bad field slot %d", slot);
   int rc = select_device(e); if (rc) return rc;
+  rc = b200_refresh_h(e); if (rc) return rc;
   const b200fdtd_grid &g = e->g;
   B200_CUDA(cudaMemcpy2DAsync(host, sizeof(double2) * g.nj,
                               e->field[slot] + (size_t)e->pitch + B200_JOFF, sizeof(double2) * e->pitch,
@@ -399,6 +436,7 @@ int b200fdtd_zero_state(b200fdtd_engine *e)
   int rc = select_device(e); if (rc) return rc;
   for (int s = 0; s < e->n_fields; s++)
     B200_CUDA(cudaMemsetAsync(e->field[s], 0, e->plane * sizeof(double2), e->stream));
+  e->h_stale = false;
   NtffState &n = e->ntff;
   if (n.ready) {
     B200_CUDA(cudaMemsetAsync(n.hist_e, 0, sizeof(double2) * (size_t)n.n_local * n.max_time, e->stream));

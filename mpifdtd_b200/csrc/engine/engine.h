@@ -38,6 +38,12 @@ struct NtffState {
   int steps_recorded;
 };
 
+struct FusedState {          // side buffers of the fused step (fused_kernels.cu)
+  bool ready;
+  int n_strips, n_bands, band_h;
+  double2 *col_e, *col_h, *row_e, *row_h;
+};
+
 struct b200fdtd_engine {
   b200fdtd_grid g;
   int device;
@@ -52,6 +58,10 @@ struct b200fdtd_engine {
   double *tab_j;            // device [B200FDTD_UPML_TABS][pitch], indexed by in-row offset
   bool have_tabs, have_eps[2];
   NtffState ntff;
+  FusedState fused;
+  bool use_fused;           // b200fdtd_step runs the one-pass kernel (serial TM kind)
+  bool store_h;             // the fused kernel also writes Hx/Hy (264 instead of 232 B/cell)
+  bool h_stale;             // Hx/Hy arrays lag Bx/By (fused step without store_h)
   uint64_t launches;
   uint64_t dev_bytes;
   cudaEvent_t ev0, ev1;
@@ -73,6 +83,12 @@ int b200_fail(int code, const char *fmt, ...);
 int b200_launch_upml_h(b200fdtd_engine *e, const b200fdtd_step_args *a);
 int b200_launch_upml_e(b200fdtd_engine *e, const b200fdtd_step_args *a);
 int b200_launch_halo(b200fdtd_engine *e, int which, void *buf, bool pack);
+
+// launchers (fused_kernels.cu)
+int b200_launch_upml_fused(b200fdtd_engine *e, const b200fdtd_step_args *a);
+int b200_refresh_h(b200fdtd_engine *e);
+int b200_fused_prepare(b200fdtd_engine *e);
+void b200_fused_release(b200fdtd_engine *e);
 
 // launchers (ntff_kernels.cu)
 int b200_launch_ntff_sample(b200fdtd_engine *e, const b200fdtd_step_args *a);

@@ -1,0 +1,309 @@
+// fused_kernels.cu -- one-pass UPML step for sm_100a: H phase and E phase fused.
+//
+// The two-kernel step (upml_kernels.cu) writes Hx/Hy in the H phase and reads them
+// back in the E phase.  Here one kernel does both so H never round-trips through
+// HBM: per cell it reads Ez,Mx,Bx,My,By,Jz,Dz (112 B) + eps (8 B) and writes
+// Mx,Bx,My,By,Jz,Dz,Ez (112 B) [+ Hx,Hy (32 B) when the H arrays are kept]:
+// 232 B (264 B) per cell-update against 296 B for the two-kernel form.
+//
+// Decomposition ("warp-strip marching").  E(i,j) needs the NEW Hy(i-1,j) and
+// Hx(i,j-1) (fdtdTM_upml.c:162), i.e. a one-cell low-side skirt of H, and all state
+// is updated in place -- a tile that recomputed its skirt would race with the tile
+// that owns it.  So:
+//   * a warp owns a strip of 32 columns (lane <-> column j, 512 contiguous bytes per
+//     field per row, 128-bit accesses) and a band of rows, and marches down the band;
+//     Hy(i-1,j) is carried in registers from the previous row, Hx(i,j-1) comes from
+//     the neighbouring lane by shuffle, Ez(i,j+1) likewise, Ez(i+1,j) is the next
+//     row's Ez(i,j) and is loaded exactly once;
+//   * the values a warp would need from ANOTHER warp -- lane 0's Hx(i,j-1), lane 31's
+//     old Ez(i,j+1), the first row's Hy(i-1,j), the last row's old Ez(i+1,j) -- are
+//     produced by a small pre-pass from the OLD state into side buffers before the
+//     main kernel starts (columns at strip edges, rows at band edges).  The pre-pass
+//     evaluates the same expressions, so the values are bit-identical to what the
+//     owning warp computes.
+// After the pre-pass every warp is independent: no barriers, no shared memory, no
+// inter-block ordering, in-place update.  Pre-pass + side-buffer traffic is ~3 % of
+// the step.  Arithmetic is the two-kernel form's, expression for expression
+// (-fmad=false), so both forms produce identical bits (tests/test_gpu_fused.py).
+#include <cstring>
+#include "upml_common.cuh"
+
+namespace {
+
+using namespace upml;
+
+constexpr int kWarpsPerBlock = 4;
+constexpr int kFusedThreads = 32 * kWarpsPerBlock;
+
+struct FusedView {
+  UpmlView u;
+  int n_strips, n_bands, band_h;
+  double2 *col_e, *col_h;       // [n_strips + 1][rows]: old E at a strip's first column,
+                                //   new H at the column just below it
+  double2 *row_e, *row_h;       // [n_bands + 1][pitch]: old E at a band's first row,
+                                //   new H at the row just above it
+};
+
+__device__ __forceinline__ double2 shfl_down1(double2 v)
+{
+  return make_double2(__shfl_down_sync(0xffffffffu, v.x, 1), __shfl_down_sync(0xffffffffu, v.y, 1));
+}
+__device__ __forceinline__ double2 shfl_up1(double2 v)
+{
+  return make_double2(__shfl_up_sync(0xffffffffu, v.x, 1), __shfl_up_sync(0xffffffffu, v.y, 1));
+}
+
+// ---- TM: the H-phase arithmetic for one cell (fdtdTM_upml.c:187-216) ------------
+struct TmH { double2 mx, bx, my, by, hx, hy; };
+
+__device__ __forceinline__ TmH tm_h_cell(const UpmlView &v, int r, int c, double2 ez, double2 ez_j1,
+                                         double2 ez_i1, double2 mx_old, double2 bx_old,
+                                         double2 my_old, double2 by_old)
+{
+  const double c_mx   = v.tj[B200FDTD_TMJ_C_MX * v.pitch + c];
+  const double c_mxez = v.tj[B200FDTD_TMJ_C_MXEZ * v.pitch + c];
+  const double num1   = v.tj[B200FDTD_TMJ_NUM_BYMY1 * v.pitch + c];
+  const double num0   = v.tj[B200FDTD_TMJ_NUM_BYMY0 * v.pitch + c];
+  const double c_bx1  = v.ti[B200FDTD_TMI_C_BXMX1 * v.rows + r];
+  const double c_bx0  = v.ti[B200FDTD_TMI_C_BXMX0 * v.rows + r];
+  const double c_by   = v.ti[B200FDTD_TMI_C_BY * v.rows + r];
+  const double den    = v.ti[B200FDTD_TMI_DEN_BYMY * v.rows + r];
+  TmH o;
+  o.mx = c_mx * mx_old - c_mxez * (ez_j1 - ez);
+  o.bx = (bx_old + c_bx1 * o.mx) - c_bx0 * mx_old;
+  o.my = my_old - ((-ez_i1) + ez);
+  const double c_by1 = num1 / den, c_by0 = num0 / den;
+  o.by = (c_by * by_old + c_by1 * o.my) - c_by0 * my_old;
+  o.hx = o.bx / v.mu0;
+  o.hy = o.by / v.mu0;
+  return o;
+}
+
+// Pre-pass over strip edges: one thread per (strip edge s, row r).
+__global__ void tm_prepass_cols_kernel(const FusedView f)
+{
+  const UpmlView &v = f.u;
+  const int n_rows = v.r_hi - v.r_lo + 1;
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= (long long)(f.n_strips + 1) * n_rows) return;
+  const int s = (int)(t / n_rows);
+  const int r = v.r_lo + (int)(t - (long long)s * n_rows);
+  const int c0 = v.c_lo + 32 * s;                       // first column of strip s
+  const size_t out = (size_t)s * v.rows + r;
+  if (c0 > v.c_hi + 1) return;                          // past the ragged end: nobody reads it
+  const size_t k0 = (size_t)r * v.pitch + c0;
+  const double2 ez0 = v.f[B200FDTD_TM_EZ][k0];
+  f.col_e[out] = ez0;                                   // old Ez(r, c0) for strip s-1's lane 31
+  if (s == 0) {
+    // column c_lo-1 is never updated by this engine: the ring (H == 0), or the low ghost
+    // column a neighbour slab's halo landed in.  The Hx array keeps it either way.
+    f.col_h[out] = v.f[B200FDTD_TM_HX][k0 - 1];
+  } else {
+    const size_t k = k0 - 1;                            // cell (r, c0-1), owned by strip s-1
+    const TmH h = tm_h_cell(v, r, c0 - 1, v.f[B200FDTD_TM_EZ][k], ez0, make_double2(0, 0),
+                            v.f[B200FDTD_TM_MX][k], v.f[B200FDTD_TM_BX][k],
+                            make_double2(0, 0), make_double2(0, 0));
+    f.col_h[out] = h.hx;                                // new Hx(r, c0-1)
+  }
+}
+
+// Pre-pass over band edges: one thread per (band edge b, column c).
+__global__ void tm_prepass_rows_kernel(const FusedView f)
+{
+  const UpmlView &v = f.u;
+  const int n_cols = v.c_hi - v.c_lo + 1;
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= (long long)(f.n_bands + 1) * n_cols) return;
+  const int b = (int)(t / n_cols);
+  const int c = v.c_lo + (int)(t - (long long)b * n_cols);
+  int r0 = v.r_lo + b * f.band_h;                       // first row of band b
+  if (r0 > v.r_hi + 1) r0 = v.r_hi + 1;
+  const size_t out = (size_t)b * v.pitch + c;
+  const size_t k0 = (size_t)r0 * v.pitch + c;
+  const double2 ez0 = v.f[B200FDTD_TM_EZ][k0];
+  f.row_e[out] = ez0;                                   // old Ez(r0, c) for band b-1's last row
+  if (b == 0) {
+    f.row_h[out] = v.f[B200FDTD_TM_HY][k0 - v.pitch];   // row r_lo-1 is never updated (ring / ghost row)
+  } else {
+    const size_t k = k0 - v.pitch;                      // cell (r0-1, c), owned by band b-1
+    const TmH h = tm_h_cell(v, r0 - 1, c, v.f[B200FDTD_TM_EZ][k], make_double2(0, 0), ez0,
+                            make_double2(0, 0), make_double2(0, 0),
+                            v.f[B200FDTD_TM_MY][k], v.f[B200FDTD_TM_BY][k]);
+    f.row_h[out] = h.hy;                                // new Hy(r0-1, c)
+  }
+}
+
+template <bool STORE_H>
+__global__ void __launch_bounds__(kFusedThreads) tm_upml_fused_kernel(const FusedView f)
+{
+  const UpmlView &v = f.u;
+  const int lane = threadIdx.x & 31;
+  const int strip = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (strip >= f.n_strips) return;                      // whole warp leaves together
+  const int band = blockIdx.y;
+  const int c = v.c_lo + 32 * strip + lane;
+  const bool active = c <= v.c_hi;                      // ragged last strip
+  const bool sees_e = c <= v.c_hi + 1;                  // one extra lane feeds Ez(i, j+1)
+  const int r0 = v.r_lo + band * f.band_h;
+  int r1 = r0 + f.band_h;
+  if (r1 > v.r_hi + 1) r1 = v.r_hi + 1;
+
+  double2 *__restrict__ Ez = v.f[B200FDTD_TM_EZ];
+  const double2 zero = make_double2(0, 0);
+
+  // per-lane column coefficients stay in registers for the whole march
+  double c_dz = 1, c_dzjz = 1;
+  if (active) {
+    c_dz = v.tj[B200FDTD_TMJ_C_DZ * v.pitch + c];
+    c_dzjz = v.tj[B200FDTD_TMJ_C_DZJZ * v.pitch + c];
+  }
+
+  size_t k = (size_t)r0 * v.pitch + c;
+  double2 ez_cur = sees_e ? Ez[k] : zero;
+  double2 hy_prev = active ? f.row_h[(size_t)band * v.pitch + c] : zero;
+  const double2 *col_e_next = f.col_e + (size_t)(strip + 1) * v.rows;   // old Ez(r, c0 + 32)
+  const double2 *col_h_mine = f.col_h + (size_t)strip * v.rows;         // new Hx(r, c0 - 1)
+
+  for (int r = r0; r < r1; r++, k += v.pitch) {
+    // ---- loads of row r (and the one new Ez row) --------------------------------
+    double2 ez_next = zero, mx_old = zero, bx_old = zero, my_old = zero, by_old = zero;
+    double2 jz_old = zero, dz_old = zero;
+    double eps = 1.0;
+    if (sees_e)
+      ez_next = (r + 1 < r1) ? Ez[k + v.pitch] : f.row_e[(size_t)(band + 1) * v.pitch + c];
+    if (active) {
+      mx_old = v.f[B200FDTD_TM_MX][k];
+      bx_old = v.f[B200FDTD_TM_BX][k];
+      my_old = v.f[B200FDTD_TM_MY][k];
+      by_old = v.f[B200FDTD_TM_BY][k];
+      jz_old = v.f[B200FDTD_TM_JZ][k];
+      dz_old = v.f[B200FDTD_TM_DZ][k];
+      eps = v.eps0[k];
+    }
+    double2 ez_right = shfl_down1(ez_cur);              // old Ez(r, c+1)
+    if (lane == 31) ez_right = col_e_next[r];
+
+    // ---- H phase ------------------------------------------------------------------
+    TmH h;
+    h.hx = zero; h.hy = zero;
+    if (active) h = tm_h_cell(v, r, c, ez_cur, ez_right, ez_next, mx_old, bx_old, my_old, by_old);
+    double2 hx_left = shfl_up1(h.hx);                   // new Hx(r, c-1)
+    if (lane == 0) hx_left = col_h_mine[r];
+
+    // ---- E phase (fdtdTM_upml.c:161-175) + source (field.c:248-253) -----------------
+    if (active) {
+      const double c_jz  = v.ti[B200FDTD_TMI_C_JZ * v.rows + r];
+      const double c_jzh = v.ti[B200FDTD_TMI_C_JZHXHY * v.rows + r];
+      const double2 jz = c_jz * jz_old + c_jzh * (((h.hy - hy_prev) - h.hx) + hx_left);
+      const double2 dz = (c_dz * dz_old + c_dzjz * jz) - c_dzjz * jz_old;
+      double2 ez = dz / eps;
+      if (v.pulse[0].enabled && eps != 1.0)
+        ez = ez + pulse_term(v.pulse[0], r - 1, v.j_base + c, eps);
+      if ((long long)k == v.point_k)
+        ez = ez + make_double2(v.point_re, v.point_im);
+
+      v.f[B200FDTD_TM_MX][k] = h.mx;
+      v.f[B200FDTD_TM_BX][k] = h.bx;
+      v.f[B200FDTD_TM_MY][k] = h.my;
+      v.f[B200FDTD_TM_BY][k] = h.by;
+      v.f[B200FDTD_TM_JZ][k] = jz;
+      v.f[B200FDTD_TM_DZ][k] = dz;
+      Ez[k] = ez;
+      if (STORE_H) {
+        v.f[B200FDTD_TM_HX][k] = h.hx;
+        v.f[B200FDTD_TM_HY][k] = h.hy;
+      }
+    }
+    hy_prev = h.hy;
+    ez_cur = ez_next;
+  }
+}
+
+// H = B / mu0 over the whole plane: refreshes the H arrays when the fused kernel
+// ran without storing them (the identity Hx == Bx/mu0 holds after every H phase).
+// Only updated cells are touched: the ring / ghost cells of H are not derived state.
+__global__ void derive_h_kernel(const double2 *__restrict__ b, double2 *h, int pitch, int r_lo, int n_rows,
+                                int c_lo, int n_cols, double mu0)
+{
+  const size_t n = (size_t)n_rows * n_cols;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) {
+    const size_t k = (size_t)(r_lo + t / n_cols) * pitch + c_lo + t % n_cols;
+    h[k] = b[k] / mu0;
+  }
+}
+
+}  // namespace
+
+int b200_fused_prepare(b200fdtd_engine *e)
+{
+  FusedState &fs = e->fused;
+  if (fs.ready) return B200FDTD_OK;
+  const int n_cols = e->c_hi - e->c_lo + 1, n_rows = e->r_hi - e->r_lo + 1;
+  if (n_cols < 1 || n_rows < 1) { fs.ready = true; fs.n_strips = fs.n_bands = 0; return B200FDTD_OK; }
+  fs.n_strips = (n_cols + 31) / 32;
+  if (fs.band_h <= 0) fs.band_h = 256;
+  fs.n_bands = (n_rows + fs.band_h - 1) / fs.band_h;
+  const size_t col_n = (size_t)(fs.n_strips + 1) * e->rows, row_n = (size_t)(fs.n_bands + 1) * e->pitch;
+  void **ptrs[4] = { (void **)&fs.col_e, (void **)&fs.col_h, (void **)&fs.row_e, (void **)&fs.row_h };
+  const size_t sizes[4] = { col_n, col_n, row_n, row_n };
+  for (int n = 0; n < 4; n++) {
+    cudaError_t err = cudaMalloc(ptrs[n], sizes[n] * sizeof(double2));
+    if (err != cudaSuccess) return b200_fail(B200FDTD_ERR_NOMEM, "fused side buffers: %s", cudaGetErrorString(err));
+    B200_CUDA(cudaMemsetAsync(*ptrs[n], 0, sizes[n] * sizeof(double2), e->stream));
+    e->dev_bytes += sizes[n] * sizeof(double2);
+  }
+  fs.ready = true;
+  return B200FDTD_OK;
+}
+
+void b200_fused_release(b200fdtd_engine *e)
+{
+  FusedState &fs = e->fused;
+  cudaFree(fs.col_e); cudaFree(fs.col_h); cudaFree(fs.row_e); cudaFree(fs.row_h);
+  const int keep_band = fs.band_h;
+  memset(&fs, 0, sizeof fs);
+  fs.band_h = keep_band;
+}
+
+int b200_launch_upml_fused(b200fdtd_engine *e, const b200fdtd_step_args *a)
+{
+  if (!is_tm(e->g.kind)) return b200_fail(B200FDTD_ERR_STATE, "fused step: TM only in this build");
+  int rc = b200_fused_prepare(e);
+  if (rc) return rc;
+  FusedState &fs = e->fused;
+  if (fs.n_strips == 0) return B200FDTD_OK;
+  FusedView f;
+  f.u = make_view(e, a);
+  f.n_strips = fs.n_strips; f.n_bands = fs.n_bands; f.band_h = fs.band_h;
+  f.col_e = fs.col_e; f.col_h = fs.col_h; f.row_e = fs.row_e; f.row_h = fs.row_h;
+
+  const int n_cols = e->c_hi - e->c_lo + 1, n_rows = e->r_hi - e->r_lo + 1;
+  const long long n_col_items = (long long)(fs.n_strips + 1) * n_rows;
+  const long long n_row_items = (long long)(fs.n_bands + 1) * n_cols;
+  tm_prepass_cols_kernel<<<(unsigned)((n_col_items + 255) / 256), 256, 0, e->stream>>>(f);
+  tm_prepass_rows_kernel<<<(unsigned)((n_row_items + 255) / 256), 256, 0, e->stream>>>(f);
+  dim3 grid((fs.n_strips + kWarpsPerBlock - 1) / kWarpsPerBlock, fs.n_bands);
+  if (e->store_h) tm_upml_fused_kernel<true><<<grid, kFusedThreads, 0, e->stream>>>(f);
+  else            tm_upml_fused_kernel<false><<<grid, kFusedThreads, 0, e->stream>>>(f);
+  e->launches += 3;
+  e->h_stale = !e->store_h;
+  B200_CUDA(cudaGetLastError());
+  return B200FDTD_OK;
+}
+
+// Bring Hx/Hy (TM) up to date from Bx/By if the fused kernel skipped storing them.
+int b200_refresh_h(b200fdtd_engine *e)
+{
+  if (!e->h_stale) return B200FDTD_OK;
+  if (is_tm(e->g.kind)) {
+    const int n_rows = e->r_hi - e->r_lo + 1, n_cols = e->c_hi - e->c_lo + 1;
+    derive_h_kernel<<<1184, 256, 0, e->stream>>>(e->field[B200FDTD_TM_BX], e->field[B200FDTD_TM_HX], e->pitch,
+                                                 e->r_lo, n_rows, e->c_lo, n_cols, e->g.mu0);
+    derive_h_kernel<<<1184, 256, 0, e->stream>>>(e->field[B200FDTD_TM_BY], e->field[B200FDTD_TM_HY], e->pitch,
+                                                 e->r_lo, n_rows, e->c_lo, n_cols, e->g.mu0);
+    e->launches += 2;
+  }
+  e->h_stale = false;
+  B200_CUDA(cudaGetLastError());
+  return B200FDTD_OK;
+}

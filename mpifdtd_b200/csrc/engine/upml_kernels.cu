@@ -15,31 +15,11 @@
 // operation gcc emits for the C99 source (real x complex is component-wise, as
 // gcc lowers it).  One thread updates one cell; a warp covers 32 consecutive j
 // = 512 contiguous bytes per field, every access a 128-bit LDG/STG.
-#include "engine.h"
+#include "upml_common.cuh"
 
 namespace {
 
-constexpr int kBlock = 256;
-
-struct UpmlView {
-  double2 *f[B200FDTD_MAX_FIELDS];
-  const double *eps0, *eps1;
-  const double *ti, *tj;
-  int pitch, rows;
-  int r_lo, c_lo, c_hi;
-  int nbx;                      // thread blocks per row
-  double mu0;
-  b200fdtd_pulse pulse[2];
-  // point source (opt-in): layout offset or -1
-  long long point_k;
-  double point_re, point_im;
-};
-
-__device__ __forceinline__ double2 operator+(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ double2 operator-(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
-__device__ __forceinline__ double2 operator-(double2 a) { return make_double2(-a.x, -a.y); }
-__device__ __forceinline__ double2 operator*(double r, double2 z) { return make_double2(r * z.x, r * z.y); }
-__device__ __forceinline__ double2 operator/(double2 z, double r) { return make_double2(z.x / r, z.y / r); }
+using namespace upml;
 
 // Cell owned by this thread, or false when past the row end.
 __device__ __forceinline__ bool locate(const UpmlView &v, int &r, int &c, size_t &k)
@@ -51,18 +31,6 @@ __device__ __forceinline__ bool locate(const UpmlView &v, int &r, int &c, size_t
   c = v.c_lo + cb * kBlock + (int)threadIdx.x;
   k = (size_t)r * (size_t)v.pitch + (size_t)c;
   return c <= v.c_hi;
-}
-
-// field_scatteredPulse (field.c:243-254) for one cell; i, j are GLOBAL indices.
-__device__ __forceinline__ double2 pulse_term(const b200fdtd_pulse &s, int i, int j, double eps)
-{
-  const double r = ((i + s.gap_x) * s.cos_per_c + (j + s.gap_y) * s.sin_per_c) - s.time_minus_t0;
-  const double q = r / s.beam_width;
-  const double gauss = exp(-(q * q));
-  const double amp = s.dot * gauss * (1.0 / eps - 1);
-  double sn, cs;
-  sincos(r * s.omega, &sn, &cs);
-  return make_double2(amp * cs, amp * sn);
 }
 
 // ------------------------------------------------------------------ TM -----
@@ -106,7 +74,7 @@ __global__ void __launch_bounds__(kBlock) tm_upml_h_kernel(const UpmlView v)
   v.f[B200FDTD_TM_HY][k] = by / v.mu0;        // fdtdTM_upml.c:216
 }
 
-__global__ void __launch_bounds__(kBlock) tm_upml_e_kernel(const UpmlView v, const int j_base)
+__global__ void __launch_bounds__(kBlock) tm_upml_e_kernel(const UpmlView v)
 {
   int r, c; size_t k;
   if (!locate(v, r, c, k)) return;
@@ -132,7 +100,7 @@ __global__ void __launch_bounds__(kBlock) tm_upml_e_kernel(const UpmlView v, con
   double2 ez = dz / eps;                      // fdtdTM_upml.c:175
 
   if (v.pulse[0].enabled && eps != 1.0)       // field.c:248
-    ez = ez + pulse_term(v.pulse[0], r - 1, j_base + c, eps);
+    ez = ez + pulse_term(v.pulse[0], r - 1, v.j_base + c, eps);
   if ((long long)k == v.point_k)
     ez = ez + make_double2(v.point_re, v.point_im);
 
@@ -171,7 +139,7 @@ __global__ void __launch_bounds__(kBlock) te_upml_h_kernel(const UpmlView v)
   v.f[B200FDTD_TE_HZ][k] = bz / v.mu0;        // fdtdTE_upml.c:312
 }
 
-__global__ void __launch_bounds__(kBlock) te_upml_e_kernel(const UpmlView v, const int j_base)
+__global__ void __launch_bounds__(kBlock) te_upml_e_kernel(const UpmlView v)
 {
   int r, c; size_t k;
   if (!locate(v, r, c, k)) return;
@@ -205,7 +173,7 @@ __global__ void __launch_bounds__(kBlock) te_upml_e_kernel(const UpmlView v, con
 
   double2 ex = dx / eps_x;                    // fdtdTE_upml.c:283
   double2 ey = dy / eps_y;                    // fdtdTE_upml.c:289
-  const int i = r - 1, j = j_base + c;
+  const int i = r - 1, j = v.j_base + c;
   if (v.pulse[0].enabled && eps_x != 1.0)     // fdtdTE_upml.c:186-187
     ex = ex + pulse_term(v.pulse[0], i, j, eps_x);
   if (v.pulse[1].enabled && eps_y != 1.0)     // fdtdTE_upml.c:188-189
@@ -231,36 +199,6 @@ __global__ void halo_column_kernel(double2 *field, double2 *buf, int pitch, int 
   else      field[k] = buf[i];
 }
 
-UpmlView make_view(const b200fdtd_engine *e, const b200fdtd_step_args *a)
-{
-  UpmlView v;
-  for (int s = 0; s < B200FDTD_MAX_FIELDS; s++) v.f[s] = e->field[s];
-  v.eps0 = e->eps[0];
-  v.eps1 = e->eps[1];
-  v.ti = e->tab_i;
-  v.tj = e->tab_j;
-  v.pitch = e->pitch;
-  v.rows = e->rows;
-  v.r_lo = e->r_lo;
-  v.c_lo = e->c_lo;
-  v.c_hi = e->c_hi;
-  v.nbx = (e->c_hi - e->c_lo + 1 + kBlock - 1) / kBlock;
-  v.mu0 = e->g.mu0;
-  v.pulse[0] = a->pulse[0];
-  v.pulse[1] = a->pulse[1];
-  v.point_k = -1;
-  v.point_re = a->point.re;
-  v.point_im = a->point.im;
-  if (a->point.enabled) {
-    const int pj = a->point.j - e->g.j0;
-    if (pj >= 0 && pj < e->g.nj && a->point.i >= 0 && a->point.i < e->g.n_px)
-      v.point_k = (long long)(a->point.i + 1) * e->pitch + pj + B200_JOFF;
-  }
-  return v;
-}
-
-bool is_tm(int kind) { return kind == B200FDTD_TM_UPML || kind == B200FDTD_MPI_TM_UPML; }
-
 }  // namespace
 
 int b200_launch_upml_h(b200fdtd_engine *e, const b200fdtd_step_args *a)
@@ -280,9 +218,8 @@ int b200_launch_upml_e(b200fdtd_engine *e, const b200fdtd_step_args *a)
   if (e->r_hi < e->r_lo || e->c_hi < e->c_lo) return B200FDTD_OK;
   const UpmlView v = make_view(e, a);
   const long long nblk = (long long)v.nbx * (e->r_hi - e->r_lo + 1);
-  const int j_base = e->g.j0 - B200_JOFF;     // global j = j_base + c
-  if (is_tm(e->g.kind)) tm_upml_e_kernel<<<(unsigned)nblk, kBlock, 0, e->stream>>>(v, j_base);
-  else                  te_upml_e_kernel<<<(unsigned)nblk, kBlock, 0, e->stream>>>(v, j_base);
+  if (is_tm(e->g.kind)) tm_upml_e_kernel<<<(unsigned)nblk, kBlock, 0, e->stream>>>(v);
+  else                  te_upml_e_kernel<<<(unsigned)nblk, kBlock, 0, e->stream>>>(v);
   e->launches++;
   B200_CUDA(cudaGetLastError());
   return B200FDTD_OK;

@@ -1,0 +1,91 @@
+"""The one-pass (fused H+E) TM step against the two-kernel step: identical bits.
+
+Both forms evaluate the same expressions in the same order (-fmad=false), so after any
+number of steps from any state every one of the nine arrays, and the NTFF history, must
+agree bit for bit -- including ragged strips (columns not a multiple of 32), bands of any
+height, strips narrower than a warp, and with/without storing Hx/Hy."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from helpers import bit_equal
+from mpifdtd_b200 import binding as B
+
+pytestmark = pytest.mark.gpu
+
+
+def make_engine(L, npx, npy, steps, eps, fused, store_h=0, band=None, j0=0, nj=None):
+    eng = B.Engine(2, npx, npy, 10, j0=j0, nj=nj)
+    ti, tj = np.empty((6, npx)), np.empty((6, npy))
+    L.mpifdtd_upml_tables(2, ti.ctypes.data, tj.ctypes.data)
+    eng.set_tables(ti, tj)
+    eng.set_eps(0, eps)
+    box = L.field_getNTFFInfo()
+    n_local = L.mpifdtd_ntff_local_count(C.byref(box), eng.j0, eng.nj)
+    ptr = L.mpifdtd_ntff_time_shift(C.byref(box), 360, 0.0, eng.j0, eng.nj)
+    plan = B.NtffPlan(box.top, box.bottom, box.left, box.right,
+                      L.mpifdtd_ntff_point_count(C.byref(box)), n_local, steps, steps, 360,
+                      box.arraySize, ptr)
+    B.check(L.b200fdtd_set_ntff_plan(eng.h, C.byref(plan)), "plan")
+    L.free(ptr)
+    eng.n_bins = steps
+    eng.set_option(B.OPT_FUSED, fused)
+    if fused:
+        eng.set_option(B.OPT_STORE_H, store_h)
+        if band:
+            eng.set_option(B.OPT_BAND_ROWS, band)
+    return eng
+
+
+@pytest.mark.parametrize("npx,npy,band", [(70, 96, 256), (45, 47, 7), (131, 200, 64), (300, 41, 33),
+                                          (64, 1030, 1), (257, 66, 256)])
+def test_fused_step_is_bit_identical_to_two_kernel_step(plugin_lib, npx, npy, band):
+    L = plugin_lib
+    steps = 6
+    L.models_setModel(B.MODELS["NO_MODEL"])
+    L.field_init(B.FieldInfo(npx * 10, npy * 10, 10, 10, 500, 30, steps))
+    rng = np.random.default_rng(npx * 1000 + npy)
+    eps = np.where(rng.random((npx, npy)) < 0.5, 1.0, 1.0 + 2.0 * rng.random((npx, npy)))
+    state = [rng.standard_normal((npx, npy)) + 1j * rng.standard_normal((npx, npy)) for _ in range(9)]
+    # H arrays must satisfy the solver's invariant Hx == Bx/mu0 (true after any H phase)
+    mu0 = B.MU_0_S
+    state[3] = (state[5].real / mu0) + 1j * (state[5].imag / mu0)
+    state[6] = (state[8].real / mu0) + 1j * (state[8].imag / mu0)
+    engines = [make_engine(L, npx, npy, steps, eps, 0),
+               make_engine(L, npx, npy, steps, eps, 1, store_h=0, band=band),
+               make_engine(L, npx, npy, steps, eps, 1, store_h=1, band=band)]
+    for eng in engines:
+        for slot in range(9):
+            eng.set_field(slot, state[slot])
+    args = B.StepArgs()
+    L.field_reset()
+    for _ in range(steps):
+        L.mpifdtd_upml_step_args(2, 1, C.byref(args))       # pulse + point source both on
+        for eng in engines:
+            eng.step(args)
+        L.field_nextStep()
+    ref = [engines[0].get_field(s) for s in range(9)]
+    assert np.abs(ref[0]).max() > 0 and np.all(np.isfinite(ref[0].view(np.float64)))
+    for which, eng in enumerate(engines[1:], 1):
+        for slot in range(9):
+            got = eng.get_field(slot)
+            assert bit_equal(got.view(np.float64), ref[slot].view(np.float64)), (which, slot)
+    for eng in engines:
+        eng.project()
+    for slot in range(3):
+        want = engines[0].uw(slot)
+        for eng in engines[1:]:
+            assert bit_equal(eng.uw(slot).view(np.float64), want.view(np.float64)), slot
+    assert engines[1].launches() > 0
+    for eng in engines:
+        eng.close()
+
+
+def test_fused_is_the_default_for_the_serial_tm_solver(plugin_lib, in_tmp_cwd):
+    gpu = B.Plugin("MIE_CYLINDER", "TM_UPML_2D", 96, steps=10, h_u_nm=20)
+    n0 = gpu.launches()
+    gpu.step(1)
+    # fused step = 2 pre-pass launches + 1 main kernel + 1 NTFF sample
+    assert gpu.launches() - n0 == 4
+    gpu.finish()
