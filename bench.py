@@ -19,9 +19,11 @@ needed between iterations.
              the timed region: eps map H2D from pinned memory, K x update(), Ez
              D2H into the pinned mirror the getter hands out.
   roofline   H-phase kernel alone (the dominant kernel): algorithmic bytes
-             (176 B/cell: reads Ez,Mx,Bx,My,By, writes Mx,Bx,My,By,Hx,Hy) over its
-             mean duration, against MEASURED_PEAKS.json hbm_gbs.  `step` carries
-             the contract figure of SURVEY 8(d): 264 B/cell-update x rate.
+             (144 B/cell: reads Ez,Mx,Bx,My,By, writes Mx,Bx,My,By; Hx/Hy are not stored,
+             the E phase forms them as B/mu0) over its mean duration, against
+             MEASURED_PEAKS.json hbm_gbs.  `e_phase` is the other kernel (120 B/cell);
+             `step` carries the contract figure of SURVEY 8(d): 264 B/cell-update x rate,
+             which is exactly what the two kernels move.
   cpu_baseline / --impl reference
              the UNMODIFIED reference (oracle/_ref/libref.so, built from
              /root/reference) on the host cores, one serial solver instance per
@@ -40,9 +42,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, HERE)
 
 N_PER_GPU = 16384
-BYTES_STEP_TM = 264          # fused-step algorithmic bytes per cell-update
-BYTES_H_TM = 176             # H-phase kernel: 5 reads + 6 writes of 16 B
-BYTES_E_TM = 120             # E-phase kernel: 4 reads + 3 writes of 16 B + eps 8 B
+BYTES_STEP_TM = 264          # SURVEY 8(d) contract figure = what the step moves: 144 + 120
+BYTES_H_TM = 144             # H-phase kernel: reads Ez,Mx,Bx,My,By (80) + writes Mx,Bx,My,By (64)
+BYTES_E_TM = 120             # E-phase kernel: reads Bx,By,Jz,Dz (64) + eps (8) + writes Jz,Dz,Ez (48)
 FALLBACK_HBM_GBS = 6650.0    # B200_PROFILING.md fallback
 
 
@@ -335,11 +337,11 @@ def gpu_arm(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": workload_config(world, n=args.n),
-            "roofline": {"bound": "hbm", "kernel": "tm_upml_h_kernel", "achieved": ach_h,
+            "roofline": {"bound": "hbm", "kernel": "tm_upml_h_kernel<STORE_H=false>", "achieved": ach_h,
                          "peak": peak, "unit": "GB/s", "frac": ach_h / peak, "peak_source": peak_kind,
                          "traffic": None, "ms_per_launch": ms_h,
                          "algorithmic_bytes_per_cell": BYTES_H_TM,
-                         "e_phase": {"kernel": "tm_upml_e_kernel", "achieved": ach_e,
+                         "e_phase": {"kernel": "tm_upml_e_kernel<FROM_B=true>", "achieved": ach_e,
                                      "frac": ach_e / peak, "ms_per_launch": ms_e,
                                      "algorithmic_bytes_per_cell": BYTES_E_TM},
                          "step": {"algorithmic_bytes_per_cell_update": BYTES_STEP_TM,

@@ -221,9 +221,16 @@ enum {
   B200FDTD_OPT_STORE_H = 2,   /* 1: the fused kernel also writes Hx/Hy every step (264 B/cell);
                                  0 (default): H is derived from B on demand (getters, NTFF,
                                  halo) -- Hx == Bx/mu0 holds after every H phase (232 B/cell)    */
-  B200FDTD_OPT_BAND_ROWS = 3  /* rows a warp marches per band in the fused kernel (default 256)  */
+  B200FDTD_OPT_BAND_ROWS = 3, /* rows a warp marches per band in the fused kernel (default 256)  */
+  B200FDTD_OPT_FUSED_SHAPE = 4 /* launch shape of the fused kernel (tuning; see fused_kernels.cu)  */
 };
 int b200fdtd_set_option(b200fdtd_engine *e, int32_t option, int32_t value);
+
+/* Device self-test: the kernels replace `x / d` (d loop-invariant, e.g. MU_0_S) by a
+ * reciprocal-multiply with an FMA correction that is claimed to be the identical,
+ * correctly rounded quotient.  Counts disagreements with IEEE division over `samples`
+ * pseudo-random operands (raw bit patterns and field-like magnitudes); must be 0. */
+int b200fdtd_selftest_division(double divisor, uint64_t samples, uint64_t *mismatches);
 
 /* ---- introspection -------------------------------------------------------- */
 /* kernels launched by this engine since creation (bench.py's gpu_launches) */

@@ -118,6 +118,7 @@ def lib():
     L.b200fdtd_set_field.argtypes = [vp, i32, vp]
     L.b200fdtd_get_field_slab.argtypes = [vp, i32, vp]
     L.b200fdtd_set_option.argtypes = [vp, i32, i32]
+    L.b200fdtd_selftest_division.argtypes = [dbl, C.c_uint64, C.POINTER(C.c_uint64)]
     L.b200fdtd_zero_state.argtypes = [vp]
     L.b200fdtd_ntff_project.argtypes = [vp]
     L.b200fdtd_ntff_get_uw.argtypes = [vp, i32, vp]

@@ -128,9 +128,13 @@ int b200fdtd_create(const b200fdtd_grid *grid, b200fdtd_engine **out)
   e->pitch = ((B200_JOFF + grid->nj + 1) + 7) / 8 * 8;
   e->plane = (size_t)e->rows * e->pitch;
   e->n_fields = 9;
-  e->use_fused = (grid->kind == B200FDTD_TM_UPML);
+  e->use_fused = false;     // the marching one-pass kernel is opt-in (B200FDTD_OPT_FUSED)
   e->store_h = false;
   e->h_stale = false;
+  if (const char *v = getenv("B200FDTD_FUSED")) e->use_fused = atoi(v) != 0 && grid->kind == B200FDTD_TM_UPML;
+  if (const char *v = getenv("B200FDTD_STORE_H")) e->store_h = atoi(v) != 0;
+  if (const char *v = getenv("B200FDTD_FUSED_SHAPE")) e->fused_variant = atoi(v);
+  if (const char *v = getenv("B200FDTD_BAND_ROWS")) e->fused.band_h = atoi(v);
 
   // update extents clipped to this slab, in layout coordinates
   const int jl = grid->j_lo > grid->j0 ? grid->j_lo : grid->j0;
@@ -309,15 +313,13 @@ static int check_ready(b200fdtd_engine *e, const b200fdtd_step_args *a)
 int b200fdtd_phase_h(b200fdtd_engine *e, const b200fdtd_step_args *a)
 {
   int rc = check_ready(e, a); if (rc) return rc;
-  e->h_stale = false;                           // the H phase rewrites every updated H cell
-  return b200_launch_upml_h(e, a);
+  return b200_launch_upml_h(e, a);              // sets h_stale = !store_h
 }
 
 int b200fdtd_phase_e(b200fdtd_engine *e, const b200fdtd_step_args *a)
 {
   int rc = check_ready(e, a); if (rc) return rc;
-  rc = b200_refresh_h(e); if (rc) return rc;
-  return b200_launch_upml_e(e, a);
+  return b200_launch_upml_e(e, a);              // reads B/mu0 when the H arrays are stale
 }
 
 int b200fdtd_set_option(b200fdtd_engine *e, int32_t option, int32_t value)
@@ -340,6 +342,9 @@ int b200fdtd_set_option(b200fdtd_engine *e, int32_t option, int32_t value)
     b200_fused_release(e);
     e->fused.band_h = value;
     return B200FDTD_OK;
+  case B200FDTD_OPT_FUSED_SHAPE:
+    e->fused_variant = value;
+    return B200FDTD_OK;
   default:
     return b200_fail(B200FDTD_ERR_ARG, "unknown option %d", option);
   }
@@ -361,7 +366,6 @@ int b200fdtd_step(b200fdtd_engine *e, const b200fdtd_step_args *a)
     rc = b200_launch_upml_e(e, a);
     if (!rc) rc = b200_launch_upml_h(e, a);
   } else {                    // fdtdTM_upml.c:54-66: H, E, source, NTFF
-    e->h_stale = false;
     rc = b200_launch_upml_h(e, a);
     if (!rc) rc = b200_launch_upml_e(e, a);
   }
@@ -381,7 +385,6 @@ int b200fdtd_halo_pack(b200fdtd_engine *e, int32_t which, void *dev_buf)
 {
   if (!e || !dev_buf || which < 0 || which > 1) return b200_fail(B200FDTD_ERR_ARG, "bad halo argument");
   int rc = select_device(e); if (rc) return rc;
-  rc = b200_refresh_h(e); if (rc) return rc;
   return b200_launch_halo(e, which, dev_buf, true);
 }
 
@@ -480,6 +483,15 @@ int b200fdtd_ntff_spectrum(b200fdtd_engine *e, const b200fdtd_spectrum_args *arg
     return b200_fail(B200FDTD_ERR_ARG, "NULL argument");
   int rc = select_device(e); if (rc) return rc;
   return b200_run_ntff_spectrum(e, args, out);
+}
+
+int b200fdtd_selftest_division(double divisor, uint64_t samples, uint64_t *mismatches)
+{
+  if (!mismatches || !(divisor > 0.0)) return b200_fail(B200FDTD_ERR_ARG, "bad argument");
+  unsigned long long bad = 0;
+  int rc = b200_selftest_division(divisor, samples, &bad);
+  *mismatches = bad;
+  return rc;
 }
 
 int b200fdtd_launch_count(b200fdtd_engine *e, uint64_t *count)

@@ -62,6 +62,7 @@ struct b200fdtd_engine {
   bool use_fused;           // b200fdtd_step runs the one-pass kernel (serial TM kind)
   bool store_h;             // the fused kernel also writes Hx/Hy (264 instead of 232 B/cell)
   bool h_stale;             // Hx/Hy arrays lag Bx/By (fused step without store_h)
+  int fused_variant;        // launch shape of the fused kernel (tuning)
   uint64_t launches;
   uint64_t dev_bytes;
   cudaEvent_t ev0, ev1;
@@ -83,6 +84,7 @@ int b200_fail(int code, const char *fmt, ...);
 int b200_launch_upml_h(b200fdtd_engine *e, const b200fdtd_step_args *a);
 int b200_launch_upml_e(b200fdtd_engine *e, const b200fdtd_step_args *a);
 int b200_launch_halo(b200fdtd_engine *e, int which, void *buf, bool pack);
+int b200_selftest_division(double divisor, unsigned long long samples, unsigned long long *mismatches);
 
 // launchers (fused_kernels.cu)
 int b200_launch_upml_fused(b200fdtd_engine *e, const b200fdtd_step_args *a);

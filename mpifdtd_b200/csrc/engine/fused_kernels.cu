@@ -32,8 +32,7 @@ namespace {
 
 using namespace upml;
 
-constexpr int kWarpsPerBlock = 4;
-constexpr int kFusedThreads = 32 * kWarpsPerBlock;
+constexpr int kMaxWarpsPerBlock = 16;
 
 struct FusedView {
   UpmlView u;
@@ -55,27 +54,40 @@ __device__ __forceinline__ double2 shfl_up1(double2 v)
 
 // ---- TM: the H-phase arithmetic for one cell (fdtdTM_upml.c:187-216) ------------
 struct TmH { double2 mx, bx, my, by, hx, hy; };
+struct TmColCoef { double c_mx, c_mxez, num1, num0; };          // by j (this lane's column)
+struct TmRowCoef { double c_bx1, c_bx0, c_by, den; };           // by i (this row)
 
-__device__ __forceinline__ TmH tm_h_cell(const UpmlView &v, int r, int c, double2 ez, double2 ez_j1,
-                                         double2 ez_i1, double2 mx_old, double2 bx_old,
-                                         double2 my_old, double2 by_old)
+__device__ __forceinline__ TmColCoef tm_col_coef(const UpmlView &v, int c)
 {
-  const double c_mx   = v.tj[B200FDTD_TMJ_C_MX * v.pitch + c];
-  const double c_mxez = v.tj[B200FDTD_TMJ_C_MXEZ * v.pitch + c];
-  const double num1   = v.tj[B200FDTD_TMJ_NUM_BYMY1 * v.pitch + c];
-  const double num0   = v.tj[B200FDTD_TMJ_NUM_BYMY0 * v.pitch + c];
-  const double c_bx1  = v.ti[B200FDTD_TMI_C_BXMX1 * v.rows + r];
-  const double c_bx0  = v.ti[B200FDTD_TMI_C_BXMX0 * v.rows + r];
-  const double c_by   = v.ti[B200FDTD_TMI_C_BY * v.rows + r];
-  const double den    = v.ti[B200FDTD_TMI_DEN_BYMY * v.rows + r];
+  TmColCoef k;
+  k.c_mx   = v.tj[B200FDTD_TMJ_C_MX * v.pitch + c];
+  k.c_mxez = v.tj[B200FDTD_TMJ_C_MXEZ * v.pitch + c];
+  k.num1   = v.tj[B200FDTD_TMJ_NUM_BYMY1 * v.pitch + c];
+  k.num0   = v.tj[B200FDTD_TMJ_NUM_BYMY0 * v.pitch + c];
+  return k;
+}
+__device__ __forceinline__ TmRowCoef tm_row_coef(const UpmlView &v, int r)
+{
+  TmRowCoef k;
+  k.c_bx1 = v.ti[B200FDTD_TMI_C_BXMX1 * v.rows + r];
+  k.c_bx0 = v.ti[B200FDTD_TMI_C_BXMX0 * v.rows + r];
+  k.c_by  = v.ti[B200FDTD_TMI_C_BY * v.rows + r];
+  k.den   = v.ti[B200FDTD_TMI_DEN_BYMY * v.rows + r];
+  return k;
+}
+
+__device__ __forceinline__ TmH tm_h_cell(const UpmlView &v, const TmColCoef &cc, const TmRowCoef &rc,
+                                         double2 ez, double2 ez_j1, double2 ez_i1, double2 mx_old,
+                                         double2 bx_old, double2 my_old, double2 by_old)
+{
   TmH o;
-  o.mx = c_mx * mx_old - c_mxez * (ez_j1 - ez);
-  o.bx = (bx_old + c_bx1 * o.mx) - c_bx0 * mx_old;
+  o.mx = cc.c_mx * mx_old - cc.c_mxez * (ez_j1 - ez);
+  o.bx = (bx_old + rc.c_bx1 * o.mx) - rc.c_bx0 * mx_old;
   o.my = my_old - ((-ez_i1) + ez);
-  const double c_by1 = num1 / den, c_by0 = num0 / den;
-  o.by = (c_by * by_old + c_by1 * o.my) - c_by0 * my_old;
-  o.hx = o.bx / v.mu0;
-  o.hy = o.by / v.mu0;
+  const double c_by1 = quotient_or_one(cc.num1, rc.den), c_by0 = quotient_or_one(cc.num0, rc.den);
+  o.by = (rc.c_by * by_old + c_by1 * o.my) - c_by0 * my_old;
+  o.hx = div_const(o.bx, v.mu0);
+  o.hy = div_const(o.by, v.mu0);
   return o;
 }
 
@@ -100,9 +112,9 @@ __global__ void tm_prepass_cols_kernel(const FusedView f)
     f.col_h[out] = v.f[B200FDTD_TM_HX][k0 - 1];
   } else {
     const size_t k = k0 - 1;                            // cell (r, c0-1), owned by strip s-1
-    const TmH h = tm_h_cell(v, r, c0 - 1, v.f[B200FDTD_TM_EZ][k], ez0, make_double2(0, 0),
-                            v.f[B200FDTD_TM_MX][k], v.f[B200FDTD_TM_BX][k],
-                            make_double2(0, 0), make_double2(0, 0));
+    const double2 zero = make_double2(0, 0);
+    const TmH h = tm_h_cell(v, tm_col_coef(v, c0 - 1), tm_row_coef(v, r), v.f[B200FDTD_TM_EZ][k], ez0,
+                            zero, v.f[B200FDTD_TM_MX][k], v.f[B200FDTD_TM_BX][k], zero, zero);
     f.col_h[out] = h.hx;                                // new Hx(r, c0-1)
   }
 }
@@ -126,79 +138,105 @@ __global__ void tm_prepass_rows_kernel(const FusedView f)
     f.row_h[out] = v.f[B200FDTD_TM_HY][k0 - v.pitch];   // row r_lo-1 is never updated (ring / ghost row)
   } else {
     const size_t k = k0 - v.pitch;                      // cell (r0-1, c), owned by band b-1
-    const TmH h = tm_h_cell(v, r0 - 1, c, v.f[B200FDTD_TM_EZ][k], make_double2(0, 0), ez0,
-                            make_double2(0, 0), make_double2(0, 0),
-                            v.f[B200FDTD_TM_MY][k], v.f[B200FDTD_TM_BY][k]);
+    const double2 zero = make_double2(0, 0);
+    const TmH h = tm_h_cell(v, tm_col_coef(v, c), tm_row_coef(v, r0 - 1), v.f[B200FDTD_TM_EZ][k], zero, ez0,
+                            zero, zero, v.f[B200FDTD_TM_MY][k], v.f[B200FDTD_TM_BY][k]);
     f.row_h[out] = h.hy;                                // new Hy(r0-1, c)
   }
 }
 
-template <bool STORE_H>
-__global__ void __launch_bounds__(kFusedThreads) tm_upml_fused_kernel(const FusedView f)
+// Operands of one row of one lane, kept in registers one row ahead of the arithmetic so
+// that two rows of loads (16 x 512 B per warp) are in flight while a row is computed.
+struct TmRowIn {
+  double2 ez_below;          // old Ez(r+1, c)
+  double2 mx, bx, my, by, jz, dz;
+  double eps;
+  double2 edge_e, edge_h;    // lane 31: old Ez(r, c0+32); lane 0: new Hx(r, c0-1)
+};
+
+template <bool STORE_H, int WARPS, bool LOCKSTEP>
+__global__ void __launch_bounds__(32 * WARPS) tm_upml_fused_kernel(const FusedView f)
 {
   const UpmlView &v = f.u;
   const int lane = threadIdx.x & 31;
-  const int strip = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-  if (strip >= f.n_strips) return;                      // whole warp leaves together
+  const int strip = blockIdx.x * WARPS + (threadIdx.x >> 5);
+  const bool idle = strip >= f.n_strips;                // whole warp idles together
+  if (idle && !LOCKSTEP) return;
   const int band = blockIdx.y;
   const int c = v.c_lo + 32 * strip + lane;
-  const bool active = c <= v.c_hi;                      // ragged last strip
-  const bool sees_e = c <= v.c_hi + 1;                  // one extra lane feeds Ez(i, j+1)
+  const bool active = !idle && c <= v.c_hi;             // ragged last strip
+  const bool sees_e = !idle && c <= v.c_hi + 1;         // one extra lane feeds Ez(i, j+1)
   const int r0 = v.r_lo + band * f.band_h;
   int r1 = r0 + f.band_h;
   if (r1 > v.r_hi + 1) r1 = v.r_hi + 1;
 
-  double2 *__restrict__ Ez = v.f[B200FDTD_TM_EZ];
+  double2 *Ez = v.f[B200FDTD_TM_EZ];
   const double2 zero = make_double2(0, 0);
+  const double2 *col_e_next = f.col_e + (size_t)(strip + 1) * v.rows;   // old Ez(r, c0 + 32)
+  const double2 *col_h_mine = f.col_h + (size_t)strip * v.rows;         // new Hx(r, c0 - 1)
+  const double2 *row_e_next = f.row_e + (size_t)(band + 1) * v.pitch;   // old Ez(r1, c)
 
   // per-lane column coefficients stay in registers for the whole march
+  TmColCoef cc = { 1.0, 1.0, 2.0, 2.0 };
   double c_dz = 1, c_dzjz = 1;
   if (active) {
+    cc = tm_col_coef(v, c);
     c_dz = v.tj[B200FDTD_TMJ_C_DZ * v.pitch + c];
     c_dzjz = v.tj[B200FDTD_TMJ_C_DZJZ * v.pitch + c];
   }
 
+  auto load_row = [&](int r, size_t k) {
+    TmRowIn in;
+    in.ez_below = zero; in.mx = in.bx = in.my = in.by = in.jz = in.dz = zero;
+    in.eps = 1.0; in.edge_e = in.edge_h = zero;
+    if (sees_e) in.ez_below = (r + 1 < r1) ? Ez[k + v.pitch] : row_e_next[c];
+    if (active) {
+      in.mx = v.f[B200FDTD_TM_MX][k];
+      in.bx = v.f[B200FDTD_TM_BX][k];
+      in.my = v.f[B200FDTD_TM_MY][k];
+      in.by = v.f[B200FDTD_TM_BY][k];
+      in.jz = v.f[B200FDTD_TM_JZ][k];
+      in.dz = v.f[B200FDTD_TM_DZ][k];
+      in.eps = v.eps0[k];
+    }
+    if (lane == 31 && !idle) in.edge_e = col_e_next[r];
+    if (lane == 0 && !idle) in.edge_h = col_h_mine[r];
+    return in;
+  };
+
   size_t k = (size_t)r0 * v.pitch + c;
   double2 ez_cur = sees_e ? Ez[k] : zero;
   double2 hy_prev = active ? f.row_h[(size_t)band * v.pitch + c] : zero;
-  const double2 *col_e_next = f.col_e + (size_t)(strip + 1) * v.rows;   // old Ez(r, c0 + 32)
-  const double2 *col_h_mine = f.col_h + (size_t)strip * v.rows;         // new Hx(r, c0 - 1)
+  TmRowIn cur = load_row(r0, k);
 
   for (int r = r0; r < r1; r++, k += v.pitch) {
-    // ---- loads of row r (and the one new Ez row) --------------------------------
-    double2 ez_next = zero, mx_old = zero, bx_old = zero, my_old = zero, by_old = zero;
-    double2 jz_old = zero, dz_old = zero;
-    double eps = 1.0;
-    if (sees_e)
-      ez_next = (r + 1 < r1) ? Ez[k + v.pitch] : f.row_e[(size_t)(band + 1) * v.pitch + c];
-    if (active) {
-      mx_old = v.f[B200FDTD_TM_MX][k];
-      bx_old = v.f[B200FDTD_TM_BX][k];
-      my_old = v.f[B200FDTD_TM_MY][k];
-      by_old = v.f[B200FDTD_TM_BY][k];
-      jz_old = v.f[B200FDTD_TM_JZ][k];
-      dz_old = v.f[B200FDTD_TM_DZ][k];
-      eps = v.eps0[k];
-    }
+    // keep the warps of a block on the same row so each field is touched in one
+    // contiguous 32*WARPS*16-byte run at a time (DRAM page locality)
+    if (LOCKSTEP) __syncthreads();
+    // next row's operands first: they travel while this row is computed and stored
+    TmRowIn nxt;
+    if (r + 1 < r1) nxt = load_row(r + 1, k + v.pitch);
+    const TmRowCoef rc = tm_row_coef(v, r);
+    const double c_jz  = v.ti[B200FDTD_TMI_C_JZ * v.rows + r];
+    const double c_jzh = v.ti[B200FDTD_TMI_C_JZHXHY * v.rows + r];
+
     double2 ez_right = shfl_down1(ez_cur);              // old Ez(r, c+1)
-    if (lane == 31) ez_right = col_e_next[r];
+    if (lane == 31) ez_right = cur.edge_e;
 
     // ---- H phase ------------------------------------------------------------------
     TmH h;
     h.hx = zero; h.hy = zero;
-    if (active) h = tm_h_cell(v, r, c, ez_cur, ez_right, ez_next, mx_old, bx_old, my_old, by_old);
+    if (active) h = tm_h_cell(v, cc, rc, ez_cur, ez_right, cur.ez_below, cur.mx, cur.bx, cur.my, cur.by);
     double2 hx_left = shfl_up1(h.hx);                   // new Hx(r, c-1)
-    if (lane == 0) hx_left = col_h_mine[r];
+    if (lane == 0) hx_left = cur.edge_h;
 
     // ---- E phase (fdtdTM_upml.c:161-175) + source (field.c:248-253) -----------------
     if (active) {
-      const double c_jz  = v.ti[B200FDTD_TMI_C_JZ * v.rows + r];
-      const double c_jzh = v.ti[B200FDTD_TMI_C_JZHXHY * v.rows + r];
-      const double2 jz = c_jz * jz_old + c_jzh * (((h.hy - hy_prev) - h.hx) + hx_left);
-      const double2 dz = (c_dz * dz_old + c_dzjz * jz) - c_dzjz * jz_old;
-      double2 ez = dz / eps;
-      if (v.pulse[0].enabled && eps != 1.0)
-        ez = ez + pulse_term(v.pulse[0], r - 1, v.j_base + c, eps);
+      const double2 jz = c_jz * cur.jz + c_jzh * (((h.hy - hy_prev) - h.hx) + hx_left);
+      const double2 dz = (c_dz * cur.dz + c_dzjz * jz) - c_dzjz * cur.jz;
+      double2 ez = div_eps(dz, cur.eps);
+      if (v.pulse[0].enabled && cur.eps != 1.0)
+        ez = ez + pulse_term(v.pulse[0], r - 1, v.j_base + c, cur.eps);
       if ((long long)k == v.point_k)
         ez = ez + make_double2(v.point_re, v.point_im);
 
@@ -215,7 +253,8 @@ __global__ void __launch_bounds__(kFusedThreads) tm_upml_fused_kernel(const Fuse
       }
     }
     hy_prev = h.hy;
-    ez_cur = ez_next;
+    ez_cur = cur.ez_below;
+    cur = nxt;
   }
 }
 
@@ -282,9 +321,22 @@ int b200_launch_upml_fused(b200fdtd_engine *e, const b200fdtd_step_args *a)
   const long long n_row_items = (long long)(fs.n_bands + 1) * n_cols;
   tm_prepass_cols_kernel<<<(unsigned)((n_col_items + 255) / 256), 256, 0, e->stream>>>(f);
   tm_prepass_rows_kernel<<<(unsigned)((n_row_items + 255) / 256), 256, 0, e->stream>>>(f);
-  dim3 grid((fs.n_strips + kWarpsPerBlock - 1) / kWarpsPerBlock, fs.n_bands);
-  if (e->store_h) tm_upml_fused_kernel<true><<<grid, kFusedThreads, 0, e->stream>>>(f);
-  else            tm_upml_fused_kernel<false><<<grid, kFusedThreads, 0, e->stream>>>(f);
+  const int variant = e->fused_variant;                 // tuning knob: warps per block / lockstep
+#define FUSED_LAUNCH(W, L)                                                                     \
+  do {                                                                                         \
+    dim3 grid((fs.n_strips + (W) - 1) / (W), fs.n_bands);                                      \
+    if (e->store_h) tm_upml_fused_kernel<true, W, L><<<grid, 32 * (W), 0, e->stream>>>(f);      \
+    else            tm_upml_fused_kernel<false, W, L><<<grid, 32 * (W), 0, e->stream>>>(f);     \
+  } while (0)
+  switch (variant) {
+  case 1: FUSED_LAUNCH(8, false); break;
+  case 2: FUSED_LAUNCH(8, true); break;
+  case 3: FUSED_LAUNCH(4, true); break;
+  case 4: FUSED_LAUNCH(2, false); break;
+  case 5: FUSED_LAUNCH(16, true); break;
+  default: FUSED_LAUNCH(4, false); break;
+  }
+#undef FUSED_LAUNCH
   e->launches += 3;
   e->h_stale = !e->store_h;
   B200_CUDA(cudaGetLastError());

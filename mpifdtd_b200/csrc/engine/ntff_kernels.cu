@@ -44,18 +44,32 @@ __global__ void ntff_sample_kernel(const NtffPoint *__restrict__ pts, int n_loca
                                    const double2 *__restrict__ h_a,   // TM Hx   | TE Hz
                                    const double2 *__restrict__ h_b,   // TM Hy   | TE Hz
                                    int pitch, double2 *hist_e, double2 *hist_h, int max_time, int t,
-                                   double h_divisor)   // 1.0, or mu0 when h_a/h_b hold B (H == B/mu0)
+                                   // when the H arrays are not kept up to date (H == B/mu0 is formed on
+                                   // demand): b_a/b_b = Bx/By (TM), divisor = mu0, and c_lo = first updated
+                                   // column -- left of it lies the ring / a halo column, which only the H
+                                   // array holds.  b_a == nullptr: read H directly.
+                                   const double2 *__restrict__ b_a, const double2 *__restrict__ b_b,
+                                   double h_divisor, int c_lo)
 {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n_local) return;
   const NtffPoint pt = pts[p];
   const bool along_x = (pt.edge == 0 || pt.edge == 2);      // bottom / top edges
   double2 ev = along_x ? e_a[pt.k] : e_b[pt.k];
-  double2 h0 = along_x ? h_a[pt.k] : h_b[pt.k];
-  double2 h1 = along_x ? h_a[pt.k - 1] : h_b[pt.k - pitch];
-  if (h_divisor != 1.0) {                               // same quotient the H phase would have stored
-    h0 = make_double2(h0.x / h_divisor, h0.y / h_divisor);
-    h1 = make_double2(h1.x / h_divisor, h1.y / h_divisor);
+  double2 h0, h1;
+  if (b_a == nullptr) {
+    h0 = along_x ? h_a[pt.k] : h_b[pt.k];
+    h1 = along_x ? h_a[pt.k - 1] : h_b[pt.k - pitch];
+  } else {                                              // same quotients the H phase would have stored
+    const double2 q0 = along_x ? b_a[pt.k] : b_b[pt.k];
+    h0 = make_double2(q0.x / h_divisor, q0.y / h_divisor);
+    const bool left_is_outside = along_x && (int)(pt.k % pitch) - 1 < c_lo;
+    if (left_is_outside) {
+      h1 = h_a[pt.k - 1];
+    } else {
+      const double2 q1 = along_x ? b_a[pt.k - 1] : b_b[pt.k - pitch];
+      h1 = make_double2(q1.x / h_divisor, q1.y / h_divisor);
+    }
   }
   double2 hv = rmul(0.5, cadd(h0, h1));
   const bool negate = is_tm ? (pt.edge >= 2) : (pt.edge < 2);
@@ -283,12 +297,14 @@ int b200_launch_ntff_sample(b200fdtd_engine *e, const b200fdtd_step_args *a)
     const bool tm = is_tm(e->g.kind);
     const double2 *ea = e->field[tm ? (int)B200FDTD_TM_EZ : (int)B200FDTD_TE_EX];
     const double2 *eb = e->field[tm ? (int)B200FDTD_TM_EZ : (int)B200FDTD_TE_EY];
-    const bool from_b = e->h_stale && tm;               // fused step without H stores: sample B/mu0
-    const double2 *ha = e->field[tm ? (from_b ? (int)B200FDTD_TM_BX : (int)B200FDTD_TM_HX) : (int)B200FDTD_TE_HZ];
-    const double2 *hb = e->field[tm ? (from_b ? (int)B200FDTD_TM_BY : (int)B200FDTD_TM_HY) : (int)B200FDTD_TE_HZ];
+    const bool from_b = e->h_stale && tm;               // H arrays not kept: sample B/mu0
+    const double2 *ha = e->field[tm ? (int)B200FDTD_TM_HX : (int)B200FDTD_TE_HZ];
+    const double2 *hb = e->field[tm ? (int)B200FDTD_TM_HY : (int)B200FDTD_TE_HZ];
+    const double2 *ba = from_b ? e->field[B200FDTD_TM_BX] : nullptr;
+    const double2 *bb = from_b ? e->field[B200FDTD_TM_BY] : nullptr;
     ntff_sample_kernel<<<(n.n_local + 127) / 128, 128, 0, e->stream>>>(
         n.pts, n.n_local, tm ? 1 : 0, ea, eb, ha, hb, e->pitch, n.hist_e, n.hist_h, n.max_time, t,
-        from_b ? e->g.mu0 : 1.0);
+        ba, bb, e->g.mu0, e->c_lo);
     e->launches++;
     B200_CUDA(cudaGetLastError());
   }

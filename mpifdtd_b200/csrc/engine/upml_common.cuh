@@ -8,6 +8,8 @@ namespace upml {
 
 constexpr int kBlock = 256;
 
+struct ConstDivisor { double d, r; };   // a loop-invariant divisor and RN(1/d), see div_const()
+
 struct UpmlView {
   double2 *f[B200FDTD_MAX_FIELDS];
   const double *eps0, *eps1;
@@ -16,7 +18,7 @@ struct UpmlView {
   int r_lo, r_hi, c_lo, c_hi;
   int nbx;                      // thread blocks per row (two-kernel form)
   int j_base;                   // global j = j_base + c
-  double mu0;
+  ConstDivisor mu0;             // MU_0_S and its rounded reciprocal
   b200fdtd_pulse pulse[2];
   long long point_k;            // layout offset of the opt-in point source, or -1
   double point_re, point_im;
@@ -27,6 +29,54 @@ __device__ __forceinline__ double2 operator-(double2 a, double2 b) { return make
 __device__ __forceinline__ double2 operator-(double2 a) { return make_double2(-a.x, -a.y); }
 __device__ __forceinline__ double2 operator*(double r, double2 z) { return make_double2(r * z.x, r * z.y); }
 __device__ __forceinline__ double2 operator/(double2 z, double r) { return make_double2(z.x / r, z.y / r); }
+
+// ---- exact division shortcuts ---------------------------------------------------------
+// The reference divides by MU_0_S four times and by eps twice per TM cell, and two of its
+// coefficients are quotients (fdtdTM_upml.c:175,209,216,270-271).  IEEE double division
+// costs ~50 SASS instructions on the GPU; these helpers return the SAME correctly rounded
+// quotient for a fraction of that, so results stay bit-identical to `x / d`:
+//   * x / d with a loop-invariant d:  q = x*r, q' = fma(fma(-q, d, x), r, q) with
+//     r = RN(1/d) is the correctly rounded quotient (Markstein 1990) as long as nothing
+//     over/underflows; outside a conservative normal range, and never for x == 0, the
+//     plain division is used.  b200fdtd_selftest_division() checks the claim on the device
+//     against `/` over random bit patterns.
+//   * x / 1.0 == x and d / d == 1.0 exactly, so vacuum cells and non-PML coefficients skip
+//     the division altogether.
+// The full IEEE division lives behind a real call so the compiler cannot hoist its ~100
+// instructions out of the (rare) branches below and execute them speculatively.
+static __device__ __noinline__ double ieee_div(double x, double d) { return x / d; }
+
+__device__ __forceinline__ double div_const(double x, const ConstDivisor c)
+{
+  // Markstein: q = RN(x*r); rem = x - q*d exactly (FMA); RN(q + rem*r) == RN(x/d).
+  // rem == 0 means q is already the exact quotient (this also keeps the sign of a zero).
+  const double q = x * c.r;
+  const double rem = fma(-q, c.d, x);
+  double res = (rem == 0.0) ? q : fma(rem, c.r, q);
+  // The proof needs x, q and rem to be normal numbers.  One integer test on the exponent
+  // field: biased exponent in [93, 1953] (|x| roughly 1e-280 .. 1e280), or x == +-0.
+  const unsigned hi = (unsigned)__double2hiint(x) & 0x7fffffffu;
+  const bool exotic = (hi - 0x05d00000u) >= (0x7a100000u - 0x05d00000u);
+  if (exotic && x != 0.0) res = ieee_div(x, c.d);       // subnormal-ish, huge, inf, nan
+  return res;
+}
+__device__ __forceinline__ double2 div_const(double2 z, const ConstDivisor c)
+{
+  return make_double2(div_const(z.x, c), div_const(z.y, c));
+}
+// num / den where both are usually the same number (2*eps outside the PML)
+__device__ __forceinline__ double quotient_or_one(double num, double den)
+{
+  double q = 1.0;
+  if (num != den) q = ieee_div(num, den);
+  return q;
+}
+// z / eps where eps is usually exactly 1 (vacuum)
+__device__ __forceinline__ double2 div_eps(double2 z, double eps)
+{
+  if (eps != 1.0) z = make_double2(ieee_div(z.x, eps), ieee_div(z.y, eps));
+  return z;
+}
 
 // field_scatteredPulse (field.c:243-254) for one cell; i, j are GLOBAL indices.
 __device__ __forceinline__ double2 pulse_term(const b200fdtd_pulse &s, int i, int j, double eps)
@@ -58,7 +108,8 @@ inline UpmlView make_view(const b200fdtd_engine *e, const b200fdtd_step_args *a)
   v.c_hi = e->c_hi;
   v.nbx = (e->c_hi - e->c_lo + 1 + kBlock - 1) / kBlock;
   v.j_base = e->g.j0 - B200_JOFF;
-  v.mu0 = e->g.mu0;
+  v.mu0.d = e->g.mu0;
+  v.mu0.r = 1.0 / e->g.mu0;
   v.pulse[0] = a->pulse[0];
   v.pulse[1] = a->pulse[1];
   v.point_k = -1;

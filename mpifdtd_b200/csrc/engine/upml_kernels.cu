@@ -35,6 +35,10 @@ __device__ __forceinline__ bool locate(const UpmlView &v, int &r, int &c, size_t
 
 // ------------------------------------------------------------------ TM -----
 // slots: 0 Ez 1 Jz 2 Dz 3 Hx 4 Mx 5 Bx 6 Hy 7 My 8 By
+// STORE_H = false: Hx/Hy are not written; the E phase recomputes them from Bx/By
+// (Hx == Bx/mu0 exactly, fdtdTM_upml.c:209), which removes one 32 B/cell write and turns
+// the E phase's H reads into B reads: 264 instead of 296 B per cell-update, in place.
+template <bool STORE_H>
 __global__ void __launch_bounds__(kBlock) tm_upml_h_kernel(const UpmlView v)
 {
   int r, c; size_t k;
@@ -63,28 +67,48 @@ __global__ void __launch_bounds__(kBlock) tm_upml_h_kernel(const UpmlView v)
   const double2 bx = (bx_old + c_bx1 * mx) - c_bx0 * mx_old;
   // fdtdTM_upml.c:196-198 (C_MY == C_MYEZ == 1 exactly)
   const double2 my = my_old - ((-ez_i1) + ez);
-  const double c_by1 = num1 / den, c_by0 = num0 / den;      // fdtdTM_upml.c:270-271
+  const double c_by1 = quotient_or_one(num1, den), c_by0 = quotient_or_one(num0, den);   // fdtdTM_upml.c:270-271
   const double2 by = (c_by * by_old + c_by1 * my) - c_by0 * my_old;
 
   v.f[B200FDTD_TM_MX][k] = mx;
   v.f[B200FDTD_TM_BX][k] = bx;
   v.f[B200FDTD_TM_MY][k] = my;
   v.f[B200FDTD_TM_BY][k] = by;
-  v.f[B200FDTD_TM_HX][k] = bx / v.mu0;        // fdtdTM_upml.c:209
-  v.f[B200FDTD_TM_HY][k] = by / v.mu0;        // fdtdTM_upml.c:216
+  if (STORE_H) {
+    v.f[B200FDTD_TM_HX][k] = div_const(bx, v.mu0);   // fdtdTM_upml.c:209
+    v.f[B200FDTD_TM_HY][k] = div_const(by, v.mu0);   // fdtdTM_upml.c:216
+  }
 }
 
+// FROM_B = true: H is formed on the fly as B/mu0.  Cells just outside the updated range
+// (the ring, or a neighbour slab's halo column) are not derived state: there the H array
+// itself is read, exactly like the STORE_H form does.
+template <bool FROM_B>
 __global__ void __launch_bounds__(kBlock) tm_upml_e_kernel(const UpmlView v)
 {
   int r, c; size_t k;
   if (!locate(v, r, c, k)) return;
-  const double2 *__restrict__ Hx = v.f[B200FDTD_TM_HX];
-  const double2 *__restrict__ Hy = v.f[B200FDTD_TM_HY];
-
-  const double2 hy = Hy[k];
-  const double2 hy_i0 = Hy[k - v.pitch];      // Hy(i-1, j)
-  const double2 hx = Hx[k];
-  const double2 hx_j0 = Hx[k - 1];            // Hx(i, j-1)
+  double2 hy, hy_i0, hx, hx_j0;
+  if (FROM_B) {
+    const double2 *__restrict__ Bx = v.f[B200FDTD_TM_BX];
+    const double2 *__restrict__ By = v.f[B200FDTD_TM_BY];
+    // all four loads are issued unconditionally; the (block-uniform, rare) edge cases
+    // then replace the derived value by the stored one
+    const double2 by = By[k], bx = Bx[k], by_i0 = By[k - v.pitch], bx_j0 = Bx[k - 1];
+    hy = div_const(by, v.mu0);
+    hx = div_const(bx, v.mu0);
+    hy_i0 = div_const(by_i0, v.mu0);
+    hx_j0 = div_const(bx_j0, v.mu0);
+    if (r == v.r_lo) hy_i0 = v.f[B200FDTD_TM_HY][k - v.pitch];
+    if (c == v.c_lo) hx_j0 = v.f[B200FDTD_TM_HX][k - 1];
+  } else {
+    const double2 *__restrict__ Hx = v.f[B200FDTD_TM_HX];
+    const double2 *__restrict__ Hy = v.f[B200FDTD_TM_HY];
+    hy = Hy[k];
+    hy_i0 = Hy[k - v.pitch];      // Hy(i-1, j)
+    hx = Hx[k];
+    hx_j0 = Hx[k - 1];            // Hx(i, j-1)
+  }
   const double2 jz_old = v.f[B200FDTD_TM_JZ][k];
   const double2 dz_old = v.f[B200FDTD_TM_DZ][k];
   const double eps = v.eps0[k];
@@ -97,7 +121,7 @@ __global__ void __launch_bounds__(kBlock) tm_upml_e_kernel(const UpmlView v)
   // fdtdTM_upml.c:161-163 (C_DZJZ1 == C_DZJZ0 because sigma_z = 0)
   const double2 jz = c_jz * jz_old + c_jzh * (((hy - hy_i0) - hx) + hx_j0);
   const double2 dz = (c_dz * dz_old + c_dzjz * jz) - c_dzjz * jz_old;
-  double2 ez = dz / eps;                      // fdtdTM_upml.c:175
+  double2 ez = div_eps(dz, eps);              // fdtdTM_upml.c:175
 
   if (v.pulse[0].enabled && eps != 1.0)       // field.c:248
     ez = ez + pulse_term(v.pulse[0], r - 1, v.j_base + c, eps);
@@ -136,7 +160,7 @@ __global__ void __launch_bounds__(kBlock) te_upml_h_kernel(const UpmlView v)
 
   v.f[B200FDTD_TE_MZ][k] = mz;
   v.f[B200FDTD_TE_BZ][k] = bz;
-  v.f[B200FDTD_TE_HZ][k] = bz / v.mu0;        // fdtdTE_upml.c:312
+  v.f[B200FDTD_TE_HZ][k] = div_const(bz, v.mu0);   // fdtdTE_upml.c:312
 }
 
 __global__ void __launch_bounds__(kBlock) te_upml_e_kernel(const UpmlView v)
@@ -168,11 +192,11 @@ __global__ void __launch_bounds__(kBlock) te_upml_e_kernel(const UpmlView v)
   const double2 dx = (dx_old + c_dx1 * jx) - c_dx0 * jx_old;
   // fdtdTE_upml.c:269-271 (C_JY == C_JYHZ == 1)
   const double2 jy = jy_old + ((-hz) + hz_i0);
-  const double c_dy1 = num1 / den, c_dy0 = num0 / den;      // fdtdTE_upml.c:402-403
+  const double c_dy1 = quotient_or_one(num1, den), c_dy0 = quotient_or_one(num0, den);   // fdtdTE_upml.c:402-403
   const double2 dy = (c_dy * dy_old + c_dy1 * jy) - c_dy0 * jy_old;
 
-  double2 ex = dx / eps_x;                    // fdtdTE_upml.c:283
-  double2 ey = dy / eps_y;                    // fdtdTE_upml.c:289
+  double2 ex = div_eps(dx, eps_x);            // fdtdTE_upml.c:283
+  double2 ey = div_eps(dy, eps_y);            // fdtdTE_upml.c:289
   const int i = r - 1, j = v.j_base + c;
   if (v.pulse[0].enabled && eps_x != 1.0)     // fdtdTE_upml.c:186-187
     ex = ex + pulse_term(v.pulse[0], i, j, eps_x);
@@ -190,24 +214,70 @@ __global__ void __launch_bounds__(kBlock) te_upml_e_kernel(const UpmlView v)
 }
 
 // One halo column <-> a contiguous buffer of n_px complex values.
-__global__ void halo_column_kernel(double2 *field, double2 *buf, int pitch, int col, int n_px, int pack)
+// divisor != 0: `field` holds B and the packed value is H = B/divisor (H arrays not kept).
+__global__ void halo_column_kernel(double2 *field, double2 *buf, int pitch, int col, int n_px, int pack,
+                                   double divisor)
 {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_px) return;
   const size_t k = (size_t)(i + 1) * pitch + col;
-  if (pack) buf[i] = field[k];
-  else      field[k] = buf[i];
+  if (pack) {
+    const double2 v = field[k];
+    buf[i] = divisor != 0.0 ? make_double2(v.x / divisor, v.y / divisor) : v;
+  } else {
+    field[k] = buf[i];
+  }
 }
 
 }  // namespace
+
+// Device self-test of div_const / quotient_or_one / div_eps against plain IEEE division.
+namespace {
+__global__ void division_selftest_kernel(unsigned long long seed, unsigned long long per_thread, double d,
+                                         unsigned long long *mismatches)
+{
+  ConstDivisor c; c.d = d; c.r = 1.0 / d;
+  unsigned long long x = seed + 0x9E3779B97F4A7C15ull * (blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x + 1);
+  unsigned long long bad = 0;
+  for (unsigned long long n = 0; n < per_thread; n++) {
+    x ^= x << 13; x ^= x >> 7; x ^= x << 17;                 // xorshift64
+    // alternate between raw bit patterns (all exponents, subnormals, inf/nan) and field-like magnitudes
+    double v = (n & 1) ? __longlong_as_double((long long)x)
+                       : ((double)(long long)x) * ((n & 2) ? 1.0e-19 : 1.0e-31);
+    const double want = v / d, got = div_const(v, c);
+    const bool same = (__double_as_longlong(want) == __double_as_longlong(got)) || (want != want && got != got);
+    if (!same) bad++;
+  }
+  if (bad) atomicAdd(mismatches, bad);
+}
+}  // namespace
+
+int b200_selftest_division(double divisor, unsigned long long samples, unsigned long long *mismatches)
+{
+  unsigned long long *d_bad = nullptr;
+  B200_CUDA(cudaMalloc(&d_bad, sizeof *d_bad));
+  B200_CUDA(cudaMemset(d_bad, 0, sizeof *d_bad));
+  const unsigned blocks = 592, threads = 256;
+  const unsigned long long per_thread = samples / ((unsigned long long)blocks * threads) + 1;
+  division_selftest_kernel<<<blocks, threads>>>(0x1234567ull, per_thread, divisor, d_bad);
+  B200_CUDA(cudaGetLastError());
+  B200_CUDA(cudaMemcpy(mismatches, d_bad, sizeof *d_bad, cudaMemcpyDeviceToHost));
+  cudaFree(d_bad);
+  return B200FDTD_OK;
+}
 
 int b200_launch_upml_h(b200fdtd_engine *e, const b200fdtd_step_args *a)
 {
   if (e->r_hi < e->r_lo || e->c_hi < e->c_lo) return B200FDTD_OK;   // slab owns no updated cell
   const UpmlView v = make_view(e, a);
   const long long nblk = (long long)v.nbx * (e->r_hi - e->r_lo + 1);
-  if (is_tm(e->g.kind)) tm_upml_h_kernel<<<(unsigned)nblk, kBlock, 0, e->stream>>>(v);
-  else                  te_upml_h_kernel<<<(unsigned)nblk, kBlock, 0, e->stream>>>(v);
+  if (is_tm(e->g.kind)) {
+    if (e->store_h) tm_upml_h_kernel<true><<<(unsigned)nblk, kBlock, 0, e->stream>>>(v);
+    else            tm_upml_h_kernel<false><<<(unsigned)nblk, kBlock, 0, e->stream>>>(v);
+    e->h_stale = !e->store_h;
+  } else {
+    te_upml_h_kernel<<<(unsigned)nblk, kBlock, 0, e->stream>>>(v);
+  }
   e->launches++;
   B200_CUDA(cudaGetLastError());
   return B200FDTD_OK;
@@ -218,8 +288,12 @@ int b200_launch_upml_e(b200fdtd_engine *e, const b200fdtd_step_args *a)
   if (e->r_hi < e->r_lo || e->c_hi < e->c_lo) return B200FDTD_OK;
   const UpmlView v = make_view(e, a);
   const long long nblk = (long long)v.nbx * (e->r_hi - e->r_lo + 1);
-  if (is_tm(e->g.kind)) tm_upml_e_kernel<<<(unsigned)nblk, kBlock, 0, e->stream>>>(v);
-  else                  te_upml_e_kernel<<<(unsigned)nblk, kBlock, 0, e->stream>>>(v);
+  if (is_tm(e->g.kind)) {
+    if (e->h_stale) tm_upml_e_kernel<true><<<(unsigned)nblk, kBlock, 0, e->stream>>>(v);
+    else            tm_upml_e_kernel<false><<<(unsigned)nblk, kBlock, 0, e->stream>>>(v);
+  } else {
+    te_upml_e_kernel<<<(unsigned)nblk, kBlock, 0, e->stream>>>(v);
+  }
   e->launches++;
   B200_CUDA(cudaGetLastError());
   return B200FDTD_OK;
@@ -236,8 +310,13 @@ int b200_launch_halo(b200fdtd_engine *e, int which, void *buf, bool pack)
     col = pack ? B200_JOFF : B200_JOFF + e->g.nj;
   }
   const int n = e->g.n_px;
+  double divisor = 0.0;
+  if (which == 0 && pack && e->h_stale && is_tm(e->g.kind)) {   // Hx column = Bx column / mu0
+    slot = B200FDTD_TM_BX;
+    divisor = e->g.mu0;
+  }
   halo_column_kernel<<<(n + 255) / 256, 256, 0, e->stream>>>(e->field[slot], (double2 *)buf,
-                                                             e->pitch, col, n, pack ? 1 : 0);
+                                                             e->pitch, col, n, pack ? 1 : 0, divisor);
   e->launches++;
   B200_CUDA(cudaGetLastError());
   return B200FDTD_OK;

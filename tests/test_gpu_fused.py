@@ -1,9 +1,13 @@
-"""The one-pass (fused H+E) TM step against the two-kernel step: identical bits.
+"""Every form of the TM step must produce identical bits:
 
-Both forms evaluate the same expressions in the same order (-fmad=false), so after any
-number of steps from any state every one of the nine arrays, and the NTFF history, must
-agree bit for bit -- including ragged strips (columns not a multiple of 32), bands of any
-height, strips narrower than a warp, and with/without storing Hx/Hy."""
+  * two-kernel step that stores Hx/Hy (the literal restatement of the reference's passes),
+  * two-kernel step that does NOT store H and forms it as B/mu0 in the E phase (default),
+  * the one-pass "warp-strip marching" kernel, with and without H stores (opt-in).
+
+All evaluate the same expressions in the same order (-fmad=false), so after any number of
+steps from any state each of the nine arrays and the NTFF history must agree bit for bit
+-- including ragged strips (columns not a multiple of 32), bands of any height and strips
+narrower than a warp."""
 import ctypes as C
 
 import numpy as np
@@ -31,10 +35,9 @@ def make_engine(L, npx, npy, steps, eps, fused, store_h=0, band=None, j0=0, nj=N
     L.free(ptr)
     eng.n_bins = steps
     eng.set_option(B.OPT_FUSED, fused)
-    if fused:
-        eng.set_option(B.OPT_STORE_H, store_h)
-        if band:
-            eng.set_option(B.OPT_BAND_ROWS, band)
+    eng.set_option(B.OPT_STORE_H, store_h)
+    if fused and band:
+        eng.set_option(B.OPT_BAND_ROWS, band)
     return eng
 
 
@@ -52,7 +55,8 @@ def test_fused_step_is_bit_identical_to_two_kernel_step(plugin_lib, npx, npy, ba
     mu0 = B.MU_0_S
     state[3] = (state[5].real / mu0) + 1j * (state[5].imag / mu0)
     state[6] = (state[8].real / mu0) + 1j * (state[8].imag / mu0)
-    engines = [make_engine(L, npx, npy, steps, eps, 0),
+    engines = [make_engine(L, npx, npy, steps, eps, 0, store_h=1),
+               make_engine(L, npx, npy, steps, eps, 0, store_h=0),
                make_engine(L, npx, npy, steps, eps, 1, store_h=0, band=band),
                make_engine(L, npx, npy, steps, eps, 1, store_h=1, band=band)]
     for eng in engines:
@@ -82,10 +86,18 @@ def test_fused_step_is_bit_identical_to_two_kernel_step(plugin_lib, npx, npy, ba
         eng.close()
 
 
-def test_fused_is_the_default_for_the_serial_tm_solver(plugin_lib, in_tmp_cwd):
+def test_launches_per_step(plugin_lib, in_tmp_cwd):
     gpu = B.Plugin("MIE_CYLINDER", "TM_UPML_2D", 96, steps=10, h_u_nm=20)
     n0 = gpu.launches()
     gpu.step(1)
-    # fused step = 2 pre-pass launches + 1 main kernel + 1 NTFF sample
-    assert gpu.launches() - n0 == 4
+    assert gpu.launches() - n0 == 3          # H phase, E phase + source, NTFF sample
     gpu.finish()
+
+
+@pytest.mark.parametrize("divisor", [B.MU_0_S, 2.56, 1.0 / 3.0, 1.5625, 15.069924])
+def test_constant_division_shortcut_is_exactly_ieee(plugin_lib, divisor):
+    """div_const(x, d) must equal x / d bit for bit (upml_common.cuh): 2^31 operands per
+    divisor, half of them raw 64-bit patterns (all exponents, subnormals, inf, nan)."""
+    bad = C.c_uint64(123)
+    B.check(plugin_lib.b200fdtd_selftest_division(divisor, 1 << 31, C.byref(bad)), "selftest")
+    assert bad.value == 0
