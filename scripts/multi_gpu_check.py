@@ -1,0 +1,65 @@
+"""torchrun worker: a y-slab run over WORLD_SIZE GPUs (NCCL halos + NTFF reduce) must
+reproduce the single-GPU run: fields bit for bit, far field to summation-order noise.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+        --master-port 29511 scripts/multi_gpu_check.py [solver] [npx] [npy] [steps]
+"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from mpifdtd_b200.slab import SlabRun, TorchHaloComm
+
+solver = sys.argv[1] if len(sys.argv) > 1 else "TM_UPML_2D"
+npx = int(sys.argv[2]) if len(sys.argv) > 2 else 160
+npy = int(sys.argv[3]) if len(sys.argv) > 3 else 240
+steps = int(sys.argv[4]) if len(sys.argv) > 4 else 600
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+stream = torch.cuda.Stream()
+with torch.cuda.stream(stream):
+    comm = TorchHaloComm(npx, torch.device("cuda", local))
+    run = SlabRun("MIE_CYLINDER", solver, npx, npy, steps, rank=rank, world=world, device=local, comm=comm,
+                  h_u_nm=20, angle_deg=20)
+    run.engine.set_stream(stream.cuda_stream)
+    run.attach_halo_buffers(*comm.pointers())
+    for _ in range(steps):
+        run.step()
+    mine = [torch.from_numpy(run.gather_field(s).view(np.float64).copy()).cuda() for s in (0, 3, 6)]
+    far = run.far_field()
+    torch.cuda.synchronize()
+    # gather every rank's columns of the three main fields on rank 0
+    parts = []
+    for t in mine:
+        sizes = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
+        dist.all_gather(sizes, torch.tensor([t.shape[1]], dtype=torch.int64, device="cuda"))
+        bufs = [torch.zeros((npx, int(s.item())), dtype=torch.float64, device="cuda") for s in sizes]
+        dist.all_gather(bufs, t.contiguous())
+        parts.append(torch.cat(bufs, dim=1).cpu().numpy())
+    run.close()
+    ok = True
+    if rank == 0:
+        single = SlabRun("MIE_CYLINDER", solver, npx, npy, steps, rank=0, world=1, device=local, h_u_nm=20,
+                         angle_deg=20)
+        single.engine.set_stream(stream.cuda_stream)
+        for _ in range(steps):
+            single.step()
+        for n, slot in enumerate((0, 3, 6)):
+            want = single.gather_field(slot).view(np.float64)
+            same = np.array_equal(parts[n], want)
+            print("slot", slot, "bit-identical:", same, "max", np.abs(want).max())
+            ok &= same
+        want_far = single.far_field()
+        err = np.abs(far - want_far).max() / np.abs(want_far).max()
+        print("far field rel err vs single GPU:", err)
+        ok &= err < 1e-12
+        single.close()
+        print("MULTI_GPU_CHECK", "OK" if ok else "FAIL")
+dist.barrier()
+dist.destroy_process_group()
+sys.exit(0 if ok else 1)
