@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define B200FDTD_ABI_VERSION 1
+#define B200FDTD_ABI_VERSION 2
 
 enum {
   B200FDTD_OK = 0,
@@ -53,6 +53,22 @@ enum { B200FDTD_TM_EZ = 0, B200FDTD_TM_JZ, B200FDTD_TM_DZ, B200FDTD_TM_HX, B200F
 enum { B200FDTD_TE_EX = 0, B200FDTD_TE_JX, B200FDTD_TE_DX, B200FDTD_TE_EY, B200FDTD_TE_JY,
        B200FDTD_TE_DY, B200FDTD_TE_HZ, B200FDTD_TE_MZ, B200FDTD_TE_BZ };
 #define B200FDTD_MAX_FIELDS 9
+/* Split-field kinds (plain Berenger-PML Yee 0/1 and NS-FDTD 6/7) keep 5 complex arrays
+ * (fdtdTM.c:10-14, fdtdTE.c:10-14, nsFdtdTM.c:10-14, nsFdtdTE.c:11-15): */
+enum { B200FDTD_STM_EZ = 0, B200FDTD_STM_EZX, B200FDTD_STM_EZY, B200FDTD_STM_HX, B200FDTD_STM_HY };
+enum { B200FDTD_STE_HZ = 0, B200FDTD_STE_HZX, B200FDTD_STE_HZY, B200FDTD_STE_EX, B200FDTD_STE_EY };
+/* Their coefficients depend on the permittivity and are therefore genuinely 2-D; the host
+ * builds them with the reference's expressions and uploads them as dense arrays
+ * (b200fdtd_set_dense).  Slots 0-7 in the order the reference declares them: */
+enum { B200FDTD_STM_C_EZX = 0, B200FDTD_STM_C_EZXLX, B200FDTD_STM_C_EZY, B200FDTD_STM_C_EZYLY,
+       B200FDTD_STM_C_HX, B200FDTD_STM_C_HXLY, B200FDTD_STM_C_HY, B200FDTD_STM_C_HYLX };
+enum { B200FDTD_STE_C_EX = 0, B200FDTD_STE_C_EXLY, B200FDTD_STE_C_EY, B200FDTD_STE_C_EYLX,
+       B200FDTD_STE_C_HZX, B200FDTD_STE_C_HZXLX, B200FDTD_STE_C_HZY, B200FDTD_STE_C_HZYLY };
+/* slots 8, 9: per-cell factor of the scattered-field CW source on target 0 / 1, i.e.
+ * (eps0/eps - 1) (field.c:193) or (1/(_n*n) - 1) for NS-FDTD (field.c:168-174) */
+#define B200FDTD_DENSE_SRC0 8
+#define B200FDTD_DENSE_SRC1 9
+#define B200FDTD_MAX_DENSE 10
 
 /* 1-D coefficient tables of the UPML kinds.  The reference stores 15 dense
  * N_CELL arrays per solver (fdtdTM_upml.c:30-35); because every one of them is
@@ -106,12 +122,29 @@ typedef struct b200fdtd_point_source {
   double re, im;
 } b200fdtd_point_source;
 
+/* Scattered-field continuous wave.  p[k] += scale * factor[k] * (cexp(i(kr - phase_a))
+ * [- cexp(i(kr - phase_b)) when two_term]), kr = (i+gap_x)*ks_cos + (j+gap_y)*ks_sin.
+ *   field_scatteredWaveNotUPML   (field.c:179-196): two_term, phases w(t+1/2), w(t-1/2)
+ *   field_nsScatteredWaveNotUPML (field.c:155-177): two_term, phases w(t+1),   w t
+ *   scatteredWave of the MPI solvers (mpiTM_UPML.c:337-374): one term, phase w t, gaps 0
+ * scale = ray_coef (* dot).  factor[k] comes from dense slot 8/9 for the split-field kinds
+ * and is (eps0/eps[k] - 1) evaluated in the kernel for the UPML kinds. */
+typedef struct b200fdtd_cw {
+  int32_t enabled, two_term;
+  double gap_x, gap_y, scale;
+  double ks_cos, ks_sin;
+  double phase_a, phase_b;
+} b200fdtd_cw;
+
 /* Everything one update() call depends on that the host owns (field.c:44-51). */
 typedef struct b200fdtd_step_args {
   double time;                     /* field_getTime() BEFORE field_nextStep()         */
   double ray_coef;                 /* field_getRayCoef()                              */
   b200fdtd_pulse pulse[2];         /* TM: [0] on Ez.  TE: [0] on Ex, [1] on Ey        */
   b200fdtd_point_source point;
+  b200fdtd_cw cw[2];               /* CW sources: target 0 / 1 of the solver kind     */
+  double ns_r2;                    /* NS-FDTD: r/2 of the 9-point operator             */
+                                   /* (nsFdtdTM.c:115-117), 0 otherwise               */
 } b200fdtd_step_args;
 
 /* Closed NTFF surface (NTFFInfo, field.h:62-68) and its sampling plan.
@@ -174,6 +207,10 @@ int b200fdtd_set_eps(b200fdtd_engine *e, int32_t eps_slot, const double *host_ep
 /* the same from a slab-shaped map [n_px][nj] (what a rank of a multi-GPU run builds) */
 int b200fdtd_set_eps_slab(b200fdtd_engine *e, int32_t eps_slot, const double *slab_eps);
 int b200fdtd_set_ntff_plan(b200fdtd_engine *e, const b200fdtd_ntff_plan *plan);   /* ntffTM_init */
+/* dense per-cell array of a split-field kind: host [n_px][n_py] map (B200FDTD_ST?_C_* or
+ * B200FDTD_DENSE_SRC?); replaces the coefficient loops of fdtdTM.c:197-242,
+ * nsFdtdTM.c:231-307 etc. */
+int b200fdtd_set_dense(b200fdtd_engine *e, int32_t slot, const double *host_map);
 
 /* ---- the hot path -------------------------------------------------------- */
 /* One update() (fdtdTM_upml.c:54-66 / fdtdTE_upml.c:168-192): H phase, E phase

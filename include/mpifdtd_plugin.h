@@ -163,6 +163,18 @@ MPIFDTD_DECLARE_SOLVER(fdtdTE, Ex, Ey, Hz)                    /* fdtdTE.h:5-17  
 MPIFDTD_DECLARE_SOLVER(nsFdtdTM, Hx, Hy, Ez)                  /* nsFdtdTM.h:5-19    */
 MPIFDTD_DECLARE_SOLVER(nsFdtdTE, Ex, Ey, Hz)                  /* nsFdtdTE.h:5-19    */
 
+/* extra getters of the split-field solvers (fdtdTM.h:10-11, fdtdTE.h:12-13,
+ * nsFdtdTM.h:11-19, nsFdtdTE.h:11-19) */
+extern double complex *fdtdTM_getEzx(void), *fdtdTM_getEzy(void);
+extern double complex *fdtdTE_getHzx(void), *fdtdTE_getHzy(void);
+extern double complex *nsFdtdTM_getEzx(void), *nsFdtdTM_getEzy(void);
+extern double complex *nsFdtdTE_getHzx(void), *nsFdtdTE_getHzy(void);
+extern double *nsFdtdTM_getEpsX(void), *nsFdtdTM_getEpsY(void), *nsFdtdTM_getEpsZ(void);
+extern double *nsFdtdTE_getEpsX(void), *nsFdtdTE_getEpsY(void), *nsFdtdTE_getEpsZ(void);
+struct Solver;                                                /* solver.h:7-20 */
+extern struct Solver *nsFdtdTM_getSolver(void);
+extern struct Solver *nsFdtdTE_getSolver(void);
+
 /* ---- far-field output format (ntff.h:4-9) ------------------------------- */
 #define LAMBDA_ST_NM 380
 #define LAMBDA_EN_NM 700

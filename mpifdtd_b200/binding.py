@@ -63,9 +63,15 @@ class PointSource(C.Structure):
                 ("re", C.c_double), ("im", C.c_double)]
 
 
+class CwSource(C.Structure):
+    _fields_ = [("enabled", C.c_int32), ("two_term", C.c_int32), ("gap_x", C.c_double),
+                ("gap_y", C.c_double), ("scale", C.c_double), ("ks_cos", C.c_double),
+                ("ks_sin", C.c_double), ("phase_a", C.c_double), ("phase_b", C.c_double)]
+
+
 class StepArgs(C.Structure):
     _fields_ = [("time", C.c_double), ("ray_coef", C.c_double), ("pulse", Pulse * 2),
-                ("point", PointSource)]
+                ("point", PointSource), ("cw", CwSource * 2), ("ns_r2", C.c_double)]
 
 
 class NtffPlan(C.Structure):
@@ -118,6 +124,13 @@ def lib():
     L.b200fdtd_set_field.argtypes = [vp, i32, vp]
     L.b200fdtd_get_field_slab.argtypes = [vp, i32, vp]
     L.b200fdtd_set_option.argtypes = [vp, i32, i32]
+    L.b200fdtd_set_dense.argtypes = [vp, i32, vp]
+    L.mpifdtd_split_prepare_host.argtypes = [C.c_int]
+    L.mpifdtd_split_dense.argtypes = [C.c_int, C.c_int]
+    L.mpifdtd_split_dense.restype = vp
+    L.mpifdtd_split_engine.argtypes = [C.c_int]
+    L.mpifdtd_split_engine.restype = vp
+    L.mpifdtd_split_step_args.argtypes = [C.c_int, C.POINTER(StepArgs)]
     L.b200fdtd_selftest_division.argtypes = [dbl, C.c_uint64, C.POINTER(C.c_uint64)]
     L.b200fdtd_zero_state.argtypes = [vp]
     L.b200fdtd_ntff_project.argtypes = [vp]
@@ -170,6 +183,11 @@ def lib():
                  "fdtdTE_upml_getEx", "fdtdTE_upml_getEy", "fdtdTE_upml_getHz",
                  "fdtdTM_upml_getEps", "fdtdTE_upml_getEps"):
         getattr(L, name).restype = vp
+    for prefix, fields in (("fdtdTM", ("Hx", "Hy", "Ez", "Ezx", "Ezy")), ("fdtdTE", ("Ex", "Ey", "Hz", "Hzx", "Hzy")),
+                           ("nsFdtdTM", ("Hx", "Hy", "Ez", "Ezx", "Ezy")),
+                           ("nsFdtdTE", ("Ex", "Ey", "Hz", "Hzx", "Hzy"))):
+        for f in fields + ("Eps",):
+            getattr(L, "%s_get%s" % (prefix, f)).restype = vp
     L.free.argtypes = [vp]
     _lib = L
     return L
@@ -199,7 +217,11 @@ class Plugin:
     """The reference's driver sequence against the plugin surface."""
 
     GETTERS = {2: dict(Hx="fdtdTM_upml_getHx", Hy="fdtdTM_upml_getHy", Ez="fdtdTM_upml_getEz"),
-               3: dict(Ex="fdtdTE_upml_getEx", Ey="fdtdTE_upml_getEy", Hz="fdtdTE_upml_getHz")}
+               3: dict(Ex="fdtdTE_upml_getEx", Ey="fdtdTE_upml_getEy", Hz="fdtdTE_upml_getHz"),
+               0: {f: "fdtdTM_get" + f for f in ("Hx", "Hy", "Ez", "Ezx", "Ezy")},
+               1: {f: "fdtdTE_get" + f for f in ("Ex", "Ey", "Hz", "Hzx", "Hzy")},
+               6: {f: "nsFdtdTM_get" + f for f in ("Hx", "Hy", "Ez", "Ezx", "Ezy")},
+               7: {f: "nsFdtdTE_get" + f for f in ("Ex", "Ey", "Hz", "Hzx", "Hzy")}}
 
     def __init__(self, model, solver, n_px, n_py=None, steps=100, h_u_nm=10, pml=10,
                  lambda_nm=500, angle_deg=0, point_source=False):
@@ -216,7 +238,9 @@ class Plugin:
         self.finished = False
 
     def engine_handle(self):
-        return self.L.mpifdtd_upml_engine(self.solver)
+        if self.solver in (2, 3):
+            return self.L.mpifdtd_upml_engine(self.solver)
+        return self.L.mpifdtd_split_engine(self.solver)
 
     def step(self, n=1):
         for _ in range(n):

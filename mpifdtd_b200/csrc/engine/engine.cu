@@ -20,6 +20,11 @@ int b200_fail(int code, const char *fmt, ...)
 
 namespace {
 
+bool kind_is_split(int kind)
+{
+  return kind == B200FDTD_TM || kind == B200FDTD_TE || kind == B200FDTD_NS_TM || kind == B200FDTD_NS_TE;
+}
+
 bool kind_is_upml(int kind)
 {
   return kind == B200FDTD_TM_UPML || kind == B200FDTD_TE_UPML || kind == B200FDTD_MPI_TM_UPML ||
@@ -96,7 +101,7 @@ int b200fdtd_create(const b200fdtd_grid *grid, b200fdtd_engine **out)
 {
   if (!grid || !out) return b200_fail(B200FDTD_ERR_ARG, "NULL argument");
   *out = nullptr;
-  if (!kind_is_upml(grid->kind))
+  if (!kind_is_upml(grid->kind) && !kind_is_split(grid->kind))
     return b200_fail(B200FDTD_ERR_ARG, "solver kind %d is not served by this engine build", grid->kind);
   if (grid->n_px < 3 || grid->n_py < 3 || grid->nj < 1 || grid->j0 < 0 ||
       grid->j0 + grid->nj > grid->n_py || grid->n_pml < 0)
@@ -127,7 +132,7 @@ int b200fdtd_create(const b200fdtd_grid *grid, b200fdtd_engine **out)
   e->rows = grid->n_px + 2;
   e->pitch = ((B200_JOFF + grid->nj + 1) + 7) / 8 * 8;
   e->plane = (size_t)e->rows * e->pitch;
-  e->n_fields = 9;
+  e->n_fields = kind_is_split(grid->kind) ? 5 : 9;
   e->use_fused = false;     // the marching one-pass kernel is opt-in (B200FDTD_OPT_FUSED)
   e->store_h = false;
   e->h_stale = false;
@@ -146,11 +151,16 @@ int b200fdtd_create(const b200fdtd_grid *grid, b200fdtd_engine **out)
 
   for (int s = 0; s < e->n_fields && !rc; s++)
     rc = dev_alloc_zero(e, (void **)&e->field[s], e->plane * sizeof(double2));
-  const int n_eps = (grid->kind == B200FDTD_TM_UPML || grid->kind == B200FDTD_MPI_TM_UPML) ? 1 : 2;
-  for (int s = 0; s < n_eps && !rc; s++)
-    rc = dev_alloc_zero(e, (void **)&e->eps[s], e->plane * sizeof(double));
-  if (!rc) rc = dev_alloc_zero(e, (void **)&e->tab_i, sizeof(double) * B200FDTD_UPML_TABS * e->rows);
-  if (!rc) rc = dev_alloc_zero(e, (void **)&e->tab_j, sizeof(double) * B200FDTD_UPML_TABS * e->pitch);
+  if (kind_is_split(grid->kind)) {
+    for (int s = 0; s < B200FDTD_MAX_DENSE && !rc; s++)
+      rc = dev_alloc_zero(e, (void **)&e->dense[s], e->plane * sizeof(double));
+  } else {
+    const int n_eps = (grid->kind == B200FDTD_TM_UPML || grid->kind == B200FDTD_MPI_TM_UPML) ? 1 : 2;
+    for (int s = 0; s < n_eps && !rc; s++)
+      rc = dev_alloc_zero(e, (void **)&e->eps[s], e->plane * sizeof(double));
+    if (!rc) rc = dev_alloc_zero(e, (void **)&e->tab_i, sizeof(double) * B200FDTD_UPML_TABS * e->rows);
+    if (!rc) rc = dev_alloc_zero(e, (void **)&e->tab_j, sizeof(double) * B200FDTD_UPML_TABS * e->pitch);
+  }
   if (rc) { b200fdtd_destroy(e); return rc; }
   if (cudaStreamSynchronize(e->stream) != cudaSuccess) {
     b200fdtd_destroy(e);
@@ -168,6 +178,7 @@ int b200fdtd_destroy(b200fdtd_engine *e)
   for (int s = 0; s < B200FDTD_MAX_FIELDS; s++) cudaFree(e->field[s]);
   cudaFree(e->eps[0]); cudaFree(e->eps[1]);
   cudaFree(e->tab_i); cudaFree(e->tab_j);
+  for (int s = 0; s < B200FDTD_MAX_DENSE; s++) cudaFree(e->dense[s]);
   free_ntff(e);
   b200_fused_release(e);
   if (e->ev0) cudaEventDestroy(e->ev0);
@@ -240,6 +251,20 @@ static int upload_eps(b200fdtd_engine *e, int32_t slot, const double *src, size_
   return B200FDTD_OK;
 }
 
+int b200fdtd_set_dense(b200fdtd_engine *e, int32_t slot, const double *host_map)
+{
+  if (!e || !host_map || slot < 0 || slot >= B200FDTD_MAX_DENSE || !e->dense[slot])
+    return b200_fail(B200FDTD_ERR_ARG, "bad dense slot %d for kind %d", slot, e ? e->g.kind : -1);
+  int rc = select_device(e); if (rc) return rc;
+  const b200fdtd_grid &g = e->g;
+  B200_CUDA(cudaMemcpy2DAsync(e->dense[slot] + (size_t)e->pitch + B200_JOFF, sizeof(double) * e->pitch,
+                              host_map + g.j0, sizeof(double) * g.n_py, sizeof(double) * g.nj, g.n_px,
+                              cudaMemcpyHostToDevice, e->stream));
+  B200_CUDA(cudaStreamSynchronize(e->stream));
+  e->have_dense[slot] = true;
+  return B200FDTD_OK;
+}
+
 int b200fdtd_set_ntff_plan(b200fdtd_engine *e, const b200fdtd_ntff_plan *p)
 {
   if (!e || !p || (!p->time_shift && p->n_local > 0)) return b200_fail(B200FDTD_ERR_ARG, "NULL argument");
@@ -304,6 +329,11 @@ int b200fdtd_set_ntff_plan(b200fdtd_engine *e, const b200fdtd_ntff_plan *p)
 static int check_ready(b200fdtd_engine *e, const b200fdtd_step_args *a)
 {
   if (!e || !a) return b200_fail(B200FDTD_ERR_ARG, "NULL argument");
+  if (kind_is_split(e->g.kind)) {
+    for (int s = 0; s < 8; s++)
+      if (!e->have_dense[s]) return b200_fail(B200FDTD_ERR_STATE, "step before set_dense(%d)", s);
+    return select_device(e);
+  }
   if (!e->have_tabs) return b200_fail(B200FDTD_ERR_STATE, "step before set_upml_tables");
   if (!e->have_eps[0] || (e->eps[1] && !e->have_eps[1]))
     return b200_fail(B200FDTD_ERR_STATE, "step before set_eps");
@@ -313,12 +343,14 @@ static int check_ready(b200fdtd_engine *e, const b200fdtd_step_args *a)
 int b200fdtd_phase_h(b200fdtd_engine *e, const b200fdtd_step_args *a)
 {
   int rc = check_ready(e, a); if (rc) return rc;
+  if (kind_is_split(e->g.kind)) return b200_fail(B200FDTD_ERR_ARG, "phase API serves the UPML kinds only");
   return b200_launch_upml_h(e, a);              // sets h_stale = !store_h
 }
 
 int b200fdtd_phase_e(b200fdtd_engine *e, const b200fdtd_step_args *a)
 {
   int rc = check_ready(e, a); if (rc) return rc;
+  if (kind_is_split(e->g.kind)) return b200_fail(B200FDTD_ERR_ARG, "phase API serves the UPML kinds only");
   return b200_launch_upml_e(e, a);              // reads B/mu0 when the H arrays are stale
 }
 
@@ -359,6 +391,7 @@ int b200fdtd_phase_sample(b200fdtd_engine *e, const b200fdtd_step_args *a)
 int b200fdtd_step(b200fdtd_engine *e, const b200fdtd_step_args *a)
 {
   int rc = check_ready(e, a); if (rc) return rc;
+  if (kind_is_split(e->g.kind)) return b200_launch_split_step(e, a);
   const bool e_first = (e->g.kind == B200FDTD_MPI_TM_UPML || e->g.kind == B200FDTD_MPI_TE_UPML);
   if (e->use_fused && e->g.kind == B200FDTD_TM_UPML) {
     rc = b200_launch_upml_fused(e, a);          // H and E in one pass

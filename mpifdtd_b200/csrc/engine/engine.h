@@ -54,6 +54,8 @@ struct b200fdtd_engine {
   int n_fields;
   double2 *field[B200FDTD_MAX_FIELDS];
   double *eps[2];
+  double *dense[B200FDTD_MAX_DENSE];   // split-field kinds: coefficients + source factors
+  bool have_dense[B200FDTD_MAX_DENSE];
   double *tab_i;            // device [B200FDTD_UPML_TABS][rows], indexed by row = i + 1
   double *tab_j;            // device [B200FDTD_UPML_TABS][pitch], indexed by in-row offset
   bool have_tabs, have_eps[2];
@@ -85,6 +87,9 @@ int b200_launch_upml_h(b200fdtd_engine *e, const b200fdtd_step_args *a);
 int b200_launch_upml_e(b200fdtd_engine *e, const b200fdtd_step_args *a);
 int b200_launch_halo(b200fdtd_engine *e, int which, void *buf, bool pack);
 int b200_selftest_division(double divisor, unsigned long long samples, unsigned long long *mismatches);
+
+// launchers (split_kernels.cu)
+int b200_launch_split_step(b200fdtd_engine *e, const b200fdtd_step_args *a);
 
 // launchers (fused_kernels.cu)
 int b200_launch_upml_fused(b200fdtd_engine *e, const b200fdtd_step_args *a);

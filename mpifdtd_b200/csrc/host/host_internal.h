@@ -28,4 +28,11 @@ extern int mpifdtd_upml_dense_coefficient(int kind, const char *name, double *ds
 /* the twelve 1-D tables of include/b200fdtd.h for the current field_init() state */
 extern void mpifdtd_upml_tables(int kind, double *tab_i, double *tab_j);
 
+
+/* split_shim.c */
+extern void mpifdtd_split_step_args(int kind, b200fdtd_step_args *a);
+extern void mpifdtd_split_prepare_host(int kind);
+extern const double *mpifdtd_split_dense(int kind, int slot);
+extern b200fdtd_engine *mpifdtd_split_engine(int kind);
+
 #endif

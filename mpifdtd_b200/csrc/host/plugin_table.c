@@ -33,9 +33,14 @@ typedef struct SolverRow {
 
 /* TM solvers draw Ez (getDataZ), TE solvers draw Ey (getDataY): simulator.c:43,62 */
 static const SolverRow solver_rows[] = {
+  [TM_2D]      = ROW(fdtdTM, Hx, Hy, Ez, "TM mode \n", "TM", 2),
+  [TE_2D]      = ROW(fdtdTE, Ex, Ey, Hz, "TE mode \n", "TE", 1),
   [TM_UPML_2D] = ROW(fdtdTM_upml, Hx, Hy, Ez, "TM UPML mode \n", "TM_UPML", 2),
   [TE_UPML_2D] = ROW(fdtdTE_upml, Ex, Ey, Hz, "TE UPML mode \n", "TE_UPML", 1),
-  [NS_TE_2D]   = { NULL, NULL, NULL, NULL, NULL, NULL, NULL, NULL, NULL, 0, NULL },
+  [MPI_TM_UPML_2D] = { NULL, NULL, NULL, NULL, NULL, NULL, NULL, NULL, NULL, 0, NULL },
+  [MPI_TE_UPML_2D] = { NULL, NULL, NULL, NULL, NULL, NULL, NULL, NULL, NULL, 0, NULL },
+  [NS_TM_2D]   = ROW(nsFdtdTM, Hx, Hy, Ez, "NS TM mode \n", "NS_TM", 2),
+  [NS_TE_2D]   = ROW(nsFdtdTE, Ex, Ey, Hz, "NS TE mode \n", "NS_TE", 1),
 };
 
 static struct {

@@ -1,0 +1,469 @@
+/* split_shim.c -- entry points of the four split-field solvers (fdtdTM_get*,
+ * fdtdTE_get*, nsFdtdTM_get*, nsFdtdTE_get*) implemented over the GPU engine.
+ *
+ * The reference keeps, per solver, five complex fields and eight dense coefficient
+ * arrays that depend on the permittivity (fdtdTM.c:10-17, fdtdTE.c:10-17,
+ * nsFdtdTM.c:10-18, nsFdtdTE.c:11-18).  The coefficient loops run here, on the host,
+ * with the reference's expressions and libm calls (so the arrays are bit-identical);
+ * the time stepping, source injection included, runs on the device.  Lifecycle as in
+ * the reference: init() builds and uploads, update() is one asynchronous step, reset()
+ * dumps |F|^2 on the validation circle (field_outputElliptic) and zeroes the fields,
+ * finish() = reset() + free.
+ */
+#define _USE_MATH_DEFINES
+#include <complex.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include "b200fdtd.h"
+#include "host_internal.h"
+
+#ifndef M_PI
+#define M_PI 3.1415926535897932384626433832795
+#endif
+
+typedef struct SplitSolver {
+  int kind;                       /* B200FDTD_TM / _TE / _NS_TM / _NS_TE          */
+  b200fdtd_engine *engine;
+  double *eps[3];                 /* TM: EZ, HX, HY      TE: EX, EY, HZ           */
+  double *coef[8];
+  double *src[2];
+  dcomplex *mirror[5];            /* host mirrors of the five fields              */
+} SplitSolver;
+
+static SplitSolver tm_plain = { .kind = B200FDTD_TM }, te_plain = { .kind = B200FDTD_TE };
+static SplitSolver tm_ns = { .kind = B200FDTD_NS_TM }, te_ns = { .kind = B200FDTD_NS_TE };
+
+static void die_on(int rc, const char *what)
+{
+  if (rc == B200FDTD_OK) return;
+  printf("b200fdtd: %s failed (%d): %s\n", what, rc, b200fdtd_last_error());
+  exit(2);
+}
+
+static int is_tm(const SplitSolver *s) { return s->kind == B200FDTD_TM || s->kind == B200FDTD_NS_TM; }
+
+/* NS-FDTD helpers (nsFdtdTM.c:221-229) */
+static double ns_beta(double alpha) { return tanh(alpha) / (1 + pow(tanh(alpha), 2)); }
+static double ns_coef1(double beta) { return (1 - beta) / (1 + beta); }
+
+/* per-cell factor of field_nsScatteredWaveNotUPML (field.c:168-174) */
+static double ns_source_factor(double eps, double w_s, double k_s)
+{
+  double n = sqrt(eps / EPSILON_0_S);
+  double u0 = sin(w_s * 0.5) / sin(k_s * 0.5);
+  double u1 = sin(w_s * 0.5) / sin(n * k_s * 0.5);
+  double _n = u0 / u1;
+  return 1.0 / (_n * n) - 1.0;
+}
+
+/* ---- coefficient loops ---------------------------------------------------------- */
+static void build_plain_tm(SplitSolver *s)                      /* fdtdTM.c:197-242 */
+{
+  double R = 1.0e-8, M = 2.0;
+  const double sig_max = -(M + 1.0) * EPSILON_0_S * LIGHT_SPEED_S / 2.0 / N_PML * log(R);
+  for (int i = 0; i < N_PX; i++)
+    for (int j = 0; j < N_PY; j++) {
+      int k = ind(i, j);
+      double eps_ez = s->eps[0][k];
+      double sig_ez_x = sig_max * field_sigmaX(i, j);
+      double sig_ez_y = sig_max * field_sigmaY(i, j);
+      double sig_hx_y = sig_max * field_sigmaY(i, j + 0.5);
+      double sig_hx_yy = MU_0_S / EPSILON_0_S * sig_hx_y;
+      double sig_hy_x = sig_max * field_sigmaX(i + 0.5, j);
+      double sig_hy_xx = MU_0_S / EPSILON_0_S * sig_hy_x;
+      s->coef[B200FDTD_STM_C_EZX][k]   = field_pmlCoef(eps_ez, sig_ez_x);
+      s->coef[B200FDTD_STM_C_EZXLX][k] = field_pmlCoef_LXY(eps_ez, sig_ez_x);
+      s->coef[B200FDTD_STM_C_EZY][k]   = field_pmlCoef(eps_ez, sig_ez_y);
+      s->coef[B200FDTD_STM_C_EZYLY][k] = field_pmlCoef_LXY(eps_ez, sig_ez_y);
+      s->coef[B200FDTD_STM_C_HX][k]    = field_pmlCoef(MU_0_S, sig_hx_yy);
+      s->coef[B200FDTD_STM_C_HXLY][k]  = field_pmlCoef_LXY(MU_0_S, sig_hx_yy);
+      s->coef[B200FDTD_STM_C_HY][k]    = field_pmlCoef(MU_0_S, sig_hy_xx);
+      s->coef[B200FDTD_STM_C_HYLX][k]  = field_pmlCoef_LXY(MU_0_S, sig_hy_xx);
+      s->src[0][k] = EPSILON_0_S / eps_ez - 1.0;               /* field.c:193 */
+    }
+}
+
+static void build_plain_te(SplitSolver *s)                      /* fdtdTE.c:199-243 */
+{
+  double R = 1.0e-8, M = 2.0;
+  const double sig_max = -(M + 1.0) * EPSILON_0_S * LIGHT_SPEED_S / 2.0 / N_PML * log(R);
+  for (int i = 0; i < N_PX; i++)
+    for (int j = 0; j < N_PY; j++) {
+      int k = ind(i, j);
+      double eps_ex = s->eps[0][k], eps_ey = s->eps[1][k];
+      double sig_ex_y = sig_max * field_sigmaY(i + 0.5, j);
+      double sig_ey_x = sig_max * field_sigmaX(i, j + 0.5);
+      double sig_hz_x = sig_max * field_sigmaX(i + 0.5, j + 0.5);
+      double sig_hz_xx = MU_0_S / EPSILON_0_S * sig_hz_x;
+      double sig_hz_y = sig_max * field_sigmaY(i + 0.5, j + 0.5);
+      double sig_hz_yy = MU_0_S / EPSILON_0_S * sig_hz_y;
+      s->coef[B200FDTD_STE_C_EX][k]    = field_pmlCoef(eps_ex, sig_ex_y);
+      s->coef[B200FDTD_STE_C_EXLY][k]  = field_pmlCoef_LXY(eps_ex, sig_ex_y);
+      s->coef[B200FDTD_STE_C_EY][k]    = field_pmlCoef(eps_ey, sig_ey_x);
+      s->coef[B200FDTD_STE_C_EYLX][k]  = field_pmlCoef_LXY(eps_ey, sig_ey_x);
+      s->coef[B200FDTD_STE_C_HZX][k]   = field_pmlCoef(MU_0_S, sig_hz_xx);
+      s->coef[B200FDTD_STE_C_HZXLX][k] = field_pmlCoef_LXY(MU_0_S, sig_hz_xx);
+      s->coef[B200FDTD_STE_C_HZY][k]   = field_pmlCoef(MU_0_S, sig_hz_yy);
+      s->coef[B200FDTD_STE_C_HZYLY][k] = field_pmlCoef_LXY(MU_0_S, sig_hz_yy);
+      s->src[1][k] = EPSILON_0_S / eps_ey - 1.0;               /* source on Ey only, fdtdTE.c:285 */
+    }
+}
+
+static void build_ns_tm(SplitSolver *s)                         /* nsFdtdTM.c:231-307 */
+{
+  const double R = 1.0e-8, M = 2.0;
+  const double sig_max = -(M + 1.0) * EPSILON_0_S * C_0_S / N_PML * log(R);
+  const double w_s = field_getOmega(), k_s = field_getK();
+  for (int i = 0; i < N_PX; i++)
+    for (int j = 0; j < N_PY; j++) {
+      int k = field_index(i, j);
+      double eps_ez = s->eps[0][k], eps_hx = s->eps[1][k], eps_hy = s->eps[2][k];
+      double sig_ez_x = sig_max * field_sigmaX(i, j);
+      double sig_ez_y = sig_max * field_sigmaY(i, j);
+      double sig_hx_y = sig_max * field_sigmaY(i, j + 0.5);
+      double sig_hy_x = sig_max * field_sigmaX(i + 0.5, j);
+      double a_hx_y = sig_hx_y / (2 * EPSILON_0_S);
+      double a_hy_x = sig_hy_x / (2 * EPSILON_0_S);
+      double a_ez_x = sig_ez_x / (2 * EPSILON_0_S);
+      double a_ez_y = sig_ez_y / (2 * EPSILON_0_S);
+      double b_hx_y = ns_beta(a_hx_y), b_hy_x = ns_beta(a_hy_x);
+      double b_ez_x = ns_beta(a_ez_x), b_ez_y = ns_beta(a_ez_y);
+
+      double z_ez = sqrt(MU_0_S / eps_ez);
+      double n_ez = sqrt(eps_ez / EPSILON_0_S);
+      double k_ez_s = k_s * n_ez;
+      double u_ez = sin(w_s * 0.5) / sin(k_ez_s * 0.5);
+      s->coef[B200FDTD_STM_C_EZX][k]   = ns_coef1(b_ez_x);
+      s->coef[B200FDTD_STM_C_EZXLX][k] = u_ez * z_ez / (1 + b_ez_x);
+      s->coef[B200FDTD_STM_C_EZY][k]   = ns_coef1(b_ez_y);
+      s->coef[B200FDTD_STM_C_EZYLY][k] = u_ez * z_ez / (1.0 + b_ez_x);   /* b_ez_x: upstream quirk, line 287 */
+
+      double z_hx = sqrt(MU_0_S / eps_hx);
+      double n_hx = sqrt(eps_hx / EPSILON_0_S);
+      double k_hx_s = k_s * n_hx;
+      double u_hx = sin(w_s * 0.5) / sin(k_hx_s * 0.5);
+      s->coef[B200FDTD_STM_C_HX][k]   = ns_coef1(b_hx_y);
+      s->coef[B200FDTD_STM_C_HXLY][k] = u_hx / z_hx / (1.0 + b_hx_y);
+
+      double z_hy = sqrt(MU_0_S / eps_hy);
+      double n_hy = sqrt(eps_hy / EPSILON_0_S);
+      double k_hy_s = k_s * n_hy;
+      double u_hy = sin(w_s * 0.5) / sin(k_hy_s * 0.5);
+      s->coef[B200FDTD_STM_C_HY][k]   = ns_coef1(b_hy_x);
+      s->coef[B200FDTD_STM_C_HYLX][k] = u_hy / z_hy / (1.0 + b_hy_x);
+
+      s->src[0][k] = ns_source_factor(eps_ez, w_s, k_s);      /* on Ezy, nsFdtdTM.c:73 */
+    }
+}
+
+static void build_ns_te(SplitSolver *s)                         /* nsFdtdTE.c:100-181: interior cells only */
+{
+  FieldInfo_S g = field_getFieldInfo_S();
+  double R = 1.0e-8, M = 2.0;
+  const double sig_max = -(M + 1.0) * EPSILON_0_S * C_0_S / g.N_PML * log(R);
+  double w_s = field_getOmega(), k_s = field_getK();
+  for (int i = 1; i < g.N_PX - 1; i++)
+    for (int j = 1; j < g.N_PY - 1; j++) {
+      int k = field_index(i, j);
+      double eps_ex = s->eps[0][k], eps_ey = s->eps[1][k], eps_hz = s->eps[2][k];
+      double sig_ex_y = sig_max * field_sigmaY(i + 0.5, j);
+      double sig_ey_x = sig_max * field_sigmaX(i, j + 0.5);
+      double sig_hz_x = sig_max * field_sigmaX(i + 0.5, j + 0.5);
+      double sig_hz_y = sig_max * field_sigmaY(i + 0.5, j + 0.5);
+      double a_ex_y = sig_ex_y / (2 * eps_ex);
+      double a_ey_x = sig_ey_x / (2 * eps_ey);
+      double a_hz_x = sig_hz_x / (2 * eps_hz);
+      double a_hz_y = sig_hz_y / (2 * eps_hz);
+      double b_ex_y = ns_beta(a_ex_y), b_ey_x = ns_beta(a_ey_x);
+      double b_hz_x = ns_beta(a_hz_x), b_hz_y = ns_beta(a_hz_y);
+
+      double z_hz = sqrt(MU_0_S / eps_hz);
+      double n_hz = sqrt(eps_hz / EPSILON_0_S);
+      double k_hz_s = k_s * n_hz;
+      double u_hz = sin(w_s * 0.5) / sin(k_hz_s * 0.5);
+      s->coef[B200FDTD_STE_C_HZX][k]   = ns_coef1(b_hz_x);
+      s->coef[B200FDTD_STE_C_HZXLX][k] = u_hz / z_hz / (1.0 + b_hz_x);
+      s->coef[B200FDTD_STE_C_HZY][k]   = ns_coef1(b_hz_y);
+      s->coef[B200FDTD_STE_C_HZYLY][k] = u_hz / z_hz / (1.0 + b_hz_y);
+
+      double z_ex = sqrt(MU_0_S / eps_ex);
+      double n_ex = sqrt(eps_ex / EPSILON_0_S);
+      double k_ex_s = k_s * n_ex;
+      double u_ex = sin(w_s * 0.5) / sin(k_ex_s * 0.5);
+      s->coef[B200FDTD_STE_C_EX][k]   = ns_coef1(b_ex_y);
+      s->coef[B200FDTD_STE_C_EXLY][k] = u_ex * z_ex / (1.0 + b_ex_y);
+
+      double z_ey = sqrt(MU_0_S / eps_ey);
+      double n_ey = sqrt(eps_ey / EPSILON_0_S);
+      double k_ey_s = k_s * n_ey;
+      double u_ey = sin(w_s * 0.5) / sin(k_ey_s * 0.5);
+      s->coef[B200FDTD_STE_C_EY][k]   = ns_coef1(b_ey_x);
+      s->coef[B200FDTD_STE_C_EYLX][k] = u_ey * z_ey / (1.0 + b_ey_x);
+
+      s->src[0][k] = ns_source_factor(eps_ex, w_s, k_s);      /* on Ex, nsFdtdTE.c:247-248 */
+      s->src[1][k] = ns_source_factor(eps_ey, w_s, k_s);      /* on Ey, nsFdtdTE.c:249-250 */
+    }
+}
+
+/* ---- init ------------------------------------------------------------------------ */
+static void free_host(SplitSolver *s)
+{
+  for (int m = 0; m < 3; m++) { free(s->eps[m]); s->eps[m] = NULL; }
+  for (int m = 0; m < 8; m++) { free(s->coef[m]); s->coef[m] = NULL; }
+  for (int m = 0; m < 2; m++) { free(s->src[m]); s->src[m] = NULL; }
+}
+
+/* host half of init(): permittivity maps, the eight coefficient arrays, source factors */
+static void build_host(SplitSolver *s)
+{
+  FieldInfo_S g = field_getFieldInfo_S();
+  const size_t n = (size_t)g.N_CELL;
+  free_host(s);
+  for (int m = 0; m < 3; m++) s->eps[m] = newDouble(g.N_CELL);
+  for (int m = 0; m < 8; m++) s->coef[m] = newDouble(g.N_CELL);
+  for (int m = 0; m < 2; m++) s->src[m] = newDouble(g.N_CELL);
+
+  /* permittivity maps (fdtdTM.c:209-211, fdtdTE.c:206-208, nsFdtdTM.c:241-243,
+   * nsFdtdTE.c:117-119).  NS TE evaluates interior cells only; its ring stays 0. */
+  if (is_tm(s)) {
+    mpifdtd_fill_eps(s->eps[0], 0, 0, D_XY);
+    mpifdtd_fill_eps(s->eps[1], 0, 0.5, D_Y);
+    mpifdtd_fill_eps(s->eps[2], 0.5, 0, D_X);
+  } else {
+    mpifdtd_fill_eps(s->eps[0], 0.5, 0, D_Y);
+    mpifdtd_fill_eps(s->eps[1], 0, 0.5, D_X);
+    if (s->kind == B200FDTD_NS_TE) {
+      mpifdtd_fill_eps(s->eps[2], 0.5, 0.5, D_XY);
+      for (int m = 0; m < 3; m++)
+        for (int i = 0; i < g.N_PX; i++)
+          for (int j = 0; j < g.N_PY; j++)
+            if (i == 0 || j == 0 || i == g.N_PX - 1 || j == g.N_PY - 1)
+              s->eps[m][field_index(i, j)] = 0;
+    } else {                                                  /* 0.5*(D_X + D_Y), fdtdTE.c:208 */
+      double *tmp = newDouble(g.N_CELL);
+      mpifdtd_fill_eps(s->eps[2], 0.5, 0.5, D_X);
+      mpifdtd_fill_eps(tmp, 0.5, 0.5, D_Y);
+      for (size_t k = 0; k < n; k++) s->eps[2][k] = 0.5 * (s->eps[2][k] + tmp[k]);
+      free(tmp);
+    }
+  }
+  switch (s->kind) {
+  case B200FDTD_TM:    build_plain_tm(s); break;
+  case B200FDTD_TE:    build_plain_te(s); break;
+  case B200FDTD_NS_TM: build_ns_tm(s); break;
+  default:             build_ns_te(s); break;
+  }
+}
+
+static void solver_init(SplitSolver *s)
+{
+  FieldInfo_S g = field_getFieldInfo_S();
+  const size_t n = (size_t)g.N_CELL;
+  build_host(s);
+
+  b200fdtd_grid grid;
+  memset(&grid, 0, sizeof grid);
+  grid.kind = s->kind;
+  grid.n_px = g.N_PX;  grid.n_py = g.N_PY;  grid.n_pml = g.N_PML;
+  grid.j0 = 0;         grid.nj = g.N_PY;
+  grid.i_lo = 1;       grid.i_hi = g.N_PX - 2;
+  grid.j_lo = 1;       grid.j_hi = g.N_PY - 2;
+  grid.device = -1;
+  grid.mu0 = MU_0_S;
+  die_on(b200fdtd_create(&grid, &s->engine), "b200fdtd_create");
+  for (int m = 0; m < 8; m++)
+    die_on(b200fdtd_set_dense(s->engine, m, s->coef[m]), "b200fdtd_set_dense");
+  die_on(b200fdtd_set_dense(s->engine, B200FDTD_DENSE_SRC0, s->src[0]), "b200fdtd_set_dense(src0)");
+  die_on(b200fdtd_set_dense(s->engine, B200FDTD_DENSE_SRC1, s->src[1]), "b200fdtd_set_dense(src1)");
+  for (int m = 0; m < 5; m++)
+    die_on(b200fdtd_host_alloc((void **)&s->mirror[m], sizeof(dcomplex) * n), "host_alloc(mirror)");
+}
+
+/* ---- update ------------------------------------------------------------------------ */
+static void fill_cw(b200fdtd_cw *c, int ns, double gap_x, double gap_y, double dot)
+{
+  double time = field_getTime(), w_s = field_getOmega(), k_s = field_getK();
+  double rad = field_getWaveAngle() * M_PI / 180.0;
+  c->enabled = 1;
+  c->two_term = 1;
+  c->gap_x = gap_x;  c->gap_y = gap_y;
+  c->ks_cos = cos(rad) * k_s;
+  c->ks_sin = sin(rad) * k_s;
+  if (ns) {                                  /* field.c:160,174 */
+    c->scale = field_getRayCoef() * dot;
+    c->phase_a = w_s * (time + 1.0);
+    c->phase_b = w_s * (time);
+  } else {                                   /* field.c:184,193 */
+    c->scale = field_getRayCoef();
+    c->phase_a = w_s * (time + 0.5);
+    c->phase_b = w_s * (time - 0.5);
+  }
+}
+
+void mpifdtd_split_step_args(int kind, b200fdtd_step_args *a)
+{
+  memset(a, 0, sizeof *a);
+  a->time = field_getTime();
+  a->ray_coef = field_getRayCoef();
+  switch (kind) {
+  case B200FDTD_TM:                                           /* fdtdTM.c:294 */
+    fill_cw(&a->cw[0], 0, 0.0, 0.0, 1.0);
+    break;
+  case B200FDTD_TE:                                           /* fdtdTE.c:285 */
+    fill_cw(&a->cw[1], 0, 0.0, 0.5, 1.0);
+    break;
+  case B200FDTD_NS_TM:                                        /* nsFdtdTM.c:73 */
+    fill_cw(&a->cw[0], 1, 0, 0, 1.0);
+    break;
+  default: {                                                  /* nsFdtdTE.c:243-250 */
+    WaveInfo_S w = field_getWaveInfo_S();
+    double co = cos((w.Angle_deg + 90) * M_PI / 180.0);
+    double si = sin((w.Angle_deg + 90) * M_PI / 180.0);
+    if (co != 0.0) fill_cw(&a->cw[0], 1, 0, 0.5, co);
+    if (si != 0.0) fill_cw(&a->cw[1], 1, 0, 0.5, si);
+    break;
+  }
+  }
+  if (kind == B200FDTD_NS_TM || kind == B200FDTD_NS_TE) {     /* nsFdtdTM.c:115-117 */
+    double k_s = field_getK();
+    double r = 1.0 / 6.0 + k_s * k_s / 180.0 - pow(k_s, 4) / 23040;
+    a->ns_r2 = r / 2.0;
+  }
+}
+
+static void solver_update(SplitSolver *s)
+{
+  b200fdtd_step_args a;
+  mpifdtd_split_step_args(s->kind, &a);
+  die_on(b200fdtd_step(s->engine, &a), "b200fdtd_step");
+}
+
+/* ---- getters / reset / finish ------------------------------------------------------ */
+static dcomplex *solver_field(SplitSolver *s, int slot)
+{
+  if (s->engine == NULL) return NULL;
+  die_on(b200fdtd_get_field(s->engine, slot, (double *)s->mirror[slot]), "b200fdtd_get_field");
+  return s->mirror[slot];
+}
+
+static void solver_reset(SplitSolver *s)
+{
+  if (s->engine == NULL) return;
+  /* validation-circle dump of the drawn field (fdtdTM.c:154-160, fdtdTE.c:273-278,
+   * nsFdtdTM.c:159-164, nsFdtdTE.c:218-223) */
+  static const char *const stem[] = { "tm_%dnm.txt", "te_%dnm.txt", NULL, NULL, NULL, NULL,
+                                      "ns_tm_%dnm.txt", "ns_te_%dnm.txt" };
+  FieldInfo phys = field_getFieldInfo();
+  char name[128];
+  sprintf(name, stem[s->kind], phys.h_u_nm);
+  field_outputElliptic(name, solver_field(s, is_tm(s) ? B200FDTD_STM_EZ : B200FDTD_STE_EY));
+  die_on(b200fdtd_zero_state(s->engine), "b200fdtd_zero_state");
+}
+
+static void solver_finish(SplitSolver *s)
+{
+  if (s->engine == NULL) return;
+  solver_reset(s);
+  die_on(b200fdtd_destroy(s->engine), "b200fdtd_destroy");
+  s->engine = NULL;
+  free_host(s);
+  for (int m = 0; m < 5; m++) { b200fdtd_host_free(s->mirror[m]); s->mirror[m] = NULL; }
+}
+
+/* test hooks: host-built dense arrays and the engine of a split solver */
+void mpifdtd_split_prepare_host(int kind)
+{
+  SplitSolver *all[] = { &tm_plain, &te_plain, &tm_ns, &te_ns };
+  for (int n = 0; n < 4; n++)
+    if (all[n]->kind == kind) build_host(all[n]);
+}
+const double *mpifdtd_split_dense(int kind, int slot)
+{
+  SplitSolver *all[] = { &tm_plain, &te_plain, &tm_ns, &te_ns };
+  for (int n = 0; n < 4; n++)
+    if (all[n]->kind == kind)
+      return slot < 8 ? all[n]->coef[slot] : (slot < 10 ? all[n]->src[slot - 8] : all[n]->eps[slot - 10]);
+  return NULL;
+}
+b200fdtd_engine *mpifdtd_split_engine(int kind)
+{
+  SplitSolver *all[] = { &tm_plain, &te_plain, &tm_ns, &te_ns };
+  for (int n = 0; n < 4; n++)
+    if (all[n]->kind == kind) return all[n]->engine;
+  return NULL;
+}
+
+/* ---- exported entry points ----------------------------------------------------------- */
+#define SPLIT_ENTRY_POINTS(PREFIX, OBJ)                                              \
+  static void PREFIX##_update(void) { solver_update(&OBJ); }                         \
+  static void PREFIX##_init(void)   { solver_init(&OBJ); }                           \
+  static void PREFIX##_reset(void)  { solver_reset(&OBJ); }                          \
+  static void PREFIX##_finish(void) { solver_finish(&OBJ); }                         \
+  void (*PREFIX##_getUpdate(void))(void) { return PREFIX##_update; }                 \
+  void (*PREFIX##_getInit(void))(void)   { return PREFIX##_init; }                   \
+  void (*PREFIX##_getReset(void))(void)  { return PREFIX##_reset; }                  \
+  void (*PREFIX##_getFinish(void))(void) { return PREFIX##_finish; }
+
+SPLIT_ENTRY_POINTS(fdtdTM, tm_plain)
+double complex *fdtdTM_getHx(void)  { return solver_field(&tm_plain, B200FDTD_STM_HX); }
+double complex *fdtdTM_getHy(void)  { return solver_field(&tm_plain, B200FDTD_STM_HY); }
+double complex *fdtdTM_getEz(void)  { return solver_field(&tm_plain, B200FDTD_STM_EZ); }
+double complex *fdtdTM_getEzx(void) { return solver_field(&tm_plain, B200FDTD_STM_EZX); }
+double complex *fdtdTM_getEzy(void) { return solver_field(&tm_plain, B200FDTD_STM_EZY); }
+double *fdtdTM_getEps(void) { return tm_plain.eps[0]; }                    /* EPS_EZ */
+
+SPLIT_ENTRY_POINTS(fdtdTE, te_plain)
+double complex *fdtdTE_getEx(void)  { return solver_field(&te_plain, B200FDTD_STE_EX); }
+double complex *fdtdTE_getEy(void)  { return solver_field(&te_plain, B200FDTD_STE_EY); }
+double complex *fdtdTE_getHz(void)  { return solver_field(&te_plain, B200FDTD_STE_HZ); }
+double complex *fdtdTE_getHzx(void) { return solver_field(&te_plain, B200FDTD_STE_HZX); }
+double complex *fdtdTE_getHzy(void) { return solver_field(&te_plain, B200FDTD_STE_HZY); }
+double *fdtdTE_getEps(void) { return te_plain.eps[1]; }                    /* EPS_EY, fdtdTE.c:63-66 */
+
+SPLIT_ENTRY_POINTS(nsFdtdTM, tm_ns)
+double complex *nsFdtdTM_getHx(void)  { return solver_field(&tm_ns, B200FDTD_STM_HX); }
+double complex *nsFdtdTM_getHy(void)  { return solver_field(&tm_ns, B200FDTD_STM_HY); }
+double complex *nsFdtdTM_getEz(void)  { return solver_field(&tm_ns, B200FDTD_STM_EZ); }
+double complex *nsFdtdTM_getEzx(void) { return solver_field(&tm_ns, B200FDTD_STM_EZX); }
+double complex *nsFdtdTM_getEzy(void) { return solver_field(&tm_ns, B200FDTD_STM_EZY); }
+double *nsFdtdTM_getEps(void)  { return tm_ns.eps[0]; }
+double *nsFdtdTM_getEpsX(void) { return tm_ns.eps[1]; }                    /* EPS_HX */
+double *nsFdtdTM_getEpsY(void) { return tm_ns.eps[2]; }                    /* EPS_HY */
+double *nsFdtdTM_getEpsZ(void) { return tm_ns.eps[0]; }                    /* EPS_EZ */
+
+SPLIT_ENTRY_POINTS(nsFdtdTE, te_ns)
+double complex *nsFdtdTE_getEx(void)  { return solver_field(&te_ns, B200FDTD_STE_EX); }
+double complex *nsFdtdTE_getEy(void)  { return solver_field(&te_ns, B200FDTD_STE_EY); }
+double complex *nsFdtdTE_getHz(void)  { return solver_field(&te_ns, B200FDTD_STE_HZ); }
+double complex *nsFdtdTE_getHzx(void) { return solver_field(&te_ns, B200FDTD_STE_HZX); }
+double complex *nsFdtdTE_getHzy(void) { return solver_field(&te_ns, B200FDTD_STE_HZY); }
+double *nsFdtdTE_getEps(void)  { return te_ns.eps[1]; }                    /* EPS_EY */
+double *nsFdtdTE_getEpsX(void) { return te_ns.eps[0]; }
+double *nsFdtdTE_getEpsY(void) { return te_ns.eps[1]; }
+double *nsFdtdTE_getEpsZ(void) { return te_ns.eps[2]; }
+
+/* solver.h:7-20: the struct upstream declares and returns zero-filled (its assignments are
+ * commented out, nsFdtdTM.c:45-61).  Kept for link compatibility, filled in for real. */
+typedef struct Solver {
+  void (*update)(void), (*finish)(void), (*init)(void), (*reset)(void);
+  dcomplex *(*getDataX)(void), *(*getDataY)(void), *(*getDataZ)(void);
+  dcomplex *(*getEpsX)(void), *(*getEpsY)(void), *(*getEpsZ)(void);
+} Solver;
+Solver *nsFdtdTM_getSolver(void)
+{
+  static Solver solver;
+  solver.update = nsFdtdTM_update;  solver.finish = nsFdtdTM_finish;
+  solver.init = nsFdtdTM_init;      solver.reset = nsFdtdTM_reset;
+  solver.getDataX = nsFdtdTM_getHx; solver.getDataY = nsFdtdTM_getHy; solver.getDataZ = nsFdtdTM_getEz;
+  return &solver;
+}
+Solver *nsFdtdTE_getSolver(void)
+{
+  static Solver solver;
+  solver.update = nsFdtdTE_update;  solver.finish = nsFdtdTE_finish;
+  solver.init = nsFdtdTE_init;      solver.reset = nsFdtdTE_reset;
+  solver.getDataX = nsFdtdTE_getEx; solver.getDataY = nsFdtdTE_getEy; solver.getDataZ = nsFdtdTE_getHz;
+  return &solver;
+}

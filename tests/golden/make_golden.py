@@ -132,3 +132,32 @@ if __name__ == "__main__":
         fft_fixture()
     if "runs" in which:
         run_fixtures()
+
+
+def split_fixtures():
+    """Split-field solvers (ids 0, 1, 6, 7): dense coefficients, eps maps and field
+    snapshots of a Mie-cylinder run (CW source, soft start)."""
+    fields = {0: ["Ez", "Ezx", "Ezy", "Hx", "Hy"], 1: ["Hz", "Hzx", "Hzy", "Ex", "Ey"],
+              6: ["Ez", "Ezx", "Ezy", "Hx", "Hy"], 7: ["Hz", "Hzx", "Hzy", "Ex", "Ey"]}
+    coefs = {0: ["C_EZX", "C_EZXLX", "C_EZY", "C_EZYLY", "C_HX", "C_HXLY", "C_HY", "C_HYLX", "EPS_EZ", "EPS_HX", "EPS_HY"],
+             1: ["C_EX", "C_EXLY", "C_EY", "C_EYLX", "C_HZX", "C_HZXLX", "C_HZY", "C_HZYLY", "EPS_EX", "EPS_EY", "EPS_HZ"]}
+    coefs[6], coefs[7] = coefs[0], coefs[1]
+    npx, npy, hu, steps, lam, angle = 88, 100, 20, 300, 500, 30
+    for kind in (0, 1, 6, 7):
+        sim = reflib.RefSim("MIE_CYLINDER", kind, npx, npy, steps=steps, h_u_nm=hu, lambda_nm=lam, angle_deg=angle)
+        out = {"meta": np.array([npx, npy, hu, steps, lam, angle, kind])}
+        for c in coefs[kind]:
+            out[c] = sim.coef(c)
+        sim.step(steps // 2)
+        for f in fields[kind]:
+            out["mid_" + f] = sim.field(f)
+        sim.step(steps - steps // 2)
+        for f in fields[kind]:
+            out["end_" + f] = sim.field(f)
+        sim.finish()
+        np.savez_compressed(os.path.join(HERE, "split_kind%d.npz" % kind), **out)
+        print("split kind", kind, "max |field|", max(float(np.abs(out["end_" + f]).max()) for f in fields[kind]))
+
+
+if __name__ == "__main__" and "split" in sys.argv[1:]:
+    split_fixtures()

@@ -1,0 +1,54 @@
+"""Split-field solvers on the GPU (ids 0 TM, 1 TE: Yee + Berenger PML; 6 NS_TM, 7 NS_TE:
+non-standard FDTD) against field snapshots recorded from the unmodified reference
+(tests/golden/split_kind*.npz) and, when it travelled, against the reference itself.
+Tolerance: fields <= 1e-12 (max-abs-diff / max-abs-ref)."""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import GOLDEN, TOL_FIELD, bit_equal, rel_err
+from mpifdtd_b200 import binding as B
+
+pytestmark = pytest.mark.gpu
+FIELDS = {0: ["Ez", "Ezx", "Ezy", "Hx", "Hy"], 1: ["Hz", "Hzx", "Hzy", "Ex", "Ey"],
+          6: ["Ez", "Ezx", "Ezy", "Hx", "Hy"], 7: ["Hz", "Hzx", "Hzy", "Ex", "Ey"]}
+DUMP = {0: "tm_%dnm.txt", 1: "te_%dnm.txt", 6: "ns_tm_%dnm.txt", 7: "ns_te_%dnm.txt"}
+
+
+@pytest.mark.parametrize("kind", [0, 1, 6, 7])
+def test_split_solver_matches_reference_golden(plugin_lib, kind, in_tmp_cwd):
+    g = np.load(os.path.join(GOLDEN, "split_kind%d.npz" % kind))
+    npx, npy, hu, steps, lam, angle = (int(v) for v in g["meta"][:6])
+    gpu = B.Plugin("MIE_CYLINDER", kind, npx, npy, steps=steps, h_u_nm=hu, lambda_nm=lam, angle_deg=angle)
+    eps_name = {0: "EPS_EZ", 1: "EPS_EY", 6: "EPS_EZ", 7: "EPS_EY"}[kind]
+    assert bit_equal(gpu.eps(), g[eps_name])
+    gpu.step(steps // 2)
+    for f in FIELDS[kind]:
+        assert rel_err(gpu.field(f), g["mid_" + f]) <= TOL_FIELD, ("mid", f)
+    gpu.step(steps - steps // 2)
+    for f in FIELDS[kind]:
+        assert rel_err(gpu.field(f), g["end_" + f]) <= TOL_FIELD, ("end", f)
+    assert np.abs(gpu.field(FIELDS[kind][0])).max() > 0.1
+    gpu.finish()                                   # reset(): validation-circle dump, then free
+    lines = open(DUMP[kind] % hu).read().split("\n")
+    assert len([l for l in lines if l.strip()]) == 181
+
+
+@pytest.mark.parametrize("kind,model", [(0, "ZIGZAG"), (1, "LAYER"), (6, "MORPHO_SCALE"), (7, "MIE_CYLINDER")])
+def test_split_solver_vs_live_reference(plugin_lib, kind, model, in_tmp_cwd):
+    from oracle import reflib
+    if not reflib.available():
+        pytest.skip("oracle/_ref/libref.so did not travel with this snapshot")
+    npx, npy, steps = 120, 200, 260
+    cwd = os.getcwd()
+    ref = reflib.RefSim(model, kind, npx, npy, steps=steps, lambda_nm=633, angle_deg=15)
+    ref.run()
+    want = {f: ref.field(f) for f in FIELDS[kind]}
+    ref.finish()
+    os.chdir(cwd)
+    gpu = B.Plugin(model, kind, npx, npy, steps=steps, lambda_nm=633, angle_deg=15)
+    gpu.run()
+    for f in FIELDS[kind]:
+        assert rel_err(gpu.field(f), want[f]) <= TOL_FIELD, f
+    gpu.finish()
