@@ -40,7 +40,7 @@ def test_split_solver_vs_live_reference(plugin_lib, kind, model, in_tmp_cwd):
     from oracle import reflib
     if not reflib.available():
         pytest.skip("oracle/_ref/libref.so did not travel with this snapshot")
-    npx, npy, steps = 120, 200, 260
+    npx, npy, steps = 200, 220, 260      # the validation circle (1.2 lambda = 76 cells) must fit
     cwd = os.getcwd()
     ref = reflib.RefSim(model, kind, npx, npy, steps=steps, lambda_nm=633, angle_deg=15)
     ref.run()
