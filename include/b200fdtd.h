@@ -236,6 +236,9 @@ int b200fdtd_set_stream(b200fdtd_engine *e, void *cuda_stream);
 /* getters: device slab -> host [n_px][n_py] complex array, columns [j0, j0+nj) */
 int b200fdtd_get_field(b200fdtd_engine *e, int32_t slot, double *host_complex);
 int b200fdtd_set_field(b200fdtd_engine *e, int32_t slot, const double *host_complex);
+/* general form: element (i = 0, j = j0) goes to host_first_cell, rows are ld_complex complex
+ * values apart (e.g. the (N+2)-wide ghost-ring mirrors of the MPI-variant solvers) */
+int b200fdtd_get_field_ld(b200fdtd_engine *e, int32_t slot, double *host_first_cell, int64_t ld_complex);
 /* slab-shaped variant: host array is [n_px][nj] complex (what one rank mirrors) */
 int b200fdtd_get_field_slab(b200fdtd_engine *e, int32_t slot, double *slab_complex);
 int b200fdtd_zero_state(b200fdtd_engine *e);        /* the memsets of reset(), fdtdTM_upml.c:98-113 */

@@ -163,6 +163,13 @@ MPIFDTD_DECLARE_SOLVER(fdtdTE, Ex, Ey, Hz)                    /* fdtdTE.h:5-17  
 MPIFDTD_DECLARE_SOLVER(nsFdtdTM, Hx, Hy, Ez)                  /* nsFdtdTM.h:5-19    */
 MPIFDTD_DECLARE_SOLVER(nsFdtdTE, Ex, Ey, Hz)                  /* nsFdtdTE.h:5-19    */
 
+/* sub-domain sizes of the MPI-variant solvers (mpiTM_UPML.h:14-18); one rank owns the
+ * whole grid here, so they report N and N+2 (ghost ring) */
+extern int mpi_fdtdTM_upml_getSubNx(void), mpi_fdtdTM_upml_getSubNy(void), mpi_fdtdTM_upml_getSubNpx(void);
+extern int mpi_fdtdTM_upml_getSubNpy(void), mpi_fdtdTM_upml_getSubNcell(void);
+extern int mpi_fdtdTE_upml_getSubNx(void), mpi_fdtdTE_upml_getSubNy(void), mpi_fdtdTE_upml_getSubNpx(void);
+extern int mpi_fdtdTE_upml_getSubNpy(void), mpi_fdtdTE_upml_getSubNcell(void);
+
 /* extra getters of the split-field solvers (fdtdTM.h:10-11, fdtdTE.h:12-13,
  * nsFdtdTM.h:11-19, nsFdtdTE.h:11-19) */
 extern double complex *fdtdTM_getEzx(void), *fdtdTM_getEzy(void);

@@ -183,7 +183,8 @@ def lib():
                  "fdtdTE_upml_getEx", "fdtdTE_upml_getEy", "fdtdTE_upml_getHz",
                  "fdtdTM_upml_getEps", "fdtdTE_upml_getEps"):
         getattr(L, name).restype = vp
-    for prefix, fields in (("fdtdTM", ("Hx", "Hy", "Ez", "Ezx", "Ezy")), ("fdtdTE", ("Ex", "Ey", "Hz", "Hzx", "Hzy")),
+    for prefix, fields in (("mpi_fdtdTM_upml", ("Hx", "Hy", "Ez")), ("mpi_fdtdTE_upml", ("Ex", "Ey", "Hz")),
+                           ("fdtdTM", ("Hx", "Hy", "Ez", "Ezx", "Ezy")), ("fdtdTE", ("Ex", "Ey", "Hz", "Hzx", "Hzy")),
                            ("nsFdtdTM", ("Hx", "Hy", "Ez", "Ezx", "Ezy")),
                            ("nsFdtdTE", ("Ex", "Ey", "Hz", "Hzx", "Hzy"))):
         for f in fields + ("Eps",):
@@ -218,6 +219,8 @@ class Plugin:
 
     GETTERS = {2: dict(Hx="fdtdTM_upml_getHx", Hy="fdtdTM_upml_getHy", Ez="fdtdTM_upml_getEz"),
                3: dict(Ex="fdtdTE_upml_getEx", Ey="fdtdTE_upml_getEy", Hz="fdtdTE_upml_getHz"),
+               4: {f: "mpi_fdtdTM_upml_get" + f for f in ("Hx", "Hy", "Ez")},
+               5: {f: "mpi_fdtdTE_upml_get" + f for f in ("Ex", "Ey", "Hz")},
                0: {f: "fdtdTM_get" + f for f in ("Hx", "Hy", "Ez", "Ezx", "Ezy")},
                1: {f: "fdtdTE_get" + f for f in ("Ex", "Ey", "Hz", "Hzx", "Hzy")},
                6: {f: "nsFdtdTM_get" + f for f in ("Hx", "Hy", "Ez", "Ezx", "Ezy")},
@@ -238,7 +241,7 @@ class Plugin:
         self.finished = False
 
     def engine_handle(self):
-        if self.solver in (2, 3):
+        if self.solver in (2, 3, 4, 5):
             return self.L.mpifdtd_upml_engine(self.solver)
         return self.L.mpifdtd_split_engine(self.solver)
 
@@ -255,13 +258,17 @@ class Plugin:
 
     SLOTS = {2: ["Ez", "Jz", "Dz", "Hx", "Mx", "Bx", "Hy", "My", "By"],
              3: ["Ex", "Jx", "Dx", "Ey", "Jy", "Dy", "Hz", "Mz", "Bz"]}
+    SLOTS[4], SLOTS[5] = SLOTS[2], SLOTS[3]
 
     def field(self, name):
         """The three public fields come through the reference's getters (borrowed host
         mirror); the auxiliary J/D/M/B arrays, which the reference keeps file-static,
-        through the engine's slot accessor."""
+        through the engine's slot accessor.  The MPI-variant ids hand out (N+2) x (N+2)
+        arrays with a ghost ring, like the reference."""
         if name in self.GETTERS[self.solver]:
             ptr = getattr(self.L, self.GETTERS[self.solver][name])()
+            if self.solver in (4, 5):
+                return _as_complex(ptr, self.n_px + 2, self.n_py + 2).copy()
             return _as_complex(ptr, self.n_px, self.n_py).copy()
         return self.any_field(self.SLOTS[self.solver].index(name))
 

@@ -441,6 +441,20 @@ int b200fdtd_get_field(b200fdtd_engine *e, int32_t slot, double *host)
   return B200FDTD_OK;
 }
 
+int b200fdtd_get_field_ld(b200fdtd_engine *e, int32_t slot, double *host, int64_t ld)
+{
+  if (!e || !host || slot < 0 || slot >= e->n_fields || ld < e->g.nj)
+    return b200_fail(B200FDTD_ERR_ARG, "bad field slot %d / leading dimension", slot);
+  int rc = select_device(e); if (rc) return rc;
+  rc = b200_refresh_h(e); if (rc) return rc;
+  const b200fdtd_grid &g = e->g;
+  B200_CUDA(cudaMemcpy2DAsync(host, sizeof(double2) * (size_t)ld,
+                              e->field[slot] + (size_t)e->pitch + B200_JOFF, sizeof(double2) * e->pitch,
+                              sizeof(double2) * g.nj, g.n_px, cudaMemcpyDeviceToHost, e->stream));
+  B200_CUDA(cudaStreamSynchronize(e->stream));
+  return B200FDTD_OK;
+}
+
 int b200fdtd_get_field_slab(b200fdtd_engine *e, int32_t slot, double *host)
 {
   if (!e || !host || slot < 0 || slot >= e->n_fields) return b200_fail(B200FDTD_ERR_ARG, "bad field slot %d", slot);

@@ -20,6 +20,7 @@ struct UpmlView {
   int j_base;                   // global j = j_base + c
   ConstDivisor mu0;             // MU_0_S and its rounded reciprocal
   b200fdtd_pulse pulse[2];
+  b200fdtd_cw cw[2];            // CW source of the MPI-variant kinds (mpiTM_UPML.c:337-374)
   long long point_k;            // layout offset of the opt-in point source, or -1
   double point_re, point_im;
 };
@@ -90,6 +91,17 @@ __device__ __forceinline__ double2 pulse_term(const b200fdtd_pulse &s, int i, in
   return make_double2(amp * cs, amp * sn);
 }
 
+// scatteredWave of the MPI solvers (mpiTM_UPML.c:366-370, mpiTE_UPML.c:270-279):
+// p += ray_coef*(eps0/eps - 1)*cexp(i(kr - w t)); i, j are GLOBAL indices.
+__device__ __forceinline__ double2 cw_eps_term(const b200fdtd_cw &s, int i, int j, double eps)
+{
+  const double kr = (i + s.gap_x) * s.ks_cos + (j + s.gap_y) * s.ks_sin;
+  double sn, cs;
+  sincos(kr - s.phase_a, &sn, &cs);
+  const double amp = s.scale * (1.0 / eps - 1.0);
+  return make_double2(amp * cs, amp * sn);
+}
+
 inline bool is_tm(int kind) { return kind == B200FDTD_TM_UPML || kind == B200FDTD_MPI_TM_UPML; }
 
 inline UpmlView make_view(const b200fdtd_engine *e, const b200fdtd_step_args *a)
@@ -112,6 +124,8 @@ inline UpmlView make_view(const b200fdtd_engine *e, const b200fdtd_step_args *a)
   v.mu0.r = 1.0 / e->g.mu0;
   v.pulse[0] = a->pulse[0];
   v.pulse[1] = a->pulse[1];
+  v.cw[0] = a->cw[0];
+  v.cw[1] = a->cw[1];
   v.point_k = -1;
   v.point_re = a->point.re;
   v.point_im = a->point.im;

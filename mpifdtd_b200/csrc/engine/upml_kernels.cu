@@ -125,6 +125,8 @@ __global__ void __launch_bounds__(kBlock) tm_upml_e_kernel(const UpmlView v)
 
   if (v.pulse[0].enabled && eps != 1.0)       // field.c:248
     ez = ez + pulse_term(v.pulse[0], r - 1, v.j_base + c, eps);
+  if (v.cw[0].enabled && eps != 1.0)          // mpiTM_UPML.c:370
+    ez = ez + cw_eps_term(v.cw[0], r - 1, v.j_base + c, eps);
   if ((long long)k == v.point_k)
     ez = ez + make_double2(v.point_re, v.point_im);
 
@@ -202,6 +204,8 @@ __global__ void __launch_bounds__(kBlock) te_upml_e_kernel(const UpmlView v)
     ex = ex + pulse_term(v.pulse[0], i, j, eps_x);
   if (v.pulse[1].enabled && eps_y != 1.0)     // fdtdTE_upml.c:188-189
     ey = ey + pulse_term(v.pulse[1], i, j, eps_y);
+  if (v.cw[0].enabled && eps_x != 1.0) ex = ex + cw_eps_term(v.cw[0], i, j, eps_x);
+  if (v.cw[1].enabled && eps_y != 1.0) ey = ey + cw_eps_term(v.cw[1], i, j, eps_y);   // mpiTE_UPML.c:278
   if ((long long)k == v.point_k)
     ex = ex + make_double2(v.point_re, v.point_im);
 

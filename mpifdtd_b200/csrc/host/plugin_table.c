@@ -6,8 +6,8 @@
  *     -> simulator_reset() | simulator_finish()
  *
  * A solver is described by one row of `solver_rows`; selecting it copies the row
- * into the active table.  Ids whose GPU kernels are not built yet keep the
- * reference's error convention: a message and exit(2).
+ * into the active table.  All eight solver ids of simulator.h:8-18 are served; an unknown
+ * id keeps the reference's error convention: a message and exit(2).
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -37,8 +37,8 @@ static const SolverRow solver_rows[] = {
   [TE_2D]      = ROW(fdtdTE, Ex, Ey, Hz, "TE mode \n", "TE", 1),
   [TM_UPML_2D] = ROW(fdtdTM_upml, Hx, Hy, Ez, "TM UPML mode \n", "TM_UPML", 2),
   [TE_UPML_2D] = ROW(fdtdTE_upml, Ex, Ey, Hz, "TE UPML mode \n", "TE_UPML", 1),
-  [MPI_TM_UPML_2D] = { NULL, NULL, NULL, NULL, NULL, NULL, NULL, NULL, NULL, 0, NULL },
-  [MPI_TE_UPML_2D] = { NULL, NULL, NULL, NULL, NULL, NULL, NULL, NULL, NULL, 0, NULL },
+  [MPI_TM_UPML_2D] = ROW(mpi_fdtdTM_upml, Hx, Hy, Ez, "MPI TM UPML mode \n", "MPI_TM_UPML", 2),
+  [MPI_TE_UPML_2D] = ROW(mpi_fdtdTE_upml, Ex, Ey, Hz, "MPI TE UPML mode \n", "MPI_TE_UPML", 1),
   [NS_TM_2D]   = ROW(nsFdtdTM, Hx, Hy, Ez, "NS TM mode \n", "NS_TM", 2),
   [NS_TE_2D]   = ROW(nsFdtdTE, Ex, Ey, Hz, "NS TE mode \n", "NS_TE", 1),
 };

@@ -39,10 +39,22 @@ typedef struct UpmlSolver {
   dcomplex *mirror[3];            /* pinned mirrors for the X, Y, Z getters        */
   int n_cell;
   int point_source;               /* opt-in, see mpifdtd_enablePointSource         */
+  double *eps_ringed;             /* MPI-variant ids: eps map inside its ghost ring */
 } UpmlSolver;
 
 static UpmlSolver tm_solver = { .kind = B200FDTD_TM_UPML };
 static UpmlSolver te_solver = { .kind = B200FDTD_TE_UPML };
+/* The "MPI" solver ids (mpiTM_UPML.c, mpiTE_UPML.c) run here as rank 0 of 1: same
+ * recurrences and coefficients, but E phase first, a CW source, every one of the N x N
+ * cells updated against a zero ghost ring, and (N+2) x (N+2) arrays behind the getters
+ * (mpiTM_UPML.c:196-217, 337-374, 674-716, 737-743).  Their per-step ntff() fills arrays
+ * the TM solver never writes out (the call is commented, mpiTM_UPML.c:240) and is not
+ * rebuilt; multi-GPU decomposition is the y-slab path of mpifdtd_b200/slab.py instead. */
+static UpmlSolver mpi_tm_solver = { .kind = B200FDTD_MPI_TM_UPML };
+static UpmlSolver mpi_te_solver = { .kind = B200FDTD_MPI_TE_UPML };
+
+static int is_mpi_kind(int kind) { return kind == B200FDTD_MPI_TM_UPML || kind == B200FDTD_MPI_TE_UPML; }
+static int is_tm_kind(int kind)  { return kind == B200FDTD_TM_UPML || kind == B200FDTD_MPI_TM_UPML; }
 static int point_source_requested;
 
 static void die_on(int rc, const char *what)
@@ -66,7 +78,7 @@ static void build_tables(const UpmlSolver *s, double *ti, double *tj)
   FieldInfo_S g = field_getFieldInfo_S();
   const double R = 1.0e-8, M = 2.0;
   const double eps = EPSILON_0_S, sig_z = 0;
-  if (s->kind == B200FDTD_TM_UPML) {
+  if (is_tm_kind(s->kind)) {
     const double sig_max = -(M + 1.0) * EPSILON_0_S * C_0_S / 2.0 / N_PML / cos(M_PI / 3) * log(R);
     for (int i = 0; i < g.N_PX; i++) {
       double sig_ez_x = sig_max * field_sigmaX(i, 0);
@@ -187,7 +199,10 @@ static void solver_init(UpmlSolver *s)
 {
   FieldInfo_S g = field_getFieldInfo_S();
   NTFFInfo box = field_getNTFFInfo();
-  const int tm = (s->kind == B200FDTD_TM_UPML);
+  const int tm = is_tm_kind(s->kind);
+  const int mpi = is_mpi_kind(s->kind);
+  const int ring = mpi ? 1 : 0;                               /* ghost ring of the getters' arrays */
+  const size_t sub_cells = (size_t)(g.N_PX + 2 * ring) * (size_t)(g.N_PY + 2 * ring);
   s->n_cell = g.N_CELL;
   s->point_source = point_source_requested;
 
@@ -198,6 +213,10 @@ static void solver_init(UpmlSolver *s)
   grid.j0 = 0;         grid.nj = g.N_PY;
   grid.i_lo = 1;       grid.i_hi = g.N_PX - 2;      /* fdtdTM_upml.c:158-159 */
   grid.j_lo = 1;       grid.j_hi = g.N_PY - 2;
+  if (mpi) {                                        /* local 1..SUB_N_PX-2 <-> global 0..N-1 */
+    grid.i_lo = 0;     grid.i_hi = g.N_PX - 1;
+    grid.j_lo = 0;     grid.j_hi = g.N_PY - 1;
+  }
   grid.device = -1;
   grid.mu0 = MU_0_S;
   die_on(b200fdtd_create(&grid, &s->engine), "b200fdtd_create");
@@ -225,7 +244,15 @@ static void solver_init(UpmlSolver *s)
   free(ti); free(tj);
 
   for (int m = 0; m < 3; m++)
-    die_on(b200fdtd_host_alloc((void **)&s->mirror[m], sizeof(dcomplex) * (size_t)g.N_CELL), "host_alloc(mirror)");
+    die_on(b200fdtd_host_alloc((void **)&s->mirror[m], sizeof(dcomplex) * sub_cells), "host_alloc(mirror)");
+  if (mpi) {                                        /* EPS array as the getter shows it: with the ring */
+    const int m = tm ? 0 : 1;                       /* TM: EPS_EZ, TE: EPS_EY (mpiTE_UPML.c:103-106) */
+    s->eps_ringed = newDouble((int)sub_cells);
+    for (int i = 0; i < g.N_PX; i++)
+      memcpy(s->eps_ringed + (size_t)(i + 1) * (g.N_PY + 2) + 1, s->eps[m] + (size_t)i * g.N_PY,
+             sizeof(double) * (size_t)g.N_PY);
+    return;                                         /* no NTFF plan for the MPI-variant ids */
+  }
 
   /* ntffT?_init: surface, history length = stepNum, bins kept = the part of
    * arraySize the far field reads (ntffTM.c:181: i < maxTime) */
@@ -269,6 +296,20 @@ void mpifdtd_upml_step_args(int kind, int point_source, b200fdtd_step_args *a)
   memset(a, 0, sizeof *a);
   a->time = field_getTime();
   a->ray_coef = field_getRayCoef();
+  if (is_mpi_kind(kind)) {
+    /* CW scattered wave, integer global coordinates, on Ez (TM) or on Ey only (TE):
+     * mpiTM_UPML.c:337-374, mpiTE_UPML.c:250-281 */
+    b200fdtd_cw *c = &a->cw[kind == B200FDTD_MPI_TM_UPML ? 0 : 1];
+    double k_s = field_getK();
+    double rad = field_getWaveAngle() * M_PI / 180;
+    c->enabled = 1;
+    c->two_term = 0;
+    c->scale = field_getRayCoef();
+    c->ks_cos = cos(rad) * k_s;
+    c->ks_sin = sin(rad) * k_s;
+    c->phase_a = field_getOmega() * field_getTime();
+    return;
+  }
   if (kind == B200FDTD_TM_UPML) {
     fill_pulse(&a->pulse[0], 0, 0, 1.0);                      /* fdtdTM_upml.c:63 */
   } else {
@@ -346,7 +387,8 @@ static void write_far_field(UpmlSolver *s)
 static void solver_reset(UpmlSolver *s)
 {
   if (s->engine == NULL) return;
-  write_far_field(s);
+  if (!is_mpi_kind(s->kind))                        /* mpiTM_UPML.c:219-232: reset only zeroes */
+    write_far_field(s);
   die_on(b200fdtd_zero_state(s->engine), "b200fdtd_zero_state");
 }
 
@@ -356,6 +398,7 @@ static void solver_finish(UpmlSolver *s)
   solver_reset(s);
   die_on(b200fdtd_destroy(s->engine), "b200fdtd_destroy");
   s->engine = NULL;
+  free(s->eps_ringed); s->eps_ringed = NULL;
   for (int m = 0; m < 3; m++) {
     b200fdtd_host_free(s->eps[m]);    s->eps[m] = NULL;
     b200fdtd_host_free(s->mirror[m]); s->mirror[m] = NULL;
@@ -365,6 +408,12 @@ static void solver_finish(UpmlSolver *s)
 static dcomplex *solver_field(UpmlSolver *s, int mirror, int slot)
 {
   if (s->engine == NULL) return NULL;                         /* upstream returns its NULL static */
+  if (is_mpi_kind(s->kind)) {                                 /* (N+2) x (N+2) with a zero ring */
+    FieldInfo_S g = field_getFieldInfo_S();
+    double *first = (double *)(s->mirror[mirror] + (size_t)(g.N_PY + 2) + 1);
+    die_on(b200fdtd_get_field_ld(s->engine, slot, first, g.N_PY + 2), "b200fdtd_get_field_ld");
+    return s->mirror[mirror];
+  }
   die_on(b200fdtd_get_field(s->engine, slot, (double *)s->mirror[mirror]), "b200fdtd_get_field");
   return s->mirror[mirror];
 }
@@ -396,9 +445,51 @@ double complex *fdtdTE_upml_getEy(void) { return solver_field(&te_solver, 1, B20
 double complex *fdtdTE_upml_getHz(void) { return solver_field(&te_solver, 2, B200FDTD_TE_HZ); }
 double *fdtdTE_upml_getEps(void) { return te_solver.eps[0]; }              /* EPS_EX, fdtdTE_upml.c:93-96 */
 
+/* ---- the MPI-variant ids (mpiTM_UPML.h:5-18, mpiTE_UPML.h) -------------------------- */
+static void mtm_update(void) { solver_update(&mpi_tm_solver); }
+static void mtm_init(void)   { solver_init(&mpi_tm_solver); }
+static void mtm_reset(void)  { solver_reset(&mpi_tm_solver); }
+static void mtm_finish(void) { solver_finish(&mpi_tm_solver); }
+void (*mpi_fdtdTM_upml_getUpdate(void))(void) { return mtm_update; }
+void (*mpi_fdtdTM_upml_getInit(void))(void)   { return mtm_init; }
+void (*mpi_fdtdTM_upml_getReset(void))(void)  { return mtm_reset; }
+void (*mpi_fdtdTM_upml_getFinish(void))(void) { return mtm_finish; }
+double complex *mpi_fdtdTM_upml_getHx(void) { return solver_field(&mpi_tm_solver, 0, B200FDTD_TM_HX); }
+double complex *mpi_fdtdTM_upml_getHy(void) { return solver_field(&mpi_tm_solver, 1, B200FDTD_TM_HY); }
+double complex *mpi_fdtdTM_upml_getEz(void) { return solver_field(&mpi_tm_solver, 2, B200FDTD_TM_EZ); }
+double *mpi_fdtdTM_upml_getEps(void) { return mpi_tm_solver.eps_ringed; }
+int mpi_fdtdTM_upml_getSubNx(void)    { return N_PX; }
+int mpi_fdtdTM_upml_getSubNy(void)    { return N_PY; }
+int mpi_fdtdTM_upml_getSubNpx(void)   { return N_PX + 2; }
+int mpi_fdtdTM_upml_getSubNpy(void)   { return N_PY + 2; }
+int mpi_fdtdTM_upml_getSubNcell(void) { return (N_PX + 2) * (N_PY + 2); }
+
+static void mte_update(void) { solver_update(&mpi_te_solver); }
+static void mte_init(void)   { solver_init(&mpi_te_solver); }
+static void mte_reset(void)  { solver_reset(&mpi_te_solver); }
+static void mte_finish(void) { solver_finish(&mpi_te_solver); }
+void (*mpi_fdtdTE_upml_getUpdate(void))(void) { return mte_update; }
+void (*mpi_fdtdTE_upml_getInit(void))(void)   { return mte_init; }
+void (*mpi_fdtdTE_upml_getReset(void))(void)  { return mte_reset; }
+void (*mpi_fdtdTE_upml_getFinish(void))(void) { return mte_finish; }
+double complex *mpi_fdtdTE_upml_getEx(void) { return solver_field(&mpi_te_solver, 0, B200FDTD_TE_EX); }
+double complex *mpi_fdtdTE_upml_getEy(void) { return solver_field(&mpi_te_solver, 1, B200FDTD_TE_EY); }
+double complex *mpi_fdtdTE_upml_getHz(void) { return solver_field(&mpi_te_solver, 2, B200FDTD_TE_HZ); }
+double *mpi_fdtdTE_upml_getEps(void) { return mpi_te_solver.eps_ringed; }
+int mpi_fdtdTE_upml_getSubNx(void)    { return N_PX; }
+int mpi_fdtdTE_upml_getSubNy(void)    { return N_PY; }
+int mpi_fdtdTE_upml_getSubNpx(void)   { return N_PX + 2; }
+int mpi_fdtdTE_upml_getSubNpy(void)   { return N_PY + 2; }
+int mpi_fdtdTE_upml_getSubNcell(void) { return (N_PX + 2) * (N_PY + 2); }
+
 /* engine handle of the active serial UPML solver, for harnesses that want device
  * timers or the U/W arrays (not part of the reference surface) */
 b200fdtd_engine *mpifdtd_upml_engine(int kind)
 {
-  return kind == B200FDTD_TM_UPML ? tm_solver.engine : te_solver.engine;
+  switch (kind) {
+  case B200FDTD_TM_UPML:     return tm_solver.engine;
+  case B200FDTD_TE_UPML:     return te_solver.engine;
+  case B200FDTD_MPI_TM_UPML: return mpi_tm_solver.engine;
+  default:                   return mpi_te_solver.engine;
+  }
 }

@@ -27,11 +27,12 @@ def declared_functions(header):
 def test_engine_header_symbols_exported(plugin_lib):
     missing = [n for n in sorted(declared_functions("b200fdtd.h")) if not hasattr(plugin_lib, n)]
     assert not missing, missing
-    assert plugin_lib.b200fdtd_abi_version() == 1
+    assert plugin_lib.b200fdtd_abi_version() == 2
 
 
-# solver families whose GPU kernels exist in this build
-BUILT_PREFIXES = ("fdtdTM_upml", "fdtdTE_upml")
+# solver families whose GPU kernels exist in this build: all eight ids of simulator.h:8-18
+BUILT_PREFIXES = ("fdtdTM_upml", "fdtdTE_upml", "mpi_fdtdTM_upml", "mpi_fdtdTE_upml", "fdtdTM", "fdtdTE",
+                  "nsFdtdTM", "nsFdtdTE")
 
 
 def test_plugin_header_symbols_exported(plugin_lib):
@@ -41,7 +42,12 @@ def test_plugin_header_symbols_exported(plugin_lib):
     for prefix, a, b, c in re.findall(r"MPIFDTD_DECLARE_SOLVER\((\w+), (\w+), (\w+), (\w+)\)", text):
         if prefix in BUILT_PREFIXES:
             names |= {"%s_get%s" % (prefix, s) for s in ("Update", "Finish", "Reset", "Init", a, b, c, "Eps")}
-    names -= {"MPIFDTD_DECLARE_SOLVER", "void"}
+    names -= {"MPIFDTD_DECLARE_SOLVER", "void", "struct"}
+    names |= {"fdtdTM_getEzx", "fdtdTM_getEzy", "fdtdTE_getHzx", "fdtdTE_getHzy", "nsFdtdTM_getEzx",
+              "nsFdtdTM_getEzy", "nsFdtdTE_getHzx", "nsFdtdTE_getHzy", "nsFdtdTM_getEpsX", "nsFdtdTM_getEpsY",
+              "nsFdtdTM_getEpsZ", "nsFdtdTE_getEpsX", "nsFdtdTE_getEpsY", "nsFdtdTE_getEpsZ",
+              "nsFdtdTM_getSolver", "nsFdtdTE_getSolver"}
+    names |= {"mpi_fdtd%s_upml_getSub%s" % (m, w) for m in ("TM", "TE") for w in ("Nx", "Ny", "Npx", "Npy", "Ncell")}
     missing = [n for n in sorted(names) if not hasattr(plugin_lib, n)]
     assert not missing, missing
     for g in ("N_X", "N_Y", "N_CELL", "N_PML", "N_PX", "N_PY"):
@@ -62,7 +68,7 @@ def test_bad_arguments_are_rejected(plugin_lib):
     h = C.c_void_p()
     bad = B.Grid(2, 2, 64, 10, 0, 64, 1, 62, 1, 62, -1, 0, B.MU_0_S)
     assert plugin_lib.b200fdtd_create(C.byref(bad), C.byref(h)) == 1          # ERR_ARG
-    unsupported = B.Grid(9, 64, 64, 10, 0, 64, 1, 62, 1, 62, -1, 0, B.MU_0_S)
+    unsupported = B.Grid(9, 64, 64, 10, 0, 64, 1, 62, 1, 62, -1, 0, B.MU_0_S)     # no such solver id
     assert plugin_lib.b200fdtd_create(C.byref(unsupported), C.byref(h)) == 1
     assert plugin_lib.b200fdtd_sync(None) == 1
 

@@ -52,3 +52,43 @@ def test_split_solver_vs_live_reference(plugin_lib, kind, model, in_tmp_cwd):
     for f in FIELDS[kind]:
         assert rel_err(gpu.field(f), want[f]) <= TOL_FIELD, f
     gpu.finish()
+
+
+# ---------------------------------------------------------------- MPI-variant ids (4, 5)
+MPI_FIELDS = {4: ["Ez", "Hx", "Hy", "Jz", "Dz", "Mx", "Bx", "My", "By"],
+              5: ["Ex", "Ey", "Hz", "Jx", "Dx", "Jy", "Dy", "Mz", "Bz"]}
+
+
+@pytest.mark.parametrize("kind,model", [(4, "MIE_CYLINDER"), (5, "MIE_CYLINDER"), (4, "ZIGZAG"), (5, "LAYER")])
+def test_mpi_variant_solver_vs_live_reference(plugin_lib, kind, model, in_tmp_cwd):
+    """Solver ids 4/5 as rank 0 of 1: E phase first, CW source, all N x N cells updated,
+    (N+2) x (N+2) arrays with a ghost ring behind the getters (mpiTM_UPML.c:196-217)."""
+    from oracle import reflib
+    if not reflib.available():
+        pytest.skip("oracle/_ref/libref.so did not travel with this snapshot")
+    npx, npy, steps = 130, 150, 300
+    cwd = os.getcwd()
+    ref = reflib.RefSim(model, kind, npx, npy, steps=steps, angle_deg=25)
+    ref.run()
+    sub = (npx + 2) * (npy + 2)
+    want = {f: ref.carray(f, sub).reshape(npx + 2, npy + 2) for f in MPI_FIELDS[kind]}
+    eps_name = "EPS_EZ" if kind == 4 else "EPS_EY"
+    want_eps = ref.darray(eps_name, sub).reshape(npx + 2, npy + 2)
+    os.chdir(cwd)          # (the reference's finish() for these ids calls MPI_Finalize and frees; not needed)
+    gpu = B.Plugin(model, kind, npx, npy, steps=steps, angle_deg=25)
+    L = gpu.L
+    assert (L.mpi_fdtdTM_upml_getSubNpx(), L.mpi_fdtdTM_upml_getSubNcell()) == (npx + 2, sub)
+    ptr = L.simulator_getEps()
+    import ctypes as C
+    mine_eps = np.frombuffer((C.c_double * sub).from_address(ptr), dtype=np.float64).reshape(npx + 2, npy + 2)
+    assert bit_equal(mine_eps[1:-1, 1:-1], want_eps[1:-1, 1:-1])
+    gpu.run()
+    for f in MPI_FIELDS[kind][:3]:
+        got = gpu.field(f)
+        assert got.shape == (npx + 2, npy + 2)
+        assert np.all(got[0, :] == 0) and np.all(got[:, -1] == 0)
+        assert rel_err(got, want[f]) <= TOL_FIELD, f
+    for slot, f in enumerate(gpu.SLOTS[kind]):
+        assert rel_err(gpu.any_field(slot), want[f][1:-1, 1:-1]) <= TOL_FIELD, f
+    assert np.abs(want[MPI_FIELDS[kind][0]]).max() > 1e-3
+    gpu.finish()
