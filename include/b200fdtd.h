@@ -254,6 +254,19 @@ int b200fdtd_ntff_uw_device(b200fdtd_engine *e, void **dev_ptr, uint64_t *n_doub
 /* out[(lambda-lambda_first)*n_angles + ang], the table ntff_outputEnormBin writes */
 int b200fdtd_ntff_spectrum(b200fdtd_engine *e, const b200fdtd_spectrum_args *args, double *out);
 
+/* One-shot frequency-domain surface integral, ntffTM_Frequency (ntffTM.c:72-158): for each
+ * direction a, Nz, Lx, Ly = sum over the surface of (tangential H or E) * cexp(i k r^.r2).
+ * Works on the current device fields of any TM-type kind (UPML, Berenger, NS).  The caller
+ * finishes with coef*(Z0*Nz + Lphi)*sqrt(h_u) on the host (ntffTM.c:82,155-156).
+ * out: [3][n_angles] complex (Nz, Lx, Ly). */
+typedef struct b200fdtd_freq_args {
+  int32_t top, bottom, left, right, cx, cy;
+  int32_t n_angles, reserved;
+  double k;                        /* field_getK()                                     */
+  const double *cos_a, *sin_a;     /* host [n_angles]: cos/sin(ang*pi/180), host libm  */
+} b200fdtd_freq_args;
+int b200fdtd_ntff_frequency(b200fdtd_engine *e, const b200fdtd_freq_args *args, double *out);
+
 /* ---- tuning switches ------------------------------------------------------ */
 enum {
   B200FDTD_OPT_FUSED = 1,     /* 1: b200fdtd_step uses the one-pass H+E kernel (default for the

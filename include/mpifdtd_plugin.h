@@ -189,6 +189,11 @@ extern struct Solver *nsFdtdTE_getSolver(void);
 extern void ntff_outputEnormTxt(double **e_norm, const char *file_name);  /* ntff.c:6  */
 extern void ntff_outputEnormBin(double **e_norm, const char *file_name);  /* ntff.c:21 */
 
+/* One-shot frequency-domain far field of the active TM-type solver (ids 0, 2, 4, 6):
+ * the surface integral of ntffTM_Frequency (ntffTM.c:72-158) evaluated on the GPU over the
+ * solver's current fields.  result[360] as the reference's resultEz. */
+extern int mpifdtd_ntffFrequency(int solver_id, double complex result[360]);
+
 /* ---- config.txt (parser.h:5, configSample.txt:6-22, main.c:319-366) ------ */
 extern bool parser_nextLine(FILE *fp, char buf[]);            /* parser.c:3 */
 typedef struct MpifdtdConfig {

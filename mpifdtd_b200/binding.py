@@ -125,6 +125,7 @@ def lib():
     L.b200fdtd_get_field_slab.argtypes = [vp, i32, vp]
     L.b200fdtd_set_option.argtypes = [vp, i32, i32]
     L.b200fdtd_set_dense.argtypes = [vp, i32, vp]
+    L.mpifdtd_ntffFrequency.argtypes = [C.c_int, vp]
     L.mpifdtd_split_prepare_host.argtypes = [C.c_int]
     L.mpifdtd_split_dense.argtypes = [C.c_int, C.c_int]
     L.mpifdtd_split_dense.restype = vp

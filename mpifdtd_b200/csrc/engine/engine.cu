@@ -541,6 +541,13 @@ int b200fdtd_selftest_division(double divisor, uint64_t samples, uint64_t *misma
   return rc;
 }
 
+int b200fdtd_ntff_frequency(b200fdtd_engine *e, const b200fdtd_freq_args *args, double *out)
+{
+  if (!e || !args || !out || !args->cos_a || !args->sin_a) return b200_fail(B200FDTD_ERR_ARG, "NULL argument");
+  int rc = select_device(e); if (rc) return rc;
+  return b200_run_ntff_frequency(e, args, out);
+}
+
 int b200fdtd_launch_count(b200fdtd_engine *e, uint64_t *count)
 {
   if (!e || !count) return b200_fail(B200FDTD_ERR_ARG, "NULL argument");

@@ -101,3 +101,4 @@ void b200_fused_release(b200fdtd_engine *e);
 int b200_launch_ntff_sample(b200fdtd_engine *e, const b200fdtd_step_args *a);
 int b200_launch_ntff_project(b200fdtd_engine *e);
 int b200_run_ntff_spectrum(b200fdtd_engine *e, const b200fdtd_spectrum_args *s, double *out);
+int b200_run_ntff_frequency(b200fdtd_engine *e, const b200fdtd_freq_args *a, double *out);

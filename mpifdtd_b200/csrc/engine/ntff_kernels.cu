@@ -278,6 +278,55 @@ __global__ void ntff_spectrum_kernel(const double2 *__restrict__ uw, int n_bins,
   }
 }
 
+// ---- one-shot frequency-domain NTFF (ntffTM.c:72-158) -----------------------------------
+// One block per direction.  Threads stride over the surface points in the reference's
+// order (bottom, right, top, left); partial sums are combined by a fixed-shape tree, so the
+// result is deterministic.  Per point: phase = cexp(i*k*(rx*r2x + ry*r2y)), Nz += H_t*phase,
+// Lx or Ly += Ez*phase, with top/left subtracted.
+constexpr int kFreqBlock = 256;
+
+__global__ void __launch_bounds__(kFreqBlock)
+ntff_frequency_kernel(const double2 *__restrict__ Ez, const double2 *__restrict__ Hx,
+                      const double2 *__restrict__ Hy, int pitch, int j0,
+                      int top, int bottom, int left, int right, int cx, int cy, double k,
+                      const double *__restrict__ cos_a, const double *__restrict__ sin_a,
+                      int n_angles, double2 *out)
+{
+  __shared__ double2 red[3][kFreqBlock];
+  const int ang = blockIdx.x;
+  const double rx = cos_a[ang], ry = sin_a[ang];
+  const int nx = right - left, ny = top - bottom, P = 2 * nx + 2 * ny;
+  double2 nz = make_double2(0, 0), lx = make_double2(0, 0), ly = make_double2(0, 0);
+  for (int p = threadIdx.x; p < P; p += kFreqBlock) {
+    int edge, i, j;
+    if (p < nx)               { edge = 0; i = left + p;               j = bottom; }
+    else if (p < nx + ny)     { edge = 1; i = right;                  j = bottom + (p - nx); }
+    else if (p < 2 * nx + ny) { edge = 2; i = left + (p - nx - ny);   j = top; }
+    else                      { edge = 3; i = left;                   j = bottom + (p - 2 * nx - ny); }
+    const size_t kk = (size_t)(i + 1) * pitch + (j - j0) + B200_JOFF;
+    const double r2x = i - cx, r2y = j - cy;
+    const double inner = rx * r2x + ry * r2y;
+    double sn, cs;
+    sincos(k * inner, &sn, &cs);
+    const double2 phase = make_double2(cs, sn);
+    const double2 ez = Ez[kk];
+    const bool along_x = (edge == 0 || edge == 2);
+    const double2 ht = along_x ? rmul(0.5, cadd(Hx[kk], Hx[kk - 1])) : rmul(0.5, cadd(Hy[kk], Hy[kk - pitch]));
+    const double2 hp = cmul(ht, phase), ep = cmul(ez, phase);
+    if (edge < 2) { nz = cadd(nz, hp); if (along_x) lx = cadd(lx, ep); else ly = cadd(ly, ep); }
+    else          { nz = csub(nz, hp); if (along_x) lx = csub(lx, ep); else ly = csub(ly, ep); }
+  }
+  red[0][threadIdx.x] = nz; red[1][threadIdx.x] = lx; red[2][threadIdx.x] = ly;
+  __syncthreads();
+  for (int half = kFreqBlock / 2; half >= 1; half >>= 1) {
+    if ((int)threadIdx.x < half)
+      for (int s = 0; s < 3; s++)
+        red[s][threadIdx.x] = cadd(red[s][threadIdx.x], red[s][threadIdx.x + half]);
+    __syncthreads();
+  }
+  if (threadIdx.x < 3) out[(size_t)threadIdx.x * n_angles + ang] = red[threadIdx.x][0];
+}
+
 bool is_tm(int kind)
 {
   return kind == B200FDTD_TM_UPML || kind == B200FDTD_MPI_TM_UPML || kind == B200FDTD_TM ||
@@ -322,6 +371,39 @@ int b200_launch_ntff_project(b200fdtd_engine *e)
       n.n_angles, is_tm(e->g.kind) ? 1 : 0, n.array_size, n.uw);
   e->launches++;
   B200_CUDA(cudaGetLastError());
+  return B200FDTD_OK;
+}
+
+int b200_run_ntff_frequency(b200fdtd_engine *e, const b200fdtd_freq_args *a, double *out)
+{
+  if (!is_tm(e->g.kind))
+    return b200_fail(B200FDTD_ERR_ARG, "frequency NTFF serves the TM-type kinds (reference: ntffTM_Frequency)");
+  if (e->g.nj != e->g.n_py)
+    return b200_fail(B200FDTD_ERR_ARG, "frequency NTFF needs the whole grid on one engine");
+  if (a->left < 1 || a->bottom < 1 || a->right >= e->g.n_px || a->top >= e->g.n_py ||
+      a->right <= a->left || a->top <= a->bottom || a->n_angles < 1)
+    return b200_fail(B200FDTD_ERR_ARG, "bad NTFF box");
+  int rc = b200_refresh_h(e);
+  if (rc) return rc;
+  const bool upml = (e->g.kind == B200FDTD_TM_UPML || e->g.kind == B200FDTD_MPI_TM_UPML);
+  const double2 *Ez = e->field[0];
+  const double2 *Hx = e->field[upml ? (int)B200FDTD_TM_HX : (int)B200FDTD_STM_HX];
+  const double2 *Hy = e->field[upml ? (int)B200FDTD_TM_HY : (int)B200FDTD_STM_HY];
+  double *d_cos = nullptr, *d_sin = nullptr;
+  double2 *d_out = nullptr;
+  B200_CUDA(cudaMalloc(&d_cos, sizeof(double) * a->n_angles));
+  B200_CUDA(cudaMalloc(&d_sin, sizeof(double) * a->n_angles));
+  B200_CUDA(cudaMalloc(&d_out, sizeof(double2) * 3 * a->n_angles));
+  B200_CUDA(cudaMemcpyAsync(d_cos, a->cos_a, sizeof(double) * a->n_angles, cudaMemcpyHostToDevice, e->stream));
+  B200_CUDA(cudaMemcpyAsync(d_sin, a->sin_a, sizeof(double) * a->n_angles, cudaMemcpyHostToDevice, e->stream));
+  ntff_frequency_kernel<<<a->n_angles, kFreqBlock, 0, e->stream>>>(Ez, Hx, Hy, e->pitch, e->g.j0, a->top, a->bottom,
+                                                                  a->left, a->right, a->cx, a->cy, a->k, d_cos,
+                                                                  d_sin, a->n_angles, d_out);
+  e->launches++;
+  B200_CUDA(cudaGetLastError());
+  B200_CUDA(cudaMemcpyAsync(out, d_out, sizeof(double2) * 3 * a->n_angles, cudaMemcpyDeviceToHost, e->stream));
+  B200_CUDA(cudaStreamSynchronize(e->stream));
+  cudaFree(d_cos); cudaFree(d_sin); cudaFree(d_out);
   return B200FDTD_OK;
 }
 

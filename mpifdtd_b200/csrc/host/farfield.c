@@ -119,6 +119,42 @@ double complex *mpifdtd_fft_twiddles(int n)
   return tw;
 }
 
+/* ---- one-shot frequency-domain far field (ntffTM_Frequency, ntffTM.c:72-158) ---------
+ * The surface sums run on the GPU over the engine's current fields; the closing algebra
+ * (polar component, coef, sqrt(h_u)) is the reference's, evaluated here with host libm.
+ * Serves the TM-type solvers (ids 0, 2, 4, 6).  result[360] like resultEz. */
+#include "b200fdtd.h"
+extern b200fdtd_engine *mpifdtd_upml_engine(int kind);
+extern b200fdtd_engine *mpifdtd_split_engine(int kind);
+
+int mpifdtd_ntffFrequency(int solver_id, double complex result[360])
+{
+  b200fdtd_engine *engine = (solver_id == TM_UPML_2D || solver_id == MPI_TM_UPML_2D)
+                                ? mpifdtd_upml_engine(solver_id) : mpifdtd_split_engine(solver_id);
+  if (engine == NULL) { printf("ntffFrequency: solver %d is not initialised\n", solver_id); exit(2); }
+  NTFFInfo box = field_getNTFFInfo();
+  FieldInfo phys = field_getFieldInfo();
+  double k_s = field_getK();
+  double R0 = 1.0e6 * field_toCellUnit(500);                  /* ntffTM.c:31 */
+  double complex coef = csqrt(I * k_s / (8 * M_PI * R0)) * cexp(I * k_s * R0);
+  double cos_a[360], sin_a[360];
+  for (int ang = 0; ang < 360; ang++) {
+    double rad = ang * M_PI / 180.0;
+    cos_a[ang] = cos(rad);
+    sin_a[ang] = sin(rad);
+  }
+  b200fdtd_freq_args fa = { box.top, box.bottom, box.left, box.right, box.cx, box.cy, 360, 0, k_s, cos_a, sin_a };
+  double complex sums[3][360];
+  int rc = b200fdtd_ntff_frequency(engine, &fa, (double *)sums);
+  if (rc != B200FDTD_OK) { printf("b200fdtd: ntff_frequency failed (%d): %s\n", rc, b200fdtd_last_error()); exit(2); }
+  for (int ang = 0; ang < 360; ang++) {
+    double complex Nz = sums[0][ang], Lx = sums[1][ang], Ly = sums[2][ang];
+    double complex Lphi = -Lx * sin_a[ang] + Ly * cos_a[ang];
+    result[ang] = coef * (Z_0_S * Nz + Lphi) * sqrt(phys.h_u_nm);
+  }
+  return 0;
+}
+
 /* ---- on-disk formats (ntff.c:6-33) ----------------------------------------
  * text: one line per wavelength, "<nm> " then 360 values printed with "%lf.20 "
  * (upstream's format string: six decimals followed by the literal ".20");

@@ -331,6 +331,47 @@ void oracle_ntff_box(const OracleSim *s, int *out6) {
   out6[0] = s->top; out6[1] = s->bottom; out6[2] = s->left; out6[3] = s->right; out6[4] = s->cx; out6[5] = s->cy;
 }
 
+/* ---- ntffTM.c:72-158: one-shot frequency-domain surface integral (TM) -------------- */
+void oracle_frequency_tm(OracleSim *s, cplx *result)
+{
+  const int N = s->npy;
+  const cplx *Ez = s->f[EZ], *Hx = s->f[HX], *Hy = s->f[HY];
+  double R0 = 1.0e6 * (500.0 / s->h_u_nm);                                   /* ntffTM.c:31 */
+  double cx = s->cx, cy = s->cy, k_s = s->k_s;
+  cplx coef = csqrt(I * k_s / (8 * M_PI * R0)) * cexp(I * k_s * R0);
+  for (int ang = 0; ang < N_ANG; ang++) {
+    double rad = ang * M_PI / 180.0;
+    double rx = cos(rad), ry = sin(rad);
+    cplx Nz = 0, Lx = 0, Ly = 0;
+    for (int i = s->left; i < s->right; i++) {                               /* bottom */
+      int k = i * N + s->bottom;
+      double inner = rx * (i - cx) + ry * (s->bottom - cy);
+      Nz += 0.5 * (Hx[k] + Hx[k - 1]) * cexp(I * k_s * inner);
+      Lx += Ez[k] * cexp(I * k_s * inner);
+    }
+    for (int j = s->bottom; j < s->top; j++) {                               /* right */
+      int k = s->right * N + j;
+      double inner = rx * (s->right - cx) + ry * (j - cy);
+      Nz += 0.5 * (Hy[k] + Hy[k - N]) * cexp(I * k_s * inner);
+      Ly += Ez[k] * cexp(I * k_s * inner);
+    }
+    for (int i = s->left; i < s->right; i++) {                               /* top */
+      int k = i * N + s->top;
+      double inner = rx * (i - cx) + ry * (s->top - cy);
+      Nz -= 0.5 * (Hx[k] + Hx[k - 1]) * cexp(I * k_s * inner);
+      Lx -= Ez[k] * cexp(I * k_s * inner);
+    }
+    for (int j = s->bottom; j < s->top; j++) {                               /* left */
+      int k = s->left * N + j;
+      double inner = rx * (s->left - cx) + ry * (j - cy);
+      Nz -= 0.5 * (Hy[k] + Hy[k - N]) * cexp(I * k_s * inner);
+      Ly -= Ez[k] * cexp(I * k_s * inner);
+    }
+    cplx Lphi = -Lx * sin(rad) + Ly * cos(rad);
+    result[ang] = coef * (Z0 * Nz + Lphi) * sqrt(s->h_u_nm);
+  }
+}
+
 /* ---- cfft.c:104-179: radix-2 DIF, e^{+i...} twiddles, then bit reversal ----- */
 void oracle_fft(cplx *a, int n)
 {

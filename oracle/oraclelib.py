@@ -50,6 +50,7 @@ def lib():
         L.oracle_set_angle.argtypes = [C.c_void_p, C.c_int]
         L.oracle_ntff_box.argtypes = [C.c_void_p, C.c_void_p]
         L.oracle_fft.argtypes = [C.c_void_p, C.c_int]
+        L.oracle_frequency_tm.argtypes = [C.c_void_p, C.c_void_p]
         L.oracle_time.restype = C.c_double
         L.oracle_time.argtypes = [C.c_void_p]
         _lib = L
@@ -95,6 +96,11 @@ class OracleSim:
     def far_field(self):
         out = np.zeros((321, 360))
         self.L.oracle_far_field(self.h, out.ctypes.data)
+        return out
+
+    def frequency_tm(self):
+        out = np.zeros(360, dtype=np.complex128)
+        self.L.oracle_frequency_tm(self.h, out.ctypes.data)
         return out
 
     def box(self):

@@ -92,3 +92,46 @@ def test_mpi_variant_solver_vs_live_reference(plugin_lib, kind, model, in_tmp_cw
         assert rel_err(gpu.any_field(slot), want[f][1:-1, 1:-1]) <= TOL_FIELD, f
     assert np.abs(want[MPI_FIELDS[kind][0]]).max() > 1e-3
     gpu.finish()
+
+
+# ---------------------------------------------------------------- frequency-domain NTFF
+def test_frequency_ntff_tm_upml_vs_oracle(plugin_lib, oracle, in_tmp_cwd):
+    """ntffTM_Frequency (ntffTM.c:72-158) on the GPU fields of the serial TM UPML solver."""
+    n, steps = 120, 520
+    gpu = B.Plugin("MIE_CYLINDER", "TM_UPML_2D", n, steps=steps, h_u_nm=20)
+    cpu = oracle.OracleSim(oracle.TM, n, n, steps, gpu.eps(), h_u_nm=20)
+    gpu.run()
+    cpu.step(steps)
+    mine = np.zeros(360, dtype=np.complex128)
+    assert gpu.L.mpifdtd_ntffFrequency(2, mine.ctypes.data) == 0
+    want = cpu.frequency_tm()
+    assert np.abs(want).max() > 0
+    assert rel_err(mine, want) <= 1e-10
+    gpu.finish()
+
+
+def test_frequency_ntff_ns_tm_vs_live_reference(plugin_lib, in_tmp_cwd):
+    """BASELINE configs[3] in miniature: NS-FDTD TM, frequency-domain far field of the final
+    fields (the reference's NS solver has no NTFF; its ntffTM_Frequency is applied to its
+    fields, after ntffTM_init() for R0, as SURVEY 8d prescribes)."""
+    import ctypes as C
+    from oracle import reflib
+    if not reflib.available():
+        pytest.skip("oracle/_ref/libref.so did not travel with this snapshot")
+    npx, npy, steps, lam = 200, 220, 320, 600
+    cwd = os.getcwd()
+    ref = reflib.RefSim("MIE_CYLINDER", 6, npx, npy, steps=steps, lambda_nm=lam)
+    L = reflib.lib()
+    L.ntffTM_init()
+    ref.run()
+    want = np.zeros(360, dtype=np.complex128)
+    L.ntffTM_Frequency.argtypes = [C.c_void_p] * 4
+    L.ntffTM_Frequency(ref._ptr("Hx"), ref._ptr("Hy"), ref._ptr("Ez"), want.ctypes.data)
+    ref.finish()
+    os.chdir(cwd)
+    gpu = B.Plugin("MIE_CYLINDER", 6, npx, npy, steps=steps, lambda_nm=lam)
+    gpu.run()
+    mine = np.zeros(360, dtype=np.complex128)
+    assert gpu.L.mpifdtd_ntffFrequency(6, mine.ctypes.data) == 0
+    assert np.abs(want).max() > 0 and rel_err(mine, want) <= 1e-10
+    gpu.finish()
