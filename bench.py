@@ -145,9 +145,9 @@ def reference_arm(args):
     return 0
 
 
-def workload_config(n_gpus, sample_note=None, n=N_PER_GPU):
-    cfg = {"workload": "zigzagModel TM_UPML (solver 2) weak scaling, %d x %d cells per GPU, "
-                       "global %d x %d, y-slabs" % (n, n, n, n * n_gpus),
+def workload_config(n_gpus, sample_note=None, n=N_PER_GPU, solver="TM_UPML_2D"):
+    cfg = {"workload": "zigzagModel %s weak scaling, %d x %d cells per GPU, "
+                       "global %d x %d, y-slabs" % (solver, n, n, n, n * n_gpus),
            "baseline_config": "BASELINE.json configs[4]",
            "h_u_nm": 10, "pml": 10, "lambda_nm": 500, "angle_deg": 0,
            "cells_per_gpu": n * n,
@@ -254,7 +254,7 @@ def gpu_arm(args):
     with torch.cuda.stream(stream):
         if world > 1:
             comm = TorchHaloComm(n_px, torch.device("cuda", local_rank))
-        run = SlabRun("ZIGZAG", "TM_UPML_2D", n_px, n_py, total_steps, rank=rank, world=world,
+        run = SlabRun("ZIGZAG", args.solver, n_px, n_py, total_steps, rank=rank, world=world,
                       device=local_rank, comm=comm)
         run.engine.set_stream(stream.cuda_stream)
         if comm is not None:
@@ -328,23 +328,28 @@ def gpu_arm(args):
     if rank == 0:
         peak, peak_kind = measured_hbm_peak()
         cells_rank = float(n_px) * float(run.nj)
-        ach_h = BYTES_H_TM * cells_rank / (ms_h * 1e-3) / 1e9
-        ach_e = BYTES_E_TM * cells_rank / (ms_e * 1e-3) / 1e9
-        step_gbs = BYTES_STEP_TM * (value / world) * 1e9 / 1e9
+        tm = args.solver == "TM_UPML_2D"
+        # TE: H phase reads Ex,Ey,Mz,Bz (64) + writes Mz,Bz (32); E phase reads Bz,Jx,Dx,Jy,Dy (80) +
+        # eps x2 (16) + writes Jx,Dx,Jy,Dy,Ex,Ey (96); step = SURVEY 8(d)'s 288 B
+        bytes_h, bytes_e, bytes_step = (BYTES_H_TM, BYTES_E_TM, BYTES_STEP_TM) if tm else (96, 192, 288)
+        kname = "tm" if tm else "te"
+        ach_h = bytes_h * cells_rank / (ms_h * 1e-3) / 1e9
+        ach_e = bytes_e * cells_rank / (ms_e * 1e-3) / 1e9
+        step_gbs = bytes_step * (value / world) * 1e9 / 1e9
         line = {
             "metric": "Gcell-updates/s", "value": value, "unit": "Gcell-updates/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_max / K,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": workload_config(world, n=args.n),
-            "roofline": {"bound": "hbm", "kernel": "tm_upml_h_kernel<STORE_H=false>", "achieved": ach_h,
+            "config": workload_config(world, n=args.n, solver=args.solver),
+            "roofline": {"bound": "hbm", "kernel": kname + "_upml_h_kernel<STORE_H=false>", "achieved": ach_h,
                          "peak": peak, "unit": "GB/s", "frac": ach_h / peak, "peak_source": peak_kind,
                          "traffic": None, "ms_per_launch": ms_h,
-                         "algorithmic_bytes_per_cell": BYTES_H_TM,
-                         "e_phase": {"kernel": "tm_upml_e_kernel<FROM_B=true>", "achieved": ach_e,
+                         "algorithmic_bytes_per_cell": bytes_h,
+                         "e_phase": {"kernel": kname + "_upml_e_kernel<FROM_B=true>", "achieved": ach_e,
                                      "frac": ach_e / peak, "ms_per_launch": ms_e,
-                                     "algorithmic_bytes_per_cell": BYTES_E_TM},
-                         "step": {"algorithmic_bytes_per_cell_update": BYTES_STEP_TM,
+                                     "algorithmic_bytes_per_cell": bytes_e},
+                         "step": {"algorithmic_bytes_per_cell_update": bytes_step,
                                   "achieved": step_gbs, "frac": step_gbs / peak,
                                   "frac_of_nominal_8TBs": step_gbs / 8000.0}},
             "cpu_baseline": cpu,
@@ -374,6 +379,8 @@ def main():
     ap.add_argument("--cpu-n", type=int, default=1024, help="grid side of the CPU sample")
     ap.add_argument("--cpu-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--solver", default="TM_UPML_2D", choices=["TM_UPML_2D", "TE_UPML_2D"],
+                    help="TM_UPML_2D is the BASELINE workload; TE_UPML_2D is reported for information")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

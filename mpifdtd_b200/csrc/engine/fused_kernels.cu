@@ -347,8 +347,12 @@ int b200_launch_upml_fused(b200fdtd_engine *e, const b200fdtd_step_args *a)
 int b200_refresh_h(b200fdtd_engine *e)
 {
   if (!e->h_stale) return B200FDTD_OK;
-  if (is_tm(e->g.kind)) {
-    const int n_rows = e->r_hi - e->r_lo + 1, n_cols = e->c_hi - e->c_lo + 1;
+  const int n_rows = e->r_hi - e->r_lo + 1, n_cols = e->c_hi - e->c_lo + 1;
+  if (!is_tm(e->g.kind)) {
+    derive_h_kernel<<<1184, 256, 0, e->stream>>>(e->field[B200FDTD_TE_BZ], e->field[B200FDTD_TE_HZ], e->pitch,
+                                                 e->r_lo, n_rows, e->c_lo, n_cols, e->g.mu0);
+    e->launches += 1;
+  } else {
     derive_h_kernel<<<1184, 256, 0, e->stream>>>(e->field[B200FDTD_TM_BX], e->field[B200FDTD_TM_HX], e->pitch,
                                                  e->r_lo, n_rows, e->c_lo, n_cols, e->g.mu0);
     derive_h_kernel<<<1184, 256, 0, e->stream>>>(e->field[B200FDTD_TM_BY], e->field[B200FDTD_TM_HY], e->pitch,

@@ -346,11 +346,11 @@ int b200_launch_ntff_sample(b200fdtd_engine *e, const b200fdtd_step_args *a)
     const bool tm = is_tm(e->g.kind);
     const double2 *ea = e->field[tm ? (int)B200FDTD_TM_EZ : (int)B200FDTD_TE_EX];
     const double2 *eb = e->field[tm ? (int)B200FDTD_TM_EZ : (int)B200FDTD_TE_EY];
-    const bool from_b = e->h_stale && tm;               // H arrays not kept: sample B/mu0
+    const bool from_b = e->h_stale;                     // H arrays not kept: sample B/mu0
     const double2 *ha = e->field[tm ? (int)B200FDTD_TM_HX : (int)B200FDTD_TE_HZ];
     const double2 *hb = e->field[tm ? (int)B200FDTD_TM_HY : (int)B200FDTD_TE_HZ];
-    const double2 *ba = from_b ? e->field[B200FDTD_TM_BX] : nullptr;
-    const double2 *bb = from_b ? e->field[B200FDTD_TM_BY] : nullptr;
+    const double2 *ba = from_b ? e->field[tm ? (int)B200FDTD_TM_BX : (int)B200FDTD_TE_BZ] : nullptr;
+    const double2 *bb = from_b ? e->field[tm ? (int)B200FDTD_TM_BY : (int)B200FDTD_TE_BZ] : nullptr;
     ntff_sample_kernel<<<(n.n_local + 127) / 128, 128, 0, e->stream>>>(
         n.pts, n.n_local, tm ? 1 : 0, ea, eb, ha, hb, e->pitch, n.hist_e, n.hist_h, n.max_time, t,
         ba, bb, e->g.mu0, e->c_lo);

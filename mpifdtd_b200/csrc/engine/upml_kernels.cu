@@ -137,6 +137,7 @@ __global__ void __launch_bounds__(kBlock) tm_upml_e_kernel(const UpmlView v)
 
 // ------------------------------------------------------------------ TE -----
 // slots: 0 Ex 1 Jx 2 Dx 3 Ey 4 Jy 5 Dy 6 Hz 7 Mz 8 Bz
+template <bool STORE_H>
 __global__ void __launch_bounds__(kBlock) te_upml_h_kernel(const UpmlView v)
 {
   int r, c; size_t k;
@@ -162,18 +163,29 @@ __global__ void __launch_bounds__(kBlock) te_upml_h_kernel(const UpmlView v)
 
   v.f[B200FDTD_TE_MZ][k] = mz;
   v.f[B200FDTD_TE_BZ][k] = bz;
-  v.f[B200FDTD_TE_HZ][k] = div_const(bz, v.mu0);   // fdtdTE_upml.c:312
+  if (STORE_H) v.f[B200FDTD_TE_HZ][k] = div_const(bz, v.mu0);   // fdtdTE_upml.c:312
 }
 
+template <bool FROM_B>
 __global__ void __launch_bounds__(kBlock) te_upml_e_kernel(const UpmlView v)
 {
   int r, c; size_t k;
   if (!locate(v, r, c, k)) return;
   const double2 *__restrict__ Hz = v.f[B200FDTD_TE_HZ];
-
-  const double2 hz = Hz[k];
-  const double2 hz_j0 = Hz[k - 1];
-  const double2 hz_i0 = Hz[k - v.pitch];
+  double2 hz, hz_j0, hz_i0;
+  if (FROM_B) {                               // Hz == Bz/mu0 (fdtdTE_upml.c:312), formed on the fly
+    const double2 *__restrict__ Bz = v.f[B200FDTD_TE_BZ];
+    const double2 bz = Bz[k], bz_j0 = Bz[k - 1], bz_i0 = Bz[k - v.pitch];
+    hz = div_const(bz, v.mu0);
+    hz_j0 = div_const(bz_j0, v.mu0);
+    hz_i0 = div_const(bz_i0, v.mu0);
+    if (c == v.c_lo) hz_j0 = Hz[k - 1];       // ring / halo column: only the H array holds it
+    if (r == v.r_lo) hz_i0 = Hz[k - v.pitch];
+  } else {
+    hz = Hz[k];
+    hz_j0 = Hz[k - 1];
+    hz_i0 = Hz[k - v.pitch];
+  }
   const double2 jx_old = v.f[B200FDTD_TE_JX][k];
   const double2 dx_old = v.f[B200FDTD_TE_DX][k];
   const double2 jy_old = v.f[B200FDTD_TE_JY][k];
@@ -280,7 +292,9 @@ int b200_launch_upml_h(b200fdtd_engine *e, const b200fdtd_step_args *a)
     else            tm_upml_h_kernel<false><<<(unsigned)nblk, kBlock, 0, e->stream>>>(v);
     e->h_stale = !e->store_h;
   } else {
-    te_upml_h_kernel<<<(unsigned)nblk, kBlock, 0, e->stream>>>(v);
+    if (e->store_h) te_upml_h_kernel<true><<<(unsigned)nblk, kBlock, 0, e->stream>>>(v);
+    else            te_upml_h_kernel<false><<<(unsigned)nblk, kBlock, 0, e->stream>>>(v);
+    e->h_stale = !e->store_h;
   }
   e->launches++;
   B200_CUDA(cudaGetLastError());
@@ -296,7 +310,8 @@ int b200_launch_upml_e(b200fdtd_engine *e, const b200fdtd_step_args *a)
     if (e->h_stale) tm_upml_e_kernel<true><<<(unsigned)nblk, kBlock, 0, e->stream>>>(v);
     else            tm_upml_e_kernel<false><<<(unsigned)nblk, kBlock, 0, e->stream>>>(v);
   } else {
-    te_upml_e_kernel<<<(unsigned)nblk, kBlock, 0, e->stream>>>(v);
+    if (e->h_stale) te_upml_e_kernel<true><<<(unsigned)nblk, kBlock, 0, e->stream>>>(v);
+    else            te_upml_e_kernel<false><<<(unsigned)nblk, kBlock, 0, e->stream>>>(v);
   }
   e->launches++;
   B200_CUDA(cudaGetLastError());
@@ -315,8 +330,8 @@ int b200_launch_halo(b200fdtd_engine *e, int which, void *buf, bool pack)
   }
   const int n = e->g.n_px;
   double divisor = 0.0;
-  if (which == 0 && pack && e->h_stale && is_tm(e->g.kind)) {   // Hx column = Bx column / mu0
-    slot = B200FDTD_TM_BX;
+  if (which == 0 && pack && e->h_stale) {     // H column = B column / mu0 (H arrays not kept)
+    slot = is_tm(e->g.kind) ? (int)B200FDTD_TM_BX : (int)B200FDTD_TE_BZ;
     divisor = e->g.mu0;
   }
   halo_column_kernel<<<(n + 255) / 256, 256, 0, e->stream>>>(e->field[slot], (double2 *)buf,
