@@ -145,7 +145,7 @@ def reference_arm(args):
     return 0
 
 
-def workload_config(n_gpus, sample_note=None, n=N_PER_GPU, solver="TM_UPML_2D"):
+def workload_config(n_gpus, sample_note=None, n=N_PER_GPU, solver="TM_UPML_2D", halo="peer"):
     cfg = {"workload": "zigzagModel %s weak scaling, %d x %d cells per GPU, "
                        "global %d x %d, y-slabs" % (solver, n, n, n, n * n_gpus),
            "baseline_config": "BASELINE.json configs[4]",
@@ -153,6 +153,8 @@ def workload_config(n_gpus, sample_note=None, n=N_PER_GPU, solver="TM_UPML_2D"):
            "cells_per_gpu": n * n,
            "l2_policy": "working set 38 GiB per GPU >> 126 MB L2, no flush needed",
            "parallelism": "y-slab x%d" % n_gpus}
+    if n_gpus > 1:
+        cfg["halo"] = halo
     if sample_note:
         cfg["note"] = sample_note
     return cfg
@@ -259,6 +261,8 @@ def gpu_arm(args):
         run.engine.set_stream(stream.cuda_stream)
         if comm is not None:
             run.attach_halo_buffers(*comm.pointers())
+            if args.halo == "peer":
+                run.enable_peer_halos(comm.gather_blobs)
 
         def barrier():
             torch.cuda.synchronize()
@@ -306,6 +310,7 @@ def gpu_arm(args):
         # ---- e2e: host buffers inside the timed region ------------------------------
         run.engine.zero()
         run.L.field_reset()
+        barrier()            # every rank has zeroed (peer-halo flags included) before anyone steps
         eps_pinned = torch.from_numpy(run.eps_host[0]).pin_memory()
         ez_pinned = torch.empty((n_px, run.nj, 2), dtype=torch.float64).pin_memory()
         for _ in range(min(W, 3)):
@@ -341,7 +346,9 @@ def gpu_arm(args):
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_max / K,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": workload_config(world, n=args.n, solver=args.solver),
+            "config": workload_config(world, n=args.n, solver=args.solver,
+                                      halo={"peer": "direct NVLink peer stores + device flags",
+                                            "nccl": "NCCL send/recv"}[args.halo]),
             "roofline": {"bound": "hbm", "kernel": kname + "_upml_h_kernel<STORE_H=false>", "achieved": ach_h,
                          "peak": peak, "unit": "GB/s", "frac": ach_h / peak, "peak_source": peak_kind,
                          "traffic": None, "ms_per_launch": ms_h,
@@ -379,6 +386,8 @@ def main():
     ap.add_argument("--cpu-n", type=int, default=1024, help="grid side of the CPU sample")
     ap.add_argument("--cpu-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--halo", default="peer", choices=["peer", "nccl"],
+                    help="multi-GPU halo transport: direct NVLink peer stores (default) or NCCL send/recv")
     ap.add_argument("--solver", default="TM_UPML_2D", choices=["TM_UPML_2D", "TE_UPML_2D"],
                     help="TM_UPML_2D is the BASELINE workload; TE_UPML_2D is reported for information")
     args = ap.parse_args()

@@ -229,6 +229,16 @@ int b200fdtd_sync(b200fdtd_engine *e);
  * device pointer to n_px complex values. */
 int b200fdtd_halo_pack(b200fdtd_engine *e, int32_t which, void *dev_buf);
 int b200fdtd_halo_unpack(b200fdtd_engine *e, int32_t which, const void *dev_buf);
+/* Direct peer (NVLink) halos between the y-slab engines of different processes on one node.
+ * Each engine exports a 256-byte blob (CUDA IPC handles of its E array, H array and flag
+ * words + its nj); the driver moves blobs between ranks (any transport) and attaches the
+ * lower (which_neighbour = 0) and/or upper (1) neighbour's blob.  From then on
+ * b200fdtd_phase_h / _phase_e store their halo column straight into the neighbour's ghost
+ * column and order themselves across GPUs with device-side flag words -- no halo_pack /
+ * halo_unpack, no NCCL call and no host synchronisation per step. */
+#define B200FDTD_PEER_BLOB_BYTES 256
+int b200fdtd_peer_export(b200fdtd_engine *e, void *blob);
+int b200fdtd_peer_attach(b200fdtd_engine *e, int32_t which_neighbour, const void *blob);
 /* Launch everything on this CUDA stream (a cudaStream_t) from now on. */
 int b200fdtd_set_stream(b200fdtd_engine *e, void *cuda_stream);
 

@@ -125,6 +125,8 @@ def lib():
     L.b200fdtd_get_field_slab.argtypes = [vp, i32, vp]
     L.b200fdtd_set_option.argtypes = [vp, i32, i32]
     L.b200fdtd_set_dense.argtypes = [vp, i32, vp]
+    L.b200fdtd_peer_export.argtypes = [vp, vp]
+    L.b200fdtd_peer_attach.argtypes = [vp, i32, vp]
     L.mpifdtd_ntffFrequency.argtypes = [C.c_int, vp]
     L.mpifdtd_split_prepare_host.argtypes = [C.c_int]
     L.mpifdtd_split_dense.argtypes = [C.c_int, C.c_int]
@@ -383,6 +385,15 @@ class Engine:
 
     def set_stream(self, stream_handle):
         check(self.L.b200fdtd_set_stream(self.h, C.c_void_p(stream_handle)), "set_stream")
+
+    def peer_export(self):
+        blob = C.create_string_buffer(256)
+        check(self.L.b200fdtd_peer_export(self.h, blob), "peer_export")
+        return blob.raw
+
+    def peer_attach(self, which_neighbour, blob):
+        buf = C.create_string_buffer(blob, 256)
+        check(self.L.b200fdtd_peer_attach(self.h, which_neighbour, buf), "peer_attach")
 
     def halo_pack(self, which, dev_ptr):
         check(self.L.b200fdtd_halo_pack(self.h, which, C.c_void_p(dev_ptr)), "halo_pack")

@@ -64,6 +64,8 @@ void free_ntff(b200fdtd_engine *e)
 
 extern "C" {
 
+static void peer_release(b200fdtd_engine *e);
+
 const char *b200fdtd_last_error(void) { return g_last_error; }
 int b200fdtd_abi_version(void) { return B200FDTD_ABI_VERSION; }
 
@@ -181,11 +183,87 @@ int b200fdtd_destroy(b200fdtd_engine *e)
   for (int s = 0; s < B200FDTD_MAX_DENSE; s++) cudaFree(e->dense[s]);
   free_ntff(e);
   b200_fused_release(e);
+  peer_release(e);
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
   if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
   delete e;
   return B200FDTD_OK;
+}
+
+// ---- peer halos ----------------------------------------------------------------------
+struct PeerBlob {                       // what b200fdtd_peer_export writes (<= 256 bytes)
+  cudaIpcMemHandle_t e_arr, h_arr, flags;
+  int32_t nj, pitch, rows, kind;
+};
+static_assert(sizeof(PeerBlob) <= B200FDTD_PEER_BLOB_BYTES, "peer blob too large");
+
+static int peer_slots(const b200fdtd_engine *e, int *e_slot, int *h_slot)
+{
+  const bool tm = (e->g.kind == B200FDTD_TM_UPML || e->g.kind == B200FDTD_MPI_TM_UPML);
+  *e_slot = tm ? (int)B200FDTD_TM_EZ : (int)B200FDTD_TE_EX;
+  *h_slot = tm ? (int)B200FDTD_TM_HX : (int)B200FDTD_TE_HZ;
+  return 0;
+}
+
+int b200fdtd_peer_export(b200fdtd_engine *e, void *blob)
+{
+  if (!e || !blob) return b200_fail(B200FDTD_ERR_ARG, "NULL argument");
+  if (!kind_is_upml(e->g.kind)) return b200_fail(B200FDTD_ERR_ARG, "peer halos serve the UPML kinds");
+  int rc = select_device(e); if (rc) return rc;
+  if (!e->peer.flags) {
+    rc = dev_alloc_zero(e, (void **)&e->peer.flags, 2 * sizeof(unsigned long long));
+    if (rc) return rc;
+    B200_CUDA(cudaStreamSynchronize(e->stream));
+  }
+  int es, hs;
+  peer_slots(e, &es, &hs);
+  PeerBlob b;
+  memset(&b, 0, sizeof b);
+  B200_CUDA(cudaIpcGetMemHandle(&b.e_arr, e->field[es]));
+  B200_CUDA(cudaIpcGetMemHandle(&b.h_arr, e->field[hs]));
+  B200_CUDA(cudaIpcGetMemHandle(&b.flags, e->peer.flags));
+  b.nj = e->g.nj; b.pitch = e->pitch; b.rows = e->rows; b.kind = e->g.kind;
+  memset(blob, 0, B200FDTD_PEER_BLOB_BYTES);
+  memcpy(blob, &b, sizeof b);
+  return B200FDTD_OK;
+}
+
+int b200fdtd_peer_attach(b200fdtd_engine *e, int32_t which, const void *blob)
+{
+  if (!e || !blob || which < 0 || which > 1) return b200_fail(B200FDTD_ERR_ARG, "bad peer argument");
+  int rc = select_device(e); if (rc) return rc;
+  if (!e->peer.flags) return b200_fail(B200FDTD_ERR_STATE, "peer_attach before peer_export");
+  PeerBlob b;
+  memcpy(&b, blob, sizeof b);
+  if (b.rows != e->rows || b.kind != e->g.kind)
+    return b200_fail(B200FDTD_ERR_ARG, "neighbour slab has another shape or solver kind");
+  void *p_e = nullptr, *p_h = nullptr, *p_f = nullptr;
+  B200_CUDA(cudaIpcOpenMemHandle(&p_f, b.flags, cudaIpcMemLazyEnablePeerAccess));
+  if (which == 1) {                     // upper neighbour: I store H into its low ghost column
+    B200_CUDA(cudaIpcOpenMemHandle(&p_h, b.h_arr, cudaIpcMemLazyEnablePeerAccess));
+    e->peer.up_h = (double2 *)p_h;
+    e->peer.up_pitch = b.pitch;
+    e->peer.up_flag = (unsigned long long *)p_f + 0;
+    e->peer.opened[3] = p_h; e->peer.opened[4] = p_f;
+  } else {                              // lower neighbour: I store E into its high ghost column
+    B200_CUDA(cudaIpcOpenMemHandle(&p_e, b.e_arr, cudaIpcMemLazyEnablePeerAccess));
+    e->peer.down_e = (double2 *)p_e;
+    e->peer.down_pitch = b.pitch;
+    e->peer.down_nj = b.nj;
+    e->peer.down_flag = (unsigned long long *)p_f + 1;
+    e->peer.opened[0] = p_e; e->peer.opened[1] = p_f;
+  }
+  e->peer.attached[which] = true;
+  return B200FDTD_OK;
+}
+
+static void peer_release(b200fdtd_engine *e)
+{
+  for (int n = 0; n < 6; n++)
+    if (e->peer.opened[n]) cudaIpcCloseMemHandle(e->peer.opened[n]);
+  cudaFree(e->peer.flags);
+  memset(&e->peer, 0, sizeof e->peer);
 }
 
 int b200fdtd_set_stream(b200fdtd_engine *e, void *cuda_stream)
@@ -344,14 +422,24 @@ int b200fdtd_phase_h(b200fdtd_engine *e, const b200fdtd_step_args *a)
 {
   int rc = check_ready(e, a); if (rc) return rc;
   if (kind_is_split(e->g.kind)) return b200_fail(B200FDTD_ERR_ARG, "phase API serves the UPML kinds only");
-  return b200_launch_upml_h(e, a);              // sets h_stale = !store_h
+  const unsigned long long step = (unsigned long long)a->time;
+  // my high ghost column (Ez / Ex) was written by the upper neighbour's E phase of step-1
+  if (e->peer.attached[1] && step > 0) { rc = b200_peer_wait(e, 1, step); if (rc) return rc; }
+  rc = b200_launch_upml_h(e, a);                // sets h_stale = !store_h; stores the halo column upward
+  if (!rc && e->peer.attached[1]) rc = b200_peer_signal(e, e->peer.up_flag, step + 1);
+  return rc;
 }
 
 int b200fdtd_phase_e(b200fdtd_engine *e, const b200fdtd_step_args *a)
 {
   int rc = check_ready(e, a); if (rc) return rc;
   if (kind_is_split(e->g.kind)) return b200_fail(B200FDTD_ERR_ARG, "phase API serves the UPML kinds only");
-  return b200_launch_upml_e(e, a);              // reads B/mu0 when the H arrays are stale
+  const unsigned long long step = (unsigned long long)a->time;
+  // my low ghost column (Hx / Hz) is written by the lower neighbour's H phase of this step
+  if (e->peer.attached[0]) { rc = b200_peer_wait(e, 0, step + 1); if (rc) return rc; }
+  rc = b200_launch_upml_e(e, a);                // reads B/mu0 when the H arrays are stale; halo column downward
+  if (!rc && e->peer.attached[0]) rc = b200_peer_signal(e, e->peer.down_flag, step + 1);
+  return rc;
 }
 
 int b200fdtd_set_option(b200fdtd_engine *e, int32_t option, int32_t value)
@@ -487,6 +575,9 @@ int b200fdtd_zero_state(b200fdtd_engine *e)
   for (int s = 0; s < e->n_fields; s++)
     B200_CUDA(cudaMemsetAsync(e->field[s], 0, e->plane * sizeof(double2), e->stream));
   e->h_stale = false;
+  // peer-halo flags restart with the step counter; a multi-rank reset must be bracketed by
+  // the driver's own barrier (no rank may be mid-step while another zeroes)
+  if (e->peer.flags) B200_CUDA(cudaMemsetAsync(e->peer.flags, 0, 2 * sizeof(unsigned long long), e->stream));
   NtffState &n = e->ntff;
   if (n.ready) {
     B200_CUDA(cudaMemsetAsync(n.hist_e, 0, sizeof(double2) * (size_t)n.n_local * n.max_time, e->stream));

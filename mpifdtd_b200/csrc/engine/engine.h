@@ -44,6 +44,20 @@ struct FusedState {          // side buffers of the fused step (fused_kernels.cu
   double2 *col_e, *col_h, *row_e, *row_h;
 };
 
+// Peer (NVLink) halo state of a y-slab engine: the neighbours' field arrays and flag words,
+// opened through CUDA IPC.  flags[0]: "the lower neighbour's H-phase halo of step n has
+// landed in my low ghost column" (value n+1); flags[1]: the same for the upper neighbour's
+// E-phase halo in my high ghost column.
+struct PeerState {
+  bool attached[2];                  // [0] lower neighbour, [1] upper neighbour
+  unsigned long long *flags;         // device, 2 words, owned
+  double2 *up_h, *down_e;            // neighbours' H / E arrays (peer pointers), or nullptr
+  unsigned long long *up_flag;       // the upper neighbour's flags[0]
+  unsigned long long *down_flag;     // the lower neighbour's flags[1]
+  void *opened[6];                   // IPC mappings to close
+  int up_pitch, down_pitch, down_nj;
+};
+
 struct b200fdtd_engine {
   b200fdtd_grid g;
   int device;
@@ -61,6 +75,7 @@ struct b200fdtd_engine {
   bool have_tabs, have_eps[2];
   NtffState ntff;
   FusedState fused;
+  PeerState peer;
   bool use_fused;           // b200fdtd_step runs the one-pass kernel (serial TM kind)
   bool store_h;             // the fused kernel also writes Hx/Hy (264 instead of 232 B/cell)
   bool h_stale;             // Hx/Hy arrays lag Bx/By (fused step without store_h)
@@ -86,6 +101,8 @@ int b200_fail(int code, const char *fmt, ...);
 int b200_launch_upml_h(b200fdtd_engine *e, const b200fdtd_step_args *a);
 int b200_launch_upml_e(b200fdtd_engine *e, const b200fdtd_step_args *a);
 int b200_launch_halo(b200fdtd_engine *e, int which, void *buf, bool pack);
+int b200_peer_wait(b200fdtd_engine *e, int which, unsigned long long value);
+int b200_peer_signal(b200fdtd_engine *e, unsigned long long *peer_flag, unsigned long long value);
 int b200_selftest_division(double divisor, unsigned long long samples, unsigned long long *mismatches);
 
 // launchers (split_kernels.cu)

@@ -21,6 +21,11 @@ struct UpmlView {
   ConstDivisor mu0;             // MU_0_S and its rounded reciprocal
   b200fdtd_pulse pulse[2];
   b200fdtd_cw cw[2];            // CW source of the MPI-variant kinds (mpiTM_UPML.c:337-374)
+  // direct halo stores into the neighbour slabs' ghost columns over NVLink (peer memory):
+  double2 *peer_up_h;           // upper neighbour's H array (Hx / Hz), or nullptr
+  double2 *peer_down_e;         // lower neighbour's E array (Ez / Ex), or nullptr
+  int peer_up_pitch, peer_down_pitch, peer_down_col;
+  int c_first, c_last;          // first / last owned column in layout coordinates
   long long point_k;            // layout offset of the opt-in point source, or -1
   double point_re, point_im;
 };
@@ -126,6 +131,13 @@ inline UpmlView make_view(const b200fdtd_engine *e, const b200fdtd_step_args *a)
   v.pulse[1] = a->pulse[1];
   v.cw[0] = a->cw[0];
   v.cw[1] = a->cw[1];
+  v.peer_up_h = e->peer.up_h;
+  v.peer_down_e = e->peer.down_e;
+  v.peer_up_pitch = e->peer.up_pitch;
+  v.peer_down_pitch = e->peer.down_pitch;
+  v.peer_down_col = B200_JOFF + e->peer.down_nj;   // the lower neighbour's high ghost column
+  v.c_first = B200_JOFF;
+  v.c_last = B200_JOFF + e->g.nj - 1;
   v.point_k = -1;
   v.point_re = a->point.re;
   v.point_im = a->point.im;

@@ -78,6 +78,9 @@ __global__ void __launch_bounds__(kBlock) tm_upml_h_kernel(const UpmlView v)
     v.f[B200FDTD_TM_HX][k] = div_const(bx, v.mu0);   // fdtdTM_upml.c:209
     v.f[B200FDTD_TM_HY][k] = div_const(by, v.mu0);   // fdtdTM_upml.c:216
   }
+  // y-slab halo: my top owned column of Hx is the upper neighbour's low ghost column
+  if (v.peer_up_h != nullptr && c == v.c_last)
+    v.peer_up_h[(size_t)r * v.peer_up_pitch + (B200_JOFF - 1)] = div_const(bx, v.mu0);
 }
 
 // FROM_B = true: H is formed on the fly as B/mu0.  Cells just outside the updated range
@@ -133,6 +136,9 @@ __global__ void __launch_bounds__(kBlock) tm_upml_e_kernel(const UpmlView v)
   v.f[B200FDTD_TM_JZ][k] = jz;
   v.f[B200FDTD_TM_DZ][k] = dz;
   v.f[B200FDTD_TM_EZ][k] = ez;
+  // y-slab halo: my bottom owned column of Ez is the lower neighbour's high ghost column
+  if (v.peer_down_e != nullptr && c == v.c_first)
+    v.peer_down_e[(size_t)r * v.peer_down_pitch + v.peer_down_col] = ez;
 }
 
 // ------------------------------------------------------------------ TE -----
@@ -164,6 +170,8 @@ __global__ void __launch_bounds__(kBlock) te_upml_h_kernel(const UpmlView v)
   v.f[B200FDTD_TE_MZ][k] = mz;
   v.f[B200FDTD_TE_BZ][k] = bz;
   if (STORE_H) v.f[B200FDTD_TE_HZ][k] = div_const(bz, v.mu0);   // fdtdTE_upml.c:312
+  if (v.peer_up_h != nullptr && c == v.c_last)
+    v.peer_up_h[(size_t)r * v.peer_up_pitch + (B200_JOFF - 1)] = div_const(bz, v.mu0);
 }
 
 template <bool FROM_B>
@@ -227,6 +235,8 @@ __global__ void __launch_bounds__(kBlock) te_upml_e_kernel(const UpmlView v)
   v.f[B200FDTD_TE_DY][k] = dy;
   v.f[B200FDTD_TE_EX][k] = ex;
   v.f[B200FDTD_TE_EY][k] = ey;
+  if (v.peer_down_e != nullptr && c == v.c_first)
+    v.peer_down_e[(size_t)r * v.peer_down_pitch + v.peer_down_col] = ex;
 }
 
 // One halo column <-> a contiguous buffer of n_px complex values.
@@ -246,6 +256,43 @@ __global__ void halo_column_kernel(double2 *field, double2 *buf, int pitch, int 
 }
 
 }  // namespace
+
+// ---- cross-GPU ordering without the host: one flag word per direction in each engine's
+// memory.  After a phase whose kernel stored halo values into a neighbour, a one-thread
+// kernel publishes the step number into that neighbour's flag (system-scope release);
+// before a phase that reads a ghost column, a one-thread kernel spins on the local flag
+// (system-scope acquire) until the producing step has been published.  Stream order ties
+// both to the phase kernels, so no NCCL call, host barrier or event is needed per step.
+namespace {
+__global__ void peer_signal_kernel(unsigned long long *peer_flag, unsigned long long value)
+{
+  __threadfence_system();
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(peer_flag), "l"(value) : "memory");
+}
+__global__ void peer_wait_kernel(const unsigned long long *my_flag, unsigned long long value)
+{
+  unsigned long long seen;
+  do {
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(my_flag) : "memory");
+  } while (seen < value);
+}
+}  // namespace
+
+int b200_peer_wait(b200fdtd_engine *e, int which, unsigned long long value)
+{
+  peer_wait_kernel<<<1, 1, 0, e->stream>>>(e->peer.flags + which, value);
+  e->launches++;
+  B200_CUDA(cudaGetLastError());
+  return B200FDTD_OK;
+}
+
+int b200_peer_signal(b200fdtd_engine *e, unsigned long long *peer_flag, unsigned long long value)
+{
+  peer_signal_kernel<<<1, 1, 0, e->stream>>>(peer_flag, value);
+  e->launches++;
+  B200_CUDA(cudaGetLastError());
+  return B200FDTD_OK;
+}
 
 // Device self-test of div_const / quotient_or_one / div_eps against plain IEEE division.
 namespace {

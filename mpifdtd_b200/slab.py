@@ -101,6 +101,20 @@ class SlabRun:
             self.n_local = n_local
         self.args = B.StepArgs()
         self.halo = None
+        self.peer_halos = False
+
+    def enable_peer_halos(self, gather_blobs):
+        """Switch from NCCL send/recv to direct NVLink stores into the neighbours' ghost
+        columns.  `gather_blobs(my_blob) -> [blob of rank 0, ..., blob of rank world-1]` is the
+        only communication needed (once); afterwards a step issues no collective at all."""
+        if self.world == 1:
+            return
+        blobs = gather_blobs(self.engine.peer_export())
+        if self.rank > 0:
+            self.engine.peer_attach(0, blobs[self.rank - 1])
+        if self.rank + 1 < self.world:
+            self.engine.peer_attach(1, blobs[self.rank + 1])
+        self.peer_halos = True
 
     # -- halo buffers are allocated by the communicator (torch tensors) ------
     def attach_halo_buffers(self, send_ptr, recv_ptr):
@@ -118,6 +132,11 @@ class SlabRun:
         e = self.engine
         if self.world == 1:
             e.step(self.args)
+        elif self.peer_halos:       # halo columns travel inside the phase kernels (peer stores)
+            e.phase_h(self.args)
+            e.phase_e(self.args)
+            if self.with_ntff:
+                e.phase_sample(self.args)
         else:
             e.phase_h(self.args)
             self._exchange(0)
@@ -164,6 +183,12 @@ class TorchHaloComm:
 
     def pointers(self):
         return self.send.data_ptr(), self.recv.data_ptr()
+
+    def gather_blobs(self, blob):
+        """all_gather of the 256-byte peer blobs (CUDA IPC handles)."""
+        out = [None] * self.dist.get_world_size()
+        self.dist.all_gather_object(out, blob)
+        return out
 
     def exchange(self, send_ptr, recv_ptr, n_complex, send_to, recv_from):
         dist = self.dist

@@ -18,6 +18,7 @@ solver = sys.argv[1] if len(sys.argv) > 1 else "TM_UPML_2D"
 npx = int(sys.argv[2]) if len(sys.argv) > 2 else 160
 npy = int(sys.argv[3]) if len(sys.argv) > 3 else 240
 steps = int(sys.argv[4]) if len(sys.argv) > 4 else 600
+halo = sys.argv[5] if len(sys.argv) > 5 else "nccl"          # "nccl" or "peer" (direct NVLink stores)
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -28,6 +29,8 @@ with torch.cuda.stream(stream):
                   h_u_nm=20, angle_deg=20)
     run.engine.set_stream(stream.cuda_stream)
     run.attach_halo_buffers(*comm.pointers())
+    if halo == "peer":
+        run.enable_peer_halos(comm.gather_blobs)
     for _ in range(steps):
         run.step()
     mine = [torch.from_numpy(run.gather_field(s).view(np.float64).copy()).cuda() for s in (0, 3, 6)]
@@ -59,7 +62,7 @@ with torch.cuda.stream(stream):
         print("far field rel err vs single GPU:", err)
         ok &= err < 1e-12
         single.close()
-        print("MULTI_GPU_CHECK", "OK" if ok else "FAIL")
+        print("MULTI_GPU_CHECK", halo, "OK" if ok else "FAIL")
 dist.barrier()
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)

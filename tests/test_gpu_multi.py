@@ -11,14 +11,15 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+@pytest.mark.parametrize("halo", ["nccl", "peer"])
 @pytest.mark.parametrize("solver", ["TM_UPML_2D", "TE_UPML_2D"])
-def test_two_rank_nccl_run_matches_single_gpu(solver):
+def test_two_rank_run_matches_single_gpu(solver, halo):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
            "--master-addr", "127.0.0.1", "--master-port", "29517",
-           os.path.join(ROOT, "scripts", "multi_gpu_check.py"), solver, "128", "200", "420"]
+           os.path.join(ROOT, "scripts", "multi_gpu_check.py"), solver, "128", "200", "420", halo]
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
-    assert "MULTI_GPU_CHECK OK" in p.stdout
+    assert "MULTI_GPU_CHECK %s OK" % halo in p.stdout
