@@ -258,6 +258,142 @@ __global__ void __launch_bounds__(32 * WARPS) tm_upml_fused_kernel(const FusedVi
   }
 }
 
+// ---- the same march with the operands staged through shared memory ------------------
+// cp.async (LDGSTS) copies each lane's own 16-byte operands of the next STAGES-1 rows into a
+// per-warp ring in shared memory, so several rows of loads are in flight per warp without
+// holding them in registers (the register-prefetch form above needs 141 registers and
+// leaves 12 warps per SM).  Every lane reads back only what it copied itself: no barrier,
+// no cross-lane hazard; cp.async.wait_group orders a lane's own copies.
+struct __align__(16) TmStage {
+  double2 ez_below[32], mx[32], bx[32], my[32], by[32], jz[32], dz[32];
+  double2 edge_e, edge_h;        // lane 31's old Ez(r, c0+32), lane 0's new Hx(r, c0-1)
+  double eps[32];
+};
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
+{
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void *smem, const void *gmem)
+{
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <bool STORE_H, int WARPS, int STAGES>
+__global__ void __launch_bounds__(32 * WARPS) tm_upml_fused_async_kernel(const FusedView f)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const UpmlView &v = f.u;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int strip = blockIdx.x * WARPS + warp;
+  if (strip >= f.n_strips) return;                      // whole warp leaves together (no block barrier used)
+  TmStage *ring = reinterpret_cast<TmStage *>(smem_raw) + (size_t)warp * STAGES;
+  const int band = blockIdx.y;
+  const int c = v.c_lo + 32 * strip + lane;
+  const bool active = c <= v.c_hi;
+  const bool sees_e = c <= v.c_hi + 1;
+  const int r0 = v.r_lo + band * f.band_h;
+  int r1 = r0 + f.band_h;
+  if (r1 > v.r_hi + 1) r1 = v.r_hi + 1;
+
+  double2 *Ez = v.f[B200FDTD_TM_EZ];
+  const double2 zero = make_double2(0, 0);
+  const double2 *col_e_next = f.col_e + (size_t)(strip + 1) * v.rows;
+  const double2 *col_h_mine = f.col_h + (size_t)strip * v.rows;
+  const double2 *row_e_next = f.row_e + (size_t)(band + 1) * v.pitch;
+
+  TmColCoef cc = { 1.0, 1.0, 2.0, 2.0 };
+  double c_dz = 1, c_dzjz = 1;
+  if (active) {
+    cc = tm_col_coef(v, c);
+    c_dz = v.tj[B200FDTD_TMJ_C_DZ * v.pitch + c];
+    c_dzjz = v.tj[B200FDTD_TMJ_C_DZJZ * v.pitch + c];
+  }
+
+  // issue the copies of row r into its ring slot (each lane: its own elements)
+  auto issue_row = [&](int r) {
+    if (r < r1) {
+      TmStage &st = ring[(r - r0) % STAGES];
+      const size_t k = (size_t)r * v.pitch + c;
+      if (sees_e) cp_async16(&st.ez_below[lane], (r + 1 < r1) ? &Ez[k + v.pitch] : &row_e_next[c]);
+      if (active) {
+        cp_async16(&st.mx[lane], &v.f[B200FDTD_TM_MX][k]);
+        cp_async16(&st.bx[lane], &v.f[B200FDTD_TM_BX][k]);
+        cp_async16(&st.my[lane], &v.f[B200FDTD_TM_MY][k]);
+        cp_async16(&st.by[lane], &v.f[B200FDTD_TM_BY][k]);
+        cp_async16(&st.jz[lane], &v.f[B200FDTD_TM_JZ][k]);
+        cp_async16(&st.dz[lane], &v.f[B200FDTD_TM_DZ][k]);
+        cp_async8(&st.eps[lane], &v.eps0[k]);
+      }
+      if (lane == 31) cp_async16(&st.edge_e, &col_e_next[r]);
+      if (lane == 0) cp_async16(&st.edge_h, &col_h_mine[r]);
+    }
+    cp_async_commit();                                  // one group per row, empty past the band end
+  };
+
+  size_t k = (size_t)r0 * v.pitch + c;
+  double2 ez_cur = sees_e ? Ez[k] : zero;
+  double2 hy_prev = active ? f.row_h[(size_t)band * v.pitch + c] : zero;
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; s++) issue_row(r0 + s);
+
+  for (int r = r0; r < r1; r++, k += v.pitch) {
+    issue_row(r + STAGES - 1);
+    cp_async_wait<STAGES - 1>();                        // this lane's copies of row r have landed
+    const TmStage &st = ring[(r - r0) % STAGES];
+    const TmRowCoef rc = tm_row_coef(v, r);
+    const double c_jz  = v.ti[B200FDTD_TMI_C_JZ * v.rows + r];
+    const double c_jzh = v.ti[B200FDTD_TMI_C_JZHXHY * v.rows + r];
+
+    const double2 ez_below = sees_e ? st.ez_below[lane] : zero;
+    double2 ez_right = shfl_down1(ez_cur);
+    if (lane == 31) ez_right = st.edge_e;
+
+    TmH h;
+    h.hx = zero; h.hy = zero;
+    double2 jz_old = zero, dz_old = zero;
+    double eps = 1.0;
+    if (active) {
+      h = tm_h_cell(v, cc, rc, ez_cur, ez_right, ez_below, st.mx[lane], st.bx[lane], st.my[lane], st.by[lane]);
+      jz_old = st.jz[lane];
+      dz_old = st.dz[lane];
+      eps = st.eps[lane];
+    }
+    double2 hx_left = shfl_up1(h.hx);
+    if (lane == 0) hx_left = st.edge_h;
+
+    if (active) {
+      const double2 jz = c_jz * jz_old + c_jzh * (((h.hy - hy_prev) - h.hx) + hx_left);
+      const double2 dz = (c_dz * dz_old + c_dzjz * jz) - c_dzjz * jz_old;
+      double2 ez = div_eps(dz, eps);
+      if (v.pulse[0].enabled && eps != 1.0)
+        ez = ez + pulse_term(v.pulse[0], r - 1, v.j_base + c, eps);
+      if ((long long)k == v.point_k)
+        ez = ez + make_double2(v.point_re, v.point_im);
+      v.f[B200FDTD_TM_MX][k] = h.mx;
+      v.f[B200FDTD_TM_BX][k] = h.bx;
+      v.f[B200FDTD_TM_MY][k] = h.my;
+      v.f[B200FDTD_TM_BY][k] = h.by;
+      v.f[B200FDTD_TM_JZ][k] = jz;
+      v.f[B200FDTD_TM_DZ][k] = dz;
+      Ez[k] = ez;
+      if (STORE_H) {
+        v.f[B200FDTD_TM_HX][k] = h.hx;
+        v.f[B200FDTD_TM_HY][k] = h.hy;
+      }
+    }
+    hy_prev = h.hy;
+    ez_cur = ez_below;
+  }
+  cp_async_wait<0>();
+}
+
 // H = B / mu0 over the whole plane: refreshes the H arrays when the fused kernel
 // ran without storing them (the identity Hx == Bx/mu0 holds after every H phase).
 // Only updated cells are touched: the ring / ghost cells of H are not derived state.
@@ -328,7 +464,27 @@ int b200_launch_upml_fused(b200fdtd_engine *e, const b200fdtd_step_args *a)
     if (e->store_h) tm_upml_fused_kernel<true, W, L><<<grid, 32 * (W), 0, e->stream>>>(f);      \
     else            tm_upml_fused_kernel<false, W, L><<<grid, 32 * (W), 0, e->stream>>>(f);     \
   } while (0)
+#define FUSED_ASYNC_LAUNCH(W, S)                                                                \
+  do {                                                                                         \
+    dim3 grid((fs.n_strips + (W) - 1) / (W), fs.n_bands);                                      \
+    const size_t smem = sizeof(TmStage) * (W) * (S);                                           \
+    if (e->store_h) {                                                                          \
+      B200_CUDA(cudaFuncSetAttribute(tm_upml_fused_async_kernel<true, W, S>,                   \
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      tm_upml_fused_async_kernel<true, W, S><<<grid, 32 * (W), smem, e->stream>>>(f);          \
+    } else {                                                                                   \
+      B200_CUDA(cudaFuncSetAttribute(tm_upml_fused_async_kernel<false, W, S>,                  \
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      tm_upml_fused_async_kernel<false, W, S><<<grid, 32 * (W), smem, e->stream>>>(f);         \
+    }                                                                                          \
+  } while (0)
   switch (variant) {
+  case 10: FUSED_ASYNC_LAUNCH(4, 3); break;
+  case 11: FUSED_ASYNC_LAUNCH(4, 4); break;
+  case 12: FUSED_ASYNC_LAUNCH(2, 4); break;
+  case 13: FUSED_ASYNC_LAUNCH(8, 3); break;
+  case 14: FUSED_ASYNC_LAUNCH(4, 2); break;
+  case 15: FUSED_ASYNC_LAUNCH(2, 6); break;
   case 1: FUSED_LAUNCH(8, false); break;
   case 2: FUSED_LAUNCH(8, true); break;
   case 3: FUSED_LAUNCH(4, true); break;
@@ -337,6 +493,7 @@ int b200_launch_upml_fused(b200fdtd_engine *e, const b200fdtd_step_args *a)
   default: FUSED_LAUNCH(4, false); break;
   }
 #undef FUSED_LAUNCH
+#undef FUSED_ASYNC_LAUNCH
   e->launches += 3;
   e->h_stale = !e->store_h;
   B200_CUDA(cudaGetLastError());

@@ -19,7 +19,7 @@ from mpifdtd_b200 import binding as B
 pytestmark = pytest.mark.gpu
 
 
-def make_engine(L, npx, npy, steps, eps, fused, store_h=0, band=None, j0=0, nj=None):
+def make_engine(L, npx, npy, steps, eps, fused, store_h=0, band=None, j0=0, nj=None, shape=0):
     eng = B.Engine(2, npx, npy, 10, j0=j0, nj=nj)
     ti, tj = np.empty((6, npx)), np.empty((6, npy))
     L.mpifdtd_upml_tables(2, ti.ctypes.data, tj.ctypes.data)
@@ -38,6 +38,8 @@ def make_engine(L, npx, npy, steps, eps, fused, store_h=0, band=None, j0=0, nj=N
     eng.set_option(B.OPT_STORE_H, store_h)
     if fused and band:
         eng.set_option(B.OPT_BAND_ROWS, band)
+    if fused:
+        eng.set_option(B.OPT_FUSED_SHAPE, shape)
     return eng
 
 
@@ -58,7 +60,9 @@ def test_fused_step_is_bit_identical_to_two_kernel_step(plugin_lib, npx, npy, ba
     engines = [make_engine(L, npx, npy, steps, eps, 0, store_h=1),
                make_engine(L, npx, npy, steps, eps, 0, store_h=0),
                make_engine(L, npx, npy, steps, eps, 1, store_h=0, band=band),
-               make_engine(L, npx, npy, steps, eps, 1, store_h=1, band=band)]
+               make_engine(L, npx, npy, steps, eps, 1, store_h=1, band=band),
+               make_engine(L, npx, npy, steps, eps, 1, store_h=0, band=band, shape=10),    # cp.async staged
+               make_engine(L, npx, npy, steps, eps, 1, store_h=1, band=band, shape=13)]
     for eng in engines:
         for slot in range(9):
             eng.set_field(slot, state[slot])
