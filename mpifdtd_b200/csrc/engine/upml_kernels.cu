@@ -17,6 +17,13 @@
 // = 512 contiguous bytes per field, every access a 128-bit LDG/STG.
 #include "upml_common.cuh"
 
+#ifndef B200_H_MIN_BLOCKS
+#define B200_H_MIN_BLOCKS 1
+#endif
+#ifndef B200_E_MIN_BLOCKS
+#define B200_E_MIN_BLOCKS 5   /* <= 51 registers: measured 23.4 -> 24.4 Gcell/s at 16384^2 */
+#endif
+
 namespace {
 
 using namespace upml;
@@ -39,7 +46,7 @@ __device__ __forceinline__ bool locate(const UpmlView &v, int &r, int &c, size_t
 // (Hx == Bx/mu0 exactly, fdtdTM_upml.c:209), which removes one 32 B/cell write and turns
 // the E phase's H reads into B reads: 264 instead of 296 B per cell-update, in place.
 template <bool STORE_H>
-__global__ void __launch_bounds__(kBlock) tm_upml_h_kernel(const UpmlView v)
+__global__ void __launch_bounds__(kBlock, B200_H_MIN_BLOCKS) tm_upml_h_kernel(const UpmlView v)
 {
   int r, c; size_t k;
   if (!locate(v, r, c, k)) return;
@@ -87,7 +94,7 @@ __global__ void __launch_bounds__(kBlock) tm_upml_h_kernel(const UpmlView v)
 // (the ring, or a neighbour slab's halo column) are not derived state: there the H array
 // itself is read, exactly like the STORE_H form does.
 template <bool FROM_B>
-__global__ void __launch_bounds__(kBlock) tm_upml_e_kernel(const UpmlView v)
+__global__ void __launch_bounds__(kBlock, B200_E_MIN_BLOCKS) tm_upml_e_kernel(const UpmlView v)
 {
   int r, c; size_t k;
   if (!locate(v, r, c, k)) return;
