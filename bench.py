@@ -48,6 +48,21 @@ BYTES_E_TM = 120             # E-phase kernel: reads Bx,By,Jz,Dz (64) + eps (8) 
 FALLBACK_HBM_GBS = 6650.0    # B200_PROFILING.md fallback
 
 
+def ncu_traffic(kernel_substr, cells):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
+    of this same command (profiles/*_full.json, written by scripts/ncu_summary.py); None when no
+    capture at this launch size is on file."""
+    import glob
+    for path in sorted(glob.glob(os.path.join(HERE, "profiles", "*_full.json")), reverse=True):
+        try:
+            for rec in json.load(open(path))["launches"]:
+                if kernel_substr in rec["kernel"] and abs(rec.get("cells", 0) - cells) < 0.01 * cells:
+                    return rec["traffic_bytes"], os.path.relpath(path, HERE)
+        except Exception:
+            continue
+    return None, None
+
+
 def measured_hbm_peak():
     try:
         with open(os.path.join(HERE, "MEASURED_PEAKS.json")) as f:
@@ -341,6 +356,7 @@ def gpu_arm(args):
         ach_h = bytes_h * cells_rank / (ms_h * 1e-3) / 1e9
         ach_e = bytes_e * cells_rank / (ms_e * 1e-3) / 1e9
         step_gbs = bytes_step * (value / world) * 1e9 / 1e9
+        traffic, traffic_src = ncu_traffic(kname + "_upml_h_kernel<0>", cells_rank)
         line = {
             "metric": "Gcell-updates/s", "value": value, "unit": "Gcell-updates/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_max / K,
@@ -351,7 +367,8 @@ def gpu_arm(args):
                                             "nccl": "NCCL send/recv"}[args.halo]),
             "roofline": {"bound": "hbm", "kernel": kname + "_upml_h_kernel<STORE_H=false>", "achieved": ach_h,
                          "peak": peak, "unit": "GB/s", "frac": ach_h / peak, "peak_source": peak_kind,
-                         "traffic": None, "ms_per_launch": ms_h,
+                         "traffic": traffic, "traffic_source": traffic_src,
+                         "algorithmic_bytes_per_launch": bytes_h * cells_rank, "ms_per_launch": ms_h,
                          "algorithmic_bytes_per_cell": bytes_h,
                          "e_phase": {"kernel": kname + "_upml_e_kernel<FROM_B=true>", "achieved": ach_e,
                                      "frac": ach_e / peak, "ms_per_launch": ms_e,

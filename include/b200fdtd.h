@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define B200FDTD_ABI_VERSION 2
+#define B200FDTD_ABI_VERSION 3
 
 enum {
   B200FDTD_OK = 0,
@@ -136,6 +136,17 @@ typedef struct b200fdtd_cw {
   double phase_a, phase_b;
 } b200fdtd_cw;
 
+/* planeWave of mpiTM_UPML.c:377-403 (no caller upstream: the call at mpiTM_UPML.c:204 is
+ * commented out; opt-in here): on the cells (i, j_lo..j_hi) of one grid row,
+ *   p += scale * cexp(I * ((i*ks_cos + j*ks_sin) - time) * omega)
+ * with i, j GLOBAL cell indices.  TM kinds, target Ez. */
+typedef struct b200fdtd_line_source {
+  int32_t enabled, i, j_lo, j_hi;
+  double scale;                    /* field_getRayCoef()                              */
+  double ks_cos, ks_sin;           /* cos(rad)*k_s, sin(rad)*k_s                       */
+  double time, omega;
+} b200fdtd_line_source;
+
 /* Everything one update() call depends on that the host owns (field.c:44-51). */
 typedef struct b200fdtd_step_args {
   double time;                     /* field_getTime() BEFORE field_nextStep()         */
@@ -145,6 +156,7 @@ typedef struct b200fdtd_step_args {
   b200fdtd_cw cw[2];               /* CW sources: target 0 / 1 of the solver kind     */
   double ns_r2;                    /* NS-FDTD: r/2 of the 9-point operator             */
                                    /* (nsFdtdTM.c:115-117), 0 otherwise               */
+  b200fdtd_line_source line;       /* opt-in plane-wave line source (TM UPML kinds)    */
 } b200fdtd_step_args;
 
 /* Closed NTFF surface (NTFFInfo, field.h:62-68) and its sampling plan.
@@ -170,6 +182,12 @@ typedef struct b200fdtd_ntff_plan {
                                    /* bound check).  The projection reproduces that   */
                                    /* spill; 0 disables it.                           */
   const double *time_shift;        /* host, [n_angles][n_local]                       */
+  /* ntff() of the MPI-variant solvers (mpiTM_UPML.c:849-1037, mpiTE_UPML.c:602-794):  */
+  double tap_scale;                /* every tap is (v*w)*tap_scale; they multiply by   */
+                                   /* coef = 1/(4 pi C 1e6) per step.  0 or 1: no scale */
+  int32_t sample_di, sample_dj;    /* surface point (i, j) reads the fields at global   */
+                                   /* cell (i+di, j+dj): those solvers use box indices  */
+                                   /* as LOCAL indices, and local i <-> global i-1      */
 } b200fdtd_ntff_plan;
 
 /* Far-field post-processing, ntffT?_TimeTranslate + TimeOutput
@@ -190,6 +208,10 @@ typedef struct b200fdtd_spectrum_args {
 int b200fdtd_device_count(int *count);
 const char *b200fdtd_last_error(void);
 int b200fdtd_abi_version(void);
+/* sizeof() of the ABI structs as this library was compiled, for foreign-language bindings to
+ * check their mirror declarations: which = 0 grid, 1 step_args, 2 ntff_plan, 3 spectrum_args,
+ * 4 freq_args; -1 for an unknown index. */
+int b200fdtd_struct_size(int32_t which);
 
 int b200fdtd_create(const b200fdtd_grid *grid, b200fdtd_engine **out);   /* allocateMemories */
 int b200fdtd_destroy(b200fdtd_engine *e);                                /* freeMemories     */

@@ -194,6 +194,19 @@ extern void ntff_outputEnormBin(double **e_norm, const char *file_name);  /* ntf
  * solver's current fields.  result[360] as the reference's resultEz. */
 extern int mpifdtd_ntffFrequency(int solver_id, double complex result[360]);
 
+/* ---- opt-in source forms (extensions; nothing of the reference calls them) ------------
+ * The reference carries source injectors it never calls.  These switches wire them in; they
+ * are read by the next init().  Default: the sources update() hard-wires.
+ *   mpifdtd_enablePointSource(1): field_pointLight() (field.c:145-152) added to Ez (TM) / Ex
+ *     (TE) at the grid centre -- gives the NoModel configuration something to propagate.
+ *   mpifdtd_setSourceForm(MPIFDTD_SRC_CW): serial TM UPML uses field_scatteredWave
+ *     (field.c:202-218) instead of the pulse, the commented line at fdtdTM_upml.c:62.
+ *   mpifdtd_setSourceForm(MPIFDTD_SRC_PLANE): planeWave (mpiTM_UPML.c:377-403, commented call
+ *     at mpiTM_UPML.c:204) added on Ez for solver ids 2 and 4. */
+enum { MPIFDTD_SRC_DEFAULT = 0, MPIFDTD_SRC_CW = 1, MPIFDTD_SRC_PLANE = 2 };
+extern void mpifdtd_enablePointSource(int on);
+extern void mpifdtd_setSourceForm(int form);
+
 /* ---- config.txt (parser.h:5, configSample.txt:6-22, main.c:319-366) ------ */
 extern bool parser_nextLine(FILE *fp, char buf[]);            /* parser.c:3 */
 typedef struct MpifdtdConfig {

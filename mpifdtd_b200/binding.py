@@ -69,16 +69,24 @@ class CwSource(C.Structure):
                 ("ks_sin", C.c_double), ("phase_a", C.c_double), ("phase_b", C.c_double)]
 
 
+class LineSource(C.Structure):
+    _fields_ = [("enabled", C.c_int32), ("i", C.c_int32), ("j_lo", C.c_int32), ("j_hi", C.c_int32),
+                ("scale", C.c_double), ("ks_cos", C.c_double), ("ks_sin", C.c_double),
+                ("time", C.c_double), ("omega", C.c_double)]
+
+
 class StepArgs(C.Structure):
     _fields_ = [("time", C.c_double), ("ray_coef", C.c_double), ("pulse", Pulse * 2),
-                ("point", PointSource), ("cw", CwSource * 2), ("ns_r2", C.c_double)]
+                ("point", PointSource), ("cw", CwSource * 2), ("ns_r2", C.c_double),
+                ("line", LineSource)]
 
 
 class NtffPlan(C.Structure):
     _fields_ = [("top", C.c_int32), ("bottom", C.c_int32), ("left", C.c_int32), ("right", C.c_int32),
                 ("n_points", C.c_int32), ("n_local", C.c_int32), ("max_time", C.c_int32),
                 ("n_bins", C.c_int32), ("n_angles", C.c_int32), ("array_size", C.c_int32),
-                ("time_shift", C.c_void_p)]
+                ("time_shift", C.c_void_p), ("tap_scale", C.c_double),
+                ("sample_di", C.c_int32), ("sample_dj", C.c_int32)]
 
 
 class SpectrumArgs(C.Structure):
@@ -181,6 +189,8 @@ def lib():
     L.mpifdtd_upml_engine.argtypes = [C.c_int]
     L.mpifdtd_upml_engine.restype = vp
     L.mpifdtd_enablePointSource.argtypes = [C.c_int]
+    L.mpifdtd_setSourceForm.argtypes = [C.c_int]
+    L.b200fdtd_struct_size.argtypes = [i32]
     L.mpifdtd_readConfig.argtypes = [C.c_char_p, vp]
     for name in ("fdtdTM_upml_getHx", "fdtdTM_upml_getHy", "fdtdTM_upml_getEz",
                  "fdtdTE_upml_getEx", "fdtdTE_upml_getEy", "fdtdTE_upml_getHz",
@@ -217,6 +227,9 @@ def _as_complex(ptr, n_px, n_py):
     return np.frombuffer(buf, dtype=np.complex128).reshape(n_px, n_py)
 
 
+SOURCE_FORMS = dict(DEFAULT=0, CW=1, PLANE=2)       # MPIFDTD_SRC_* of mpifdtd_plugin.h
+
+
 class Plugin:
     """The reference's driver sequence against the plugin surface."""
 
@@ -230,7 +243,7 @@ class Plugin:
                7: {f: "nsFdtdTE_get" + f for f in ("Ex", "Ey", "Hz", "Hzx", "Hzy")}}
 
     def __init__(self, model, solver, n_px, n_py=None, steps=100, h_u_nm=10, pml=10,
-                 lambda_nm=500, angle_deg=0, point_source=False):
+                 lambda_nm=500, angle_deg=0, point_source=False, source_form=0):
         self.L = lib()
         self.model = MODELS[model] if isinstance(model, str) else int(model)
         self.solver = SOLVERS[solver] if isinstance(solver, str) else int(solver)
@@ -238,6 +251,7 @@ class Plugin:
         self.n_px, self.n_py, self.steps = n_px, n_py, steps
         self.info = FieldInfo(n_px * h_u_nm, n_py * h_u_nm, h_u_nm, pml, lambda_nm, angle_deg, steps)
         self.L.mpifdtd_enablePointSource(1 if point_source else 0)
+        self.L.mpifdtd_setSourceForm(SOURCE_FORMS[source_form] if isinstance(source_form, str) else source_form)
         self.L.models_setModel(self.model)
         self.L.simulator_setSolver(self.solver)
         self.L.simulator_init(self.info)
@@ -364,8 +378,9 @@ class Engine:
         assert ts.shape == (n_angles, n_points)
         self.n_bins = max_time if n_bins is None else n_bins
         array_size = box.arraySize if array_size is None else array_size
-        plan = NtffPlan(box.top, box.bottom, box.left, box.right, n_points, max_time, self.n_bins,
-                        n_angles, array_size, 0, ts.ctypes.data)
+        plan = NtffPlan(top=box.top, bottom=box.bottom, left=box.left, right=box.right,
+                        n_points=n_points, n_local=n_points, max_time=max_time, n_bins=self.n_bins,
+                        n_angles=n_angles, array_size=array_size, time_shift=ts.ctypes.data)
         check(self.L.b200fdtd_set_ntff_plan(self.h, C.byref(plan)), "set_ntff_plan")
 
     def step(self, args):

@@ -69,6 +69,18 @@ static void peer_release(b200fdtd_engine *e);
 const char *b200fdtd_last_error(void) { return g_last_error; }
 int b200fdtd_abi_version(void) { return B200FDTD_ABI_VERSION; }
 
+int b200fdtd_struct_size(int32_t which)
+{
+  switch (which) {
+  case 0: return (int)sizeof(b200fdtd_grid);
+  case 1: return (int)sizeof(b200fdtd_step_args);
+  case 2: return (int)sizeof(b200fdtd_ntff_plan);
+  case 3: return (int)sizeof(b200fdtd_spectrum_args);
+  case 4: return (int)sizeof(b200fdtd_freq_args);
+  default: return -1;
+  }
+}
+
 int b200fdtd_device_count(int *count)
 {
   if (!count) return b200_fail(B200FDTD_ERR_ARG, "count is NULL");
@@ -350,8 +362,9 @@ int b200fdtd_set_ntff_plan(b200fdtd_engine *e, const b200fdtd_ntff_plan *p)
   const b200fdtd_grid &g = e->g;
   const int nx = p->right - p->left, ny = p->top - p->bottom;
   if (nx <= 0 || ny <= 0 || p->n_points != 2 * nx + 2 * ny || p->max_time < 1 ||
-      p->n_bins < 1 || p->n_angles < 1 || p->left < 1 || p->bottom < 1 ||
-      p->right >= g.n_px || p->top >= g.n_py)
+      p->n_bins < 1 || p->n_angles < 1 || p->left + p->sample_di < 0 || p->bottom + p->sample_dj < 0 ||
+      p->left < 1 || p->bottom < 1 || p->right >= g.n_px || p->top >= g.n_py ||
+      p->right + p->sample_di >= g.n_px || p->top + p->sample_dj >= g.n_py)
     return b200_fail(B200FDTD_ERR_ARG, "inconsistent NTFF plan (box %d..%d x %d..%d, %d points)",
                      p->left, p->right, p->bottom, p->top, p->n_points);
   B200_CUDA(cudaStreamSynchronize(e->stream));
@@ -361,10 +374,14 @@ int b200fdtd_set_ntff_plan(b200fdtd_engine *e, const b200fdtd_ntff_plan *p)
   n.n_points_global = p->n_points;
   n.max_time = p->max_time; n.n_bins = p->n_bins; n.n_angles = p->n_angles;
   n.array_size = p->array_size;
+  n.tap_scale = p->tap_scale != 0.0 ? p->tap_scale : 1.0;
 
-  // perimeter in the reference's loop order, keeping the points this slab owns
+  // perimeter in the reference's loop order, keeping the points this slab owns; the cell
+  // actually read is (i + sample_di, j + sample_dj) (non-zero for the MPI-variant ids only)
   std::vector<NtffPoint> pts;
+  const int di = p->sample_di, dj = p->sample_dj;
   auto push = [&](int i, int j, int edge, int pg) {
+    i += di; j += dj;
     if (j < g.j0 || j >= g.j0 + g.nj) return;
     NtffPoint q;
     q.k = (long long)(i + 1) * e->pitch + (j - g.j0) + B200_JOFF;
@@ -481,7 +498,7 @@ int b200fdtd_step(b200fdtd_engine *e, const b200fdtd_step_args *a)
   int rc = check_ready(e, a); if (rc) return rc;
   if (kind_is_split(e->g.kind)) return b200_launch_split_step(e, a);
   const bool e_first = (e->g.kind == B200FDTD_MPI_TM_UPML || e->g.kind == B200FDTD_MPI_TE_UPML);
-  if (e->use_fused && e->g.kind == B200FDTD_TM_UPML) {
+  if (e->use_fused && e->g.kind == B200FDTD_TM_UPML && !a->line.enabled && !a->cw[0].enabled) {
     rc = b200_launch_upml_fused(e, a);          // H and E in one pass
   } else if (e_first) {              // mpiTM_UPML.c:196-217: E, source, H, NTFF
     rc = b200_launch_upml_e(e, a);

@@ -31,6 +31,7 @@ struct NtffState {
   int n_points_global;
   int n_local;              // perimeter points whose column lies in this slab
   int max_time, n_bins, n_angles, array_size;
+  double tap_scale;         // per-tap factor of the MPI-variant ntff() (1 = none)
   NtffPoint *pts;           // device [n_local]
   double *ts;               // device [n_angles][n_local]
   double2 *hist_e, *hist_h; // device [n_local][max_time]

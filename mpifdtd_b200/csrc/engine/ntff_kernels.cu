@@ -88,7 +88,7 @@ constexpr int kProjBlock = 128;
 constexpr int kSpillBins = 8;
 
 __device__ __forceinline__ void gather(double2 &acc, const double2 *__restrict__ series, int max_time,
-                                       int q, double ts, double lag, int t_center, int reach)
+                                       int q, double ts, double lag, int t_center, int reach, double scale)
 {
   for (int dt = -reach; dt <= reach; dt++) {
     const int t = t_center + dt;
@@ -100,7 +100,9 @@ __device__ __forceinline__ void gather(double2 &acc, const double2 *__restrict__
     const double a = (0.5 + T) - m;
     const double b = 1.0 - a;
     const double w = tap < 0 ? b : (tap == 0 ? a - b : -a);
-    acc = cadd(acc, rmul(w, series[t]));
+    // scale = 1 (exact identity) for the serial solvers; the MPI-variant ntff() multiplies
+    // every tap by coef after the weight: Ux[..] += ez*b_e*coef (mpiTM_UPML.c:901-906)
+    acc = cadd(acc, rmul(scale, rmul(w, series[t])));
   }
 }
 
@@ -108,7 +110,7 @@ __global__ void __launch_bounds__(kProjBlock)
 ntff_project_kernel(const NtffPoint *__restrict__ pts, const double *__restrict__ ts_tab, int n_local,
                     const double2 *__restrict__ hist_e, const double2 *__restrict__ hist_h,
                     int max_time, int steps, int n_bins, int n_angles, int is_tm, int array_size,
-                    double2 *uw)
+                    double tap_scale, double2 *uw)
 {
   __shared__ double s_ts[kProjBlock];
   __shared__ int s_edge[kProjBlock];
@@ -157,8 +159,8 @@ ntff_project_kernel(const NtffPoint *__restrict__ pts, const double *__restrict_
       const int slot_e = is_tm ? (along_x ? 0 : 1) : 2;
       const int slot_h = is_tm ? 2 : (along_x ? 0 : 1);
       if (q < n_bins) {
-        gather(acc[slot_e], hist_e + (size_t)p * max_time, t_limit, q, ts, 1.0, q - shift_e, reach_e);
-        gather(acc[slot_h], hist_h + (size_t)p * max_time, t_limit, q, ts, 0.5, q - shift_h, reach_h);
+        gather(acc[slot_e], hist_e + (size_t)p * max_time, t_limit, q, ts, 1.0, q - shift_e, reach_e, tap_scale);
+        gather(acc[slot_h], hist_h + (size_t)p * max_time, t_limit, q, ts, 0.5, q - shift_h, reach_h, tap_scale);
       }
     }
     __syncthreads();
@@ -193,9 +195,9 @@ ntff_project_kernel(const NtffPoint *__restrict__ pts, const double *__restrict_
           const int slot_e = is_tm ? (along_x ? 0 : 1) : 2;
           const int slot_h = is_tm ? 2 : (along_x ? 0 : 1);
           gather(acc[slot_e], hist_e + (size_t)p * max_time, t_limit, qv, ts, 1.0,
-                 qv - ((int)floor(ts + 0.5) - 1), 2);
+                 qv - ((int)floor(ts + 0.5) - 1), 2, tap_scale);
           gather(acc[slot_h], hist_h + (size_t)p * max_time, t_limit, qv, ts, 0.5,
-                 qv - (int)floor(ts), 2);
+                 qv - (int)floor(ts), 2, tap_scale);
         }
       }
       __syncthreads();
@@ -368,7 +370,7 @@ int b200_launch_ntff_project(b200fdtd_engine *e)
   dim3 grid((n.n_bins + kProjBlock - 1) / kProjBlock, n.n_angles);
   ntff_project_kernel<<<grid, kProjBlock, 0, e->stream>>>(
       n.pts, n.ts, n.n_local, n.hist_e, n.hist_h, n.max_time, n.steps_recorded, n.n_bins,
-      n.n_angles, is_tm(e->g.kind) ? 1 : 0, n.array_size, n.uw);
+      n.n_angles, is_tm(e->g.kind) ? 1 : 0, n.array_size, n.tap_scale, n.uw);
   e->launches++;
   B200_CUDA(cudaGetLastError());
   return B200FDTD_OK;

@@ -26,6 +26,7 @@ struct UpmlView {
   double2 *peer_down_e;         // lower neighbour's E array (Ez / Ex), or nullptr
   int peer_up_pitch, peer_down_pitch, peer_down_col;
   int c_first, c_last;          // first / last owned column in layout coordinates
+  b200fdtd_line_source line;    // opt-in planeWave line source (mpiTM_UPML.c:377-403)
   long long point_k;            // layout offset of the opt-in point source, or -1
   double point_re, point_im;
 };
@@ -107,6 +108,15 @@ __device__ __forceinline__ double2 cw_eps_term(const b200fdtd_cw &s, int i, int 
   return make_double2(amp * cs, amp * sn);
 }
 
+// planeWave (mpiTM_UPML.c:396-400): kr = (x*ks_cos + y*ks_sin) - time; p += ray_coef*cexp(I*kr*w_s)
+__device__ __forceinline__ double2 line_term(const b200fdtd_line_source &s, int i, int j)
+{
+  const double kr = (i * s.ks_cos + j * s.ks_sin) - s.time;
+  double sn, cs;
+  sincos(kr * s.omega, &sn, &cs);
+  return make_double2(s.scale * cs, s.scale * sn);
+}
+
 inline bool is_tm(int kind) { return kind == B200FDTD_TM_UPML || kind == B200FDTD_MPI_TM_UPML; }
 
 inline UpmlView make_view(const b200fdtd_engine *e, const b200fdtd_step_args *a)
@@ -138,6 +148,7 @@ inline UpmlView make_view(const b200fdtd_engine *e, const b200fdtd_step_args *a)
   v.peer_down_col = B200_JOFF + e->peer.down_nj;   // the lower neighbour's high ghost column
   v.c_first = B200_JOFF;
   v.c_last = B200_JOFF + e->g.nj - 1;
+  v.line = a->line;
   v.point_k = -1;
   v.point_re = a->point.re;
   v.point_im = a->point.im;

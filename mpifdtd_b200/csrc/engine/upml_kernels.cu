@@ -139,6 +139,10 @@ __global__ void __launch_bounds__(kBlock, B200_E_MIN_BLOCKS) tm_upml_e_kernel(co
     ez = ez + cw_eps_term(v.cw[0], r - 1, v.j_base + c, eps);
   if ((long long)k == v.point_k)
     ez = ez + make_double2(v.point_re, v.point_im);
+  if (v.line.enabled && r - 1 == v.line.i) {  // block-uniform: one grid row
+    const int j = v.j_base + c;
+    if (j >= v.line.j_lo && j <= v.line.j_hi) ez = ez + line_term(v.line, r - 1, j);
+  }
 
   v.f[B200FDTD_TM_JZ][k] = jz;
   v.f[B200FDTD_TM_DZ][k] = dz;

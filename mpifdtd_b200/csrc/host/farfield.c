@@ -84,6 +84,41 @@ double *mpifdtd_ntff_time_shift(const NTFFInfo *box, int n_angles, double stagge
   return table;
 }
 
+/* The MPI-variant solvers' ntff() (mpiTM_UPML.c:849-1037, mpiTE_UPML.c:602-794) evaluates
+ * timeShift = -(r1x*r2x + r1y*r2y)/C + RFperC afresh at every surface point, with
+ * r1 = (cos, sin) NOT pre-divided by C, and (TE) the half-cell stagger added to the integer
+ * difference: r2x = i - cx + 0.5.  Same point order as above; whole surface (one rank). */
+double *mpifdtd_ntff_time_shift_direct(const NTFFInfo *box, int n_angles, double stagger)
+{
+  const int nx = box->right - box->left, ny = box->top - box->bottom;
+  const int P = 2 * nx + 2 * ny;
+  double *table = (double *)malloc(sizeof(double) * (size_t)n_angles * (size_t)(P > 0 ? P : 1));
+  if (table == NULL) { printf("cannot allocate NTFF time-shift table\n"); exit(2); }
+  const int cx = box->cx, cy = box->cy;          /* N_PX/2 - offsetX with offset 0 */
+  for (int a = 0; a < n_angles; a++) {
+    double rad = a * M_PI / 180.0;
+    double r1x = cos(rad), r1y = sin(rad);
+    double *row = table + (size_t)a * P;
+    int q = 0;
+    for (int edge = 0; edge < 4; edge++) {
+      const int along_x = (edge == 0 || edge == 2);
+      const int len = along_x ? nx : ny;
+      for (int n = 0; n < len; n++) {
+        double r2x, r2y;
+        if (along_x) {
+          const int i = box->left + n, j = (edge == 0) ? box->bottom : box->top;
+          r2x = i - cx + stagger;  r2y = j - cy;
+        } else {
+          const int i = (edge == 1) ? box->right : box->left, j = box->bottom + n;
+          r2x = i - cx;            r2y = j - cy + stagger;
+        }
+        row[q++] = -(r1x * r2x + r1y * r2y) / C_0_S + box->RFperC;
+      }
+    }
+  }
+  return table;
+}
+
 /* 1/(4 pi C) * csqrt(2 pi C / (i omega))  (ntffTM.c:165, ntffTE.c:25) */
 double complex mpifdtd_ntff_translate_coef(double omega)
 {

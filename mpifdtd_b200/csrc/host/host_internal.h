@@ -15,6 +15,7 @@ extern void mpifdtd_fill_eps_slab(double *dst, double xoff, double yoff, enum MO
 extern int mpifdtd_ntff_point_count(const NTFFInfo *box);
 extern int mpifdtd_ntff_local_count(const NTFFInfo *box, int j0, int nj);
 extern double *mpifdtd_ntff_time_shift(const NTFFInfo *box, int n_angles, double stagger, int j0, int nj);
+extern double *mpifdtd_ntff_time_shift_direct(const NTFFInfo *box, int n_angles, double stagger);
 extern double complex mpifdtd_ntff_translate_coef(double omega);
 extern void mpifdtd_ntff_direction_cosines(int n_angles, int is_tm, double *cos_phi, double *sin_phi);
 extern double complex *mpifdtd_fft_twiddles(int n);
@@ -23,7 +24,9 @@ extern double complex *mpifdtd_fft_twiddles(int n);
 #include "b200fdtd.h"
 extern void mpifdtd_upml_step_args(int kind, int point_source, b200fdtd_step_args *a);
 extern void mpifdtd_upml_far_field(b200fdtd_engine *engine, int kind, int project, double *table);
-extern void mpifdtd_enablePointSource(int on);
+extern void mpifdtd_upml_step_args_form(int kind, int point_source, int form, b200fdtd_step_args *a);
+/* E_theta / E_phi [360][maxTime] of the MPI TE solver (mpiTE_UPML.c:840-878) */
+extern int mpifdtd_mpi_te_far_series(dcomplex *eth, dcomplex *eph);
 extern int mpifdtd_upml_dense_coefficient(int kind, const char *name, double *dst);
 /* the twelve 1-D tables of include/b200fdtd.h for the current field_init() state */
 extern void mpifdtd_upml_tables(int kind, double *tab_i, double *tab_j);

@@ -39,6 +39,7 @@ typedef struct UpmlSolver {
   dcomplex *mirror[3];            /* pinned mirrors for the X, Y, Z getters        */
   int n_cell;
   int point_source;               /* opt-in, see mpifdtd_enablePointSource         */
+  int source_form;                /* opt-in, see mpifdtd_setSourceForm             */
   double *eps_ringed;             /* MPI-variant ids: eps map inside its ghost ring */
 } UpmlSolver;
 
@@ -47,15 +48,16 @@ static UpmlSolver te_solver = { .kind = B200FDTD_TE_UPML };
 /* The "MPI" solver ids (mpiTM_UPML.c, mpiTE_UPML.c) run here as rank 0 of 1: same
  * recurrences and coefficients, but E phase first, a CW source, every one of the N x N
  * cells updated against a zero ghost ring, and (N+2) x (N+2) arrays behind the getters
- * (mpiTM_UPML.c:196-217, 337-374, 674-716, 737-743).  Their per-step ntff() fills arrays
- * the TM solver never writes out (the call is commented, mpiTM_UPML.c:240) and is not
- * rebuilt; multi-GPU decomposition is the y-slab path of mpifdtd_b200/slab.py instead. */
+ * (mpiTM_UPML.c:196-217, 337-374, 674-716, 737-743).  Their per-step ntff() runs through the
+ * same sample + deferred-projection kernels with its own plan (see solver_init); multi-GPU
+ * decomposition is the y-slab path of mpifdtd_b200/slab.py instead. */
 static UpmlSolver mpi_tm_solver = { .kind = B200FDTD_MPI_TM_UPML };
 static UpmlSolver mpi_te_solver = { .kind = B200FDTD_MPI_TE_UPML };
 
 static int is_mpi_kind(int kind) { return kind == B200FDTD_MPI_TM_UPML || kind == B200FDTD_MPI_TE_UPML; }
 static int is_tm_kind(int kind)  { return kind == B200FDTD_TM_UPML || kind == B200FDTD_MPI_TM_UPML; }
 static int point_source_requested;
+static int source_form_requested;      /* MPIFDTD_SRC_* */
 
 static void die_on(int rc, const char *what)
 {
@@ -68,6 +70,18 @@ static void die_on(int rc, const char *what)
  * field.c:145-152, has no caller).  Exists so the NoModel configuration, whose
  * scattered-field sources are identically zero, has something to propagate. */
 void mpifdtd_enablePointSource(int on) { point_source_requested = on; }
+
+/* Opt-in source forms the reference carries but does not call:
+ *   MPIFDTD_SRC_CW     serial TM UPML: field_scatteredWave(Ez, EPS_EZ, 0, 0) INSTEAD of the
+ *                      pulse -- the commented alternative at fdtdTM_upml.c:62 (field.c:202-218)
+ *   MPIFDTD_SRC_PLANE  planeWave(Ez, EPS_EZ) (mpiTM_UPML.c:377-403) IN ADDITION to the
+ *                      solver's own source, as the commented call at mpiTM_UPML.c:204 would:
+ *                      a line source on the grid row of the NTFF box's left edge.  Id 4 keeps
+ *                      the local/global shift (local i = left is global left-1, all N columns);
+ *                      the serial TM UPML solver, which has no ghost ring, drives global row
+ *                      `left`, columns 1..N_PY-2.
+ * Read at init(), like the point source. */
+void mpifdtd_setSourceForm(int form) { source_form_requested = form; }
 
 /* ---- coefficient tables ------------------------------------------------------
  * Same expressions as setCoefficient (fdtdTM_upml.c:230-271, fdtdTE_upml.c:367-409)
@@ -205,6 +219,7 @@ static void solver_init(UpmlSolver *s)
   const size_t sub_cells = (size_t)(g.N_PX + 2 * ring) * (size_t)(g.N_PY + 2 * ring);
   s->n_cell = g.N_CELL;
   s->point_source = point_source_requested;
+  s->source_form = source_form_requested;
 
   b200fdtd_grid grid;
   memset(&grid, 0, sizeof grid);
@@ -251,7 +266,28 @@ static void solver_init(UpmlSolver *s)
     for (int i = 0; i < g.N_PX; i++)
       memcpy(s->eps_ringed + (size_t)(i + 1) * (g.N_PY + 2) + 1, s->eps[m] + (size_t)i * g.N_PY,
              sizeof(double) * (size_t)g.N_PY);
-    return;                                         /* no NTFF plan for the MPI-variant ids */
+    /* ntff() of these solvers (mpiTM_UPML.c:849-1037, mpiTE_UPML.c:602-794): the serial
+     * binning with three differences, all carried by the plan -- timeShift evaluated
+     * directly per point, every tap multiplied by coef = 1/(4 pi C R), R = 1e6, and the box
+     * indices used as LOCAL indices (local i is global i-1, so the cells read sit one cell
+     * down-left of where r2 says). */
+    b200fdtd_ntff_plan mp;
+    memset(&mp, 0, sizeof mp);
+    mp.top = box.top; mp.bottom = box.bottom; mp.left = box.left; mp.right = box.right;
+    mp.n_points = mpifdtd_ntff_point_count(&box);
+    mp.n_local = mp.n_points;
+    mp.max_time = (int)field_getMaxTime();
+    mp.n_bins = getenv("MPIFDTD_NTFF_FULL_BINS") ? box.arraySize : mp.max_time;
+    mp.n_angles = N_ANGLES;
+    mp.array_size = box.arraySize;
+    mp.tap_scale = 1.0 / (4 * M_PI * C_0_S * 1.0e6);
+    mp.sample_di = -1; mp.sample_dj = -1;
+    double *direct = mpifdtd_ntff_time_shift_direct(&box, N_ANGLES, tm ? 0.0 : 0.5);
+    mp.time_shift = direct;
+    if (mp.n_points > 0 && mp.max_time > 0)
+      die_on(b200fdtd_set_ntff_plan(s->engine, &mp), "b200fdtd_set_ntff_plan");
+    free(direct);
+    return;
   }
 
   /* ntffT?_init: surface, history length = stepNum, bins kept = the part of
@@ -291,11 +327,44 @@ static void fill_pulse(b200fdtd_pulse *p, double gap_x, double gap_y, double dot
 /* Everything update() reads from the host's grid/time state, packed for the
  * engine.  Also used by slab (multi-GPU) drivers, which call the engine phases
  * themselves and then field_nextStep(). */
+static void fill_plane_wave(int kind, b200fdtd_line_source *l)
+{
+  NTFFInfo box = field_getNTFFInfo();
+  const double k_s = field_getK();
+  const double rad = field_getWaveAngle() * M_PI / 180;        /* mpiTM_UPML.c:383 */
+  l->enabled = 1;
+  if (is_mpi_kind(kind)) { l->i = box.left - 1;  l->j_lo = 0;  l->j_hi = N_PY - 1; }
+  else                   { l->i = box.left;      l->j_lo = 1;  l->j_hi = N_PY - 2; }
+  l->scale = field_getRayCoef();
+  l->ks_cos = cos(rad) * k_s;  l->ks_sin = sin(rad) * k_s;
+  l->time = field_getTime();
+  l->omega = field_getOmega();
+}
+
+void mpifdtd_upml_step_args_form(int kind, int point_source, int form, b200fdtd_step_args *a);
 void mpifdtd_upml_step_args(int kind, int point_source, b200fdtd_step_args *a)
+{
+  mpifdtd_upml_step_args_form(kind, point_source, MPIFDTD_SRC_DEFAULT, a);
+}
+
+void mpifdtd_upml_step_args_form(int kind, int point_source, int form, b200fdtd_step_args *a)
 {
   memset(a, 0, sizeof *a);
   a->time = field_getTime();
   a->ray_coef = field_getRayCoef();
+  if (form == MPIFDTD_SRC_PLANE && is_tm_kind(kind)) fill_plane_wave(kind, &a->line);
+  if (form == MPIFDTD_SRC_CW && kind == B200FDTD_TM_UPML) {
+    /* field_scatteredWave (field.c:202-218): p += ray_coef*(eps0/eps - 1)*cexp(I*(kr - w t)) */
+    b200fdtd_cw *c = &a->cw[0];
+    double k_s = field_getK();
+    double rad = field_getWaveAngle() * M_PI / 180.0;
+    c->enabled = 1;
+    c->scale = field_getRayCoef();
+    c->ks_cos = cos(rad) * k_s;
+    c->ks_sin = sin(rad) * k_s;
+    c->phase_a = field_getOmega() * field_getTime();
+    return;
+  }
   if (is_mpi_kind(kind)) {
     /* CW scattered wave, integer global coordinates, on Ez (TM) or on Ey only (TE):
      * mpiTM_UPML.c:337-374, mpiTE_UPML.c:250-281 */
@@ -332,7 +401,7 @@ void mpifdtd_upml_step_args(int kind, int point_source, b200fdtd_step_args *a)
 static void solver_update(UpmlSolver *s)
 {
   b200fdtd_step_args a;
-  mpifdtd_upml_step_args(s->kind, s->point_source, &a);
+  mpifdtd_upml_step_args_form(s->kind, s->point_source, s->source_form, &a);
   die_on(b200fdtd_step(s->engine, &a), "b200fdtd_step");
 }
 
@@ -384,6 +453,89 @@ static void write_far_field(UpmlSolver *s)
   free(by_row); free(table);
 }
 
+/* ntffOutput + ntffSaveData of the MPI TE solver (mpiTE_UPML.c:795-878): translate the first
+ * maxTime bins of Wx, Wy, Uz into E_theta / E_phi at theta = 0 and print them, one line per
+ * direction, "%.20lf " per value, into MPI_TE_UPML/E{ph,th}_{r,i}.txt (the directory must
+ * exist, as upstream; a missing one is "cannot open file" + exit(2)).  The accumulation ran
+ * on the GPU; this is 360 x maxTime values of closing algebra and formatting.  (Upstream then
+ * walks its debug arrays, which are NULL without -DDEBUG, and crashes; that is not kept.) */
+static FILE *open_in_mpi_te_dir(const char *file_name)
+{
+  char name[256];
+  sprintf(name, "MPI_TE_UPML/%s", file_name);
+  FILE *fp = fopen(name, "w");
+  if (fp == NULL) { printf("cannot open file %s \n", name); exit(2); }
+  return fp;
+}
+
+static void save_mpi_ntff_series(const char *stem, const dcomplex *data, int max_time)
+{
+  char real_file[256], imag_file[256];
+  sprintf(real_file, "%s_r.txt", stem);
+  sprintf(imag_file, "%s_i.txt", stem);
+  FILE *fr = open_in_mpi_te_dir(real_file), *fi = open_in_mpi_te_dir(imag_file);
+  for (int ang = 0; ang < N_ANGLES; ang++) {
+    for (int i = 0; i < max_time; i++) {
+      fprintf(fr, "%.20lf ", creal(data[(size_t)ang * max_time + i]));
+      fprintf(fi, "%.20lf ", cimag(data[(size_t)ang * max_time + i]));
+    }
+    fprintf(fr, "\n");
+    fprintf(fi, "\n");
+  }
+  fclose(fr); fclose(fi);
+  printf("saved at %s & %s\n", real_file, imag_file);
+}
+
+/* E_theta, E_phi [360][maxTime] of the MPI TE solver from the GPU's U/W (exposed for tests) */
+int mpifdtd_mpi_te_far_series(dcomplex *eth, dcomplex *eph)
+{
+  UpmlSolver *s = &mpi_te_solver;
+  const int max_time = (int)field_getMaxTime();
+  if (s->engine == NULL || max_time < 1) return -1;
+  const int n_bins = getenv("MPIFDTD_NTFF_FULL_BINS") ? field_getNTFFInfo().arraySize : max_time;
+  const size_t count = (size_t)N_ANGLES * (size_t)n_bins;
+  dcomplex *uw[3];
+  die_on(b200fdtd_ntff_project(s->engine), "b200fdtd_ntff_project");
+  for (int m = 0; m < 3; m++) {
+    uw[m] = (dcomplex *)malloc(sizeof(dcomplex) * count);
+    die_on(b200fdtd_ntff_get_uw(s->engine, m, (double *)uw[m]), "b200fdtd_ntff_get_uw");
+  }
+  const double w_s = field_getOmega();
+  const double complex coef = csqrt(2 * M_PI * C_0_S / (I * w_s));        /* mpiTE_UPML.c:844 */
+  const double theta = 0;
+  for (int ang = 0; ang < N_ANGLES; ang++) {
+    double phi = ang * M_PI / 180.0;
+    double sx = cos(theta) * cos(phi), sy = cos(theta) * sin(phi), sz = -cos(theta);
+    double px = -sin(phi), py = cos(phi);
+    const dcomplex *Wx = uw[0] + (size_t)ang * n_bins, *Wy = uw[1] + (size_t)ang * n_bins;
+    const dcomplex *Uz = uw[2] + (size_t)ang * n_bins;
+    for (int i = 0; i < max_time; i++) {
+      double complex WTH = Wx[i] * sx + Wy[i] * sy + 0;
+      double complex WPH = Wx[i] * px + Wy[i] * py;
+      double complex UTH = 0 + 0 + Uz[i] * sz;
+      double complex UPH = 0 + 0;
+      eth[(size_t)ang * max_time + i] = coef * (-Z_0_S * WTH - UPH);
+      eph[(size_t)ang * max_time + i] = coef * (-Z_0_S * WPH + UTH);
+    }
+  }
+  for (int m = 0; m < 3; m++) free(uw[m]);
+  return 0;
+}
+
+static void write_mpi_te_far_field(void)
+{
+  const int max_time = (int)field_getMaxTime();
+  if (max_time < 1) return;
+  const size_t count = (size_t)N_ANGLES * (size_t)max_time;
+  dcomplex *eth = (dcomplex *)malloc(sizeof(dcomplex) * count);
+  dcomplex *eph = (dcomplex *)malloc(sizeof(dcomplex) * count);
+  if (mpifdtd_mpi_te_far_series(eth, eph) == 0) {
+    save_mpi_ntff_series("Eph", eph, max_time);
+    save_mpi_ntff_series("Eth", eth, max_time);
+  }
+  free(eph); free(eth);
+}
+
 static void solver_reset(UpmlSolver *s)
 {
   if (s->engine == NULL) return;
@@ -395,6 +547,9 @@ static void solver_reset(UpmlSolver *s)
 static void solver_finish(UpmlSolver *s)
 {
   if (s->engine == NULL) return;
+  /* mpiTE_UPML.c:304-317: finish() = ntffOutput + free (no reset); the TM twin's ntffOutput
+   * call is commented out (mpiTM_UPML.c:240), so id 4 writes nothing */
+  if (s->kind == B200FDTD_MPI_TE_UPML) write_mpi_te_far_field();
   solver_reset(s);
   die_on(b200fdtd_destroy(s->engine), "b200fdtd_destroy");
   s->engine = NULL;

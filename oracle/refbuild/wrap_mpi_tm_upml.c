@@ -8,3 +8,14 @@ HOOK(C_DZ) HOOK(C_BX) HOOK(C_BY) HOOK(C_DZJZ0) HOOK(C_DZJZ1)
 HOOK(C_BXMX0) HOOK(C_BXMX1) HOOK(C_BYMY0) HOOK(C_BYMY1)
 HOOK(EPS_EZ) HOOK(EPS_HX) HOOK(EPS_HY)
 HOOK_END
+/* update() (mpiTM_UPML.c:196-217) with the commented planeWave call at line 204 enabled */
+void refhook_mpi_tm_upml_update_plane_wave(void)
+{
+  calcJD(); calcE();
+  scatteredWave(Ez, EPS_EZ);
+  planeWave(Ez, EPS_EZ);
+  Connection_ISend_IRecvE();
+  calcMB(); calcH();
+  Connection_ISend_IRecvH();
+  ntff();
+}

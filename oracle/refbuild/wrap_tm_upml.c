@@ -25,3 +25,34 @@ void refhook_tm_upml_update_point_source(void)
   Ez[field_index(N_PX/2, N_PY/2)] += field_pointLight();
   ntffTM_TimeCalc(Hx,Hy,Ez,Ux,Uy,Wz);
 }
+/* update() with the alternative source the reference keeps commented out at
+ * fdtdTM_upml.c:62: field_scatteredWave (field.c:202-218) instead of the pulse */
+void refhook_tm_upml_update_cw(void)
+{
+  calcMB(); calcH(); calcJD(); calcE();
+  field_scatteredWave(Ez, EPS_EZ, 0, 0);
+  ntffTM_TimeCalc(Hx,Hy,Ez,Ux,Uy,Wz);
+}
+/* opt-in plane-wave line source for the NoModel configuration: the expression of
+ * planeWave (mpiTM_UPML.c:377-403, no caller) on the serial grid -- row i = NTFF left
+ * edge, columns 1..N_PY-2, x = i, y = j -- added to Ez after the pulse */
+void refhook_tm_upml_update_plane_wave(void)
+{
+  calcMB(); calcH(); calcJD(); calcE();
+  field_scatteredPulse(Ez, EPS_EZ, 0, 0, 1.0);
+  {
+    const double time = field_getTime();
+    const double w_s  = field_getOmega();
+    const double ray_coef = field_getRayCoef();
+    const double k_s = field_getK();
+    const double rad = field_getWaveAngle()*M_PI/180;
+    const double ks_cos = cos(rad)*k_s, ks_sin = sin(rad)*k_s;
+    NTFFInfo nInfo = field_getNTFFInfo();
+    const int x = nInfo.left;
+    for (int y = 1; y < N_PY-1; y++) {
+      double kr = (x*ks_cos + y*ks_sin) - time;
+      Ez[field_index(x, y)] += ray_coef*cexp(I*kr*w_s);
+    }
+  }
+  ntffTM_TimeCalc(Hx,Hy,Ez,Ux,Uy,Wz);
+}

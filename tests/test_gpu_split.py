@@ -94,6 +94,89 @@ def test_mpi_variant_solver_vs_live_reference(plugin_lib, kind, model, in_tmp_cw
     gpu.finish()
 
 
+UW_NAMES = {4: ["Ux", "Uy", "Wz"], 5: ["Wx", "Wy", "Uz"]}
+
+
+@pytest.mark.parametrize("kind,model,angle", [(4, "MIE_CYLINDER", 0), (5, "MIE_CYLINDER", 0), (4, "LAYER", 25),
+                                              (5, "ZIGZAG", 25)])
+def test_mpi_variant_ntff_vs_live_reference(plugin_lib, kind, model, angle, in_tmp_cwd, monkeypatch):
+    """ntff() of the MPI-variant solvers (mpiTM_UPML.c:849-1037,
+    mpiTE_UPML.c:602-794) -- direct time shift, coef per tap, box indices used as local
+    indices -- and, for id 5, the E_theta/E_phi text files finish() writes."""
+    from oracle import reflib
+    if not reflib.available():
+        pytest.skip("oracle/_ref/libref.so did not travel with this snapshot")
+    monkeypatch.setenv("MPIFDTD_NTFF_FULL_BINS", "1")
+    npx, npy, steps = 120, 132, 420
+    cwd = os.getcwd()
+    ref = reflib.RefSim(model, kind, npx, npy, steps=steps, angle_deg=angle)
+    ref.run()
+    want = {n: ref.ntff_uw(n) for n in UW_NAMES[kind]}
+    ref_files = {}
+    if kind == 5:
+        reflib.lib().refhook_mpi_te_upml_ntff_output()
+        for stem in ("Eph_r", "Eph_i", "Eth_r", "Eth_i"):
+            ref_files[stem] = np.loadtxt(os.path.join(ref.workdir, "MPI_TE_UPML", stem + ".txt"))
+    os.chdir(cwd)
+    gpu = B.Plugin(model, kind, npx, npy, steps=steps, angle_deg=angle)
+    gpu.run()
+    scale = max(np.abs(w).max() for w in want.values())
+    assert scale > 0
+    for slot, n in enumerate(UW_NAMES[kind]):
+        got = gpu.ntff_uw(slot, project=(slot == 0))
+        assert got.shape == want[n].shape
+        assert np.abs(got - want[n]).max() <= 1e-10 * scale, n
+    os.makedirs("MPI_TE_UPML", exist_ok=True)
+    gpu.finish()
+    if kind == 5:
+        fscale = max(np.abs(v).max() for v in ref_files.values())
+        assert fscale > 0
+        for stem, ref_table in ref_files.items():
+            mine = np.loadtxt(os.path.join("MPI_TE_UPML", stem + ".txt"))
+            assert mine.shape == ref_table.shape == (360, steps)
+            assert np.abs(mine - ref_table).max() <= 1e-10 * fscale, stem
+    else:
+        assert not os.listdir("MPI_TE_UPML")        # id 4 writes nothing (mpiTM_UPML.c:240)
+
+
+# ---------------------------------------------------------------- opt-in source forms (row a10)
+@pytest.mark.parametrize("kind,model,form,hook", [
+    (2, "MIE_CYLINDER", "CW", "refhook_tm_upml_update_cw"),
+    (2, "NO_MODEL", "PLANE", "refhook_tm_upml_update_plane_wave"),
+    (4, "NO_MODEL", "PLANE", "refhook_mpi_tm_upml_update_plane_wave"),
+    (4, "ZIGZAG", "PLANE", "refhook_mpi_tm_upml_update_plane_wave")])
+def test_optional_source_forms_vs_live_reference(plugin_lib, kind, model, form, hook, in_tmp_cwd, monkeypatch):
+    """field_scatteredWave (the commented alternative at fdtdTM_upml.c:62) and planeWave
+    (mpiTM_UPML.c:377-403, commented call at :204): the reference's own static functions,
+    composed by oracle/refbuild/wrap_*.c in the order the commented lines give."""
+    from oracle import reflib
+    if not reflib.available():
+        pytest.skip("oracle/_ref/libref.so did not travel with this snapshot")
+    monkeypatch.setenv("MPIFDTD_NTFF_FULL_BINS", "1")
+    npx, npy, steps = (256, 256, 300) if model == "NO_MODEL" else (120, 140, 360)
+    cwd = os.getcwd()
+    ref = reflib.RefSim(model, kind, npx, npy, steps=steps, angle_deg=20)
+    ref.step_fn(hook, steps)
+    ring = 2 if kind == 4 else 0
+    shape = (npx + ring, npy + ring)
+    want = {f: ref.carray(f, shape[0] * shape[1]).reshape(shape) for f in ("Ez", "Hx", "Hy")}
+    want_uw = {n: ref.ntff_uw(n) for n in ("Ux", "Uy", "Wz")}
+    os.chdir(cwd)
+    gpu = B.Plugin(model, kind, npx, npy, steps=steps, angle_deg=20, source_form=form)
+    try:
+        gpu.run()
+        assert np.abs(want["Ez"]).max() > 1e-3
+        for f in ("Ez", "Hx", "Hy"):
+            assert rel_err(gpu.field(f), want[f]) <= TOL_FIELD, f
+        scale = max(np.abs(w).max() for w in want_uw.values())
+        for slot, n in enumerate(("Ux", "Uy", "Wz")):
+            got = gpu.ntff_uw(slot, project=(slot == 0))
+            assert np.abs(got - want_uw[n]).max() <= 1e-10 * scale, n
+        gpu.finish()
+    finally:
+        B.lib().mpifdtd_setSourceForm(0)
+
+
 # ---------------------------------------------------------------- frequency-domain NTFF
 def test_frequency_ntff_tm_upml_vs_oracle(plugin_lib, oracle, in_tmp_cwd):
     """ntffTM_Frequency (ntffTM.c:72-158) on the GPU fields of the serial TM UPML solver."""
