@@ -203,6 +203,47 @@ ntff_project_kernel(const NtffPoint *__restrict__ pts, const double *__restrict_
       __syncthreads();
     }
   }
+  // The same storage quirk at the other end: during the first steps a point whose shift is
+  // ~0 or slightly negative (C_0_S = 0.7071 makes |r|/C exceed RFperC by 2e-5 at the box
+  // corners) has m = floor(T + 1/2) <= 0, and its taps at index -1, -2 of direction ang+1 are
+  // physically bins arraySize-1, arraySize-2 of direction ang.  They carry exact zeros unless
+  // a source sits on the surface (the opt-in plane wave does); visible only when all
+  // arraySize bins are kept.
+  if (array_size > 0 && ang + 1 < n_angles && q_block + kProjBlock > array_size - kSpillBins &&
+      q_block < array_size) {                                   // uniform per block
+    const int qv = q - array_size;
+    for (int p0 = 0; p0 < n_local; p0 += kProjBlock) {
+      const int pm = p0 + (int)threadIdx.x;
+      double my_ts = 0.0;
+      int my_edge = -1;
+      if (pm < n_local) {
+        my_ts = ts_tab[(size_t)(ang + 1) * n_local + pm];
+        if (my_ts < 2.0) my_edge = pts[pm].edge;
+      }
+      const int any = __syncthreads_or(my_edge >= 0);
+      if (!any) continue;
+      s_ts[threadIdx.x] = my_ts;
+      s_edge[threadIdx.x] = my_edge;
+      __syncthreads();
+      const int chunk = (n_local - p0) < kProjBlock ? (n_local - p0) : kProjBlock;
+      if (qv < 0 && qv >= -kSpillBins && q < n_bins) {
+        for (int c = 0; c < chunk; c++) {
+          const int edge = s_edge[c];
+          if (edge < 0) continue;
+          const int p = p0 + c;
+          const double ts = s_ts[c];
+          const bool along_x = (edge == 0 || edge == 2);
+          const int slot_e = is_tm ? (along_x ? 0 : 1) : 2;
+          const int slot_h = is_tm ? 2 : (along_x ? 0 : 1);
+          gather(acc[slot_e], hist_e + (size_t)p * max_time, t_limit, qv, ts, 1.0,
+                 qv - ((int)floor(ts + 0.5) - 1), 2, tap_scale);
+          gather(acc[slot_h], hist_h + (size_t)p * max_time, t_limit, qv, ts, 0.5,
+                 qv - (int)floor(ts), 2, tap_scale);
+        }
+      }
+      __syncthreads();
+    }
+  }
   if (q < n_bins)
     for (int s = 0; s < 3; s++)
       uw[((size_t)s * n_angles + ang) * n_bins + q] = acc[s];

@@ -455,14 +455,15 @@ static void write_far_field(UpmlSolver *s)
 
 /* ntffOutput + ntffSaveData of the MPI TE solver (mpiTE_UPML.c:795-878): translate the first
  * maxTime bins of Wx, Wy, Uz into E_theta / E_phi at theta = 0 and print them, one line per
- * direction, "%.20lf " per value, into MPI_TE_UPML/E{ph,th}_{r,i}.txt (the directory must
- * exist, as upstream; a missing one is "cannot open file" + exit(2)).  The accumulation ran
+ * direction, "%.20lf " per value, into MPI_TE_UPML/E{ph,th}_{r,i}.txt (upstream requires the
+ * directory to exist and exit(2)s otherwise; here it is created when missing).  The accumulation ran
  * on the GPU; this is 360 x maxTime values of closing algebra and formatting.  (Upstream then
  * walks its debug arrays, which are NULL without -DDEBUG, and crashes; that is not kept.) */
 static FILE *open_in_mpi_te_dir(const char *file_name)
 {
   char name[256];
   sprintf(name, "MPI_TE_UPML/%s", file_name);
+  makeDirectory("MPI_TE_UPML");     /* upstream expects it to exist; a missing one costs the run */
   FILE *fp = fopen(name, "w");
   if (fp == NULL) { printf("cannot open file %s \n", name); exit(2); }
   return fp;

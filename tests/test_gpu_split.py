@@ -171,7 +171,8 @@ def test_optional_source_forms_vs_live_reference(plugin_lib, kind, model, form, 
         scale = max(np.abs(w).max() for w in want_uw.values())
         for slot, n in enumerate(("Ux", "Uy", "Wz")):
             got = gpu.ntff_uw(slot, project=(slot == 0))
-            assert np.abs(got - want_uw[n]).max() <= 1e-10 * scale, n
+            d = np.abs(got - want_uw[n])
+            assert d.max() <= 1e-10 * scale, (n, np.unravel_index(d.argmax(), d.shape), d.max())
         gpu.finish()
     finally:
         B.lib().mpifdtd_setSourceForm(0)
