@@ -272,7 +272,7 @@ def gpu_arm(args):
         if world > 1:
             comm = TorchHaloComm(n_px, torch.device("cuda", local_rank))
         run = SlabRun("ZIGZAG", args.solver, n_px, n_py, total_steps, rank=rank, world=world,
-                      device=local_rank, comm=comm)
+                      device=local_rank, comm=comm, precision=args.precision)
         run.engine.set_stream(stream.cuda_stream)
         if comm is not None:
             run.attach_halo_buffers(*comm.pointers())
@@ -352,16 +352,19 @@ def gpu_arm(args):
         # TE: H phase reads Ex,Ey,Mz,Bz (64) + writes Mz,Bz (32); E phase reads Bz,Jx,Dx,Jy,Dy (80) +
         # eps x2 (16) + writes Jx,Dx,Jy,Dy,Ex,Ey (96); step = SURVEY 8(d)'s 288 B
         bytes_h, bytes_e, bytes_step = (BYTES_H_TM, BYTES_E_TM, BYTES_STEP_TM) if tm else (96, 192, 288)
+        if args.precision == "f32":     # complex64 fields, f32 eps: every array element is half as wide
+            bytes_h, bytes_e, bytes_step = bytes_h // 2, bytes_e // 2, bytes_step // 2
         kname = "tm" if tm else "te"
         ach_h = bytes_h * cells_rank / (ms_h * 1e-3) / 1e9
         ach_e = bytes_e * cells_rank / (ms_e * 1e-3) / 1e9
         step_gbs = bytes_step * (value / world) * 1e9 / 1e9
-        traffic, traffic_src = ncu_traffic(kname + "_upml_h_kernel<0>", cells_rank)
+        traffic, traffic_src = (ncu_traffic(kname + "_upml_h_kernel<0>", cells_rank) if args.precision == "f64"
+                                else (None, None))
         line = {
             "metric": "Gcell-updates/s", "value": value, "unit": "Gcell-updates/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_max / K,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
+            "dtype": args.precision, "data": "synthetic",
             "config": workload_config(world, n=args.n, solver=args.solver,
                                       halo={"peer": "direct NVLink peer stores + device flags",
                                             "nccl": "NCCL send/recv"}[args.halo]),
@@ -405,6 +408,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--halo", default="peer", choices=["peer", "nccl"],
                     help="multi-GPU halo transport: direct NVLink peer stores (default) or NCCL send/recv")
+    ap.add_argument("--precision", default="f64", choices=["f64", "f32"],
+                    help="f64 is the reference's arithmetic and the BASELINE metric; f32 is the optional "
+                         "single-precision path (own tolerance), reported for information only")
     ap.add_argument("--solver", default="TM_UPML_2D", choices=["TM_UPML_2D", "TE_UPML_2D"],
                     help="TM_UPML_2D is the BASELINE workload; TE_UPML_2D is reported for information")
     args = ap.parse_args()

@@ -53,6 +53,7 @@ enum { B200FDTD_TM_EZ = 0, B200FDTD_TM_JZ, B200FDTD_TM_DZ, B200FDTD_TM_HX, B200F
 enum { B200FDTD_TE_EX = 0, B200FDTD_TE_JX, B200FDTD_TE_DX, B200FDTD_TE_EY, B200FDTD_TE_JY,
        B200FDTD_TE_DY, B200FDTD_TE_HZ, B200FDTD_TE_MZ, B200FDTD_TE_BZ };
 #define B200FDTD_MAX_FIELDS 9
+enum { B200FDTD_F64 = 0, B200FDTD_F32 = 1 };
 /* Split-field kinds (plain Berenger-PML Yee 0/1 and NS-FDTD 6/7) keep 5 complex arrays
  * (fdtdTM.c:10-14, fdtdTE.c:10-14, nsFdtdTM.c:10-14, nsFdtdTE.c:11-15): */
 enum { B200FDTD_STM_EZ = 0, B200FDTD_STM_EZX, B200FDTD_STM_EZY, B200FDTD_STM_HX, B200FDTD_STM_HY };
@@ -100,7 +101,9 @@ typedef struct b200fdtd_grid {
   int32_t i_lo, i_hi;       /* updated cells, inclusive, global; the serial solvers */
   int32_t j_lo, j_hi;       /*   use 1 .. N-2 (fdtdTM_upml.c:158-159)              */
   int32_t device;           /* CUDA device ordinal, or -1 for the current device   */
-  int32_t reserved;
+  int32_t precision;        /* B200FDTD_F64 (0, the reference's arithmetic) or      */
+                            /* B200FDTD_F32: complex64 fields, f32 eps/coefficients  */
+                            /* (UPML kinds; own tolerance)            */
   double mu0;               /* MU_0_S, passed so the divisor is the host's value   */
 } b200fdtd_grid;
 

@@ -206,6 +206,10 @@ extern int mpifdtd_ntffFrequency(int solver_id, double complex result[360]);
 enum { MPIFDTD_SRC_DEFAULT = 0, MPIFDTD_SRC_CW = 1, MPIFDTD_SRC_PLANE = 2 };
 extern void mpifdtd_enablePointSource(int on);
 extern void mpifdtd_setSourceForm(int form);
+/* Optional single-precision path of the UPML solvers (ids 2-5), read by the next init():
+ * 0 = double (default, the reference's arithmetic), 1 = float fields/eps/coefficients on the
+ * GPU.  Getters and far-field files keep their double formats. */
+extern void mpifdtd_setPrecision(int precision);
 
 /* ---- config.txt (parser.h:5, configSample.txt:6-22, main.c:319-366) ------ */
 extern bool parser_nextLine(FILE *fp, char buf[]);            /* parser.c:3 */

@@ -48,7 +48,7 @@ class Grid(C.Structure):
     _fields_ = [("kind", C.c_int32), ("n_px", C.c_int32), ("n_py", C.c_int32), ("n_pml", C.c_int32),
                 ("j0", C.c_int32), ("nj", C.c_int32), ("i_lo", C.c_int32), ("i_hi", C.c_int32),
                 ("j_lo", C.c_int32), ("j_hi", C.c_int32), ("device", C.c_int32),
-                ("reserved", C.c_int32), ("mu0", C.c_double)]
+                ("precision", C.c_int32), ("mu0", C.c_double)]
 
 
 class Pulse(C.Structure):
@@ -190,6 +190,7 @@ def lib():
     L.mpifdtd_upml_engine.restype = vp
     L.mpifdtd_enablePointSource.argtypes = [C.c_int]
     L.mpifdtd_setSourceForm.argtypes = [C.c_int]
+    L.mpifdtd_setPrecision.argtypes = [C.c_int]
     L.b200fdtd_struct_size.argtypes = [i32]
     L.mpifdtd_readConfig.argtypes = [C.c_char_p, vp]
     for name in ("fdtdTM_upml_getHx", "fdtdTM_upml_getHy", "fdtdTM_upml_getEz",
@@ -227,6 +228,7 @@ def _as_complex(ptr, n_px, n_py):
     return np.frombuffer(buf, dtype=np.complex128).reshape(n_px, n_py)
 
 
+PRECISIONS = dict(f64=0, f32=1)                     # B200FDTD_F64 / B200FDTD_F32
 SOURCE_FORMS = dict(DEFAULT=0, CW=1, PLANE=2)       # MPIFDTD_SRC_* of mpifdtd_plugin.h
 
 
@@ -243,7 +245,7 @@ class Plugin:
                7: {f: "nsFdtdTE_get" + f for f in ("Ex", "Ey", "Hz", "Hzx", "Hzy")}}
 
     def __init__(self, model, solver, n_px, n_py=None, steps=100, h_u_nm=10, pml=10,
-                 lambda_nm=500, angle_deg=0, point_source=False, source_form=0):
+                 lambda_nm=500, angle_deg=0, point_source=False, source_form=0, precision=0):
         self.L = lib()
         self.model = MODELS[model] if isinstance(model, str) else int(model)
         self.solver = SOLVERS[solver] if isinstance(solver, str) else int(solver)
@@ -252,6 +254,7 @@ class Plugin:
         self.info = FieldInfo(n_px * h_u_nm, n_py * h_u_nm, h_u_nm, pml, lambda_nm, angle_deg, steps)
         self.L.mpifdtd_enablePointSource(1 if point_source else 0)
         self.L.mpifdtd_setSourceForm(SOURCE_FORMS[source_form] if isinstance(source_form, str) else source_form)
+        self.L.mpifdtd_setPrecision(PRECISIONS[precision] if isinstance(precision, str) else precision)
         self.L.models_setModel(self.model)
         self.L.simulator_setSolver(self.solver)
         self.L.simulator_init(self.info)
@@ -346,11 +349,12 @@ class Engine:
     coefficient tables, NTFF plan) comes from the plugin's own C helpers after
     field_init(), so a slab engine sees exactly what the serial shim would."""
 
-    def __init__(self, kind, n_px, n_py, n_pml, j0=0, nj=None, device=-1, extents=None):
+    def __init__(self, kind, n_px, n_py, n_pml, j0=0, nj=None, device=-1, extents=None, precision=0):
         self.L = lib()
+        precision = PRECISIONS[precision] if isinstance(precision, str) else precision
         nj = n_py - j0 if nj is None else nj
         i_lo, i_hi, j_lo, j_hi = extents if extents else (1, n_px - 2, 1, n_py - 2)
-        self.grid = Grid(kind, n_px, n_py, n_pml, j0, nj, i_lo, i_hi, j_lo, j_hi, device, 0, MU_0_S)
+        self.grid = Grid(kind, n_px, n_py, n_pml, j0, nj, i_lo, i_hi, j_lo, j_hi, device, precision, MU_0_S)
         self.h = C.c_void_p()
         check(self.L.b200fdtd_create(C.byref(self.grid), C.byref(self.h)), "create")
         self.kind, self.n_px, self.n_py, self.j0, self.nj = kind, n_px, n_py, j0, nj

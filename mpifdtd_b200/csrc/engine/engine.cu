@@ -123,6 +123,10 @@ int b200fdtd_create(const b200fdtd_grid *grid, b200fdtd_engine **out)
                      grid->j0, grid->nj);
   if (grid->i_lo < 0 || grid->i_hi >= grid->n_px || grid->j_lo < 0 || grid->j_hi >= grid->n_py)
     return b200_fail(B200FDTD_ERR_ARG, "update extents outside the grid");
+  if (grid->precision != B200FDTD_F64 && grid->precision != B200FDTD_F32)
+    return b200_fail(B200FDTD_ERR_ARG, "unknown precision %d", grid->precision);
+  if (grid->precision == B200FDTD_F32 && !kind_is_upml(grid->kind))
+    return b200_fail(B200FDTD_ERR_ARG, "the single-precision path serves the UPML kinds (2-5)");
 
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
@@ -147,10 +151,14 @@ int b200fdtd_create(const b200fdtd_grid *grid, b200fdtd_engine **out)
   e->pitch = ((B200_JOFF + grid->nj + 1) + 7) / 8 * 8;
   e->plane = (size_t)e->rows * e->pitch;
   e->n_fields = kind_is_split(grid->kind) ? 5 : 9;
+  e->fp32 = grid->precision == B200FDTD_F32;
+  e->csize = e->fp32 ? sizeof(float2) : sizeof(double2);
+  e->rsize = e->fp32 ? sizeof(float) : sizeof(double);
   e->use_fused = false;     // the marching one-pass kernel is opt-in (B200FDTD_OPT_FUSED)
   e->store_h = false;
   e->h_stale = false;
-  if (const char *v = getenv("B200FDTD_FUSED")) e->use_fused = atoi(v) != 0 && grid->kind == B200FDTD_TM_UPML;
+  if (const char *v = getenv("B200FDTD_FUSED"))
+    e->use_fused = atoi(v) != 0 && grid->kind == B200FDTD_TM_UPML && !e->fp32;
   if (const char *v = getenv("B200FDTD_STORE_H")) e->store_h = atoi(v) != 0;
   if (const char *v = getenv("B200FDTD_FUSED_SHAPE")) e->fused_variant = atoi(v);
   if (const char *v = getenv("B200FDTD_BAND_ROWS")) e->fused.band_h = atoi(v);
@@ -164,14 +172,14 @@ int b200fdtd_create(const b200fdtd_grid *grid, b200fdtd_engine **out)
   e->c_hi = jh - grid->j0 + B200_JOFF;
 
   for (int s = 0; s < e->n_fields && !rc; s++)
-    rc = dev_alloc_zero(e, (void **)&e->field[s], e->plane * sizeof(double2));
+    rc = dev_alloc_zero(e, (void **)&e->field[s], e->plane * e->csize);
   if (kind_is_split(grid->kind)) {
     for (int s = 0; s < B200FDTD_MAX_DENSE && !rc; s++)
       rc = dev_alloc_zero(e, (void **)&e->dense[s], e->plane * sizeof(double));
   } else {
     const int n_eps = (grid->kind == B200FDTD_TM_UPML || grid->kind == B200FDTD_MPI_TM_UPML) ? 1 : 2;
     for (int s = 0; s < n_eps && !rc; s++)
-      rc = dev_alloc_zero(e, (void **)&e->eps[s], e->plane * sizeof(double));
+      rc = dev_alloc_zero(e, (void **)&e->eps[s], e->plane * e->rsize);
     if (!rc) rc = dev_alloc_zero(e, (void **)&e->tab_i, sizeof(double) * B200FDTD_UPML_TABS * e->rows);
     if (!rc) rc = dev_alloc_zero(e, (void **)&e->tab_j, sizeof(double) * B200FDTD_UPML_TABS * e->pitch);
   }
@@ -235,7 +243,7 @@ int b200fdtd_peer_export(b200fdtd_engine *e, void *blob)
   B200_CUDA(cudaIpcGetMemHandle(&b.e_arr, e->field[es]));
   B200_CUDA(cudaIpcGetMemHandle(&b.h_arr, e->field[hs]));
   B200_CUDA(cudaIpcGetMemHandle(&b.flags, e->peer.flags));
-  b.nj = e->g.nj; b.pitch = e->pitch; b.rows = e->rows; b.kind = e->g.kind;
+  b.nj = e->g.nj; b.pitch = e->pitch; b.rows = e->rows; b.kind = e->g.kind | (e->fp32 ? 0x100 : 0);
   memset(blob, 0, B200FDTD_PEER_BLOB_BYTES);
   memcpy(blob, &b, sizeof b);
   return B200FDTD_OK;
@@ -248,8 +256,8 @@ int b200fdtd_peer_attach(b200fdtd_engine *e, int32_t which, const void *blob)
   if (!e->peer.flags) return b200_fail(B200FDTD_ERR_STATE, "peer_attach before peer_export");
   PeerBlob b;
   memcpy(&b, blob, sizeof b);
-  if (b.rows != e->rows || b.kind != e->g.kind)
-    return b200_fail(B200FDTD_ERR_ARG, "neighbour slab has another shape or solver kind");
+  if (b.rows != e->rows || b.kind != (e->g.kind | (e->fp32 ? 0x100 : 0)))
+    return b200_fail(B200FDTD_ERR_ARG, "neighbour slab has another shape, solver kind or precision");
   void *p_e = nullptr, *p_h = nullptr, *p_f = nullptr;
   B200_CUDA(cudaIpcOpenMemHandle(&p_f, b.flags, cudaIpcMemLazyEnablePeerAccess));
   if (which == 1) {                     // upper neighbour: I store H into its low ghost column
@@ -301,6 +309,14 @@ int b200fdtd_set_upml_tables(b200fdtd_engine *e, const double *tab_i, const doub
     for (int c = 0; c < g.nj; c++)
       hj[(size_t)s * e->pitch + B200_JOFF + c] = tab_j[(size_t)s * g.n_py + g.j0 + c];
   }
+  if (e->fp32) {                        // same tables rounded once to float, behind the same pointers
+    std::vector<float> fi(hi.begin(), hi.end()), fj(hj.begin(), hj.end());
+    B200_CUDA(cudaMemcpyAsync(e->tab_i, fi.data(), fi.size() * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+    B200_CUDA(cudaMemcpyAsync(e->tab_j, fj.data(), fj.size() * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+    B200_CUDA(cudaStreamSynchronize(e->stream));
+    e->have_tabs = true;
+    return B200FDTD_OK;
+  }
   B200_CUDA(cudaMemcpyAsync(e->tab_i, hi.data(), hi.size() * sizeof(double), cudaMemcpyHostToDevice, e->stream));
   B200_CUDA(cudaMemcpyAsync(e->tab_j, hj.data(), hj.size() * sizeof(double), cudaMemcpyHostToDevice, e->stream));
   B200_CUDA(cudaStreamSynchronize(e->stream));
@@ -329,6 +345,23 @@ static int upload_eps(b200fdtd_engine *e, int32_t slot, const double *src, size_
     return b200_fail(B200FDTD_ERR_ARG, "bad eps slot %d", slot);
   int rc = select_device(e); if (rc) return rc;
   const b200fdtd_grid &g = e->g;
+  if (e->fp32) {                        // stage the double map on the device, round once to float
+    double *stage = nullptr;
+    const size_t count = (size_t)g.n_px * g.nj;
+    cudaError_t err = cudaMalloc(&stage, count * sizeof(double));
+    if (err != cudaSuccess) return b200_fail(B200FDTD_ERR_NOMEM, "eps staging buffer: %s", cudaGetErrorString(err));
+    rc = b200_fill_float(e, (float *)e->eps[slot], e->plane, 1.0f);
+    if (!rc) {
+      cudaError_t c2 = cudaMemcpy2DAsync(stage, sizeof(double) * g.nj, src, sizeof(double) * ld,
+                                         sizeof(double) * g.nj, g.n_px, cudaMemcpyHostToDevice, e->stream);
+      if (c2 != cudaSuccess) rc = b200_fail(B200FDTD_ERR_CUDA, "eps upload: %s", cudaGetErrorString(c2));
+    }
+    if (!rc) rc = b200_narrow_real_region(e, stage, (size_t)g.nj, (float *)e->eps[slot]);
+    cudaStreamSynchronize(e->stream);
+    cudaFree(stage);
+    if (!rc) e->have_eps[slot] = true;
+    return rc;
+  }
   // ghosts and row padding hold vacuum (1.0) so no kernel can ever divide by zero there
   fill_double_kernel<<<1184, 256, 0, e->stream>>>(e->eps[slot], e->plane, 1.0);
   e->launches++;
@@ -465,8 +498,8 @@ int b200fdtd_set_option(b200fdtd_engine *e, int32_t option, int32_t value)
   int rc = select_device(e); if (rc) return rc;
   switch (option) {
   case B200FDTD_OPT_FUSED:
-    if (value && e->g.kind != B200FDTD_TM_UPML)
-      return b200_fail(B200FDTD_ERR_ARG, "the fused step serves the serial TM kind only");
+    if (value && (e->g.kind != B200FDTD_TM_UPML || e->fp32))
+      return b200_fail(B200FDTD_ERR_ARG, "the fused step serves the serial TM kind in double precision only");
     e->use_fused = value != 0;
     return B200FDTD_OK;
   case B200FDTD_OPT_STORE_H:
@@ -533,17 +566,41 @@ int b200fdtd_halo_unpack(b200fdtd_engine *e, int32_t which, const void *dev_buf)
   return b200_launch_halo(e, which, const_cast<void *>(dev_buf), false);
 }
 
+// Device plane of a field as double2: the array itself, or (single-precision engines) a
+// widened temporary the caller frees after its copy has completed.
+static int field_plane_f64(b200fdtd_engine *e, int slot, const double2 **plane, double2 **temp)
+{
+  *temp = nullptr;
+  *plane = e->field[slot];
+  if (!e->fp32) return B200FDTD_OK;
+  cudaError_t err = cudaMalloc(temp, e->plane * sizeof(double2));
+  if (err != cudaSuccess) return b200_fail(B200FDTD_ERR_NOMEM, "getter staging plane: %s", cudaGetErrorString(err));
+  int rc = b200_widen_plane(e, e->field[slot], *temp, e->plane);
+  if (rc) { cudaFree(*temp); *temp = nullptr; return rc; }
+  *plane = *temp;
+  return B200FDTD_OK;
+}
+
+static int copy_field_out(b200fdtd_engine *e, int slot, double *host_first, size_t host_ld_complex)
+{
+  int rc = b200_refresh_h(e); if (rc) return rc;
+  const double2 *plane; double2 *temp;
+  rc = field_plane_f64(e, slot, &plane, &temp); if (rc) return rc;
+  const b200fdtd_grid &g = e->g;
+  cudaError_t err = cudaMemcpy2DAsync(host_first, sizeof(double2) * host_ld_complex,
+                                      plane + (size_t)e->pitch + B200_JOFF, sizeof(double2) * e->pitch,
+                                      sizeof(double2) * g.nj, g.n_px, cudaMemcpyDeviceToHost, e->stream);
+  if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
+  cudaFree(temp);
+  if (err != cudaSuccess) return b200_fail(B200FDTD_ERR_CUDA, "field download: %s", cudaGetErrorString(err));
+  return B200FDTD_OK;
+}
+
 int b200fdtd_get_field(b200fdtd_engine *e, int32_t slot, double *host)
 {
   if (!e || !host || slot < 0 || slot >= e->n_fields) return b200_fail(B200FDTD_ERR_ARG, "bad field slot %d", slot);
   int rc = select_device(e); if (rc) return rc;
-  rc = b200_refresh_h(e); if (rc) return rc;
-  const b200fdtd_grid &g = e->g;
-  B200_CUDA(cudaMemcpy2DAsync(host + 2 * (size_t)g.j0, sizeof(double2) * g.n_py,
-                              e->field[slot] + (size_t)e->pitch + B200_JOFF, sizeof(double2) * e->pitch,
-                              sizeof(double2) * g.nj, g.n_px, cudaMemcpyDeviceToHost, e->stream));
-  B200_CUDA(cudaStreamSynchronize(e->stream));
-  return B200FDTD_OK;
+  return copy_field_out(e, slot, host + 2 * (size_t)e->g.j0, (size_t)e->g.n_py);
 }
 
 int b200fdtd_get_field_ld(b200fdtd_engine *e, int32_t slot, double *host, int64_t ld)
@@ -551,26 +608,14 @@ int b200fdtd_get_field_ld(b200fdtd_engine *e, int32_t slot, double *host, int64_
   if (!e || !host || slot < 0 || slot >= e->n_fields || ld < e->g.nj)
     return b200_fail(B200FDTD_ERR_ARG, "bad field slot %d / leading dimension", slot);
   int rc = select_device(e); if (rc) return rc;
-  rc = b200_refresh_h(e); if (rc) return rc;
-  const b200fdtd_grid &g = e->g;
-  B200_CUDA(cudaMemcpy2DAsync(host, sizeof(double2) * (size_t)ld,
-                              e->field[slot] + (size_t)e->pitch + B200_JOFF, sizeof(double2) * e->pitch,
-                              sizeof(double2) * g.nj, g.n_px, cudaMemcpyDeviceToHost, e->stream));
-  B200_CUDA(cudaStreamSynchronize(e->stream));
-  return B200FDTD_OK;
+  return copy_field_out(e, slot, host, (size_t)ld);
 }
 
 int b200fdtd_get_field_slab(b200fdtd_engine *e, int32_t slot, double *host)
 {
   if (!e || !host || slot < 0 || slot >= e->n_fields) return b200_fail(B200FDTD_ERR_ARG, "bad field slot %d", slot);
   int rc = select_device(e); if (rc) return rc;
-  rc = b200_refresh_h(e); if (rc) return rc;
-  const b200fdtd_grid &g = e->g;
-  B200_CUDA(cudaMemcpy2DAsync(host, sizeof(double2) * g.nj,
-                              e->field[slot] + (size_t)e->pitch + B200_JOFF, sizeof(double2) * e->pitch,
-                              sizeof(double2) * g.nj, g.n_px, cudaMemcpyDeviceToHost, e->stream));
-  B200_CUDA(cudaStreamSynchronize(e->stream));
-  return B200FDTD_OK;
+  return copy_field_out(e, slot, host, (size_t)e->g.nj);
 }
 
 int b200fdtd_set_field(b200fdtd_engine *e, int32_t slot, const double *host)
@@ -578,11 +623,20 @@ int b200fdtd_set_field(b200fdtd_engine *e, int32_t slot, const double *host)
   if (!e || !host || slot < 0 || slot >= e->n_fields) return b200_fail(B200FDTD_ERR_ARG, "bad field slot %d", slot);
   int rc = select_device(e); if (rc) return rc;
   const b200fdtd_grid &g = e->g;
-  B200_CUDA(cudaMemcpy2DAsync(e->field[slot] + (size_t)e->pitch + B200_JOFF, sizeof(double2) * e->pitch,
-                              host + 2 * (size_t)g.j0, sizeof(double2) * g.n_py,
-                              sizeof(double2) * g.nj, g.n_px, cudaMemcpyHostToDevice, e->stream));
-  B200_CUDA(cudaStreamSynchronize(e->stream));
-  return B200FDTD_OK;
+  double2 *dst = e->field[slot], *temp = nullptr;
+  if (e->fp32) {
+    cudaError_t err = cudaMalloc(&temp, e->plane * sizeof(double2));
+    if (err != cudaSuccess) return b200_fail(B200FDTD_ERR_NOMEM, "setter staging plane: %s", cudaGetErrorString(err));
+    dst = temp;
+  }
+  cudaError_t err = cudaMemcpy2DAsync(dst + (size_t)e->pitch + B200_JOFF, sizeof(double2) * e->pitch,
+                                      host + 2 * (size_t)g.j0, sizeof(double2) * g.n_py,
+                                      sizeof(double2) * g.nj, g.n_px, cudaMemcpyHostToDevice, e->stream);
+  if (err == cudaSuccess && e->fp32) rc = b200_narrow_region(e, temp, e->field[slot]);
+  if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
+  cudaFree(temp);
+  if (err != cudaSuccess) return b200_fail(B200FDTD_ERR_CUDA, "field upload: %s", cudaGetErrorString(err));
+  return rc;
 }
 
 int b200fdtd_zero_state(b200fdtd_engine *e)
@@ -590,7 +644,7 @@ int b200fdtd_zero_state(b200fdtd_engine *e)
   if (!e) return b200_fail(B200FDTD_ERR_ARG, "NULL engine");
   int rc = select_device(e); if (rc) return rc;
   for (int s = 0; s < e->n_fields; s++)
-    B200_CUDA(cudaMemsetAsync(e->field[s], 0, e->plane * sizeof(double2), e->stream));
+    B200_CUDA(cudaMemsetAsync(e->field[s], 0, e->plane * e->csize, e->stream));
   e->h_stale = false;
   // peer-halo flags restart with the step counter; a multi-rank reset must be bracketed by
   // the driver's own barrier (no rank may be mid-step while another zeroes)

@@ -67,6 +67,8 @@ struct b200fdtd_engine {
   int pitch, rows;
   size_t plane;             // rows * pitch elements
   int n_fields;
+  bool fp32;                // optional single-precision path: the arrays below then hold
+  size_t csize, rsize;      //   float2 / float elements (csize = 8, rsize = 4) behind the same pointers
   double2 *field[B200FDTD_MAX_FIELDS];
   double *eps[2];
   double *dense[B200FDTD_MAX_DENSE];   // split-field kinds: coefficients + source factors
@@ -105,6 +107,14 @@ int b200_launch_halo(b200fdtd_engine *e, int which, void *buf, bool pack);
 int b200_peer_wait(b200fdtd_engine *e, int which, unsigned long long value);
 int b200_peer_signal(b200fdtd_engine *e, unsigned long long *peer_flag, unsigned long long value);
 int b200_selftest_division(double divisor, unsigned long long samples, unsigned long long *mismatches);
+
+// single-precision support (upml_kernels.cu): widen / narrow between the float2 device
+// arrays and double2 staging planes of the same pitched shape, typed halo column copies
+int b200_widen_plane(b200fdtd_engine *e, const void *src_c64, double2 *dst, size_t count);
+int b200_narrow_region(b200fdtd_engine *e, const double2 *src_plane, void *dst_c64);
+int b200_narrow_real_region(b200fdtd_engine *e, const double *src_region, size_t ld, float *dst_plane);
+int b200_fill_float(b200fdtd_engine *e, float *dst, size_t n, float value);
+int b200_derive_h_f32(b200fdtd_engine *e, int b_slot, int h_slot);
 
 // launchers (split_kernels.cu)
 int b200_launch_split_step(b200fdtd_engine *e, const b200fdtd_step_args *a);

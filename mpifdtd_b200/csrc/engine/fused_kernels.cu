@@ -442,6 +442,7 @@ void b200_fused_release(b200fdtd_engine *e)
 
 int b200_launch_upml_fused(b200fdtd_engine *e, const b200fdtd_step_args *a)
 {
+  if (e->fp32) return b200_fail(B200FDTD_ERR_ARG, "the fused step is double precision only");
   if (!is_tm(e->g.kind)) return b200_fail(B200FDTD_ERR_STATE, "fused step: TM only in this build");
   int rc = b200_fused_prepare(e);
   if (rc) return rc;
@@ -505,6 +506,16 @@ int b200_refresh_h(b200fdtd_engine *e)
 {
   if (!e->h_stale) return B200FDTD_OK;
   const int n_rows = e->r_hi - e->r_lo + 1, n_cols = e->c_hi - e->c_lo + 1;
+  if (e->fp32) {
+    int rc;
+    if (!is_tm(e->g.kind)) rc = b200_derive_h_f32(e, B200FDTD_TE_BZ, B200FDTD_TE_HZ);
+    else {
+      rc = b200_derive_h_f32(e, B200FDTD_TM_BX, B200FDTD_TM_HX);
+      if (!rc) rc = b200_derive_h_f32(e, B200FDTD_TM_BY, B200FDTD_TM_HY);
+    }
+    if (!rc) e->h_stale = false;
+    return rc;
+  }
   if (!is_tm(e->g.kind)) {
     derive_h_kernel<<<1184, 256, 0, e->stream>>>(e->field[B200FDTD_TE_BZ], e->field[B200FDTD_TE_HZ], e->pitch,
                                                  e->r_lo, n_rows, e->c_lo, n_cols, e->g.mu0);

@@ -38,38 +38,45 @@ __device__ __forceinline__ double2 cmul(double2 a, double2 b)
 // sample Ez and the i-averaged Hy; top and left are negated.
 // TE (ntffTE.c:100-155): bottom/top sample Ex and j-averaged Hz, right/left Ey and
 // i-averaged Hz; here bottom and right are the negated ones.
+template <typename C> __device__ __forceinline__ double2 widen(C v) { return make_double2((double)v.x, (double)v.y); }
+// B/mu0 as the engine's H phase forms it: IEEE division in double, one multiplication by
+// RN(1/mu0) in the single-precision path (upml_common.cuh div_const)
+__device__ __forceinline__ double2 h_from_b(double2 b, double mu0) { return make_double2(b.x / mu0, b.y / mu0); }
+__device__ __forceinline__ double2 h_from_b(float2 b, double mu0)
+{
+  const float r = (float)(1.0 / mu0);
+  return make_double2((double)(b.x * r), (double)(b.y * r));
+}
+
+// C = double2, or float2 for single-precision engines (the history is double either way)
+template <typename C>
 __global__ void ntff_sample_kernel(const NtffPoint *__restrict__ pts, int n_local, int is_tm,
-                                   const double2 *__restrict__ e_a,   // TM Ez   | TE Ex
-                                   const double2 *__restrict__ e_b,   // TM Ez   | TE Ey
-                                   const double2 *__restrict__ h_a,   // TM Hx   | TE Hz
-                                   const double2 *__restrict__ h_b,   // TM Hy   | TE Hz
+                                   const C *__restrict__ e_a,   // TM Ez   | TE Ex
+                                   const C *__restrict__ e_b,   // TM Ez   | TE Ey
+                                   const C *__restrict__ h_a,   // TM Hx   | TE Hz
+                                   const C *__restrict__ h_b,   // TM Hy   | TE Hz
                                    int pitch, double2 *hist_e, double2 *hist_h, int max_time, int t,
                                    // when the H arrays are not kept up to date (H == B/mu0 is formed on
                                    // demand): b_a/b_b = Bx/By (TM), divisor = mu0, and c_lo = first updated
                                    // column -- left of it lies the ring / a halo column, which only the H
                                    // array holds.  b_a == nullptr: read H directly.
-                                   const double2 *__restrict__ b_a, const double2 *__restrict__ b_b,
+                                   const C *__restrict__ b_a, const C *__restrict__ b_b,
                                    double h_divisor, int c_lo)
 {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n_local) return;
   const NtffPoint pt = pts[p];
   const bool along_x = (pt.edge == 0 || pt.edge == 2);      // bottom / top edges
-  double2 ev = along_x ? e_a[pt.k] : e_b[pt.k];
+  double2 ev = widen(along_x ? e_a[pt.k] : e_b[pt.k]);
   double2 h0, h1;
   if (b_a == nullptr) {
-    h0 = along_x ? h_a[pt.k] : h_b[pt.k];
-    h1 = along_x ? h_a[pt.k - 1] : h_b[pt.k - pitch];
+    h0 = widen(along_x ? h_a[pt.k] : h_b[pt.k]);
+    h1 = widen(along_x ? h_a[pt.k - 1] : h_b[pt.k - pitch]);
   } else {                                              // same quotients the H phase would have stored
-    const double2 q0 = along_x ? b_a[pt.k] : b_b[pt.k];
-    h0 = make_double2(q0.x / h_divisor, q0.y / h_divisor);
+    h0 = h_from_b(along_x ? b_a[pt.k] : b_b[pt.k], h_divisor);
     const bool left_is_outside = along_x && (int)(pt.k % pitch) - 1 < c_lo;
-    if (left_is_outside) {
-      h1 = h_a[pt.k - 1];
-    } else {
-      const double2 q1 = along_x ? b_a[pt.k - 1] : b_b[pt.k - pitch];
-      h1 = make_double2(q1.x / h_divisor, q1.y / h_divisor);
-    }
+    if (left_is_outside) h1 = widen(h_a[pt.k - 1]);
+    else                 h1 = h_from_b(along_x ? b_a[pt.k - 1] : b_b[pt.k - pitch], h_divisor);
   }
   double2 hv = rmul(0.5, cadd(h0, h1));
   const bool negate = is_tm ? (pt.edge >= 2) : (pt.edge < 2);
@@ -387,16 +394,22 @@ int b200_launch_ntff_sample(b200fdtd_engine *e, const b200fdtd_step_args *a)
     return b200_fail(B200FDTD_ERR_ARG, "NTFF sample at step %d outside [0, %d)", t, n.max_time);
   if (n.n_local > 0) {
     const bool tm = is_tm(e->g.kind);
-    const double2 *ea = e->field[tm ? (int)B200FDTD_TM_EZ : (int)B200FDTD_TE_EX];
-    const double2 *eb = e->field[tm ? (int)B200FDTD_TM_EZ : (int)B200FDTD_TE_EY];
+    const int s_ea = tm ? (int)B200FDTD_TM_EZ : (int)B200FDTD_TE_EX, s_eb = tm ? (int)B200FDTD_TM_EZ : (int)B200FDTD_TE_EY;
+    const int s_ha = tm ? (int)B200FDTD_TM_HX : (int)B200FDTD_TE_HZ, s_hb = tm ? (int)B200FDTD_TM_HY : (int)B200FDTD_TE_HZ;
+    const int s_ba = tm ? (int)B200FDTD_TM_BX : (int)B200FDTD_TE_BZ, s_bb = tm ? (int)B200FDTD_TM_BY : (int)B200FDTD_TE_BZ;
     const bool from_b = e->h_stale;                     // H arrays not kept: sample B/mu0
-    const double2 *ha = e->field[tm ? (int)B200FDTD_TM_HX : (int)B200FDTD_TE_HZ];
-    const double2 *hb = e->field[tm ? (int)B200FDTD_TM_HY : (int)B200FDTD_TE_HZ];
-    const double2 *ba = from_b ? e->field[tm ? (int)B200FDTD_TM_BX : (int)B200FDTD_TE_BZ] : nullptr;
-    const double2 *bb = from_b ? e->field[tm ? (int)B200FDTD_TM_BY : (int)B200FDTD_TE_BZ] : nullptr;
-    ntff_sample_kernel<<<(n.n_local + 127) / 128, 128, 0, e->stream>>>(
-        n.pts, n.n_local, tm ? 1 : 0, ea, eb, ha, hb, e->pitch, n.hist_e, n.hist_h, n.max_time, t,
-        ba, bb, e->g.mu0, e->c_lo);
+    const unsigned blocks = (n.n_local + 127) / 128;
+    if (e->fp32) {
+      const float2 *const *f = (const float2 *const *)e->field;
+      ntff_sample_kernel<float2><<<blocks, 128, 0, e->stream>>>(
+          n.pts, n.n_local, tm ? 1 : 0, f[s_ea], f[s_eb], f[s_ha], f[s_hb], e->pitch, n.hist_e, n.hist_h,
+          n.max_time, t, from_b ? f[s_ba] : nullptr, from_b ? f[s_bb] : nullptr, e->g.mu0, e->c_lo);
+    } else {
+      double2 *const *f = e->field;
+      ntff_sample_kernel<double2><<<blocks, 128, 0, e->stream>>>(
+          n.pts, n.n_local, tm ? 1 : 0, f[s_ea], f[s_eb], f[s_ha], f[s_hb], e->pitch, n.hist_e, n.hist_h,
+          n.max_time, t, from_b ? f[s_ba] : nullptr, from_b ? f[s_bb] : nullptr, e->g.mu0, e->c_lo);
+    }
     e->launches++;
     B200_CUDA(cudaGetLastError());
   }
@@ -423,6 +436,8 @@ int b200_run_ntff_frequency(b200fdtd_engine *e, const b200fdtd_freq_args *a, dou
     return b200_fail(B200FDTD_ERR_ARG, "frequency NTFF serves the TM-type kinds (reference: ntffTM_Frequency)");
   if (e->g.nj != e->g.n_py)
     return b200_fail(B200FDTD_ERR_ARG, "frequency NTFF needs the whole grid on one engine");
+  if (e->fp32)
+    return b200_fail(B200FDTD_ERR_ARG, "frequency NTFF is built for double-precision engines");
   if (a->left < 1 || a->bottom < 1 || a->right >= e->g.n_px || a->top >= e->g.n_py ||
       a->right <= a->left || a->top <= a->bottom || a->n_angles < 1)
     return b200_fail(B200FDTD_ERR_ARG, "bad NTFF box");

@@ -8,34 +8,55 @@ namespace upml {
 
 constexpr int kBlock = 256;
 
-struct ConstDivisor { double d, r; };   // a loop-invariant divisor and RN(1/d), see div_const()
+// complex vector type of a real type: double -> double2 (the reference's arithmetic),
+// float -> float2 (the optional single-precision path, its own tolerance)
+template <typename T> struct Cx;
+template <> struct Cx<double> { using type = double2; };
+template <> struct Cx<float>  { using type = float2; };
 
-struct UpmlView {
-  double2 *f[B200FDTD_MAX_FIELDS];
-  const double *eps0, *eps1;
-  const double *ti, *tj;
+template <typename T> struct ConstDivisorT { T d, r; };   // a loop-invariant divisor and RN(1/d), see div_const()
+using ConstDivisor = ConstDivisorT<double>;
+
+template <typename T>
+struct UpmlViewT {
+  using C = typename Cx<T>::type;
+  C *f[B200FDTD_MAX_FIELDS];
+  const T *eps0, *eps1;
+  const T *ti, *tj;
   int pitch, rows;
   int r_lo, r_hi, c_lo, c_hi;
   int nbx;                      // thread blocks per row (two-kernel form)
   int j_base;                   // global j = j_base + c
-  ConstDivisor mu0;             // MU_0_S and its rounded reciprocal
+  ConstDivisorT<T> mu0;         // MU_0_S and its rounded reciprocal
   b200fdtd_pulse pulse[2];
   b200fdtd_cw cw[2];            // CW source of the MPI-variant kinds (mpiTM_UPML.c:337-374)
   // direct halo stores into the neighbour slabs' ghost columns over NVLink (peer memory):
-  double2 *peer_up_h;           // upper neighbour's H array (Hx / Hz), or nullptr
-  double2 *peer_down_e;         // lower neighbour's E array (Ez / Ex), or nullptr
+  C *peer_up_h;                 // upper neighbour's H array (Hx / Hz), or nullptr
+  C *peer_down_e;               // lower neighbour's E array (Ez / Ex), or nullptr
   int peer_up_pitch, peer_down_pitch, peer_down_col;
   int c_first, c_last;          // first / last owned column in layout coordinates
   b200fdtd_line_source line;    // opt-in planeWave line source (mpiTM_UPML.c:377-403)
   long long point_k;            // layout offset of the opt-in point source, or -1
   double point_re, point_im;
 };
+using UpmlView = UpmlViewT<double>;
 
 __device__ __forceinline__ double2 operator+(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ double2 operator-(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
 __device__ __forceinline__ double2 operator-(double2 a) { return make_double2(-a.x, -a.y); }
 __device__ __forceinline__ double2 operator*(double r, double2 z) { return make_double2(r * z.x, r * z.y); }
 __device__ __forceinline__ double2 operator/(double2 z, double r) { return make_double2(z.x / r, z.y / r); }
+
+__device__ __forceinline__ float2 operator+(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 operator-(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 operator-(float2 a) { return make_float2(-a.x, -a.y); }
+__device__ __forceinline__ float2 operator*(float r, float2 z) { return make_float2(r * z.x, r * z.y); }
+// a source term is always evaluated in double (it touches material cells only) and then
+// rounded once to the field type
+__device__ __forceinline__ double2 to_field(double2 z, double2) { return z; }
+__device__ __forceinline__ float2 to_field(double2 z, float2) { return make_float2((float)z.x, (float)z.y); }
+__device__ __forceinline__ double2 add_source(double2 f, double2 s) { return f + s; }
+__device__ __forceinline__ float2 add_source(float2 f, double2 s) { return f + make_float2((float)s.x, (float)s.y); }
 
 // ---- exact division shortcuts ---------------------------------------------------------
 // The reference divides by MU_0_S four times and by eps twice per TM cell, and two of its
@@ -85,6 +106,19 @@ __device__ __forceinline__ double2 div_eps(double2 z, double eps)
   return z;
 }
 
+// Single-precision path: no bit-exactness contract, so a division by a loop-invariant is one
+// multiplication by the rounded reciprocal and the rest is plain float arithmetic.
+__device__ __forceinline__ float2 div_const(float2 z, const ConstDivisorT<float> c)
+{
+  return make_float2(z.x * c.r, z.y * c.r);
+}
+__device__ __forceinline__ float quotient_or_one(float num, float den) { return num == den ? 1.0f : num / den; }
+__device__ __forceinline__ float2 div_eps(float2 z, float eps)
+{
+  if (eps != 1.0f) z = make_float2(z.x / eps, z.y / eps);
+  return z;
+}
+
 // field_scatteredPulse (field.c:243-254) for one cell; i, j are GLOBAL indices.
 __device__ __forceinline__ double2 pulse_term(const b200fdtd_pulse &s, int i, int j, double eps)
 {
@@ -119,14 +153,16 @@ __device__ __forceinline__ double2 line_term(const b200fdtd_line_source &s, int 
 
 inline bool is_tm(int kind) { return kind == B200FDTD_TM_UPML || kind == B200FDTD_MPI_TM_UPML; }
 
-inline UpmlView make_view(const b200fdtd_engine *e, const b200fdtd_step_args *a)
+template <typename T>
+inline UpmlViewT<T> make_view_t(const b200fdtd_engine *e, const b200fdtd_step_args *a)
 {
-  UpmlView v;
-  for (int s = 0; s < B200FDTD_MAX_FIELDS; s++) v.f[s] = e->field[s];
-  v.eps0 = e->eps[0];
-  v.eps1 = e->eps[1];
-  v.ti = e->tab_i;
-  v.tj = e->tab_j;
+  using C = typename Cx<T>::type;
+  UpmlViewT<T> v;
+  for (int s = 0; s < B200FDTD_MAX_FIELDS; s++) v.f[s] = (C *)e->field[s];
+  v.eps0 = (const T *)e->eps[0];
+  v.eps1 = (const T *)e->eps[1];
+  v.ti = (const T *)e->tab_i;
+  v.tj = (const T *)e->tab_j;
   v.pitch = e->pitch;
   v.rows = e->rows;
   v.r_lo = e->r_lo;
@@ -135,14 +171,14 @@ inline UpmlView make_view(const b200fdtd_engine *e, const b200fdtd_step_args *a)
   v.c_hi = e->c_hi;
   v.nbx = (e->c_hi - e->c_lo + 1 + kBlock - 1) / kBlock;
   v.j_base = e->g.j0 - B200_JOFF;
-  v.mu0.d = e->g.mu0;
-  v.mu0.r = 1.0 / e->g.mu0;
+  v.mu0.d = (T)e->g.mu0;
+  v.mu0.r = (T)(1.0 / e->g.mu0);
   v.pulse[0] = a->pulse[0];
   v.pulse[1] = a->pulse[1];
   v.cw[0] = a->cw[0];
   v.cw[1] = a->cw[1];
-  v.peer_up_h = e->peer.up_h;
-  v.peer_down_e = e->peer.down_e;
+  v.peer_up_h = (C *)e->peer.up_h;
+  v.peer_down_e = (C *)e->peer.down_e;
   v.peer_up_pitch = e->peer.up_pitch;
   v.peer_down_pitch = e->peer.down_pitch;
   v.peer_down_col = B200_JOFF + e->peer.down_nj;   // the lower neighbour's high ghost column
@@ -158,6 +194,10 @@ inline UpmlView make_view(const b200fdtd_engine *e, const b200fdtd_step_args *a)
       v.point_k = (long long)(a->point.i + 1) * e->pitch + pj + B200_JOFF;
   }
   return v;
+}
+inline UpmlView make_view(const b200fdtd_engine *e, const b200fdtd_step_args *a)
+{
+  return make_view_t<double>(e, a);
 }
 
 }  // namespace upml

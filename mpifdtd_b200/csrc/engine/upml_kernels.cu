@@ -29,7 +29,8 @@ namespace {
 using namespace upml;
 
 // Cell owned by this thread, or false when past the row end.
-__device__ __forceinline__ bool locate(const UpmlView &v, int &r, int &c, size_t &k)
+template <typename T>
+__device__ __forceinline__ bool locate(const UpmlViewT<T> &v, int &r, int &c, size_t &k)
 {
   const long long b = blockIdx.x;
   const int rb = (int)(b / v.nbx);
@@ -45,37 +46,38 @@ __device__ __forceinline__ bool locate(const UpmlView &v, int &r, int &c, size_t
 // STORE_H = false: Hx/Hy are not written; the E phase recomputes them from Bx/By
 // (Hx == Bx/mu0 exactly, fdtdTM_upml.c:209), which removes one 32 B/cell write and turns
 // the E phase's H reads into B reads: 264 instead of 296 B per cell-update, in place.
-template <bool STORE_H>
-__global__ void __launch_bounds__(kBlock, B200_H_MIN_BLOCKS) tm_upml_h_kernel(const UpmlView v)
+template <typename T, bool STORE_H>
+__global__ void __launch_bounds__(kBlock, B200_H_MIN_BLOCKS) tm_upml_h_kernel(const UpmlViewT<T> v)
 {
+  using C = typename Cx<T>::type;
   int r, c; size_t k;
   if (!locate(v, r, c, k)) return;
-  const double2 *__restrict__ Ez = v.f[B200FDTD_TM_EZ];
+  const C *__restrict__ Ez = v.f[B200FDTD_TM_EZ];
 
-  const double2 ez = Ez[k];
-  const double2 ez_j1 = Ez[k + 1];            // Ez(i, j+1)
-  const double2 ez_i1 = Ez[k + v.pitch];      // Ez(i+1, j)
-  const double2 mx_old = v.f[B200FDTD_TM_MX][k];
-  const double2 bx_old = v.f[B200FDTD_TM_BX][k];
-  const double2 my_old = v.f[B200FDTD_TM_MY][k];
-  const double2 by_old = v.f[B200FDTD_TM_BY][k];
+  const C ez = Ez[k];
+  const C ez_j1 = Ez[k + 1];            // Ez(i, j+1)
+  const C ez_i1 = Ez[k + v.pitch];      // Ez(i+1, j)
+  const C mx_old = v.f[B200FDTD_TM_MX][k];
+  const C bx_old = v.f[B200FDTD_TM_BX][k];
+  const C my_old = v.f[B200FDTD_TM_MY][k];
+  const C by_old = v.f[B200FDTD_TM_BY][k];
 
-  const double c_mx   = v.tj[B200FDTD_TMJ_C_MX * v.pitch + c];
-  const double c_mxez = v.tj[B200FDTD_TMJ_C_MXEZ * v.pitch + c];
-  const double num1   = v.tj[B200FDTD_TMJ_NUM_BYMY1 * v.pitch + c];
-  const double num0   = v.tj[B200FDTD_TMJ_NUM_BYMY0 * v.pitch + c];
-  const double c_bx1  = v.ti[B200FDTD_TMI_C_BXMX1 * v.rows + r];
-  const double c_bx0  = v.ti[B200FDTD_TMI_C_BXMX0 * v.rows + r];
-  const double c_by   = v.ti[B200FDTD_TMI_C_BY * v.rows + r];
-  const double den    = v.ti[B200FDTD_TMI_DEN_BYMY * v.rows + r];
+  const T c_mx   = v.tj[B200FDTD_TMJ_C_MX * v.pitch + c];
+  const T c_mxez = v.tj[B200FDTD_TMJ_C_MXEZ * v.pitch + c];
+  const T num1   = v.tj[B200FDTD_TMJ_NUM_BYMY1 * v.pitch + c];
+  const T num0   = v.tj[B200FDTD_TMJ_NUM_BYMY0 * v.pitch + c];
+  const T c_bx1  = v.ti[B200FDTD_TMI_C_BXMX1 * v.rows + r];
+  const T c_bx0  = v.ti[B200FDTD_TMI_C_BXMX0 * v.rows + r];
+  const T c_by   = v.ti[B200FDTD_TMI_C_BY * v.rows + r];
+  const T den    = v.ti[B200FDTD_TMI_DEN_BYMY * v.rows + r];
 
   // fdtdTM_upml.c:187-189 (C_BX == 1 exactly)
-  const double2 mx = c_mx * mx_old - c_mxez * (ez_j1 - ez);
-  const double2 bx = (bx_old + c_bx1 * mx) - c_bx0 * mx_old;
+  const C mx = c_mx * mx_old - c_mxez * (ez_j1 - ez);
+  const C bx = (bx_old + c_bx1 * mx) - c_bx0 * mx_old;
   // fdtdTM_upml.c:196-198 (C_MY == C_MYEZ == 1 exactly)
-  const double2 my = my_old - ((-ez_i1) + ez);
-  const double c_by1 = quotient_or_one(num1, den), c_by0 = quotient_or_one(num0, den);   // fdtdTM_upml.c:270-271
-  const double2 by = (c_by * by_old + c_by1 * my) - c_by0 * my_old;
+  const C my = my_old - ((-ez_i1) + ez);
+  const T c_by1 = quotient_or_one(num1, den), c_by0 = quotient_or_one(num0, den);   // fdtdTM_upml.c:270-271
+  const C by = (c_by * by_old + c_by1 * my) - c_by0 * my_old;
 
   v.f[B200FDTD_TM_MX][k] = mx;
   v.f[B200FDTD_TM_BX][k] = bx;
@@ -93,18 +95,19 @@ __global__ void __launch_bounds__(kBlock, B200_H_MIN_BLOCKS) tm_upml_h_kernel(co
 // FROM_B = true: H is formed on the fly as B/mu0.  Cells just outside the updated range
 // (the ring, or a neighbour slab's halo column) are not derived state: there the H array
 // itself is read, exactly like the STORE_H form does.
-template <bool FROM_B>
-__global__ void __launch_bounds__(kBlock, B200_E_MIN_BLOCKS) tm_upml_e_kernel(const UpmlView v)
+template <typename T, bool FROM_B>
+__global__ void __launch_bounds__(kBlock, B200_E_MIN_BLOCKS) tm_upml_e_kernel(const UpmlViewT<T> v)
 {
+  using C = typename Cx<T>::type;
   int r, c; size_t k;
   if (!locate(v, r, c, k)) return;
-  double2 hy, hy_i0, hx, hx_j0;
+  C hy, hy_i0, hx, hx_j0;
   if (FROM_B) {
-    const double2 *__restrict__ Bx = v.f[B200FDTD_TM_BX];
-    const double2 *__restrict__ By = v.f[B200FDTD_TM_BY];
+    const C *__restrict__ Bx = v.f[B200FDTD_TM_BX];
+    const C *__restrict__ By = v.f[B200FDTD_TM_BY];
     // all four loads are issued unconditionally; the (block-uniform, rare) edge cases
     // then replace the derived value by the stored one
-    const double2 by = By[k], bx = Bx[k], by_i0 = By[k - v.pitch], bx_j0 = Bx[k - 1];
+    const C by = By[k], bx = Bx[k], by_i0 = By[k - v.pitch], bx_j0 = Bx[k - 1];
     hy = div_const(by, v.mu0);
     hx = div_const(bx, v.mu0);
     hy_i0 = div_const(by_i0, v.mu0);
@@ -112,36 +115,36 @@ __global__ void __launch_bounds__(kBlock, B200_E_MIN_BLOCKS) tm_upml_e_kernel(co
     if (r == v.r_lo) hy_i0 = v.f[B200FDTD_TM_HY][k - v.pitch];
     if (c == v.c_lo) hx_j0 = v.f[B200FDTD_TM_HX][k - 1];
   } else {
-    const double2 *__restrict__ Hx = v.f[B200FDTD_TM_HX];
-    const double2 *__restrict__ Hy = v.f[B200FDTD_TM_HY];
+    const C *__restrict__ Hx = v.f[B200FDTD_TM_HX];
+    const C *__restrict__ Hy = v.f[B200FDTD_TM_HY];
     hy = Hy[k];
     hy_i0 = Hy[k - v.pitch];      // Hy(i-1, j)
     hx = Hx[k];
     hx_j0 = Hx[k - 1];            // Hx(i, j-1)
   }
-  const double2 jz_old = v.f[B200FDTD_TM_JZ][k];
-  const double2 dz_old = v.f[B200FDTD_TM_DZ][k];
-  const double eps = v.eps0[k];
+  const C jz_old = v.f[B200FDTD_TM_JZ][k];
+  const C dz_old = v.f[B200FDTD_TM_DZ][k];
+  const T eps = v.eps0[k];
 
-  const double c_jz   = v.ti[B200FDTD_TMI_C_JZ * v.rows + r];
-  const double c_jzh  = v.ti[B200FDTD_TMI_C_JZHXHY * v.rows + r];
-  const double c_dz   = v.tj[B200FDTD_TMJ_C_DZ * v.pitch + c];
-  const double c_dzjz = v.tj[B200FDTD_TMJ_C_DZJZ * v.pitch + c];
+  const T c_jz   = v.ti[B200FDTD_TMI_C_JZ * v.rows + r];
+  const T c_jzh  = v.ti[B200FDTD_TMI_C_JZHXHY * v.rows + r];
+  const T c_dz   = v.tj[B200FDTD_TMJ_C_DZ * v.pitch + c];
+  const T c_dzjz = v.tj[B200FDTD_TMJ_C_DZJZ * v.pitch + c];
 
   // fdtdTM_upml.c:161-163 (C_DZJZ1 == C_DZJZ0 because sigma_z = 0)
-  const double2 jz = c_jz * jz_old + c_jzh * (((hy - hy_i0) - hx) + hx_j0);
-  const double2 dz = (c_dz * dz_old + c_dzjz * jz) - c_dzjz * jz_old;
-  double2 ez = div_eps(dz, eps);              // fdtdTM_upml.c:175
+  const C jz = c_jz * jz_old + c_jzh * (((hy - hy_i0) - hx) + hx_j0);
+  const C dz = (c_dz * dz_old + c_dzjz * jz) - c_dzjz * jz_old;
+  C ez = div_eps(dz, eps);              // fdtdTM_upml.c:175
 
-  if (v.pulse[0].enabled && eps != 1.0)       // field.c:248
-    ez = ez + pulse_term(v.pulse[0], r - 1, v.j_base + c, eps);
-  if (v.cw[0].enabled && eps != 1.0)          // mpiTM_UPML.c:370
-    ez = ez + cw_eps_term(v.cw[0], r - 1, v.j_base + c, eps);
+  if (v.pulse[0].enabled && eps != (T)1)       // field.c:248
+    ez = add_source(ez, pulse_term(v.pulse[0], r - 1, v.j_base + c, (double)eps));
+  if (v.cw[0].enabled && eps != (T)1)          // mpiTM_UPML.c:370
+    ez = add_source(ez, cw_eps_term(v.cw[0], r - 1, v.j_base + c, (double)eps));
   if ((long long)k == v.point_k)
-    ez = ez + make_double2(v.point_re, v.point_im);
+    ez = add_source(ez, make_double2(v.point_re, v.point_im));
   if (v.line.enabled && r - 1 == v.line.i) {  // block-uniform: one grid row
     const int j = v.j_base + c;
-    if (j >= v.line.j_lo && j <= v.line.j_hi) ez = ez + line_term(v.line, r - 1, j);
+    if (j >= v.line.j_lo && j <= v.line.j_hi) ez = add_source(ez, line_term(v.line, r - 1, j));
   }
 
   v.f[B200FDTD_TM_JZ][k] = jz;
@@ -154,29 +157,30 @@ __global__ void __launch_bounds__(kBlock, B200_E_MIN_BLOCKS) tm_upml_e_kernel(co
 
 // ------------------------------------------------------------------ TE -----
 // slots: 0 Ex 1 Jx 2 Dx 3 Ey 4 Jy 5 Dy 6 Hz 7 Mz 8 Bz
-template <bool STORE_H>
-__global__ void __launch_bounds__(kBlock) te_upml_h_kernel(const UpmlView v)
+template <typename T, bool STORE_H>
+__global__ void __launch_bounds__(kBlock) te_upml_h_kernel(const UpmlViewT<T> v)
 {
+  using C = typename Cx<T>::type;
   int r, c; size_t k;
   if (!locate(v, r, c, k)) return;
-  const double2 *__restrict__ Ex = v.f[B200FDTD_TE_EX];
-  const double2 *__restrict__ Ey = v.f[B200FDTD_TE_EY];
+  const C *__restrict__ Ex = v.f[B200FDTD_TE_EX];
+  const C *__restrict__ Ey = v.f[B200FDTD_TE_EY];
 
-  const double2 ey_i1 = Ey[k + v.pitch];
-  const double2 ey = Ey[k];
-  const double2 ex_j1 = Ex[k + 1];
-  const double2 ex = Ex[k];
-  const double2 mz_old = v.f[B200FDTD_TE_MZ][k];
-  const double2 bz_old = v.f[B200FDTD_TE_BZ][k];
+  const C ey_i1 = Ey[k + v.pitch];
+  const C ey = Ey[k];
+  const C ex_j1 = Ex[k + 1];
+  const C ex = Ex[k];
+  const C mz_old = v.f[B200FDTD_TE_MZ][k];
+  const C bz_old = v.f[B200FDTD_TE_BZ][k];
 
-  const double c_mz   = v.ti[B200FDTD_TEI_C_MZ * v.rows + r];
-  const double c_mze  = v.ti[B200FDTD_TEI_C_MZEXEY * v.rows + r];
-  const double c_bz   = v.tj[B200FDTD_TEJ_C_BZ * v.pitch + c];
-  const double c_bzmz = v.tj[B200FDTD_TEJ_C_BZMZ * v.pitch + c];
+  const T c_mz   = v.ti[B200FDTD_TEI_C_MZ * v.rows + r];
+  const T c_mze  = v.ti[B200FDTD_TEI_C_MZEXEY * v.rows + r];
+  const T c_bz   = v.tj[B200FDTD_TEJ_C_BZ * v.pitch + c];
+  const T c_bzmz = v.tj[B200FDTD_TEJ_C_BZMZ * v.pitch + c];
 
   // fdtdTE_upml.c:299-301 (C_BZMZ1 == C_BZMZ0 because sigma_z = 0)
-  const double2 mz = c_mz * mz_old - c_mze * (((ey_i1 - ey) - ex_j1) + ex);
-  const double2 bz = (c_bz * bz_old + c_bzmz * mz) - c_bzmz * mz_old;
+  const C mz = c_mz * mz_old - c_mze * (((ey_i1 - ey) - ex_j1) + ex);
+  const C bz = (c_bz * bz_old + c_bzmz * mz) - c_bzmz * mz_old;
 
   v.f[B200FDTD_TE_MZ][k] = mz;
   v.f[B200FDTD_TE_BZ][k] = bz;
@@ -185,16 +189,17 @@ __global__ void __launch_bounds__(kBlock) te_upml_h_kernel(const UpmlView v)
     v.peer_up_h[(size_t)r * v.peer_up_pitch + (B200_JOFF - 1)] = div_const(bz, v.mu0);
 }
 
-template <bool FROM_B>
-__global__ void __launch_bounds__(kBlock) te_upml_e_kernel(const UpmlView v)
+template <typename T, bool FROM_B>
+__global__ void __launch_bounds__(kBlock) te_upml_e_kernel(const UpmlViewT<T> v)
 {
+  using C = typename Cx<T>::type;
   int r, c; size_t k;
   if (!locate(v, r, c, k)) return;
-  const double2 *__restrict__ Hz = v.f[B200FDTD_TE_HZ];
-  double2 hz, hz_j0, hz_i0;
+  const C *__restrict__ Hz = v.f[B200FDTD_TE_HZ];
+  C hz, hz_j0, hz_i0;
   if (FROM_B) {                               // Hz == Bz/mu0 (fdtdTE_upml.c:312), formed on the fly
-    const double2 *__restrict__ Bz = v.f[B200FDTD_TE_BZ];
-    const double2 bz = Bz[k], bz_j0 = Bz[k - 1], bz_i0 = Bz[k - v.pitch];
+    const C *__restrict__ Bz = v.f[B200FDTD_TE_BZ];
+    const C bz = Bz[k], bz_j0 = Bz[k - 1], bz_i0 = Bz[k - v.pitch];
     hz = div_const(bz, v.mu0);
     hz_j0 = div_const(bz_j0, v.mu0);
     hz_i0 = div_const(bz_i0, v.mu0);
@@ -205,40 +210,40 @@ __global__ void __launch_bounds__(kBlock) te_upml_e_kernel(const UpmlView v)
     hz_j0 = Hz[k - 1];
     hz_i0 = Hz[k - v.pitch];
   }
-  const double2 jx_old = v.f[B200FDTD_TE_JX][k];
-  const double2 dx_old = v.f[B200FDTD_TE_DX][k];
-  const double2 jy_old = v.f[B200FDTD_TE_JY][k];
-  const double2 dy_old = v.f[B200FDTD_TE_DY][k];
-  const double eps_x = v.eps0[k], eps_y = v.eps1[k];
+  const C jx_old = v.f[B200FDTD_TE_JX][k];
+  const C dx_old = v.f[B200FDTD_TE_DX][k];
+  const C jy_old = v.f[B200FDTD_TE_JY][k];
+  const C dy_old = v.f[B200FDTD_TE_DY][k];
+  const T eps_x = v.eps0[k], eps_y = v.eps1[k];
 
-  const double c_jx   = v.tj[B200FDTD_TEJ_C_JX * v.pitch + c];
-  const double c_jxhz = v.tj[B200FDTD_TEJ_C_JXHZ * v.pitch + c];
-  const double num1   = v.tj[B200FDTD_TEJ_NUM_DYJY1 * v.pitch + c];
-  const double num0   = v.tj[B200FDTD_TEJ_NUM_DYJY0 * v.pitch + c];
-  const double c_dx1  = v.ti[B200FDTD_TEI_C_DXJX1 * v.rows + r];
-  const double c_dx0  = v.ti[B200FDTD_TEI_C_DXJX0 * v.rows + r];
-  const double c_dy   = v.ti[B200FDTD_TEI_C_DY * v.rows + r];
-  const double den    = v.ti[B200FDTD_TEI_DEN_DYJY * v.rows + r];
+  const T c_jx   = v.tj[B200FDTD_TEJ_C_JX * v.pitch + c];
+  const T c_jxhz = v.tj[B200FDTD_TEJ_C_JXHZ * v.pitch + c];
+  const T num1   = v.tj[B200FDTD_TEJ_NUM_DYJY1 * v.pitch + c];
+  const T num0   = v.tj[B200FDTD_TEJ_NUM_DYJY0 * v.pitch + c];
+  const T c_dx1  = v.ti[B200FDTD_TEI_C_DXJX1 * v.rows + r];
+  const T c_dx0  = v.ti[B200FDTD_TEI_C_DXJX0 * v.rows + r];
+  const T c_dy   = v.ti[B200FDTD_TEI_C_DY * v.rows + r];
+  const T den    = v.ti[B200FDTD_TEI_DEN_DYJY * v.rows + r];
 
   // fdtdTE_upml.c:259-262 (C_DX == 1)
-  const double2 jx = c_jx * jx_old + c_jxhz * (hz - hz_j0);
-  const double2 dx = (dx_old + c_dx1 * jx) - c_dx0 * jx_old;
+  const C jx = c_jx * jx_old + c_jxhz * (hz - hz_j0);
+  const C dx = (dx_old + c_dx1 * jx) - c_dx0 * jx_old;
   // fdtdTE_upml.c:269-271 (C_JY == C_JYHZ == 1)
-  const double2 jy = jy_old + ((-hz) + hz_i0);
-  const double c_dy1 = quotient_or_one(num1, den), c_dy0 = quotient_or_one(num0, den);   // fdtdTE_upml.c:402-403
-  const double2 dy = (c_dy * dy_old + c_dy1 * jy) - c_dy0 * jy_old;
+  const C jy = jy_old + ((-hz) + hz_i0);
+  const T c_dy1 = quotient_or_one(num1, den), c_dy0 = quotient_or_one(num0, den);   // fdtdTE_upml.c:402-403
+  const C dy = (c_dy * dy_old + c_dy1 * jy) - c_dy0 * jy_old;
 
-  double2 ex = div_eps(dx, eps_x);            // fdtdTE_upml.c:283
-  double2 ey = div_eps(dy, eps_y);            // fdtdTE_upml.c:289
+  C ex = div_eps(dx, eps_x);            // fdtdTE_upml.c:283
+  C ey = div_eps(dy, eps_y);            // fdtdTE_upml.c:289
   const int i = r - 1, j = v.j_base + c;
-  if (v.pulse[0].enabled && eps_x != 1.0)     // fdtdTE_upml.c:186-187
-    ex = ex + pulse_term(v.pulse[0], i, j, eps_x);
-  if (v.pulse[1].enabled && eps_y != 1.0)     // fdtdTE_upml.c:188-189
-    ey = ey + pulse_term(v.pulse[1], i, j, eps_y);
-  if (v.cw[0].enabled && eps_x != 1.0) ex = ex + cw_eps_term(v.cw[0], i, j, eps_x);
-  if (v.cw[1].enabled && eps_y != 1.0) ey = ey + cw_eps_term(v.cw[1], i, j, eps_y);   // mpiTE_UPML.c:278
+  if (v.pulse[0].enabled && eps_x != (T)1)     // fdtdTE_upml.c:186-187
+    ex = add_source(ex, pulse_term(v.pulse[0], i, j, (double)eps_x));
+  if (v.pulse[1].enabled && eps_y != (T)1)     // fdtdTE_upml.c:188-189
+    ey = add_source(ey, pulse_term(v.pulse[1], i, j, (double)eps_y));
+  if (v.cw[0].enabled && eps_x != (T)1) ex = add_source(ex, cw_eps_term(v.cw[0], i, j, (double)eps_x));
+  if (v.cw[1].enabled && eps_y != (T)1) ey = add_source(ey, cw_eps_term(v.cw[1], i, j, (double)eps_y));   // mpiTE_UPML.c:278
   if ((long long)k == v.point_k)
-    ex = ex + make_double2(v.point_re, v.point_im);
+    ex = add_source(ex, make_double2(v.point_re, v.point_im));
 
   v.f[B200FDTD_TE_JX][k] = jx;
   v.f[B200FDTD_TE_DX][k] = dx;
@@ -250,19 +255,68 @@ __global__ void __launch_bounds__(kBlock) te_upml_e_kernel(const UpmlView v)
     v.peer_down_e[(size_t)r * v.peer_down_pitch + v.peer_down_col] = ex;
 }
 
-// One halo column <-> a contiguous buffer of n_px complex values.
-// divisor != 0: `field` holds B and the packed value is H = B/divisor (H arrays not kept).
-__global__ void halo_column_kernel(double2 *field, double2 *buf, int pitch, int col, int n_px, int pack,
-                                   double divisor)
+// One halo column <-> a contiguous buffer of n_px complex values (always double complex on
+// the wire, whatever the engine's precision).
+// divisor.d != 0: `field` holds B and the packed value is H = B/divisor (H arrays not kept).
+template <typename T>
+__global__ void halo_column_kernel(typename Cx<T>::type *field, double2 *buf, int pitch, int col, int n_px,
+                                   int pack, ConstDivisorT<T> divisor, int derive)
 {
+  using C = typename Cx<T>::type;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_px) return;
   const size_t k = (size_t)(i + 1) * pitch + col;
   if (pack) {
-    const double2 v = field[k];
-    buf[i] = divisor != 0.0 ? make_double2(v.x / divisor, v.y / divisor) : v;
+    C v = field[k];
+    if (derive) v = div_const(v, divisor);
+    buf[i] = make_double2((double)v.x, (double)v.y);
   } else {
-    field[k] = buf[i];
+    const double2 w = buf[i];
+    C v; v.x = (T)w.x; v.y = (T)w.y;
+    field[k] = v;
+  }
+}
+
+// ---- single-precision support: widen / narrow between float device arrays and double staging
+__global__ void widen_plane_kernel(const float2 *__restrict__ src, double2 *dst, size_t n)
+{
+  for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) {
+    const float2 v = src[k];
+    dst[k] = make_double2((double)v.x, (double)v.y);
+  }
+}
+// owned cells only (rows 1..n_px, columns JOFF..JOFF+nj-1): ghosts keep what they hold
+__global__ void narrow_region_kernel(const double2 *__restrict__ src, float2 *dst, int pitch, int n_px, int nj)
+{
+  const size_t n = (size_t)n_px * nj;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) {
+    const size_t k = (size_t)(1 + t / nj) * pitch + B200_JOFF + t % nj;
+    const double2 v = src[k];
+    dst[k] = make_float2((float)v.x, (float)v.y);
+  }
+}
+__global__ void narrow_real_region_kernel(const double *__restrict__ src, size_t ld, float *dst, int pitch,
+                                          int n_px, int nj)
+{
+  const size_t n = (size_t)n_px * nj;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) {
+    const size_t i = t / nj, c = t % nj;
+    dst[(size_t)(1 + i) * pitch + B200_JOFF + c] = (float)src[i * ld + c];
+  }
+}
+__global__ void fill_float_kernel(float *dst, size_t n, float value)
+{
+  for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x)
+    dst[k] = value;
+}
+// H = B/mu0 exactly as the float STORE_H kernels form it (one multiplication by RN(1/mu0))
+__global__ void derive_h_f32_kernel(const float2 *__restrict__ b, float2 *h, int pitch, int r_lo, int n_rows,
+                                    int c_lo, int n_cols, ConstDivisorT<float> mu0)
+{
+  const size_t n = (size_t)n_rows * n_cols;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) {
+    const size_t k = (size_t)(r_lo + t / n_cols) * pitch + c_lo + t % n_cols;
+    h[k] = div_const(b[k], mu0);
   }
 }
 
@@ -340,40 +394,60 @@ int b200_selftest_division(double divisor, unsigned long long samples, unsigned 
   return B200FDTD_OK;
 }
 
-int b200_launch_upml_h(b200fdtd_engine *e, const b200fdtd_step_args *a)
+template <typename T>
+static int launch_h(b200fdtd_engine *e, const b200fdtd_step_args *a)
 {
-  if (e->r_hi < e->r_lo || e->c_hi < e->c_lo) return B200FDTD_OK;   // slab owns no updated cell
-  const UpmlView v = make_view(e, a);
+  const UpmlViewT<T> v = make_view_t<T>(e, a);
   const long long nblk = (long long)v.nbx * (e->r_hi - e->r_lo + 1);
   if (is_tm(e->g.kind)) {
-    if (e->store_h) tm_upml_h_kernel<true><<<(unsigned)nblk, kBlock, 0, e->stream>>>(v);
-    else            tm_upml_h_kernel<false><<<(unsigned)nblk, kBlock, 0, e->stream>>>(v);
-    e->h_stale = !e->store_h;
+    if (e->store_h) tm_upml_h_kernel<T, true><<<(unsigned)nblk, kBlock, 0, e->stream>>>(v);
+    else            tm_upml_h_kernel<T, false><<<(unsigned)nblk, kBlock, 0, e->stream>>>(v);
   } else {
-    if (e->store_h) te_upml_h_kernel<true><<<(unsigned)nblk, kBlock, 0, e->stream>>>(v);
-    else            te_upml_h_kernel<false><<<(unsigned)nblk, kBlock, 0, e->stream>>>(v);
-    e->h_stale = !e->store_h;
+    if (e->store_h) te_upml_h_kernel<T, true><<<(unsigned)nblk, kBlock, 0, e->stream>>>(v);
+    else            te_upml_h_kernel<T, false><<<(unsigned)nblk, kBlock, 0, e->stream>>>(v);
+  }
+  e->h_stale = !e->store_h;
+  e->launches++;
+  B200_CUDA(cudaGetLastError());
+  return B200FDTD_OK;
+}
+
+template <typename T>
+static int launch_e(b200fdtd_engine *e, const b200fdtd_step_args *a)
+{
+  const UpmlViewT<T> v = make_view_t<T>(e, a);
+  const long long nblk = (long long)v.nbx * (e->r_hi - e->r_lo + 1);
+  if (is_tm(e->g.kind)) {
+    if (e->h_stale) tm_upml_e_kernel<T, true><<<(unsigned)nblk, kBlock, 0, e->stream>>>(v);
+    else            tm_upml_e_kernel<T, false><<<(unsigned)nblk, kBlock, 0, e->stream>>>(v);
+  } else {
+    if (e->h_stale) te_upml_e_kernel<T, true><<<(unsigned)nblk, kBlock, 0, e->stream>>>(v);
+    else            te_upml_e_kernel<T, false><<<(unsigned)nblk, kBlock, 0, e->stream>>>(v);
   }
   e->launches++;
   B200_CUDA(cudaGetLastError());
   return B200FDTD_OK;
 }
 
+int b200_launch_upml_h(b200fdtd_engine *e, const b200fdtd_step_args *a)
+{
+  if (e->r_hi < e->r_lo || e->c_hi < e->c_lo) return B200FDTD_OK;   // slab owns no updated cell
+  return e->fp32 ? launch_h<float>(e, a) : launch_h<double>(e, a);
+}
+
 int b200_launch_upml_e(b200fdtd_engine *e, const b200fdtd_step_args *a)
 {
   if (e->r_hi < e->r_lo || e->c_hi < e->c_lo) return B200FDTD_OK;
-  const UpmlView v = make_view(e, a);
-  const long long nblk = (long long)v.nbx * (e->r_hi - e->r_lo + 1);
-  if (is_tm(e->g.kind)) {
-    if (e->h_stale) tm_upml_e_kernel<true><<<(unsigned)nblk, kBlock, 0, e->stream>>>(v);
-    else            tm_upml_e_kernel<false><<<(unsigned)nblk, kBlock, 0, e->stream>>>(v);
-  } else {
-    if (e->h_stale) te_upml_e_kernel<true><<<(unsigned)nblk, kBlock, 0, e->stream>>>(v);
-    else            te_upml_e_kernel<false><<<(unsigned)nblk, kBlock, 0, e->stream>>>(v);
-  }
-  e->launches++;
-  B200_CUDA(cudaGetLastError());
-  return B200FDTD_OK;
+  return e->fp32 ? launch_e<float>(e, a) : launch_e<double>(e, a);
+}
+
+template <typename T>
+static void launch_halo_t(b200fdtd_engine *e, int slot, void *buf, int col, bool pack, bool derive)
+{
+  const int n = e->g.n_px;
+  ConstDivisorT<T> d; d.d = (T)e->g.mu0; d.r = (T)(1.0 / e->g.mu0);
+  halo_column_kernel<T><<<(n + 255) / 256, 256, 0, e->stream>>>((typename Cx<T>::type *)e->field[slot], (double2 *)buf,
+                                                               e->pitch, col, n, pack ? 1 : 0, d, derive ? 1 : 0);
 }
 
 int b200_launch_halo(b200fdtd_engine *e, int which, void *buf, bool pack)
@@ -386,14 +460,57 @@ int b200_launch_halo(b200fdtd_engine *e, int which, void *buf, bool pack)
     slot = is_tm(e->g.kind) ? (int)B200FDTD_TM_EZ : (int)B200FDTD_TE_EX;
     col = pack ? B200_JOFF : B200_JOFF + e->g.nj;
   }
-  const int n = e->g.n_px;
-  double divisor = 0.0;
+  bool derive = false;
   if (which == 0 && pack && e->h_stale) {     // H column = B column / mu0 (H arrays not kept)
     slot = is_tm(e->g.kind) ? (int)B200FDTD_TM_BX : (int)B200FDTD_TE_BZ;
-    divisor = e->g.mu0;
+    derive = true;
   }
-  halo_column_kernel<<<(n + 255) / 256, 256, 0, e->stream>>>(e->field[slot], (double2 *)buf,
-                                                             e->pitch, col, n, pack ? 1 : 0, divisor);
+  if (e->fp32) launch_halo_t<float>(e, slot, buf, col, pack, derive);
+  else         launch_halo_t<double>(e, slot, buf, col, pack, derive);
+  e->launches++;
+  B200_CUDA(cudaGetLastError());
+  return B200FDTD_OK;
+}
+
+// ---- single-precision support launchers ---------------------------------------------------
+int b200_widen_plane(b200fdtd_engine *e, const void *src_c64, double2 *dst, size_t count)
+{
+  widen_plane_kernel<<<1184, 256, 0, e->stream>>>((const float2 *)src_c64, dst, count);
+  e->launches++;
+  B200_CUDA(cudaGetLastError());
+  return B200FDTD_OK;
+}
+
+int b200_narrow_region(b200fdtd_engine *e, const double2 *src_plane, void *dst_c64)
+{
+  narrow_region_kernel<<<1184, 256, 0, e->stream>>>(src_plane, (float2 *)dst_c64, e->pitch, e->g.n_px, e->g.nj);
+  e->launches++;
+  B200_CUDA(cudaGetLastError());
+  return B200FDTD_OK;
+}
+
+int b200_narrow_real_region(b200fdtd_engine *e, const double *src_region, size_t ld, float *dst_plane)
+{
+  narrow_real_region_kernel<<<1184, 256, 0, e->stream>>>(src_region, ld, dst_plane, e->pitch, e->g.n_px, e->g.nj);
+  e->launches++;
+  B200_CUDA(cudaGetLastError());
+  return B200FDTD_OK;
+}
+
+int b200_fill_float(b200fdtd_engine *e, float *dst, size_t n, float value)
+{
+  fill_float_kernel<<<1184, 256, 0, e->stream>>>(dst, n, value);
+  e->launches++;
+  B200_CUDA(cudaGetLastError());
+  return B200FDTD_OK;
+}
+
+int b200_derive_h_f32(b200fdtd_engine *e, int b_slot, int h_slot)
+{
+  ConstDivisorT<float> d; d.d = (float)e->g.mu0; d.r = (float)(1.0 / e->g.mu0);
+  derive_h_f32_kernel<<<1184, 256, 0, e->stream>>>((const float2 *)e->field[b_slot], (float2 *)e->field[h_slot],
+                                                   e->pitch, e->r_lo, e->r_hi - e->r_lo + 1, e->c_lo,
+                                                   e->c_hi - e->c_lo + 1, d);
   e->launches++;
   B200_CUDA(cudaGetLastError());
   return B200FDTD_OK;

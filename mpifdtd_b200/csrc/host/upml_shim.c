@@ -58,6 +58,7 @@ static int is_mpi_kind(int kind) { return kind == B200FDTD_MPI_TM_UPML || kind =
 static int is_tm_kind(int kind)  { return kind == B200FDTD_TM_UPML || kind == B200FDTD_MPI_TM_UPML; }
 static int point_source_requested;
 static int source_form_requested;      /* MPIFDTD_SRC_* */
+static int precision_requested;        /* B200FDTD_F64 / B200FDTD_F32 */
 
 static void die_on(int rc, const char *what)
 {
@@ -82,6 +83,18 @@ void mpifdtd_enablePointSource(int on) { point_source_requested = on; }
  *                      `left`, columns 1..N_PY-2.
  * Read at init(), like the point source. */
 void mpifdtd_setSourceForm(int form) { source_form_requested = form; }
+
+/* Optional single-precision path of the UPML solvers (ids 2-5): complex64 fields, f32
+ * permittivity and coefficients on the GPU; getters still hand out double complex mirrors and
+ * the NTFF history / far field stay double.  Read at init(); anything but 0/1 is exit(2). */
+void mpifdtd_setPrecision(int precision)
+{
+  if (precision != B200FDTD_F64 && precision != B200FDTD_F32) {
+    printf("mpifdtd_setPrecision: unknown precision %d\n", precision);
+    exit(2);
+  }
+  precision_requested = precision;
+}
 
 /* ---- coefficient tables ------------------------------------------------------
  * Same expressions as setCoefficient (fdtdTM_upml.c:230-271, fdtdTE_upml.c:367-409)
@@ -233,6 +246,7 @@ static void solver_init(UpmlSolver *s)
     grid.j_lo = 0;     grid.j_hi = g.N_PY - 1;
   }
   grid.device = -1;
+  grid.precision = precision_requested;
   grid.mu0 = MU_0_S;
   die_on(b200fdtd_create(&grid, &s->engine), "b200fdtd_create");
 

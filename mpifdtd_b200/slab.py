@@ -57,7 +57,7 @@ class SlabRun:
 
     def __init__(self, model, solver, n_px, n_py, steps, rank=0, world=1, device=-1,
                  h_u_nm=10, pml=10, lambda_nm=500, angle_deg=0, comm=None, n_bins=None,
-                 with_ntff=True):
+                 with_ntff=True, precision=0):
         self.L = B.lib()
         self.kind = KIND[solver] if isinstance(solver, str) else int(solver)
         self.rank, self.world, self.comm = rank, world, comm
@@ -68,7 +68,7 @@ class SlabRun:
                                       angle_deg, steps))
         self.L.models_initModel()
         self.j0, self.nj = split_columns(n_py, world, rank)
-        self.engine = B.Engine(self.kind, n_px, n_py, pml, self.j0, self.nj, device)
+        self.engine = B.Engine(self.kind, n_px, n_py, pml, self.j0, self.nj, device, precision=precision)
 
         ti = np.empty((B.UPML_TABS, n_px))
         tj = np.empty((B.UPML_TABS, n_py))

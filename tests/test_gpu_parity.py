@@ -242,12 +242,13 @@ def test_engine_call_order_is_enforced(plugin_lib):
 
 
 # ---------------------------------------------------------------- y-slab split on one GPU
-def run_slabs(model, solver, npx, npy, steps, world, angle=0):
+def run_slabs(model, solver, npx, npy, steps, world, angle=0, precision=0):
     """`world` engines on one GPU exchanging halo columns through device buffers: the
     multi-GPU data path minus NCCL."""
     import torch
     L = B.lib()
-    runs = [SlabRun(model, solver, npx, npy, steps, rank=r, world=world, device=0, angle_deg=angle)
+    runs = [SlabRun(model, solver, npx, npy, steps, rank=r, world=world, device=0, angle_deg=angle,
+                    precision=precision)
             for r in range(world)]
     bufs = [torch.zeros(2 * npx, dtype=torch.float64, device="cuda") for _ in range(world)]
     args = B.StepArgs()
