@@ -261,6 +261,9 @@ def gpu_arm(args):
     dist = None
     if world > 1:
         import torch.distributed as dist
+        # NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION; stdout carries the JSON line only
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     n_px, n_py = args.n, args.n * world

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define B200FDTD_ABI_VERSION 3
+#define B200FDTD_ABI_VERSION 4
 
 enum {
   B200FDTD_OK = 0,
@@ -105,6 +105,12 @@ typedef struct b200fdtd_grid {
                             /* B200FDTD_F32: complex64 fields, f32 eps/coefficients  */
                             /* (UPML kinds; own tolerance)            */
   double mu0;               /* MU_0_S, passed so the divisor is the host's value   */
+  int32_t n_batch;          /* independent simulations sharing this grid, eps and   */
+                            /* coefficients and differing only in their source      */
+                            /* (incidence angle): the angle sweep of main.c:114-211  */
+                            /* as ONE engine.  0 or 1 = a single simulation.  Serial */
+                            /* UPML kinds (2, 3), whole grid on one engine.          */
+  int32_t reserved2;
 } b200fdtd_grid;
 
 /* Scattered-field Gaussian pulse, field_scatteredPulse (field.c:224-256):
@@ -117,6 +123,15 @@ typedef struct b200fdtd_pulse {
   double time_minus_t0;            /* (time - t0), t0 = -center_peak + 500            */
   double omega, beam_width;
 } b200fdtd_pulse;
+
+/* Per-simulation source of a batched engine (b200fdtd_grid.n_batch > 1): the pulse
+ * parameters that depend on the incidence angle.  pulse[m].time_minus_t0 is ignored; the
+ * kernels form it as step_args.time - t0[m], the very subtraction the host does for a single
+ * simulation (field.c:241,251).  Uploaded once per sweep with b200fdtd_set_batch_sources. */
+typedef struct b200fdtd_batch_source {
+  b200fdtd_pulse pulse[2];
+  double t0[2];
+} b200fdtd_batch_source;
 
 /* Opt-in soft-started point source for the NoModel configuration:
  * value field_pointLight() (field.c:145-152) added to E-slot 0 at (i, j). */
@@ -213,7 +228,7 @@ const char *b200fdtd_last_error(void);
 int b200fdtd_abi_version(void);
 /* sizeof() of the ABI structs as this library was compiled, for foreign-language bindings to
  * check their mirror declarations: which = 0 grid, 1 step_args, 2 ntff_plan, 3 spectrum_args,
- * 4 freq_args; -1 for an unknown index. */
+ * 4 freq_args, 5 batch_source; -1 for an unknown index. */
 int b200fdtd_struct_size(int32_t which);
 
 int b200fdtd_create(const b200fdtd_grid *grid, b200fdtd_engine **out);   /* allocateMemories */
@@ -232,6 +247,12 @@ int b200fdtd_set_eps(b200fdtd_engine *e, int32_t eps_slot, const double *host_ep
 /* the same from a slab-shaped map [n_px][nj] (what a rank of a multi-GPU run builds) */
 int b200fdtd_set_eps_slab(b200fdtd_engine *e, int32_t eps_slot, const double *slab_eps);
 int b200fdtd_set_ntff_plan(b200fdtd_engine *e, const b200fdtd_ntff_plan *plan);   /* ntffTM_init */
+/* batched engines: the n_batch per-simulation sources (host array) */
+int b200fdtd_set_batch_sources(b200fdtd_engine *e, const b200fdtd_batch_source *sources);
+/* batched engines: the simulation the state-access and NTFF read-out calls below refer to
+ * (get/set_field*, ntff_get_uw, ntff_spectrum, ntff_frequency); default 0 */
+int b200fdtd_select_batch(b200fdtd_engine *e, int32_t index);
+
 /* dense per-cell array of a split-field kind: host [n_px][n_py] map (B200FDTD_ST?_C_* or
  * B200FDTD_DENSE_SRC?); replaces the coefficient loops of fdtdTM.c:197-242,
  * nsFdtdTM.c:231-307 etc. */

@@ -211,6 +211,20 @@ extern void mpifdtd_setSourceForm(int form);
  * GPU.  Getters and far-field files keep their double formats. */
 extern void mpifdtd_setPrecision(int precision);
 
+/* ---- angle sweeps as one batched GPU job (extension; replaces the one-angle-per-rank loop
+ * of main.c:114-138,183-211) ------------------------------------------------------------
+ * mpifdtd_setAngleBatch(angles, n): the next init() of a serial UPML solver (ids 2, 3) runs
+ * all n incidence angles at once in one batched engine (they share grid, permittivity and
+ * coefficients); every simulator_calc() advances all of them, reset()/finish() write each
+ * angle's "<ang>[deg].txt" / "<ang>[deg]_380nm_700nm_b.dat" into cwd.  n = 0: off.
+ * mpifdtd_selectAngle(k): the simulation the getters show (default 0).
+ * mpifdtd_runAngleSweep: the whole batch loop for the current model and solver -- angles
+ * start, start+delta, .. <= end in chunks of at most max_batch simulations (0 = as many as
+ * fit), each chunk init -> stepNum x calc -> finish.  Returns the number of simulations run. */
+extern void mpifdtd_setAngleBatch(const int *angles_deg, int n);
+extern void mpifdtd_selectAngle(int index);
+extern int mpifdtd_runAngleSweep(FieldInfo field_info, int start_deg, int end_deg, int delta_deg, int max_batch);
+
 /* ---- config.txt (parser.h:5, configSample.txt:6-22, main.c:319-366) ------ */
 extern bool parser_nextLine(FILE *fp, char buf[]);            /* parser.c:3 */
 typedef struct MpifdtdConfig {

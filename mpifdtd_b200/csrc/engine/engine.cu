@@ -77,6 +77,7 @@ int b200fdtd_struct_size(int32_t which)
   case 2: return (int)sizeof(b200fdtd_ntff_plan);
   case 3: return (int)sizeof(b200fdtd_spectrum_args);
   case 4: return (int)sizeof(b200fdtd_freq_args);
+  case 5: return (int)sizeof(b200fdtd_batch_source);
   default: return -1;
   }
 }
@@ -127,6 +128,11 @@ int b200fdtd_create(const b200fdtd_grid *grid, b200fdtd_engine **out)
     return b200_fail(B200FDTD_ERR_ARG, "unknown precision %d", grid->precision);
   if (grid->precision == B200FDTD_F32 && !kind_is_upml(grid->kind))
     return b200_fail(B200FDTD_ERR_ARG, "the single-precision path serves the UPML kinds (2-5)");
+  const int n_batch = grid->n_batch > 1 ? grid->n_batch : 1;
+  if (n_batch > 1 && ((grid->kind != B200FDTD_TM_UPML && grid->kind != B200FDTD_TE_UPML) ||
+                      grid->j0 != 0 || grid->nj != grid->n_py || n_batch > 65535))
+    return b200_fail(B200FDTD_ERR_ARG, "batched engines serve the serial UPML kinds (2, 3) with the whole "
+                                       "grid on one engine, n_batch <= 65535");
 
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
@@ -151,6 +157,7 @@ int b200fdtd_create(const b200fdtd_grid *grid, b200fdtd_engine **out)
   e->pitch = ((B200_JOFF + grid->nj + 1) + 7) / 8 * 8;
   e->plane = (size_t)e->rows * e->pitch;
   e->n_fields = kind_is_split(grid->kind) ? 5 : 9;
+  e->n_batch = n_batch;
   e->fp32 = grid->precision == B200FDTD_F32;
   e->csize = e->fp32 ? sizeof(float2) : sizeof(double2);
   e->rsize = e->fp32 ? sizeof(float) : sizeof(double);
@@ -158,7 +165,7 @@ int b200fdtd_create(const b200fdtd_grid *grid, b200fdtd_engine **out)
   e->store_h = false;
   e->h_stale = false;
   if (const char *v = getenv("B200FDTD_FUSED"))
-    e->use_fused = atoi(v) != 0 && grid->kind == B200FDTD_TM_UPML && !e->fp32;
+    e->use_fused = atoi(v) != 0 && grid->kind == B200FDTD_TM_UPML && !e->fp32 && n_batch == 1;
   if (const char *v = getenv("B200FDTD_STORE_H")) e->store_h = atoi(v) != 0;
   if (const char *v = getenv("B200FDTD_FUSED_SHAPE")) e->fused_variant = atoi(v);
   if (const char *v = getenv("B200FDTD_BAND_ROWS")) e->fused.band_h = atoi(v);
@@ -172,7 +179,7 @@ int b200fdtd_create(const b200fdtd_grid *grid, b200fdtd_engine **out)
   e->c_hi = jh - grid->j0 + B200_JOFF;
 
   for (int s = 0; s < e->n_fields && !rc; s++)
-    rc = dev_alloc_zero(e, (void **)&e->field[s], e->plane * e->csize);
+    rc = dev_alloc_zero(e, (void **)&e->field[s], e->plane * e->csize * (size_t)n_batch);
   if (kind_is_split(grid->kind)) {
     for (int s = 0; s < B200FDTD_MAX_DENSE && !rc; s++)
       rc = dev_alloc_zero(e, (void **)&e->dense[s], e->plane * sizeof(double));
@@ -182,6 +189,8 @@ int b200fdtd_create(const b200fdtd_grid *grid, b200fdtd_engine **out)
       rc = dev_alloc_zero(e, (void **)&e->eps[s], e->plane * e->rsize);
     if (!rc) rc = dev_alloc_zero(e, (void **)&e->tab_i, sizeof(double) * B200FDTD_UPML_TABS * e->rows);
     if (!rc) rc = dev_alloc_zero(e, (void **)&e->tab_j, sizeof(double) * B200FDTD_UPML_TABS * e->pitch);
+    if (!rc && n_batch > 1)
+      rc = dev_alloc_zero(e, (void **)&e->batch_src, sizeof(b200fdtd_batch_source) * (size_t)n_batch);
   }
   if (rc) { b200fdtd_destroy(e); return rc; }
   if (cudaStreamSynchronize(e->stream) != cudaSuccess) {
@@ -199,7 +208,7 @@ int b200fdtd_destroy(b200fdtd_engine *e)
   if (e->stream) cudaStreamSynchronize(e->stream);
   for (int s = 0; s < B200FDTD_MAX_FIELDS; s++) cudaFree(e->field[s]);
   cudaFree(e->eps[0]); cudaFree(e->eps[1]);
-  cudaFree(e->tab_i); cudaFree(e->tab_j);
+  cudaFree(e->tab_i); cudaFree(e->tab_j); cudaFree(e->batch_src);
   for (int s = 0; s < B200FDTD_MAX_DENSE; s++) cudaFree(e->dense[s]);
   free_ntff(e);
   b200_fused_release(e);
@@ -229,7 +238,8 @@ static int peer_slots(const b200fdtd_engine *e, int *e_slot, int *h_slot)
 int b200fdtd_peer_export(b200fdtd_engine *e, void *blob)
 {
   if (!e || !blob) return b200_fail(B200FDTD_ERR_ARG, "NULL argument");
-  if (!kind_is_upml(e->g.kind)) return b200_fail(B200FDTD_ERR_ARG, "peer halos serve the UPML kinds");
+  if (!kind_is_upml(e->g.kind) || e->n_batch > 1)
+    return b200_fail(B200FDTD_ERR_ARG, "peer halos serve unbatched engines of the UPML kinds");
   int rc = select_device(e); if (rc) return rc;
   if (!e->peer.flags) {
     rc = dev_alloc_zero(e, (void **)&e->peer.flags, 2 * sizeof(unsigned long long));
@@ -388,6 +398,25 @@ int b200fdtd_set_dense(b200fdtd_engine *e, int32_t slot, const double *host_map)
   return B200FDTD_OK;
 }
 
+int b200fdtd_set_batch_sources(b200fdtd_engine *e, const b200fdtd_batch_source *sources)
+{
+  if (!e || !sources) return b200_fail(B200FDTD_ERR_ARG, "NULL argument");
+  if (!e->batch_src) return b200_fail(B200FDTD_ERR_ARG, "engine was not created with n_batch > 1");
+  int rc = select_device(e); if (rc) return rc;
+  B200_CUDA(cudaMemcpyAsync(e->batch_src, sources, sizeof(b200fdtd_batch_source) * (size_t)e->n_batch,
+                            cudaMemcpyHostToDevice, e->stream));
+  B200_CUDA(cudaStreamSynchronize(e->stream));
+  e->have_batch_src = true;
+  return B200FDTD_OK;
+}
+
+int b200fdtd_select_batch(b200fdtd_engine *e, int32_t index)
+{
+  if (!e || index < 0 || index >= e->n_batch) return b200_fail(B200FDTD_ERR_ARG, "batch index %d out of range", index);
+  e->sel = index;
+  return B200FDTD_OK;
+}
+
 int b200fdtd_set_ntff_plan(b200fdtd_engine *e, const b200fdtd_ntff_plan *p)
 {
   if (!e || !p || (!p->time_shift && p->n_local > 0)) return b200_fail(B200FDTD_ERR_ARG, "NULL argument");
@@ -439,9 +468,10 @@ int b200fdtd_set_ntff_plan(b200fdtd_engine *e, const b200fdtd_ntff_plan *p)
   rc = dev_alloc_zero(e, (void **)&n.pts, sizeof(NtffPoint) * (size_t)(n.n_local ? n.n_local : 1));
   const size_t ts_count = (size_t)n.n_angles * (size_t)(n.n_local ? n.n_local : 1);
   if (!rc) rc = dev_alloc_zero(e, (void **)&n.ts, sizeof(double) * ts_count);
-  if (!rc) rc = dev_alloc_zero(e, (void **)&n.hist_e, sizeof(double2) * (size_t)n.n_local * n.max_time);
-  if (!rc) rc = dev_alloc_zero(e, (void **)&n.hist_h, sizeof(double2) * (size_t)n.n_local * n.max_time);
-  if (!rc) rc = dev_alloc_zero(e, (void **)&n.uw, sizeof(double2) * 3 * (size_t)n.n_angles * n.n_bins);
+  const size_t nb = (size_t)e->n_batch;
+  if (!rc) rc = dev_alloc_zero(e, (void **)&n.hist_e, sizeof(double2) * (size_t)n.n_local * n.max_time * nb);
+  if (!rc) rc = dev_alloc_zero(e, (void **)&n.hist_h, sizeof(double2) * (size_t)n.n_local * n.max_time * nb);
+  if (!rc) rc = dev_alloc_zero(e, (void **)&n.uw, sizeof(double2) * 3 * (size_t)n.n_angles * n.n_bins * nb);
   if (rc) { free_ntff(e); return rc; }
   if (n.n_local) {
     B200_CUDA(cudaMemcpyAsync(n.pts, pts.data(), sizeof(NtffPoint) * pts.size(), cudaMemcpyHostToDevice, e->stream));
@@ -465,6 +495,8 @@ static int check_ready(b200fdtd_engine *e, const b200fdtd_step_args *a)
   if (!e->have_tabs) return b200_fail(B200FDTD_ERR_STATE, "step before set_upml_tables");
   if (!e->have_eps[0] || (e->eps[1] && !e->have_eps[1]))
     return b200_fail(B200FDTD_ERR_STATE, "step before set_eps");
+  if (e->n_batch > 1 && !e->have_batch_src)
+    return b200_fail(B200FDTD_ERR_STATE, "step of a batched engine before set_batch_sources");
   return select_device(e);
 }
 
@@ -498,7 +530,7 @@ int b200fdtd_set_option(b200fdtd_engine *e, int32_t option, int32_t value)
   int rc = select_device(e); if (rc) return rc;
   switch (option) {
   case B200FDTD_OPT_FUSED:
-    if (value && (e->g.kind != B200FDTD_TM_UPML || e->fp32))
+    if (value && (e->g.kind != B200FDTD_TM_UPML || e->fp32 || e->n_batch > 1))
       return b200_fail(B200FDTD_ERR_ARG, "the fused step serves the serial TM kind in double precision only");
     e->use_fused = value != 0;
     return B200FDTD_OK;
@@ -554,7 +586,7 @@ int b200fdtd_sync(b200fdtd_engine *e)
 
 int b200fdtd_halo_pack(b200fdtd_engine *e, int32_t which, void *dev_buf)
 {
-  if (!e || !dev_buf || which < 0 || which > 1) return b200_fail(B200FDTD_ERR_ARG, "bad halo argument");
+  if (!e || !dev_buf || which < 0 || which > 1 || e->n_batch > 1) return b200_fail(B200FDTD_ERR_ARG, "bad halo argument");
   int rc = select_device(e); if (rc) return rc;
   return b200_launch_halo(e, which, dev_buf, true);
 }
@@ -571,11 +603,11 @@ int b200fdtd_halo_unpack(b200fdtd_engine *e, int32_t which, const void *dev_buf)
 static int field_plane_f64(b200fdtd_engine *e, int slot, const double2 **plane, double2 **temp)
 {
   *temp = nullptr;
-  *plane = e->field[slot];
+  *plane = e->field[slot] + (size_t)e->sel * e->plane;
   if (!e->fp32) return B200FDTD_OK;
   cudaError_t err = cudaMalloc(temp, e->plane * sizeof(double2));
   if (err != cudaSuccess) return b200_fail(B200FDTD_ERR_NOMEM, "getter staging plane: %s", cudaGetErrorString(err));
-  int rc = b200_widen_plane(e, e->field[slot], *temp, e->plane);
+  int rc = b200_widen_plane(e, (const float2 *)e->field[slot] + (size_t)e->sel * e->plane, *temp, e->plane);
   if (rc) { cudaFree(*temp); *temp = nullptr; return rc; }
   *plane = *temp;
   return B200FDTD_OK;
@@ -623,7 +655,7 @@ int b200fdtd_set_field(b200fdtd_engine *e, int32_t slot, const double *host)
   if (!e || !host || slot < 0 || slot >= e->n_fields) return b200_fail(B200FDTD_ERR_ARG, "bad field slot %d", slot);
   int rc = select_device(e); if (rc) return rc;
   const b200fdtd_grid &g = e->g;
-  double2 *dst = e->field[slot], *temp = nullptr;
+  double2 *dst = e->field[slot] + (size_t)e->sel * e->plane, *temp = nullptr;
   if (e->fp32) {
     cudaError_t err = cudaMalloc(&temp, e->plane * sizeof(double2));
     if (err != cudaSuccess) return b200_fail(B200FDTD_ERR_NOMEM, "setter staging plane: %s", cudaGetErrorString(err));
@@ -632,7 +664,8 @@ int b200fdtd_set_field(b200fdtd_engine *e, int32_t slot, const double *host)
   cudaError_t err = cudaMemcpy2DAsync(dst + (size_t)e->pitch + B200_JOFF, sizeof(double2) * e->pitch,
                                       host + 2 * (size_t)g.j0, sizeof(double2) * g.n_py,
                                       sizeof(double2) * g.nj, g.n_px, cudaMemcpyHostToDevice, e->stream);
-  if (err == cudaSuccess && e->fp32) rc = b200_narrow_region(e, temp, e->field[slot]);
+  if (err == cudaSuccess && e->fp32)
+    rc = b200_narrow_region(e, temp, (float2 *)e->field[slot] + (size_t)e->sel * e->plane);
   if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
   cudaFree(temp);
   if (err != cudaSuccess) return b200_fail(B200FDTD_ERR_CUDA, "field upload: %s", cudaGetErrorString(err));
@@ -644,16 +677,17 @@ int b200fdtd_zero_state(b200fdtd_engine *e)
   if (!e) return b200_fail(B200FDTD_ERR_ARG, "NULL engine");
   int rc = select_device(e); if (rc) return rc;
   for (int s = 0; s < e->n_fields; s++)
-    B200_CUDA(cudaMemsetAsync(e->field[s], 0, e->plane * e->csize, e->stream));
+    B200_CUDA(cudaMemsetAsync(e->field[s], 0, e->plane * e->csize * (size_t)e->n_batch, e->stream));
   e->h_stale = false;
   // peer-halo flags restart with the step counter; a multi-rank reset must be bracketed by
   // the driver's own barrier (no rank may be mid-step while another zeroes)
   if (e->peer.flags) B200_CUDA(cudaMemsetAsync(e->peer.flags, 0, 2 * sizeof(unsigned long long), e->stream));
   NtffState &n = e->ntff;
   if (n.ready) {
-    B200_CUDA(cudaMemsetAsync(n.hist_e, 0, sizeof(double2) * (size_t)n.n_local * n.max_time, e->stream));
-    B200_CUDA(cudaMemsetAsync(n.hist_h, 0, sizeof(double2) * (size_t)n.n_local * n.max_time, e->stream));
-    B200_CUDA(cudaMemsetAsync(n.uw, 0, sizeof(double2) * 3 * (size_t)n.n_angles * n.n_bins, e->stream));
+    const size_t nb = (size_t)e->n_batch;
+    B200_CUDA(cudaMemsetAsync(n.hist_e, 0, sizeof(double2) * (size_t)n.n_local * n.max_time * nb, e->stream));
+    B200_CUDA(cudaMemsetAsync(n.hist_h, 0, sizeof(double2) * (size_t)n.n_local * n.max_time * nb, e->stream));
+    B200_CUDA(cudaMemsetAsync(n.uw, 0, sizeof(double2) * 3 * (size_t)n.n_angles * n.n_bins * nb, e->stream));
     n.steps_recorded = 0;
   }
   B200_CUDA(cudaStreamSynchronize(e->stream));
@@ -673,7 +707,8 @@ int b200fdtd_ntff_get_uw(b200fdtd_engine *e, int32_t slot, double *host)
   int rc = select_device(e); if (rc) return rc;
   const NtffState &n = e->ntff;
   const size_t count = (size_t)n.n_angles * n.n_bins;
-  B200_CUDA(cudaMemcpyAsync(host, n.uw + (size_t)slot * count, sizeof(double2) * count, cudaMemcpyDeviceToHost, e->stream));
+  B200_CUDA(cudaMemcpyAsync(host, n.uw + ((size_t)e->sel * 3 + (size_t)slot) * count, sizeof(double2) * count,
+                            cudaMemcpyDeviceToHost, e->stream));
   B200_CUDA(cudaStreamSynchronize(e->stream));
   return B200FDTD_OK;
 }
@@ -682,7 +717,7 @@ int b200fdtd_ntff_uw_device(b200fdtd_engine *e, void **dev_ptr, uint64_t *n_doub
 {
   if (!e || !dev_ptr || !n_doubles || !e->ntff.ready) return b200_fail(B200FDTD_ERR_ARG, "bad U/W request");
   *dev_ptr = e->ntff.uw;
-  *n_doubles = 2ull * 3ull * (uint64_t)e->ntff.n_angles * (uint64_t)e->ntff.n_bins;
+  *n_doubles = 2ull * 3ull * (uint64_t)e->ntff.n_angles * (uint64_t)e->ntff.n_bins * (uint64_t)e->n_batch;
   return B200FDTD_OK;
 }
 

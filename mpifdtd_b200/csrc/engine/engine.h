@@ -34,8 +34,8 @@ struct NtffState {
   double tap_scale;         // per-tap factor of the MPI-variant ntff() (1 = none)
   NtffPoint *pts;           // device [n_local]
   double *ts;               // device [n_angles][n_local]
-  double2 *hist_e, *hist_h; // device [n_local][max_time]
-  double2 *uw;              // device [3][n_angles][n_bins]
+  double2 *hist_e, *hist_h; // device [n_batch][n_local][max_time]
+  double2 *uw;              // device [n_batch][3][n_angles][n_bins]
   int steps_recorded;
 };
 
@@ -65,7 +65,11 @@ struct b200fdtd_engine {
   cudaStream_t stream;
   bool own_stream;
   int pitch, rows;
-  size_t plane;             // rows * pitch elements
+  size_t plane;             // rows * pitch elements (one simulation)
+  int n_batch;              // simulations stacked in every field array: element offset b * plane
+  int sel;                  // simulation the getters / NTFF read-out refer to
+  b200fdtd_batch_source *batch_src;   // device [n_batch], or nullptr
+  bool have_batch_src;
   int n_fields;
   bool fp32;                // optional single-precision path: the arrays below then hold
   size_t csize, rsize;      //   float2 / float elements (csize = 8, rsize = 4) behind the same pointers

@@ -442,7 +442,8 @@ void b200_fused_release(b200fdtd_engine *e)
 
 int b200_launch_upml_fused(b200fdtd_engine *e, const b200fdtd_step_args *a)
 {
-  if (e->fp32) return b200_fail(B200FDTD_ERR_ARG, "the fused step is double precision only");
+  if (e->fp32 || e->n_batch > 1)
+    return b200_fail(B200FDTD_ERR_ARG, "the fused step serves unbatched double-precision engines");
   if (!is_tm(e->g.kind)) return b200_fail(B200FDTD_ERR_STATE, "fused step: TM only in this build");
   int rc = b200_fused_prepare(e);
   if (rc) return rc;
@@ -516,16 +517,19 @@ int b200_refresh_h(b200fdtd_engine *e)
     if (!rc) e->h_stale = false;
     return rc;
   }
-  if (!is_tm(e->g.kind)) {
-    derive_h_kernel<<<1184, 256, 0, e->stream>>>(e->field[B200FDTD_TE_BZ], e->field[B200FDTD_TE_HZ], e->pitch,
-                                                 e->r_lo, n_rows, e->c_lo, n_cols, e->g.mu0);
-    e->launches += 1;
-  } else {
-    derive_h_kernel<<<1184, 256, 0, e->stream>>>(e->field[B200FDTD_TM_BX], e->field[B200FDTD_TM_HX], e->pitch,
-                                                 e->r_lo, n_rows, e->c_lo, n_cols, e->g.mu0);
-    derive_h_kernel<<<1184, 256, 0, e->stream>>>(e->field[B200FDTD_TM_BY], e->field[B200FDTD_TM_HY], e->pitch,
-                                                 e->r_lo, n_rows, e->c_lo, n_cols, e->g.mu0);
-    e->launches += 2;
+  for (int b = 0; b < e->n_batch; b++) {          // every simulation of a batched engine
+    const size_t off = (size_t)b * e->plane;
+    if (!is_tm(e->g.kind)) {
+      derive_h_kernel<<<1184, 256, 0, e->stream>>>(e->field[B200FDTD_TE_BZ] + off, e->field[B200FDTD_TE_HZ] + off,
+                                                   e->pitch, e->r_lo, n_rows, e->c_lo, n_cols, e->g.mu0);
+      e->launches += 1;
+    } else {
+      derive_h_kernel<<<1184, 256, 0, e->stream>>>(e->field[B200FDTD_TM_BX] + off, e->field[B200FDTD_TM_HX] + off,
+                                                   e->pitch, e->r_lo, n_rows, e->c_lo, n_cols, e->g.mu0);
+      derive_h_kernel<<<1184, 256, 0, e->stream>>>(e->field[B200FDTD_TM_BY] + off, e->field[B200FDTD_TM_HY] + off,
+                                                   e->pitch, e->r_lo, n_rows, e->c_lo, n_cols, e->g.mu0);
+      e->launches += 2;
+    }
   }
   e->h_stale = false;
   B200_CUDA(cudaGetLastError());

@@ -61,11 +61,17 @@ __global__ void ntff_sample_kernel(const NtffPoint *__restrict__ pts, int n_loca
                                    // column -- left of it lies the ring / a halo column, which only the H
                                    // array holds.  b_a == nullptr: read H directly.
                                    const C *__restrict__ b_a, const C *__restrict__ b_b,
-                                   double h_divisor, int c_lo)
+                                   double h_divisor, int c_lo, size_t plane)
 {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n_local) return;
   const NtffPoint pt = pts[p];
+  // blockIdx.y = simulation of a batched engine (0 otherwise): shift every array to its plane
+  const size_t off = (size_t)blockIdx.y * plane;
+  e_a += off; e_b += off; h_a += off; h_b += off;
+  if (b_a != nullptr) { b_a += off; b_b += off; }
+  hist_e += (size_t)blockIdx.y * n_local * max_time;
+  hist_h += (size_t)blockIdx.y * n_local * max_time;
   const bool along_x = (pt.edge == 0 || pt.edge == 2);      // bottom / top edges
   double2 ev = widen(along_x ? e_a[pt.k] : e_b[pt.k]);
   double2 h0, h1;
@@ -122,6 +128,10 @@ ntff_project_kernel(const NtffPoint *__restrict__ pts, const double *__restrict_
   __shared__ double s_ts[kProjBlock];
   __shared__ int s_edge[kProjBlock];
   const int ang = blockIdx.y;
+  // blockIdx.z = simulation of a batched engine: its own history and U/W block, same plan
+  hist_e += (size_t)blockIdx.z * n_local * max_time;
+  hist_h += (size_t)blockIdx.z * n_local * max_time;
+  uw += (size_t)blockIdx.z * 3 * n_angles * n_bins;
   const int q_block = blockIdx.x * kProjBlock;
   const int q = q_block + (int)threadIdx.x;
   double2 acc[3] = { make_double2(0, 0), make_double2(0, 0), make_double2(0, 0) };
@@ -398,17 +408,17 @@ int b200_launch_ntff_sample(b200fdtd_engine *e, const b200fdtd_step_args *a)
     const int s_ha = tm ? (int)B200FDTD_TM_HX : (int)B200FDTD_TE_HZ, s_hb = tm ? (int)B200FDTD_TM_HY : (int)B200FDTD_TE_HZ;
     const int s_ba = tm ? (int)B200FDTD_TM_BX : (int)B200FDTD_TE_BZ, s_bb = tm ? (int)B200FDTD_TM_BY : (int)B200FDTD_TE_BZ;
     const bool from_b = e->h_stale;                     // H arrays not kept: sample B/mu0
-    const unsigned blocks = (n.n_local + 127) / 128;
+    const dim3 blocks((n.n_local + 127) / 128, e->n_batch);
     if (e->fp32) {
       const float2 *const *f = (const float2 *const *)e->field;
       ntff_sample_kernel<float2><<<blocks, 128, 0, e->stream>>>(
           n.pts, n.n_local, tm ? 1 : 0, f[s_ea], f[s_eb], f[s_ha], f[s_hb], e->pitch, n.hist_e, n.hist_h,
-          n.max_time, t, from_b ? f[s_ba] : nullptr, from_b ? f[s_bb] : nullptr, e->g.mu0, e->c_lo);
+          n.max_time, t, from_b ? f[s_ba] : nullptr, from_b ? f[s_bb] : nullptr, e->g.mu0, e->c_lo, e->plane);
     } else {
       double2 *const *f = e->field;
       ntff_sample_kernel<double2><<<blocks, 128, 0, e->stream>>>(
           n.pts, n.n_local, tm ? 1 : 0, f[s_ea], f[s_eb], f[s_ha], f[s_hb], e->pitch, n.hist_e, n.hist_h,
-          n.max_time, t, from_b ? f[s_ba] : nullptr, from_b ? f[s_bb] : nullptr, e->g.mu0, e->c_lo);
+          n.max_time, t, from_b ? f[s_ba] : nullptr, from_b ? f[s_bb] : nullptr, e->g.mu0, e->c_lo, e->plane);
     }
     e->launches++;
     B200_CUDA(cudaGetLastError());
@@ -421,7 +431,7 @@ int b200_launch_ntff_project(b200fdtd_engine *e)
 {
   NtffState &n = e->ntff;
   if (!n.ready) return b200_fail(B200FDTD_ERR_STATE, "ntff_project before set_ntff_plan");
-  dim3 grid((n.n_bins + kProjBlock - 1) / kProjBlock, n.n_angles);
+  dim3 grid((n.n_bins + kProjBlock - 1) / kProjBlock, n.n_angles, e->n_batch);
   ntff_project_kernel<<<grid, kProjBlock, 0, e->stream>>>(
       n.pts, n.ts, n.n_local, n.hist_e, n.hist_h, n.max_time, n.steps_recorded, n.n_bins,
       n.n_angles, is_tm(e->g.kind) ? 1 : 0, n.array_size, n.tap_scale, n.uw);
@@ -444,9 +454,10 @@ int b200_run_ntff_frequency(b200fdtd_engine *e, const b200fdtd_freq_args *a, dou
   int rc = b200_refresh_h(e);
   if (rc) return rc;
   const bool upml = (e->g.kind == B200FDTD_TM_UPML || e->g.kind == B200FDTD_MPI_TM_UPML);
-  const double2 *Ez = e->field[0];
-  const double2 *Hx = e->field[upml ? (int)B200FDTD_TM_HX : (int)B200FDTD_STM_HX];
-  const double2 *Hy = e->field[upml ? (int)B200FDTD_TM_HY : (int)B200FDTD_STM_HY];
+  const size_t sel = (size_t)e->sel * e->plane;
+  const double2 *Ez = e->field[0] + sel;
+  const double2 *Hx = e->field[upml ? (int)B200FDTD_TM_HX : (int)B200FDTD_STM_HX] + sel;
+  const double2 *Hy = e->field[upml ? (int)B200FDTD_TM_HY : (int)B200FDTD_STM_HY] + sel;
   double *d_cos = nullptr, *d_sin = nullptr;
   double2 *d_out = nullptr;
   B200_CUDA(cudaMalloc(&d_cos, sizeof(double) * a->n_angles));
@@ -491,7 +502,7 @@ int b200_run_ntff_spectrum(b200fdtd_engine *e, const b200fdtd_spectrum_args *s, 
   const size_t smem = sizeof(double2) * (size_t)s->n_fft;
   B200_CUDA(cudaFuncSetAttribute(ntff_spectrum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   ntff_spectrum_kernel<<<n.n_angles, 1024, smem, e->stream>>>(
-      n.uw, n.n_bins, n.n_angles, n.max_time, is_tm(e->g.kind) ? 1 : 0,
+      n.uw + (size_t)e->sel * 3 * n.n_angles * n.n_bins, n.n_bins, n.n_angles, n.max_time, is_tm(e->g.kind) ? 1 : 0,
       make_double2(s->coef_re, s->coef_im), s->z0, d_cos, d_sin, d_tw, s->n_fft, log2n,
       s->lambda_first_nm, s->lambda_last_nm, s->c_hu_nfft, d_out);
   e->launches++;

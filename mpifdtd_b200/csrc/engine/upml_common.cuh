@@ -24,6 +24,9 @@ struct UpmlViewT {
   const T *eps0, *eps1;
   const T *ti, *tj;
   int pitch, rows;
+  size_t plane;                 // elements per simulation; blockIdx.y selects the simulation of a batch
+  const b200fdtd_batch_source *batch;   // per-simulation sources of a batched engine, or nullptr
+  double time;                  // step_args.time (batched pulses form time - t0 themselves)
   int r_lo, r_hi, c_lo, c_hi;
   int nbx;                      // thread blocks per row (two-kernel form)
   int j_base;                   // global j = j_base + c
@@ -131,6 +134,22 @@ __device__ __forceinline__ double2 pulse_term(const b200fdtd_pulse &s, int i, in
   return make_double2(amp * cs, amp * sn);
 }
 
+// The pulse of source slot m for this block's simulation: the step's own parameters, or -- in a
+// batched engine -- the per-simulation record with time - t0 formed here (field.c:241,251).
+template <typename T>
+__device__ __forceinline__ b200fdtd_pulse pulse_of(const UpmlViewT<T> &v, int m)
+{
+  if (v.batch == nullptr) return v.pulse[m];
+  b200fdtd_pulse p = v.batch[blockIdx.y].pulse[m];
+  p.time_minus_t0 = v.time - v.batch[blockIdx.y].t0[m];
+  return p;
+}
+template <typename T>
+__device__ __forceinline__ bool pulse_on(const UpmlViewT<T> &v, int m)
+{
+  return v.batch == nullptr ? v.pulse[m].enabled != 0 : v.batch[blockIdx.y].pulse[m].enabled != 0;
+}
+
 // scatteredWave of the MPI solvers (mpiTM_UPML.c:366-370, mpiTE_UPML.c:270-279):
 // p += ray_coef*(eps0/eps - 1)*cexp(i(kr - w t)); i, j are GLOBAL indices.
 __device__ __forceinline__ double2 cw_eps_term(const b200fdtd_cw &s, int i, int j, double eps)
@@ -165,6 +184,9 @@ inline UpmlViewT<T> make_view_t(const b200fdtd_engine *e, const b200fdtd_step_ar
   v.tj = (const T *)e->tab_j;
   v.pitch = e->pitch;
   v.rows = e->rows;
+  v.plane = e->plane;
+  v.batch = e->n_batch > 1 ? e->batch_src : nullptr;
+  v.time = a->time;
   v.r_lo = e->r_lo;
   v.r_hi = e->r_hi;
   v.c_lo = e->c_lo;

@@ -29,15 +29,18 @@ namespace {
 using namespace upml;
 
 // Cell owned by this thread, or false when past the row end.
+// k0 indexes what all simulations of a batch share (eps, the point source); k = k0 + the
+// simulation's plane offset (blockIdx.y, 0 for an unbatched engine) indexes the fields.
 template <typename T>
-__device__ __forceinline__ bool locate(const UpmlViewT<T> &v, int &r, int &c, size_t &k)
+__device__ __forceinline__ bool locate(const UpmlViewT<T> &v, int &r, int &c, size_t &k, size_t &k0)
 {
   const long long b = blockIdx.x;
   const int rb = (int)(b / v.nbx);
   const int cb = (int)(b - (long long)rb * v.nbx);
   r = v.r_lo + rb;
   c = v.c_lo + cb * kBlock + (int)threadIdx.x;
-  k = (size_t)r * (size_t)v.pitch + (size_t)c;
+  k0 = (size_t)r * (size_t)v.pitch + (size_t)c;
+  k = k0 + (size_t)blockIdx.y * v.plane;
   return c <= v.c_hi;
 }
 
@@ -50,8 +53,8 @@ template <typename T, bool STORE_H>
 __global__ void __launch_bounds__(kBlock, B200_H_MIN_BLOCKS) tm_upml_h_kernel(const UpmlViewT<T> v)
 {
   using C = typename Cx<T>::type;
-  int r, c; size_t k;
-  if (!locate(v, r, c, k)) return;
+  int r, c; size_t k, k0;
+  if (!locate(v, r, c, k, k0)) return;
   const C *__restrict__ Ez = v.f[B200FDTD_TM_EZ];
 
   const C ez = Ez[k];
@@ -99,8 +102,8 @@ template <typename T, bool FROM_B>
 __global__ void __launch_bounds__(kBlock, B200_E_MIN_BLOCKS) tm_upml_e_kernel(const UpmlViewT<T> v)
 {
   using C = typename Cx<T>::type;
-  int r, c; size_t k;
-  if (!locate(v, r, c, k)) return;
+  int r, c; size_t k, k0;
+  if (!locate(v, r, c, k, k0)) return;
   C hy, hy_i0, hx, hx_j0;
   if (FROM_B) {
     const C *__restrict__ Bx = v.f[B200FDTD_TM_BX];
@@ -124,7 +127,7 @@ __global__ void __launch_bounds__(kBlock, B200_E_MIN_BLOCKS) tm_upml_e_kernel(co
   }
   const C jz_old = v.f[B200FDTD_TM_JZ][k];
   const C dz_old = v.f[B200FDTD_TM_DZ][k];
-  const T eps = v.eps0[k];
+  const T eps = v.eps0[k0];
 
   const T c_jz   = v.ti[B200FDTD_TMI_C_JZ * v.rows + r];
   const T c_jzh  = v.ti[B200FDTD_TMI_C_JZHXHY * v.rows + r];
@@ -136,11 +139,11 @@ __global__ void __launch_bounds__(kBlock, B200_E_MIN_BLOCKS) tm_upml_e_kernel(co
   const C dz = (c_dz * dz_old + c_dzjz * jz) - c_dzjz * jz_old;
   C ez = div_eps(dz, eps);              // fdtdTM_upml.c:175
 
-  if (v.pulse[0].enabled && eps != (T)1)       // field.c:248
-    ez = add_source(ez, pulse_term(v.pulse[0], r - 1, v.j_base + c, (double)eps));
+  if (eps != (T)1 && pulse_on(v, 0))       // field.c:248
+    ez = add_source(ez, pulse_term(pulse_of(v, 0), r - 1, v.j_base + c, (double)eps));
   if (v.cw[0].enabled && eps != (T)1)          // mpiTM_UPML.c:370
     ez = add_source(ez, cw_eps_term(v.cw[0], r - 1, v.j_base + c, (double)eps));
-  if ((long long)k == v.point_k)
+  if ((long long)k0 == v.point_k)
     ez = add_source(ez, make_double2(v.point_re, v.point_im));
   if (v.line.enabled && r - 1 == v.line.i) {  // block-uniform: one grid row
     const int j = v.j_base + c;
@@ -161,8 +164,8 @@ template <typename T, bool STORE_H>
 __global__ void __launch_bounds__(kBlock) te_upml_h_kernel(const UpmlViewT<T> v)
 {
   using C = typename Cx<T>::type;
-  int r, c; size_t k;
-  if (!locate(v, r, c, k)) return;
+  int r, c; size_t k, k0;
+  if (!locate(v, r, c, k, k0)) return;
   const C *__restrict__ Ex = v.f[B200FDTD_TE_EX];
   const C *__restrict__ Ey = v.f[B200FDTD_TE_EY];
 
@@ -193,8 +196,8 @@ template <typename T, bool FROM_B>
 __global__ void __launch_bounds__(kBlock) te_upml_e_kernel(const UpmlViewT<T> v)
 {
   using C = typename Cx<T>::type;
-  int r, c; size_t k;
-  if (!locate(v, r, c, k)) return;
+  int r, c; size_t k, k0;
+  if (!locate(v, r, c, k, k0)) return;
   const C *__restrict__ Hz = v.f[B200FDTD_TE_HZ];
   C hz, hz_j0, hz_i0;
   if (FROM_B) {                               // Hz == Bz/mu0 (fdtdTE_upml.c:312), formed on the fly
@@ -214,7 +217,7 @@ __global__ void __launch_bounds__(kBlock) te_upml_e_kernel(const UpmlViewT<T> v)
   const C dx_old = v.f[B200FDTD_TE_DX][k];
   const C jy_old = v.f[B200FDTD_TE_JY][k];
   const C dy_old = v.f[B200FDTD_TE_DY][k];
-  const T eps_x = v.eps0[k], eps_y = v.eps1[k];
+  const T eps_x = v.eps0[k0], eps_y = v.eps1[k0];
 
   const T c_jx   = v.tj[B200FDTD_TEJ_C_JX * v.pitch + c];
   const T c_jxhz = v.tj[B200FDTD_TEJ_C_JXHZ * v.pitch + c];
@@ -236,13 +239,13 @@ __global__ void __launch_bounds__(kBlock) te_upml_e_kernel(const UpmlViewT<T> v)
   C ex = div_eps(dx, eps_x);            // fdtdTE_upml.c:283
   C ey = div_eps(dy, eps_y);            // fdtdTE_upml.c:289
   const int i = r - 1, j = v.j_base + c;
-  if (v.pulse[0].enabled && eps_x != (T)1)     // fdtdTE_upml.c:186-187
-    ex = add_source(ex, pulse_term(v.pulse[0], i, j, (double)eps_x));
-  if (v.pulse[1].enabled && eps_y != (T)1)     // fdtdTE_upml.c:188-189
-    ey = add_source(ey, pulse_term(v.pulse[1], i, j, (double)eps_y));
+  if (eps_x != (T)1 && pulse_on(v, 0))     // fdtdTE_upml.c:186-187
+    ex = add_source(ex, pulse_term(pulse_of(v, 0), i, j, (double)eps_x));
+  if (eps_y != (T)1 && pulse_on(v, 1))     // fdtdTE_upml.c:188-189
+    ey = add_source(ey, pulse_term(pulse_of(v, 1), i, j, (double)eps_y));
   if (v.cw[0].enabled && eps_x != (T)1) ex = add_source(ex, cw_eps_term(v.cw[0], i, j, (double)eps_x));
   if (v.cw[1].enabled && eps_y != (T)1) ey = add_source(ey, cw_eps_term(v.cw[1], i, j, (double)eps_y));   // mpiTE_UPML.c:278
-  if ((long long)k == v.point_k)
+  if ((long long)k0 == v.point_k)
     ex = add_source(ex, make_double2(v.point_re, v.point_im));
 
   v.f[B200FDTD_TE_JX][k] = jx;
@@ -400,11 +403,11 @@ static int launch_h(b200fdtd_engine *e, const b200fdtd_step_args *a)
   const UpmlViewT<T> v = make_view_t<T>(e, a);
   const long long nblk = (long long)v.nbx * (e->r_hi - e->r_lo + 1);
   if (is_tm(e->g.kind)) {
-    if (e->store_h) tm_upml_h_kernel<T, true><<<(unsigned)nblk, kBlock, 0, e->stream>>>(v);
-    else            tm_upml_h_kernel<T, false><<<(unsigned)nblk, kBlock, 0, e->stream>>>(v);
+    if (e->store_h) tm_upml_h_kernel<T, true><<<dim3((unsigned)nblk, (unsigned)e->n_batch), kBlock, 0, e->stream>>>(v);
+    else            tm_upml_h_kernel<T, false><<<dim3((unsigned)nblk, (unsigned)e->n_batch), kBlock, 0, e->stream>>>(v);
   } else {
-    if (e->store_h) te_upml_h_kernel<T, true><<<(unsigned)nblk, kBlock, 0, e->stream>>>(v);
-    else            te_upml_h_kernel<T, false><<<(unsigned)nblk, kBlock, 0, e->stream>>>(v);
+    if (e->store_h) te_upml_h_kernel<T, true><<<dim3((unsigned)nblk, (unsigned)e->n_batch), kBlock, 0, e->stream>>>(v);
+    else            te_upml_h_kernel<T, false><<<dim3((unsigned)nblk, (unsigned)e->n_batch), kBlock, 0, e->stream>>>(v);
   }
   e->h_stale = !e->store_h;
   e->launches++;
@@ -418,11 +421,11 @@ static int launch_e(b200fdtd_engine *e, const b200fdtd_step_args *a)
   const UpmlViewT<T> v = make_view_t<T>(e, a);
   const long long nblk = (long long)v.nbx * (e->r_hi - e->r_lo + 1);
   if (is_tm(e->g.kind)) {
-    if (e->h_stale) tm_upml_e_kernel<T, true><<<(unsigned)nblk, kBlock, 0, e->stream>>>(v);
-    else            tm_upml_e_kernel<T, false><<<(unsigned)nblk, kBlock, 0, e->stream>>>(v);
+    if (e->h_stale) tm_upml_e_kernel<T, true><<<dim3((unsigned)nblk, (unsigned)e->n_batch), kBlock, 0, e->stream>>>(v);
+    else            tm_upml_e_kernel<T, false><<<dim3((unsigned)nblk, (unsigned)e->n_batch), kBlock, 0, e->stream>>>(v);
   } else {
-    if (e->h_stale) te_upml_e_kernel<T, true><<<(unsigned)nblk, kBlock, 0, e->stream>>>(v);
-    else            te_upml_e_kernel<T, false><<<(unsigned)nblk, kBlock, 0, e->stream>>>(v);
+    if (e->h_stale) te_upml_e_kernel<T, true><<<dim3((unsigned)nblk, (unsigned)e->n_batch), kBlock, 0, e->stream>>>(v);
+    else            te_upml_e_kernel<T, false><<<dim3((unsigned)nblk, (unsigned)e->n_batch), kBlock, 0, e->stream>>>(v);
   }
   e->launches++;
   B200_CUDA(cudaGetLastError());
@@ -508,10 +511,13 @@ int b200_fill_float(b200fdtd_engine *e, float *dst, size_t n, float value)
 int b200_derive_h_f32(b200fdtd_engine *e, int b_slot, int h_slot)
 {
   ConstDivisorT<float> d; d.d = (float)e->g.mu0; d.r = (float)(1.0 / e->g.mu0);
-  derive_h_f32_kernel<<<1184, 256, 0, e->stream>>>((const float2 *)e->field[b_slot], (float2 *)e->field[h_slot],
-                                                   e->pitch, e->r_lo, e->r_hi - e->r_lo + 1, e->c_lo,
-                                                   e->c_hi - e->c_lo + 1, d);
-  e->launches++;
+  for (int b = 0; b < e->n_batch; b++) {
+    const size_t off = (size_t)b * e->plane;
+    derive_h_f32_kernel<<<1184, 256, 0, e->stream>>>((const float2 *)e->field[b_slot] + off,
+                                                     (float2 *)e->field[h_slot] + off, e->pitch, e->r_lo,
+                                                     e->r_hi - e->r_lo + 1, e->c_lo, e->c_hi - e->c_lo + 1, d);
+    e->launches++;
+  }
   B200_CUDA(cudaGetLastError());
   return B200FDTD_OK;
 }

@@ -40,6 +40,8 @@ typedef struct UpmlSolver {
   int n_cell;
   int point_source;               /* opt-in, see mpifdtd_enablePointSource         */
   int source_form;                /* opt-in, see mpifdtd_setSourceForm             */
+  int n_batch;                    /* > 1: angle batch, see mpifdtd_setAngleBatch    */
+  int batch_angles[MPIFDTD_MAX_ANGLE_BATCH];
   double *eps_ringed;             /* MPI-variant ids: eps map inside its ghost ring */
 } UpmlSolver;
 
@@ -59,6 +61,9 @@ static int is_tm_kind(int kind)  { return kind == B200FDTD_TM_UPML || kind == B2
 static int point_source_requested;
 static int source_form_requested;      /* MPIFDTD_SRC_* */
 static int precision_requested;        /* B200FDTD_F64 / B200FDTD_F32 */
+#define MPIFDTD_MAX_ANGLE_BATCH 4096
+static int batch_requested;            /* number of angles of the next init(), 0 = unbatched */
+static int batch_angles_requested[MPIFDTD_MAX_ANGLE_BATCH];
 
 static void die_on(int rc, const char *what)
 {
@@ -94,6 +99,23 @@ void mpifdtd_setPrecision(int precision)
     exit(2);
   }
   precision_requested = precision;
+}
+
+/* Angle batch.  The reference sweeps incidence angles one simulation at a
+ * time -- one angle per MPI rank, reset() + field_setWaveAngle() in between (main.c:114-138,
+ * 183-211).  The simulations of a sweep share grid, permittivity and coefficients and differ
+ * only in the source, so here the next init() of a serial UPML solver (ids 2, 3) can take ALL
+ * angles at once: one batched engine, every update() advances every angle in the same two
+ * kernel launches, and reset()/finish() write each angle's "<ang>[deg]..." files.
+ * mpifdtd_selectAngle(k) picks the simulation the getters show.  n = 0 switches it off. */
+void mpifdtd_setAngleBatch(const int *angles_deg, int n)
+{
+  if (n < 0 || n > MPIFDTD_MAX_ANGLE_BATCH || (n > 0 && angles_deg == NULL)) {
+    printf("mpifdtd_setAngleBatch: bad batch of %d angles (max %d)\n", n, MPIFDTD_MAX_ANGLE_BATCH);
+    exit(2);
+  }
+  batch_requested = n;
+  for (int k = 0; k < n; k++) batch_angles_requested[k] = angles_deg[k];
 }
 
 /* ---- coefficient tables ------------------------------------------------------
@@ -233,6 +255,11 @@ static void solver_init(UpmlSolver *s)
   s->n_cell = g.N_CELL;
   s->point_source = point_source_requested;
   s->source_form = source_form_requested;
+  s->n_batch = 0;
+  if (batch_requested > 0 && !mpi) {
+    s->n_batch = batch_requested;
+    memcpy(s->batch_angles, batch_angles_requested, sizeof(int) * (size_t)batch_requested);
+  }
 
   b200fdtd_grid grid;
   memset(&grid, 0, sizeof grid);
@@ -248,7 +275,14 @@ static void solver_init(UpmlSolver *s)
   grid.device = -1;
   grid.precision = precision_requested;
   grid.mu0 = MU_0_S;
+  grid.n_batch = s->n_batch;
   die_on(b200fdtd_create(&grid, &s->engine), "b200fdtd_create");
+  if (s->n_batch > 1) {
+    b200fdtd_batch_source *src = (b200fdtd_batch_source *)malloc(sizeof *src * (size_t)s->n_batch);
+    for (int k = 0; k < s->n_batch; k++) fill_batch_source(s->kind, (double)s->batch_angles[k], &src[k]);
+    die_on(b200fdtd_set_batch_sources(s->engine, src), "b200fdtd_set_batch_sources");
+    free(src);
+  }
 
   /* permittivity maps.  TM: EPS_EZ at (i,j) area-averaged; EPS_HX/EPS_HY are
    * computed upstream but never read (fdtdTM_upml.c:237-239), so they are not
@@ -323,10 +357,10 @@ static void solver_init(UpmlSolver *s)
 }
 
 /* ---- update ------------------------------------------------------------------ */
-static void fill_pulse(b200fdtd_pulse *p, double gap_x, double gap_y, double dot)
+static double fill_pulse_at(b200fdtd_pulse *p, double angle_deg, double gap_x, double gap_y, double dot)
 {
   FieldInfo_S g = field_getFieldInfo_S();
-  double rad = field_getWaveAngle() * M_PI / 180.0;           /* field.c:228-241 */
+  double rad = angle_deg * M_PI / 180.0;                      /* field.c:228-241 */
   double cos_per_c = cos(rad) / C_0_S, sin_per_c = sin(rad) / C_0_S;
   const double center_peak = (g.N_PX / 2.0 + gap_x) * cos_per_c + (g.N_PY / 2 + gap_y) * sin_per_c;
   const double t0 = -center_peak + 500;
@@ -336,6 +370,27 @@ static void fill_pulse(b200fdtd_pulse *p, double gap_x, double gap_y, double dot
   p->time_minus_t0 = field_getTime() - t0;
   p->omega = field_getOmega();
   p->beam_width = 50;
+  return t0;
+}
+
+static void fill_pulse(b200fdtd_pulse *p, double gap_x, double gap_y, double dot)
+{
+  fill_pulse_at(p, field_getWaveAngle(), gap_x, gap_y, dot);
+}
+
+/* The pulse(s) update() fires for one incidence angle (fdtdTM_upml.c:63, fdtdTE_upml.c:182-189),
+ * as the per-simulation record of a batched engine. */
+static void fill_batch_source(int kind, double angle_deg, b200fdtd_batch_source *b)
+{
+  memset(b, 0, sizeof *b);
+  if (kind == B200FDTD_TM_UPML) {
+    b->t0[0] = fill_pulse_at(&b->pulse[0], angle_deg, 0, 0, 1.0);
+  } else {
+    double co = cos((angle_deg + 90) * M_PI / 180.0);
+    double si = sin((angle_deg + 90) * M_PI / 180.0);
+    if (co != 0.0) b->t0[0] = fill_pulse_at(&b->pulse[0], angle_deg, 0.5, 0.0, co);
+    if (si != 0.0) b->t0[1] = fill_pulse_at(&b->pulse[1], angle_deg, 0.0, 0.5, si);
+  }
 }
 
 /* Everything update() reads from the host's grid/time state, packed for the
@@ -453,18 +508,35 @@ static void write_far_field(UpmlSolver *s)
   const int rows = LAMBDA_EN_NM - LAMBDA_ST_NM + 1;
   double *table = (double *)malloc(sizeof(double) * (size_t)rows * N_ANGLES);
   double **by_row = (double **)malloc(sizeof(double *) * (size_t)rows);
-  mpifdtd_upml_far_field(s->engine, s->kind, 1, table);
   for (int r = 0; r < rows; r++) by_row[r] = table + (size_t)r * N_ANGLES;
-
   char name[256], cwd[512];
   if (getcwd(cwd, sizeof cwd) == NULL) cwd[0] = '\0';
-  sprintf(name, "%d[deg].txt", (int)field_getWaveAngle());
-  ntff_outputEnormTxt(by_row, name);
-  printf("saved %s/%s\n", cwd, name);
-  sprintf(name, "%d[deg]_%dnm_%dnm_b.dat", (int)field_getWaveAngle(), LAMBDA_ST_NM, LAMBDA_EN_NM);
-  ntff_outputEnormBin(by_row, name);
-  printf("saved %s/%s\n", cwd, name);
+
+  /* an angle batch writes one pair of files per simulation, named by its own angle; the
+   * projection kernel turns every simulation's history into U/W in one launch */
+  const int n = s->n_batch > 1 ? s->n_batch : 1;
+  for (int k = 0; k < n; k++) {
+    const int angle = s->n_batch > 1 ? s->batch_angles[k] : (int)field_getWaveAngle();
+    if (s->n_batch > 1) die_on(b200fdtd_select_batch(s->engine, k), "b200fdtd_select_batch");
+    mpifdtd_upml_far_field(s->engine, s->kind, k == 0, table);
+    sprintf(name, "%d[deg].txt", angle);
+    ntff_outputEnormTxt(by_row, name);
+    printf("saved %s/%s\n", cwd, name);
+    sprintf(name, "%d[deg]_%dnm_%dnm_b.dat", angle, LAMBDA_ST_NM, LAMBDA_EN_NM);
+    ntff_outputEnormBin(by_row, name);
+    printf("saved %s/%s\n", cwd, name);
+  }
+  if (s->n_batch > 1) die_on(b200fdtd_select_batch(s->engine, 0), "b200fdtd_select_batch");
   free(by_row); free(table);
+}
+
+/* which simulation of an angle batch the getters (and mpifdtd_upml_far_field) refer to */
+void mpifdtd_selectAngle(int index)
+{
+  UpmlSolver *all[2] = { &tm_solver, &te_solver };
+  for (int m = 0; m < 2; m++)
+    if (all[m]->engine != NULL && all[m]->n_batch > 1)
+      die_on(b200fdtd_select_batch(all[m]->engine, index), "b200fdtd_select_batch");
 }
 
 /* ntffOutput + ntffSaveData of the MPI TE solver (mpiTE_UPML.c:795-878): translate the first
