@@ -345,6 +345,8 @@ int b200fdtd_selftest_division(double divisor, uint64_t samples, uint64_t *misma
 /* kernels launched by this engine since creation (bench.py's gpu_launches) */
 int b200fdtd_launch_count(b200fdtd_engine *e, uint64_t *count);
 int b200fdtd_device_bytes(b200fdtd_engine *e, uint64_t *bytes);
+/* free / total memory of a CUDA device (-1 = current), for sizing angle batches */
+int b200fdtd_mem_info(int32_t device, uint64_t *free_bytes, uint64_t *total_bytes);
 /* CUDA-event timing on the engine's stream: elapsed ms between the two marks */
 int b200fdtd_timer_start(b200fdtd_engine *e);
 int b200fdtd_timer_stop(b200fdtd_engine *e, float *elapsed_ms);

@@ -48,7 +48,8 @@ class Grid(C.Structure):
     _fields_ = [("kind", C.c_int32), ("n_px", C.c_int32), ("n_py", C.c_int32), ("n_pml", C.c_int32),
                 ("j0", C.c_int32), ("nj", C.c_int32), ("i_lo", C.c_int32), ("i_hi", C.c_int32),
                 ("j_lo", C.c_int32), ("j_hi", C.c_int32), ("device", C.c_int32),
-                ("precision", C.c_int32), ("mu0", C.c_double)]
+                ("precision", C.c_int32), ("mu0", C.c_double),
+                ("n_batch", C.c_int32), ("reserved2", C.c_int32)]
 
 
 class Pulse(C.Structure):
@@ -191,6 +192,12 @@ def lib():
     L.mpifdtd_enablePointSource.argtypes = [C.c_int]
     L.mpifdtd_setSourceForm.argtypes = [C.c_int]
     L.mpifdtd_setPrecision.argtypes = [C.c_int]
+    L.mpifdtd_setAngleBatch.argtypes = [C.POINTER(C.c_int), C.c_int]
+    L.mpifdtd_selectAngle.argtypes = [C.c_int]
+    L.mpifdtd_runAngleSweep.argtypes = [FieldInfo, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.b200fdtd_mem_info.argtypes = [i32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.b200fdtd_select_batch.argtypes = [vp, i32]
+    L.b200fdtd_set_batch_sources.argtypes = [vp, vp]
     L.b200fdtd_struct_size.argtypes = [i32]
     L.mpifdtd_readConfig.argtypes = [C.c_char_p, vp]
     for name in ("fdtdTM_upml_getHx", "fdtdTM_upml_getHy", "fdtdTM_upml_getEz",
@@ -245,7 +252,7 @@ class Plugin:
                7: {f: "nsFdtdTE_get" + f for f in ("Ex", "Ey", "Hz", "Hzx", "Hzy")}}
 
     def __init__(self, model, solver, n_px, n_py=None, steps=100, h_u_nm=10, pml=10,
-                 lambda_nm=500, angle_deg=0, point_source=False, source_form=0, precision=0):
+                 lambda_nm=500, angle_deg=0, point_source=False, source_form=0, precision=0, angle_batch=None):
         self.L = lib()
         self.model = MODELS[model] if isinstance(model, str) else int(model)
         self.solver = SOLVERS[solver] if isinstance(solver, str) else int(solver)
@@ -255,6 +262,12 @@ class Plugin:
         self.L.mpifdtd_enablePointSource(1 if point_source else 0)
         self.L.mpifdtd_setSourceForm(SOURCE_FORMS[source_form] if isinstance(source_form, str) else source_form)
         self.L.mpifdtd_setPrecision(PRECISIONS[precision] if isinstance(precision, str) else precision)
+        self.angle_batch = list(angle_batch) if angle_batch else []
+        if self.angle_batch:      # all these incidence angles at once, one batched engine
+            arr = (C.c_int * len(self.angle_batch))(*self.angle_batch)
+            self.L.mpifdtd_setAngleBatch(arr, len(self.angle_batch))
+        else:
+            self.L.mpifdtd_setAngleBatch(None, 0)
         self.L.models_setModel(self.model)
         self.L.simulator_setSolver(self.solver)
         self.L.simulator_init(self.info)
@@ -264,6 +277,14 @@ class Plugin:
         if self.solver in (2, 3, 4, 5):
             return self.L.mpifdtd_upml_engine(self.solver)
         return self.L.mpifdtd_split_engine(self.solver)
+
+    def select_angle(self, index):
+        """Which simulation of an angle batch the getters refer to."""
+        self.L.mpifdtd_selectAngle(index)
+
+    def far_field_file(self, angle_deg, workdir="."):
+        fn = os.path.join(workdir, "%d[deg]_380nm_700nm_b.dat" % angle_deg)
+        return np.fromfile(fn, dtype=np.float64).reshape(321, 360)
 
     def step(self, n=1):
         for _ in range(n):

@@ -759,6 +759,19 @@ int b200fdtd_device_bytes(b200fdtd_engine *e, uint64_t *bytes)
   return B200FDTD_OK;
 }
 
+int b200fdtd_mem_info(int32_t device, uint64_t *free_bytes, uint64_t *total_bytes)
+{
+  if (!free_bytes || !total_bytes) return b200_fail(B200FDTD_ERR_ARG, "NULL argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return b200_fail(B200FDTD_ERR_NODEVICE, "no CUDA device: the FDTD engine has no CPU path");
+  if (device >= 0) B200_CUDA(cudaSetDevice(device));
+  size_t f = 0, t = 0;
+  B200_CUDA(cudaMemGetInfo(&f, &t));
+  *free_bytes = f; *total_bytes = t;
+  return B200FDTD_OK;
+}
+
 int b200fdtd_timer_start(b200fdtd_engine *e)
 {
   if (!e) return b200_fail(B200FDTD_ERR_ARG, "NULL engine");

@@ -32,6 +32,8 @@
 
 #define N_ANGLES 360
 
+#define MPIFDTD_MAX_ANGLE_BATCH 4096
+
 typedef struct UpmlSolver {
   int kind;                       /* B200FDTD_TM_UPML or B200FDTD_TE_UPML          */
   b200fdtd_engine *engine;
@@ -61,9 +63,10 @@ static int is_tm_kind(int kind)  { return kind == B200FDTD_TM_UPML || kind == B2
 static int point_source_requested;
 static int source_form_requested;      /* MPIFDTD_SRC_* */
 static int precision_requested;        /* B200FDTD_F64 / B200FDTD_F32 */
-#define MPIFDTD_MAX_ANGLE_BATCH 4096
 static int batch_requested;            /* number of angles of the next init(), 0 = unbatched */
 static int batch_angles_requested[MPIFDTD_MAX_ANGLE_BATCH];
+
+static void fill_batch_source(int kind, double angle_deg, b200fdtd_batch_source *b);
 
 static void die_on(int rc, const char *what)
 {

@@ -19,6 +19,11 @@ def rel_err(a, b):
 
 
 def bit_equal(a, b):
+    """Same shape and the same bit patterns (complex arrays: both components)."""
+    a, b = np.asarray(a), np.asarray(b)
+    if np.iscomplexobj(a) or np.iscomplexobj(b):
+        a = np.ascontiguousarray(a, dtype=np.complex128).view(np.float64)
+        b = np.ascontiguousarray(b, dtype=np.complex128).view(np.float64)
     a = np.ascontiguousarray(a, dtype=np.float64)
     b = np.ascontiguousarray(b, dtype=np.float64)
     return a.shape == b.shape and np.array_equal(a.view(np.uint64), b.view(np.uint64))

@@ -1,0 +1,119 @@
+"""Angle sweeps as one batched GPU job (replaces the one-angle-per-rank loop
+of main.c:114-138,183-211).  A batched engine runs the same kernels with the same arithmetic
+on every simulation, so each angle of a batch must be BIT-IDENTICAL to the unbatched run at
+that angle -- fields and far-field files alike -- which in turn is pinned to the reference by
+tests/test_gpu_parity.py."""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import TOL_FARFIELD, TOL_FIELD, bit_equal, rel_err
+from mpifdtd_b200 import binding as B
+
+pytestmark = pytest.mark.gpu
+FIELDS = {2: ("Ez", "Hx", "Hy", "Jz", "Bx"), 3: ("Ex", "Ey", "Hz", "Dy", "Mz")}
+
+
+@pytest.fixture(autouse=True)
+def _unbatched_afterwards(in_tmp_cwd):
+    yield
+    B.lib().mpifdtd_setAngleBatch(None, 0)
+    B.lib().mpifdtd_setPrecision(0)
+
+
+@pytest.mark.parametrize("solver,model,precision", [(2, "MIE_CYLINDER", "f64"), (3, "MIE_CYLINDER", "f64"),
+                                                    (2, "ZIGZAG", "f64"), (3, "LAYER", "f32")])
+def test_batched_angles_equal_single_runs(plugin_lib, solver, model, precision):
+    npx, npy, steps, angles = 104, 120, 520, [0, 25, 90, 135]
+    singles = {}
+    for ang in angles:
+        gpu = B.Plugin(model, solver, npx, npy, steps=steps, h_u_nm=20, angle_deg=ang, precision=precision)
+        gpu.run()
+        fields = {f: gpu.field(f) for f in FIELDS[solver]}
+        singles[ang] = (fields, gpu.finish())
+    assert np.abs(singles[25][0][FIELDS[solver][0]]).max() > 1e-3
+    assert not np.array_equal(singles[0][1], singles[90][1])          # the angles really differ
+
+    batch = B.Plugin(model, solver, npx, npy, steps=steps, h_u_nm=20, angle_deg=angles[0], precision=precision,
+                     angle_batch=angles)
+    launches0 = batch.launches()
+    batch.run()
+    assert batch.launches() - launches0 <= 3 * steps                  # still H, E, sample per step
+    for k, ang in enumerate(angles):
+        batch.select_angle(k)
+        for f in FIELDS[solver]:
+            assert bit_equal(batch.field(f), singles[ang][0][f]), (ang, f)
+    batch.finish()
+    for ang in angles:
+        assert bit_equal(batch.far_field_file(ang), singles[ang][1]), ang
+        assert os.path.exists("%d[deg].txt" % ang)
+
+
+def test_batch_vs_oracle_directly(plugin_lib, oracle):
+    """One angle of a batch against the CPU oracle itself (not only against our own single run)."""
+    n, steps, angles = 96, 400, [10, 60]
+    batch = B.Plugin("MIE_CYLINDER", 2, n, steps=steps, h_u_nm=20, angle_batch=angles)
+    eps = batch.eps()
+    batch.run()
+    batch.select_angle(1)
+    cpu = oracle.OracleSim(oracle.TM, n, n, steps, eps, h_u_nm=20, angle_deg=60)
+    cpu.step(steps)
+    for f in ("Ez", "Hx", "Hy"):
+        assert rel_err(batch.field(f), cpu.field(f)) <= TOL_FIELD, f
+    batch.finish()
+    assert rel_err(batch.far_field_file(60), cpu.far_field()) <= TOL_FARFIELD
+
+
+def test_reset_of_a_batch_restarts_every_angle(plugin_lib):
+    n, steps, angles = 88, 200, [0, 45, 75]
+    batch = B.Plugin("MIE_CYLINDER", 2, n, steps=steps, h_u_nm=20, angle_batch=angles)
+    batch.run()
+    first = []
+    for k in range(len(angles)):
+        batch.select_angle(k)
+        first.append(batch.field("Ez"))
+    L = batch.L
+    L.simulator_reset()                    # writes every angle's files, zeroes every simulation
+    L.field_reset()
+    tables = [batch.far_field_file(a) for a in angles]
+    batch.select_angle(2)
+    assert np.all(batch.field("Ez") == 0)
+    batch.run()
+    for k in range(len(angles)):
+        batch.select_angle(k)
+        assert bit_equal(batch.field("Ez"), first[k]), k
+    batch.finish()
+    for a, t in zip(angles, tables):
+        assert bit_equal(batch.far_field_file(a), t), a
+
+
+def test_run_angle_sweep_chunks_and_names(plugin_lib):
+    """mpifdtd_runAngleSweep: 0..60 step 15 in chunks of at most 2 -> 3 batches, 5 simulations,
+    every angle's files present and equal to a plain single run."""
+    L = B.lib()
+    n, steps = 80, 160
+    L.models_setModel(B.MODELS["MIE_CYLINDER"])
+    L.simulator_setSolver(2)
+    info = B.FieldInfo(n * 20, n * 20, 20, 10, 500, 0, steps)
+    assert L.mpifdtd_runAngleSweep(info, 0, 60, 15, 2) == 5
+    swept = {a: np.fromfile("%d[deg]_380nm_700nm_b.dat" % a).reshape(321, 360) for a in range(0, 61, 15)}
+    os.makedirs("single", exist_ok=True)
+    os.chdir("single")
+    gpu = B.Plugin("MIE_CYLINDER", 2, n, steps=steps, h_u_nm=20, angle_deg=45)
+    gpu.run()
+    assert bit_equal(gpu.finish(), swept[45])
+
+
+def test_batch_rejected_where_not_built(plugin_lib):
+    import ctypes as C
+    h = C.c_void_p()
+    for kind, j0, nj in ((4, 0, 64), (0, 0, 64), (2, 0, 32)):          # MPI variant, split-field, slab
+        grid = B.Grid(kind, 64, 64, 10, j0, nj, 1, 62, 1, 62, -1, 0, B.MU_0_S, 4, 0)
+        assert plugin_lib.b200fdtd_create(C.byref(grid), C.byref(h)) == 1, kind
+    grid = B.Grid(2, 64, 64, 10, 0, 64, 1, 62, 1, 62, -1, 0, B.MU_0_S, 3, 0)
+    assert plugin_lib.b200fdtd_create(C.byref(grid), C.byref(h)) == 0
+    args = B.StepArgs()
+    assert plugin_lib.b200fdtd_step(h, C.byref(args)) == 4               # ERR_STATE: nothing uploaded yet
+    assert plugin_lib.b200fdtd_select_batch(h, 3) == 1
+    plugin_lib.b200fdtd_destroy(h)
