@@ -57,6 +57,7 @@ void free_ntff(b200fdtd_engine *e)
 {
   NtffState &n = e->ntff;
   cudaFree(n.pts); cudaFree(n.ts); cudaFree(n.hist_e); cudaFree(n.hist_h); cudaFree(n.uw);
+  cudaFree(n.sp_cos); cudaFree(n.sp_sin); cudaFree(n.sp_out); cudaFree(n.sp_tw);
   memset(&n, 0, sizeof n);
 }
 

@@ -37,6 +37,10 @@ struct NtffState {
   double2 *hist_e, *hist_h; // device [n_batch][n_local][max_time]
   double2 *uw;              // device [n_batch][3][n_angles][n_bins]
   int steps_recorded;
+  // device scratch of the spectrum step, kept between calls (a sweep calls it once per angle)
+  double *sp_cos, *sp_sin, *sp_out;
+  double2 *sp_tw;
+  int sp_n_fft, sp_n_lam;
 };
 
 struct FusedState {          // side buffers of the fused step (fused_kernels.cu)

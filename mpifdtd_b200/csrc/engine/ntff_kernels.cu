@@ -488,13 +488,18 @@ int b200_run_ntff_spectrum(b200fdtd_engine *e, const b200fdtd_spectrum_args *s, 
   const int n_lam = s->lambda_last_nm - s->lambda_first_nm + 1;
   if (n_lam <= 0) return b200_fail(B200FDTD_ERR_ARG, "empty wavelength range");
 
-  double *d_cos = nullptr, *d_sin = nullptr, *d_out = nullptr;
-  double2 *d_tw = nullptr;
   const size_t tw_count = (size_t)s->n_fft - 1;
-  B200_CUDA(cudaMalloc(&d_cos, sizeof(double) * n.n_angles));
-  B200_CUDA(cudaMalloc(&d_sin, sizeof(double) * n.n_angles));
-  B200_CUDA(cudaMalloc(&d_tw, sizeof(double2) * tw_count));
-  B200_CUDA(cudaMalloc(&d_out, sizeof(double) * (size_t)n_lam * n.n_angles));
+  if (n.sp_n_fft != s->n_fft || n.sp_n_lam != n_lam) {          // (re)allocate the scratch once
+    cudaFree(n.sp_cos); cudaFree(n.sp_sin); cudaFree(n.sp_out); cudaFree(n.sp_tw);
+    n.sp_cos = n.sp_sin = n.sp_out = nullptr; n.sp_tw = nullptr; n.sp_n_fft = 0;
+    B200_CUDA(cudaMalloc(&n.sp_cos, sizeof(double) * n.n_angles));
+    B200_CUDA(cudaMalloc(&n.sp_sin, sizeof(double) * n.n_angles));
+    B200_CUDA(cudaMalloc(&n.sp_tw, sizeof(double2) * tw_count));
+    B200_CUDA(cudaMalloc(&n.sp_out, sizeof(double) * (size_t)n_lam * n.n_angles));
+    n.sp_n_fft = s->n_fft; n.sp_n_lam = n_lam;
+  }
+  double *d_cos = n.sp_cos, *d_sin = n.sp_sin, *d_out = n.sp_out;
+  double2 *d_tw = n.sp_tw;
   B200_CUDA(cudaMemcpyAsync(d_cos, s->cos_phi, sizeof(double) * n.n_angles, cudaMemcpyHostToDevice, e->stream));
   B200_CUDA(cudaMemcpyAsync(d_sin, s->sin_phi, sizeof(double) * n.n_angles, cudaMemcpyHostToDevice, e->stream));
   B200_CUDA(cudaMemcpyAsync(d_tw, s->twiddle, sizeof(double2) * tw_count, cudaMemcpyHostToDevice, e->stream));
@@ -509,6 +514,5 @@ int b200_run_ntff_spectrum(b200fdtd_engine *e, const b200fdtd_spectrum_args *s, 
   B200_CUDA(cudaGetLastError());
   B200_CUDA(cudaMemcpyAsync(out, d_out, sizeof(double) * (size_t)n_lam * n.n_angles, cudaMemcpyDeviceToHost, e->stream));
   B200_CUDA(cudaStreamSynchronize(e->stream));
-  cudaFree(d_cos); cudaFree(d_sin); cudaFree(d_tw); cudaFree(d_out);
   return B200FDTD_OK;
 }

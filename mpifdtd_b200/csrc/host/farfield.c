@@ -194,14 +194,58 @@ int mpifdtd_ntffFrequency(int solver_id, double complex result[360])
  * text: one line per wavelength, "<nm> " then 360 values printed with "%lf.20 "
  * (upstream's format string: six decimals followed by the literal ".20");
  * binary: 321 rows of 360 float64, row = wavelength 380..700 nm. */
+/* The text twin is 321 x 360 printf conversions (~21 ms single-threaded), which is what an
+ * angle sweep on the GPU ends up waiting for; the rows are formatted by a few threads with the
+ * same conversion ("%lf.20 ") into private buffers and written out in order, so the file is
+ * byte-identical to the sequential fprintf loop. */
+#include <pthread.h>
+#include <string.h>
+typedef struct TxtJob { double **e_norm; int row0, row1; char *buf; size_t len; } TxtJob;
+
+static void *format_rows(void *arg)
+{
+  TxtJob *job = (TxtJob *)arg;
+  const size_t cap = (size_t)(job->row1 - job->row0) * (16 + 360 * 40) + 64;   /* "%lf.20 " of |x| < 1e21 is <= 34 chars */
+  char *p = job->buf = (char *)malloc(cap);
+  if (p == NULL) return NULL;
+  for (int row = job->row0; row < job->row1; row++) {
+    p += sprintf(p, "%d ", LAMBDA_ST_NM + row);
+    for (int ang = 0; ang < 360; ang++) {
+      const double v = job->e_norm[row][ang];
+      if (!(v > -1e21 && v < 1e21)) {            /* huge / inf / nan: keep the bounded path safe */
+        p += snprintf(p, 400, "%lf.20 ", v);
+        if ((size_t)(p - job->buf) + 512 > cap) break;
+        continue;
+      }
+      p += sprintf(p, "%lf.20 ", v);
+    }
+    *p++ = '\n';
+  }
+  job->len = (size_t)(p - job->buf);
+  return NULL;
+}
+
 void ntff_outputEnormTxt(double **e_norm, const char *file_name)
 {
   FILE *fp = FileOpen(file_name, "w");
-  for (int nm = LAMBDA_ST_NM; nm <= LAMBDA_EN_NM; nm++) {
-    fprintf(fp, "%d ", nm);
-    for (int ang = 0; ang < 360; ang++)
-      fprintf(fp, "%lf.20 ", e_norm[nm - LAMBDA_ST_NM][ang]);
-    fprintf(fp, "\n");
+  enum { N_THREADS = 8 };
+  const int rows = LAMBDA_EN_NM - LAMBDA_ST_NM + 1;
+  TxtJob jobs[N_THREADS];
+  pthread_t tid[N_THREADS];
+  int started[N_THREADS];
+  for (int t = 0; t < N_THREADS; t++) {
+    jobs[t].e_norm = e_norm;
+    jobs[t].row0 = rows * t / N_THREADS;
+    jobs[t].row1 = rows * (t + 1) / N_THREADS;
+    jobs[t].buf = NULL; jobs[t].len = 0;
+    started[t] = pthread_create(&tid[t], NULL, format_rows, &jobs[t]) == 0;
+    if (!started[t]) format_rows(&jobs[t]);        /* no thread to be had: format inline */
+  }
+  for (int t = 0; t < N_THREADS; t++) {
+    if (started[t]) pthread_join(tid[t], NULL);
+    if (jobs[t].buf == NULL) { printf("cannot allocate the text buffer for %s\n", file_name); exit(2); }
+    fwrite(jobs[t].buf, 1, jobs[t].len, fp);
+    free(jobs[t].buf);
   }
   fclose(fp);
 }

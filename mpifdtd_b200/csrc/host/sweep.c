@@ -45,6 +45,22 @@ int mpifdtd_runAngleSweep(FieldInfo field_info, int start_deg, int end_deg, int 
   if ((double)chunk > fit) chunk = (int)fit;
   if (chunk > 4096) chunk = 4096;
 
+  if (chunk == 1) {
+    /* one angle at a time, exactly the reference's loop (main.c:183-211): init once, then
+     * reset() -- far-field files + zeroed state -- and field_setWaveAngle() between angles */
+    mpifdtd_setAngleBatch(NULL, 0);
+    field_info.angle_deg = start_deg;
+    simulator_init(field_info);
+    for (int k = 0; k < total; k++) {
+      while (!simulator_isFinish()) simulator_calc();
+      if (k + 1 == total) break;
+      simulator_reset();
+      field_setWaveAngle(start_deg + (k + 1) * delta_deg);
+    }
+    simulator_finish();
+    return total;
+  }
+
   int *angles = (int *)malloc(sizeof(int) * (size_t)chunk);
   int done = 0;
   while (done < total) {

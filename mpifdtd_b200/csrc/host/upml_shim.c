@@ -38,7 +38,8 @@ typedef struct UpmlSolver {
   int kind;                       /* B200FDTD_TM_UPML or B200FDTD_TE_UPML          */
   b200fdtd_engine *engine;
   double *eps[3];                 /* host maps: TM EZ,HX,HY (HX/HY lazily) | TE EX,EY,HZ */
-  dcomplex *mirror[3];            /* pinned mirrors for the X, Y, Z getters        */
+  dcomplex *mirror[3];            /* pinned mirrors for the X, Y, Z getters (lazy)  */
+  size_t mirror_cells;
   int n_cell;
   int point_source;               /* opt-in, see mpifdtd_enablePointSource         */
   int source_form;                /* opt-in, see mpifdtd_setSourceForm             */
@@ -67,6 +68,22 @@ static int batch_requested;            /* number of angles of the next init(), 0
 static int batch_angles_requested[MPIFDTD_MAX_ANGLE_BATCH];
 
 static void fill_batch_source(int kind, double angle_deg, b200fdtd_batch_source *b);
+
+/* MPIFDTD_TIMING=1: where init() and the far-field output spend their wall time (stderr) */
+#include <time.h>
+static double now_s(void)
+{
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+static void lap(const char *what, double *t)
+{
+  if (getenv("MPIFDTD_TIMING") == NULL) return;
+  double n = now_s();
+  fprintf(stderr, "[timing] %-28s %8.3f ms\n", what, 1e3 * (n - *t));
+  *t = n;
+}
 
 static void die_on(int rc, const char *what)
 {
@@ -279,7 +296,9 @@ static void solver_init(UpmlSolver *s)
   grid.precision = precision_requested;
   grid.mu0 = MU_0_S;
   grid.n_batch = s->n_batch;
+  double t_lap = now_s();
   die_on(b200fdtd_create(&grid, &s->engine), "b200fdtd_create");
+  lap("init: engine create", &t_lap);
   if (s->n_batch > 1) {
     b200fdtd_batch_source *src = (b200fdtd_batch_source *)malloc(sizeof *src * (size_t)s->n_batch);
     for (int k = 0; k < s->n_batch; k++) fill_batch_source(s->kind, (double)s->batch_angles[k], &src[k]);
@@ -300,8 +319,10 @@ static void solver_init(UpmlSolver *s)
     mpifdtd_fill_eps(s->eps[0], 0.5, 0, D_Y);
     mpifdtd_fill_eps(s->eps[1], 0, 0.5, D_X);
   }
+  lap("init: eps maps (host)", &t_lap);
   for (int m = 0; m < n_eps; m++)
     die_on(b200fdtd_set_eps(s->engine, m, s->eps[m]), "b200fdtd_set_eps");
+  lap("init: eps upload", &t_lap);
 
   double *ti = (double *)malloc(sizeof(double) * B200FDTD_UPML_TABS * g.N_PX);
   double *tj = (double *)malloc(sizeof(double) * B200FDTD_UPML_TABS * g.N_PY);
@@ -309,8 +330,7 @@ static void solver_init(UpmlSolver *s)
   die_on(b200fdtd_set_upml_tables(s->engine, ti, tj), "b200fdtd_set_upml_tables");
   free(ti); free(tj);
 
-  for (int m = 0; m < 3; m++)
-    die_on(b200fdtd_host_alloc((void **)&s->mirror[m], sizeof(dcomplex) * sub_cells), "host_alloc(mirror)");
+  s->mirror_cells = sub_cells;          /* the pinned mirrors are allocated by the first getter call */
   if (mpi) {                                        /* EPS array as the getter shows it: with the ring */
     const int m = tm ? 0 : 1;                       /* TM: EPS_EZ, TE: EPS_EY (mpiTE_UPML.c:103-106) */
     s->eps_ringed = newDouble((int)sub_cells);
@@ -352,11 +372,14 @@ static void solver_init(UpmlSolver *s)
   plan.n_bins = getenv("MPIFDTD_NTFF_FULL_BINS") ? box.arraySize : plan.max_time;
   plan.n_angles = N_ANGLES;
   plan.array_size = box.arraySize;
+  lap("init: tables", &t_lap);
   double *shift = mpifdtd_ntff_time_shift(&box, N_ANGLES, tm ? 0.0 : 0.5, 0, g.N_PY);
   plan.time_shift = shift;
+  lap("init: ntff time shifts", &t_lap);
   if (plan.n_points > 0 && plan.max_time > 0)
     die_on(b200fdtd_set_ntff_plan(s->engine, &plan), "b200fdtd_set_ntff_plan");
   free(shift);
+  lap("init: ntff plan upload", &t_lap);
 }
 
 /* ---- update ------------------------------------------------------------------ */
@@ -499,8 +522,11 @@ void mpifdtd_upml_far_field(b200fdtd_engine *engine, int kind, int project, doub
   sa.lambda_first_nm = LAMBDA_ST_NM;  sa.lambda_last_nm = LAMBDA_EN_NM;
   sa.c_hu_nfft = C_0_S * phys.h_u_nm * NTFF_NUM;              /* ntffTM.c:227 */
   sa.twiddle = (const double *)tw;
-  if (project)
+  if (project) {
+    double t_lap = now_s();
     die_on(b200fdtd_ntff_project(engine), "b200fdtd_ntff_project");
+    if (getenv("MPIFDTD_TIMING")) { die_on(b200fdtd_sync(engine), "b200fdtd_sync"); lap("finish: ntff projection", &t_lap); }
+  }
   die_on(b200fdtd_ntff_spectrum(engine, &sa, table), "b200fdtd_ntff_spectrum");
   free(tw);
 }
@@ -518,17 +544,27 @@ static void write_far_field(UpmlSolver *s)
   /* an angle batch writes one pair of files per simulation, named by its own angle; the
    * projection kernel turns every simulation's history into U/W in one launch */
   const int n = s->n_batch > 1 ? s->n_batch : 1;
+  double t_lap = now_s(), t_gpu = 0, t_txt = 0, t_bin = 0;
+  die_on(b200fdtd_sync(s->engine), "b200fdtd_sync");
+  lap("finish: drain the stepping", &t_lap);
   for (int k = 0; k < n; k++) {
     const int angle = s->n_batch > 1 ? s->batch_angles[k] : (int)field_getWaveAngle();
     if (s->n_batch > 1) die_on(b200fdtd_select_batch(s->engine, k), "b200fdtd_select_batch");
+    double t0 = now_s();
     mpifdtd_upml_far_field(s->engine, s->kind, k == 0, table);
+    double t1 = now_s();
     sprintf(name, "%d[deg].txt", angle);
     ntff_outputEnormTxt(by_row, name);
     printf("saved %s/%s\n", cwd, name);
+    double t2 = now_s();
     sprintf(name, "%d[deg]_%dnm_%dnm_b.dat", angle, LAMBDA_ST_NM, LAMBDA_EN_NM);
     ntff_outputEnormBin(by_row, name);
     printf("saved %s/%s\n", cwd, name);
+    t_gpu += t1 - t0; t_txt += t2 - t1; t_bin += now_s() - t2;
   }
+  if (getenv("MPIFDTD_TIMING"))
+    fprintf(stderr, "[timing] finish: project+spectrum %.3f ms, .txt %.3f ms, .dat %.3f ms (%d simulation(s))\n",
+            1e3 * t_gpu, 1e3 * t_txt, 1e3 * t_bin, n);
   if (s->n_batch > 1) die_on(b200fdtd_select_batch(s->engine, 0), "b200fdtd_select_batch");
   free(by_row); free(table);
 }
@@ -653,6 +689,8 @@ static void solver_finish(UpmlSolver *s)
 static dcomplex *solver_field(UpmlSolver *s, int mirror, int slot)
 {
   if (s->engine == NULL) return NULL;                         /* upstream returns its NULL static */
+  if (s->mirror[mirror] == NULL)        /* pinned allocation is slow (~30 ms per 16 MB): only if somebody looks */
+    die_on(b200fdtd_host_alloc((void **)&s->mirror[mirror], sizeof(dcomplex) * s->mirror_cells), "host_alloc(mirror)");
   if (is_mpi_kind(s->kind)) {                                 /* (N+2) x (N+2) with a zero ring */
     FieldInfo_S g = field_getFieldInfo_S();
     double *first = (double *)(s->mirror[mirror] + (size_t)(g.N_PY + 2) + 1);

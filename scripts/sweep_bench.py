@@ -1,0 +1,57 @@
+#!/usr/bin/env python
+"""SURVEY 8f row 1 measured: an incidence-angle sweep of one structure (the production loop of
+main.c:114-211) run (a) one angle at a time, as the reference does, and (b) as one batched
+engine.  Wall clock around mpifdtd_runAngleSweep, i.e. including init, eps maps, the deferred
+NTFF projection, FFT and file output for every angle -- what a user of the sweep sees.
+
+  python scripts/sweep_bench.py [N ...]      -> one JSON line per grid size on stdout
+"""
+import json
+import os
+import sys
+import tempfile
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from mpifdtd_b200 import binding as B
+
+
+def sweep(n, steps, start, end, delta, max_batch, solver=2):
+    L = B.lib()
+    L.models_setModel(B.MODELS["MIE_CYLINDER"])
+    L.simulator_setSolver(solver)
+    info = B.FieldInfo(n * 10, n * 10, 10, 10, 500, start, steps)
+    cwd = os.getcwd()
+    os.chdir(tempfile.mkdtemp(prefix="sweep_"))
+    devnull = os.open(os.devnull, os.O_WRONLY)
+    saved = os.dup(1)
+    os.dup2(devnull, 1)                     # the plugin printf()s like the reference
+    try:
+        t0 = time.perf_counter()
+        count = L.mpifdtd_runAngleSweep(info, start, end, delta, max_batch)
+        dt = time.perf_counter() - t0
+    finally:
+        os.dup2(saved, 1)
+        os.chdir(cwd)
+    return count, dt
+
+
+def main():
+    sizes = [int(a) for a in sys.argv[1:]] or [256, 1024]
+    start, end, delta = 0, 180, 5
+    sweep(128, 50, 0, 10, 5, 0)             # warm-up: context, module load
+    for n in sizes:
+        steps = 2000 if n <= 512 else 1000
+        rows = {}
+        for label, max_batch in (("one_angle_at_a_time", 1), ("batched", 0)):
+            count, dt = sweep(n, steps, start, end, delta, max_batch)
+            rows[label] = {"seconds": dt, "simulations": count,
+                           "gcell_updates_per_s": count * n * n * steps / dt / 1e9}
+        print(json.dumps({"workload": "MieCylinder TM_UPML %dx%d, %d steps, angles %d..%d step %d, "
+                                      "far-field files for every angle" % (n, n, steps, start, end, delta),
+                          "speedup_batched": rows["one_angle_at_a_time"]["seconds"] / rows["batched"]["seconds"],
+                          **rows}))
+
+
+if __name__ == "__main__":
+    main()

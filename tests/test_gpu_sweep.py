@@ -97,6 +97,10 @@ def test_run_angle_sweep_chunks_and_names(plugin_lib):
     L.simulator_setSolver(2)
     info = B.FieldInfo(n * 20, n * 20, 20, 10, 500, 0, steps)
     assert L.mpifdtd_runAngleSweep(info, 0, 60, 15, 2) == 5
+    first = {a: np.fromfile("%d[deg]_380nm_700nm_b.dat" % a).reshape(321, 360) for a in range(0, 61, 15)}
+    assert L.mpifdtd_runAngleSweep(info, 0, 60, 15, 1) == 5          # the reference's own one-at-a-time loop
+    for a in first:
+        assert bit_equal(np.fromfile("%d[deg]_380nm_700nm_b.dat" % a).reshape(321, 360), first[a]), a
     swept = {a: np.fromfile("%d[deg]_380nm_700nm_b.dat" % a).reshape(321, 360) for a in range(0, 61, 15)}
     os.makedirs("single", exist_ok=True)
     os.chdir("single")
