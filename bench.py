@@ -160,13 +160,20 @@ def reference_arm(args):
     return 0
 
 
-def workload_config(n_gpus, sample_note=None, n=N_PER_GPU, solver="TM_UPML_2D", halo="peer"):
-    cfg = {"workload": "zigzagModel %s weak scaling, %d x %d cells per GPU, "
-                       "global %d x %d, y-slabs" % (solver, n, n, n, n * n_gpus),
-           "baseline_config": "BASELINE.json configs[4]",
+MODEL_NAMES = {"ZIGZAG": "zigzagModel", "LAYER": "multiLayerModel", "MORPHO_SCALE": "morphoScaleModel",
+               "MIE_CYLINDER": "MieCylinderModel", "NO_MODEL": "noModel"}
+
+
+def workload_config(n_gpus, sample_note=None, n=N_PER_GPU, solver="TM_UPML_2D", halo="peer", model="ZIGZAG",
+                    strong=False):
+    n_py = n if strong else n * n_gpus
+    per_gpu = n * n_py // n_gpus
+    cfg = {"workload": "%s %s %s scaling, %d x %d cells per GPU, global %d x %d, y-slabs"
+                       % (MODEL_NAMES[model], solver, "strong" if strong else "weak", n, n_py // n_gpus, n, n_py),
+           "baseline_config": ("BASELINE.json configs[2]" if strong else "BASELINE.json configs[4]"),
            "h_u_nm": 10, "pml": 10, "lambda_nm": 500, "angle_deg": 0,
-           "cells_per_gpu": n * n,
-           "l2_policy": "working set 38 GiB per GPU >> 126 MB L2, no flush needed",
+           "cells_per_gpu": per_gpu,
+           "l2_policy": "working set %.1f GiB per GPU >> 126 MB L2, no flush needed" % (per_gpu * 152.0 / 2**30),
            "parallelism": "y-slab x%d" % n_gpus}
     if n_gpus > 1:
         cfg["halo"] = halo
@@ -266,7 +273,7 @@ def gpu_arm(args):
             os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    n_px, n_py = args.n, args.n * world
+    n_px, n_py = args.n, (args.n if args.strong else args.n * world)
     K, W = args.steps, args.warmup
     total_steps = W + K
     stream = torch.cuda.Stream()
@@ -274,7 +281,7 @@ def gpu_arm(args):
     with torch.cuda.stream(stream):
         if world > 1:
             comm = TorchHaloComm(n_px, torch.device("cuda", local_rank))
-        run = SlabRun("ZIGZAG", args.solver, n_px, n_py, total_steps, rank=rank, world=world,
+        run = SlabRun(args.model, args.solver, n_px, n_py, total_steps, rank=rank, world=world,
                       device=local_rank, comm=comm, precision=args.precision)
         run.engine.set_stream(stream.cuda_stream)
         if comm is not None:
@@ -366,9 +373,9 @@ def gpu_arm(args):
         line = {
             "metric": "Gcell-updates/s", "value": value, "unit": "Gcell-updates/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_max / K,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None,
             "dtype": args.precision, "data": "synthetic",
-            "config": workload_config(world, n=args.n, solver=args.solver,
+            "config": workload_config(world, n=args.n, solver=args.solver, model=args.model, strong=args.strong,
                                       halo={"peer": "direct NVLink peer stores + device flags",
                                             "nccl": "NCCL send/recv"}[args.halo]),
             "roofline": {"bound": "hbm", "kernel": kname + "_upml_h_kernel<STORE_H=false>", "achieved": ach_h,
@@ -411,6 +418,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--halo", default="peer", choices=["peer", "nccl"],
                     help="multi-GPU halo transport: direct NVLink peer stores (default) or NCCL send/recv")
+    ap.add_argument("--model", default="ZIGZAG", choices=sorted(MODEL_NAMES),
+                    help="material model of the synthetic structure (ZIGZAG = BASELINE configs[4])")
+    ap.add_argument("--strong", action="store_true",
+                    help="fixed global grid n x n split over the GPUs (BASELINE configs[2]: --model LAYER "
+                         "--n 8192 --strong at 2/4 GPUs) instead of n x n per GPU")
     ap.add_argument("--precision", default="f64", choices=["f64", "f32"],
                     help="f64 is the reference's arithmetic and the BASELINE metric; f32 is the optional "
                          "single-precision path (own tolerance), reported for information only")
