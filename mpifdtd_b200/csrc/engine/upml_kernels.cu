@@ -23,6 +23,12 @@
 #ifndef B200_E_MIN_BLOCKS
 #define B200_E_MIN_BLOCKS 5   /* <= 51 registers: measured 23.4 -> 24.4 Gcell/s at 16384^2 */
 #endif
+#ifndef B200_TE_H_MIN_BLOCKS
+#define B200_TE_H_MIN_BLOCKS 1
+#endif
+#ifndef B200_TE_E_MIN_BLOCKS
+#define B200_TE_E_MIN_BLOCKS 1
+#endif
 
 namespace {
 
@@ -161,7 +167,7 @@ __global__ void __launch_bounds__(kBlock, B200_E_MIN_BLOCKS) tm_upml_e_kernel(co
 // ------------------------------------------------------------------ TE -----
 // slots: 0 Ex 1 Jx 2 Dx 3 Ey 4 Jy 5 Dy 6 Hz 7 Mz 8 Bz
 template <typename T, bool STORE_H>
-__global__ void __launch_bounds__(kBlock) te_upml_h_kernel(const UpmlViewT<T> v)
+__global__ void __launch_bounds__(kBlock, B200_TE_H_MIN_BLOCKS) te_upml_h_kernel(const UpmlViewT<T> v)
 {
   using C = typename Cx<T>::type;
   int r, c; size_t k, k0;
@@ -193,7 +199,7 @@ __global__ void __launch_bounds__(kBlock) te_upml_h_kernel(const UpmlViewT<T> v)
 }
 
 template <typename T, bool FROM_B>
-__global__ void __launch_bounds__(kBlock) te_upml_e_kernel(const UpmlViewT<T> v)
+__global__ void __launch_bounds__(kBlock, B200_TE_E_MIN_BLOCKS) te_upml_e_kernel(const UpmlViewT<T> v)
 {
   using C = typename Cx<T>::type;
   int r, c; size_t k, k0;
