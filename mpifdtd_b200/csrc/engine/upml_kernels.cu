@@ -27,7 +27,7 @@
 #define B200_TE_H_MIN_BLOCKS 1
 #endif
 #ifndef B200_TE_E_MIN_BLOCKS
-#define B200_TE_E_MIN_BLOCKS 1
+#define B200_TE_E_MIN_BLOCKS 4   /* measured 20.9 -> 22.7 Gcell/s at 16384^2 (1: 20.9, 5: 20.8, 6: 19.9) */
 #endif
 
 namespace {
