@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define B200FDTD_ABI_VERSION 4
+#define B200FDTD_ABI_VERSION 5
 
 enum {
   B200FDTD_OK = 0,
@@ -70,6 +70,30 @@ enum { B200FDTD_STE_C_EX = 0, B200FDTD_STE_C_EXLY, B200FDTD_STE_C_EY, B200FDTD_S
 #define B200FDTD_DENSE_SRC0 8
 #define B200FDTD_DENSE_SRC1 9
 #define B200FDTD_MAX_DENSE 10
+
+/* "Lean" form of the split-field kinds 0, 1 and 6 (b200fdtd_set_split_tables): most of the
+ * eight coefficients are separable after all.  Berenger (fdtdTM.c:197-242, fdtdTE.c:199-243):
+ * the H coefficients use MU_0_S and a sigma that depends on i only or j only -> 1-D tables; the
+ * E coefficients are field_pmlCoef(eps, sigma) / field_pmlCoef_LXY(eps, sigma) of the cell's
+ * eps and a 1-D sigma, which the kernel evaluates itself with the reference's operations
+ * (exactly 1 and 1/eps outside the PML, three IEEE divisions inside).  NS-FDTD TM
+ * (nsFdtdTM.c:231-307): the decay coefficients coef1(beta) are 1-D; the curl coefficients are
+ * (u*z)(eps) / (1 + beta(sigma)) -> one dense per-cell array G (host libm) divided by a 1-D
+ * table in the kernel.  Per cell-update this reads eps (8 B, kinds 0/1) or three G arrays +
+ * the source factor (32 B, kind 6) instead of nine dense doubles (72 B).  Bit-identical to the
+ * dense form.  NS-FDTD TE (kind 7) keeps the dense form: its beta depends on eps inside the PML
+ * (nsFdtdTE.c:130-137) through tanh, which only the host libm reproduces.
+ * tab_i[slot*n_px + i], tab_j[slot*n_py + j]: */
+enum { /* kind 0, by i */ B200FDTD_LTM_I_SIG_EZ_X = 0, B200FDTD_LTM_I_C_HY, B200FDTD_LTM_I_C_HYLX,
+       /* kind 0, by j */ B200FDTD_LTM_J_SIG_EZ_Y = 0, B200FDTD_LTM_J_C_HX, B200FDTD_LTM_J_C_HXLY };
+enum { /* kind 1, by i */ B200FDTD_LTE_I_SIG_EY_X = 0, B200FDTD_LTE_I_C_HZX, B200FDTD_LTE_I_C_HZXLX,
+       /* kind 1, by j */ B200FDTD_LTE_J_SIG_EX_Y = 0, B200FDTD_LTE_J_C_HZY, B200FDTD_LTE_J_C_HZYLY };
+enum { /* kind 6, by i */ B200FDTD_LNS_I_C_EZX = 0, B200FDTD_LNS_I_DEN_EZ /* 1 + b_ez_x */, B200FDTD_LNS_I_C_HY,
+       B200FDTD_LNS_I_DEN_HY /* 1 + b_hy_x */,
+       /* kind 6, by j */ B200FDTD_LNS_J_C_EZY = 0, B200FDTD_LNS_J_C_HX, B200FDTD_LNS_J_DEN_HX /* 1 + b_hx_y */ };
+/* kind 6 lean: dense slots C_EZXLX, C_HXLY, C_HYLX hold G_EZ = u_ez*z_ez, G_HX = u_hx/z_hx,
+ * G_HY = u_hy/z_hy; slot 8 the source factor; the other dense slots are not uploaded */
+#define B200FDTD_SPLIT_TABS 4
 
 /* 1-D coefficient tables of the UPML kinds.  The reference stores 15 dense
  * N_CELL arrays per solver (fdtdTM_upml.c:30-35); because every one of them is
@@ -253,6 +277,9 @@ int b200fdtd_set_batch_sources(b200fdtd_engine *e, const b200fdtd_batch_source *
  * (get/set_field*, ntff_get_uw, ntff_spectrum, ntff_frequency); default 0 */
 int b200fdtd_select_batch(b200fdtd_engine *e, int32_t index);
 
+/* lean form of the split-field kinds 0, 1, 6 (see B200FDTD_LTM_* above); eps through
+ * b200fdtd_set_eps (kind 0: slot 0 = EPS_EZ; kind 1: slot 0 = EPS_EX, 1 = EPS_EY) */
+int b200fdtd_set_split_tables(b200fdtd_engine *e, const double *tab_i, const double *tab_j);
 /* dense per-cell array of a split-field kind: host [n_px][n_py] map (B200FDTD_ST?_C_* or
  * B200FDTD_DENSE_SRC?); replaces the coefficient loops of fdtdTM.c:197-242,
  * nsFdtdTM.c:231-307 etc. */

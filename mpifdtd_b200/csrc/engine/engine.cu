@@ -182,8 +182,10 @@ int b200fdtd_create(const b200fdtd_grid *grid, b200fdtd_engine **out)
   for (int s = 0; s < e->n_fields && !rc; s++)
     rc = dev_alloc_zero(e, (void **)&e->field[s], e->plane * e->csize * (size_t)n_batch);
   if (kind_is_split(grid->kind)) {
-    for (int s = 0; s < B200FDTD_MAX_DENSE && !rc; s++)
-      rc = dev_alloc_zero(e, (void **)&e->dense[s], e->plane * sizeof(double));
+    // dense coefficient arrays and eps maps are allocated by the first set_dense / set_eps
+    // call for their slot: the lean form needs only a few of them
+    rc = dev_alloc_zero(e, (void **)&e->tab_i, sizeof(double) * B200FDTD_SPLIT_TABS * e->rows);
+    if (!rc) rc = dev_alloc_zero(e, (void **)&e->tab_j, sizeof(double) * B200FDTD_SPLIT_TABS * e->pitch);
   } else {
     const int n_eps = (grid->kind == B200FDTD_TM_UPML || grid->kind == B200FDTD_MPI_TM_UPML) ? 1 : 2;
     for (int s = 0; s < n_eps && !rc; s++)
@@ -335,6 +337,28 @@ int b200fdtd_set_upml_tables(b200fdtd_engine *e, const double *tab_i, const doub
   return B200FDTD_OK;
 }
 
+int b200fdtd_set_split_tables(b200fdtd_engine *e, const double *tab_i, const double *tab_j)
+{
+  if (!e || !tab_i || !tab_j) return b200_fail(B200FDTD_ERR_ARG, "NULL argument");
+  if (e->g.kind != B200FDTD_TM && e->g.kind != B200FDTD_TE && e->g.kind != B200FDTD_NS_TM)
+    return b200_fail(B200FDTD_ERR_ARG, "the lean split-field form serves kinds 0, 1 and 6");
+  int rc = select_device(e); if (rc) return rc;
+  const b200fdtd_grid &g = e->g;
+  std::vector<double> hi((size_t)B200FDTD_SPLIT_TABS * e->rows, 1.0);
+  std::vector<double> hj((size_t)B200FDTD_SPLIT_TABS * e->pitch, 1.0);
+  for (int s = 0; s < B200FDTD_SPLIT_TABS; s++) {
+    for (int i = 0; i < g.n_px; i++) hi[(size_t)s * e->rows + i + 1] = tab_i[(size_t)s * g.n_px + i];
+    for (int c = 0; c < g.nj; c++)
+      hj[(size_t)s * e->pitch + B200_JOFF + c] = tab_j[(size_t)s * g.n_py + g.j0 + c];
+  }
+  B200_CUDA(cudaMemcpyAsync(e->tab_i, hi.data(), hi.size() * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+  B200_CUDA(cudaMemcpyAsync(e->tab_j, hj.data(), hj.size() * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+  B200_CUDA(cudaStreamSynchronize(e->stream));
+  e->have_tabs = true;
+  e->split_lean = true;
+  return B200FDTD_OK;
+}
+
 static int upload_eps(b200fdtd_engine *e, int32_t slot, const double *host_eps, size_t ld);
 
 int b200fdtd_set_eps(b200fdtd_engine *e, int32_t slot, const double *host_eps)
@@ -352,9 +376,10 @@ int b200fdtd_set_eps_slab(b200fdtd_engine *e, int32_t slot, const double *slab_e
 // src points at (i = 0, first owned column); ld = host row stride in doubles
 static int upload_eps(b200fdtd_engine *e, int32_t slot, const double *src, size_t ld)
 {
-  if (slot < 0 || slot > 1 || !e->eps[slot])
+  if (slot < 0 || slot > 1 || (!e->eps[slot] && !kind_is_split(e->g.kind)))
     return b200_fail(B200FDTD_ERR_ARG, "bad eps slot %d", slot);
   int rc = select_device(e); if (rc) return rc;
+  if (!e->eps[slot]) { rc = dev_alloc_zero(e, (void **)&e->eps[slot], e->plane * e->rsize); if (rc) return rc; }
   const b200fdtd_grid &g = e->g;
   if (e->fp32) {                        // stage the double map on the device, round once to float
     double *stage = nullptr;
@@ -387,9 +412,10 @@ static int upload_eps(b200fdtd_engine *e, int32_t slot, const double *src, size_
 
 int b200fdtd_set_dense(b200fdtd_engine *e, int32_t slot, const double *host_map)
 {
-  if (!e || !host_map || slot < 0 || slot >= B200FDTD_MAX_DENSE || !e->dense[slot])
+  if (!e || !host_map || slot < 0 || slot >= B200FDTD_MAX_DENSE || !kind_is_split(e->g.kind))
     return b200_fail(B200FDTD_ERR_ARG, "bad dense slot %d for kind %d", slot, e ? e->g.kind : -1);
   int rc = select_device(e); if (rc) return rc;
+  if (!e->dense[slot]) { rc = dev_alloc_zero(e, (void **)&e->dense[slot], e->plane * sizeof(double)); if (rc) return rc; }
   const b200fdtd_grid &g = e->g;
   B200_CUDA(cudaMemcpy2DAsync(e->dense[slot] + (size_t)e->pitch + B200_JOFF, sizeof(double) * e->pitch,
                               host_map + g.j0, sizeof(double) * g.n_py, sizeof(double) * g.nj, g.n_px,
@@ -489,9 +515,23 @@ static int check_ready(b200fdtd_engine *e, const b200fdtd_step_args *a)
 {
   if (!e || !a) return b200_fail(B200FDTD_ERR_ARG, "NULL argument");
   if (kind_is_split(e->g.kind)) {
+    if (e->split_lean) {            // 1-D tables + eps (kinds 0, 1) or G arrays + source factor (kind 6)
+      const int k = e->g.kind;
+      if (k == B200FDTD_NS_TM) {
+        const int need[4] = { B200FDTD_STM_C_EZXLX, B200FDTD_STM_C_HXLY, B200FDTD_STM_C_HYLX, B200FDTD_DENSE_SRC0 };
+        for (int s = 0; s < 4; s++)
+          if (!e->have_dense[need[s]]) return b200_fail(B200FDTD_ERR_STATE, "step before set_dense(%d)", need[s]);
+      } else if (!e->have_eps[0] || (k == B200FDTD_TE && !e->have_eps[1])) {
+        return b200_fail(B200FDTD_ERR_STATE, "step before set_eps");
+      }
+      return select_device(e);
+    }
     for (int s = 0; s < 8; s++)
       if (!e->have_dense[s]) return b200_fail(B200FDTD_ERR_STATE, "step before set_dense(%d)", s);
-    return select_device(e);
+    int rc = select_device(e);
+    for (int s = B200FDTD_DENSE_SRC0; s <= B200FDTD_DENSE_SRC1 && !rc; s++)     // no source factor uploaded: zeros
+      if (!e->dense[s]) rc = dev_alloc_zero(e, (void **)&e->dense[s], e->plane * sizeof(double));
+    return rc;
   }
   if (!e->have_tabs) return b200_fail(B200FDTD_ERR_STATE, "step before set_upml_tables");
   if (!e->have_eps[0] || (e->eps[1] && !e->have_eps[1]))

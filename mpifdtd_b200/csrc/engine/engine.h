@@ -84,6 +84,7 @@ struct b200fdtd_engine {
   double *tab_i;            // device [B200FDTD_UPML_TABS][rows], indexed by row = i + 1
   double *tab_j;            // device [B200FDTD_UPML_TABS][pitch], indexed by in-row offset
   bool have_tabs, have_eps[2];
+  bool split_lean;          // split-field kinds 0/1/6: 1-D tables + eps / G arrays instead of 8 dense arrays
   NtffState ntff;
   FusedState fused;
   PeerState peer;

@@ -20,6 +20,9 @@ using namespace upml;
 struct SplitView {
   double2 *f[5];
   const double *c[B200FDTD_MAX_DENSE];
+  const double *eps0, *eps1;            // lean form, kinds 0 / 1
+  const double *ti, *tj;                // lean form: 1-D tables [B200FDTD_SPLIT_TABS][rows | pitch]
+  int rows;
   int pitch;
   int r_lo, c_lo, c_hi, nbx;
   int j_base;
@@ -56,9 +59,34 @@ __device__ __forceinline__ double2 cw_term(const b200fdtd_cw &s, int i, int j, d
 
 __device__ __forceinline__ double2 twice(double2 z) { return make_double2(2 * z.x, 2 * z.y); }
 
+// ---- lean form: coefficients evaluated in the kernel with the reference's operations -------
+// field_pmlCoef(eps, sig) = (1.0 - sig/eps)/(1.0 + sig/eps) and field_pmlCoef_LXY(eps, sig) =
+// 1.0/(eps + sig) (field.c:288-295).  Outside the PML sig == 0 and they are exactly 1.0 and
+// 1.0/eps (inv_eps, shared by both directions and by the source factor eps0/eps - 1); inside,
+// three IEEE divisions -- rows (sig_x) are block-uniform, columns (sig_y) diverge only at the
+// row ends.
+struct PmlPair { double c, l; };
+__device__ __forceinline__ PmlPair pml_pair(double eps, double sig, double inv_eps)
+{
+  PmlPair p;
+  p.c = 1.0;
+  p.l = inv_eps;
+  if (sig != 0.0) {
+    const double q = ieee_div(sig, eps);
+    p.c = ieee_div(1.0 - q, 1.0 + q);
+    p.l = ieee_div(1.0, eps + sig);
+  }
+  return p;
+}
+__device__ __forceinline__ double one_over(double eps) { return eps == 1.0 ? 1.0 : ieee_div(1.0, eps); }
+// g / den where den == 1.0 outside the PML (NS-FDTD: (u*z) / (1 + beta), nsFdtdTM.c:285-305)
+__device__ __forceinline__ double over_den(double g, double den) { return den == 1.0 ? g : ieee_div(g, den); }
+
 // ---------------------------------------------------------------- TM family ------
 // slots: 0 Ez 1 Ezx 2 Ezy 3 Hx 4 Hy
-template <bool NS>
+// LEAN: see b200fdtd.h "lean form".  Kind 0 (Berenger): the four H coefficients are 1-D tables.
+// Kind 6 (NS): decay coefficients 1-D, curl coefficients G[k] / DEN (1-D).
+template <bool NS, bool LEAN>
 __global__ void __launch_bounds__(kBlock) split_tm_h_kernel(const SplitView v)
 {
   int r, c; size_t k;
@@ -80,23 +108,51 @@ __global__ void __launch_bounds__(kBlock) split_tm_h_kernel(const SplitView v)
     dy_term = ((Ezx[k + 1] - zx) + Ezy[k + 1]) - zy;
     dx_term = ((Ezx[k + P] - zx) + Ezy[k + P]) - zy;
   }
-  v.f[B200FDTD_STM_HX][k] = v.c[B200FDTD_STM_C_HX][k] * v.f[B200FDTD_STM_HX][k] - v.c[B200FDTD_STM_C_HXLY][k] * dy_term;
-  v.f[B200FDTD_STM_HY][k] = v.c[B200FDTD_STM_C_HY][k] * v.f[B200FDTD_STM_HY][k] + v.c[B200FDTD_STM_C_HYLX][k] * dx_term;
+  double c_hx, c_hxly, c_hy, c_hylx;
+  if (!LEAN) {
+    c_hx = v.c[B200FDTD_STM_C_HX][k];  c_hxly = v.c[B200FDTD_STM_C_HXLY][k];
+    c_hy = v.c[B200FDTD_STM_C_HY][k];  c_hylx = v.c[B200FDTD_STM_C_HYLX][k];
+  } else if (NS) {
+    c_hx = v.tj[B200FDTD_LNS_J_C_HX * v.pitch + c];
+    c_hy = v.ti[B200FDTD_LNS_I_C_HY * v.rows + r];
+    c_hxly = over_den(v.c[B200FDTD_STM_C_HXLY][k], v.tj[B200FDTD_LNS_J_DEN_HX * v.pitch + c]);
+    c_hylx = over_den(v.c[B200FDTD_STM_C_HYLX][k], v.ti[B200FDTD_LNS_I_DEN_HY * v.rows + r]);
+  } else {
+    c_hx = v.tj[B200FDTD_LTM_J_C_HX * v.pitch + c];  c_hxly = v.tj[B200FDTD_LTM_J_C_HXLY * v.pitch + c];
+    c_hy = v.ti[B200FDTD_LTM_I_C_HY * v.rows + r];   c_hylx = v.ti[B200FDTD_LTM_I_C_HYLX * v.rows + r];
+  }
+  v.f[B200FDTD_STM_HX][k] = c_hx * v.f[B200FDTD_STM_HX][k] - c_hxly * dy_term;
+  v.f[B200FDTD_STM_HY][k] = c_hy * v.f[B200FDTD_STM_HY][k] + c_hylx * dx_term;
 }
 
-template <bool NS>
+template <bool NS, bool LEAN>
 __global__ void __launch_bounds__(kBlock) split_tm_e_kernel(const SplitView v)
 {
   int r, c; size_t k;
   if (!locate(v, r, c, k)) return;
   const double2 *__restrict__ Hx = v.f[B200FDTD_STM_HX];
   const double2 *__restrict__ Hy = v.f[B200FDTD_STM_HY];
+  double c_ezx, c_ezxlx, c_ezy, c_ezyly, factor;
+  if (!LEAN) {
+    c_ezx = v.c[B200FDTD_STM_C_EZX][k];  c_ezxlx = v.c[B200FDTD_STM_C_EZXLX][k];
+    c_ezy = v.c[B200FDTD_STM_C_EZY][k];  c_ezyly = v.c[B200FDTD_STM_C_EZYLY][k];
+    factor = v.c[B200FDTD_DENSE_SRC0][k];
+  } else if (NS) {        // nsFdtdTM.c:283-287: both curl coefficients are (u*z)/(1 + b_ez_x)
+    c_ezx = v.ti[B200FDTD_LNS_I_C_EZX * v.rows + r];
+    c_ezy = v.tj[B200FDTD_LNS_J_C_EZY * v.pitch + c];
+    c_ezxlx = c_ezyly = over_den(v.c[B200FDTD_STM_C_EZXLX][k], v.ti[B200FDTD_LNS_I_DEN_EZ * v.rows + r]);
+    factor = v.c[B200FDTD_DENSE_SRC0][k];
+  } else {                // fdtdTM.c:230-234 evaluated here from eps and the 1-D sigmas
+    const double eps = v.eps0[k];
+    const double inv_eps = one_over(eps);
+    const PmlPair px = pml_pair(eps, v.ti[B200FDTD_LTM_I_SIG_EZ_X * v.rows + r], inv_eps);
+    const PmlPair py = pml_pair(eps, v.tj[B200FDTD_LTM_J_SIG_EZ_Y * v.pitch + c], inv_eps);
+    c_ezx = px.c;  c_ezxlx = px.l;  c_ezy = py.c;  c_ezyly = py.l;
+    factor = inv_eps - 1.0;                        // EPSILON_0_S / eps - 1.0 (field.c:193)
+  }
   // fdtdTM.c:302-308 / nsFdtdTM.c:95-108
-  double2 ezx = v.c[B200FDTD_STM_C_EZX][k] * v.f[B200FDTD_STM_EZX][k]
-              + v.c[B200FDTD_STM_C_EZXLX][k] * (Hy[k] - Hy[k - v.pitch]);
-  double2 ezy = v.c[B200FDTD_STM_C_EZY][k] * v.f[B200FDTD_STM_EZY][k]
-              - v.c[B200FDTD_STM_C_EZYLY][k] * (Hx[k] - Hx[k - 1]);
-  const double factor = v.c[B200FDTD_DENSE_SRC0][k];
+  double2 ezx = c_ezx * v.f[B200FDTD_STM_EZX][k] + c_ezxlx * (Hy[k] - Hy[k - v.pitch]);
+  double2 ezy = c_ezy * v.f[B200FDTD_STM_EZY][k] - c_ezyly * (Hx[k] - Hx[k - 1]);
   double2 ez;
   if (NS) {          // source on Ezy, then Ez = Ezx + Ezy (nsFdtdTM.c:73-79)
     if (v.cw[0].enabled && factor != 0.0) ezy = ezy + cw_term(v.cw[0], r - 1, v.j_base + c, factor);
@@ -112,7 +168,7 @@ __global__ void __launch_bounds__(kBlock) split_tm_e_kernel(const SplitView v)
 
 // ---------------------------------------------------------------- TE family ------
 // slots: 0 Hz 1 Hzx 2 Hzy 3 Ex 4 Ey
-template <bool NS>
+template <bool NS, bool LEAN>          // LEAN: kind 1 only (NS TE keeps its dense arrays)
 __global__ void __launch_bounds__(kBlock) split_te_e_kernel(const SplitView v)
 {
   int r, c; size_t k;
@@ -134,27 +190,46 @@ __global__ void __launch_bounds__(kBlock) split_te_e_kernel(const SplitView v)
     dy_term = ((zx - Hzx[k - 1]) + zy) - Hzy[k - 1];
     dx_term = ((zx - Hzx[k - P]) + zy) - Hzy[k - P];
   }
-  double2 ex = v.c[B200FDTD_STE_C_EX][k] * v.f[B200FDTD_STE_EX][k] + v.c[B200FDTD_STE_C_EXLY][k] * dy_term;
-  double2 ey = v.c[B200FDTD_STE_C_EY][k] * v.f[B200FDTD_STE_EY][k] - v.c[B200FDTD_STE_C_EYLX][k] * dx_term;
+  double c_ex, c_exly, c_ey, c_eylx, fx, fy;
+  if (!LEAN) {
+    c_ex = v.c[B200FDTD_STE_C_EX][k];  c_exly = v.c[B200FDTD_STE_C_EXLY][k];
+    c_ey = v.c[B200FDTD_STE_C_EY][k];  c_eylx = v.c[B200FDTD_STE_C_EYLX][k];
+    fx = v.c[B200FDTD_DENSE_SRC0][k];  fy = v.c[B200FDTD_DENSE_SRC1][k];
+  } else {                // fdtdTE.c:229-233 evaluated here; the source acts on Ey only (fdtdTE.c:285)
+    const double eps_x = v.eps0[k], eps_y = v.eps1[k];
+    const double inv_y = one_over(eps_y);
+    const PmlPair px = pml_pair(eps_x, v.tj[B200FDTD_LTE_J_SIG_EX_Y * v.pitch + c], one_over(eps_x));
+    const PmlPair py = pml_pair(eps_y, v.ti[B200FDTD_LTE_I_SIG_EY_X * v.rows + r], inv_y);
+    c_ex = px.c;  c_exly = px.l;  c_ey = py.c;  c_eylx = py.l;
+    fx = 0.0;  fy = inv_y - 1.0;
+  }
+  double2 ex = c_ex * v.f[B200FDTD_STE_EX][k] + c_exly * dy_term;
+  double2 ey = c_ey * v.f[B200FDTD_STE_EY][k] - c_eylx * dx_term;
   const int i = r - 1, j = v.j_base + c;
-  const double fx = v.c[B200FDTD_DENSE_SRC0][k], fy = v.c[B200FDTD_DENSE_SRC1][k];
   if (v.cw[0].enabled && fx != 0.0) ex = ex + cw_term(v.cw[0], i, j, fx);     // nsFdtdTE.c:247-248
   if (v.cw[1].enabled && fy != 0.0) ey = ey + cw_term(v.cw[1], i, j, fy);     // fdtdTE.c:285, nsFdtdTE.c:249-250
   v.f[B200FDTD_STE_EX][k] = ex;
   v.f[B200FDTD_STE_EY][k] = ey;
 }
 
+template <bool LEAN>
 __global__ void __launch_bounds__(kBlock) split_te_h_kernel(const SplitView v)
 {
   int r, c; size_t k;
   if (!locate(v, r, c, k)) return;
   const double2 *__restrict__ Ex = v.f[B200FDTD_STE_EX];
   const double2 *__restrict__ Ey = v.f[B200FDTD_STE_EY];
+  double c_hzx, c_hzxlx, c_hzy, c_hzyly;
+  if (!LEAN) {
+    c_hzx = v.c[B200FDTD_STE_C_HZX][k];  c_hzxlx = v.c[B200FDTD_STE_C_HZXLX][k];
+    c_hzy = v.c[B200FDTD_STE_C_HZY][k];  c_hzyly = v.c[B200FDTD_STE_C_HZYLY][k];
+  } else {                // fdtdTE.c:236-240: MU_0_S and a 1-D sigma each
+    c_hzx = v.ti[B200FDTD_LTE_I_C_HZX * v.rows + r];   c_hzxlx = v.ti[B200FDTD_LTE_I_C_HZXLX * v.rows + r];
+    c_hzy = v.tj[B200FDTD_LTE_J_C_HZY * v.pitch + c];  c_hzyly = v.tj[B200FDTD_LTE_J_C_HZYLY * v.pitch + c];
+  }
   // fdtdTE.c:308-320 / nsFdtdTE.c:293-307,237-240
-  const double2 hzx = v.c[B200FDTD_STE_C_HZX][k] * v.f[B200FDTD_STE_HZX][k]
-                    - v.c[B200FDTD_STE_C_HZXLX][k] * (Ey[k + v.pitch] - Ey[k]);
-  const double2 hzy = v.c[B200FDTD_STE_C_HZY][k] * v.f[B200FDTD_STE_HZY][k]
-                    + v.c[B200FDTD_STE_C_HZYLY][k] * (Ex[k + 1] - Ex[k]);
+  const double2 hzx = c_hzx * v.f[B200FDTD_STE_HZX][k] - c_hzxlx * (Ey[k + v.pitch] - Ey[k]);
+  const double2 hzy = c_hzy * v.f[B200FDTD_STE_HZY][k] + c_hzyly * (Ex[k + 1] - Ex[k]);
   v.f[B200FDTD_STE_HZX][k] = hzx;
   v.f[B200FDTD_STE_HZY][k] = hzy;
   v.f[B200FDTD_STE_HZ][k] = hzx + hzy;
@@ -174,24 +249,28 @@ int b200_launch_split_step(b200fdtd_engine *e, const b200fdtd_step_args *a)
   v.j_base = e->g.j0 - B200_JOFF;
   v.cw[0] = a->cw[0]; v.cw[1] = a->cw[1];
   v.ns_r2 = a->ns_r2;
+  v.eps0 = e->eps[0]; v.eps1 = e->eps[1];
+  v.ti = e->tab_i; v.tj = e->tab_j;
+  v.rows = e->rows;
   const unsigned nblk = (unsigned)((long long)v.nbx * (e->r_hi - e->r_lo + 1));
   cudaStream_t st = e->stream;
+  const bool lean = e->split_lean;
   switch (e->g.kind) {
   case B200FDTD_TM:        // fdtdTM.c:290-297: calcH, calcE, source
-    split_tm_h_kernel<false><<<nblk, kBlock, 0, st>>>(v);
-    split_tm_e_kernel<false><<<nblk, kBlock, 0, st>>>(v);
+    if (lean) { split_tm_h_kernel<false, true><<<nblk, kBlock, 0, st>>>(v);  split_tm_e_kernel<false, true><<<nblk, kBlock, 0, st>>>(v); }
+    else      { split_tm_h_kernel<false, false><<<nblk, kBlock, 0, st>>>(v); split_tm_e_kernel<false, false><<<nblk, kBlock, 0, st>>>(v); }
     break;
   case B200FDTD_TE:        // fdtdTE.c:283-287: calcE, source, calcH
-    split_te_e_kernel<false><<<nblk, kBlock, 0, st>>>(v);
-    split_te_h_kernel<<<nblk, kBlock, 0, st>>>(v);
+    if (lean) { split_te_e_kernel<false, true><<<nblk, kBlock, 0, st>>>(v);  split_te_h_kernel<true><<<nblk, kBlock, 0, st>>>(v); }
+    else      { split_te_e_kernel<false, false><<<nblk, kBlock, 0, st>>>(v); split_te_h_kernel<false><<<nblk, kBlock, 0, st>>>(v); }
     break;
   case B200FDTD_NS_TM:     // nsFdtdTM.c:68-80: calcH, calcE, source, Ez = Ezx + Ezy
-    split_tm_h_kernel<true><<<nblk, kBlock, 0, st>>>(v);
-    split_tm_e_kernel<true><<<nblk, kBlock, 0, st>>>(v);
+    if (lean) { split_tm_h_kernel<true, true><<<nblk, kBlock, 0, st>>>(v);  split_tm_e_kernel<true, true><<<nblk, kBlock, 0, st>>>(v); }
+    else      { split_tm_h_kernel<true, false><<<nblk, kBlock, 0, st>>>(v); split_tm_e_kernel<true, false><<<nblk, kBlock, 0, st>>>(v); }
     break;
   case B200FDTD_NS_TE:     // nsFdtdTE.c:233-251: calcH, Hz = Hzx + Hzy, calcE, sources
-    split_te_h_kernel<<<nblk, kBlock, 0, st>>>(v);
-    split_te_e_kernel<true><<<nblk, kBlock, 0, st>>>(v);
+    split_te_h_kernel<false><<<nblk, kBlock, 0, st>>>(v);
+    split_te_e_kernel<true, false><<<nblk, kBlock, 0, st>>>(v);
     break;
   default:
     return b200_fail(B200FDTD_ERR_STATE, "not a split-field kind: %d", e->g.kind);

@@ -235,6 +235,103 @@ static void build_rows_parallel(void (*fn)(SplitSolver *, int, int), SplitSolver
     if (spawned[t]) pthread_join(tid[t], NULL);
 }
 
+/* ---- lean form (kinds 0, 1, 6; include/b200fdtd.h "lean form") ---------------------
+ * The same expressions as the dense builders above, evaluated once per row / column where
+ * they do not depend on eps; what does depend on eps goes to the device as the eps map
+ * itself (kinds 0, 1) or as one G array per curl coefficient (kind 6).
+ * MPIFDTD_SPLIT_DENSE=1 keeps the dense form (A/B tests). */
+static int lean_wanted(int kind)
+{
+  const char *v = getenv("MPIFDTD_SPLIT_DENSE");
+  if (v != NULL && v[0] == '1') return 0;
+  return kind == B200FDTD_TM || kind == B200FDTD_TE || kind == B200FDTD_NS_TM;
+}
+
+static void build_lean_tables(int kind, double *ti, double *tj)
+{
+  const double R = 1.0e-8, M = 2.0;
+  for (int k = 0; k < B200FDTD_SPLIT_TABS * N_PX; k++) ti[k] = 1.0;
+  for (int k = 0; k < B200FDTD_SPLIT_TABS * N_PY; k++) tj[k] = 1.0;
+  if (kind == B200FDTD_TM) {                                   /* fdtdTM.c:204-238 */
+    const double sig_max = -(M + 1.0) * EPSILON_0_S * LIGHT_SPEED_S / 2.0 / N_PML * log(R);
+    for (int i = 0; i < N_PX; i++) {
+      double sig_hy_x = sig_max * field_sigmaX(i + 0.5, 0);
+      double sig_hy_xx = MU_0_S / EPSILON_0_S * sig_hy_x;
+      ti[B200FDTD_LTM_I_SIG_EZ_X * N_PX + i] = sig_max * field_sigmaX(i, 0);
+      ti[B200FDTD_LTM_I_C_HY * N_PX + i]     = field_pmlCoef(MU_0_S, sig_hy_xx);
+      ti[B200FDTD_LTM_I_C_HYLX * N_PX + i]   = field_pmlCoef_LXY(MU_0_S, sig_hy_xx);
+    }
+    for (int j = 0; j < N_PY; j++) {
+      double sig_hx_y = sig_max * field_sigmaY(0, j + 0.5);
+      double sig_hx_yy = MU_0_S / EPSILON_0_S * sig_hx_y;
+      tj[B200FDTD_LTM_J_SIG_EZ_Y * N_PY + j] = sig_max * field_sigmaY(0, j);
+      tj[B200FDTD_LTM_J_C_HX * N_PY + j]     = field_pmlCoef(MU_0_S, sig_hx_yy);
+      tj[B200FDTD_LTM_J_C_HXLY * N_PY + j]   = field_pmlCoef_LXY(MU_0_S, sig_hx_yy);
+    }
+  } else if (kind == B200FDTD_TE) {                            /* fdtdTE.c:203-240 */
+    const double sig_max = -(M + 1.0) * EPSILON_0_S * LIGHT_SPEED_S / 2.0 / N_PML * log(R);
+    for (int i = 0; i < N_PX; i++) {
+      double sig_hz_x = sig_max * field_sigmaX(i + 0.5, 0.5);
+      double sig_hz_xx = MU_0_S / EPSILON_0_S * sig_hz_x;
+      ti[B200FDTD_LTE_I_SIG_EY_X * N_PX + i] = sig_max * field_sigmaX(i, 0.5);
+      ti[B200FDTD_LTE_I_C_HZX * N_PX + i]    = field_pmlCoef(MU_0_S, sig_hz_xx);
+      ti[B200FDTD_LTE_I_C_HZXLX * N_PX + i]  = field_pmlCoef_LXY(MU_0_S, sig_hz_xx);
+    }
+    for (int j = 0; j < N_PY; j++) {
+      double sig_hz_y = sig_max * field_sigmaY(0.5, j + 0.5);
+      double sig_hz_yy = MU_0_S / EPSILON_0_S * sig_hz_y;
+      tj[B200FDTD_LTE_J_SIG_EX_Y * N_PY + j] = sig_max * field_sigmaY(0.5, j);
+      tj[B200FDTD_LTE_J_C_HZY * N_PY + j]    = field_pmlCoef(MU_0_S, sig_hz_yy);
+      tj[B200FDTD_LTE_J_C_HZYLY * N_PY + j]  = field_pmlCoef_LXY(MU_0_S, sig_hz_yy);
+    }
+  } else {                                                     /* NS TM, nsFdtdTM.c:231-305 */
+    const double sig_max = -(M + 1.0) * EPSILON_0_S * C_0_S / N_PML * log(R);
+    for (int i = 0; i < N_PX; i++) {
+      double b_ez_x = ns_beta(sig_max * field_sigmaX(i, 0) / (2 * EPSILON_0_S));
+      double b_hy_x = ns_beta(sig_max * field_sigmaX(i + 0.5, 0) / (2 * EPSILON_0_S));
+      ti[B200FDTD_LNS_I_C_EZX * N_PX + i]  = ns_coef1(b_ez_x);
+      ti[B200FDTD_LNS_I_DEN_EZ * N_PX + i] = 1 + b_ez_x;
+      ti[B200FDTD_LNS_I_C_HY * N_PX + i]   = ns_coef1(b_hy_x);
+      ti[B200FDTD_LNS_I_DEN_HY * N_PX + i] = 1.0 + b_hy_x;
+    }
+    for (int j = 0; j < N_PY; j++) {
+      double b_ez_y = ns_beta(sig_max * field_sigmaY(0, j) / (2 * EPSILON_0_S));
+      double b_hx_y = ns_beta(sig_max * field_sigmaY(0, j + 0.5) / (2 * EPSILON_0_S));
+      tj[B200FDTD_LNS_J_C_EZY * N_PY + j]  = ns_coef1(b_ez_y);
+      tj[B200FDTD_LNS_J_C_HX * N_PY + j]   = ns_coef1(b_hx_y);
+      tj[B200FDTD_LNS_J_DEN_HX * N_PY + j] = 1.0 + b_hx_y;
+    }
+  }
+}
+
+/* kind 6: the eps-dependent numerators of the three curl coefficients and the source factor
+ * (nsFdtdTM.c:279-305, field.c:168-174); written into the coef slots the device reads them from */
+static void build_ns_tm_numerators(SplitSolver *s, int i_first, int i_end)
+{
+  const double w_s = field_getOmega(), k_s = field_getK();
+  for (int i = i_first; i < i_end; i++)
+    for (int j = 0; j < N_PY; j++) {
+      int k = field_index(i, j);
+      double eps_ez = s->eps[0][k], eps_hx = s->eps[1][k], eps_hy = s->eps[2][k];
+      double z_ez = sqrt(MU_0_S / eps_ez);
+      double n_ez = sqrt(eps_ez / EPSILON_0_S);
+      double k_ez_s = k_s * n_ez;
+      double u_ez = sin(w_s * 0.5) / sin(k_ez_s * 0.5);
+      s->coef[B200FDTD_STM_C_EZXLX][k] = u_ez * z_ez;
+      double z_hx = sqrt(MU_0_S / eps_hx);
+      double n_hx = sqrt(eps_hx / EPSILON_0_S);
+      double k_hx_s = k_s * n_hx;
+      double u_hx = sin(w_s * 0.5) / sin(k_hx_s * 0.5);
+      s->coef[B200FDTD_STM_C_HXLY][k] = u_hx / z_hx;
+      double z_hy = sqrt(MU_0_S / eps_hy);
+      double n_hy = sqrt(eps_hy / EPSILON_0_S);
+      double k_hy_s = k_s * n_hy;
+      double u_hy = sin(w_s * 0.5) / sin(k_hy_s * 0.5);
+      s->coef[B200FDTD_STM_C_HYLX][k] = u_hy / z_hy;
+      s->src[0][k] = ns_source_factor(eps_ez, w_s, k_s);
+    }
+}
+
 /* ---- init ------------------------------------------------------------------------ */
 static void free_host(SplitSolver *s)
 {
@@ -244,11 +341,34 @@ static void free_host(SplitSolver *s)
 }
 
 /* host half of init(): permittivity maps, the eight coefficient arrays, source factors */
-static void build_host(SplitSolver *s)
+static void build_host(SplitSolver *s, int lean)
 {
   FieldInfo_S g = field_getFieldInfo_S();
   const size_t n = (size_t)g.N_CELL;
   free_host(s);
+  if (lean) {
+    /* only what the lean kernels read: EPS_EZ (kind 0); EPS_EX, EPS_EY (kind 1); all three
+     * maps, three numerator arrays and the source factor (kind 6) */
+    if (s->kind == B200FDTD_TM) {
+      s->eps[0] = newDouble(g.N_CELL);
+      mpifdtd_fill_eps(s->eps[0], 0, 0, D_XY);
+    } else if (s->kind == B200FDTD_TE) {
+      s->eps[0] = newDouble(g.N_CELL);  s->eps[1] = newDouble(g.N_CELL);
+      mpifdtd_fill_eps(s->eps[0], 0.5, 0, D_Y);
+      mpifdtd_fill_eps(s->eps[1], 0, 0.5, D_X);
+    } else {
+      for (int m = 0; m < 3; m++) s->eps[m] = newDouble(g.N_CELL);
+      mpifdtd_fill_eps(s->eps[0], 0, 0, D_XY);
+      mpifdtd_fill_eps(s->eps[1], 0, 0.5, D_Y);
+      mpifdtd_fill_eps(s->eps[2], 0.5, 0, D_X);
+      s->coef[B200FDTD_STM_C_EZXLX] = newDouble(g.N_CELL);
+      s->coef[B200FDTD_STM_C_HXLY] = newDouble(g.N_CELL);
+      s->coef[B200FDTD_STM_C_HYLX] = newDouble(g.N_CELL);
+      s->src[0] = newDouble(g.N_CELL);
+      build_rows_parallel(build_ns_tm_numerators, s);
+    }
+    return;
+  }
   for (int m = 0; m < 3; m++) s->eps[m] = newDouble(g.N_CELL);
   for (int m = 0; m < 8; m++) s->coef[m] = newDouble(g.N_CELL);
   for (int m = 0; m < 2; m++) s->src[m] = newDouble(g.N_CELL);
@@ -288,8 +408,8 @@ static void build_host(SplitSolver *s)
 static void solver_init(SplitSolver *s)
 {
   FieldInfo_S g = field_getFieldInfo_S();
-  const size_t n = (size_t)g.N_CELL;
-  build_host(s);
+  const int lean = lean_wanted(s->kind);
+  build_host(s, lean);
 
   b200fdtd_grid grid;
   memset(&grid, 0, sizeof grid);
@@ -301,11 +421,28 @@ static void solver_init(SplitSolver *s)
   grid.device = -1;
   grid.mu0 = MU_0_S;
   die_on(b200fdtd_create(&grid, &s->engine), "b200fdtd_create");
+  if (lean) {
+    double *ti = (double *)malloc(sizeof(double) * B200FDTD_SPLIT_TABS * (size_t)g.N_PX);
+    double *tj = (double *)malloc(sizeof(double) * B200FDTD_SPLIT_TABS * (size_t)g.N_PY);
+    build_lean_tables(s->kind, ti, tj);
+    die_on(b200fdtd_set_split_tables(s->engine, ti, tj), "b200fdtd_set_split_tables");
+    free(ti); free(tj);
+    if (s->kind == B200FDTD_NS_TM) {
+      const int slots[3] = { B200FDTD_STM_C_EZXLX, B200FDTD_STM_C_HXLY, B200FDTD_STM_C_HYLX };
+      for (int m = 0; m < 3; m++)
+        die_on(b200fdtd_set_dense(s->engine, slots[m], s->coef[slots[m]]), "b200fdtd_set_dense");
+      die_on(b200fdtd_set_dense(s->engine, B200FDTD_DENSE_SRC0, s->src[0]), "b200fdtd_set_dense(src0)");
+    } else {
+      die_on(b200fdtd_set_eps(s->engine, 0, s->eps[0]), "b200fdtd_set_eps");
+      if (s->kind == B200FDTD_TE) die_on(b200fdtd_set_eps(s->engine, 1, s->eps[1]), "b200fdtd_set_eps");
+    }
+    return;
+  }
   for (int m = 0; m < 8; m++)
     die_on(b200fdtd_set_dense(s->engine, m, s->coef[m]), "b200fdtd_set_dense");
   die_on(b200fdtd_set_dense(s->engine, B200FDTD_DENSE_SRC0, s->src[0]), "b200fdtd_set_dense(src0)");
   die_on(b200fdtd_set_dense(s->engine, B200FDTD_DENSE_SRC1, s->src[1]), "b200fdtd_set_dense(src1)");
-  (void)n;       /* the pinned getter mirrors are allocated by the first getter call (solver_field) */
+  /* the pinned getter mirrors are allocated by the first getter call (solver_field) */
 }
 
 /* ---- update ------------------------------------------------------------------------ */
@@ -407,7 +544,7 @@ void mpifdtd_split_prepare_host(int kind)
 {
   SplitSolver *all[] = { &tm_plain, &te_plain, &tm_ns, &te_ns };
   for (int n = 0; n < 4; n++)
-    if (all[n]->kind == kind) build_host(all[n]);
+    if (all[n]->kind == kind) build_host(all[n], 0);        /* the dense arrays, whatever the solver runs */
 }
 const double *mpifdtd_split_dense(int kind, int slot)
 {

@@ -2,8 +2,9 @@
 """Throughput of the split-field solvers (ids 0, 1: Yee + Berenger PML; 6, 7: NS-FDTD) at
 BASELINE configs[3]'s size, 4096 x 4096, Mie cylinder, through the plugin surface
 (simulator_calc).  CUDA-event timed on the engine's stream; one JSON line per solver id.
-Algorithmic bytes per cell-update: 5 complex fields, 8 dense coefficients and one
-or two source factors: TM 280 B, TE 288 B."""
+Algorithmic bytes per cell-update: lean form (default for ids 0, 1, 6):
+id 0 216 B, id 1 224 B, id 6 224 B; dense form (id 7, or MPIFDTD_SPLIT_DENSE=1): 5 complex
+fields read/written + 8 coefficients + source factors = 264-288 B."""
 import ctypes as C
 import json
 import os
@@ -12,9 +13,13 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from mpifdtd_b200 import binding as B
 
-BYTES = {0: 280, 6: 280 + 0, 1: 288, 7: 288}     # NS TM reads Ez (1 field) instead of Ezx+Ezy in the H phase: 264
-BYTES[6] = 264
-BYTES[7] = 272
+DENSE = os.environ.get("MPIFDTD_SPLIT_DENSE") == "1"
+# id 0: H phase reads Ezx,Ezy,Hx,Hy (64) + writes Hx,Hy (32); E phase reads Hx,Hy,Ezx,Ezy (64) + eps (8) + writes 3 (48)
+# id 1: E phase reads Hzx,Hzy,Ex,Ey (64) + 2 eps (16) + writes 2 (32); H phase reads 4 (64) + writes 3 (48)
+# id 6: H phase reads Ez,Hx,Hy (48) + 2 numerators (16) + writes 2 (32); E phase reads 4 (64) + numerator + source
+#       factor (16) + writes 3 (48)
+# id 7 (dense): H phase reads 4 + 4 coef (96) + writes 3 (48); E phase reads Hz,Ex,Ey (48) + 4 coef + 2 factors (48) + writes 2 (32)
+BYTES = {0: 280, 1: 288, 6: 264, 7: 272} if DENSE else {0: 216, 1: 224, 6: 224, 7: 272}
 
 
 def main():

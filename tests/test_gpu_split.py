@@ -16,8 +16,49 @@ FIELDS = {0: ["Ez", "Ezx", "Ezy", "Hx", "Hy"], 1: ["Hz", "Hzx", "Hzy", "Ex", "Ey
 DUMP = {0: "tm_%dnm.txt", 1: "te_%dnm.txt", 6: "ns_tm_%dnm.txt", 7: "ns_te_%dnm.txt"}
 
 
+@pytest.fixture(params=["lean", "dense"])
+def split_form(request, monkeypatch):
+    """Kinds 0, 1, 6 run the lean form by default (1-D tables + eps / numerator arrays, DESIGN.md);
+    MPIFDTD_SPLIT_DENSE=1 keeps the reference's eight dense coefficient arrays.  Both must pass."""
+    if request.param == "dense":
+        monkeypatch.setenv("MPIFDTD_SPLIT_DENSE", "1")
+    else:
+        monkeypatch.delenv("MPIFDTD_SPLIT_DENSE", raising=False)
+    return request.param
+
+
+@pytest.mark.parametrize("kind,model", [(0, "LAYER"), (0, "MIE_CYLINDER"), (1, "LAYER"), (1, "ZIGZAG"),
+                                        (6, "LAYER"), (6, "MORPHO_SCALE")])
+def test_lean_form_is_bit_identical_to_dense(plugin_lib, kind, model, in_tmp_cwd, monkeypatch):
+    """LAYER puts eps != 1 inside the PML, i.e. the in-kernel field_pmlCoef path with its three
+    IEEE divisions; the others cover the 1/eps-only path and the NS numerators."""
+    npx, npy, steps = 200, 220, 240      # the validation circle of finish() (1.2 lambda = 76 cells) must fit
+    runs = {}
+    for form in ("dense", "lean"):
+        if form == "dense":
+            monkeypatch.setenv("MPIFDTD_SPLIT_DENSE", "1")
+        else:
+            monkeypatch.delenv("MPIFDTD_SPLIT_DENSE")
+        gpu = B.Plugin(model, kind, npx, npy, steps=steps, lambda_nm=633, angle_deg=15)
+        bytes_on_device = C_uint64_device_bytes(gpu)
+        gpu.run()
+        runs[form] = ({f: gpu.field(f) for f in FIELDS[kind]}, bytes_on_device)
+        gpu.finish()
+    assert np.abs(runs["dense"][0][FIELDS[kind][0]]).max() > 1e-3
+    for f in FIELDS[kind]:
+        assert bit_equal(runs["lean"][0][f], runs["dense"][0][f]), f
+    assert runs["lean"][1] < 0.8 * runs["dense"][1]              # and it really keeps fewer arrays
+
+
+def C_uint64_device_bytes(gpu):
+    import ctypes as C
+    n = C.c_uint64(0)
+    gpu.L.b200fdtd_device_bytes(gpu.engine_handle(), C.byref(n))
+    return n.value
+
+
 @pytest.mark.parametrize("kind", [0, 1, 6, 7])
-def test_split_solver_matches_reference_golden(plugin_lib, kind, in_tmp_cwd):
+def test_split_solver_matches_reference_golden(plugin_lib, kind, in_tmp_cwd, split_form):
     g = np.load(os.path.join(GOLDEN, "split_kind%d.npz" % kind))
     npx, npy, hu, steps, lam, angle = (int(v) for v in g["meta"][:6])
     gpu = B.Plugin("MIE_CYLINDER", kind, npx, npy, steps=steps, h_u_nm=hu, lambda_nm=lam, angle_deg=angle)
@@ -36,7 +77,7 @@ def test_split_solver_matches_reference_golden(plugin_lib, kind, in_tmp_cwd):
 
 
 @pytest.mark.parametrize("kind,model", [(0, "ZIGZAG"), (1, "LAYER"), (6, "MORPHO_SCALE"), (7, "MIE_CYLINDER")])
-def test_split_solver_vs_live_reference(plugin_lib, kind, model, in_tmp_cwd):
+def test_split_solver_vs_live_reference(plugin_lib, kind, model, in_tmp_cwd, split_form):
     from oracle import reflib
     if not reflib.available():
         pytest.skip("oracle/_ref/libref.so did not travel with this snapshot")
