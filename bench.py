@@ -412,7 +412,8 @@ def main():
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=N_PER_GPU, help="cells per side per GPU")
+    ap.add_argument("--n", "--size", dest="n", type=int, default=N_PER_GPU,
+                    help="cells per side per GPU (use --size under torchrun, whose own parser trips over --n)")
     ap.add_argument("--cpu-n", type=int, default=1024, help="grid side of the CPU sample")
     ap.add_argument("--cpu-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -121,3 +121,29 @@ def test_batch_rejected_where_not_built(plugin_lib):
     assert plugin_lib.b200fdtd_step(h, C.byref(args)) == 4               # ERR_STATE: nothing uploaded yet
     assert plugin_lib.b200fdtd_select_batch(h, 3) == 1
     plugin_lib.b200fdtd_destroy(h)
+
+
+def test_sweep_tool_directory_chain_and_rank_striding(plugin_lib, tmp_path):
+    """mpifdtd_b200/mpifdtd_sweep: main.c's batch mode (structure loop, moveDir chain) with each
+    structure's angles as one batched engine; two 'ranks' stride through the angle list like
+    the reference's MPI ranks (main.c:126-138)."""
+    import subprocess
+    tool = os.path.join(os.path.dirname(B.LIB_PATH), "mpifdtd_sweep")
+    assert os.path.exists(tool), "run __graft_entry__.build()"
+    cfg = tmp_path / "config.txt"
+    # width height h_u pml lambda steps startAngle endAngle deltaAngle model solver
+    cfg.write_text("# sweep test\n2000\n2000\n20\n10\n500\n160\n0\n50\n10\n1\n2\n")
+    for rank in (0, 1):
+        env = dict(os.environ, RANK=str(rank), WORLD_SIZE="2")
+        p = subprocess.run([tool, str(cfg)], cwd=tmp_path, env=env, capture_output=True, text=True, timeout=600)
+        assert p.returncode == 0, p.stdout[-2000:]
+        assert "rank %d of 2 ran 3 simulation(s) over 1 structure(s)" % rank in p.stdout
+    out = tmp_path / "MieCylinderModel" / "radius_500nm" / "hu_20nm" / "TM_UPML"
+    names = sorted(os.listdir(out))
+    assert [n for n in names if n.endswith("_b.dat")] == sorted("%d[deg]_380nm_700nm_b.dat" % a for a in range(0, 51, 10))
+    os.chdir(tmp_path)
+    gpu = B.Plugin("MIE_CYLINDER", 2, 100, steps=160, h_u_nm=20, angle_deg=30)
+    gpu.run()
+    want = gpu.finish()
+    got = np.fromfile(str(out / "30[deg]_380nm_700nm_b.dat")).reshape(321, 360)
+    assert bit_equal(got, want)
