@@ -358,7 +358,13 @@ enum {
                                  0 (default): H is derived from B on demand (getters, NTFF,
                                  halo) -- Hx == Bx/mu0 holds after every H phase (232 B/cell)    */
   B200FDTD_OPT_BAND_ROWS = 3, /* rows a warp marches per band in the fused kernel (default 256)  */
-  B200FDTD_OPT_FUSED_SHAPE = 4 /* launch shape of the fused kernel (tuning; see fused_kernels.cu)  */
+  B200FDTD_OPT_FUSED_SHAPE = 4, /* launch shape of the fused kernel (tuning; see fused_kernels.cu) */
+  B200FDTD_OPT_PIPELINED = 5,  /* 1: b200fdtd_step of an unbatched, peer-less UPML engine runs ONE
+                                  persistent kernel per step that overlaps the H phase of row band
+                                  k+1 with the E phase of band k, so the E phase finds Bx/By (Bz) in
+                                  L2: 232 instead of 264 B/cell of DRAM traffic (TM).  Bit-identical
+                                  to the two-kernel step.  0: two kernels.                        */
+  B200FDTD_OPT_PIPE_BAND_ROWS = 6 /* rows per band of the pipelined step (default 4)             */
 };
 int b200fdtd_set_option(b200fdtd_engine *e, int32_t option, int32_t value);
 

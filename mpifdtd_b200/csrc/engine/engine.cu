@@ -168,6 +168,9 @@ int b200fdtd_create(const b200fdtd_grid *grid, b200fdtd_engine **out)
   if (const char *v = getenv("B200FDTD_FUSED"))
     e->use_fused = atoi(v) != 0 && grid->kind == B200FDTD_TM_UPML && !e->fp32 && n_batch == 1;
   if (const char *v = getenv("B200FDTD_STORE_H")) e->store_h = atoi(v) != 0;
+  e->use_pipelined = false;
+  if (const char *v = getenv("B200FDTD_PIPELINED")) e->use_pipelined = atoi(v) != 0;
+  if (const char *v = getenv("B200FDTD_PIPE_BAND_ROWS")) e->pipe.band_rows = atoi(v);
   if (const char *v = getenv("B200FDTD_FUSED_SHAPE")) e->fused_variant = atoi(v);
   if (const char *v = getenv("B200FDTD_BAND_ROWS")) e->fused.band_h = atoi(v);
 
@@ -215,6 +218,7 @@ int b200fdtd_destroy(b200fdtd_engine *e)
   for (int s = 0; s < B200FDTD_MAX_DENSE; s++) cudaFree(e->dense[s]);
   free_ntff(e);
   b200_fused_release(e);
+  b200_pipe_release(e);
   peer_release(e);
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
@@ -588,6 +592,17 @@ int b200fdtd_set_option(b200fdtd_engine *e, int32_t option, int32_t value)
   case B200FDTD_OPT_FUSED_SHAPE:
     e->fused_variant = value;
     return B200FDTD_OK;
+  case B200FDTD_OPT_PIPELINED:
+    if (value && !kind_is_upml(e->g.kind))
+      return b200_fail(B200FDTD_ERR_ARG, "the pipelined step serves the UPML kinds");
+    e->use_pipelined = value != 0;
+    return B200FDTD_OK;
+  case B200FDTD_OPT_PIPE_BAND_ROWS:
+    if (value < 1) return b200_fail(B200FDTD_ERR_ARG, "band rows must be >= 1");
+    B200_CUDA(cudaStreamSynchronize(e->stream));
+    b200_pipe_release(e);
+    e->pipe.band_rows = value;
+    return B200FDTD_OK;
   default:
     return b200_fail(B200FDTD_ERR_ARG, "unknown option %d", option);
   }
@@ -604,7 +619,11 @@ int b200fdtd_step(b200fdtd_engine *e, const b200fdtd_step_args *a)
   int rc = check_ready(e, a); if (rc) return rc;
   if (kind_is_split(e->g.kind)) return b200_launch_split_step(e, a);
   const bool e_first = (e->g.kind == B200FDTD_MPI_TM_UPML || e->g.kind == B200FDTD_MPI_TE_UPML);
-  if (e->use_fused && e->g.kind == B200FDTD_TM_UPML && !a->line.enabled && !a->cw[0].enabled) {
+  const bool can_pipeline = e->use_pipelined && !e_first && e->n_batch == 1 && !e->store_h &&
+                            !e->peer.attached[0] && !e->peer.attached[1];
+  if (can_pipeline) {
+    rc = b200_launch_upml_pipelined(e, a);      // H and E of one step in one persistent kernel
+  } else if (e->use_fused && e->g.kind == B200FDTD_TM_UPML && !a->line.enabled && !a->cw[0].enabled) {
     rc = b200_launch_upml_fused(e, a);          // H and E in one pass
   } else if (e_first) {              // mpiTM_UPML.c:196-217: E, source, H, NTFF
     rc = b200_launch_upml_e(e, a);

@@ -49,6 +49,18 @@ struct FusedState {          // side buffers of the fused step (fused_kernels.cu
   double2 *col_e, *col_h, *row_e, *row_h;
 };
 
+// Pipelined step (upml_kernels.cu): one persistent kernel per time step that runs the H phase
+// of row band k+1 and the E phase of band k side by side, so the B arrays the E phase reads
+// are still in the 126 MB L2 when it gets to them.
+struct PipeState {
+  bool ready;
+  int band_rows, n_bands, n_ctas;
+  unsigned long long *queue;         // device: task counter, monotonic across launches
+  unsigned int *done_h;              // device [n_bands]: finished H tasks per band, monotonic
+  unsigned long long queue_value;    // host copy of *queue at the next launch
+  unsigned int epoch;                // launches so far
+};
+
 // Peer (NVLink) halo state of a y-slab engine: the neighbours' field arrays and flag words,
 // opened through CUDA IPC.  flags[0]: "the lower neighbour's H-phase halo of step n has
 // landed in my low ghost column" (value n+1); flags[1]: the same for the upper neighbour's
@@ -88,6 +100,8 @@ struct b200fdtd_engine {
   NtffState ntff;
   FusedState fused;
   PeerState peer;
+  PipeState pipe;
+  bool use_pipelined;       // b200fdtd_step runs the pipelined persistent kernel (serial UPML kinds, one slab)
   bool use_fused;           // b200fdtd_step runs the one-pass kernel (serial TM kind)
   bool store_h;             // the fused kernel also writes Hx/Hy (264 instead of 232 B/cell)
   bool h_stale;             // Hx/Hy arrays lag Bx/By (fused step without store_h)
@@ -112,6 +126,8 @@ int b200_fail(int code, const char *fmt, ...);
 // launchers (upml_kernels.cu)
 int b200_launch_upml_h(b200fdtd_engine *e, const b200fdtd_step_args *a);
 int b200_launch_upml_e(b200fdtd_engine *e, const b200fdtd_step_args *a);
+int b200_launch_upml_pipelined(b200fdtd_engine *e, const b200fdtd_step_args *a);
+void b200_pipe_release(b200fdtd_engine *e);
 int b200_launch_halo(b200fdtd_engine *e, int which, void *buf, bool pack);
 int b200_peer_wait(b200fdtd_engine *e, int which, unsigned long long value);
 int b200_peer_signal(b200fdtd_engine *e, unsigned long long *peer_flag, unsigned long long value);
