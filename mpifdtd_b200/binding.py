@@ -138,6 +138,8 @@ def lib():
     L.b200fdtd_peer_attach.argtypes = [vp, i32, vp]
     L.mpifdtd_ntffFrequency.argtypes = [C.c_int, vp]
     L.mpifdtd_split_prepare_host.argtypes = [C.c_int]
+    L.mpifdtd_split_prepare_host_lean.argtypes = [C.c_int]
+    L.mpifdtd_split_lean_tables.argtypes = [C.c_int, vp, vp]
     L.mpifdtd_split_dense.argtypes = [C.c_int, C.c_int]
     L.mpifdtd_split_dense.restype = vp
     L.mpifdtd_split_engine.argtypes = [C.c_int]

@@ -36,6 +36,8 @@ extern void mpifdtd_upml_tables(int kind, double *tab_i, double *tab_j);
 extern void mpifdtd_split_step_args(int kind, b200fdtd_step_args *a);
 extern void mpifdtd_split_prepare_host(int kind);
 extern const double *mpifdtd_split_dense(int kind, int slot);
+extern void mpifdtd_split_prepare_host_lean(int kind);
+extern void mpifdtd_split_lean_tables(int kind, double *tab_i, double *tab_j);
 extern b200fdtd_engine *mpifdtd_split_engine(int kind);
 
 #endif

@@ -546,6 +546,18 @@ void mpifdtd_split_prepare_host(int kind)
   for (int n = 0; n < 4; n++)
     if (all[n]->kind == kind) build_host(all[n], 0);        /* the dense arrays, whatever the solver runs */
 }
+/* test hooks for the lean form: the host arrays a lean init() builds (eps maps; kind 6: the
+ * three numerator arrays in their coef slots + the source factor) and the 1-D tables */
+void mpifdtd_split_prepare_host_lean(int kind)
+{
+  SplitSolver *all[] = { &tm_plain, &te_plain, &tm_ns, &te_ns };
+  for (int n = 0; n < 4; n++)
+    if (all[n]->kind == kind && kind != B200FDTD_NS_TE) build_host(all[n], 1);
+}
+void mpifdtd_split_lean_tables(int kind, double *tab_i, double *tab_j)
+{
+  build_lean_tables(kind, tab_i, tab_j);
+}
 const double *mpifdtd_split_dense(int kind, int slot)
 {
   SplitSolver *all[] = { &tm_plain, &te_plain, &tm_ns, &te_ns };
