@@ -56,7 +56,8 @@ def ncu_traffic(kernel_substr, cells):
     for path in sorted(glob.glob(os.path.join(HERE, "profiles", "*_full.json")), reverse=True):
         try:
             for rec in json.load(open(path))["launches"]:
-                if kernel_substr in rec["kernel"] and abs(rec.get("cells", 0) - cells) < 0.01 * cells:
+                name = rec["kernel"].replace("double, ", "").replace(" ", "")      # "<double, 0>" == "<0>"
+                if kernel_substr in name and abs(rec.get("cells", 0) - cells) < 0.01 * cells:
                     return rec["traffic_bytes"], os.path.relpath(path, HERE)
         except Exception:
             continue
