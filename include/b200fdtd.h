@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define B200FDTD_ABI_VERSION 5
+#define B200FDTD_ABI_VERSION 6
 
 enum {
   B200FDTD_OK = 0,
@@ -294,6 +294,15 @@ int b200fdtd_phase_h(b200fdtd_engine *e, const b200fdtd_step_args *args);
 int b200fdtd_phase_e(b200fdtd_engine *e, const b200fdtd_step_args *args);
 int b200fdtd_phase_sample(b200fdtd_engine *e, const b200fdtd_step_args *args);
 int b200fdtd_sync(b200fdtd_engine *e);
+/* n_steps consecutive update() calls starting at time0, replayed from a CUDA graph: the step's
+ * only time dependence -- the pulse's (time - t0) and the NTFF sample index -- is read from a
+ * device-side clock that a one-thread kernel advances after every step, so the launch sequence
+ * [H phase, E phase + source, surface sample, clock] is identical for every step and a chunk of
+ * it is captured once and replayed.  Removes the per-launch host cost that dominates small
+ * grids (a 256 x 256 step is ~3 us of device work).  Serial UPML kinds (2, 3) driven by the
+ * pulse sources of b200fdtd_set_batch_sources (also accepted for n_batch = 1); no point / CW /
+ * line source, no peer halos.  Bit-identical to n_steps b200fdtd_step calls. */
+int b200fdtd_run_steps(b200fdtd_engine *e, double time0, int32_t n_steps);
 
 /* Halo columns for the y-slab split (replaces Connection_ISend_IRecvH/E,
  * mpiTM_UPML.c:252-296).  which: 0 = after the H phase (TM Hx / TE Hz, my last

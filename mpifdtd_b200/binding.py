@@ -199,6 +199,7 @@ def lib():
     L.mpifdtd_runAngleSweep.argtypes = [FieldInfo, C.c_int, C.c_int, C.c_int, C.c_int]
     L.b200fdtd_mem_info.argtypes = [i32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.b200fdtd_select_batch.argtypes = [vp, i32]
+    L.b200fdtd_run_steps.argtypes = [vp, dbl, i32]
     L.b200fdtd_set_batch_sources.argtypes = [vp, vp]
     L.b200fdtd_struct_size.argtypes = [i32]
     L.mpifdtd_readConfig.argtypes = [C.c_char_p, vp]

@@ -195,8 +195,12 @@ int b200fdtd_create(const b200fdtd_grid *grid, b200fdtd_engine **out)
       rc = dev_alloc_zero(e, (void **)&e->eps[s], e->plane * e->rsize);
     if (!rc) rc = dev_alloc_zero(e, (void **)&e->tab_i, sizeof(double) * B200FDTD_UPML_TABS * e->rows);
     if (!rc) rc = dev_alloc_zero(e, (void **)&e->tab_j, sizeof(double) * B200FDTD_UPML_TABS * e->pitch);
-    if (!rc && n_batch > 1)
+    if (!rc && (grid->kind == B200FDTD_TM_UPML || grid->kind == B200FDTD_TE_UPML)) {
+      // per-simulation pulse records: a batched engine needs them, a single one uses them for
+      // multi-step replay (b200fdtd_run_steps)
       rc = dev_alloc_zero(e, (void **)&e->batch_src, sizeof(b200fdtd_batch_source) * (size_t)n_batch);
+      if (!rc) rc = dev_alloc_zero(e, (void **)&e->clock_dev, sizeof(double));
+    }
   }
   if (rc) { b200fdtd_destroy(e); return rc; }
   if (cudaStreamSynchronize(e->stream) != cudaSuccess) {
@@ -214,7 +218,8 @@ int b200fdtd_destroy(b200fdtd_engine *e)
   if (e->stream) cudaStreamSynchronize(e->stream);
   for (int s = 0; s < B200FDTD_MAX_FIELDS; s++) cudaFree(e->field[s]);
   cudaFree(e->eps[0]); cudaFree(e->eps[1]);
-  cudaFree(e->tab_i); cudaFree(e->tab_j); cudaFree(e->batch_src);
+  cudaFree(e->tab_i); cudaFree(e->tab_j); cudaFree(e->batch_src); cudaFree(e->clock_dev);
+  if (e->graph_exec) cudaGraphExecDestroy((cudaGraphExec_t)e->graph_exec);
   for (int s = 0; s < B200FDTD_MAX_DENSE; s++) cudaFree(e->dense[s]);
   free_ntff(e);
   b200_fused_release(e);
@@ -310,6 +315,7 @@ int b200fdtd_set_stream(b200fdtd_engine *e, void *cuda_stream)
   B200_CUDA(cudaStreamSynchronize(e->stream));
   if (e->own_stream) { cudaStreamDestroy(e->stream); e->own_stream = false; }
   e->stream = (cudaStream_t)cuda_stream;
+  e->graph_epoch++;
   return B200FDTD_OK;
 }
 
@@ -432,7 +438,7 @@ int b200fdtd_set_dense(b200fdtd_engine *e, int32_t slot, const double *host_map)
 int b200fdtd_set_batch_sources(b200fdtd_engine *e, const b200fdtd_batch_source *sources)
 {
   if (!e || !sources) return b200_fail(B200FDTD_ERR_ARG, "NULL argument");
-  if (!e->batch_src) return b200_fail(B200FDTD_ERR_ARG, "engine was not created with n_batch > 1");
+  if (!e->batch_src) return b200_fail(B200FDTD_ERR_ARG, "batch sources serve the serial UPML kinds (2, 3)");
   int rc = select_device(e); if (rc) return rc;
   B200_CUDA(cudaMemcpyAsync(e->batch_src, sources, sizeof(b200fdtd_batch_source) * (size_t)e->n_batch,
                             cudaMemcpyHostToDevice, e->stream));
@@ -512,6 +518,7 @@ int b200fdtd_set_ntff_plan(b200fdtd_engine *e, const b200fdtd_ntff_plan *p)
   B200_CUDA(cudaStreamSynchronize(e->stream));
   n.ready = true;
   n.steps_recorded = 0;
+  e->graph_epoch++;
   return B200FDTD_OK;
 }
 
@@ -573,6 +580,7 @@ int b200fdtd_set_option(b200fdtd_engine *e, int32_t option, int32_t value)
 {
   if (!e) return b200_fail(B200FDTD_ERR_ARG, "NULL engine");
   int rc = select_device(e); if (rc) return rc;
+  e->graph_epoch++;
   switch (option) {
   case B200FDTD_OPT_FUSED:
     if (value && (e->g.kind != B200FDTD_TM_UPML || e->fp32 || e->n_batch > 1))
@@ -633,6 +641,83 @@ int b200fdtd_step(b200fdtd_engine *e, const b200fdtd_step_args *a)
     if (!rc) rc = b200_launch_upml_e(e, a);
   }
   if (!rc) rc = b200_launch_ntff_sample(e, a);
+  return rc;
+}
+
+// One update() with the time taken from the device clock (capturable: nothing in the launch
+// sequence depends on the step number).
+static int launch_clocked_step(b200fdtd_engine *e, const b200fdtd_step_args *a)
+{
+  // (always the two-kernel step: the pipelined kernel's queue base and epoch change per launch,
+  // which a replayed graph cannot express)
+  int rc = b200_launch_upml_h(e, a);
+  if (!rc) rc = b200_launch_upml_e(e, a);
+  if (!rc) rc = b200_launch_ntff_sample(e, a);
+  if (!rc) rc = b200_launch_clock_advance(e);
+  return rc;
+}
+
+int b200fdtd_run_steps(b200fdtd_engine *e, double time0, int32_t n_steps)
+{
+  if (!e || n_steps < 0) return b200_fail(B200FDTD_ERR_ARG, "bad argument");
+  if (e->g.kind != B200FDTD_TM_UPML && e->g.kind != B200FDTD_TE_UPML)
+    return b200_fail(B200FDTD_ERR_ARG, "multi-step replay serves the serial UPML kinds (2, 3)");
+  if (!e->have_batch_src) return b200_fail(B200FDTD_ERR_STATE, "run_steps before set_batch_sources");
+  if (e->peer.attached[0] || e->peer.attached[1] || e->use_fused)
+    return b200_fail(B200FDTD_ERR_ARG, "multi-step replay: no peer halos, no fused step");
+  b200fdtd_step_args a;
+  memset(&a, 0, sizeof a);
+  a.time = time0;
+  int rc = check_ready(e, &a); if (rc) return rc;
+  if (n_steps == 0) return B200FDTD_OK;
+  NtffState &n = e->ntff;
+  if (n.ready && ((int)time0 < 0 || (int)time0 + n_steps > n.max_time))
+    return b200_fail(B200FDTD_ERR_ARG, "steps %d..%d outside the NTFF history [0, %d)", (int)time0,
+                     (int)time0 + n_steps - 1, n.max_time);
+  B200_CUDA(cudaMemcpyAsync(e->clock_dev, &time0, sizeof(double), cudaMemcpyHostToDevice, e->stream));
+  B200_CUDA(cudaStreamSynchronize(e->stream));          // time0 is a stack variable
+
+  const int kChunk = 128;
+  e->clock_mode = true;
+  int done = 0;
+  while (done < n_steps && !rc) {
+    const int chunk = n_steps - done < kChunk ? n_steps - done : kChunk;
+    cudaGraphExec_t exec = (cudaGraphExec_t)e->graph_exec;
+    if (exec == nullptr || e->graph_steps != chunk || e->graph_built_epoch != e->graph_epoch) {
+      if (exec) { cudaGraphExecDestroy(exec); e->graph_exec = nullptr; }
+      // a chunk shorter than 8 steps is not worth a graph
+      if (chunk < 8) {
+        for (int s = 0; s < chunk && !rc; s++) rc = launch_clocked_step(e, &a);
+        done += chunk;
+        continue;
+      }
+      const uint64_t launches_before = e->launches;
+      cudaGraph_t graph = nullptr;
+      cudaError_t err = cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal);
+      if (err != cudaSuccess) { rc = b200_fail(B200FDTD_ERR_CUDA, "begin capture: %s", cudaGetErrorString(err)); break; }
+      for (int s = 0; s < chunk && !rc; s++) rc = launch_clocked_step(e, &a);
+      err = cudaStreamEndCapture(e->stream, &graph);
+      e->launches = launches_before;                    // captured, not launched yet
+      if (rc) { if (graph) cudaGraphDestroy(graph); break; }
+      if (err != cudaSuccess) { rc = b200_fail(B200FDTD_ERR_CUDA, "end capture: %s", cudaGetErrorString(err)); break; }
+      err = cudaGraphInstantiate(&exec, graph, 0);
+      cudaGraphDestroy(graph);
+      if (err != cudaSuccess) { rc = b200_fail(B200FDTD_ERR_CUDA, "graph instantiate: %s", cudaGetErrorString(err)); break; }
+      e->graph_exec = exec;
+      e->graph_steps = chunk;
+      e->graph_built_epoch = e->graph_epoch;
+    }
+    cudaError_t err = cudaGraphLaunch((cudaGraphExec_t)e->graph_exec, e->stream);
+    if (err != cudaSuccess) { rc = b200_fail(B200FDTD_ERR_CUDA, "graph launch: %s", cudaGetErrorString(err)); break; }
+    const int per_step = 2 + (n.ready && n.n_local > 0 ? 1 : 0) + 1;     // H, E, sample, clock
+    e->launches += (uint64_t)per_step * chunk;
+    done += chunk;
+  }
+  e->clock_mode = false;
+  if (!rc) {
+    e->h_stale = !e->store_h;
+    if (n.ready && (int)time0 + n_steps > n.steps_recorded) n.steps_recorded = (int)time0 + n_steps;
+  }
   return rc;
 }
 

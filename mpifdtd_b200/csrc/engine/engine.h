@@ -101,6 +101,12 @@ struct b200fdtd_engine {
   FusedState fused;
   PeerState peer;
   PipeState pipe;
+  // multi-step replay (b200fdtd_run_steps): device clock {time} and the cached graph of a chunk
+  double *clock_dev;        // device: [0] = time of the step being computed
+  bool clock_mode;          // launchers build views that read the time from clock_dev
+  void *graph_exec;         // cudaGraphExec_t of `graph_steps` steps, or nullptr
+  int graph_steps;
+  unsigned graph_epoch, graph_built_epoch;   // bumped by anything that changes what a step launches
   bool use_pipelined;       // b200fdtd_step runs the pipelined persistent kernel (serial UPML kinds, one slab)
   bool use_fused;           // b200fdtd_step runs the one-pass kernel (serial TM kind)
   bool store_h;             // the fused kernel also writes Hx/Hy (264 instead of 232 B/cell)
@@ -152,6 +158,7 @@ void b200_fused_release(b200fdtd_engine *e);
 
 // launchers (ntff_kernels.cu)
 int b200_launch_ntff_sample(b200fdtd_engine *e, const b200fdtd_step_args *a);
+int b200_launch_clock_advance(b200fdtd_engine *e);
 int b200_launch_ntff_project(b200fdtd_engine *e);
 int b200_run_ntff_spectrum(b200fdtd_engine *e, const b200fdtd_spectrum_args *s, double *out);
 int b200_run_ntff_frequency(b200fdtd_engine *e, const b200fdtd_freq_args *a, double *out);

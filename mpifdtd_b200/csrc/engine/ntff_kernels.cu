@@ -61,10 +61,15 @@ __global__ void ntff_sample_kernel(const NtffPoint *__restrict__ pts, int n_loca
                                    // column -- left of it lies the ring / a halo column, which only the H
                                    // array holds.  b_a == nullptr: read H directly.
                                    const C *__restrict__ b_a, const C *__restrict__ b_b,
-                                   double h_divisor, int c_lo, size_t plane)
+                                   double h_divisor, int c_lo, size_t plane,
+                                   const double *__restrict__ clock)     // multi-step replay: t = (int)*clock
 {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n_local) return;
+  if (clock != nullptr) {
+    t = (int)*clock;
+    if (t < 0 || t >= max_time) return;
+  }
   const NtffPoint pt = pts[p];
   // blockIdx.y = simulation of a batched engine (0 otherwise): shift every array to its plane
   const size_t off = (size_t)blockIdx.y * plane;
@@ -400,7 +405,7 @@ int b200_launch_ntff_sample(b200fdtd_engine *e, const b200fdtd_step_args *a)
   NtffState &n = e->ntff;
   if (!n.ready) return B200FDTD_OK;
   const int t = (int)a->time;
-  if (t < 0 || t >= n.max_time)
+  if (!e->clock_mode && (t < 0 || t >= n.max_time))
     return b200_fail(B200FDTD_ERR_ARG, "NTFF sample at step %d outside [0, %d)", t, n.max_time);
   if (n.n_local > 0) {
     const bool tm = is_tm(e->g.kind);
@@ -413,17 +418,31 @@ int b200_launch_ntff_sample(b200fdtd_engine *e, const b200fdtd_step_args *a)
       const float2 *const *f = (const float2 *const *)e->field;
       ntff_sample_kernel<float2><<<blocks, 128, 0, e->stream>>>(
           n.pts, n.n_local, tm ? 1 : 0, f[s_ea], f[s_eb], f[s_ha], f[s_hb], e->pitch, n.hist_e, n.hist_h,
-          n.max_time, t, from_b ? f[s_ba] : nullptr, from_b ? f[s_bb] : nullptr, e->g.mu0, e->c_lo, e->plane);
+          n.max_time, t, from_b ? f[s_ba] : nullptr, from_b ? f[s_bb] : nullptr, e->g.mu0, e->c_lo, e->plane,
+          e->clock_mode ? e->clock_dev : nullptr);
     } else {
       double2 *const *f = e->field;
       ntff_sample_kernel<double2><<<blocks, 128, 0, e->stream>>>(
           n.pts, n.n_local, tm ? 1 : 0, f[s_ea], f[s_eb], f[s_ha], f[s_hb], e->pitch, n.hist_e, n.hist_h,
-          n.max_time, t, from_b ? f[s_ba] : nullptr, from_b ? f[s_bb] : nullptr, e->g.mu0, e->c_lo, e->plane);
+          n.max_time, t, from_b ? f[s_ba] : nullptr, from_b ? f[s_bb] : nullptr, e->g.mu0, e->c_lo, e->plane,
+          e->clock_mode ? e->clock_dev : nullptr);
     }
     e->launches++;
     B200_CUDA(cudaGetLastError());
   }
-  if (t + 1 > n.steps_recorded) n.steps_recorded = t + 1;
+  if (!e->clock_mode && t + 1 > n.steps_recorded) n.steps_recorded = t + 1;
+  return B200FDTD_OK;
+}
+
+namespace {
+__global__ void clock_advance_kernel(double *clock) { clock[0] += 1.0; }   // field_nextStep: time += 1 (field.c:313)
+}
+
+int b200_launch_clock_advance(b200fdtd_engine *e)
+{
+  clock_advance_kernel<<<1, 1, 0, e->stream>>>(e->clock_dev);
+  e->launches++;
+  B200_CUDA(cudaGetLastError());
   return B200FDTD_OK;
 }
 

@@ -27,6 +27,7 @@ struct UpmlViewT {
   size_t plane;                 // elements per simulation; blockIdx.y selects the simulation of a batch
   const b200fdtd_batch_source *batch;   // per-simulation sources of a batched engine, or nullptr
   double time;                  // step_args.time (batched pulses form time - t0 themselves)
+  const double *time_ptr;       // multi-step replay: the time lives in a device-side clock instead
   int r_lo, r_hi, c_lo, c_hi;
   int nbx;                      // thread blocks per row (two-kernel form)
   int j_base;                   // global j = j_base + c
@@ -141,7 +142,8 @@ __device__ __forceinline__ b200fdtd_pulse pulse_of(const UpmlViewT<T> &v, int m)
 {
   if (v.batch == nullptr) return v.pulse[m];
   b200fdtd_pulse p = v.batch[blockIdx.y].pulse[m];
-  p.time_minus_t0 = v.time - v.batch[blockIdx.y].t0[m];
+  const double time = v.time_ptr != nullptr ? *v.time_ptr : v.time;
+  p.time_minus_t0 = time - v.batch[blockIdx.y].t0[m];
   return p;
 }
 template <typename T>
@@ -185,8 +187,9 @@ inline UpmlViewT<T> make_view_t(const b200fdtd_engine *e, const b200fdtd_step_ar
   v.pitch = e->pitch;
   v.rows = e->rows;
   v.plane = e->plane;
-  v.batch = e->n_batch > 1 ? e->batch_src : nullptr;
+  v.batch = (e->n_batch > 1 || e->clock_mode) ? e->batch_src : nullptr;
   v.time = a->time;
+  v.time_ptr = e->clock_mode ? e->clock_dev : nullptr;
   v.r_lo = e->r_lo;
   v.r_hi = e->r_hi;
   v.c_lo = e->c_lo;

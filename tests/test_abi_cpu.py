@@ -27,7 +27,7 @@ def declared_functions(header):
 def test_engine_header_symbols_exported(plugin_lib):
     missing = [n for n in sorted(declared_functions("b200fdtd.h")) if not hasattr(plugin_lib, n)]
     assert not missing, missing
-    assert plugin_lib.b200fdtd_abi_version() == 5
+    assert plugin_lib.b200fdtd_abi_version() == 6
 
 
 def test_ctypes_mirrors_match_the_compiled_structs(plugin_lib):

@@ -90,11 +90,17 @@ def test_fused_step_is_bit_identical_to_two_kernel_step(plugin_lib, npx, npy, ba
         eng.close()
 
 
-def test_launches_per_step(plugin_lib, in_tmp_cwd):
+def test_launches_per_step(plugin_lib, in_tmp_cwd, monkeypatch):
     gpu = B.Plugin("MIE_CYLINDER", "TM_UPML_2D", 96, steps=10, h_u_nm=20)
     n0 = gpu.launches()
     gpu.step(1)
-    assert gpu.launches() - n0 == 3          # H phase, E phase + source, NTFF sample
+    assert gpu.launches() - n0 == 4          # H phase, E phase + source, NTFF sample, device clock tick
+    gpu.finish()
+    monkeypatch.setenv("MPIFDTD_DEFER_STEPS", "0")      # every update() handed over on its own: no clock
+    gpu = B.Plugin("MIE_CYLINDER", "TM_UPML_2D", 96, steps=10, h_u_nm=20)
+    n0 = gpu.launches()
+    gpu.step(1)
+    assert gpu.launches() - n0 == 3
     gpu.finish()
 
 
