@@ -44,8 +44,14 @@ def main():
         steps = 2000 if n <= 512 else 1000
         rows = {}
         for label, max_batch in (("one_angle_at_a_time", 1), ("batched", 0)):
-            count, dt = sweep(n, steps, start, end, delta, max_batch)
-            rows[label] = {"seconds": dt, "simulations": count,
+            # wall clock with host-side parts (eps maps, text formatting threads): the box's host
+            # cores are shared with other jobs, so take the best of three and keep all samples
+            samples = []
+            for _ in range(3):
+                count, dt = sweep(n, steps, start, end, delta, max_batch)
+                samples.append(dt)
+            dt = min(samples)
+            rows[label] = {"seconds": dt, "samples_s": samples, "simulations": count,
                            "gcell_updates_per_s": count * n * n * steps / dt / 1e9}
         print(json.dumps({"workload": "MieCylinder TM_UPML %dx%d, %d steps, angles %d..%d step %d, "
                                       "far-field files for every angle" % (n, n, steps, start, end, delta),
