@@ -32,8 +32,6 @@ namespace {
 
 using namespace upml;
 
-constexpr int kMaxWarpsPerBlock = 16;
-
 struct FusedView {
   UpmlView u;
   int n_strips, n_bands, band_h;
