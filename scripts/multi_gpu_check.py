@@ -19,6 +19,7 @@ npx = int(sys.argv[2]) if len(sys.argv) > 2 else 160
 npy = int(sys.argv[3]) if len(sys.argv) > 3 else 240
 steps = int(sys.argv[4]) if len(sys.argv) > 4 else 600
 halo = sys.argv[5] if len(sys.argv) > 5 else "nccl"          # "nccl" or "peer" (direct NVLink stores)
+precision = sys.argv[6] if len(sys.argv) > 6 else "f64"     # "f32": the optional single-precision path
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -26,7 +27,7 @@ stream = torch.cuda.Stream()
 with torch.cuda.stream(stream):
     comm = TorchHaloComm(npx, torch.device("cuda", local))
     run = SlabRun("MIE_CYLINDER", solver, npx, npy, steps, rank=rank, world=world, device=local, comm=comm,
-                  h_u_nm=20, angle_deg=20)
+                  h_u_nm=20, angle_deg=20, precision=precision)
     run.engine.set_stream(stream.cuda_stream)
     run.attach_halo_buffers(*comm.pointers())
     if halo == "peer":
@@ -48,7 +49,7 @@ with torch.cuda.stream(stream):
     ok = True
     if rank == 0:
         single = SlabRun("MIE_CYLINDER", solver, npx, npy, steps, rank=0, world=1, device=local, h_u_nm=20,
-                         angle_deg=20)
+                         angle_deg=20, precision=precision)
         single.engine.set_stream(stream.cuda_stream)
         for _ in range(steps):
             single.step()
