@@ -373,7 +373,9 @@ enum {
                                   k+1 with the E phase of band k, so the E phase finds Bx/By (Bz) in
                                   L2: 232 instead of 264 B/cell of DRAM traffic (TM).  Bit-identical
                                   to the two-kernel step.  0: two kernels.                        */
-  B200FDTD_OPT_PIPE_BAND_ROWS = 6 /* rows per band of the pipelined step (default 4)             */
+  B200FDTD_OPT_PIPE_BAND_ROWS = 6, /* rows per band of the pipelined step (default 4)            */
+  B200FDTD_OPT_F32_PAIRS = 7   /* single-precision engines: 1 (default) two cells per thread with
+                                  128-bit accesses, 0 the one-cell-per-thread kernels; identical bits */
 };
 int b200fdtd_set_option(b200fdtd_engine *e, int32_t option, int32_t value);
 

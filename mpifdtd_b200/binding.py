@@ -25,7 +25,7 @@ SOLVERS = dict(TM_2D=0, TE_2D=1, TM_UPML_2D=2, TE_UPML_2D=3,
                MPI_TM_UPML_2D=4, MPI_TE_UPML_2D=5, NS_TM_2D=6, NS_TE_2D=7)
 D_X, D_Y, D_XY = 0, 1, 2
 UPML_TABS = 6
-OPT_FUSED, OPT_STORE_H, OPT_BAND_ROWS, OPT_FUSED_SHAPE, OPT_PIPELINED, OPT_PIPE_BAND_ROWS = 1, 2, 3, 4, 5, 6
+OPT_FUSED, OPT_STORE_H, OPT_BAND_ROWS, OPT_FUSED_SHAPE, OPT_PIPELINED, OPT_PIPE_BAND_ROWS, OPT_F32_PAIRS = 1, 2, 3, 4, 5, 6, 7
 
 
 class FieldInfo(C.Structure):

@@ -168,6 +168,8 @@ int b200fdtd_create(const b200fdtd_grid *grid, b200fdtd_engine **out)
   if (const char *v = getenv("B200FDTD_FUSED"))
     e->use_fused = atoi(v) != 0 && grid->kind == B200FDTD_TM_UPML && !e->fp32 && n_batch == 1;
   if (const char *v = getenv("B200FDTD_STORE_H")) e->store_h = atoi(v) != 0;
+  e->f32_pairs = true;
+  if (const char *v = getenv("B200FDTD_F32_PAIRS")) e->f32_pairs = atoi(v) != 0;
   e->use_pipelined = false;
   if (const char *v = getenv("B200FDTD_PIPELINED")) e->use_pipelined = atoi(v) != 0;
   if (const char *v = getenv("B200FDTD_PIPE_BAND_ROWS")) e->pipe.band_rows = atoi(v);
@@ -604,6 +606,9 @@ int b200fdtd_set_option(b200fdtd_engine *e, int32_t option, int32_t value)
     if (value && !kind_is_upml(e->g.kind))
       return b200_fail(B200FDTD_ERR_ARG, "the pipelined step serves the UPML kinds");
     e->use_pipelined = value != 0;
+    return B200FDTD_OK;
+  case B200FDTD_OPT_F32_PAIRS:
+    e->f32_pairs = value != 0;
     return B200FDTD_OK;
   case B200FDTD_OPT_PIPE_BAND_ROWS:
     if (value < 1) return b200_fail(B200FDTD_ERR_ARG, "band rows must be >= 1");

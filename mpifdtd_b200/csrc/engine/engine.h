@@ -107,6 +107,7 @@ struct b200fdtd_engine {
   void *graph_exec;         // cudaGraphExec_t of `graph_steps` steps, or nullptr
   int graph_steps;
   unsigned graph_epoch, graph_built_epoch;   // bumped by anything that changes what a step launches
+  bool f32_pairs;           // single precision: two cells per thread (default on)
   bool use_pipelined;       // b200fdtd_step runs the pipelined persistent kernel (serial UPML kinds, one slab)
   bool use_fused;           // b200fdtd_step runs the one-pass kernel (serial TM kind)
   bool store_h;             // the fused kernel also writes Hx/Hy (264 instead of 232 B/cell)

@@ -16,6 +16,7 @@
 // gcc lowers it).  One thread updates one cell; a warp covers 32 consecutive j
 // = 512 contiguous bytes per field, every access a 128-bit LDG/STG.
 #include <cstring>
+#include <type_traits>
 #include "upml_common.cuh"
 
 #ifndef B200_H_MIN_BLOCKS
@@ -57,6 +58,81 @@ __device__ __forceinline__ bool locate(const UpmlViewT<T> &v, int &r, int &c, si
 template <bool L2_ONLY, typename C>
 __device__ __forceinline__ C ld_b(const C *p) { return L2_ONLY ? __ldcg(p) : *p; }
 
+// ---- the arithmetic of one cell, shared by the one-cell-per-thread kernels, the pipelined
+// step and the two-cells-per-thread single-precision kernels.  Expression order is the
+// reference's (see the citations); compiled with -fmad=false.
+template <typename T, typename C = typename Cx<T>::type>
+__device__ __forceinline__ void tm_h_math(C ez, C ez_j1, C ez_i1, C mx_old, C bx_old, C my_old, C by_old, T c_mx,
+                                          T c_mxez, T num1, T num0, T c_bx1, T c_bx0, T c_by, T den, C &mx, C &bx,
+                                          C &my, C &by)
+{
+  // fdtdTM_upml.c:187-189 (C_BX == 1 exactly)
+  mx = c_mx * mx_old - c_mxez * (ez_j1 - ez);
+  bx = (bx_old + c_bx1 * mx) - c_bx0 * mx_old;
+  // fdtdTM_upml.c:196-198 (C_MY == C_MYEZ == 1 exactly)
+  my = my_old - ((-ez_i1) + ez);
+  const T c_by1 = quotient_or_one(num1, den), c_by0 = quotient_or_one(num0, den);   // fdtdTM_upml.c:270-271
+  by = (c_by * by_old + c_by1 * my) - c_by0 * my_old;
+}
+
+template <typename T, typename C = typename Cx<T>::type>
+__device__ __forceinline__ void tm_e_math(const UpmlViewT<T> &v, int r, int c, size_t k0, C hy, C hy_i0, C hx, C hx_j0,
+                                          C jz_old, C dz_old, T eps, T c_jz, T c_jzh, T c_dz, T c_dzjz, C &jz, C &dz,
+                                          C &ez)
+{
+  // fdtdTM_upml.c:161-163 (C_DZJZ1 == C_DZJZ0 because sigma_z = 0)
+  jz = c_jz * jz_old + c_jzh * (((hy - hy_i0) - hx) + hx_j0);
+  dz = (c_dz * dz_old + c_dzjz * jz) - c_dzjz * jz_old;
+  ez = div_eps(dz, eps);              // fdtdTM_upml.c:175
+
+  if (eps != (T)1 && pulse_on(v, 0))       // field.c:248
+    ez = add_source(ez, pulse_term(pulse_of(v, 0), r - 1, v.j_base + c, (double)eps));
+  if (v.cw[0].enabled && eps != (T)1)          // mpiTM_UPML.c:370
+    ez = add_source(ez, cw_eps_term(v.cw[0], r - 1, v.j_base + c, (double)eps));
+  if ((long long)k0 == v.point_k)
+    ez = add_source(ez, make_double2(v.point_re, v.point_im));
+  if (v.line.enabled && r - 1 == v.line.i) {  // block-uniform: one grid row
+    const int j = v.j_base + c;
+    if (j >= v.line.j_lo && j <= v.line.j_hi) ez = add_source(ez, line_term(v.line, r - 1, j));
+  }
+}
+
+template <typename T, typename C = typename Cx<T>::type>
+__device__ __forceinline__ void te_h_math(C ey_i1, C ey, C ex_j1, C ex, C mz_old, C bz_old, T c_mz, T c_mze, T c_bz,
+                                          T c_bzmz, C &mz, C &bz)
+{
+  // fdtdTE_upml.c:299-301 (C_BZMZ1 == C_BZMZ0 because sigma_z = 0)
+  mz = c_mz * mz_old - c_mze * (((ey_i1 - ey) - ex_j1) + ex);
+  bz = (c_bz * bz_old + c_bzmz * mz) - c_bzmz * mz_old;
+}
+
+template <typename T, typename C = typename Cx<T>::type>
+__device__ __forceinline__ void te_e_math(const UpmlViewT<T> &v, int r, int c, size_t k0, C hz, C hz_j0, C hz_i0,
+                                          C jx_old, C dx_old, C jy_old, C dy_old, T eps_x, T eps_y, T c_jx, T c_jxhz,
+                                          T num1, T num0, T c_dx1, T c_dx0, T c_dy, T den, C &jx, C &dx, C &jy, C &dy,
+                                          C &ex, C &ey)
+{
+  // fdtdTE_upml.c:259-262 (C_DX == 1)
+  jx = c_jx * jx_old + c_jxhz * (hz - hz_j0);
+  dx = (dx_old + c_dx1 * jx) - c_dx0 * jx_old;
+  // fdtdTE_upml.c:269-271 (C_JY == C_JYHZ == 1)
+  jy = jy_old + ((-hz) + hz_i0);
+  const T c_dy1 = quotient_or_one(num1, den), c_dy0 = quotient_or_one(num0, den);   // fdtdTE_upml.c:402-403
+  dy = (c_dy * dy_old + c_dy1 * jy) - c_dy0 * jy_old;
+
+  ex = div_eps(dx, eps_x);            // fdtdTE_upml.c:283
+  ey = div_eps(dy, eps_y);            // fdtdTE_upml.c:289
+  const int i = r - 1, j = v.j_base + c;
+  if (eps_x != (T)1 && pulse_on(v, 0))     // fdtdTE_upml.c:186-187
+    ex = add_source(ex, pulse_term(pulse_of(v, 0), i, j, (double)eps_x));
+  if (eps_y != (T)1 && pulse_on(v, 1))     // fdtdTE_upml.c:188-189
+    ey = add_source(ey, pulse_term(pulse_of(v, 1), i, j, (double)eps_y));
+  if (v.cw[0].enabled && eps_x != (T)1) ex = add_source(ex, cw_eps_term(v.cw[0], i, j, (double)eps_x));
+  if (v.cw[1].enabled && eps_y != (T)1) ey = add_source(ey, cw_eps_term(v.cw[1], i, j, (double)eps_y));   // mpiTE_UPML.c:278
+  if ((long long)k0 == v.point_k)
+    ex = add_source(ex, make_double2(v.point_re, v.point_im));
+}
+
 // ------------------------------------------------------------------ TM -----
 // slots: 0 Ez 1 Jz 2 Dz 3 Hx 4 Mx 5 Bx 6 Hy 7 My 8 By
 // STORE_H = false: Hx/Hy are not written; the E phase recomputes them from Bx/By
@@ -86,13 +162,9 @@ __device__ __forceinline__ void tm_upml_h_cell(const UpmlViewT<T> &v, int r, int
   const T c_by   = v.ti[B200FDTD_TMI_C_BY * v.rows + r];
   const T den    = v.ti[B200FDTD_TMI_DEN_BYMY * v.rows + r];
 
-  // fdtdTM_upml.c:187-189 (C_BX == 1 exactly)
-  const C mx = c_mx * mx_old - c_mxez * (ez_j1 - ez);
-  const C bx = (bx_old + c_bx1 * mx) - c_bx0 * mx_old;
-  // fdtdTM_upml.c:196-198 (C_MY == C_MYEZ == 1 exactly)
-  const C my = my_old - ((-ez_i1) + ez);
-  const T c_by1 = quotient_or_one(num1, den), c_by0 = quotient_or_one(num0, den);   // fdtdTM_upml.c:270-271
-  const C by = (c_by * by_old + c_by1 * my) - c_by0 * my_old;
+  C mx, bx, my, by;
+  tm_h_math<T>(ez, ez_j1, ez_i1, mx_old, bx_old, my_old, by_old, c_mx, c_mxez, num1, num0, c_bx1, c_bx0, c_by, den,
+               mx, bx, my, by);
 
   v.f[B200FDTD_TM_MX][k] = mx;
   v.f[B200FDTD_TM_BX][k] = bx;
@@ -153,21 +225,8 @@ __device__ __forceinline__ void tm_upml_e_cell(const UpmlViewT<T> &v, int r, int
   const T c_dz   = v.tj[B200FDTD_TMJ_C_DZ * v.pitch + c];
   const T c_dzjz = v.tj[B200FDTD_TMJ_C_DZJZ * v.pitch + c];
 
-  // fdtdTM_upml.c:161-163 (C_DZJZ1 == C_DZJZ0 because sigma_z = 0)
-  const C jz = c_jz * jz_old + c_jzh * (((hy - hy_i0) - hx) + hx_j0);
-  const C dz = (c_dz * dz_old + c_dzjz * jz) - c_dzjz * jz_old;
-  C ez = div_eps(dz, eps);              // fdtdTM_upml.c:175
-
-  if (eps != (T)1 && pulse_on(v, 0))       // field.c:248
-    ez = add_source(ez, pulse_term(pulse_of(v, 0), r - 1, v.j_base + c, (double)eps));
-  if (v.cw[0].enabled && eps != (T)1)          // mpiTM_UPML.c:370
-    ez = add_source(ez, cw_eps_term(v.cw[0], r - 1, v.j_base + c, (double)eps));
-  if ((long long)k0 == v.point_k)
-    ez = add_source(ez, make_double2(v.point_re, v.point_im));
-  if (v.line.enabled && r - 1 == v.line.i) {  // block-uniform: one grid row
-    const int j = v.j_base + c;
-    if (j >= v.line.j_lo && j <= v.line.j_hi) ez = add_source(ez, line_term(v.line, r - 1, j));
-  }
+  C jz, dz, ez;
+  tm_e_math<T>(v, r, c, k0, hy, hy_i0, hx, hx_j0, jz_old, dz_old, eps, c_jz, c_jzh, c_dz, c_dzjz, jz, dz, ez);
 
   v.f[B200FDTD_TM_JZ][k] = jz;
   v.f[B200FDTD_TM_DZ][k] = dz;
@@ -207,9 +266,8 @@ __device__ __forceinline__ void te_upml_h_cell(const UpmlViewT<T> &v, int r, int
   const T c_bz   = v.tj[B200FDTD_TEJ_C_BZ * v.pitch + c];
   const T c_bzmz = v.tj[B200FDTD_TEJ_C_BZMZ * v.pitch + c];
 
-  // fdtdTE_upml.c:299-301 (C_BZMZ1 == C_BZMZ0 because sigma_z = 0)
-  const C mz = c_mz * mz_old - c_mze * (((ey_i1 - ey) - ex_j1) + ex);
-  const C bz = (c_bz * bz_old + c_bzmz * mz) - c_bzmz * mz_old;
+  C mz, bz;
+  te_h_math<T>(ey_i1, ey, ex_j1, ex, mz_old, bz_old, c_mz, c_mze, c_bz, c_bzmz, mz, bz);
 
   v.f[B200FDTD_TE_MZ][k] = mz;
   v.f[B200FDTD_TE_BZ][k] = bz;
@@ -260,25 +318,9 @@ __device__ __forceinline__ void te_upml_e_cell(const UpmlViewT<T> &v, int r, int
   const T c_dy   = v.ti[B200FDTD_TEI_C_DY * v.rows + r];
   const T den    = v.ti[B200FDTD_TEI_DEN_DYJY * v.rows + r];
 
-  // fdtdTE_upml.c:259-262 (C_DX == 1)
-  const C jx = c_jx * jx_old + c_jxhz * (hz - hz_j0);
-  const C dx = (dx_old + c_dx1 * jx) - c_dx0 * jx_old;
-  // fdtdTE_upml.c:269-271 (C_JY == C_JYHZ == 1)
-  const C jy = jy_old + ((-hz) + hz_i0);
-  const T c_dy1 = quotient_or_one(num1, den), c_dy0 = quotient_or_one(num0, den);   // fdtdTE_upml.c:402-403
-  const C dy = (c_dy * dy_old + c_dy1 * jy) - c_dy0 * jy_old;
-
-  C ex = div_eps(dx, eps_x);            // fdtdTE_upml.c:283
-  C ey = div_eps(dy, eps_y);            // fdtdTE_upml.c:289
-  const int i = r - 1, j = v.j_base + c;
-  if (eps_x != (T)1 && pulse_on(v, 0))     // fdtdTE_upml.c:186-187
-    ex = add_source(ex, pulse_term(pulse_of(v, 0), i, j, (double)eps_x));
-  if (eps_y != (T)1 && pulse_on(v, 1))     // fdtdTE_upml.c:188-189
-    ey = add_source(ey, pulse_term(pulse_of(v, 1), i, j, (double)eps_y));
-  if (v.cw[0].enabled && eps_x != (T)1) ex = add_source(ex, cw_eps_term(v.cw[0], i, j, (double)eps_x));
-  if (v.cw[1].enabled && eps_y != (T)1) ey = add_source(ey, cw_eps_term(v.cw[1], i, j, (double)eps_y));   // mpiTE_UPML.c:278
-  if ((long long)k0 == v.point_k)
-    ex = add_source(ex, make_double2(v.point_re, v.point_im));
+  C jx, dx, jy, dy, ex, ey;
+  te_e_math<T>(v, r, c, k0, hz, hz_j0, hz_i0, jx_old, dx_old, jy_old, dy_old, eps_x, eps_y, c_jx, c_jxhz, num1, num0,
+               c_dx1, c_dx0, c_dy, den, jx, dx, jy, dy, ex, ey);
 
   v.f[B200FDTD_TE_JX][k] = jx;
   v.f[B200FDTD_TE_DX][k] = dx;
@@ -297,6 +339,8 @@ __global__ void __launch_bounds__(kBlock, B200_TE_E_MIN_BLOCKS) te_upml_e_kernel
   if (!locate(v, r, c, k, k0)) return;
   te_upml_e_cell<T, FROM_B>(v, r, c, k, k0);
 }
+
+#include "upml_pairs_f32.cuh"
 
 // ------------------------------------------------------------------ pipelined step -----
 // One persistent kernel per time step.  The grid is cut into bands of `band_rows` rows; a task
@@ -516,10 +560,30 @@ int b200_selftest_division(double divisor, unsigned long long samples, unsigned 
   return B200FDTD_OK;
 }
 
+// single precision, default forms: two cells per thread (upml_pairs_f32.cuh)
+static PairGeom pair_geom(const b200fdtd_engine *e)
+{
+  PairGeom g;
+  g.nbx2 = (e->c_hi - (e->c_lo & ~1) + 1 + 2 * kBlock - 1) / (2 * kBlock);
+  return g;
+}
+
 template <typename T>
 static int launch_h(b200fdtd_engine *e, const b200fdtd_step_args *a)
 {
   const UpmlViewT<T> v = make_view_t<T>(e, a);
+  if constexpr (std::is_same<T, float>::value) {
+    if (e->f32_pairs && !e->store_h) {
+      const PairGeom g = pair_geom(e);
+      const dim3 grid((unsigned)((long long)g.nbx2 * (e->r_hi - e->r_lo + 1)), (unsigned)e->n_batch);
+      if (is_tm(e->g.kind)) tm_upml_h_pair_kernel<<<grid, kBlock, 0, e->stream>>>(v, g);
+      else                  te_upml_h_pair_kernel<<<grid, kBlock, 0, e->stream>>>(v, g);
+      e->h_stale = true;
+      e->launches++;
+      B200_CUDA(cudaGetLastError());
+      return B200FDTD_OK;
+    }
+  }
   const long long nblk = (long long)v.nbx * (e->r_hi - e->r_lo + 1);
   if (is_tm(e->g.kind)) {
     if (e->store_h) tm_upml_h_kernel<T, true><<<dim3((unsigned)nblk, (unsigned)e->n_batch), kBlock, 0, e->stream>>>(v);
@@ -538,6 +602,17 @@ template <typename T>
 static int launch_e(b200fdtd_engine *e, const b200fdtd_step_args *a)
 {
   const UpmlViewT<T> v = make_view_t<T>(e, a);
+  if constexpr (std::is_same<T, float>::value) {
+    if (e->f32_pairs && e->h_stale) {
+      const PairGeom g = pair_geom(e);
+      const dim3 grid((unsigned)((long long)g.nbx2 * (e->r_hi - e->r_lo + 1)), (unsigned)e->n_batch);
+      if (is_tm(e->g.kind)) tm_upml_e_pair_kernel<<<grid, kBlock, 0, e->stream>>>(v, g);
+      else                  te_upml_e_pair_kernel<<<grid, kBlock, 0, e->stream>>>(v, g);
+      e->launches++;
+      B200_CUDA(cudaGetLastError());
+      return B200FDTD_OK;
+    }
+  }
   const long long nblk = (long long)v.nbx * (e->r_hi - e->r_lo + 1);
   if (is_tm(e->g.kind)) {
     if (e->h_stale) tm_upml_e_kernel<T, true><<<dim3((unsigned)nblk, (unsigned)e->n_batch), kBlock, 0, e->stream>>>(v);

@@ -88,3 +88,26 @@ def test_f32_rejected_where_not_built(plugin_lib):
     assert plugin_lib.b200fdtd_create(C.byref(grid), C.byref(h)) == 1
     grid = B.Grid(2, 64, 64, 10, 0, 64, 1, 62, 1, 62, -1, 7, B.MU_0_S)      # unknown precision
     assert plugin_lib.b200fdtd_create(C.byref(grid), C.byref(h)) == 1
+
+
+@pytest.mark.parametrize("solver,model,npx,npy,batch", [
+    ("TM_UPML_2D", "MIE_CYLINDER", 120, 120, None), ("TE_UPML_2D", "MIE_CYLINDER", 120, 121, None),
+    ("TM_UPML_2D", "ZIGZAG", 97, 301, None), ("TE_UPML_2D", "LAYER", 301, 98, None),
+    ("TM_UPML_2D", "MIE_CYLINDER", 110, 113, [0, 30, 65])])
+def test_f32_pair_kernels_are_bit_identical_to_one_cell_kernels(plugin_lib, monkeypatch, solver, model, npx, npy, batch):
+    """Two cells per thread with 128-bit accesses (upml_pairs_f32.cuh) share the arithmetic of the
+    one-cell kernels: every array must agree bit for bit, odd and even widths alike."""
+    steps = 540
+    results = {}
+    for pairs in ("0", "1"):
+        monkeypatch.setenv("B200FDTD_F32_PAIRS", pairs)
+        monkeypatch.setenv("MPIFDTD_DEFER_STEPS", "0")
+        gpu = B.Plugin(model, solver, npx, npy, steps=steps, h_u_nm=20, angle_deg=25, precision="f32", angle_batch=batch)
+        gpu.run()
+        if batch:
+            gpu.select_angle(2)
+        results[pairs] = [gpu.any_field(s) for s in range(9)] + [gpu.ntff_uw(s, project=(s == 0)) for s in range(3)]
+        gpu.finish()
+    assert np.abs(results["0"][0]).max() > 1e-4
+    for n, (a, b) in enumerate(zip(results["0"], results["1"])):
+        assert np.array_equal(a.view(np.float64), b.view(np.float64)), n
