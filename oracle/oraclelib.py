@@ -1,5 +1,6 @@
 """TEST INFRASTRUCTURE ONLY -- ctypes driver for oracle/liboracle.so, the plain-C
-restatement of the reference's serial UPML path (oracle/fdtd_oracle.c).
+restatement of the reference's serial UPML path (oracle/fdtd_oracle.c) and of its four
+split-field solvers (oracle/split_oracle.c).
 
 Used by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg as the
 checker; never by the product.
@@ -30,8 +31,8 @@ def build():
 def lib():
     global _lib
     if _lib is None:
-        src = os.path.join(HERE, "fdtd_oracle.c")
-        if not os.path.exists(LIB) or os.path.getmtime(LIB) < os.path.getmtime(src):
+        srcs = [os.path.join(HERE, "fdtd_oracle.c"), os.path.join(HERE, "split_oracle.c")]
+        if not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(p) for p in srcs):
             build()
         L = C.CDLL(LIB)
         L.oracle_create.restype = C.c_void_p
@@ -53,6 +54,14 @@ def lib():
         L.oracle_frequency_tm.argtypes = [C.c_void_p, C.c_void_p]
         L.oracle_time.restype = C.c_double
         L.oracle_time.argtypes = [C.c_void_p]
+        L.split_oracle_create.restype = C.c_void_p
+        L.split_oracle_create.argtypes = [C.c_int] * 4 + [C.c_double, C.c_double] + [C.c_void_p] * 3
+        L.split_oracle_destroy.argtypes = [C.c_void_p]
+        L.split_oracle_step.argtypes = [C.c_void_p, C.c_int]
+        L.split_oracle_field.restype = C.c_void_p
+        L.split_oracle_field.argtypes = [C.c_void_p, C.c_int]
+        L.split_oracle_coef.restype = C.c_void_p
+        L.split_oracle_coef.argtypes = [C.c_void_p, C.c_int]
         _lib = L
     return _lib
 
@@ -118,3 +127,43 @@ def fft(values):
     a = np.ascontiguousarray(values, dtype=np.complex128).copy()
     lib().oracle_fft(a.ctypes.data, a.size)
     return a
+
+
+SPLIT_FIELDS = {0: ["Ez", "Ezx", "Ezy", "Hx", "Hy"], 6: ["Ez", "Ezx", "Ezy", "Hx", "Hy"],
+                1: ["Hz", "Hzx", "Hzy", "Ex", "Ey"], 7: ["Hz", "Hzx", "Hzy", "Ex", "Ey"]}
+SPLIT_COEFS = {0: ["C_EZX", "C_EZXLX", "C_EZY", "C_EZYLY", "C_HX", "C_HXLY", "C_HY", "C_HYLX"],
+               1: ["C_EX", "C_EXLY", "C_EY", "C_EYLX", "C_HZX", "C_HZXLX", "C_HZY", "C_HZYLY"]}
+SPLIT_COEFS[6], SPLIT_COEFS[7] = SPLIT_COEFS[0], SPLIT_COEFS[1]
+
+
+class SplitOracleSim:
+    """oracle/split_oracle.c: solver ids 0 (Yee TM + Berenger), 1 (TE), 6 (NS-FDTD TM), 7 (NS TE).
+    eps_maps: the solver's three permittivity maps in the reference's order (TM kinds EPS_EZ,
+    EPS_HX, EPS_HY; TE kinds EPS_EX, EPS_EY, EPS_HZ), each [n_px, n_py]."""
+
+    def __init__(self, kind, n_px, n_py, eps_maps, h_u_nm=10, pml=10, lambda_nm=500, angle_deg=0):
+        self.L = lib()
+        self.kind, self.n_px, self.n_py = kind, n_px, n_py
+        maps = [np.ascontiguousarray(m, dtype=np.float64) for m in eps_maps]
+        assert len(maps) == 3 and all(m.shape == (n_px, n_py) for m in maps)
+        # field_toCellUnit: nm / h_u in double (field.c:76)
+        self.h = self.L.split_oracle_create(kind, n_px, n_py, pml, lambda_nm / float(h_u_nm), float(angle_deg),
+                                            maps[0].ctypes.data, maps[1].ctypes.data, maps[2].ctypes.data)
+
+    def step(self, n=1):
+        self.L.split_oracle_step(self.h, n)
+
+    def field(self, name):
+        n = self.n_px * self.n_py
+        buf = (C.c_double * (2 * n)).from_address(self.L.split_oracle_field(self.h, SPLIT_FIELDS[self.kind].index(name)))
+        return np.frombuffer(buf, dtype=np.complex128).reshape(self.n_px, self.n_py).copy()
+
+    def coef(self, name):
+        n = self.n_px * self.n_py
+        buf = (C.c_double * n).from_address(self.L.split_oracle_coef(self.h, SPLIT_COEFS[self.kind].index(name)))
+        return np.frombuffer(buf, dtype=np.float64).reshape(self.n_px, self.n_py).copy()
+
+    def close(self):
+        if self.h:
+            self.L.split_oracle_destroy(self.h)
+            self.h = None

@@ -95,6 +95,31 @@ def test_split_solver_vs_live_reference(plugin_lib, kind, model, in_tmp_cwd, spl
     gpu.finish()
 
 
+@pytest.mark.parametrize("kind,model,angle", [(0, "LAYER", 20), (1, "MIE_CYLINDER", 0), (6, "ZIGZAG", 15),
+                                              (7, "LAYER", 40), (7, "MORPHO_SCALE", 0)])
+def test_split_solver_vs_c_oracle(plugin_lib, oracle, kind, model, angle, in_tmp_cwd, split_form):
+    """The CUDA path against oracle/split_oracle.c (itself bit-exact against the reference,
+    tests/test_oracle_cpu.py), fed with the eps maps the plugin's host code built."""
+    import ctypes as C
+    npx, npy, steps, lam = 200, 216, 300, 633
+    gpu = B.Plugin(model, kind, npx, npy, steps=steps, lambda_nm=lam, angle_deg=angle)
+    L = gpu.L
+    L.mpifdtd_split_prepare_host(kind)                 # test hook: all three eps maps on the host
+
+    def eps_map(slot):
+        buf = (C.c_double * (npx * npy)).from_address(L.mpifdtd_split_dense(kind, 10 + slot))
+        return np.frombuffer(buf, dtype=np.float64).reshape(npx, npy).copy()
+
+    cpu = oracle.SplitOracleSim(kind, npx, npy, [eps_map(m) for m in range(3)], lambda_nm=lam, angle_deg=angle)
+    gpu.run()
+    cpu.step(steps)
+    assert np.abs(cpu.field(FIELDS[kind][0])).max() > 1e-3
+    for f in FIELDS[kind]:
+        assert rel_err(gpu.field(f), cpu.field(f)) <= TOL_FIELD, f
+    gpu.finish()
+    cpu.close()
+
+
 # ---------------------------------------------------------------- MPI-variant ids (4, 5)
 MPI_FIELDS = {4: ["Ez", "Hx", "Hy", "Jz", "Dz", "Mx", "Bx", "My", "By"],
               5: ["Ex", "Ey", "Hz", "Jx", "Dx", "Jy", "Dy", "Mz", "Bz"]}

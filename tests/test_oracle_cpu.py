@@ -1,11 +1,13 @@
-"""Pins oracle/fdtd_oracle.c (the plain-C restatement) to the unmodified reference:
+"""Pins oracle/fdtd_oracle.c and oracle/split_oracle.c (the plain-C restatements) to the unmodified reference:
 golden vectors recorded from the reference (tests/golden/*.npz) and, when present,
 the reference library itself.  On the machine that generated the goldens the match
 is bit-exact; the asserted tolerance leaves room for a different host libm."""
+import os
+
 import numpy as np
 import pytest
 
-from helpers import ANGLE_ROWS, LAMBDA_ROWS, bit_equal, golden, rel_err
+from helpers import ANGLE_ROWS, GOLDEN, LAMBDA_ROWS, bit_equal, golden, rel_err
 
 RUNS = ["mie_tm_upml_88x96", "mie_te_upml_88x96", "zigzag_tm_upml_72x120_a30", "layer_te_upml_80x110_a45"]
 
@@ -64,3 +66,46 @@ def test_oracle_vs_live_reference(oracle):
         assert bit_equal(sim.uw(slot).view(np.float64), ref.ntff_uw(name).view(np.float64)), name
     assert bit_equal(sim.far_field(), ref.finish())
     sim.close()
+
+
+# ---------------------------------------------------------------- split-field solvers (ids 0, 1, 6, 7)
+EPS_NAMES = {0: ["EPS_EZ", "EPS_HX", "EPS_HY"], 1: ["EPS_EX", "EPS_EY", "EPS_HZ"]}
+EPS_NAMES[6], EPS_NAMES[7] = EPS_NAMES[0], EPS_NAMES[1]
+
+
+@pytest.mark.parametrize("kind,model,angle", [(0, "MIE_CYLINDER", 0), (1, "LAYER", 15), (6, "ZIGZAG", 30),
+                                              (7, "MIE_CYLINDER", 15), (7, "LAYER", 0), (6, "MORPHO_SCALE", 0)])
+def test_split_oracle_is_bit_exact_vs_live_reference(oracle, kind, model, angle):
+    """oracle/split_oracle.c against the unmodified reference: the eight coefficient arrays and
+    all five fields after 260 steps, bit for bit (same host libm, same expression order)."""
+    from oracle import reflib
+    if not reflib.available():
+        pytest.skip("oracle/_ref/libref.so not present")
+    npx, npy, steps, lam = 96, 110, 260, 633
+    ref = reflib.RefSim(model, kind, npx, npy, steps=steps, lambda_nm=lam, angle_deg=angle)
+    eps = [ref.coef(n) for n in EPS_NAMES[kind]]
+    cpu = oracle.SplitOracleSim(kind, npx, npy, eps, lambda_nm=lam, angle_deg=angle)
+    inner = (slice(1, -1), slice(1, -1)) if kind == 7 else (slice(None), slice(None))
+    for n in oracle.SPLIT_COEFS[kind]:
+        assert bit_equal(np.ascontiguousarray(cpu.coef(n)[inner]), np.ascontiguousarray(ref.coef(n)[inner])), n
+    ref.run()
+    cpu.step(steps)
+    assert np.abs(ref.field(oracle.SPLIT_FIELDS[kind][0])).max() > 1e-3
+    for f in oracle.SPLIT_FIELDS[kind]:
+        assert bit_equal(cpu.field(f), ref.field(f)), f
+    cpu.close()
+
+
+@pytest.mark.parametrize("kind", [0, 1, 6, 7])
+def test_split_oracle_vs_reference_recorded_snapshots(oracle, kind):
+    g = np.load(os.path.join(GOLDEN, "split_kind%d.npz" % kind))
+    npx, npy, hu, steps, lam, angle = (int(v) for v in g["meta"][:6])
+    cpu = oracle.SplitOracleSim(kind, npx, npy, [g[n] for n in EPS_NAMES[kind]], h_u_nm=hu, lambda_nm=lam,
+                                angle_deg=angle)
+    cpu.step(steps // 2)
+    for f in oracle.SPLIT_FIELDS[kind]:
+        assert rel_err(cpu.field(f), g["mid_" + f]) <= 1e-13, ("mid", f)
+    cpu.step(steps - steps // 2)
+    for f in oracle.SPLIT_FIELDS[kind]:
+        assert rel_err(cpu.field(f), g["end_" + f]) <= 1e-13, ("end", f)
+    cpu.close()
