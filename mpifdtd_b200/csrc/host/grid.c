@@ -13,6 +13,8 @@
 #include <string.h>
 #include "mpifdtd_plugin.h"
 
+extern void mpifdtd_flush_pending_steps(void);     /* upml_shim.c: deferred update() calls */
+
 #ifndef M_PI
 #define M_PI 3.1415926535897932384626433832795
 #endif
@@ -93,6 +95,7 @@ bool field_isFinish(void) { return G.now >= G.last; }             /* field.c:317
 
 void field_setWaveAngle(int deg)                                  /* field.c:39  */
 {
+  mpifdtd_flush_pending_steps();    /* deferred update() calls were made under the old angle */
   G.phys.angle_deg = deg;
   G.wave.Angle_deg = deg;
 }

@@ -21,6 +21,8 @@ extern void mpifdtd_ntff_direction_cosines(int n_angles, int is_tm, double *cos_
 extern double complex *mpifdtd_fft_twiddles(int n);
 
 /* upml_shim.c */
+/* hands every update() the serial UPML solvers have only counted so far to the engine */
+extern void mpifdtd_flush_pending_steps(void);
 #include "b200fdtd.h"
 extern void mpifdtd_upml_step_args(int kind, int point_source, b200fdtd_step_args *a);
 extern void mpifdtd_upml_far_field(b200fdtd_engine *engine, int kind, int project, double *table);

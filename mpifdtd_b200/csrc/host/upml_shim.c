@@ -527,6 +527,12 @@ static void flush_pending(UpmlSolver *s)
   die_on(b200fdtd_run_steps(s->engine, s->pending_from, n), "b200fdtd_run_steps");
 }
 
+void mpifdtd_flush_pending_steps(void)
+{
+  flush_pending(&tm_solver);
+  flush_pending(&te_solver);
+}
+
 static void solver_update(UpmlSolver *s)
 {
   if (s->defer) {
