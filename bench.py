@@ -24,6 +24,12 @@ needed between iterations.
              MEASURED_PEAKS.json hbm_gbs.  `e_phase` is the other kernel (120 B/cell);
              `step` carries the contract figure of SURVEY 8(d): 264 B/cell-update x rate,
              which is exactly what the two kernels move.
+  lean_interior
+             the same K steps with B200FDTD_OPT_LEAN_INTERIOR (opt-in tolerance form: cells
+             outside the absorbing frame advance B / D directly, 168 instead of 264 B per TM
+             cell-update; fields within 1e-12 of the reference instead of bit-identical).
+             Reported BESIDE `value`, which stays the reference's arithmetic in every cell;
+             `--lean` makes it the measured form of the whole line instead.
   cpu_baseline / --impl reference
              the UNMODIFIED reference (oracle/_ref/libref.so, built from
              /root/reference) on the host cores, one serial solver instance per
@@ -285,6 +291,8 @@ def gpu_arm(args):
         run = SlabRun(args.model, args.solver, n_px, n_py, total_steps, rank=rank, world=world,
                       device=local_rank, comm=comm, precision=args.precision)
         run.engine.set_stream(stream.cuda_stream)
+        if args.lean:
+            run.engine.set_option(B.OPT_LEAN_INTERIOR, 1)
         if comm is not None:
             run.attach_halo_buffers(*comm.pointers())
             if args.halo == "peer":
@@ -333,6 +341,39 @@ def gpu_arm(args):
         ms_e = run.engine.timer_stop() / reps
         barrier()
 
+        # ---- the opt-in lean-interior form, same state, same K steps (reported beside `value`)
+        lean = None
+        if not args.lean and not args.no_lean_leg:
+            run.engine.zero()
+            run.L.field_reset()
+            run.engine.set_option(B.OPT_LEAN_INTERIOR, 1)
+            barrier()
+            for _ in range(W):
+                run.step()
+            barrier()
+            run.engine.timer_start()
+            for _ in range(K):
+                run.step()
+            run.project()
+            t = torch.tensor([run.engine.timer_stop()], dtype=torch.float64, device="cuda")
+            if dist is not None:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_lean = float(t.item())
+            run.engine.phase_h(run.args); run.engine.sync()
+            run.engine.timer_start()
+            for _ in range(reps):
+                run.engine.phase_h(run.args)
+            ms_h_lean = run.engine.timer_stop() / reps
+            run.engine.phase_e(run.args); run.engine.sync()
+            run.engine.timer_start()
+            for _ in range(reps):
+                run.engine.phase_e(run.args)
+            ms_e_lean = run.engine.timer_stop() / reps
+            run.engine.sync()
+            run.engine.set_option(B.OPT_LEAN_INTERIOR, 0)
+            barrier()
+            lean = (ms_lean, ms_h_lean, ms_e_lean)
+
         # ---- e2e: host buffers inside the timed region ------------------------------
         run.engine.zero()
         run.L.field_reset()
@@ -363,14 +404,26 @@ def gpu_arm(args):
         # TE: H phase reads Ex,Ey,Mz,Bz (64) + writes Mz,Bz (32); E phase reads Bz,Jx,Dx,Jy,Dy (80) +
         # eps x2 (16) + writes Jx,Dx,Jy,Dy,Ex,Ey (96); step = SURVEY 8(d)'s 288 B
         bytes_h, bytes_e, bytes_step = (BYTES_H_TM, BYTES_E_TM, BYTES_STEP_TM) if tm else (96, 192, 288)
+        # lean interior: H reads Ez,Bx,By + writes Bx,By (TE: Ex,Ey,Bz + Bz); E reads Bx,By,Dz,eps +
+        # writes Dz,Ez (TE: Bz,Dx,Dy,2 eps + Dx,Dy,Ex,Ey); the 10-cell frame adds < 0.3 % at 16384^2
+        lean_h, lean_e = (80, 88) if tm else (64, 128)
+        if args.lean:
+            bytes_h, bytes_e = lean_h, lean_e
         if args.precision == "f32":     # complex64 fields, f32 eps: every array element is half as wide
             bytes_h, bytes_e, bytes_step = bytes_h // 2, bytes_e // 2, bytes_step // 2
+            lean_h, lean_e = lean_h // 2, lean_e // 2
         kname = "tm" if tm else "te"
         ach_h = bytes_h * cells_rank / (ms_h * 1e-3) / 1e9
         ach_e = bytes_e * cells_rank / (ms_e * 1e-3) / 1e9
         step_gbs = bytes_step * (value / world) * 1e9 / 1e9
-        traffic, traffic_src = (ncu_traffic(kname + "_upml_h_kernel<0>", cells_rank) if args.precision == "f64"
-                                else (None, None))
+        # ncu prints the kernel as <double, STORE_H, LEAN>: "<0,0>" default form, "<0,1>" lean
+        traffic, traffic_src = None, None
+        if args.precision == "f64":
+            for tag in (["0,1"] if args.lean else ["0,0", "0"]):    # "<0>": captures older than the LEAN parameter
+                traffic, traffic_src = ncu_traffic(kname + "_upml_h_kernel<%s>" % tag, cells_rank)
+                if traffic is not None:
+                    break
+        lean_tag = ", LEAN=true" if args.lean else ""
         line = {
             "metric": "Gcell-updates/s", "value": value, "unit": "Gcell-updates/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_max / K,
@@ -379,12 +432,12 @@ def gpu_arm(args):
             "config": workload_config(world, n=args.n, solver=args.solver, model=args.model, strong=args.strong,
                                       halo={"peer": "direct NVLink peer stores + device flags",
                                             "nccl": "NCCL send/recv"}[args.halo]),
-            "roofline": {"bound": "hbm", "kernel": kname + "_upml_h_kernel<STORE_H=false>", "achieved": ach_h,
+            "roofline": {"bound": "hbm", "kernel": kname + "_upml_h_kernel<STORE_H=false%s>" % lean_tag, "achieved": ach_h,
                          "peak": peak, "unit": "GB/s", "frac": ach_h / peak, "peak_source": peak_kind,
                          "traffic": traffic, "traffic_source": traffic_src,
                          "algorithmic_bytes_per_launch": bytes_h * cells_rank, "ms_per_launch": ms_h,
                          "algorithmic_bytes_per_cell": bytes_h,
-                         "e_phase": {"kernel": kname + "_upml_e_kernel<FROM_B=true>", "achieved": ach_e,
+                         "e_phase": {"kernel": kname + "_upml_e_kernel<FROM_B=true%s>" % lean_tag, "achieved": ach_e,
                                      "frac": ach_e / peak, "ms_per_launch": ms_e,
                                      "algorithmic_bytes_per_cell": bytes_e},
                          "step": {"algorithmic_bytes_per_cell_update": bytes_step,
@@ -399,6 +452,30 @@ def gpu_arm(args):
             "clocks": clocks,
             "device_bytes": run.engine.device_bytes(),
         }
+        if args.lean:
+            line["config"]["form"] = ("lean interior (B200FDTD_OPT_LEAN_INTERIOR): tolerance form, fields within "
+                                      "1e-12 of the reference; moves %d B per cell-update" % (bytes_h + bytes_e))
+            line["roofline"]["step"]["moved_bytes_per_cell_update"] = bytes_h + bytes_e
+            line["roofline"]["step"]["moved"] = (bytes_h + bytes_e) * (value / world)
+            line["roofline"]["step"]["moved_frac"] = (bytes_h + bytes_e) * (value / world) / peak
+        if lean is not None:
+            ms_lean, ms_h_lean, ms_e_lean = lean
+            v_lean = cells * K / (ms_lean * 1e-3) / 1e9
+            moved = (lean_h + lean_e) * (v_lean / world)
+            line["lean_interior"] = {
+                "value": v_lean, "unit": "Gcell-updates/s", "ms_per_step": ms_lean / K,
+                "speedup_vs_value": v_lean / value,
+                "note": "opt-in B200FDTD_OPT_LEAN_INTERIOR: cells outside the absorbing frame skip the M / J "
+                        "recurrences (all coefficients exactly 1 there); tolerance form, fields within 1e-12 of "
+                        "the reference (tests/test_gpu_lean.py); `value` above is the bit-exact default",
+                "moved_bytes_per_cell_update": lean_h + lean_e,
+                "moved": moved, "moved_frac": moved / peak,
+                "h_phase": {"ms_per_launch": ms_h_lean, "bytes_per_cell": lean_h,
+                            "achieved": lean_h * cells_rank / (ms_h_lean * 1e-3) / 1e9,
+                            "frac": lean_h * cells_rank / (ms_h_lean * 1e-3) / 1e9 / peak},
+                "e_phase": {"ms_per_launch": ms_e_lean, "bytes_per_cell": lean_e,
+                            "achieved": lean_e * cells_rank / (ms_e_lean * 1e-3) / 1e9,
+                            "frac": lean_e * cells_rank / (ms_e_lean * 1e-3) / 1e9 / peak}}
         print(json.dumps(line))
     run.close()
     if dist is not None:
@@ -428,6 +505,10 @@ def main():
     ap.add_argument("--precision", default="f64", choices=["f64", "f32"],
                     help="f64 is the reference's arithmetic and the BASELINE metric; f32 is the optional "
                          "single-precision path (own tolerance), reported for information only")
+    ap.add_argument("--lean", action="store_true",
+                    help="measure the whole line in the opt-in lean-interior form (tolerance form, not the "
+                         "bit-exact default)")
+    ap.add_argument("--no-lean-leg", action="store_true", help="skip the extra lean_interior measurement")
     ap.add_argument("--solver", default="TM_UPML_2D", choices=["TM_UPML_2D", "TE_UPML_2D"],
                     help="TM_UPML_2D is the BASELINE workload; TE_UPML_2D is reported for information")
     args = ap.parse_args()

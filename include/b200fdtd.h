@@ -374,10 +374,30 @@ enum {
                                   L2: 232 instead of 264 B/cell of DRAM traffic (TM).  Bit-identical
                                   to the two-kernel step.  0: two kernels.                        */
   B200FDTD_OPT_PIPE_BAND_ROWS = 6, /* rows per band of the pipelined step (default 4)            */
-  B200FDTD_OPT_F32_PAIRS = 7   /* single-precision engines: 1 (default) two cells per thread with
+  B200FDTD_OPT_F32_PAIRS = 7,  /* single-precision engines: 1 (default) two cells per thread with
                                   128-bit accesses, 0 the one-cell-per-thread kernels; identical bits */
+  B200FDTD_OPT_LEAN_INTERIOR = 8 /* UPML kinds, two-kernel step.  1: cells outside the absorbing frame
+                                  -- where every UPML coefficient of fdtdTM_upml.c:253-271 /
+                                  fdtdTE_upml.c:384-403 is exactly 1 -- advance B and D directly
+                                  (B' = B - curl E, D' = D + curl H) and skip the M / J recurrences,
+                                  which cancel there: 168 instead of 264 B per cell-update (TM), 192
+                                  instead of 288 (TE).  Mathematically the same update with fewer
+                                  roundings, so NOT bit-identical to the reference: fields agree to
+                                  ~1e-13 relative (tests: <= 1e-12, far field <= 1e-10).  The M / J
+                                  arrays then only mean something inside the frame.  0 (default): the
+                                  reference's arithmetic in every cell.                            */
 };
 int b200fdtd_set_option(b200fdtd_engine *e, int32_t option, int32_t value);
+
+/* The region OPT_LEAN_INTERIOR may treat as frame-free, from the 1-D coefficient tables alone
+ * (host arithmetic, no device needed): the longest run of i (rows) and of j (columns) around the
+ * grid centre whose table entries all hold their sigma == 0 values.  kind: a UPML kind (2-5);
+ * tab_i / tab_j as for b200fdtd_set_upml_tables ([B200FDTD_UPML_TABS][n_px] / [..][n_py]).
+ * out = { i_lo, i_hi, j_lo, j_hi } inclusive, an empty range as lo > hi. */
+int b200fdtd_upml_interior(int32_t kind, const double *tab_i, int32_t n_px, const double *tab_j, int32_t n_py,
+                           int32_t out[4]);
+/* what the engine uses (global i / j of this slab's share), {1,0,1,0} when the option is off */
+int b200fdtd_get_lean_extent(b200fdtd_engine *e, int32_t out[4]);
 
 /* Device self-test: the kernels replace `x / d` (d loop-invariant, e.g. MU_0_S) by a
  * reciprocal-multiply with an FMA correction that is claimed to be the identical,

@@ -26,6 +26,7 @@ SOLVERS = dict(TM_2D=0, TE_2D=1, TM_UPML_2D=2, TE_UPML_2D=3,
 D_X, D_Y, D_XY = 0, 1, 2
 UPML_TABS = 6
 OPT_FUSED, OPT_STORE_H, OPT_BAND_ROWS, OPT_FUSED_SHAPE, OPT_PIPELINED, OPT_PIPE_BAND_ROWS, OPT_F32_PAIRS = 1, 2, 3, 4, 5, 6, 7
+OPT_LEAN_INTERIOR = 8
 
 
 class FieldInfo(C.Structure):
@@ -202,6 +203,8 @@ def lib():
     L.b200fdtd_run_steps.argtypes = [vp, dbl, i32]
     L.b200fdtd_set_batch_sources.argtypes = [vp, vp]
     L.b200fdtd_struct_size.argtypes = [i32]
+    L.b200fdtd_upml_interior.argtypes = [i32, vp, i32, vp, i32, vp]
+    L.b200fdtd_get_lean_extent.argtypes = [vp, vp]
     L.mpifdtd_readConfig.argtypes = [C.c_char_p, vp]
     for name in ("fdtdTM_upml_getHx", "fdtdTM_upml_getHy", "fdtdTM_upml_getEz",
                  "fdtdTE_upml_getEx", "fdtdTE_upml_getEy", "fdtdTE_upml_getHz",
@@ -344,6 +347,13 @@ class Plugin:
         n = C.c_uint64(0)
         self.L.b200fdtd_launch_count(self.engine_handle(), C.byref(n))
         return n.value
+
+    def lean_extent(self):
+        """(i_lo, i_hi, j_lo, j_hi) of the cells B200FDTD_OPT_LEAN_INTERIOR treats as frame-free
+        (inclusive; lo > hi when the option is off)."""
+        out = (C.c_int32 * 4)()
+        check(self.L.b200fdtd_get_lean_extent(self.engine_handle(), out), "get_lean_extent")
+        return tuple(out)
 
     def finish(self, workdir=None):
         """simulator_finish(); returns the 321 x 360 table written to cwd."""

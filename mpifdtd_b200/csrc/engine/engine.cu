@@ -175,6 +175,10 @@ int b200fdtd_create(const b200fdtd_grid *grid, b200fdtd_engine **out)
   if (const char *v = getenv("B200FDTD_PIPE_BAND_ROWS")) e->pipe.band_rows = atoi(v);
   if (const char *v = getenv("B200FDTD_FUSED_SHAPE")) e->fused_variant = atoi(v);
   if (const char *v = getenv("B200FDTD_BAND_ROWS")) e->fused.band_h = atoi(v);
+  e->lean_interior = false;
+  if (const char *v = getenv("B200FDTD_LEAN_INTERIOR")) e->lean_interior = atoi(v) != 0 && kind_is_upml(grid->kind);
+  e->lean_r_lo = e->lean_c_lo = 1;
+  e->lean_r_hi = e->lean_c_hi = 0;
 
   // update extents clipped to this slab, in layout coordinates
   const int jl = grid->j_lo > grid->j0 ? grid->j_lo : grid->j0;
@@ -321,11 +325,91 @@ int b200fdtd_set_stream(b200fdtd_engine *e, void *cuda_stream)
   return B200FDTD_OK;
 }
 
+// Longest run around the middle of [0, n) on which every listed table holds `want`.
+static void run_around_centre(const double *tab, int n, const int *slots, const double *want, int n_slots,
+                              int32_t *lo, int32_t *hi)
+{
+  auto ok = [&](int x) {
+    for (int s = 0; s < n_slots; s++)
+      if (tab[(size_t)slots[s] * n + x] != want[s]) return false;
+    return true;
+  };
+  const int mid = n / 2;
+  *lo = 1; *hi = 0;
+  if (n < 1 || !ok(mid)) return;
+  int a = mid, b = mid;
+  while (a > 0 && ok(a - 1)) a--;
+  while (b < n - 1 && ok(b + 1)) b++;
+  *lo = a; *hi = b;
+}
+
+int b200fdtd_upml_interior(int32_t kind, const double *tab_i, int32_t n_px, const double *tab_j, int32_t n_py,
+                           int32_t out[4])
+{
+  if (!tab_i || !tab_j || !out || n_px < 1 || n_py < 1) return b200_fail(B200FDTD_ERR_ARG, "bad argument");
+  if (!kind_is_upml(kind)) return b200_fail(B200FDTD_ERR_ARG, "kind %d has no UPML tables", kind);
+  const bool tm = kind == B200FDTD_TM_UPML || kind == B200FDTD_MPI_TM_UPML;
+  // The two quotient coefficients (C_BYMY0/1, C_DYJY0/1) are num(j) / den(i): 1 where both hold
+  // the sigma == 0 value 2*eps0, which the centre of the grid defines.
+  const int den_slot = tm ? (int)B200FDTD_TMI_DEN_BYMY : (int)B200FDTD_TEI_DEN_DYJY;
+  const double two_eps = tab_i[(size_t)den_slot * n_px + n_px / 2];
+  if (tm) {
+    const int si[6] = { B200FDTD_TMI_C_JZ, B200FDTD_TMI_C_JZHXHY, B200FDTD_TMI_C_BXMX1, B200FDTD_TMI_C_BXMX0,
+                        B200FDTD_TMI_C_BY, B200FDTD_TMI_DEN_BYMY };
+    const double wi[6] = { 1, 1, 1, 1, 1, two_eps };
+    const int sj[6] = { B200FDTD_TMJ_C_DZ, B200FDTD_TMJ_C_DZJZ, B200FDTD_TMJ_C_MX, B200FDTD_TMJ_C_MXEZ,
+                        B200FDTD_TMJ_NUM_BYMY1, B200FDTD_TMJ_NUM_BYMY0 };
+    const double wj[6] = { 1, 1, 1, 1, two_eps, two_eps };
+    run_around_centre(tab_i, n_px, si, wi, 6, &out[0], &out[1]);
+    run_around_centre(tab_j, n_py, sj, wj, 6, &out[2], &out[3]);
+  } else {
+    const int si[6] = { B200FDTD_TEI_C_DXJX1, B200FDTD_TEI_C_DXJX0, B200FDTD_TEI_C_DY, B200FDTD_TEI_DEN_DYJY,
+                        B200FDTD_TEI_C_MZ, B200FDTD_TEI_C_MZEXEY };
+    const double wi[6] = { 1, 1, 1, two_eps, 1, 1 };
+    const int sj[6] = { B200FDTD_TEJ_C_JX, B200FDTD_TEJ_C_JXHZ, B200FDTD_TEJ_NUM_DYJY1, B200FDTD_TEJ_NUM_DYJY0,
+                        B200FDTD_TEJ_C_BZ, B200FDTD_TEJ_C_BZMZ };
+    const double wj[6] = { 1, 1, two_eps, two_eps, 1, 1 };
+    run_around_centre(tab_i, n_px, si, wi, 6, &out[0], &out[1]);
+    run_around_centre(tab_j, n_py, sj, wj, 6, &out[2], &out[3]);
+  }
+  if (out[0] > out[1] || out[2] > out[3]) { out[0] = out[2] = 1; out[1] = out[3] = 0; }
+  return B200FDTD_OK;
+}
+
+int b200fdtd_get_lean_extent(b200fdtd_engine *e, int32_t out[4])
+{
+  if (!e || !out) return b200_fail(B200FDTD_ERR_ARG, "NULL argument");
+  out[0] = out[2] = 1; out[1] = out[3] = 0;
+  if (e->lean_interior && e->lean_r_hi >= e->lean_r_lo && e->lean_c_hi >= e->lean_c_lo) {
+    out[0] = e->lean_r_lo - 1;  out[1] = e->lean_r_hi - 1;
+    out[2] = e->lean_c_lo - B200_JOFF + e->g.j0;  out[3] = e->lean_c_hi - B200_JOFF + e->g.j0;
+  }
+  return B200FDTD_OK;
+}
+
 int b200fdtd_set_upml_tables(b200fdtd_engine *e, const double *tab_i, const double *tab_j)
 {
   if (!e || !tab_i || !tab_j) return b200_fail(B200FDTD_ERR_ARG, "NULL argument");
   int rc = select_device(e); if (rc) return rc;
   const b200fdtd_grid &g = e->g;
+  {
+    // frame-free region of this slab, clipped to the cells the engine updates
+    int32_t x[4];
+    rc = b200fdtd_upml_interior(g.kind, tab_i, g.n_px, tab_j, g.n_py, x); if (rc) return rc;
+    e->lean_r_lo = e->lean_c_lo = 1;
+    e->lean_r_hi = e->lean_c_hi = 0;
+    if (x[0] <= x[1]) {
+      const int jl = x[2] > g.j0 ? x[2] : g.j0, jh = x[3] < g.j0 + g.nj - 1 ? x[3] : g.j0 + g.nj - 1;
+      const int r_lo = x[0] + 1 > e->r_lo ? x[0] + 1 : e->r_lo, r_hi = x[1] + 1 < e->r_hi ? x[1] + 1 : e->r_hi;
+      int c_lo = jl - g.j0 + B200_JOFF, c_hi = jh - g.j0 + B200_JOFF;
+      if (c_lo < e->c_lo) c_lo = e->c_lo;
+      if (c_hi > e->c_hi) c_hi = e->c_hi;
+      if (r_lo <= r_hi && c_lo <= c_hi) {
+        e->lean_r_lo = r_lo; e->lean_r_hi = r_hi; e->lean_c_lo = c_lo; e->lean_c_hi = c_hi;
+      }
+    }
+    e->graph_epoch++;
+  }
   // ghost rows/columns get the neutral coefficient 1 (never used by an update)
   std::vector<double> hi((size_t)B200FDTD_UPML_TABS * e->rows, 1.0);
   std::vector<double> hj((size_t)B200FDTD_UPML_TABS * e->pitch, 1.0);
@@ -615,6 +699,11 @@ int b200fdtd_set_option(b200fdtd_engine *e, int32_t option, int32_t value)
     B200_CUDA(cudaStreamSynchronize(e->stream));
     b200_pipe_release(e);
     e->pipe.band_rows = value;
+    return B200FDTD_OK;
+  case B200FDTD_OPT_LEAN_INTERIOR:
+    if (value && !kind_is_upml(e->g.kind))
+      return b200_fail(B200FDTD_ERR_ARG, "the lean interior form serves the UPML kinds");
+    e->lean_interior = value != 0;
     return B200FDTD_OK;
   default:
     return b200_fail(B200FDTD_ERR_ARG, "unknown option %d", option);

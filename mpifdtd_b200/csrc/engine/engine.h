@@ -113,6 +113,8 @@ struct b200fdtd_engine {
   bool store_h;             // the fused kernel also writes Hx/Hy (264 instead of 232 B/cell)
   bool h_stale;             // Hx/Hy arrays lag Bx/By (fused step without store_h)
   int fused_variant;        // launch shape of the fused kernel (tuning)
+  bool lean_interior;       // opt-in: cells outside the absorbing frame skip the M / J recurrences
+  int lean_r_lo, lean_r_hi, lean_c_lo, lean_c_hi;   // that region (layout coordinates), from the tables
   uint64_t launches;
   uint64_t dev_bytes;
   cudaEvent_t ev0, ev1;

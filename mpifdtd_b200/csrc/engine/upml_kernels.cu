@@ -75,16 +75,10 @@ __device__ __forceinline__ void tm_h_math(C ez, C ez_j1, C ez_i1, C mx_old, C bx
   by = (c_by * by_old + c_by1 * my) - c_by0 * my_old;
 }
 
+// the source terms the reference adds to Ez after calcE (shared by the full and the lean E phase)
 template <typename T, typename C = typename Cx<T>::type>
-__device__ __forceinline__ void tm_e_math(const UpmlViewT<T> &v, int r, int c, size_t k0, C hy, C hy_i0, C hx, C hx_j0,
-                                          C jz_old, C dz_old, T eps, T c_jz, T c_jzh, T c_dz, T c_dzjz, C &jz, C &dz,
-                                          C &ez)
+__device__ __forceinline__ void tm_e_sources(const UpmlViewT<T> &v, int r, int c, size_t k0, T eps, C &ez)
 {
-  // fdtdTM_upml.c:161-163 (C_DZJZ1 == C_DZJZ0 because sigma_z = 0)
-  jz = c_jz * jz_old + c_jzh * (((hy - hy_i0) - hx) + hx_j0);
-  dz = (c_dz * dz_old + c_dzjz * jz) - c_dzjz * jz_old;
-  ez = div_eps(dz, eps);              // fdtdTM_upml.c:175
-
   if (eps != (T)1 && pulse_on(v, 0))       // field.c:248
     ez = add_source(ez, pulse_term(pulse_of(v, 0), r - 1, v.j_base + c, (double)eps));
   if (v.cw[0].enabled && eps != (T)1)          // mpiTM_UPML.c:370
@@ -98,12 +92,40 @@ __device__ __forceinline__ void tm_e_math(const UpmlViewT<T> &v, int r, int c, s
 }
 
 template <typename T, typename C = typename Cx<T>::type>
+__device__ __forceinline__ void tm_e_math(const UpmlViewT<T> &v, int r, int c, size_t k0, C hy, C hy_i0, C hx, C hx_j0,
+                                          C jz_old, C dz_old, T eps, T c_jz, T c_jzh, T c_dz, T c_dzjz, C &jz, C &dz,
+                                          C &ez)
+{
+  // fdtdTM_upml.c:161-163 (C_DZJZ1 == C_DZJZ0 because sigma_z = 0)
+  jz = c_jz * jz_old + c_jzh * (((hy - hy_i0) - hx) + hx_j0);
+  dz = (c_dz * dz_old + c_dzjz * jz) - c_dzjz * jz_old;
+  ez = div_eps(dz, eps);              // fdtdTM_upml.c:175
+  tm_e_sources<T>(v, r, c, k0, eps, ez);
+}
+
+template <typename T, typename C = typename Cx<T>::type>
 __device__ __forceinline__ void te_h_math(C ey_i1, C ey, C ex_j1, C ex, C mz_old, C bz_old, T c_mz, T c_mze, T c_bz,
                                           T c_bzmz, C &mz, C &bz)
 {
   // fdtdTE_upml.c:299-301 (C_BZMZ1 == C_BZMZ0 because sigma_z = 0)
   mz = c_mz * mz_old - c_mze * (((ey_i1 - ey) - ex_j1) + ex);
   bz = (c_bz * bz_old + c_bzmz * mz) - c_bzmz * mz_old;
+}
+
+// the source terms the reference adds to Ex / Ey after calcE (shared by the full and the lean E phase)
+template <typename T, typename C = typename Cx<T>::type>
+__device__ __forceinline__ void te_e_sources(const UpmlViewT<T> &v, int r, int c, size_t k0, T eps_x, T eps_y, C &ex,
+                                             C &ey)
+{
+  const int i = r - 1, j = v.j_base + c;
+  if (eps_x != (T)1 && pulse_on(v, 0))     // fdtdTE_upml.c:186-187
+    ex = add_source(ex, pulse_term(pulse_of(v, 0), i, j, (double)eps_x));
+  if (eps_y != (T)1 && pulse_on(v, 1))     // fdtdTE_upml.c:188-189
+    ey = add_source(ey, pulse_term(pulse_of(v, 1), i, j, (double)eps_y));
+  if (v.cw[0].enabled && eps_x != (T)1) ex = add_source(ex, cw_eps_term(v.cw[0], i, j, (double)eps_x));
+  if (v.cw[1].enabled && eps_y != (T)1) ey = add_source(ey, cw_eps_term(v.cw[1], i, j, (double)eps_y));   // mpiTE_UPML.c:278
+  if ((long long)k0 == v.point_k)
+    ex = add_source(ex, make_double2(v.point_re, v.point_im));
 }
 
 template <typename T, typename C = typename Cx<T>::type>
@@ -122,15 +144,7 @@ __device__ __forceinline__ void te_e_math(const UpmlViewT<T> &v, int r, int c, s
 
   ex = div_eps(dx, eps_x);            // fdtdTE_upml.c:283
   ey = div_eps(dy, eps_y);            // fdtdTE_upml.c:289
-  const int i = r - 1, j = v.j_base + c;
-  if (eps_x != (T)1 && pulse_on(v, 0))     // fdtdTE_upml.c:186-187
-    ex = add_source(ex, pulse_term(pulse_of(v, 0), i, j, (double)eps_x));
-  if (eps_y != (T)1 && pulse_on(v, 1))     // fdtdTE_upml.c:188-189
-    ey = add_source(ey, pulse_term(pulse_of(v, 1), i, j, (double)eps_y));
-  if (v.cw[0].enabled && eps_x != (T)1) ex = add_source(ex, cw_eps_term(v.cw[0], i, j, (double)eps_x));
-  if (v.cw[1].enabled && eps_y != (T)1) ey = add_source(ey, cw_eps_term(v.cw[1], i, j, (double)eps_y));   // mpiTE_UPML.c:278
-  if ((long long)k0 == v.point_k)
-    ex = add_source(ex, make_double2(v.point_re, v.point_im));
+  te_e_sources<T>(v, r, c, k0, eps_x, eps_y, ex, ey);
 }
 
 // ------------------------------------------------------------------ TM -----
@@ -138,7 +152,14 @@ __device__ __forceinline__ void te_e_math(const UpmlViewT<T> &v, int r, int c, s
 // STORE_H = false: Hx/Hy are not written; the E phase recomputes them from Bx/By
 // (Hx == Bx/mu0 exactly, fdtdTM_upml.c:209), which removes one 32 B/cell write and turns
 // the E phase's H reads into B reads: 264 instead of 296 B per cell-update, in place.
-template <typename T, bool STORE_H>
+// LEAN = true ("lean interior", opt-in): a cell outside the absorbing frame, where every UPML
+// coefficient is exactly 1, advances B directly --
+//   Mx' = Mx - d, Bx' = (Bx + Mx') - Mx   ==>   Bx' = Bx - d   (d = Ez(j+1) - Ez)
+// -- and neither reads nor writes Mx/My: 80 instead of 144 B per cell.  Same mathematics,
+// different rounding (one operation instead of three), so this form has a tolerance instead
+// of the bit-for-bit contract; M is left untouched outside the frame (only differences of M
+// enter the update there, so switching forms mid-run is harmless).
+template <typename T, bool STORE_H, bool LEAN = false>
 __device__ __forceinline__ void tm_upml_h_cell(const UpmlViewT<T> &v, int r, int c, size_t k, size_t k0)
 {
   using C = typename Cx<T>::type;
@@ -148,27 +169,34 @@ __device__ __forceinline__ void tm_upml_h_cell(const UpmlViewT<T> &v, int r, int
   const C ez = Ez[k];
   const C ez_j1 = Ez[k + 1];            // Ez(i, j+1)
   const C ez_i1 = Ez[k + v.pitch];      // Ez(i+1, j)
-  const C mx_old = v.f[B200FDTD_TM_MX][k];
   const C bx_old = v.f[B200FDTD_TM_BX][k];
-  const C my_old = v.f[B200FDTD_TM_MY][k];
   const C by_old = v.f[B200FDTD_TM_BY][k];
 
-  const T c_mx   = v.tj[B200FDTD_TMJ_C_MX * v.pitch + c];
-  const T c_mxez = v.tj[B200FDTD_TMJ_C_MXEZ * v.pitch + c];
-  const T num1   = v.tj[B200FDTD_TMJ_NUM_BYMY1 * v.pitch + c];
-  const T num0   = v.tj[B200FDTD_TMJ_NUM_BYMY0 * v.pitch + c];
-  const T c_bx1  = v.ti[B200FDTD_TMI_C_BXMX1 * v.rows + r];
-  const T c_bx0  = v.ti[B200FDTD_TMI_C_BXMX0 * v.rows + r];
-  const T c_by   = v.ti[B200FDTD_TMI_C_BY * v.rows + r];
-  const T den    = v.ti[B200FDTD_TMI_DEN_BYMY * v.rows + r];
+  C bx, by;
+  if (LEAN && cell_in_interior(v, r, c)) {
+    bx = bx_old - (ez_j1 - ez);
+    by = by_old - ((-ez_i1) + ez);
+  } else {
+    const C mx_old = v.f[B200FDTD_TM_MX][k];
+    const C my_old = v.f[B200FDTD_TM_MY][k];
 
-  C mx, bx, my, by;
-  tm_h_math<T>(ez, ez_j1, ez_i1, mx_old, bx_old, my_old, by_old, c_mx, c_mxez, num1, num0, c_bx1, c_bx0, c_by, den,
-               mx, bx, my, by);
+    const T c_mx   = v.tj[B200FDTD_TMJ_C_MX * v.pitch + c];
+    const T c_mxez = v.tj[B200FDTD_TMJ_C_MXEZ * v.pitch + c];
+    const T num1   = v.tj[B200FDTD_TMJ_NUM_BYMY1 * v.pitch + c];
+    const T num0   = v.tj[B200FDTD_TMJ_NUM_BYMY0 * v.pitch + c];
+    const T c_bx1  = v.ti[B200FDTD_TMI_C_BXMX1 * v.rows + r];
+    const T c_bx0  = v.ti[B200FDTD_TMI_C_BXMX0 * v.rows + r];
+    const T c_by   = v.ti[B200FDTD_TMI_C_BY * v.rows + r];
+    const T den    = v.ti[B200FDTD_TMI_DEN_BYMY * v.rows + r];
 
-  v.f[B200FDTD_TM_MX][k] = mx;
+    C mx, my;
+    tm_h_math<T>(ez, ez_j1, ez_i1, mx_old, bx_old, my_old, by_old, c_mx, c_mxez, num1, num0, c_bx1, c_bx0, c_by, den,
+                 mx, bx, my, by);
+    v.f[B200FDTD_TM_MX][k] = mx;
+    v.f[B200FDTD_TM_MY][k] = my;
+  }
+
   v.f[B200FDTD_TM_BX][k] = bx;
-  v.f[B200FDTD_TM_MY][k] = my;
   v.f[B200FDTD_TM_BY][k] = by;
   if (STORE_H) {
     v.f[B200FDTD_TM_HX][k] = div_const(bx, v.mu0);   // fdtdTM_upml.c:209
@@ -179,18 +207,18 @@ __device__ __forceinline__ void tm_upml_h_cell(const UpmlViewT<T> &v, int r, int
     v.peer_up_h[(size_t)r * v.peer_up_pitch + (B200_JOFF - 1)] = div_const(bx, v.mu0);
 }
 
-template <typename T, bool STORE_H>
+template <typename T, bool STORE_H, bool LEAN = false>
 __global__ void __launch_bounds__(kBlock, B200_H_MIN_BLOCKS) tm_upml_h_kernel(const UpmlViewT<T> v)
 {
   int r, c; size_t k, k0;
   if (!locate(v, r, c, k, k0)) return;
-  tm_upml_h_cell<T, STORE_H>(v, r, c, k, k0);
+  tm_upml_h_cell<T, STORE_H, LEAN>(v, r, c, k, k0);
 }
 
 // FROM_B = true: H is formed on the fly as B/mu0.  Cells just outside the updated range
 // (the ring, or a neighbour slab's halo column) are not derived state: there the H array
 // itself is read, exactly like the STORE_H form does.
-template <typename T, bool FROM_B, bool L2_B = false>
+template <typename T, bool FROM_B, bool L2_B = false, bool LEAN = false>
 __device__ __forceinline__ void tm_upml_e_cell(const UpmlViewT<T> &v, int r, int c, size_t k, size_t k0)
 {
   using C = typename Cx<T>::type;
@@ -216,19 +244,28 @@ __device__ __forceinline__ void tm_upml_e_cell(const UpmlViewT<T> &v, int r, int
     hx = Hx[k];
     hx_j0 = Hx[k - 1];            // Hx(i, j-1)
   }
-  const C jz_old = v.f[B200FDTD_TM_JZ][k];
   const C dz_old = v.f[B200FDTD_TM_DZ][k];
   const T eps = v.eps0[k0];
 
-  const T c_jz   = v.ti[B200FDTD_TMI_C_JZ * v.rows + r];
-  const T c_jzh  = v.ti[B200FDTD_TMI_C_JZHXHY * v.rows + r];
-  const T c_dz   = v.tj[B200FDTD_TMJ_C_DZ * v.pitch + c];
-  const T c_dzjz = v.tj[B200FDTD_TMJ_C_DZJZ * v.pitch + c];
+  C dz, ez;
+  if (LEAN && cell_in_interior(v, r, c)) {
+    // outside the frame Jz' = Jz + curl and Dz' = (Dz + Jz') - Jz, i.e. Dz' = Dz + curl: Jz is
+    // neither read nor written (88 instead of 120 B per cell)
+    dz = dz_old + (((hy - hy_i0) - hx) + hx_j0);
+    ez = div_eps(dz, eps);
+    tm_e_sources<T>(v, r, c, k0, eps, ez);
+  } else {
+    const C jz_old = v.f[B200FDTD_TM_JZ][k];
+    const T c_jz   = v.ti[B200FDTD_TMI_C_JZ * v.rows + r];
+    const T c_jzh  = v.ti[B200FDTD_TMI_C_JZHXHY * v.rows + r];
+    const T c_dz   = v.tj[B200FDTD_TMJ_C_DZ * v.pitch + c];
+    const T c_dzjz = v.tj[B200FDTD_TMJ_C_DZJZ * v.pitch + c];
 
-  C jz, dz, ez;
-  tm_e_math<T>(v, r, c, k0, hy, hy_i0, hx, hx_j0, jz_old, dz_old, eps, c_jz, c_jzh, c_dz, c_dzjz, jz, dz, ez);
+    C jz;
+    tm_e_math<T>(v, r, c, k0, hy, hy_i0, hx, hx_j0, jz_old, dz_old, eps, c_jz, c_jzh, c_dz, c_dzjz, jz, dz, ez);
+    v.f[B200FDTD_TM_JZ][k] = jz;
+  }
 
-  v.f[B200FDTD_TM_JZ][k] = jz;
   v.f[B200FDTD_TM_DZ][k] = dz;
   v.f[B200FDTD_TM_EZ][k] = ez;
   // y-slab halo: my bottom owned column of Ez is the lower neighbour's high ghost column
@@ -236,17 +273,17 @@ __device__ __forceinline__ void tm_upml_e_cell(const UpmlViewT<T> &v, int r, int
     v.peer_down_e[(size_t)r * v.peer_down_pitch + v.peer_down_col] = ez;
 }
 
-template <typename T, bool FROM_B>
+template <typename T, bool FROM_B, bool LEAN = false>
 __global__ void __launch_bounds__(kBlock, B200_E_MIN_BLOCKS) tm_upml_e_kernel(const UpmlViewT<T> v)
 {
   int r, c; size_t k, k0;
   if (!locate(v, r, c, k, k0)) return;
-  tm_upml_e_cell<T, FROM_B>(v, r, c, k, k0);
+  tm_upml_e_cell<T, FROM_B, false, LEAN>(v, r, c, k, k0);
 }
 
 // ------------------------------------------------------------------ TE -----
 // slots: 0 Ex 1 Jx 2 Dx 3 Ey 4 Jy 5 Dy 6 Hz 7 Mz 8 Bz
-template <typename T, bool STORE_H>
+template <typename T, bool STORE_H, bool LEAN = false>
 __device__ __forceinline__ void te_upml_h_cell(const UpmlViewT<T> &v, int r, int c, size_t k, size_t k0)
 {
   using C = typename Cx<T>::type;
@@ -258,33 +295,39 @@ __device__ __forceinline__ void te_upml_h_cell(const UpmlViewT<T> &v, int r, int
   const C ey = Ey[k];
   const C ex_j1 = Ex[k + 1];
   const C ex = Ex[k];
-  const C mz_old = v.f[B200FDTD_TE_MZ][k];
   const C bz_old = v.f[B200FDTD_TE_BZ][k];
 
-  const T c_mz   = v.ti[B200FDTD_TEI_C_MZ * v.rows + r];
-  const T c_mze  = v.ti[B200FDTD_TEI_C_MZEXEY * v.rows + r];
-  const T c_bz   = v.tj[B200FDTD_TEJ_C_BZ * v.pitch + c];
-  const T c_bzmz = v.tj[B200FDTD_TEJ_C_BZMZ * v.pitch + c];
+  C bz;
+  if (LEAN && cell_in_interior(v, r, c)) {
+    // outside the frame Mz' = Mz - curl and Bz' = (Bz + Mz') - Mz, i.e. Bz' = Bz - curl
+    bz = bz_old - (((ey_i1 - ey) - ex_j1) + ex);
+  } else {
+    const C mz_old = v.f[B200FDTD_TE_MZ][k];
+    const T c_mz   = v.ti[B200FDTD_TEI_C_MZ * v.rows + r];
+    const T c_mze  = v.ti[B200FDTD_TEI_C_MZEXEY * v.rows + r];
+    const T c_bz   = v.tj[B200FDTD_TEJ_C_BZ * v.pitch + c];
+    const T c_bzmz = v.tj[B200FDTD_TEJ_C_BZMZ * v.pitch + c];
 
-  C mz, bz;
-  te_h_math<T>(ey_i1, ey, ex_j1, ex, mz_old, bz_old, c_mz, c_mze, c_bz, c_bzmz, mz, bz);
+    C mz;
+    te_h_math<T>(ey_i1, ey, ex_j1, ex, mz_old, bz_old, c_mz, c_mze, c_bz, c_bzmz, mz, bz);
+    v.f[B200FDTD_TE_MZ][k] = mz;
+  }
 
-  v.f[B200FDTD_TE_MZ][k] = mz;
   v.f[B200FDTD_TE_BZ][k] = bz;
   if (STORE_H) v.f[B200FDTD_TE_HZ][k] = div_const(bz, v.mu0);   // fdtdTE_upml.c:312
   if (v.peer_up_h != nullptr && c == v.c_last)
     v.peer_up_h[(size_t)r * v.peer_up_pitch + (B200_JOFF - 1)] = div_const(bz, v.mu0);
 }
 
-template <typename T, bool STORE_H>
+template <typename T, bool STORE_H, bool LEAN = false>
 __global__ void __launch_bounds__(kBlock, B200_TE_H_MIN_BLOCKS) te_upml_h_kernel(const UpmlViewT<T> v)
 {
   int r, c; size_t k, k0;
   if (!locate(v, r, c, k, k0)) return;
-  te_upml_h_cell<T, STORE_H>(v, r, c, k, k0);
+  te_upml_h_cell<T, STORE_H, LEAN>(v, r, c, k, k0);
 }
 
-template <typename T, bool FROM_B, bool L2_B = false>
+template <typename T, bool FROM_B, bool L2_B = false, bool LEAN = false>
 __device__ __forceinline__ void te_upml_e_cell(const UpmlViewT<T> &v, int r, int c, size_t k, size_t k0)
 {
   using C = typename Cx<T>::type;
@@ -303,28 +346,38 @@ __device__ __forceinline__ void te_upml_e_cell(const UpmlViewT<T> &v, int r, int
     hz_j0 = Hz[k - 1];
     hz_i0 = Hz[k - v.pitch];
   }
-  const C jx_old = v.f[B200FDTD_TE_JX][k];
   const C dx_old = v.f[B200FDTD_TE_DX][k];
-  const C jy_old = v.f[B200FDTD_TE_JY][k];
   const C dy_old = v.f[B200FDTD_TE_DY][k];
   const T eps_x = v.eps0[k0], eps_y = v.eps1[k0];
 
-  const T c_jx   = v.tj[B200FDTD_TEJ_C_JX * v.pitch + c];
-  const T c_jxhz = v.tj[B200FDTD_TEJ_C_JXHZ * v.pitch + c];
-  const T num1   = v.tj[B200FDTD_TEJ_NUM_DYJY1 * v.pitch + c];
-  const T num0   = v.tj[B200FDTD_TEJ_NUM_DYJY0 * v.pitch + c];
-  const T c_dx1  = v.ti[B200FDTD_TEI_C_DXJX1 * v.rows + r];
-  const T c_dx0  = v.ti[B200FDTD_TEI_C_DXJX0 * v.rows + r];
-  const T c_dy   = v.ti[B200FDTD_TEI_C_DY * v.rows + r];
-  const T den    = v.ti[B200FDTD_TEI_DEN_DYJY * v.rows + r];
+  C dx, dy, ex, ey;
+  if (LEAN && cell_in_interior(v, r, c)) {
+    // outside the frame D' = (D + J') - J with J' = J + curl, i.e. D' = D + curl
+    dx = dx_old + (hz - hz_j0);
+    dy = dy_old + ((-hz) + hz_i0);
+    ex = div_eps(dx, eps_x);
+    ey = div_eps(dy, eps_y);
+    te_e_sources<T>(v, r, c, k0, eps_x, eps_y, ex, ey);
+  } else {
+    const C jx_old = v.f[B200FDTD_TE_JX][k];
+    const C jy_old = v.f[B200FDTD_TE_JY][k];
+    const T c_jx   = v.tj[B200FDTD_TEJ_C_JX * v.pitch + c];
+    const T c_jxhz = v.tj[B200FDTD_TEJ_C_JXHZ * v.pitch + c];
+    const T num1   = v.tj[B200FDTD_TEJ_NUM_DYJY1 * v.pitch + c];
+    const T num0   = v.tj[B200FDTD_TEJ_NUM_DYJY0 * v.pitch + c];
+    const T c_dx1  = v.ti[B200FDTD_TEI_C_DXJX1 * v.rows + r];
+    const T c_dx0  = v.ti[B200FDTD_TEI_C_DXJX0 * v.rows + r];
+    const T c_dy   = v.ti[B200FDTD_TEI_C_DY * v.rows + r];
+    const T den    = v.ti[B200FDTD_TEI_DEN_DYJY * v.rows + r];
 
-  C jx, dx, jy, dy, ex, ey;
-  te_e_math<T>(v, r, c, k0, hz, hz_j0, hz_i0, jx_old, dx_old, jy_old, dy_old, eps_x, eps_y, c_jx, c_jxhz, num1, num0,
-               c_dx1, c_dx0, c_dy, den, jx, dx, jy, dy, ex, ey);
+    C jx, jy;
+    te_e_math<T>(v, r, c, k0, hz, hz_j0, hz_i0, jx_old, dx_old, jy_old, dy_old, eps_x, eps_y, c_jx, c_jxhz, num1, num0,
+                 c_dx1, c_dx0, c_dy, den, jx, dx, jy, dy, ex, ey);
+    v.f[B200FDTD_TE_JX][k] = jx;
+    v.f[B200FDTD_TE_JY][k] = jy;
+  }
 
-  v.f[B200FDTD_TE_JX][k] = jx;
   v.f[B200FDTD_TE_DX][k] = dx;
-  v.f[B200FDTD_TE_JY][k] = jy;
   v.f[B200FDTD_TE_DY][k] = dy;
   v.f[B200FDTD_TE_EX][k] = ex;
   v.f[B200FDTD_TE_EY][k] = ey;
@@ -332,12 +385,12 @@ __device__ __forceinline__ void te_upml_e_cell(const UpmlViewT<T> &v, int r, int
     v.peer_down_e[(size_t)r * v.peer_down_pitch + v.peer_down_col] = ex;
 }
 
-template <typename T, bool FROM_B>
+template <typename T, bool FROM_B, bool LEAN = false>
 __global__ void __launch_bounds__(kBlock, B200_TE_E_MIN_BLOCKS) te_upml_e_kernel(const UpmlViewT<T> v)
 {
   int r, c; size_t k, k0;
   if (!locate(v, r, c, k, k0)) return;
-  te_upml_e_cell<T, FROM_B>(v, r, c, k, k0);
+  te_upml_e_cell<T, FROM_B, false, LEAN>(v, r, c, k, k0);
 }
 
 #include "upml_pairs_f32.cuh"
@@ -573,7 +626,7 @@ static int launch_h(b200fdtd_engine *e, const b200fdtd_step_args *a)
 {
   const UpmlViewT<T> v = make_view_t<T>(e, a);
   if constexpr (std::is_same<T, float>::value) {
-    if (e->f32_pairs && !e->store_h) {
+    if (e->f32_pairs && !e->store_h && !e->lean_interior) {
       const PairGeom g = pair_geom(e);
       const dim3 grid((unsigned)((long long)g.nbx2 * (e->r_hi - e->r_lo + 1)), (unsigned)e->n_batch);
       if (is_tm(e->g.kind)) tm_upml_h_pair_kernel<<<grid, kBlock, 0, e->stream>>>(v, g);
@@ -585,13 +638,21 @@ static int launch_h(b200fdtd_engine *e, const b200fdtd_step_args *a)
     }
   }
   const long long nblk = (long long)v.nbx * (e->r_hi - e->r_lo + 1);
-  if (is_tm(e->g.kind)) {
-    if (e->store_h) tm_upml_h_kernel<T, true><<<dim3((unsigned)nblk, (unsigned)e->n_batch), kBlock, 0, e->stream>>>(v);
-    else            tm_upml_h_kernel<T, false><<<dim3((unsigned)nblk, (unsigned)e->n_batch), kBlock, 0, e->stream>>>(v);
-  } else {
-    if (e->store_h) te_upml_h_kernel<T, true><<<dim3((unsigned)nblk, (unsigned)e->n_batch), kBlock, 0, e->stream>>>(v);
-    else            te_upml_h_kernel<T, false><<<dim3((unsigned)nblk, (unsigned)e->n_batch), kBlock, 0, e->stream>>>(v);
-  }
+  const dim3 grid((unsigned)nblk, (unsigned)e->n_batch);
+  const bool lean = v.lean_r_hi >= v.lean_r_lo && v.lean_c_hi >= v.lean_c_lo;
+#define LAUNCH_H(KERNEL)                                                                    \
+  do {                                                                                      \
+    if (lean) {                                                                             \
+      if (e->store_h) KERNEL<T, true, true><<<grid, kBlock, 0, e->stream>>>(v);             \
+      else            KERNEL<T, false, true><<<grid, kBlock, 0, e->stream>>>(v);            \
+    } else {                                                                                \
+      if (e->store_h) KERNEL<T, true, false><<<grid, kBlock, 0, e->stream>>>(v);            \
+      else            KERNEL<T, false, false><<<grid, kBlock, 0, e->stream>>>(v);           \
+    }                                                                                       \
+  } while (0)
+  if (is_tm(e->g.kind)) LAUNCH_H(tm_upml_h_kernel);
+  else                  LAUNCH_H(te_upml_h_kernel);
+#undef LAUNCH_H
   e->h_stale = !e->store_h;
   e->launches++;
   B200_CUDA(cudaGetLastError());
@@ -603,7 +664,7 @@ static int launch_e(b200fdtd_engine *e, const b200fdtd_step_args *a)
 {
   const UpmlViewT<T> v = make_view_t<T>(e, a);
   if constexpr (std::is_same<T, float>::value) {
-    if (e->f32_pairs && e->h_stale) {
+    if (e->f32_pairs && e->h_stale && !e->lean_interior) {
       const PairGeom g = pair_geom(e);
       const dim3 grid((unsigned)((long long)g.nbx2 * (e->r_hi - e->r_lo + 1)), (unsigned)e->n_batch);
       if (is_tm(e->g.kind)) tm_upml_e_pair_kernel<<<grid, kBlock, 0, e->stream>>>(v, g);
@@ -614,13 +675,21 @@ static int launch_e(b200fdtd_engine *e, const b200fdtd_step_args *a)
     }
   }
   const long long nblk = (long long)v.nbx * (e->r_hi - e->r_lo + 1);
-  if (is_tm(e->g.kind)) {
-    if (e->h_stale) tm_upml_e_kernel<T, true><<<dim3((unsigned)nblk, (unsigned)e->n_batch), kBlock, 0, e->stream>>>(v);
-    else            tm_upml_e_kernel<T, false><<<dim3((unsigned)nblk, (unsigned)e->n_batch), kBlock, 0, e->stream>>>(v);
-  } else {
-    if (e->h_stale) te_upml_e_kernel<T, true><<<dim3((unsigned)nblk, (unsigned)e->n_batch), kBlock, 0, e->stream>>>(v);
-    else            te_upml_e_kernel<T, false><<<dim3((unsigned)nblk, (unsigned)e->n_batch), kBlock, 0, e->stream>>>(v);
-  }
+  const dim3 grid((unsigned)nblk, (unsigned)e->n_batch);
+  const bool lean = v.lean_r_hi >= v.lean_r_lo && v.lean_c_hi >= v.lean_c_lo;
+#define LAUNCH_E(KERNEL)                                                                    \
+  do {                                                                                      \
+    if (lean) {                                                                             \
+      if (e->h_stale) KERNEL<T, true, true><<<grid, kBlock, 0, e->stream>>>(v);             \
+      else            KERNEL<T, false, true><<<grid, kBlock, 0, e->stream>>>(v);            \
+    } else {                                                                                \
+      if (e->h_stale) KERNEL<T, true, false><<<grid, kBlock, 0, e->stream>>>(v);            \
+      else            KERNEL<T, false, false><<<grid, kBlock, 0, e->stream>>>(v);           \
+    }                                                                                       \
+  } while (0)
+  if (is_tm(e->g.kind)) LAUNCH_E(tm_upml_e_kernel);
+  else                  LAUNCH_E(te_upml_e_kernel);
+#undef LAUNCH_E
   e->launches++;
   B200_CUDA(cudaGetLastError());
   return B200FDTD_OK;

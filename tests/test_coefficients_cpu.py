@@ -40,3 +40,38 @@ def test_interior_coefficients_are_exactly_one(plugin_lib):
             assert np.all(ti[s, 10:53] == want_i), (kind, "i", s)
             assert np.all(tj[s, 10:59] == want_j), (kind, "j", s)
         assert np.any(ti[:, :10] != ti[:, 20:30]) and np.any(tj[:, 60:] != tj[:, 20:30])
+
+
+@pytest.mark.parametrize("kind", [2, 3, 4, 5])
+def test_frame_free_region_from_the_tables(plugin_lib, kind):
+    """b200fdtd_upml_interior (what B200FDTD_OPT_LEAN_INTERIOR relies on): inside the region every
+    dense coefficient of the reference is exactly 1, and the region cannot be grown."""
+    L = plugin_lib
+    npx, npy = 64, 70
+    L.models_setModel(B.MODELS["MIE_CYLINDER"])
+    L.field_init(B.FieldInfo(npx * 10, npy * 10, 10, 10, 500, 0, 10))
+    ti, tj = np.empty((6, npx)), np.empty((6, npy))
+    L.mpifdtd_upml_tables(kind, ti.ctypes.data, tj.ctypes.data)
+    out = np.zeros(4, dtype=np.int32)
+    assert L.b200fdtd_upml_interior(kind, ti.ctypes.data, npx, tj.ctypes.data, npy, out.ctypes.data) == 0
+    i_lo, i_hi, j_lo, j_hi = (int(v) for v in out)
+    assert (i_lo, i_hi, j_lo, j_hi) == (10, npx - 11, 10, npy - 11)
+    if kind in (2, 3):        # the dense-coefficient probe serves the serial kinds
+        grown = np.zeros((npx, npy), dtype=bool)
+        for name in (TM if kind == 2 else TE):
+            dense = np.empty((npx, npy))
+            assert L.mpifdtd_upml_dense_coefficient(kind, name.encode(), dense.ctypes.data) == 0, name
+            assert np.all(dense[i_lo:i_hi + 1, j_lo:j_hi + 1] == 1.0), name
+            grown |= dense != 1.0
+        # one more row or column on any side meets a coefficient != 1
+        assert grown[i_lo - 1, j_lo:j_hi + 1].any() and grown[i_hi + 1, j_lo:j_hi + 1].any()
+        assert grown[i_lo:i_hi + 1, j_lo - 1].any() and grown[i_lo:i_hi + 1, j_hi + 1].any()
+    else:
+        assert len(np.unique(ti[:, i_lo:i_hi + 1])) <= 2 and len(np.unique(tj[:, j_lo:j_hi + 1])) <= 2
+        assert len(np.unique(ti[:, i_lo - 1:i_hi + 2])) > 2 and len(np.unique(tj[:, j_lo - 1:j_hi + 2])) > 2
+    # a grid that is all frame has no such region
+    L.field_init(B.FieldInfo(200, 200, 10, 10, 500, 0, 10))
+    ti, tj = np.empty((6, 20)), np.empty((6, 20))
+    L.mpifdtd_upml_tables(kind, ti.ctypes.data, tj.ctypes.data)
+    assert L.b200fdtd_upml_interior(kind, ti.ctypes.data, 20, tj.ctypes.data, 20, out.ctypes.data) == 0
+    assert out[0] > out[1] and out[2] > out[3]
