@@ -400,9 +400,11 @@ int b200fdtd_set_upml_tables(b200fdtd_engine *e, const double *tab_i, const doub
     e->lean_r_hi = e->lean_c_hi = 0;
     if (x[0] <= x[1]) {
       const int jl = x[2] > g.j0 ? x[2] : g.j0, jh = x[3] < g.j0 + g.nj - 1 ? x[3] : g.j0 + g.nj - 1;
-      const int r_lo = x[0] + 1 > e->r_lo ? x[0] + 1 : e->r_lo, r_hi = x[1] + 1 < e->r_hi ? x[1] + 1 : e->r_hi;
+      const int r_lo = x[0] + 1 > e->r_lo + 1 ? x[0] + 1 : e->r_lo + 1, r_hi = x[1] + 1 < e->r_hi ? x[1] + 1 : e->r_hi;
       int c_lo = jl - g.j0 + B200_JOFF, c_hi = jh - g.j0 + B200_JOFF;
-      if (c_lo < e->c_lo) c_lo = e->c_lo;
+      // Row r_lo and column c_lo stay with the frame kernels: their low-side neighbour is the ring
+      // or a neighbour slab's halo column, which only the H arrays hold (the lean E kernels read B).
+      if (c_lo < e->c_lo + 1) c_lo = e->c_lo + 1;
       if (c_hi > e->c_hi) c_hi = e->c_hi;
       if (r_lo <= r_hi && c_lo <= c_hi) {
         e->lean_r_lo = r_lo; e->lean_r_hi = r_hi; e->lean_c_lo = c_lo; e->lean_c_hi = c_hi;

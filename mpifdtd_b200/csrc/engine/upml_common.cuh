@@ -2,6 +2,7 @@
 // the kernel-side view of an engine, complex helpers with the reference's
 // component-wise semantics, and the Gaussian-pulse source term.
 #pragma once
+#include <cstring>
 #include "engine.h"
 
 namespace upml {
@@ -16,6 +17,14 @@ template <> struct Cx<float>  { using type = float2; };
 
 template <typename T> struct ConstDivisorT { T d, r; };   // a loop-invariant divisor and RN(1/d), see div_const()
 using ConstDivisor = ConstDivisorT<double>;
+
+// one rectangle of a multi-rectangle launch, layout coordinates, inclusive
+struct LaunchRect {
+  int r_lo, r_hi, c_lo, c_hi;
+  int bw_log2;                  // a block covers 2^bw_log2 columns x (kBlock >> bw_log2) rows
+  int nbx;                      // blocks per block-row
+  unsigned blk_end;             // cumulative block count up to and including this rectangle
+};
 
 template <typename T>
 struct UpmlViewT {
@@ -42,9 +51,9 @@ struct UpmlViewT {
   b200fdtd_line_source line;    // opt-in planeWave line source (mpiTM_UPML.c:377-403)
   long long point_k;            // layout offset of the opt-in point source, or -1
   double point_re, point_im;
-  // "lean interior" (opt-in): rows / columns whose UPML coefficients are all exactly 1, i.e.
-  // the cells outside the absorbing frame, in layout coordinates, inclusive; empty when off
-  int lean_r_lo, lean_r_hi, lean_c_lo, lean_c_hi;
+  // launches over a table of rectangles (lean interior form: the frame-free rectangle, or the
+  // up to four pieces of the frame around it); see locate_rect() in upml_kernels.cu
+  LaunchRect rect[4];
 };
 using UpmlView = UpmlViewT<double>;
 
@@ -175,16 +184,6 @@ __device__ __forceinline__ double2 line_term(const b200fdtd_line_source &s, int 
   return make_double2(s.scale * cs, s.scale * sn);
 }
 
-// Does cell (r, c) lie outside the absorbing frame?  Decided per cell, so the answer -- and with
-// it every rounding -- is a property of the cell's global position and does not depend on how
-// the grid is cut into slabs or warps; all but the two warps per row that straddle the frame's
-// edge take one side of the branch together.
-template <typename T>
-__device__ __forceinline__ bool cell_in_interior(const UpmlViewT<T> &v, int r, int c)
-{
-  return r >= v.lean_r_lo && r <= v.lean_r_hi && c >= v.lean_c_lo && c <= v.lean_c_hi;
-}
-
 inline bool is_tm(int kind) { return kind == B200FDTD_TM_UPML || kind == B200FDTD_MPI_TM_UPML; }
 
 template <typename T>
@@ -231,12 +230,7 @@ inline UpmlViewT<T> make_view_t(const b200fdtd_engine *e, const b200fdtd_step_ar
     if (pj >= 0 && pj < e->g.nj && a->point.i >= 0 && a->point.i < e->g.n_px)
       v.point_k = (long long)(a->point.i + 1) * e->pitch + pj + B200_JOFF;
   }
-  v.lean_r_lo = v.lean_c_lo = 1;
-  v.lean_r_hi = v.lean_c_hi = 0;
-  if (e->lean_interior) {
-    v.lean_r_lo = e->lean_r_lo; v.lean_r_hi = e->lean_r_hi;
-    v.lean_c_lo = e->lean_c_lo; v.lean_c_hi = e->lean_c_hi;
-  }
+  memset(v.rect, 0, sizeof v.rect);
   return v;
 }
 inline UpmlView make_view(const b200fdtd_engine *e, const b200fdtd_step_args *a)

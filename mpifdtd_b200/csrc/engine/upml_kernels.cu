@@ -52,6 +52,28 @@ __device__ __forceinline__ bool locate(const UpmlViewT<T> &v, int &r, int &c, si
   return c <= v.c_hi;
 }
 
+// The same for a launch over a table of up to four rectangles (the absorbing frame around the
+// lean interior, or the interior itself): blocks are numbered rectangle after rectangle; a block
+// covers 2^bw_log2 columns x (kBlock >> bw_log2) rows, so the narrow side strips of the frame do
+// not waste 245 of 256 threads.  Which rectangle: three compares on launch constants.
+template <typename T>
+__device__ __forceinline__ bool locate_rect(const UpmlViewT<T> &v, int &r, int &c, size_t &k, size_t &k0)
+{
+  unsigned b = blockIdx.x;
+  LaunchRect R = v.rect[0];
+  if (b >= v.rect[2].blk_end)      { R = v.rect[3]; b -= v.rect[2].blk_end; }
+  else if (b >= v.rect[1].blk_end) { R = v.rect[2]; b -= v.rect[1].blk_end; }
+  else if (b >= v.rect[0].blk_end) { R = v.rect[1]; b -= v.rect[0].blk_end; }
+  const int rb = (int)(b / (unsigned)R.nbx);
+  const int cb = (int)(b - (unsigned)rb * (unsigned)R.nbx);
+  const int tx = (int)threadIdx.x & ((1 << R.bw_log2) - 1), ty = (int)threadIdx.x >> R.bw_log2;
+  r = R.r_lo + rb * (kBlock >> R.bw_log2) + ty;
+  c = R.c_lo + (cb << R.bw_log2) + tx;
+  k0 = (size_t)r * (size_t)v.pitch + (size_t)c;
+  k = k0 + (size_t)blockIdx.y * v.plane;
+  return r <= R.r_hi && c <= R.c_hi;
+}
+
 // B loads of the E phase.  In the pipelined step another SM may have written these values
 // moments ago while this SM's L1 can still hold the line from its own H-phase reads of the
 // neighbouring cells, so there they are read at L2 (ld.global.cg); otherwise a plain load.
@@ -152,14 +174,7 @@ __device__ __forceinline__ void te_e_math(const UpmlViewT<T> &v, int r, int c, s
 // STORE_H = false: Hx/Hy are not written; the E phase recomputes them from Bx/By
 // (Hx == Bx/mu0 exactly, fdtdTM_upml.c:209), which removes one 32 B/cell write and turns
 // the E phase's H reads into B reads: 264 instead of 296 B per cell-update, in place.
-// LEAN = true ("lean interior", opt-in): a cell outside the absorbing frame, where every UPML
-// coefficient is exactly 1, advances B directly --
-//   Mx' = Mx - d, Bx' = (Bx + Mx') - Mx   ==>   Bx' = Bx - d   (d = Ez(j+1) - Ez)
-// -- and neither reads nor writes Mx/My: 80 instead of 144 B per cell.  Same mathematics,
-// different rounding (one operation instead of three), so this form has a tolerance instead
-// of the bit-for-bit contract; M is left untouched outside the frame (only differences of M
-// enter the update there, so switching forms mid-run is harmless).
-template <typename T, bool STORE_H, bool LEAN = false>
+template <typename T, bool STORE_H>
 __device__ __forceinline__ void tm_upml_h_cell(const UpmlViewT<T> &v, int r, int c, size_t k, size_t k0)
 {
   using C = typename Cx<T>::type;
@@ -169,34 +184,27 @@ __device__ __forceinline__ void tm_upml_h_cell(const UpmlViewT<T> &v, int r, int
   const C ez = Ez[k];
   const C ez_j1 = Ez[k + 1];            // Ez(i, j+1)
   const C ez_i1 = Ez[k + v.pitch];      // Ez(i+1, j)
+  const C mx_old = v.f[B200FDTD_TM_MX][k];
   const C bx_old = v.f[B200FDTD_TM_BX][k];
+  const C my_old = v.f[B200FDTD_TM_MY][k];
   const C by_old = v.f[B200FDTD_TM_BY][k];
 
-  C bx, by;
-  if (LEAN && cell_in_interior(v, r, c)) {
-    bx = bx_old - (ez_j1 - ez);
-    by = by_old - ((-ez_i1) + ez);
-  } else {
-    const C mx_old = v.f[B200FDTD_TM_MX][k];
-    const C my_old = v.f[B200FDTD_TM_MY][k];
+  const T c_mx   = v.tj[B200FDTD_TMJ_C_MX * v.pitch + c];
+  const T c_mxez = v.tj[B200FDTD_TMJ_C_MXEZ * v.pitch + c];
+  const T num1   = v.tj[B200FDTD_TMJ_NUM_BYMY1 * v.pitch + c];
+  const T num0   = v.tj[B200FDTD_TMJ_NUM_BYMY0 * v.pitch + c];
+  const T c_bx1  = v.ti[B200FDTD_TMI_C_BXMX1 * v.rows + r];
+  const T c_bx0  = v.ti[B200FDTD_TMI_C_BXMX0 * v.rows + r];
+  const T c_by   = v.ti[B200FDTD_TMI_C_BY * v.rows + r];
+  const T den    = v.ti[B200FDTD_TMI_DEN_BYMY * v.rows + r];
 
-    const T c_mx   = v.tj[B200FDTD_TMJ_C_MX * v.pitch + c];
-    const T c_mxez = v.tj[B200FDTD_TMJ_C_MXEZ * v.pitch + c];
-    const T num1   = v.tj[B200FDTD_TMJ_NUM_BYMY1 * v.pitch + c];
-    const T num0   = v.tj[B200FDTD_TMJ_NUM_BYMY0 * v.pitch + c];
-    const T c_bx1  = v.ti[B200FDTD_TMI_C_BXMX1 * v.rows + r];
-    const T c_bx0  = v.ti[B200FDTD_TMI_C_BXMX0 * v.rows + r];
-    const T c_by   = v.ti[B200FDTD_TMI_C_BY * v.rows + r];
-    const T den    = v.ti[B200FDTD_TMI_DEN_BYMY * v.rows + r];
+  C mx, bx, my, by;
+  tm_h_math<T>(ez, ez_j1, ez_i1, mx_old, bx_old, my_old, by_old, c_mx, c_mxez, num1, num0, c_bx1, c_bx0, c_by, den,
+               mx, bx, my, by);
 
-    C mx, my;
-    tm_h_math<T>(ez, ez_j1, ez_i1, mx_old, bx_old, my_old, by_old, c_mx, c_mxez, num1, num0, c_bx1, c_bx0, c_by, den,
-                 mx, bx, my, by);
-    v.f[B200FDTD_TM_MX][k] = mx;
-    v.f[B200FDTD_TM_MY][k] = my;
-  }
-
+  v.f[B200FDTD_TM_MX][k] = mx;
   v.f[B200FDTD_TM_BX][k] = bx;
+  v.f[B200FDTD_TM_MY][k] = my;
   v.f[B200FDTD_TM_BY][k] = by;
   if (STORE_H) {
     v.f[B200FDTD_TM_HX][k] = div_const(bx, v.mu0);   // fdtdTM_upml.c:209
@@ -207,18 +215,18 @@ __device__ __forceinline__ void tm_upml_h_cell(const UpmlViewT<T> &v, int r, int
     v.peer_up_h[(size_t)r * v.peer_up_pitch + (B200_JOFF - 1)] = div_const(bx, v.mu0);
 }
 
-template <typename T, bool STORE_H, bool LEAN = false>
+template <typename T, bool STORE_H, bool RECTS = false>
 __global__ void __launch_bounds__(kBlock, B200_H_MIN_BLOCKS) tm_upml_h_kernel(const UpmlViewT<T> v)
 {
   int r, c; size_t k, k0;
-  if (!locate(v, r, c, k, k0)) return;
-  tm_upml_h_cell<T, STORE_H, LEAN>(v, r, c, k, k0);
+  if (!(RECTS ? locate_rect(v, r, c, k, k0) : locate(v, r, c, k, k0))) return;
+  tm_upml_h_cell<T, STORE_H>(v, r, c, k, k0);
 }
 
 // FROM_B = true: H is formed on the fly as B/mu0.  Cells just outside the updated range
 // (the ring, or a neighbour slab's halo column) are not derived state: there the H array
 // itself is read, exactly like the STORE_H form does.
-template <typename T, bool FROM_B, bool L2_B = false, bool LEAN = false>
+template <typename T, bool FROM_B, bool L2_B = false>
 __device__ __forceinline__ void tm_upml_e_cell(const UpmlViewT<T> &v, int r, int c, size_t k, size_t k0)
 {
   using C = typename Cx<T>::type;
@@ -244,28 +252,19 @@ __device__ __forceinline__ void tm_upml_e_cell(const UpmlViewT<T> &v, int r, int
     hx = Hx[k];
     hx_j0 = Hx[k - 1];            // Hx(i, j-1)
   }
+  const C jz_old = v.f[B200FDTD_TM_JZ][k];
   const C dz_old = v.f[B200FDTD_TM_DZ][k];
   const T eps = v.eps0[k0];
 
-  C dz, ez;
-  if (LEAN && cell_in_interior(v, r, c)) {
-    // outside the frame Jz' = Jz + curl and Dz' = (Dz + Jz') - Jz, i.e. Dz' = Dz + curl: Jz is
-    // neither read nor written (88 instead of 120 B per cell)
-    dz = dz_old + (((hy - hy_i0) - hx) + hx_j0);
-    ez = div_eps(dz, eps);
-    tm_e_sources<T>(v, r, c, k0, eps, ez);
-  } else {
-    const C jz_old = v.f[B200FDTD_TM_JZ][k];
-    const T c_jz   = v.ti[B200FDTD_TMI_C_JZ * v.rows + r];
-    const T c_jzh  = v.ti[B200FDTD_TMI_C_JZHXHY * v.rows + r];
-    const T c_dz   = v.tj[B200FDTD_TMJ_C_DZ * v.pitch + c];
-    const T c_dzjz = v.tj[B200FDTD_TMJ_C_DZJZ * v.pitch + c];
+  const T c_jz   = v.ti[B200FDTD_TMI_C_JZ * v.rows + r];
+  const T c_jzh  = v.ti[B200FDTD_TMI_C_JZHXHY * v.rows + r];
+  const T c_dz   = v.tj[B200FDTD_TMJ_C_DZ * v.pitch + c];
+  const T c_dzjz = v.tj[B200FDTD_TMJ_C_DZJZ * v.pitch + c];
 
-    C jz;
-    tm_e_math<T>(v, r, c, k0, hy, hy_i0, hx, hx_j0, jz_old, dz_old, eps, c_jz, c_jzh, c_dz, c_dzjz, jz, dz, ez);
-    v.f[B200FDTD_TM_JZ][k] = jz;
-  }
+  C jz, dz, ez;
+  tm_e_math<T>(v, r, c, k0, hy, hy_i0, hx, hx_j0, jz_old, dz_old, eps, c_jz, c_jzh, c_dz, c_dzjz, jz, dz, ez);
 
+  v.f[B200FDTD_TM_JZ][k] = jz;
   v.f[B200FDTD_TM_DZ][k] = dz;
   v.f[B200FDTD_TM_EZ][k] = ez;
   // y-slab halo: my bottom owned column of Ez is the lower neighbour's high ghost column
@@ -273,17 +272,17 @@ __device__ __forceinline__ void tm_upml_e_cell(const UpmlViewT<T> &v, int r, int
     v.peer_down_e[(size_t)r * v.peer_down_pitch + v.peer_down_col] = ez;
 }
 
-template <typename T, bool FROM_B, bool LEAN = false>
+template <typename T, bool FROM_B, bool RECTS = false>
 __global__ void __launch_bounds__(kBlock, B200_E_MIN_BLOCKS) tm_upml_e_kernel(const UpmlViewT<T> v)
 {
   int r, c; size_t k, k0;
-  if (!locate(v, r, c, k, k0)) return;
-  tm_upml_e_cell<T, FROM_B, false, LEAN>(v, r, c, k, k0);
+  if (!(RECTS ? locate_rect(v, r, c, k, k0) : locate(v, r, c, k, k0))) return;
+  tm_upml_e_cell<T, FROM_B>(v, r, c, k, k0);
 }
 
 // ------------------------------------------------------------------ TE -----
 // slots: 0 Ex 1 Jx 2 Dx 3 Ey 4 Jy 5 Dy 6 Hz 7 Mz 8 Bz
-template <typename T, bool STORE_H, bool LEAN = false>
+template <typename T, bool STORE_H>
 __device__ __forceinline__ void te_upml_h_cell(const UpmlViewT<T> &v, int r, int c, size_t k, size_t k0)
 {
   using C = typename Cx<T>::type;
@@ -295,39 +294,33 @@ __device__ __forceinline__ void te_upml_h_cell(const UpmlViewT<T> &v, int r, int
   const C ey = Ey[k];
   const C ex_j1 = Ex[k + 1];
   const C ex = Ex[k];
+  const C mz_old = v.f[B200FDTD_TE_MZ][k];
   const C bz_old = v.f[B200FDTD_TE_BZ][k];
 
-  C bz;
-  if (LEAN && cell_in_interior(v, r, c)) {
-    // outside the frame Mz' = Mz - curl and Bz' = (Bz + Mz') - Mz, i.e. Bz' = Bz - curl
-    bz = bz_old - (((ey_i1 - ey) - ex_j1) + ex);
-  } else {
-    const C mz_old = v.f[B200FDTD_TE_MZ][k];
-    const T c_mz   = v.ti[B200FDTD_TEI_C_MZ * v.rows + r];
-    const T c_mze  = v.ti[B200FDTD_TEI_C_MZEXEY * v.rows + r];
-    const T c_bz   = v.tj[B200FDTD_TEJ_C_BZ * v.pitch + c];
-    const T c_bzmz = v.tj[B200FDTD_TEJ_C_BZMZ * v.pitch + c];
+  const T c_mz   = v.ti[B200FDTD_TEI_C_MZ * v.rows + r];
+  const T c_mze  = v.ti[B200FDTD_TEI_C_MZEXEY * v.rows + r];
+  const T c_bz   = v.tj[B200FDTD_TEJ_C_BZ * v.pitch + c];
+  const T c_bzmz = v.tj[B200FDTD_TEJ_C_BZMZ * v.pitch + c];
 
-    C mz;
-    te_h_math<T>(ey_i1, ey, ex_j1, ex, mz_old, bz_old, c_mz, c_mze, c_bz, c_bzmz, mz, bz);
-    v.f[B200FDTD_TE_MZ][k] = mz;
-  }
+  C mz, bz;
+  te_h_math<T>(ey_i1, ey, ex_j1, ex, mz_old, bz_old, c_mz, c_mze, c_bz, c_bzmz, mz, bz);
 
+  v.f[B200FDTD_TE_MZ][k] = mz;
   v.f[B200FDTD_TE_BZ][k] = bz;
   if (STORE_H) v.f[B200FDTD_TE_HZ][k] = div_const(bz, v.mu0);   // fdtdTE_upml.c:312
   if (v.peer_up_h != nullptr && c == v.c_last)
     v.peer_up_h[(size_t)r * v.peer_up_pitch + (B200_JOFF - 1)] = div_const(bz, v.mu0);
 }
 
-template <typename T, bool STORE_H, bool LEAN = false>
+template <typename T, bool STORE_H, bool RECTS = false>
 __global__ void __launch_bounds__(kBlock, B200_TE_H_MIN_BLOCKS) te_upml_h_kernel(const UpmlViewT<T> v)
 {
   int r, c; size_t k, k0;
-  if (!locate(v, r, c, k, k0)) return;
-  te_upml_h_cell<T, STORE_H, LEAN>(v, r, c, k, k0);
+  if (!(RECTS ? locate_rect(v, r, c, k, k0) : locate(v, r, c, k, k0))) return;
+  te_upml_h_cell<T, STORE_H>(v, r, c, k, k0);
 }
 
-template <typename T, bool FROM_B, bool L2_B = false, bool LEAN = false>
+template <typename T, bool FROM_B, bool L2_B = false>
 __device__ __forceinline__ void te_upml_e_cell(const UpmlViewT<T> &v, int r, int c, size_t k, size_t k0)
 {
   using C = typename Cx<T>::type;
@@ -346,38 +339,28 @@ __device__ __forceinline__ void te_upml_e_cell(const UpmlViewT<T> &v, int r, int
     hz_j0 = Hz[k - 1];
     hz_i0 = Hz[k - v.pitch];
   }
+  const C jx_old = v.f[B200FDTD_TE_JX][k];
   const C dx_old = v.f[B200FDTD_TE_DX][k];
+  const C jy_old = v.f[B200FDTD_TE_JY][k];
   const C dy_old = v.f[B200FDTD_TE_DY][k];
   const T eps_x = v.eps0[k0], eps_y = v.eps1[k0];
 
-  C dx, dy, ex, ey;
-  if (LEAN && cell_in_interior(v, r, c)) {
-    // outside the frame D' = (D + J') - J with J' = J + curl, i.e. D' = D + curl
-    dx = dx_old + (hz - hz_j0);
-    dy = dy_old + ((-hz) + hz_i0);
-    ex = div_eps(dx, eps_x);
-    ey = div_eps(dy, eps_y);
-    te_e_sources<T>(v, r, c, k0, eps_x, eps_y, ex, ey);
-  } else {
-    const C jx_old = v.f[B200FDTD_TE_JX][k];
-    const C jy_old = v.f[B200FDTD_TE_JY][k];
-    const T c_jx   = v.tj[B200FDTD_TEJ_C_JX * v.pitch + c];
-    const T c_jxhz = v.tj[B200FDTD_TEJ_C_JXHZ * v.pitch + c];
-    const T num1   = v.tj[B200FDTD_TEJ_NUM_DYJY1 * v.pitch + c];
-    const T num0   = v.tj[B200FDTD_TEJ_NUM_DYJY0 * v.pitch + c];
-    const T c_dx1  = v.ti[B200FDTD_TEI_C_DXJX1 * v.rows + r];
-    const T c_dx0  = v.ti[B200FDTD_TEI_C_DXJX0 * v.rows + r];
-    const T c_dy   = v.ti[B200FDTD_TEI_C_DY * v.rows + r];
-    const T den    = v.ti[B200FDTD_TEI_DEN_DYJY * v.rows + r];
+  const T c_jx   = v.tj[B200FDTD_TEJ_C_JX * v.pitch + c];
+  const T c_jxhz = v.tj[B200FDTD_TEJ_C_JXHZ * v.pitch + c];
+  const T num1   = v.tj[B200FDTD_TEJ_NUM_DYJY1 * v.pitch + c];
+  const T num0   = v.tj[B200FDTD_TEJ_NUM_DYJY0 * v.pitch + c];
+  const T c_dx1  = v.ti[B200FDTD_TEI_C_DXJX1 * v.rows + r];
+  const T c_dx0  = v.ti[B200FDTD_TEI_C_DXJX0 * v.rows + r];
+  const T c_dy   = v.ti[B200FDTD_TEI_C_DY * v.rows + r];
+  const T den    = v.ti[B200FDTD_TEI_DEN_DYJY * v.rows + r];
 
-    C jx, jy;
-    te_e_math<T>(v, r, c, k0, hz, hz_j0, hz_i0, jx_old, dx_old, jy_old, dy_old, eps_x, eps_y, c_jx, c_jxhz, num1, num0,
-                 c_dx1, c_dx0, c_dy, den, jx, dx, jy, dy, ex, ey);
-    v.f[B200FDTD_TE_JX][k] = jx;
-    v.f[B200FDTD_TE_JY][k] = jy;
-  }
+  C jx, dx, jy, dy, ex, ey;
+  te_e_math<T>(v, r, c, k0, hz, hz_j0, hz_i0, jx_old, dx_old, jy_old, dy_old, eps_x, eps_y, c_jx, c_jxhz, num1, num0,
+               c_dx1, c_dx0, c_dy, den, jx, dx, jy, dy, ex, ey);
 
+  v.f[B200FDTD_TE_JX][k] = jx;
   v.f[B200FDTD_TE_DX][k] = dx;
+  v.f[B200FDTD_TE_JY][k] = jy;
   v.f[B200FDTD_TE_DY][k] = dy;
   v.f[B200FDTD_TE_EX][k] = ex;
   v.f[B200FDTD_TE_EY][k] = ey;
@@ -385,12 +368,146 @@ __device__ __forceinline__ void te_upml_e_cell(const UpmlViewT<T> &v, int r, int
     v.peer_down_e[(size_t)r * v.peer_down_pitch + v.peer_down_col] = ex;
 }
 
-template <typename T, bool FROM_B, bool LEAN = false>
+template <typename T, bool FROM_B, bool RECTS = false>
 __global__ void __launch_bounds__(kBlock, B200_TE_E_MIN_BLOCKS) te_upml_e_kernel(const UpmlViewT<T> v)
 {
   int r, c; size_t k, k0;
-  if (!locate(v, r, c, k, k0)) return;
-  te_upml_e_cell<T, FROM_B, false, LEAN>(v, r, c, k, k0);
+  if (!(RECTS ? locate_rect(v, r, c, k, k0) : locate(v, r, c, k, k0))) return;
+  te_upml_e_cell<T, FROM_B>(v, r, c, k, k0);
+}
+
+// ------------------------------------------------------------------ lean interior -----
+// Opt-in (B200FDTD_OPT_LEAN_INTERIOR).  Outside the absorbing frame every UPML coefficient of
+// fdtdTM_upml.c:253-271 / fdtdTE_upml.c:384-403 is exactly 1, and the recurrences collapse:
+//   Mx' = Mx - d,  Bx' = (Bx + Mx') - Mx   ==>  Bx' = Bx - d          (d = Ez(j+1) - Ez)
+//   Jz' = Jz + q,  Dz' = (Dz + Jz') - Jz   ==>  Dz' = Dz + q          (q = curl H = curl B / mu0)
+// These kernels run over that rectangle only and neither read nor write M / J: 80 + 88 = 168 B
+// per TM cell-update instead of 144 + 120 = 264 (TE: 64 + 128 = 192 instead of 288); the frame
+// keeps the reference's arithmetic through the kernels above (RECTS = true).  Same mathematics,
+// fewer roundings -- curl H is formed as RN(1/mu0) * curl B, one multiplication instead of four
+// divisions -- so this form carries a tolerance (fields <= 1e-12 of the reference) instead of the
+// bit-for-bit contract.  Only differences of M / J enter the update out here, so the arrays may
+// go stale and the form can be switched between steps.  Few registers, no division: 8 blocks/SM.
+#ifndef B200_LEAN_MIN_BLOCKS
+#define B200_LEAN_MIN_BLOCKS 8
+#endif
+
+template <typename T, bool STORE_H>
+__global__ void __launch_bounds__(kBlock, B200_LEAN_MIN_BLOCKS) tm_lean_h_kernel(const UpmlViewT<T> v)
+{
+  using C = typename Cx<T>::type;
+  int r, c; size_t k, k0;
+  if (!locate_rect(v, r, c, k, k0)) return;
+  const C *__restrict__ Ez = v.f[B200FDTD_TM_EZ];
+  const C ez = Ez[k], ez_j1 = Ez[k + 1], ez_i1 = Ez[k + v.pitch];
+  const C bx = v.f[B200FDTD_TM_BX][k] - (ez_j1 - ez);
+  const C by = v.f[B200FDTD_TM_BY][k] - ((-ez_i1) + ez);
+  v.f[B200FDTD_TM_BX][k] = bx;
+  v.f[B200FDTD_TM_BY][k] = by;
+  if (STORE_H) {
+    v.f[B200FDTD_TM_HX][k] = div_const(bx, v.mu0);
+    v.f[B200FDTD_TM_HY][k] = div_const(by, v.mu0);
+  }
+  if (v.peer_up_h != nullptr && c == v.c_last)
+    v.peer_up_h[(size_t)r * v.peer_up_pitch + (B200_JOFF - 1)] = div_const(bx, v.mu0);
+}
+
+// Rare work of the lean E kernels, kept out of line so the streaming path stays within 32
+// registers (8 blocks/SM): material cells (eps != 1: the division and the source terms with
+// their exp / sincos) and the opt-in point / line sources.  `v` is the kernel's __grid_constant__
+// parameter, so passing its address copies nothing.
+template <typename T, typename C = typename Cx<T>::type>
+static __device__ __noinline__ C lean_tm_material(const UpmlViewT<T> *v, int r, int c, size_t k0, T eps, C dz)
+{
+  C ez = div_eps(dz, eps);
+  tm_e_sources<T>(*v, r, c, k0, eps, ez);
+  return ez;
+}
+template <typename T, typename C = typename Cx<T>::type>
+static __device__ __noinline__ void lean_te_material(const UpmlViewT<T> *v, int r, int c, size_t k0, T eps_x, T eps_y,
+                                                     C dx, C dy, C *ex, C *ey)
+{
+  C x = div_eps(dx, eps_x), y = div_eps(dy, eps_y);
+  te_e_sources<T>(*v, r, c, k0, eps_x, eps_y, x, y);
+  *ex = x;
+  *ey = y;
+}
+
+// (The lean rectangle never touches row r_lo or column c_lo -- see b200fdtd_set_upml_tables -- so
+// every neighbour read below is a B value this engine keeps up to date.)
+template <typename T, bool FROM_B>
+__global__ void __launch_bounds__(kBlock, B200_LEAN_MIN_BLOCKS) tm_lean_e_kernel(const __grid_constant__ UpmlViewT<T> v)
+{
+  using C = typename Cx<T>::type;
+  int r, c; size_t k, k0;
+  if (!locate_rect(v, r, c, k, k0)) return;
+  C curl;
+  if (FROM_B) {
+    const C *__restrict__ Bx = v.f[B200FDTD_TM_BX];
+    const C *__restrict__ By = v.f[B200FDTD_TM_BY];
+    curl = v.mu0.r * (((By[k] - By[k - v.pitch]) - Bx[k]) + Bx[k - 1]);
+  } else {
+    const C *__restrict__ Hx = v.f[B200FDTD_TM_HX];
+    const C *__restrict__ Hy = v.f[B200FDTD_TM_HY];
+    curl = ((Hy[k] - Hy[k - v.pitch]) - Hx[k]) + Hx[k - 1];
+  }
+  const T eps = v.eps0[k0];
+  const C dz = v.f[B200FDTD_TM_DZ][k] + curl;
+  v.f[B200FDTD_TM_DZ][k] = dz;
+  C ez = dz;
+  if (eps != (T)1 || (long long)k0 == v.point_k || (v.line.enabled && r - 1 == v.line.i))
+    ez = lean_tm_material<T>(&v, r, c, k0, eps, dz);
+  v.f[B200FDTD_TM_EZ][k] = ez;
+  if (v.peer_down_e != nullptr && c == v.c_first)
+    v.peer_down_e[(size_t)r * v.peer_down_pitch + v.peer_down_col] = ez;
+}
+
+template <typename T, bool STORE_H>
+__global__ void __launch_bounds__(kBlock, B200_LEAN_MIN_BLOCKS) te_lean_h_kernel(const UpmlViewT<T> v)
+{
+  using C = typename Cx<T>::type;
+  int r, c; size_t k, k0;
+  if (!locate_rect(v, r, c, k, k0)) return;
+  const C *__restrict__ Ex = v.f[B200FDTD_TE_EX];
+  const C *__restrict__ Ey = v.f[B200FDTD_TE_EY];
+  const C ey_i1 = Ey[k + v.pitch], ey = Ey[k], ex_j1 = Ex[k + 1], ex = Ex[k];
+  const C bz = v.f[B200FDTD_TE_BZ][k] - (((ey_i1 - ey) - ex_j1) + ex);
+  v.f[B200FDTD_TE_BZ][k] = bz;
+  if (STORE_H) v.f[B200FDTD_TE_HZ][k] = div_const(bz, v.mu0);
+  if (v.peer_up_h != nullptr && c == v.c_last)
+    v.peer_up_h[(size_t)r * v.peer_up_pitch + (B200_JOFF - 1)] = div_const(bz, v.mu0);
+}
+
+template <typename T, bool FROM_B>
+__global__ void __launch_bounds__(kBlock, B200_LEAN_MIN_BLOCKS) te_lean_e_kernel(const __grid_constant__ UpmlViewT<T> v)
+{
+  using C = typename Cx<T>::type;
+  int r, c; size_t k, k0;
+  if (!locate_rect(v, r, c, k, k0)) return;
+  C curl_x, curl_y;                     // Hz - Hz(j-1) and -Hz + Hz(i-1)
+  if (FROM_B) {
+    const C *__restrict__ Bz = v.f[B200FDTD_TE_BZ];
+    const C bz = Bz[k];
+    curl_x = v.mu0.r * (bz - Bz[k - 1]);
+    curl_y = v.mu0.r * ((-bz) + Bz[k - v.pitch]);
+  } else {
+    const C *__restrict__ Hz = v.f[B200FDTD_TE_HZ];
+    const C hz = Hz[k];
+    curl_x = hz - Hz[k - 1];
+    curl_y = (-hz) + Hz[k - v.pitch];
+  }
+  const T eps_x = v.eps0[k0], eps_y = v.eps1[k0];
+  const C dx = v.f[B200FDTD_TE_DX][k] + curl_x;
+  const C dy = v.f[B200FDTD_TE_DY][k] + curl_y;
+  v.f[B200FDTD_TE_DX][k] = dx;
+  v.f[B200FDTD_TE_DY][k] = dy;
+  C ex = dx, ey = dy;
+  if (eps_x != (T)1 || eps_y != (T)1 || (long long)k0 == v.point_k)
+    lean_te_material<T>(&v, r, c, k0, eps_x, eps_y, dx, dy, &ex, &ey);
+  v.f[B200FDTD_TE_EX][k] = ex;
+  v.f[B200FDTD_TE_EY][k] = ey;
+  if (v.peer_down_e != nullptr && c == v.c_first)
+    v.peer_down_e[(size_t)r * v.peer_down_pitch + v.peer_down_col] = ex;
 }
 
 #include "upml_pairs_f32.cuh"
@@ -621,6 +738,61 @@ static PairGeom pair_geom(const b200fdtd_engine *e)
   return g;
 }
 
+// ---- launch geometry of the lean interior form -------------------------------------------
+static bool lean_active(const b200fdtd_engine *e)
+{
+  return e->lean_interior && e->lean_r_hi >= e->lean_r_lo && e->lean_c_hi >= e->lean_c_lo;
+}
+
+// blocks of one rectangle; narrow rectangles get narrow, tall blocks
+static unsigned add_rect(LaunchRect *rect, int &n, unsigned blk_end, int r_lo, int r_hi, int c_lo, int c_hi)
+{
+  if (r_hi < r_lo || c_hi < c_lo) return blk_end;
+  const int w = c_hi - c_lo + 1, h = r_hi - r_lo + 1;
+  int lg = 8;                                   // kBlock = 256 columns x 1 row
+  while (lg > 4 && (1 << (lg - 1)) >= w) lg--;  // down to 16 columns x 16 rows
+  LaunchRect &R = rect[n++];
+  R.r_lo = r_lo; R.r_hi = r_hi; R.c_lo = c_lo; R.c_hi = c_hi; R.bw_log2 = lg;
+  R.nbx = (w + (1 << lg) - 1) >> lg;
+  const int rows_per_blk = kBlock >> lg;
+  R.blk_end = blk_end + (unsigned)((long long)R.nbx * ((h + rows_per_blk - 1) / rows_per_blk));
+  return R.blk_end;
+}
+
+static void pad_rects(LaunchRect *rect, int n, unsigned blk_end)
+{
+  for (int q = n; q < 4; q++) {                 // unused entries: empty, never selected
+    rect[q] = rect[n ? n - 1 : 0];
+    rect[q].blk_end = blk_end;
+    rect[q].r_hi = rect[q].r_lo - 1;
+  }
+}
+
+template <typename T>
+static unsigned interior_rect(const b200fdtd_engine *e, UpmlViewT<T> &v)
+{
+  int n = 0;
+  const unsigned end = add_rect(v.rect, n, 0, e->lean_r_lo, e->lean_r_hi, e->lean_c_lo, e->lean_c_hi);
+  pad_rects(v.rect, n, end);
+  return end;
+}
+
+// the updated cells outside the lean rectangle: rows below and above it over the full width, then
+// the two side strips beside it
+template <typename T>
+static unsigned frame_rects(const b200fdtd_engine *e, UpmlViewT<T> &v)
+{
+  int n = 0;
+  unsigned end = 0;
+  end = add_rect(v.rect, n, end, e->r_lo, e->lean_r_lo - 1, e->c_lo, e->c_hi);
+  end = add_rect(v.rect, n, end, e->lean_r_hi + 1, e->r_hi, e->c_lo, e->c_hi);
+  end = add_rect(v.rect, n, end, e->lean_r_lo, e->lean_r_hi, e->c_lo, e->lean_c_lo - 1);
+  end = add_rect(v.rect, n, end, e->lean_r_lo, e->lean_r_hi, e->lean_c_hi + 1, e->c_hi);
+  if (n == 0) { memset(v.rect, 0, sizeof v.rect); return 0; }
+  pad_rects(v.rect, n, end);
+  return end;
+}
+
 template <typename T>
 static int launch_h(b200fdtd_engine *e, const b200fdtd_step_args *a)
 {
@@ -639,20 +811,34 @@ static int launch_h(b200fdtd_engine *e, const b200fdtd_step_args *a)
   }
   const long long nblk = (long long)v.nbx * (e->r_hi - e->r_lo + 1);
   const dim3 grid((unsigned)nblk, (unsigned)e->n_batch);
-  const bool lean = v.lean_r_hi >= v.lean_r_lo && v.lean_c_hi >= v.lean_c_lo;
-#define LAUNCH_H(KERNEL)                                                                    \
-  do {                                                                                      \
-    if (lean) {                                                                             \
-      if (e->store_h) KERNEL<T, true, true><<<grid, kBlock, 0, e->stream>>>(v);             \
-      else            KERNEL<T, false, true><<<grid, kBlock, 0, e->stream>>>(v);            \
-    } else {                                                                                \
-      if (e->store_h) KERNEL<T, true, false><<<grid, kBlock, 0, e->stream>>>(v);            \
-      else            KERNEL<T, false, false><<<grid, kBlock, 0, e->stream>>>(v);           \
-    }                                                                                       \
-  } while (0)
-  if (is_tm(e->g.kind)) LAUNCH_H(tm_upml_h_kernel);
-  else                  LAUNCH_H(te_upml_h_kernel);
-#undef LAUNCH_H
+  if (lean_active(e)) {
+    // the frame-free rectangle through the lean kernel, the frame around it through the full one
+    UpmlViewT<T> vi = v, vf = v;
+    const unsigned nb_i = interior_rect(e, vi), nb_f = frame_rects(e, vf);
+    const dim3 gi(nb_i, (unsigned)e->n_batch), gf(nb_f, (unsigned)e->n_batch);
+    if (is_tm(e->g.kind)) {
+      if (e->store_h) tm_lean_h_kernel<T, true><<<gi, kBlock, 0, e->stream>>>(vi);
+      else            tm_lean_h_kernel<T, false><<<gi, kBlock, 0, e->stream>>>(vi);
+      if (nb_f) {
+        if (e->store_h) tm_upml_h_kernel<T, true, true><<<gf, kBlock, 0, e->stream>>>(vf);
+        else            tm_upml_h_kernel<T, false, true><<<gf, kBlock, 0, e->stream>>>(vf);
+      }
+    } else {
+      if (e->store_h) te_lean_h_kernel<T, true><<<gi, kBlock, 0, e->stream>>>(vi);
+      else            te_lean_h_kernel<T, false><<<gi, kBlock, 0, e->stream>>>(vi);
+      if (nb_f) {
+        if (e->store_h) te_upml_h_kernel<T, true, true><<<gf, kBlock, 0, e->stream>>>(vf);
+        else            te_upml_h_kernel<T, false, true><<<gf, kBlock, 0, e->stream>>>(vf);
+      }
+    }
+    if (nb_f) e->launches++;
+  } else if (is_tm(e->g.kind)) {
+    if (e->store_h) tm_upml_h_kernel<T, true><<<grid, kBlock, 0, e->stream>>>(v);
+    else            tm_upml_h_kernel<T, false><<<grid, kBlock, 0, e->stream>>>(v);
+  } else {
+    if (e->store_h) te_upml_h_kernel<T, true><<<grid, kBlock, 0, e->stream>>>(v);
+    else            te_upml_h_kernel<T, false><<<grid, kBlock, 0, e->stream>>>(v);
+  }
   e->h_stale = !e->store_h;
   e->launches++;
   B200_CUDA(cudaGetLastError());
@@ -676,20 +862,33 @@ static int launch_e(b200fdtd_engine *e, const b200fdtd_step_args *a)
   }
   const long long nblk = (long long)v.nbx * (e->r_hi - e->r_lo + 1);
   const dim3 grid((unsigned)nblk, (unsigned)e->n_batch);
-  const bool lean = v.lean_r_hi >= v.lean_r_lo && v.lean_c_hi >= v.lean_c_lo;
-#define LAUNCH_E(KERNEL)                                                                    \
-  do {                                                                                      \
-    if (lean) {                                                                             \
-      if (e->h_stale) KERNEL<T, true, true><<<grid, kBlock, 0, e->stream>>>(v);             \
-      else            KERNEL<T, false, true><<<grid, kBlock, 0, e->stream>>>(v);            \
-    } else {                                                                                \
-      if (e->h_stale) KERNEL<T, true, false><<<grid, kBlock, 0, e->stream>>>(v);            \
-      else            KERNEL<T, false, false><<<grid, kBlock, 0, e->stream>>>(v);           \
-    }                                                                                       \
-  } while (0)
-  if (is_tm(e->g.kind)) LAUNCH_E(tm_upml_e_kernel);
-  else                  LAUNCH_E(te_upml_e_kernel);
-#undef LAUNCH_E
+  if (lean_active(e)) {
+    UpmlViewT<T> vi = v, vf = v;
+    const unsigned nb_i = interior_rect(e, vi), nb_f = frame_rects(e, vf);
+    const dim3 gi(nb_i, (unsigned)e->n_batch), gf(nb_f, (unsigned)e->n_batch);
+    if (is_tm(e->g.kind)) {
+      if (e->h_stale) tm_lean_e_kernel<T, true><<<gi, kBlock, 0, e->stream>>>(vi);
+      else            tm_lean_e_kernel<T, false><<<gi, kBlock, 0, e->stream>>>(vi);
+      if (nb_f) {
+        if (e->h_stale) tm_upml_e_kernel<T, true, true><<<gf, kBlock, 0, e->stream>>>(vf);
+        else            tm_upml_e_kernel<T, false, true><<<gf, kBlock, 0, e->stream>>>(vf);
+      }
+    } else {
+      if (e->h_stale) te_lean_e_kernel<T, true><<<gi, kBlock, 0, e->stream>>>(vi);
+      else            te_lean_e_kernel<T, false><<<gi, kBlock, 0, e->stream>>>(vi);
+      if (nb_f) {
+        if (e->h_stale) te_upml_e_kernel<T, true, true><<<gf, kBlock, 0, e->stream>>>(vf);
+        else            te_upml_e_kernel<T, false, true><<<gf, kBlock, 0, e->stream>>>(vf);
+      }
+    }
+    if (nb_f) e->launches++;
+  } else if (is_tm(e->g.kind)) {
+    if (e->h_stale) tm_upml_e_kernel<T, true><<<grid, kBlock, 0, e->stream>>>(v);
+    else            tm_upml_e_kernel<T, false><<<grid, kBlock, 0, e->stream>>>(v);
+  } else {
+    if (e->h_stale) te_upml_e_kernel<T, true><<<grid, kBlock, 0, e->stream>>>(v);
+    else            te_upml_e_kernel<T, false><<<grid, kBlock, 0, e->stream>>>(v);
+  }
   e->launches++;
   B200_CUDA(cudaGetLastError());
   return B200FDTD_OK;

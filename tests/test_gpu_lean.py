@@ -10,7 +10,7 @@ and checks that the lean cells really were taken (M / J stay untouched outside t
 import numpy as np
 import pytest
 
-from helpers import TOL_FARFIELD, TOL_FIELD, bit_equal, rel_err
+from helpers import TOL_FARFIELD, TOL_FIELD, rel_err
 from mpifdtd_b200 import binding as B
 from test_gpu_parity import oracle_for, run_slabs
 
@@ -95,20 +95,24 @@ def test_lean_mpi_variants_vs_exact_form(plugin_lib, solver, monkeypatch):
 
 
 @pytest.mark.parametrize("solver", ["TM_UPML_2D", "TE_UPML_2D"])
-def test_lean_slab_split_equals_single_engine(plugin_lib, solver):
-    """The lean decision is per cell (global position), so a y-slab split reproduces the single
-    engine bit for bit in this form too."""
-    npx, npy, steps = 96, 150, 200
+def test_lean_slab_split_vs_single_engine(plugin_lib, solver):
+    """y-slab split in the lean form.  A slab's first owned column stays with the frame kernels (its
+    low-side neighbour is a halo column only the H array holds), so those cells round differently
+    from the single engine's: equal to rounding, not bit for bit (the default form is, see
+    test_gpu_parity.py::test_slab_split_equals_single_engine)."""
+    npx, npy, steps = 96, 150, 300
     single = run_slabs("ZIGZAG", solver, npx, npy, steps, 1, angle=20)[0]
     split = run_slabs("ZIGZAG", solver, npx, npy, steps, 3, angle=20)
     ext = (B.C.c_int32 * 4)()
     single.L.b200fdtd_get_lean_extent(single.engine.h, ext)
     assert tuple(ext) == (10, npx - 11, 10, npy - 11)
-    for slot in range(9):
+    split[1].L.b200fdtd_get_lean_extent(split[1].engine.h, ext)
+    assert tuple(ext) == (10, npx - 11, split[1].j0 + 1, split[1].j0 + split[1].nj - 1)
+    for slot in (0, 2, 3, 5, 6, 8):           # E, D, H, B (TM: Ez Dz Hx Bx Hy By; TE: Ex Dx Ey Dy Hz Bz)
         whole = single.gather_field(slot)
         parts = np.concatenate([r.gather_field(slot) for r in split], axis=1)
-        assert bit_equal(parts.view(np.float64), whole.view(np.float64)), slot
-    assert np.abs(single.gather_field(0)).max() > 0
+        assert np.abs(whole).max() > 0, slot
+        assert rel_err(parts, whole) <= TOL_FIELD, slot
     for r in split + [single]:
         r.close()
 
