@@ -113,6 +113,32 @@ __device__ __forceinline__ void tm_e_sources(const UpmlViewT<T> &v, int r, int c
   }
 }
 
+template <typename T, typename C>
+__device__ __forceinline__ void te_e_sources(const UpmlViewT<T> &v, int r, int c, size_t k0, T eps_x, T eps_y, C &ex,
+                                             C &ey);
+
+// Rare work of the lean E kernels, kept out of line so the streaming path stays within 32
+// registers (8 blocks/SM): material cells (eps != 1: the division and the source terms with their
+// exp / sincos) and the opt-in point / line sources.  `v` is the kernel's __grid_constant__
+// parameter, so passing its address copies nothing.  (The same trick does nothing for the full
+// kernels: forcing them to 6-8 blocks/SM spills the coefficient arithmetic, measured slower.)
+template <typename T, typename C = typename Cx<T>::type>
+static __device__ __noinline__ C tm_e_material(const UpmlViewT<T> *v, int r, int c, size_t k0, T eps, C dz)
+{
+  C ez = div_eps(dz, eps);
+  tm_e_sources<T>(*v, r, c, k0, eps, ez);
+  return ez;
+}
+template <typename T, typename C = typename Cx<T>::type>
+static __device__ __noinline__ void te_e_material(const UpmlViewT<T> *v, int r, int c, size_t k0, T eps_x, T eps_y,
+                                                     C dx, C dy, C *ex, C *ey)
+{
+  C x = div_eps(dx, eps_x), y = div_eps(dy, eps_y);
+  te_e_sources<T, C>(*v, r, c, k0, eps_x, eps_y, x, y);
+  *ex = x;
+  *ey = y;
+}
+
 template <typename T, typename C = typename Cx<T>::type>
 __device__ __forceinline__ void tm_e_math(const UpmlViewT<T> &v, int r, int c, size_t k0, C hy, C hy_i0, C hx, C hx_j0,
                                           C jz_old, C dz_old, T eps, T c_jz, T c_jzh, T c_dz, T c_dzjz, C &jz, C &dz,
@@ -135,7 +161,7 @@ __device__ __forceinline__ void te_h_math(C ey_i1, C ey, C ex_j1, C ex, C mz_old
 }
 
 // the source terms the reference adds to Ex / Ey after calcE (shared by the full and the lean E phase)
-template <typename T, typename C = typename Cx<T>::type>
+template <typename T, typename C>
 __device__ __forceinline__ void te_e_sources(const UpmlViewT<T> &v, int r, int c, size_t k0, T eps_x, T eps_y, C &ex,
                                              C &ey)
 {
@@ -166,7 +192,7 @@ __device__ __forceinline__ void te_e_math(const UpmlViewT<T> &v, int r, int c, s
 
   ex = div_eps(dx, eps_x);            // fdtdTE_upml.c:283
   ey = div_eps(dy, eps_y);            // fdtdTE_upml.c:289
-  te_e_sources<T>(v, r, c, k0, eps_x, eps_y, ex, ey);
+  te_e_sources<T, C>(v, r, c, k0, eps_x, eps_y, ex, ey);
 }
 
 // ------------------------------------------------------------------ TM -----
@@ -216,7 +242,7 @@ __device__ __forceinline__ void tm_upml_h_cell(const UpmlViewT<T> &v, int r, int
 }
 
 template <typename T, bool STORE_H, bool RECTS = false>
-__global__ void __launch_bounds__(kBlock, B200_H_MIN_BLOCKS) tm_upml_h_kernel(const UpmlViewT<T> v)
+__global__ void __launch_bounds__(kBlock, B200_H_MIN_BLOCKS) tm_upml_h_kernel(const __grid_constant__ UpmlViewT<T> v)
 {
   int r, c; size_t k, k0;
   if (!(RECTS ? locate_rect(v, r, c, k, k0) : locate(v, r, c, k, k0))) return;
@@ -273,7 +299,7 @@ __device__ __forceinline__ void tm_upml_e_cell(const UpmlViewT<T> &v, int r, int
 }
 
 template <typename T, bool FROM_B, bool RECTS = false>
-__global__ void __launch_bounds__(kBlock, B200_E_MIN_BLOCKS) tm_upml_e_kernel(const UpmlViewT<T> v)
+__global__ void __launch_bounds__(kBlock, B200_E_MIN_BLOCKS) tm_upml_e_kernel(const __grid_constant__ UpmlViewT<T> v)
 {
   int r, c; size_t k, k0;
   if (!(RECTS ? locate_rect(v, r, c, k, k0) : locate(v, r, c, k, k0))) return;
@@ -313,7 +339,7 @@ __device__ __forceinline__ void te_upml_h_cell(const UpmlViewT<T> &v, int r, int
 }
 
 template <typename T, bool STORE_H, bool RECTS = false>
-__global__ void __launch_bounds__(kBlock, B200_TE_H_MIN_BLOCKS) te_upml_h_kernel(const UpmlViewT<T> v)
+__global__ void __launch_bounds__(kBlock, B200_TE_H_MIN_BLOCKS) te_upml_h_kernel(const __grid_constant__ UpmlViewT<T> v)
 {
   int r, c; size_t k, k0;
   if (!(RECTS ? locate_rect(v, r, c, k, k0) : locate(v, r, c, k, k0))) return;
@@ -369,7 +395,7 @@ __device__ __forceinline__ void te_upml_e_cell(const UpmlViewT<T> &v, int r, int
 }
 
 template <typename T, bool FROM_B, bool RECTS = false>
-__global__ void __launch_bounds__(kBlock, B200_TE_E_MIN_BLOCKS) te_upml_e_kernel(const UpmlViewT<T> v)
+__global__ void __launch_bounds__(kBlock, B200_TE_E_MIN_BLOCKS) te_upml_e_kernel(const __grid_constant__ UpmlViewT<T> v)
 {
   int r, c; size_t k, k0;
   if (!(RECTS ? locate_rect(v, r, c, k, k0) : locate(v, r, c, k, k0))) return;
@@ -393,7 +419,7 @@ __global__ void __launch_bounds__(kBlock, B200_TE_E_MIN_BLOCKS) te_upml_e_kernel
 #endif
 
 template <typename T, bool STORE_H>
-__global__ void __launch_bounds__(kBlock, B200_LEAN_MIN_BLOCKS) tm_lean_h_kernel(const UpmlViewT<T> v)
+__global__ void __launch_bounds__(kBlock, B200_LEAN_MIN_BLOCKS) tm_lean_h_kernel(const __grid_constant__ UpmlViewT<T> v)
 {
   using C = typename Cx<T>::type;
   int r, c; size_t k, k0;
@@ -410,27 +436,6 @@ __global__ void __launch_bounds__(kBlock, B200_LEAN_MIN_BLOCKS) tm_lean_h_kernel
   }
   if (v.peer_up_h != nullptr && c == v.c_last)
     v.peer_up_h[(size_t)r * v.peer_up_pitch + (B200_JOFF - 1)] = div_const(bx, v.mu0);
-}
-
-// Rare work of the lean E kernels, kept out of line so the streaming path stays within 32
-// registers (8 blocks/SM): material cells (eps != 1: the division and the source terms with
-// their exp / sincos) and the opt-in point / line sources.  `v` is the kernel's __grid_constant__
-// parameter, so passing its address copies nothing.
-template <typename T, typename C = typename Cx<T>::type>
-static __device__ __noinline__ C lean_tm_material(const UpmlViewT<T> *v, int r, int c, size_t k0, T eps, C dz)
-{
-  C ez = div_eps(dz, eps);
-  tm_e_sources<T>(*v, r, c, k0, eps, ez);
-  return ez;
-}
-template <typename T, typename C = typename Cx<T>::type>
-static __device__ __noinline__ void lean_te_material(const UpmlViewT<T> *v, int r, int c, size_t k0, T eps_x, T eps_y,
-                                                     C dx, C dy, C *ex, C *ey)
-{
-  C x = div_eps(dx, eps_x), y = div_eps(dy, eps_y);
-  te_e_sources<T>(*v, r, c, k0, eps_x, eps_y, x, y);
-  *ex = x;
-  *ey = y;
 }
 
 // (The lean rectangle never touches row r_lo or column c_lo -- see b200fdtd_set_upml_tables -- so
@@ -456,14 +461,14 @@ __global__ void __launch_bounds__(kBlock, B200_LEAN_MIN_BLOCKS) tm_lean_e_kernel
   v.f[B200FDTD_TM_DZ][k] = dz;
   C ez = dz;
   if (eps != (T)1 || (long long)k0 == v.point_k || (v.line.enabled && r - 1 == v.line.i))
-    ez = lean_tm_material<T>(&v, r, c, k0, eps, dz);
+    ez = tm_e_material<T>(&v, r, c, k0, eps, dz);
   v.f[B200FDTD_TM_EZ][k] = ez;
   if (v.peer_down_e != nullptr && c == v.c_first)
     v.peer_down_e[(size_t)r * v.peer_down_pitch + v.peer_down_col] = ez;
 }
 
 template <typename T, bool STORE_H>
-__global__ void __launch_bounds__(kBlock, B200_LEAN_MIN_BLOCKS) te_lean_h_kernel(const UpmlViewT<T> v)
+__global__ void __launch_bounds__(kBlock, B200_LEAN_MIN_BLOCKS) te_lean_h_kernel(const __grid_constant__ UpmlViewT<T> v)
 {
   using C = typename Cx<T>::type;
   int r, c; size_t k, k0;
@@ -503,7 +508,7 @@ __global__ void __launch_bounds__(kBlock, B200_LEAN_MIN_BLOCKS) te_lean_e_kernel
   v.f[B200FDTD_TE_DY][k] = dy;
   C ex = dx, ey = dy;
   if (eps_x != (T)1 || eps_y != (T)1 || (long long)k0 == v.point_k)
-    lean_te_material<T>(&v, r, c, k0, eps_x, eps_y, dx, dy, &ex, &ey);
+    te_e_material<T>(&v, r, c, k0, eps_x, eps_y, dx, dy, &ex, &ey);
   v.f[B200FDTD_TE_EX][k] = ex;
   v.f[B200FDTD_TE_EY][k] = ey;
   if (v.peer_down_e != nullptr && c == v.c_first)
@@ -540,7 +545,7 @@ struct PipeArgs {
 #endif
 
 template <typename T, bool TM>
-__global__ void __launch_bounds__(kBlock, B200_PIPE_MIN_BLOCKS) upml_pipelined_kernel(const UpmlViewT<T> v, const PipeArgs p)
+__global__ void __launch_bounds__(kBlock, B200_PIPE_MIN_BLOCKS) upml_pipelined_kernel(const __grid_constant__ UpmlViewT<T> v, const PipeArgs p)
 {
   __shared__ unsigned long long s_task;
   const long long per_stage = 2LL * p.nbx;

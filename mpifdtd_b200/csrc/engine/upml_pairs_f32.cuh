@@ -42,7 +42,7 @@ __device__ __forceinline__ bool locate_pair(const UpmlViewT<float> &v, const Pai
 }
 
 // ------------------------------------------------------------------ TM -----
-__global__ void __launch_bounds__(kBlock, 4) tm_upml_h_pair_kernel(const UpmlViewT<float> v, const PairGeom g)
+__global__ void __launch_bounds__(kBlock, 4) tm_upml_h_pair_kernel(const __grid_constant__ UpmlViewT<float> v, const PairGeom g)
 {
   int r, c0; size_t k, k0; bool va, vb;
   if (!locate_pair(v, g, r, c0, k, k0, va, vb)) return;
@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(kBlock, 4) tm_upml_h_pair_kernel(const UpmlVie
   }
 }
 
-__global__ void __launch_bounds__(kBlock, 4) tm_upml_e_pair_kernel(const UpmlViewT<float> v, const PairGeom g)
+__global__ void __launch_bounds__(kBlock, 4) tm_upml_e_pair_kernel(const __grid_constant__ UpmlViewT<float> v, const PairGeom g)
 {
   int r, c0; size_t k, k0; bool va, vb;
   if (!locate_pair(v, g, r, c0, k, k0, va, vb)) return;
@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(kBlock, 4) tm_upml_e_pair_kernel(const UpmlVie
 }
 
 // ------------------------------------------------------------------ TE -----
-__global__ void __launch_bounds__(kBlock, 4) te_upml_h_pair_kernel(const UpmlViewT<float> v, const PairGeom g)
+__global__ void __launch_bounds__(kBlock, 4) te_upml_h_pair_kernel(const __grid_constant__ UpmlViewT<float> v, const PairGeom g)
 {
   int r, c0; size_t k, k0; bool va, vb;
   if (!locate_pair(v, g, r, c0, k, k0, va, vb)) return;
@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(kBlock, 4) te_upml_h_pair_kernel(const UpmlVie
 #ifndef B200_TE_E_PAIR_MIN_BLOCKS
 #define B200_TE_E_PAIR_MIN_BLOCKS 3     /* 4 blocks/SM (64 registers) spills */
 #endif
-__global__ void __launch_bounds__(kBlock, B200_TE_E_PAIR_MIN_BLOCKS) te_upml_e_pair_kernel(const UpmlViewT<float> v, const PairGeom g)
+__global__ void __launch_bounds__(kBlock, B200_TE_E_PAIR_MIN_BLOCKS) te_upml_e_pair_kernel(const __grid_constant__ UpmlViewT<float> v, const PairGeom g)
 {
   int r, c0; size_t k, k0; bool va, vb;
   if (!locate_pair(v, g, r, c0, k, k0, va, vb)) return;

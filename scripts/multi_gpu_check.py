@@ -2,7 +2,7 @@
 reproduce the single-GPU run: fields bit for bit, far field to summation-order noise.
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
-        --master-port 29511 scripts/multi_gpu_check.py [solver] [npx] [npy] [steps]
+        --master-port 29511 scripts/multi_gpu_check.py [solver] [npx] [npy] [steps] [nccl|peer] [f64|f32] [exact|lean]
 """
 import os
 import sys
@@ -20,6 +20,9 @@ npy = int(sys.argv[3]) if len(sys.argv) > 3 else 240
 steps = int(sys.argv[4]) if len(sys.argv) > 4 else 600
 halo = sys.argv[5] if len(sys.argv) > 5 else "nccl"          # "nccl" or "peer" (direct NVLink stores)
 precision = sys.argv[6] if len(sys.argv) > 6 else "f64"     # "f32": the optional single-precision path
+form = sys.argv[7] if len(sys.argv) > 7 else "exact"        # "lean": B200FDTD_OPT_LEAN_INTERIOR (tolerance form)
+if form == "lean":
+    os.environ["B200FDTD_LEAN_INTERIOR"] = "1"
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -55,13 +58,18 @@ with torch.cuda.stream(stream):
             single.step()
         for n, slot in enumerate((0, 3, 6)):
             want = single.gather_field(slot).view(np.float64)
-            same = np.array_equal(parts[n], want)
-            print("slot", slot, "bit-identical:", same, "max", np.abs(want).max())
+            if form == "lean":       # a slab's first column rounds differently from the single engine's
+                err = np.abs(parts[n] - want).max() / np.abs(want).max()
+                same = err <= 1e-12
+                print("slot", slot, "rel err", err, "max", np.abs(want).max())
+            else:
+                same = np.array_equal(parts[n], want)
+                print("slot", slot, "bit-identical:", same, "max", np.abs(want).max())
             ok &= same
         want_far = single.far_field()
         err = np.abs(far - want_far).max() / np.abs(want_far).max()
         print("far field rel err vs single GPU:", err)
-        ok &= err < 1e-12
+        ok &= err < (1e-10 if form == "lean" else 1e-12)
         single.close()
         print("MULTI_GPU_CHECK", halo, "OK" if ok else "FAIL")
 dist.barrier()
