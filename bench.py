@@ -417,13 +417,17 @@ def gpu_arm(args):
         ach_e = bytes_e * cells_rank / (ms_e * 1e-3) / 1e9
         step_gbs = bytes_step * (value / world) * 1e9 / 1e9
         # ncu prints the kernel as <double, STORE_H, LEAN>: "<0,0>" default form, "<0,1>" lean
+        # kernel names as ncu prints them, minus "double, " and blanks: the full kernels are
+        # <STORE_H, RECTS> ("<0>" in captures older than the RECTS parameter), the lean ones <STORE_H>
         traffic, traffic_src = None, None
         if args.precision == "f64":
-            for tag in (["0,1"] if args.lean else ["0,0", "0"]):    # "<0>": captures older than the LEAN parameter
-                traffic, traffic_src = ncu_traffic(kname + "_upml_h_kernel<%s>" % tag, cells_rank)
+            tags = [kname + "_lean_h_kernel<0>"] if args.lean else [kname + "_upml_h_kernel<0,0>", kname + "_upml_h_kernel<0>"]
+            for tag in tags:
+                traffic, traffic_src = ncu_traffic(tag, cells_rank)
                 if traffic is not None:
                     break
-        lean_tag = ", LEAN=true" if args.lean else ""
+        h_name = kname + ("_lean_h_kernel<STORE_H=false>" if args.lean else "_upml_h_kernel<STORE_H=false>")
+        e_name = kname + ("_lean_e_kernel<FROM_B=true>" if args.lean else "_upml_e_kernel<FROM_B=true>")
         line = {
             "metric": "Gcell-updates/s", "value": value, "unit": "Gcell-updates/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_max / K,
@@ -432,12 +436,12 @@ def gpu_arm(args):
             "config": workload_config(world, n=args.n, solver=args.solver, model=args.model, strong=args.strong,
                                       halo={"peer": "direct NVLink peer stores + device flags",
                                             "nccl": "NCCL send/recv"}[args.halo]),
-            "roofline": {"bound": "hbm", "kernel": kname + "_upml_h_kernel<STORE_H=false%s>" % lean_tag, "achieved": ach_h,
+            "roofline": {"bound": "hbm", "kernel": h_name, "achieved": ach_h,
                          "peak": peak, "unit": "GB/s", "frac": ach_h / peak, "peak_source": peak_kind,
                          "traffic": traffic, "traffic_source": traffic_src,
                          "algorithmic_bytes_per_launch": bytes_h * cells_rank, "ms_per_launch": ms_h,
                          "algorithmic_bytes_per_cell": bytes_h,
-                         "e_phase": {"kernel": kname + "_upml_e_kernel<FROM_B=true%s>" % lean_tag, "achieved": ach_e,
+                         "e_phase": {"kernel": e_name, "achieved": ach_e,
                                      "frac": ach_e / peak, "ms_per_launch": ms_e,
                                      "algorithmic_bytes_per_cell": bytes_e},
                          "step": {"algorithmic_bytes_per_cell_update": bytes_step,
