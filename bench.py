@@ -304,6 +304,8 @@ def gpu_arm(args):
                 dist.barrier()
             torch.cuda.synchronize()
 
+        form = run.engine.step_form()    # 0 full kernels, 1 unit-coefficient interior + frame, 2 lean interior + frame
+
         # ---- value: device-resident K steps + deferred projection ----------------
         for _ in range(W):
             run.step()
@@ -421,13 +423,14 @@ def gpu_arm(args):
         # <STORE_H, RECTS> ("<0>" in captures older than the RECTS parameter), the lean ones <STORE_H>
         traffic, traffic_src = None, None
         if args.precision == "f64":
-            tags = [kname + "_lean_h_kernel<0>"] if args.lean else [kname + "_upml_h_kernel<0,0>", kname + "_upml_h_kernel<0>"]
+            tags = {0: [kname + "_upml_h_kernel<0,0>", kname + "_upml_h_kernel<0>"],
+                    1: [kname + "_unit_h_kernel<0>"], 2: [kname + "_lean_h_kernel<0>"]}[form]
             for tag in tags:
                 traffic, traffic_src = ncu_traffic(tag, cells_rank)
                 if traffic is not None:
                     break
-        h_name = kname + ("_lean_h_kernel<STORE_H=false>" if args.lean else "_upml_h_kernel<STORE_H=false>")
-        e_name = kname + ("_lean_e_kernel<FROM_B=true>" if args.lean else "_upml_e_kernel<FROM_B=true>")
+        stem = kname + {0: "_upml", 1: "_unit", 2: "_lean"}[form]
+        h_name, e_name = stem + "_h_kernel<STORE_H=false>", stem + "_e_kernel<FROM_B=true>"
         line = {
             "metric": "Gcell-updates/s", "value": value, "unit": "Gcell-updates/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_max / K,
@@ -453,6 +456,10 @@ def gpu_arm(args):
                     "path": "b200fdtd_set_eps_slab(pinned host eps) + K x [mpifdtd_upml_step_args + "
                             "b200fdtd_step + field_nextStep] + b200fdtd_get_field_slab(Ez -> pinned host)"},
             "gpu_launches": int(launches),
+            "step_form": {0: "one full kernel per phase",
+                          1: "unit-coefficient interior kernel + frame kernel per phase (bit-identical to the "
+                             "one-kernel form; B200FDTD_OPT_UNIT_SPLIT, default on large grids)",
+                          2: "lean interior kernel + frame kernel per phase (tolerance form)"}[form],
             "clocks": clocks,
             "device_bytes": run.engine.device_bytes(),
         }

@@ -376,6 +376,14 @@ enum {
   B200FDTD_OPT_PIPE_BAND_ROWS = 6, /* rows per band of the pipelined step (default 4)            */
   B200FDTD_OPT_F32_PAIRS = 7,  /* single-precision engines: 1 (default) two cells per thread with
                                   128-bit accesses, 0 the one-cell-per-thread kernels; identical bits */
+  B200FDTD_OPT_UNIT_SPLIT = 9,  /* UPML kinds, double precision, two-kernel step.  Inside the frame-free
+                                  rectangle (b200fdtd_upml_interior) every coefficient is exactly 1.0
+                                  and 1.0 * x == x, so dedicated kernels evaluate the reference's
+                                  expressions there without table reads and multiplications -- same
+                                  bits, fewer registers, more loads in flight; the frame goes through
+                                  the full kernels.  0: one kernel per phase over the whole grid,
+                                  1: split whenever the rectangle exists, 2 (default): split when the
+                                  rectangle holds >= 2^20 cells and >= 3/4 of the updated cells.     */
   B200FDTD_OPT_LEAN_INTERIOR = 8 /* UPML kinds, two-kernel step.  1: cells outside the absorbing frame
                                   -- where every UPML coefficient of fdtdTM_upml.c:253-271 /
                                   fdtdTE_upml.c:384-403 is exactly 1 -- advance B and D directly
@@ -396,8 +404,12 @@ int b200fdtd_set_option(b200fdtd_engine *e, int32_t option, int32_t value);
  * out = { i_lo, i_hi, j_lo, j_hi } inclusive, an empty range as lo > hi. */
 int b200fdtd_upml_interior(int32_t kind, const double *tab_i, int32_t n_px, const double *tab_j, int32_t n_py,
                            int32_t out[4]);
-/* what the engine uses (global i / j of this slab's share), {1,0,1,0} when the option is off */
+/* the rectangle this engine's split forms use (global i / j of this slab's share; without row
+ * r_lo / column c_lo, which stay with the frame kernels); {1,0,1,0} when no split form is active */
 int b200fdtd_get_lean_extent(b200fdtd_engine *e, int32_t out[4]);
+/* which form b200fdtd_step / phase_h / phase_e launch right now: 0 one full kernel per phase,
+ * 1 unit-coefficient interior kernel + frame (bit-identical to 0), 2 lean interior + frame */
+int b200fdtd_get_step_form(b200fdtd_engine *e, int32_t *form);
 
 /* Device self-test: the kernels replace `x / d` (d loop-invariant, e.g. MU_0_S) by a
  * reciprocal-multiply with an FMA correction that is claimed to be the identical,

@@ -27,6 +27,7 @@ D_X, D_Y, D_XY = 0, 1, 2
 UPML_TABS = 6
 OPT_FUSED, OPT_STORE_H, OPT_BAND_ROWS, OPT_FUSED_SHAPE, OPT_PIPELINED, OPT_PIPE_BAND_ROWS, OPT_F32_PAIRS = 1, 2, 3, 4, 5, 6, 7
 OPT_LEAN_INTERIOR = 8
+OPT_UNIT_SPLIT = 9
 
 
 class FieldInfo(C.Structure):
@@ -205,6 +206,7 @@ def lib():
     L.b200fdtd_struct_size.argtypes = [i32]
     L.b200fdtd_upml_interior.argtypes = [i32, vp, i32, vp, i32, vp]
     L.b200fdtd_get_lean_extent.argtypes = [vp, vp]
+    L.b200fdtd_get_step_form.argtypes = [vp, C.POINTER(i32)]
     L.mpifdtd_readConfig.argtypes = [C.c_char_p, vp]
     for name in ("fdtdTM_upml_getHx", "fdtdTM_upml_getHy", "fdtdTM_upml_getEz",
                  "fdtdTE_upml_getEx", "fdtdTE_upml_getEy", "fdtdTE_upml_getHz",
@@ -475,6 +477,12 @@ class Engine:
 
     def set_option(self, option, value):
         check(self.L.b200fdtd_set_option(self.h, option, value), "set_option")
+
+    def step_form(self):
+        """0 one full kernel per phase, 1 unit-coefficient interior + frame, 2 lean interior + frame."""
+        form = C.c_int32(-1)
+        check(self.L.b200fdtd_get_step_form(self.h, C.byref(form)), "get_step_form")
+        return form.value
 
     def project(self):
         check(self.L.b200fdtd_ntff_project(self.h), "ntff_project")

@@ -175,6 +175,8 @@ int b200fdtd_create(const b200fdtd_grid *grid, b200fdtd_engine **out)
   if (const char *v = getenv("B200FDTD_PIPE_BAND_ROWS")) e->pipe.band_rows = atoi(v);
   if (const char *v = getenv("B200FDTD_FUSED_SHAPE")) e->fused_variant = atoi(v);
   if (const char *v = getenv("B200FDTD_BAND_ROWS")) e->fused.band_h = atoi(v);
+  e->unit_split = 2;
+  if (const char *v = getenv("B200FDTD_UNIT_SPLIT")) e->unit_split = atoi(v);
   e->lean_interior = false;
   if (const char *v = getenv("B200FDTD_LEAN_INTERIOR")) e->lean_interior = atoi(v) != 0 && kind_is_upml(grid->kind);
   e->lean_r_lo = e->lean_c_lo = 1;
@@ -376,11 +378,18 @@ int b200fdtd_upml_interior(int32_t kind, const double *tab_i, int32_t n_px, cons
   return B200FDTD_OK;
 }
 
+int b200fdtd_get_step_form(b200fdtd_engine *e, int32_t *form)
+{
+  if (!e || !form) return b200_fail(B200FDTD_ERR_ARG, "NULL argument");
+  *form = kind_is_upml(e->g.kind) && e->have_tabs ? b200_step_form(e) : 0;
+  return B200FDTD_OK;
+}
+
 int b200fdtd_get_lean_extent(b200fdtd_engine *e, int32_t out[4])
 {
   if (!e || !out) return b200_fail(B200FDTD_ERR_ARG, "NULL argument");
   out[0] = out[2] = 1; out[1] = out[3] = 0;
-  if (e->lean_interior && e->lean_r_hi >= e->lean_r_lo && e->lean_c_hi >= e->lean_c_lo) {
+  if (kind_is_upml(e->g.kind) && e->have_tabs && b200_step_form(e) != 0) {
     out[0] = e->lean_r_lo - 1;  out[1] = e->lean_r_hi - 1;
     out[2] = e->lean_c_lo - B200_JOFF + e->g.j0;  out[3] = e->lean_c_hi - B200_JOFF + e->g.j0;
   }
@@ -701,6 +710,10 @@ int b200fdtd_set_option(b200fdtd_engine *e, int32_t option, int32_t value)
     B200_CUDA(cudaStreamSynchronize(e->stream));
     b200_pipe_release(e);
     e->pipe.band_rows = value;
+    return B200FDTD_OK;
+  case B200FDTD_OPT_UNIT_SPLIT:
+    if (value < 0 || value > 2) return b200_fail(B200FDTD_ERR_ARG, "unit split: 0 off, 1 on, 2 auto");
+    e->unit_split = value;
     return B200FDTD_OK;
   case B200FDTD_OPT_LEAN_INTERIOR:
     if (value && !kind_is_upml(e->g.kind))

@@ -113,6 +113,7 @@ struct b200fdtd_engine {
   bool store_h;             // the fused kernel also writes Hx/Hy (264 instead of 232 B/cell)
   bool h_stale;             // Hx/Hy arrays lag Bx/By (fused step without store_h)
   int fused_variant;        // launch shape of the fused kernel (tuning)
+  int unit_split;           // frame-free rectangle through the unit-coefficient kernels: 0 off, 1 on, 2 auto
   bool lean_interior;       // opt-in: cells outside the absorbing frame skip the M / J recurrences
   int lean_r_lo, lean_r_hi, lean_c_lo, lean_c_hi;   // that region (layout coordinates), from the tables
   uint64_t launches;
@@ -134,6 +135,7 @@ int b200_fail(int code, const char *fmt, ...);
 
 // launchers (upml_kernels.cu)
 int b200_launch_upml_h(b200fdtd_engine *e, const b200fdtd_step_args *a);
+int b200_step_form(const b200fdtd_engine *e);   // 0 one kernel per phase, 1 unit-coefficient interior + frame, 2 lean interior + frame
 int b200_launch_upml_e(b200fdtd_engine *e, const b200fdtd_step_args *a);
 int b200_launch_upml_pipelined(b200fdtd_engine *e, const b200fdtd_step_args *a);
 void b200_pipe_release(b200fdtd_engine *e);

@@ -402,6 +402,146 @@ __global__ void __launch_bounds__(kBlock, B200_TE_E_MIN_BLOCKS) te_upml_e_kernel
   te_upml_e_cell<T, FROM_B>(v, r, c, k, k0);
 }
 
+// ------------------------------------------------------------------ unit-coefficient interior -----
+// The DEFAULT form on large grids.  Inside the frame-free rectangle every coefficient the full
+// kernels would fetch is exactly 1.0, and 1.0 * x == x for every double, so the reference's
+// expressions can be evaluated there without the twelve table reads, the two quotients and the
+// multiplications -- with the identical IEEE results, operation for operation:
+//   Mx' = Mx - (Ez(j+1) - Ez),  Bx' = (Bx + Mx') - Mx,  Jz' = Jz + curl H,  Dz' = (Dz + Jz') - Jz ...
+// Same arrays, same 264 / 288 B per cell-update, bit-identical to the one-kernel-per-phase form
+// (tests/test_gpu_unit.py); what it buys is registers (more blocks per SM, more loads in flight).
+// The frame goes through the full kernels (RECTS = true), exactly as in the lean form below.
+// blocks/SM measured at 16384^2 (scripts/variant_bench.sh): TM H 4/5/6/7/8 -> 5.60/5.60/5.58/5.67/5.67 ms,
+// TM E 4/5/6/7 -> 5.41/4.93/5.00/5.03 ms, TE E 4/5/6/7/8 -> 8.65/8.68/8.60/10.0/10.0 ms
+#ifndef B200_UNIT_H_MIN_BLOCKS
+#define B200_UNIT_H_MIN_BLOCKS 6
+#endif
+#ifndef B200_UNIT_E_MIN_BLOCKS
+#define B200_UNIT_E_MIN_BLOCKS 5
+#endif
+#ifndef B200_UNIT_TE_H_MIN_BLOCKS
+#define B200_UNIT_TE_H_MIN_BLOCKS 6
+#endif
+#ifndef B200_UNIT_TE_E_MIN_BLOCKS
+#define B200_UNIT_TE_E_MIN_BLOCKS 6
+#endif
+
+template <typename T, bool STORE_H>
+__global__ void __launch_bounds__(kBlock, B200_UNIT_H_MIN_BLOCKS) tm_unit_h_kernel(const __grid_constant__ UpmlViewT<T> v)
+{
+  using C = typename Cx<T>::type;
+  int r, c; size_t k, k0;
+  if (!locate_rect(v, r, c, k, k0)) return;
+  const C *__restrict__ Ez = v.f[B200FDTD_TM_EZ];
+  const C ez = Ez[k], ez_j1 = Ez[k + 1], ez_i1 = Ez[k + v.pitch];
+  const C mx_old = v.f[B200FDTD_TM_MX][k], bx_old = v.f[B200FDTD_TM_BX][k];
+  const C my_old = v.f[B200FDTD_TM_MY][k], by_old = v.f[B200FDTD_TM_BY][k];
+  const C mx = mx_old - (ez_j1 - ez);              // fdtdTM_upml.c:188 with C_MX = C_MXEZ = 1
+  const C bx = (bx_old + mx) - mx_old;             // :189 with C_BX = C_BXMX1 = C_BXMX0 = 1
+  const C my = my_old - ((-ez_i1) + ez);           // :197
+  const C by = (by_old + my) - my_old;             // :198 with C_BY = C_BYMY1 = C_BYMY0 = 1
+  v.f[B200FDTD_TM_MX][k] = mx;
+  v.f[B200FDTD_TM_BX][k] = bx;
+  v.f[B200FDTD_TM_MY][k] = my;
+  v.f[B200FDTD_TM_BY][k] = by;
+  if (STORE_H) {
+    v.f[B200FDTD_TM_HX][k] = div_const(bx, v.mu0);
+    v.f[B200FDTD_TM_HY][k] = div_const(by, v.mu0);
+  }
+  if (v.peer_up_h != nullptr && c == v.c_last)
+    v.peer_up_h[(size_t)r * v.peer_up_pitch + (B200_JOFF - 1)] = div_const(bx, v.mu0);
+}
+
+template <typename T, bool FROM_B>
+__global__ void __launch_bounds__(kBlock, B200_UNIT_E_MIN_BLOCKS) tm_unit_e_kernel(const __grid_constant__ UpmlViewT<T> v)
+{
+  using C = typename Cx<T>::type;
+  int r, c; size_t k, k0;
+  if (!locate_rect(v, r, c, k, k0)) return;
+  C hy, hy_i0, hx, hx_j0;
+  if (FROM_B) {       // the rectangle never touches row r_lo / column c_lo: every neighbour is a kept B value
+    const C *__restrict__ Bx = v.f[B200FDTD_TM_BX];
+    const C *__restrict__ By = v.f[B200FDTD_TM_BY];
+    const C by = By[k], bx = Bx[k], by_i0 = By[k - v.pitch], bx_j0 = Bx[k - 1];
+    hy = div_const(by, v.mu0);
+    hx = div_const(bx, v.mu0);
+    hy_i0 = div_const(by_i0, v.mu0);
+    hx_j0 = div_const(bx_j0, v.mu0);
+  } else {
+    const C *__restrict__ Hx = v.f[B200FDTD_TM_HX];
+    const C *__restrict__ Hy = v.f[B200FDTD_TM_HY];
+    hy = Hy[k]; hy_i0 = Hy[k - v.pitch]; hx = Hx[k]; hx_j0 = Hx[k - 1];
+  }
+  const C jz_old = v.f[B200FDTD_TM_JZ][k];
+  const C dz_old = v.f[B200FDTD_TM_DZ][k];
+  const T eps = v.eps0[k0];
+  const C jz = jz_old + (((hy - hy_i0) - hx) + hx_j0);   // fdtdTM_upml.c:162 with C_JZ = C_JZHXHY = 1
+  const C dz = (dz_old + jz) - jz_old;                   // :163 with C_DZ = C_DZJZ1 = C_DZJZ0 = 1
+  v.f[B200FDTD_TM_JZ][k] = jz;
+  v.f[B200FDTD_TM_DZ][k] = dz;
+  C ez = dz;                                             // :175 with eps == 1: x / 1.0 == x
+  if (eps != (T)1 || (long long)k0 == v.point_k || (v.line.enabled && r - 1 == v.line.i))
+    ez = tm_e_material<T>(&v, r, c, k0, eps, dz);
+  v.f[B200FDTD_TM_EZ][k] = ez;
+  if (v.peer_down_e != nullptr && c == v.c_first)
+    v.peer_down_e[(size_t)r * v.peer_down_pitch + v.peer_down_col] = ez;
+}
+
+template <typename T, bool STORE_H>
+__global__ void __launch_bounds__(kBlock, B200_UNIT_TE_H_MIN_BLOCKS) te_unit_h_kernel(const __grid_constant__ UpmlViewT<T> v)
+{
+  using C = typename Cx<T>::type;
+  int r, c; size_t k, k0;
+  if (!locate_rect(v, r, c, k, k0)) return;
+  const C *__restrict__ Ex = v.f[B200FDTD_TE_EX];
+  const C *__restrict__ Ey = v.f[B200FDTD_TE_EY];
+  const C ey_i1 = Ey[k + v.pitch], ey = Ey[k], ex_j1 = Ex[k + 1], ex = Ex[k];
+  const C mz_old = v.f[B200FDTD_TE_MZ][k], bz_old = v.f[B200FDTD_TE_BZ][k];
+  const C mz = mz_old - (((ey_i1 - ey) - ex_j1) + ex);   // fdtdTE_upml.c:300 with C_MZ = C_MZEXEY = 1
+  const C bz = (bz_old + mz) - mz_old;                   // :301 with C_BZ = C_BZMZ1 = C_BZMZ0 = 1
+  v.f[B200FDTD_TE_MZ][k] = mz;
+  v.f[B200FDTD_TE_BZ][k] = bz;
+  if (STORE_H) v.f[B200FDTD_TE_HZ][k] = div_const(bz, v.mu0);
+  if (v.peer_up_h != nullptr && c == v.c_last)
+    v.peer_up_h[(size_t)r * v.peer_up_pitch + (B200_JOFF - 1)] = div_const(bz, v.mu0);
+}
+
+template <typename T, bool FROM_B>
+__global__ void __launch_bounds__(kBlock, B200_UNIT_TE_E_MIN_BLOCKS) te_unit_e_kernel(const __grid_constant__ UpmlViewT<T> v)
+{
+  using C = typename Cx<T>::type;
+  int r, c; size_t k, k0;
+  if (!locate_rect(v, r, c, k, k0)) return;
+  C hz, hz_j0, hz_i0;
+  if (FROM_B) {
+    const C *__restrict__ Bz = v.f[B200FDTD_TE_BZ];
+    hz = div_const(Bz[k], v.mu0);
+    hz_j0 = div_const(Bz[k - 1], v.mu0);
+    hz_i0 = div_const(Bz[k - v.pitch], v.mu0);
+  } else {
+    const C *__restrict__ Hz = v.f[B200FDTD_TE_HZ];
+    hz = Hz[k]; hz_j0 = Hz[k - 1]; hz_i0 = Hz[k - v.pitch];
+  }
+  const C jx_old = v.f[B200FDTD_TE_JX][k], dx_old = v.f[B200FDTD_TE_DX][k];
+  const C jy_old = v.f[B200FDTD_TE_JY][k], dy_old = v.f[B200FDTD_TE_DY][k];
+  const T eps_x = v.eps0[k0], eps_y = v.eps1[k0];
+  const C jx = jx_old + (hz - hz_j0);                    // fdtdTE_upml.c:260 with C_JX = C_JXHZ = 1
+  const C dx = (dx_old + jx) - jx_old;                   // :261
+  const C jy = jy_old + ((-hz) + hz_i0);                 // :270
+  const C dy = (dy_old + jy) - jy_old;                   // :271 with C_DY = C_DYJY1 = C_DYJY0 = 1
+  v.f[B200FDTD_TE_JX][k] = jx;
+  v.f[B200FDTD_TE_DX][k] = dx;
+  v.f[B200FDTD_TE_JY][k] = jy;
+  v.f[B200FDTD_TE_DY][k] = dy;
+  C ex = dx, ey = dy;
+  if (eps_x != (T)1 || eps_y != (T)1 || (long long)k0 == v.point_k)
+    te_e_material<T>(&v, r, c, k0, eps_x, eps_y, dx, dy, &ex, &ey);
+  v.f[B200FDTD_TE_EX][k] = ex;
+  v.f[B200FDTD_TE_EY][k] = ey;
+  if (v.peer_down_e != nullptr && c == v.c_first)
+    v.peer_down_e[(size_t)r * v.peer_down_pitch + v.peer_down_col] = ex;
+}
+
 // ------------------------------------------------------------------ lean interior -----
 // Opt-in (B200FDTD_OPT_LEAN_INTERIOR).  Outside the absorbing frame every UPML coefficient of
 // fdtdTM_upml.c:253-271 / fdtdTE_upml.c:384-403 is exactly 1, and the recurrences collapse:
@@ -744,9 +884,22 @@ static PairGeom pair_geom(const b200fdtd_engine *e)
 }
 
 // ---- launch geometry of the lean interior form -------------------------------------------
-static bool lean_active(const b200fdtd_engine *e)
+static bool have_interior(const b200fdtd_engine *e)
 {
-  return e->lean_interior && e->lean_r_hi >= e->lean_r_lo && e->lean_c_hi >= e->lean_c_lo;
+  return e->lean_r_hi >= e->lean_r_lo && e->lean_c_hi >= e->lean_c_lo;
+}
+static bool lean_active(const b200fdtd_engine *e) { return e->lean_interior && have_interior(e); }
+
+// Unit-coefficient interior kernels (bit-identical to the full ones): double precision, and by
+// default only where the rectangle is most of a large grid -- on small grids a step is launch-
+// bound and one kernel per phase is the better deal.
+static bool unit_active(const b200fdtd_engine *e)
+{
+  if (e->fp32 || e->lean_interior || !have_interior(e) || e->unit_split == 0) return false;
+  if (e->unit_split == 1) return true;
+  const double inner = (double)(e->lean_r_hi - e->lean_r_lo + 1) * (e->lean_c_hi - e->lean_c_lo + 1);
+  const double all = (double)(e->r_hi - e->r_lo + 1) * (e->c_hi - e->c_lo + 1);
+  return inner >= 1048576.0 && inner >= 0.75 * all;
 }
 
 // blocks of one rectangle; narrow rectangles get narrow, tall blocks
@@ -816,26 +969,32 @@ static int launch_h(b200fdtd_engine *e, const b200fdtd_step_args *a)
   }
   const long long nblk = (long long)v.nbx * (e->r_hi - e->r_lo + 1);
   const dim3 grid((unsigned)nblk, (unsigned)e->n_batch);
-  if (lean_active(e)) {
-    // the frame-free rectangle through the lean kernel, the frame around it through the full one
+  if (lean_active(e) || unit_active(e)) {
+    // the frame-free rectangle through the lean / unit-coefficient kernel, the frame around it
+    // through the full one
+    const bool lean = lean_active(e);
     UpmlViewT<T> vi = v, vf = v;
     const unsigned nb_i = interior_rect(e, vi), nb_f = frame_rects(e, vf);
     const dim3 gi(nb_i, (unsigned)e->n_batch), gf(nb_f, (unsigned)e->n_batch);
+#define INTERIOR_H(KERNEL)                                                        \
+    do {                                                                          \
+      if (e->store_h) KERNEL<T, true><<<gi, kBlock, 0, e->stream>>>(vi);          \
+      else            KERNEL<T, false><<<gi, kBlock, 0, e->stream>>>(vi);         \
+    } while (0)
     if (is_tm(e->g.kind)) {
-      if (e->store_h) tm_lean_h_kernel<T, true><<<gi, kBlock, 0, e->stream>>>(vi);
-      else            tm_lean_h_kernel<T, false><<<gi, kBlock, 0, e->stream>>>(vi);
+      if (lean) INTERIOR_H(tm_lean_h_kernel); else INTERIOR_H(tm_unit_h_kernel);
       if (nb_f) {
         if (e->store_h) tm_upml_h_kernel<T, true, true><<<gf, kBlock, 0, e->stream>>>(vf);
         else            tm_upml_h_kernel<T, false, true><<<gf, kBlock, 0, e->stream>>>(vf);
       }
     } else {
-      if (e->store_h) te_lean_h_kernel<T, true><<<gi, kBlock, 0, e->stream>>>(vi);
-      else            te_lean_h_kernel<T, false><<<gi, kBlock, 0, e->stream>>>(vi);
+      if (lean) INTERIOR_H(te_lean_h_kernel); else INTERIOR_H(te_unit_h_kernel);
       if (nb_f) {
         if (e->store_h) te_upml_h_kernel<T, true, true><<<gf, kBlock, 0, e->stream>>>(vf);
         else            te_upml_h_kernel<T, false, true><<<gf, kBlock, 0, e->stream>>>(vf);
       }
     }
+#undef INTERIOR_H
     if (nb_f) e->launches++;
   } else if (is_tm(e->g.kind)) {
     if (e->store_h) tm_upml_h_kernel<T, true><<<grid, kBlock, 0, e->stream>>>(v);
@@ -867,25 +1026,30 @@ static int launch_e(b200fdtd_engine *e, const b200fdtd_step_args *a)
   }
   const long long nblk = (long long)v.nbx * (e->r_hi - e->r_lo + 1);
   const dim3 grid((unsigned)nblk, (unsigned)e->n_batch);
-  if (lean_active(e)) {
+  if (lean_active(e) || unit_active(e)) {
+    const bool lean = lean_active(e);
     UpmlViewT<T> vi = v, vf = v;
     const unsigned nb_i = interior_rect(e, vi), nb_f = frame_rects(e, vf);
     const dim3 gi(nb_i, (unsigned)e->n_batch), gf(nb_f, (unsigned)e->n_batch);
+#define INTERIOR_E(KERNEL)                                                        \
+    do {                                                                          \
+      if (e->h_stale) KERNEL<T, true><<<gi, kBlock, 0, e->stream>>>(vi);          \
+      else            KERNEL<T, false><<<gi, kBlock, 0, e->stream>>>(vi);         \
+    } while (0)
     if (is_tm(e->g.kind)) {
-      if (e->h_stale) tm_lean_e_kernel<T, true><<<gi, kBlock, 0, e->stream>>>(vi);
-      else            tm_lean_e_kernel<T, false><<<gi, kBlock, 0, e->stream>>>(vi);
+      if (lean) INTERIOR_E(tm_lean_e_kernel); else INTERIOR_E(tm_unit_e_kernel);
       if (nb_f) {
         if (e->h_stale) tm_upml_e_kernel<T, true, true><<<gf, kBlock, 0, e->stream>>>(vf);
         else            tm_upml_e_kernel<T, false, true><<<gf, kBlock, 0, e->stream>>>(vf);
       }
     } else {
-      if (e->h_stale) te_lean_e_kernel<T, true><<<gi, kBlock, 0, e->stream>>>(vi);
-      else            te_lean_e_kernel<T, false><<<gi, kBlock, 0, e->stream>>>(vi);
+      if (lean) INTERIOR_E(te_lean_e_kernel); else INTERIOR_E(te_unit_e_kernel);
       if (nb_f) {
         if (e->h_stale) te_upml_e_kernel<T, true, true><<<gf, kBlock, 0, e->stream>>>(vf);
         else            te_upml_e_kernel<T, false, true><<<gf, kBlock, 0, e->stream>>>(vf);
       }
     }
+#undef INTERIOR_E
     if (nb_f) e->launches++;
   } else if (is_tm(e->g.kind)) {
     if (e->h_stale) tm_upml_e_kernel<T, true><<<grid, kBlock, 0, e->stream>>>(v);
@@ -951,6 +1115,11 @@ int b200_launch_upml_pipelined(b200fdtd_engine *e, const b200fdtd_step_args *a)
 {
   if (e->r_hi < e->r_lo || e->c_hi < e->c_lo) return B200FDTD_OK;
   return e->fp32 ? launch_pipelined<float>(e, a) : launch_pipelined<double>(e, a);
+}
+
+int b200_step_form(const b200fdtd_engine *e)
+{
+  return lean_active(e) ? 2 : unit_active(e) ? 1 : 0;
 }
 
 int b200_launch_upml_h(b200fdtd_engine *e, const b200fdtd_step_args *a)
