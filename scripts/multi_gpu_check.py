@@ -2,7 +2,7 @@
 reproduce the single-GPU run: fields bit for bit, far field to summation-order noise.
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
-        --master-port 29511 scripts/multi_gpu_check.py [solver] [npx] [npy] [steps] [nccl|peer] [f64|f32] [exact|lean]
+        --master-port 29511 scripts/multi_gpu_check.py [solver] [npx] [npy] [steps] [nccl|peer] [f64|f32] [exact|unit|lean]
 """
 import os
 import sys
@@ -20,9 +20,11 @@ npy = int(sys.argv[3]) if len(sys.argv) > 3 else 240
 steps = int(sys.argv[4]) if len(sys.argv) > 4 else 600
 halo = sys.argv[5] if len(sys.argv) > 5 else "nccl"          # "nccl" or "peer" (direct NVLink stores)
 precision = sys.argv[6] if len(sys.argv) > 6 else "f64"     # "f32": the optional single-precision path
-form = sys.argv[7] if len(sys.argv) > 7 else "exact"        # "lean": B200FDTD_OPT_LEAN_INTERIOR (tolerance form)
+form = sys.argv[7] if len(sys.argv) > 7 else "exact"        # "unit": bit-identical split form; "lean": tolerance form
 if form == "lean":
     os.environ["B200FDTD_LEAN_INTERIOR"] = "1"
+if form == "unit":      # unit-coefficient interior kernels forced on (auto would not pick them at test sizes)
+    os.environ["B200FDTD_UNIT_SPLIT"] = "1"
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
