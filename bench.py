@@ -275,9 +275,8 @@ def gpu_arm(args):
     dist = None
     if world > 1:
         import torch.distributed as dist
-        # NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION; stdout carries the JSON line only
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # (NCCL prints its version banner on stdout at NCCL_DEBUG >= VERSION: main() has pointed fd 1
+        # at stderr for the whole run, the JSON line goes out through the saved descriptor)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     n_px, n_py = args.n, (args.n if args.strong else args.n * world)
@@ -487,12 +486,32 @@ def gpu_arm(args):
                 "e_phase": {"ms_per_launch": ms_e_lean, "bytes_per_cell": lean_e,
                             "achieved": lean_e * cells_rank / (ms_e_lean * 1e-3) / 1e9,
                             "frac": lean_e * cells_rank / (ms_e_lean * 1e-3) / 1e9 / peak}}
-        print(json.dumps(line))
+        emit(json.dumps(line))
     run.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+_json_out = None
+
+
+def emit(text):
+    """The one JSON line, on the process's ORIGINAL stdout."""
+    if _json_out is None:
+        print(text, flush=True)
+    else:
+        os.write(_json_out, (text + "\n").encode())
+
+
+def quiet_stdout():
+    """stdout carries the JSON line only: whatever libraries print to fd 1 during the run (the NCCL
+    version banner, ...) goes to stderr instead."""
+    global _json_out
+    sys.stdout.flush()
+    _json_out = os.dup(1)
+    os.dup2(2, 1)
 
 
 def main():
@@ -527,6 +546,7 @@ def main():
         args.warmup = 3
     if args.impl == "reference":
         return reference_arm(args)
+    quiet_stdout()
     return gpu_arm(args)
 
 
