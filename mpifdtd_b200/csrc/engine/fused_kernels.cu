@@ -35,10 +35,13 @@ using namespace upml;
 struct FusedView {
   UpmlView u;
   int n_strips, n_bands, band_h;
-  double2 *col_e, *col_h;       // [n_strips + 1][rows]: old E at a strip's first column,
+  int strip_w, n_edges;         // the column pre-pass serves strips of strip_w columns (32: every warp
+                                //   strip; 32*WARPS: only CTA strips, TMA form); n_edges = ceil(cols / strip_w)
+  double2 *col_e, *col_h;       // [n_edges + 1][rows]: old E at a strip's first column,
                                 //   new H at the column just below it
   double2 *row_e, *row_h;       // [n_bands + 1][pitch]: old E at a band's first row,
                                 //   new H at the row just above it
+  int unit_r_lo, unit_r_hi, unit_c_lo, unit_c_hi;   // frame-free rectangle (all coefficients exactly 1), or empty
 };
 
 __device__ __forceinline__ double2 shfl_down1(double2 v)
@@ -95,10 +98,10 @@ __global__ void tm_prepass_cols_kernel(const FusedView f)
   const UpmlView &v = f.u;
   const int n_rows = v.r_hi - v.r_lo + 1;
   const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (t >= (long long)(f.n_strips + 1) * n_rows) return;
+  if (t >= (long long)(f.n_edges + 1) * n_rows) return;
   const int s = (int)(t / n_rows);
   const int r = v.r_lo + (int)(t - (long long)s * n_rows);
-  const int c0 = v.c_lo + 32 * s;                       // first column of strip s
+  const int c0 = v.c_lo + f.strip_w * s;                // first column of strip s
   const size_t out = (size_t)s * v.rows + r;
   if (c0 > v.c_hi + 1) return;                          // past the ragged end: nobody reads it
   const size_t k0 = (size_t)r * v.pitch + c0;
@@ -392,6 +395,250 @@ __global__ void __launch_bounds__(32 * WARPS) tm_upml_fused_async_kernel(const F
   cp_async_wait<0>();
 }
 
+// ---- the same march with the operands staged by TMA -----------------------------------
+// Blackwell form of the one-pass step.  A CTA owns a strip of 32*WARPS columns and a band of rows.
+// One producer warp streams the band through a ring of STAGES row buffers in shared memory with
+// bulk asynchronous copies (cp.async.bulk, completion counted on an mbarrier per stage): per row
+// the strip's segments of Ez(r+1), Mx, Bx, My, By, Jz, Dz (4 KB each at 256 columns) and eps.
+// WARPS consumer warps march down the band exactly like tm_upml_fused_kernel -- a lane owns a
+// column, Hy(i-1,j) is carried in registers, Hx(i,j-1) / Ez(i,j+1) come from the neighbouring lane,
+// warp-edge values from the pre-pass side buffers -- but read their operands from the ring, so
+// the bytes in flight (STAGES x 30 KB per SM) no longer depend on registers or occupancy: one CTA
+// per SM, no spills, no block barrier; a warp hands a row buffer back with one mbarrier arrive.
+// Tiles inside the frame-free rectangle use the unit-coefficient expressions (1.0 * x == x), the
+// others the full ones: bit-identical to the two-kernel step either way.
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
+{
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, unsigned bytes, unsigned long long *bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <int W>
+struct __align__(128) TmaRow {
+  double2 ez[W], mx[W], bx[W], my[W], by[W], jz[W], dz[W];
+  double eps[W + 2];             // starts at an even column so the copy is 16-byte aligned
+};
+
+template <bool STORE_H, int WARPS, int STAGES, int MINB = 1>
+__global__ void __launch_bounds__(32 * (WARPS + 1), MINB) tm_upml_fused_tma_kernel(const __grid_constant__ FusedView f)
+{
+  constexpr int W = 32 * WARPS;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  TmaRow<W> *ring = reinterpret_cast<TmaRow<W> *>(smem_raw);
+  double2 *ez_first = reinterpret_cast<double2 *>(smem_raw + sizeof(TmaRow<W>) * STAGES);   // Ez(r0, strip)
+  unsigned long long *full = reinterpret_cast<unsigned long long *>(ez_first + W);
+  unsigned long long *empty = full + STAGES;
+  unsigned long long *first_bar = empty + STAGES;
+
+  const UpmlView &v = f.u;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int band = blockIdx.y;
+  const int c0 = v.c_lo + W * (int)blockIdx.x;          // first column of this CTA's strip
+  const int r0 = v.r_lo + band * f.band_h;
+  int r1 = r0 + f.band_h;
+  if (r1 > v.r_hi + 1) r1 = v.r_hi + 1;
+  int live_warps = f.n_strips - (int)blockIdx.x * WARPS; // 32-column strips that exist in this CTA
+  if (live_warps > WARPS) live_warps = WARPS;
+  const int eps_off = c0 & 1;
+  int wcopy = v.pitch - c0;                               // never read past the row's pitch
+  if (wcopy > W) wcopy = W;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], (unsigned)live_warps); }
+    mbar_init(first_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  double2 *Ez = v.f[B200FDTD_TM_EZ];
+  if (warp == WARPS) {
+    // ---- producer: one lane streams the band, STAGES rows ahead of the slowest consumer ----
+    if (lane != 0) return;
+    const int n_eps = (wcopy + eps_off + 1) & ~1;
+    const unsigned tx = (unsigned)(7 * wcopy * sizeof(double2) + n_eps * sizeof(double));
+    const double2 *row_e_next = f.row_e + (size_t)(band + 1) * v.pitch;
+    // the band's first Ez row: nobody has written it yet (only this CTA's consumers will, and they
+    // wait for this copy), so every consumer sees the OLD values of its own and its neighbours' cells
+    mbar_expect_tx(first_bar, (unsigned)(wcopy * sizeof(double2)));
+    bulk_g2s(ez_first, &Ez[(size_t)r0 * v.pitch + c0], wcopy * sizeof(double2), first_bar);
+    int s = 0; unsigned ph = 0;
+    for (int r = r0; r < r1; r++) {
+      if (r - r0 >= STAGES) mbar_wait(&empty[s], ph ^ 1u);   // every consumer has handed the slot back
+      TmaRow<W> &st = ring[s];
+      const size_t k = (size_t)r * v.pitch + c0;
+      mbar_expect_tx(&full[s], tx);
+      bulk_g2s(st.ez, (r + 1 < r1) ? &Ez[k + v.pitch] : &row_e_next[c0], wcopy * sizeof(double2), &full[s]);
+      bulk_g2s(st.mx, &v.f[B200FDTD_TM_MX][k], wcopy * sizeof(double2), &full[s]);
+      bulk_g2s(st.bx, &v.f[B200FDTD_TM_BX][k], wcopy * sizeof(double2), &full[s]);
+      bulk_g2s(st.my, &v.f[B200FDTD_TM_MY][k], wcopy * sizeof(double2), &full[s]);
+      bulk_g2s(st.by, &v.f[B200FDTD_TM_BY][k], wcopy * sizeof(double2), &full[s]);
+      bulk_g2s(st.jz, &v.f[B200FDTD_TM_JZ][k], wcopy * sizeof(double2), &full[s]);
+      bulk_g2s(st.dz, &v.f[B200FDTD_TM_DZ][k], wcopy * sizeof(double2), &full[s]);
+      bulk_g2s(st.eps, &v.eps0[k - eps_off], n_eps * sizeof(double), &full[s]);
+      if (++s == STAGES) { s = 0; ph ^= 1u; }
+    }
+    return;
+  }
+
+  // ---- consumers ------------------------------------------------------------------------
+  if (warp >= live_warps) return;
+  const int t = 32 * warp + lane;
+  const int c = c0 + t;
+  const bool active = c <= v.c_hi;
+  const bool sees_e = c <= v.c_hi + 1;
+  const double2 zero = make_double2(0, 0);
+  // Values from OTHER CTAs come from the pre-pass side buffers (CTA-strip granularity); values from
+  // other warps of this CTA come from the ring: old Ez of the neighbouring columns directly, the new
+  // Hx(r, c-1) a warp's lane 0 needs by evaluating the left neighbour's x-half itself (same
+  // expressions on the same old values as the owning lane, so the same bits).
+  const bool cta_left = t == 0;                           // lane 0 of warp 0
+  const bool cta_right = t == W - 1;                      // lane 31 of the last warp of a full strip
+  const double2 *col_e_next = f.col_e + (size_t)(blockIdx.x + 1) * v.rows;   // old Ez(r, c0 + W)
+  const double2 *col_h_mine = f.col_h + (size_t)blockIdx.x * v.rows;         // new Hx(r, c0 - 1)
+  // this warp's tile inside the frame-free rectangle: every coefficient is exactly 1.0
+  const bool unit = r0 >= f.unit_r_lo && r1 - 1 <= f.unit_r_hi && c0 + 32 * warp >= f.unit_c_lo &&
+                    c0 + 32 * warp + 31 <= f.unit_c_hi;
+
+  TmColCoef cc = { 1.0, 1.0, 2.0, 2.0 };
+  double c_dz = 1, c_dzjz = 1;
+  if (active && !unit) {
+    cc = tm_col_coef(v, c);
+    c_dz = v.tj[B200FDTD_TMJ_C_DZ * v.pitch + c];
+    c_dzjz = v.tj[B200FDTD_TMJ_C_DZJZ * v.pitch + c];
+  }
+  // lane 0 of warps 1..: the x-half coefficients of column c-1 (full expressions, whatever the
+  // neighbouring tile uses: with unit coefficients they give the same bits)
+  const bool inner_left = lane == 0 && t > 0;
+  double l_c_mx = 1, l_c_mxez = 1;
+  if (inner_left) {
+    l_c_mx = v.tj[B200FDTD_TMJ_C_MX * v.pitch + c - 1];
+    l_c_mxez = v.tj[B200FDTD_TMJ_C_MXEZ * v.pitch + c - 1];
+  }
+
+  size_t k = (size_t)r0 * v.pitch + c;
+  double2 hy_prev = active ? f.row_h[(size_t)band * v.pitch + c] : zero;
+  double2 edge_e = zero, edge_h = zero;                   // CTA-edge lanes only, one row ahead
+  if (cta_right) edge_e = col_e_next[r0];
+  if (cta_left) edge_h = col_h_mine[r0];
+
+  mbar_wait(first_bar, 0);
+  double2 ez_cur = (sees_e && t < wcopy) ? ez_first[t] : zero;
+  double2 ez_nb = zero;                                   // lane 31: old Ez(r, c+1); lane 0: old Ez(r, c-1)
+  if (lane == 31 && !cta_right && t + 1 < wcopy) ez_nb = ez_first[t + 1];
+  if (inner_left) ez_nb = ez_first[t - 1];
+
+  int s = 0; unsigned ph = 0;
+  for (int r = r0; r < r1; r++, k += v.pitch) {
+    double2 edge_e_nxt = zero, edge_h_nxt = zero;
+    if (r + 1 < r1) {
+      if (cta_right) edge_e_nxt = col_e_next[r + 1];
+      if (cta_left) edge_h_nxt = col_h_mine[r + 1];
+    }
+    mbar_wait(&full[s], ph);                              // this row's operands have landed
+    const TmaRow<W> &st = ring[s];
+    const double2 ez_below = (sees_e && t < wcopy) ? st.ez[t] : zero;
+    double2 ez_nb_nxt = zero;
+    if (lane == 31 && !cta_right && t + 1 < wcopy) ez_nb_nxt = st.ez[t + 1];
+    double2 mx_old = zero, bx_old = zero, my_old = zero, by_old = zero, jz_old = zero, dz_old = zero;
+    double2 l_mx = zero, l_bx = zero;
+    double eps = 1.0;
+    if (active) {
+      mx_old = st.mx[t]; bx_old = st.bx[t]; my_old = st.my[t]; by_old = st.by[t];
+      jz_old = st.jz[t]; dz_old = st.dz[t];
+      eps = st.eps[t + eps_off];
+    }
+    if (inner_left) { ez_nb_nxt = st.ez[t - 1]; l_mx = st.mx[t - 1]; l_bx = st.bx[t - 1]; }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);                // the slot may be refilled
+    if (++s == STAGES) { s = 0; ph ^= 1u; }
+
+    double2 ez_right = shfl_down1(ez_cur);                // old Ez(r, c+1)
+    if (lane == 31) ez_right = cta_right ? edge_e : ez_nb;
+
+    const TmRowCoef rc = tm_row_coef(v, r);               // warp-uniform, L1-resident
+    TmH h;
+    h.hx = zero; h.hy = zero; h.mx = h.bx = h.my = h.by = zero;
+    if (active) {
+      if (unit) {
+        h.mx = mx_old - (ez_right - ez_cur);
+        h.bx = (bx_old + h.mx) - mx_old;
+        h.my = my_old - ((-ez_below) + ez_cur);
+        h.by = (by_old + h.my) - my_old;
+        h.hx = div_const(h.bx, v.mu0);
+        h.hy = div_const(h.by, v.mu0);
+      } else {
+        h = tm_h_cell(v, cc, rc, ez_cur, ez_right, ez_below, mx_old, bx_old, my_old, by_old);
+      }
+    }
+    double2 hx_left = shfl_up1(h.hx);                     // new Hx(r, c-1)
+    if (cta_left) hx_left = edge_h;
+    if (inner_left) {
+      // fdtdTM_upml.c:188-189,209 for cell (r, c-1), as its owner evaluates them
+      const double2 mx = l_c_mx * l_mx - l_c_mxez * (ez_cur - ez_nb);
+      const double2 bx = (l_bx + rc.c_bx1 * mx) - rc.c_bx0 * l_mx;
+      hx_left = div_const(bx, v.mu0);
+    }
+
+    if (active) {
+      double2 jz, dz;
+      if (unit) {
+        jz = jz_old + (((h.hy - hy_prev) - h.hx) + hx_left);
+        dz = (dz_old + jz) - jz_old;
+      } else {
+        const double c_jz  = v.ti[B200FDTD_TMI_C_JZ * v.rows + r];
+        const double c_jzh = v.ti[B200FDTD_TMI_C_JZHXHY * v.rows + r];
+        jz = c_jz * jz_old + c_jzh * (((h.hy - hy_prev) - h.hx) + hx_left);
+        dz = (c_dz * dz_old + c_dzjz * jz) - c_dzjz * jz_old;
+      }
+      double2 ez = div_eps(dz, eps);
+      if (v.pulse[0].enabled && eps != 1.0)
+        ez = ez + pulse_term(v.pulse[0], r - 1, v.j_base + c, eps);
+      if ((long long)k == v.point_k)
+        ez = ez + make_double2(v.point_re, v.point_im);
+      v.f[B200FDTD_TM_MX][k] = h.mx;
+      v.f[B200FDTD_TM_BX][k] = h.bx;
+      v.f[B200FDTD_TM_MY][k] = h.my;
+      v.f[B200FDTD_TM_BY][k] = h.by;
+      v.f[B200FDTD_TM_JZ][k] = jz;
+      v.f[B200FDTD_TM_DZ][k] = dz;
+      Ez[k] = ez;
+      if (STORE_H) {
+        v.f[B200FDTD_TM_HX][k] = h.hx;
+        v.f[B200FDTD_TM_HY][k] = h.hy;
+      }
+    }
+    hy_prev = h.hy;
+    ez_cur = ez_below;
+    ez_nb = ez_nb_nxt;
+    edge_e = edge_e_nxt;
+    edge_h = edge_h_nxt;
+  }
+}
+
 // H = B / mu0 over the whole plane: refreshes the H arrays when the fused kernel
 // ran without storing them (the identity Hx == Bx/mu0 holds after every H phase).
 // Only updated cells are touched: the ring / ghost cells of H are not derived state.
@@ -450,14 +697,20 @@ int b200_launch_upml_fused(b200fdtd_engine *e, const b200fdtd_step_args *a)
   FusedView f;
   f.u = make_view(e, a);
   f.n_strips = fs.n_strips; f.n_bands = fs.n_bands; f.band_h = fs.band_h;
+  const int variant = e->fused_variant;                 // tuning knob: launch shape / staging of the main kernel
+  // TMA form: warps of a CTA serve each other from shared memory, only CTA strips need the pre-pass
+  static const int tma_warps[] = { 8, 8, 16, 4, 8, 12, 8, 6, 5, 4, 8 };     // variants 20..30
+  f.strip_w = (variant >= 20 && variant <= 30) ? 32 * tma_warps[variant - 20] : 32;
+  f.n_edges = (e->c_hi - e->c_lo + 1 + f.strip_w - 1) / f.strip_w;
   f.col_e = fs.col_e; f.col_h = fs.col_h; f.row_e = fs.row_e; f.row_h = fs.row_h;
+  f.unit_r_lo = e->lean_r_lo; f.unit_r_hi = e->lean_r_hi;       // empty (1, 0) when the tables have no such region
+  f.unit_c_lo = e->lean_c_lo; f.unit_c_hi = e->lean_c_hi;
 
   const int n_cols = e->c_hi - e->c_lo + 1, n_rows = e->r_hi - e->r_lo + 1;
-  const long long n_col_items = (long long)(fs.n_strips + 1) * n_rows;
+  const long long n_col_items = (long long)(f.n_edges + 1) * n_rows;
   const long long n_row_items = (long long)(fs.n_bands + 1) * n_cols;
   tm_prepass_cols_kernel<<<(unsigned)((n_col_items + 255) / 256), 256, 0, e->stream>>>(f);
   tm_prepass_rows_kernel<<<(unsigned)((n_row_items + 255) / 256), 256, 0, e->stream>>>(f);
-  const int variant = e->fused_variant;                 // tuning knob: warps per block / lockstep
 #define FUSED_LAUNCH(W, L)                                                                     \
   do {                                                                                         \
     dim3 grid((fs.n_strips + (W) - 1) / (W), fs.n_bands);                                      \
@@ -478,7 +731,33 @@ int b200_launch_upml_fused(b200fdtd_engine *e, const b200fdtd_step_args *a)
       tm_upml_fused_async_kernel<false, W, S><<<grid, 32 * (W), smem, e->stream>>>(f);         \
     }                                                                                          \
   } while (0)
+#define FUSED_TMA_LAUNCH(W, S, MB)                                                              \
+  do {                                                                                         \
+    dim3 grid((fs.n_strips + (W) - 1) / (W), fs.n_bands);                                      \
+    const size_t smem = sizeof(TmaRow<32 * (W)>) * (S) + sizeof(double2) * 32 * (W) +          \
+                        sizeof(unsigned long long) * (2 * (S) + 1);                            \
+    if (e->store_h) {                                                                          \
+      B200_CUDA(cudaFuncSetAttribute(tm_upml_fused_tma_kernel<true, W, S, MB>,                 \
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      tm_upml_fused_tma_kernel<true, W, S, MB><<<grid, 32 * ((W) + 1), smem, e->stream>>>(f);  \
+    } else {                                                                                   \
+      B200_CUDA(cudaFuncSetAttribute(tm_upml_fused_tma_kernel<false, W, S, MB>,                \
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      tm_upml_fused_tma_kernel<false, W, S, MB><<<grid, 32 * ((W) + 1), smem, e->stream>>>(f); \
+    }                                                                                          \
+  } while (0)
   switch (variant) {
+  case 20: FUSED_TMA_LAUNCH(8, 4, 1); break;
+  case 21: FUSED_TMA_LAUNCH(8, 6, 1); break;
+  case 22: FUSED_TMA_LAUNCH(16, 3, 1); break;
+  case 23: FUSED_TMA_LAUNCH(4, 8, 1); break;
+  case 24: FUSED_TMA_LAUNCH(8, 3, 1); break;
+  case 25: FUSED_TMA_LAUNCH(12, 4, 1); break;
+  case 26: FUSED_TMA_LAUNCH(8, 3, 2); break;      // two CTAs per SM: 16 consumer warps
+  case 27: FUSED_TMA_LAUNCH(6, 4, 2); break;
+  case 28: FUSED_TMA_LAUNCH(5, 3, 3); break;
+  case 29: FUSED_TMA_LAUNCH(4, 3, 4); break;
+  case 30: FUSED_TMA_LAUNCH(8, 2, 3); break;
   case 10: FUSED_ASYNC_LAUNCH(4, 3); break;
   case 11: FUSED_ASYNC_LAUNCH(4, 4); break;
   case 12: FUSED_ASYNC_LAUNCH(2, 4); break;
@@ -494,6 +773,7 @@ int b200_launch_upml_fused(b200fdtd_engine *e, const b200fdtd_step_args *a)
   }
 #undef FUSED_LAUNCH
 #undef FUSED_ASYNC_LAUNCH
+#undef FUSED_TMA_LAUNCH
   e->launches += 3;
   e->h_stale = !e->store_h;
   B200_CUDA(cudaGetLastError());

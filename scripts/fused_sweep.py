@@ -6,7 +6,9 @@ from mpifdtd_b200.slab import SlabRun
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
 K = 10
 configs = [dict(B200FDTD_FUSED="0", B200FDTD_STORE_H="1"), dict(B200FDTD_FUSED="0", B200FDTD_STORE_H="0")]
-for shape, band, store in itertools.product([], [64, 256], [0]):
+shapes = [int(x) for x in sys.argv[2].split(',')] if len(sys.argv) > 2 else [20, 21, 24, 22, 25, 23]
+bands = [int(x) for x in sys.argv[3].split(',')] if len(sys.argv) > 3 else [256, 1024]
+for shape, band, store in itertools.product(shapes, bands, [0]):
     configs.append(dict(B200FDTD_FUSED="1", B200FDTD_FUSED_SHAPE=str(shape), B200FDTD_BAND_ROWS=str(band),
                         B200FDTD_STORE_H=str(store)))
 

@@ -2,7 +2,9 @@
 
   * two-kernel step that stores Hx/Hy (the literal restatement of the reference's passes),
   * two-kernel step that does NOT store H and forms it as B/mu0 in the E phase (default),
-  * the one-pass "warp-strip marching" kernel, with and without H stores (opt-in).
+  * the one-pass "warp-strip marching" kernel, with and without H stores (opt-in), with its
+    operands prefetched in registers, staged by cp.async, or staged by TMA bulk copies behind
+    an mbarrier ring (producer warp + consumer warps).
 
 All evaluate the same expressions in the same order (-fmad=false), so after any number of
 steps from any state each of the nine arrays and the NTFF history must agree bit for bit
@@ -44,7 +46,7 @@ def make_engine(L, npx, npy, steps, eps, fused, store_h=0, band=None, j0=0, nj=N
 
 
 @pytest.mark.parametrize("npx,npy,band", [(70, 96, 256), (45, 47, 7), (131, 200, 64), (300, 41, 33),
-                                          (64, 1030, 1), (257, 66, 256)])
+                                          (64, 1030, 1), (257, 66, 256), (300, 700, 48)])
 def test_fused_step_is_bit_identical_to_two_kernel_step(plugin_lib, npx, npy, band):
     L = plugin_lib
     steps = 6
@@ -62,7 +64,10 @@ def test_fused_step_is_bit_identical_to_two_kernel_step(plugin_lib, npx, npy, ba
                make_engine(L, npx, npy, steps, eps, 1, store_h=0, band=band),
                make_engine(L, npx, npy, steps, eps, 1, store_h=1, band=band),
                make_engine(L, npx, npy, steps, eps, 1, store_h=0, band=band, shape=10),    # cp.async staged
-               make_engine(L, npx, npy, steps, eps, 1, store_h=1, band=band, shape=13)]
+               make_engine(L, npx, npy, steps, eps, 1, store_h=1, band=band, shape=13),
+               make_engine(L, npx, npy, steps, eps, 1, store_h=0, band=band, shape=20),    # TMA staged, 256 columns
+               make_engine(L, npx, npy, steps, eps, 1, store_h=1, band=band, shape=23),    # 128 columns, 8 stages
+               make_engine(L, npx, npy, steps, eps, 1, store_h=0, band=band, shape=22)]    # 512 columns, 3 stages
     for eng in engines:
         for slot in range(9):
             eng.set_field(slot, state[slot])
