@@ -303,7 +303,13 @@ def gpu_arm(args):
                 dist.barrier()
             torch.cuda.synchronize()
 
-        form = run.engine.step_form()    # 0 full kernels, 1 unit-coefficient interior + frame, 2 lean interior + frame
+        # 0 full kernels, 1 unit-coefficient interior + frame, 2 lean interior + frame, 3 one-pass step
+        form = run.engine.step_form()
+        two_kernel_form = form
+        if form == 3:       # phase_h / phase_e (timed separately below, for reference) use this form:
+            run.engine.set_option(B.OPT_FUSED, 0)
+            two_kernel_form = run.engine.step_form()
+            run.engine.set_option(B.OPT_FUSED, 2)
 
         # ---- value: device-resident K steps + deferred projection ----------------
         for _ in range(W):
@@ -340,6 +346,13 @@ def gpu_arm(args):
         for _ in range(reps):
             run.engine.phase_e(run.args)
         ms_e = run.engine.timer_stop() / reps
+        ms_fused = None
+        if form == 3:        # the step is ONE pass: edge pre-pass + TMA-staged marching kernel
+            run.engine.phase_fused(run.args); run.engine.sync()
+            run.engine.timer_start()
+            for _ in range(reps):
+                run.engine.phase_fused(run.args)
+            ms_fused = run.engine.timer_stop() / reps
         barrier()
 
         # ---- the opt-in lean-interior form, same state, same K steps (reported beside `value`)
@@ -423,12 +436,13 @@ def gpu_arm(args):
         traffic, traffic_src = None, None
         if args.precision == "f64":
             tags = {0: [kname + "_upml_h_kernel<0,0>", kname + "_upml_h_kernel<0>"],
-                    1: [kname + "_unit_h_kernel<0>"], 2: [kname + "_lean_h_kernel<0>"]}[form]
+                    1: [kname + "_unit_h_kernel<0>"], 2: [kname + "_lean_h_kernel<0>"],
+                    3: [kname + "_upml_fused_tma_kernel<0"]}[form]
             for tag in tags:
                 traffic, traffic_src = ncu_traffic(tag, cells_rank)
                 if traffic is not None:
                     break
-        stem = kname + {0: "_upml", 1: "_unit", 2: "_lean"}[form]
+        stem = kname + {0: "_upml", 1: "_unit", 2: "_lean"}[two_kernel_form]
         h_name, e_name = stem + "_h_kernel<STORE_H=false>", stem + "_e_kernel<FROM_B=true>"
         line = {
             "metric": "Gcell-updates/s", "value": value, "unit": "Gcell-updates/s",
@@ -455,13 +469,36 @@ def gpu_arm(args):
                     "path": "b200fdtd_set_eps_slab(pinned host eps) + K x [mpifdtd_upml_step_args + "
                             "b200fdtd_step + field_nextStep] + b200fdtd_get_field_slab(Ez -> pinned host)"},
             "gpu_launches": int(launches),
-            "step_form": {0: "one full kernel per phase",
+            "step_form": {3: "one pass: edge pre-pass + TMA-staged marching kernel (H and E fused, 232 B per "
+                             "cell-update, bit-identical to the two-kernel forms; B200FDTD_OPT_FUSED, default on "
+                             "large single-slab TM grids)",
+                          0: "one full kernel per phase",
                           1: "unit-coefficient interior kernel + frame kernel per phase (bit-identical to the "
                              "one-kernel form; B200FDTD_OPT_UNIT_SPLIT, default on large grids)",
                           2: "lean interior kernel + frame kernel per phase (tolerance form)"}[form],
             "clocks": clocks,
             "device_bytes": run.engine.device_bytes(),
         }
+        if form == 3:
+            bytes_fused = 232 if args.precision == "f64" else 116
+            ach_f = bytes_fused * cells_rank / (ms_fused * 1e-3) / 1e9
+            two = dict(line["roofline"])
+            line["roofline"] = {
+                "bound": "hbm", "kernel": kname + "_upml_fused_tma_kernel<STORE_H=false, 8 warps, 4 stages> (+ its "
+                                          "edge pre-pass, timed together)",
+                "achieved": ach_f, "peak": peak, "unit": "GB/s", "frac": ach_f / peak, "peak_source": peak_kind,
+                "traffic": traffic, "traffic_source": traffic_src,
+                "algorithmic_bytes_per_launch": bytes_fused * cells_rank, "ms_per_launch": ms_fused,
+                "algorithmic_bytes_per_cell": bytes_fused,
+                "note": "one pass reads Ez,Mx,Bx,My,By,Jz,Dz + eps (120 B) and writes Mx,Bx,My,By,Jz,Dz,Ez (112 B): "
+                        "232 B per cell-update against SURVEY 8(d)'s 264 B contract figure for two passes",
+                "step": {"algorithmic_bytes_per_cell_update": bytes_step,
+                         "achieved": step_gbs, "frac": step_gbs / peak, "frac_of_nominal_8TBs": step_gbs / 8000.0,
+                         "moved_bytes_per_cell_update": bytes_fused,
+                         "moved": bytes_fused * (value / world), "moved_frac": bytes_fused * (value / world) / peak},
+                "two_kernel_form": {"h_phase": {k: two[k] for k in ("kernel", "achieved", "frac", "ms_per_launch",
+                                                                    "algorithmic_bytes_per_cell")},
+                                    "e_phase": two["e_phase"]}}
         if args.lean:
             line["config"]["form"] = ("lean interior (B200FDTD_OPT_LEAN_INTERIOR): tolerance form, fields within "
                                       "1e-12 of the reference; moves %d B per cell-update" % (bytes_h + bytes_e))

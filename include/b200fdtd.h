@@ -293,6 +293,10 @@ int b200fdtd_step(b200fdtd_engine *e, const b200fdtd_step_args *args);
 int b200fdtd_phase_h(b200fdtd_engine *e, const b200fdtd_step_args *args);
 int b200fdtd_phase_e(b200fdtd_engine *e, const b200fdtd_step_args *args);
 int b200fdtd_phase_sample(b200fdtd_engine *e, const b200fdtd_step_args *args);
+/* H and E phase of the serial TM kind in ONE pass (what b200fdtd_step launches when
+ * b200fdtd_get_step_form says 3): edge pre-pass + the TMA-staged marching kernel; an error if the
+ * engine / source is not served by it (see B200FDTD_OPT_FUSED). */
+int b200fdtd_phase_fused(b200fdtd_engine *e, const b200fdtd_step_args *args);
 int b200fdtd_sync(b200fdtd_engine *e);
 /* n_steps consecutive update() calls starting at time0, replayed from a CUDA graph: the step's
  * only time dependence -- the pulse's (time - t0) and the NTFF sample index -- is read from a
@@ -361,13 +365,18 @@ int b200fdtd_ntff_frequency(b200fdtd_engine *e, const b200fdtd_freq_args *args, 
 
 /* ---- tuning switches ------------------------------------------------------ */
 enum {
-  B200FDTD_OPT_FUSED = 1,     /* 1: b200fdtd_step uses the one-pass H+E kernel (default for the
-                                 serial TM kind), 0: the two-kernel form                        */
+  B200FDTD_OPT_FUSED = 1,     /* the one-pass H+E step of the serial TM kind (one unbatched double-
+                                 precision slab without peer halos; 232 instead of 264 B per
+                                 cell-update, bit-identical): 1 wherever it can run, 0 never,
+                                 2 (default) on grids of >= 2^22 updated cells                   */
   B200FDTD_OPT_STORE_H = 2,   /* 1: the fused kernel also writes Hx/Hy every step (264 B/cell);
                                  0 (default): H is derived from B on demand (getters, NTFF,
                                  halo) -- Hx == Bx/mu0 holds after every H phase (232 B/cell)    */
-  B200FDTD_OPT_BAND_ROWS = 3, /* rows a warp marches per band in the fused kernel (default 256)  */
-  B200FDTD_OPT_FUSED_SHAPE = 4, /* launch shape of the fused kernel (tuning; see fused_kernels.cu) */
+  B200FDTD_OPT_BAND_ROWS = 3, /* rows a warp marches per band in the fused kernel (default 32 for
+                                 the TMA-staged forms, 256 for the others)                       */
+  B200FDTD_OPT_FUSED_SHAPE = 4, /* form of the fused kernel: 20 (default) .. 30 operands staged by
+                                 TMA bulk copies behind an mbarrier ring, 10..15 by cp.async,
+                                 0..5 prefetched in registers (see fused_kernels.cu)             */
   B200FDTD_OPT_PIPELINED = 5,  /* 1: b200fdtd_step of an unbatched, peer-less UPML engine runs ONE
                                   persistent kernel per step that overlaps the H phase of row band
                                   k+1 with the E phase of band k, so the E phase finds Bx/By (Bz) in
@@ -407,8 +416,9 @@ int b200fdtd_upml_interior(int32_t kind, const double *tab_i, int32_t n_px, cons
 /* the rectangle this engine's split forms use (global i / j of this slab's share; without row
  * r_lo / column c_lo, which stay with the frame kernels); {1,0,1,0} when no split form is active */
 int b200fdtd_get_lean_extent(b200fdtd_engine *e, int32_t out[4]);
-/* which form b200fdtd_step / phase_h / phase_e launch right now: 0 one full kernel per phase,
- * 1 unit-coefficient interior kernel + frame (bit-identical to 0), 2 lean interior + frame */
+/* which form b200fdtd_step launches right now: 0 one full kernel per phase, 1 unit-coefficient
+ * interior kernel + frame (bit-identical to 0), 2 lean interior + frame, 3 the one-pass step
+ * (bit-identical to 0; phase_h / phase_e then still launch form 0 or 1) */
 int b200fdtd_get_step_form(b200fdtd_engine *e, int32_t *form);
 
 /* Device self-test: the kernels replace `x / d` (d loop-invariant, e.g. MU_0_S) by a

@@ -125,7 +125,8 @@ def lib():
     L.b200fdtd_set_upml_tables.argtypes = [vp, vp, vp]
     L.b200fdtd_set_eps.argtypes = [vp, i32, vp]
     L.b200fdtd_set_ntff_plan.argtypes = [vp, C.POINTER(NtffPlan)]
-    for fn in ("b200fdtd_step", "b200fdtd_phase_h", "b200fdtd_phase_e", "b200fdtd_phase_sample"):
+    for fn in ("b200fdtd_step", "b200fdtd_phase_h", "b200fdtd_phase_e", "b200fdtd_phase_sample",
+               "b200fdtd_phase_fused"):
         getattr(L, fn).argtypes = [vp, C.POINTER(StepArgs)]
     L.b200fdtd_sync.argtypes = [vp]
     L.b200fdtd_halo_pack.argtypes = [vp, i32, vp]
@@ -432,6 +433,9 @@ class Engine:
     def phase_e(self, args):
         check(self.L.b200fdtd_phase_e(self.h, C.byref(args)), "phase_e")
 
+    def phase_fused(self, args):
+        check(self.L.b200fdtd_phase_fused(self.h, C.byref(args)), "phase_fused")
+
     def phase_sample(self, args):
         check(self.L.b200fdtd_phase_sample(self.h, C.byref(args)), "phase_sample")
 
@@ -479,7 +483,8 @@ class Engine:
         check(self.L.b200fdtd_set_option(self.h, option, value), "set_option")
 
     def step_form(self):
-        """0 one full kernel per phase, 1 unit-coefficient interior + frame, 2 lean interior + frame."""
+        """0 one full kernel per phase, 1 unit-coefficient interior + frame, 2 lean interior + frame,
+        3 the one-pass step (phase_h / phase_e then still launch form 0 or 1)."""
         form = C.c_int32(-1)
         check(self.L.b200fdtd_get_step_form(self.h, C.byref(form)), "get_step_form")
         return form.value

@@ -162,11 +162,15 @@ int b200fdtd_create(const b200fdtd_grid *grid, b200fdtd_engine **out)
   e->fp32 = grid->precision == B200FDTD_F32;
   e->csize = e->fp32 ? sizeof(float2) : sizeof(double2);
   e->rsize = e->fp32 ? sizeof(float) : sizeof(double);
-  e->use_fused = false;     // the marching one-pass kernel is opt-in (B200FDTD_OPT_FUSED)
+  e->use_fused = false;     // the one-pass kernel: everywhere it can run (B200FDTD_OPT_FUSED = 1) ...
+  e->fused_auto = true;     // ... or, by default, on large single-slab TM grids (2 = auto)
+  e->fused_variant = 20;    // TMA-staged form, 256 columns x 4 row buffers
   e->store_h = false;
   e->h_stale = false;
-  if (const char *v = getenv("B200FDTD_FUSED"))
-    e->use_fused = atoi(v) != 0 && grid->kind == B200FDTD_TM_UPML && !e->fp32 && n_batch == 1;
+  if (const char *v = getenv("B200FDTD_FUSED")) {
+    e->use_fused = atoi(v) == 1 && grid->kind == B200FDTD_TM_UPML && !e->fp32 && n_batch == 1;
+    e->fused_auto = atoi(v) == 2;
+  }
   if (const char *v = getenv("B200FDTD_STORE_H")) e->store_h = atoi(v) != 0;
   e->f32_pairs = true;
   if (const char *v = getenv("B200FDTD_F32_PAIRS")) e->f32_pairs = atoi(v) != 0;
@@ -382,6 +386,7 @@ int b200fdtd_get_step_form(b200fdtd_engine *e, int32_t *form)
 {
   if (!e || !form) return b200_fail(B200FDTD_ERR_ARG, "NULL argument");
   *form = kind_is_upml(e->g.kind) && e->have_tabs ? b200_step_form(e) : 0;
+  if (kind_is_upml(e->g.kind) && e->have_tabs && b200_want_fused(e, nullptr)) *form = 3;
   return B200FDTD_OK;
 }
 
@@ -682,7 +687,8 @@ int b200fdtd_set_option(b200fdtd_engine *e, int32_t option, int32_t value)
   case B200FDTD_OPT_FUSED:
     if (value && (e->g.kind != B200FDTD_TM_UPML || e->fp32 || e->n_batch > 1))
       return b200_fail(B200FDTD_ERR_ARG, "the fused step serves the serial TM kind in double precision only");
-    e->use_fused = value != 0;
+    e->use_fused = value == 1;
+    e->fused_auto = value == 2;
     return B200FDTD_OK;
   case B200FDTD_OPT_STORE_H:
     rc = b200_refresh_h(e); if (rc) return rc;
@@ -725,6 +731,13 @@ int b200fdtd_set_option(b200fdtd_engine *e, int32_t option, int32_t value)
   }
 }
 
+int b200fdtd_phase_fused(b200fdtd_engine *e, const b200fdtd_step_args *a)
+{
+  int rc = check_ready(e, a); if (rc) return rc;
+  if (!b200_want_fused(e, a)) return b200_fail(B200FDTD_ERR_STATE, "the one-pass step does not serve this engine / source");
+  return b200_launch_upml_fused(e, a);
+}
+
 int b200fdtd_phase_sample(b200fdtd_engine *e, const b200fdtd_step_args *a)
 {
   int rc = check_ready(e, a); if (rc) return rc;
@@ -740,7 +753,7 @@ int b200fdtd_step(b200fdtd_engine *e, const b200fdtd_step_args *a)
                             !e->peer.attached[0] && !e->peer.attached[1];
   if (can_pipeline) {
     rc = b200_launch_upml_pipelined(e, a);      // H and E of one step in one persistent kernel
-  } else if (e->use_fused && e->g.kind == B200FDTD_TM_UPML && !a->line.enabled && !a->cw[0].enabled) {
+  } else if (b200_want_fused(e, a)) {
     rc = b200_launch_upml_fused(e, a);          // H and E in one pass
   } else if (e_first) {              // mpiTM_UPML.c:196-217: E, source, H, NTFF
     rc = b200_launch_upml_e(e, a);
@@ -757,10 +770,15 @@ int b200fdtd_step(b200fdtd_engine *e, const b200fdtd_step_args *a)
 // sequence depends on the step number).
 static int launch_clocked_step(b200fdtd_engine *e, const b200fdtd_step_args *a)
 {
-  // (always the two-kernel step: the pipelined kernel's queue base and epoch change per launch,
-  // which a replayed graph cannot express)
-  int rc = b200_launch_upml_h(e, a);
-  if (!rc) rc = b200_launch_upml_e(e, a);
+  // (never the pipelined kernel: its queue base and epoch change per launch, which a replayed
+  // graph cannot express)
+  int rc;
+  if (b200_want_fused(e, a)) {
+    rc = b200_launch_upml_fused(e, a);
+  } else {
+    rc = b200_launch_upml_h(e, a);
+    if (!rc) rc = b200_launch_upml_e(e, a);
+  }
   if (!rc) rc = b200_launch_ntff_sample(e, a);
   if (!rc) rc = b200_launch_clock_advance(e);
   return rc;
@@ -772,13 +790,16 @@ int b200fdtd_run_steps(b200fdtd_engine *e, double time0, int32_t n_steps)
   if (e->g.kind != B200FDTD_TM_UPML && e->g.kind != B200FDTD_TE_UPML)
     return b200_fail(B200FDTD_ERR_ARG, "multi-step replay serves the serial UPML kinds (2, 3)");
   if (!e->have_batch_src) return b200_fail(B200FDTD_ERR_STATE, "run_steps before set_batch_sources");
-  if (e->peer.attached[0] || e->peer.attached[1] || e->use_fused)
-    return b200_fail(B200FDTD_ERR_ARG, "multi-step replay: no peer halos, no fused step");
+  if (e->peer.attached[0] || e->peer.attached[1])
+    return b200_fail(B200FDTD_ERR_ARG, "multi-step replay: no peer halos");
   b200fdtd_step_args a;
   memset(&a, 0, sizeof a);
   a.time = time0;
   int rc = check_ready(e, &a); if (rc) return rc;
   if (n_steps == 0) return B200FDTD_OK;
+  if (b200_want_fused(e, &a)) {       // side buffers are allocated outside any stream capture
+    rc = b200_fused_prepare(e); if (rc) return rc;
+  }
   NtffState &n = e->ntff;
   if (n.ready && ((int)time0 < 0 || (int)time0 + n_steps > n.max_time))
     return b200_fail(B200FDTD_ERR_ARG, "steps %d..%d outside the NTFF history [0, %d)", (int)time0,
@@ -806,6 +827,7 @@ int b200fdtd_run_steps(b200fdtd_engine *e, double time0, int32_t n_steps)
       if (err != cudaSuccess) { rc = b200_fail(B200FDTD_ERR_CUDA, "begin capture: %s", cudaGetErrorString(err)); break; }
       for (int s = 0; s < chunk && !rc; s++) rc = launch_clocked_step(e, &a);
       err = cudaStreamEndCapture(e->stream, &graph);
+      e->graph_launches = e->launches - launches_before;   // kernels in the chunk
       e->launches = launches_before;                    // captured, not launched yet
       if (rc) { if (graph) cudaGraphDestroy(graph); break; }
       if (err != cudaSuccess) { rc = b200_fail(B200FDTD_ERR_CUDA, "end capture: %s", cudaGetErrorString(err)); break; }
@@ -818,8 +840,7 @@ int b200fdtd_run_steps(b200fdtd_engine *e, double time0, int32_t n_steps)
     }
     cudaError_t err = cudaGraphLaunch((cudaGraphExec_t)e->graph_exec, e->stream);
     if (err != cudaSuccess) { rc = b200_fail(B200FDTD_ERR_CUDA, "graph launch: %s", cudaGetErrorString(err)); break; }
-    const int per_step = 2 + (n.ready && n.n_local > 0 ? 1 : 0) + 1;     // H, E, sample, clock
-    e->launches += (uint64_t)per_step * chunk;
+    e->launches += e->graph_launches;
     done += chunk;
   }
   e->clock_mode = false;

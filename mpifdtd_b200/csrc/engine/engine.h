@@ -106,10 +106,12 @@ struct b200fdtd_engine {
   bool clock_mode;          // launchers build views that read the time from clock_dev
   void *graph_exec;         // cudaGraphExec_t of `graph_steps` steps, or nullptr
   int graph_steps;
+  uint64_t graph_launches;  // kernels one replay of the cached graph launches
   unsigned graph_epoch, graph_built_epoch;   // bumped by anything that changes what a step launches
   bool f32_pairs;           // single precision: two cells per thread (default on)
   bool use_pipelined;       // b200fdtd_step runs the pipelined persistent kernel (serial UPML kinds, one slab)
-  bool use_fused;           // b200fdtd_step runs the one-pass kernel (serial TM kind)
+  bool use_fused;           // b200fdtd_step runs the one-pass kernel (serial TM kind) wherever it can
+  bool fused_auto;          // ... or on large grids only (default)
   bool store_h;             // the fused kernel also writes Hx/Hy (264 instead of 232 B/cell)
   bool h_stale;             // Hx/Hy arrays lag Bx/By (fused step without store_h)
   int fused_variant;        // launch shape of the fused kernel (tuning)
@@ -157,6 +159,7 @@ int b200_launch_split_step(b200fdtd_engine *e, const b200fdtd_step_args *a);
 
 // launchers (fused_kernels.cu)
 int b200_launch_upml_fused(b200fdtd_engine *e, const b200fdtd_step_args *a);
+bool b200_want_fused(const b200fdtd_engine *e, const b200fdtd_step_args *a);
 int b200_refresh_h(b200fdtd_engine *e);
 int b200_fused_prepare(b200fdtd_engine *e);
 void b200_fused_release(b200fdtd_engine *e);

@@ -53,6 +53,18 @@ __device__ __forceinline__ double2 shfl_up1(double2 v)
   return make_double2(__shfl_up_sync(0xffffffffu, v.x, 1), __shfl_up_sync(0xffffffffu, v.y, 1));
 }
 
+// The pulse of source slot 0 as the two-kernel form sees it (pulse_of in upml_common.cuh with
+// blockIdx.y == 0): the step's own parameters, or -- multi-step replay -- the engine's source
+// record with time - t0 formed from the device clock.
+__device__ __forceinline__ b200fdtd_pulse fused_pulse(const UpmlView &v)
+{
+  if (v.batch == nullptr) return v.pulse[0];
+  b200fdtd_pulse p = v.batch[0].pulse[0];
+  const double time = v.time_ptr != nullptr ? *v.time_ptr : v.time;
+  p.time_minus_t0 = time - v.batch[0].t0[0];
+  return p;
+}
+
 // ---- TM: the H-phase arithmetic for one cell (fdtdTM_upml.c:187-216) ------------
 struct TmH { double2 mx, bx, my, by, hx, hy; };
 struct TmColCoef { double c_mx, c_mxez, num1, num0; };          // by j (this lane's column)
@@ -173,6 +185,7 @@ __global__ void __launch_bounds__(32 * WARPS) tm_upml_fused_kernel(const FusedVi
 
   double2 *Ez = v.f[B200FDTD_TM_EZ];
   const double2 zero = make_double2(0, 0);
+  const b200fdtd_pulse pulse = fused_pulse(v);
   const double2 *col_e_next = f.col_e + (size_t)(strip + 1) * v.rows;   // old Ez(r, c0 + 32)
   const double2 *col_h_mine = f.col_h + (size_t)strip * v.rows;         // new Hx(r, c0 - 1)
   const double2 *row_e_next = f.row_e + (size_t)(band + 1) * v.pitch;   // old Ez(r1, c)
@@ -236,8 +249,8 @@ __global__ void __launch_bounds__(32 * WARPS) tm_upml_fused_kernel(const FusedVi
       const double2 jz = c_jz * cur.jz + c_jzh * (((h.hy - hy_prev) - h.hx) + hx_left);
       const double2 dz = (c_dz * cur.dz + c_dzjz * jz) - c_dzjz * cur.jz;
       double2 ez = div_eps(dz, cur.eps);
-      if (v.pulse[0].enabled && cur.eps != 1.0)
-        ez = ez + pulse_term(v.pulse[0], r - 1, v.j_base + c, cur.eps);
+      if (pulse.enabled && cur.eps != 1.0)
+        ez = ez + pulse_term(pulse, r - 1, v.j_base + c, cur.eps);
       if ((long long)k == v.point_k)
         ez = ez + make_double2(v.point_re, v.point_im);
 
@@ -305,6 +318,7 @@ __global__ void __launch_bounds__(32 * WARPS) tm_upml_fused_async_kernel(const F
 
   double2 *Ez = v.f[B200FDTD_TM_EZ];
   const double2 zero = make_double2(0, 0);
+  const b200fdtd_pulse pulse = fused_pulse(v);
   const double2 *col_e_next = f.col_e + (size_t)(strip + 1) * v.rows;
   const double2 *col_h_mine = f.col_h + (size_t)strip * v.rows;
   const double2 *row_e_next = f.row_e + (size_t)(band + 1) * v.pitch;
@@ -373,8 +387,8 @@ __global__ void __launch_bounds__(32 * WARPS) tm_upml_fused_async_kernel(const F
       const double2 jz = c_jz * jz_old + c_jzh * (((h.hy - hy_prev) - h.hx) + hx_left);
       const double2 dz = (c_dz * dz_old + c_dzjz * jz) - c_dzjz * jz_old;
       double2 ez = div_eps(dz, eps);
-      if (v.pulse[0].enabled && eps != 1.0)
-        ez = ez + pulse_term(v.pulse[0], r - 1, v.j_base + c, eps);
+      if (pulse.enabled && eps != 1.0)
+        ez = ez + pulse_term(pulse, r - 1, v.j_base + c, eps);
       if ((long long)k == v.point_k)
         ez = ez + make_double2(v.point_re, v.point_im);
       v.f[B200FDTD_TM_MX][k] = h.mx;
@@ -446,9 +460,9 @@ template <bool STORE_H, int WARPS, int STAGES, int MINB = 1>
 __global__ void __launch_bounds__(32 * (WARPS + 1), MINB) tm_upml_fused_tma_kernel(const __grid_constant__ FusedView f)
 {
   constexpr int W = 32 * WARPS;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  TmaRow<W> *ring = reinterpret_cast<TmaRow<W> *>(smem_raw);
-  double2 *ez_first = reinterpret_cast<double2 *>(smem_raw + sizeof(TmaRow<W>) * STAGES);   // Ez(r0, strip)
+  extern __shared__ __align__(128) unsigned char tma_smem[];
+  TmaRow<W> *ring = reinterpret_cast<TmaRow<W> *>(tma_smem);
+  double2 *ez_first = reinterpret_cast<double2 *>(tma_smem + sizeof(TmaRow<W>) * STAGES);   // Ez(r0, strip)
   unsigned long long *full = reinterpret_cast<unsigned long long *>(ez_first + W);
   unsigned long long *empty = full + STAGES;
   unsigned long long *first_bar = empty + STAGES;
@@ -539,6 +553,7 @@ __global__ void __launch_bounds__(32 * (WARPS + 1), MINB) tm_upml_fused_tma_kern
     l_c_mxez = v.tj[B200FDTD_TMJ_C_MXEZ * v.pitch + c - 1];
   }
 
+  const b200fdtd_pulse pulse = fused_pulse(v);
   size_t k = (size_t)r0 * v.pitch + c;
   double2 hy_prev = active ? f.row_h[(size_t)band * v.pitch + c] : zero;
   double2 edge_e = zero, edge_h = zero;                   // CTA-edge lanes only, one row ahead
@@ -615,8 +630,8 @@ __global__ void __launch_bounds__(32 * (WARPS + 1), MINB) tm_upml_fused_tma_kern
         dz = (c_dz * dz_old + c_dzjz * jz) - c_dzjz * jz_old;
       }
       double2 ez = div_eps(dz, eps);
-      if (v.pulse[0].enabled && eps != 1.0)
-        ez = ez + pulse_term(v.pulse[0], r - 1, v.j_base + c, eps);
+      if (pulse.enabled && eps != 1.0)
+        ez = ez + pulse_term(pulse, r - 1, v.j_base + c, eps);
       if ((long long)k == v.point_k)
         ez = ez + make_double2(v.point_re, v.point_im);
       v.f[B200FDTD_TM_MX][k] = h.mx;
@@ -654,6 +669,20 @@ __global__ void derive_h_kernel(const double2 *__restrict__ b, double2 *h, int p
 
 }  // namespace
 
+// The one-pass TM step (fused_kernels.cu): a single unbatched double-precision slab without peer
+// halos, default pulse / point sources only; by default on grids of >= 2^22 updated cells, where
+// its 232 B per cell-update beat the two kernels' 264 (on small grids a step is launch-bound and
+// the pre-pass launches cost more than the bytes save).
+bool b200_want_fused(const b200fdtd_engine *e, const b200fdtd_step_args *a)
+{
+  if (e->g.kind != B200FDTD_TM_UPML || e->fp32 || e->n_batch > 1 || e->lean_interior) return false;
+  if (e->peer.attached[0] || e->peer.attached[1]) return false;
+  if (a != nullptr && (a->line.enabled || a->cw[0].enabled)) return false;
+  if (e->use_fused) return true;
+  if (!e->fused_auto) return false;
+  return (double)(e->r_hi - e->r_lo + 1) * (double)(e->c_hi - e->c_lo + 1) >= 4194304.0;
+}
+
 int b200_fused_prepare(b200fdtd_engine *e)
 {
   FusedState &fs = e->fused;
@@ -661,7 +690,7 @@ int b200_fused_prepare(b200fdtd_engine *e)
   const int n_cols = e->c_hi - e->c_lo + 1, n_rows = e->r_hi - e->r_lo + 1;
   if (n_cols < 1 || n_rows < 1) { fs.ready = true; fs.n_strips = fs.n_bands = 0; return B200FDTD_OK; }
   fs.n_strips = (n_cols + 31) / 32;
-  if (fs.band_h <= 0) fs.band_h = 256;
+  if (fs.band_h <= 0) fs.band_h = (e->fused_variant >= 20 && e->fused_variant <= 30) ? 32 : 256;
   fs.n_bands = (n_rows + fs.band_h - 1) / fs.band_h;
   const size_t col_n = (size_t)(fs.n_strips + 1) * e->rows, row_n = (size_t)(fs.n_bands + 1) * e->pitch;
   void **ptrs[4] = { (void **)&fs.col_e, (void **)&fs.col_h, (void **)&fs.row_e, (void **)&fs.row_h };

@@ -116,3 +116,33 @@ def test_constant_division_shortcut_is_exactly_ieee(plugin_lib, divisor):
     bad = C.c_uint64(123)
     B.check(plugin_lib.b200fdtd_selftest_division(divisor, 1 << 31, C.byref(bad)), "selftest")
     assert bad.value == 0
+
+
+def test_one_pass_step_is_the_default_on_large_grids(plugin_lib, in_tmp_cwd, monkeypatch):
+    """auto (default): grids of >= 2^22 updated cells take the TMA-staged one-pass step -- through
+    b200fdtd_step and through the plugin's deferred multi-step replay (device clock, CUDA graph) --
+    and produce the bits of the two-kernel step on all nine arrays and the NTFF history."""
+    npx, npy, steps = 2048, 2100, 24
+    res = {}
+    for mode in ("2", "0"):
+        monkeypatch.setenv("B200FDTD_FUSED", mode)
+        gpu = B.Plugin("MIE_CYLINDER", "TM_UPML_2D", npx, npy, steps=steps, h_u_nm=10, angle_deg=20)
+        form = C.c_int32(-1)
+        B.check(gpu.L.b200fdtd_get_step_form(gpu.engine_handle(), C.byref(form)), "get_step_form")
+        assert form.value == (3 if mode == "2" else 1)
+        n0 = gpu.launches()
+        gpu.run()
+        gpu.sync()
+        per_step = (gpu.launches() - n0) / steps
+        assert per_step == (5 if mode == "2" else 6)     # pre-pass x2 + one pass | (interior + frame) x2; + sample + clock
+        res[mode] = [gpu.any_field(s) for s in range(9)] + [gpu.ntff_uw(s, project=(s == 0)) for s in range(3)]
+        gpu.finish()
+    assert np.abs(res["0"][0]).max() > 0
+    for n, (a, b) in enumerate(zip(res["2"], res["0"])):
+        assert bit_equal(a, b), n
+    # small grids keep one kernel per phase
+    monkeypatch.setenv("B200FDTD_FUSED", "2")
+    small = B.Plugin("MIE_CYLINDER", "TM_UPML_2D", 256, 256, steps=8, h_u_nm=10)
+    B.check(small.L.b200fdtd_get_step_form(small.engine_handle(), C.byref(form)), "get_step_form")
+    assert form.value == 0
+    small.finish()
