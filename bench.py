@@ -306,10 +306,14 @@ def gpu_arm(args):
         # 0 full kernels, 1 unit-coefficient interior + frame, 2 lean interior + frame, 3 one-pass step
         form = run.engine.step_form()
         two_kernel_form = form
-        if form == 3:       # phase_h / phase_e (timed separately below, for reference) use this form:
+        if form == 3 and world > 1 and args.halo != "peer":
+            form = -1       # NCCL send/recv halos run between the two phase kernels: no one-pass step there
+        if form in (3, -1):       # phase_h / phase_e (timed separately below, for reference) use this form:
             run.engine.set_option(B.OPT_FUSED, 0)
             two_kernel_form = run.engine.step_form()
             run.engine.set_option(B.OPT_FUSED, 2)
+            if form == -1:
+                form = two_kernel_form
 
         # ---- value: device-resident K steps + deferred projection ----------------
         for _ in range(W):

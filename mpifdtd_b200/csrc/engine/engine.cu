@@ -754,7 +754,18 @@ int b200fdtd_step(b200fdtd_engine *e, const b200fdtd_step_args *a)
   if (can_pipeline) {
     rc = b200_launch_upml_pipelined(e, a);      // H and E of one step in one persistent kernel
   } else if (b200_want_fused(e, a)) {
-    rc = b200_launch_upml_fused(e, a);          // H and E in one pass
+    // H and E in one pass.  On a y-slab with peer halos: my last column's Hx goes up first (edge
+    // kernel; it also saves the old ghost Ez the pass needs), the pass waits for the lower
+    // neighbour's, and stores my first column's Ez downward itself.
+    const unsigned long long step = (unsigned long long)a->time;
+    if (e->peer.attached[1]) {
+      if (step > 0) rc = b200_peer_wait(e, 1, step);        // upper neighbour's Ez of step-1 is in my ghost column
+      if (!rc) rc = b200_launch_fused_edge(e, a);
+      if (!rc) rc = b200_peer_signal(e, e->peer.up_flag, step + 1);
+    }
+    if (!rc && e->peer.attached[0]) rc = b200_peer_wait(e, 0, step + 1);   // lower neighbour's Hx of this step
+    if (!rc) rc = b200_launch_upml_fused(e, a);
+    if (!rc && e->peer.attached[0]) rc = b200_peer_signal(e, e->peer.down_flag, step + 1);
   } else if (e_first) {              // mpiTM_UPML.c:196-217: E, source, H, NTFF
     rc = b200_launch_upml_e(e, a);
     if (!rc) rc = b200_launch_upml_h(e, a);

@@ -47,6 +47,7 @@ struct FusedState {          // side buffers of the fused step (fused_kernels.cu
   bool ready;
   int n_strips, n_bands, band_h;
   double2 *col_e, *col_h, *row_e, *row_h;
+  double2 *ghost_e;          // y-slab with an upper neighbour: old Ez of the high ghost column (see fused_kernels.cu)
 };
 
 // Pipelined step (upml_kernels.cu): one persistent kernel per time step that runs the H phase
@@ -160,6 +161,7 @@ int b200_launch_split_step(b200fdtd_engine *e, const b200fdtd_step_args *a);
 // launchers (fused_kernels.cu)
 int b200_launch_upml_fused(b200fdtd_engine *e, const b200fdtd_step_args *a);
 bool b200_want_fused(const b200fdtd_engine *e, const b200fdtd_step_args *a);
+int b200_launch_fused_edge(b200fdtd_engine *e, const b200fdtd_step_args *a);
 int b200_refresh_h(b200fdtd_engine *e);
 int b200_fused_prepare(b200fdtd_engine *e);
 void b200_fused_release(b200fdtd_engine *e);

@@ -42,6 +42,8 @@ struct FusedView {
   double2 *row_e, *row_h;       // [n_bands + 1][pitch]: old E at a band's first row,
                                 //   new H at the row just above it
   int unit_r_lo, unit_r_hi, unit_c_lo, unit_c_hi;   // frame-free rectangle (all coefficients exactly 1), or empty
+  double2 *ghost_e;             // [rows]: y-slab with an upper neighbour: the OLD Ez of my high ghost column,
+                                //   captured by the edge kernel before the neighbour may overwrite it; else nullptr
 };
 
 __device__ __forceinline__ double2 shfl_down1(double2 v)
@@ -409,6 +411,32 @@ __global__ void __launch_bounds__(32 * WARPS) tm_upml_fused_async_kernel(const F
   cp_async_wait<0>();
 }
 
+// ---- y-slab halos of the one-pass step (peer stores over NVLink) ----------------------------
+// The two-kernel step ships my last column's new Hx upward inside the H kernel and reads the upper
+// neighbour's Ez from the ghost column while no one writes it.  In one pass both need care: the
+// upper neighbour must have my Hx before ITS pass starts, and once it has been told so it may
+// overwrite my Ez ghost column at any time.  So a step opens with this kernel over my last owned
+// column: it evaluates the x-half of that column's H phase from the old state (the expressions of
+// fdtdTM_upml.c:188-189,209, i.e. the bits the pass itself will produce), stores Hx into the
+// neighbour's low ghost column, and copies the old ghost Ez into a side column the pass reads
+// instead of the live ghost.  b200fdtd_step orders it with the device-side flags (engine.cu).
+__global__ void tm_fused_edge_kernel(const FusedView f)
+{
+  const UpmlView &v = f.u;
+  const int r = v.r_lo + blockIdx.x * blockDim.x + threadIdx.x;
+  if (r > v.r_hi) return;
+  const int c = v.c_hi;                                   // == c_last: the slab has an upper neighbour
+  const size_t k = (size_t)r * v.pitch + c;
+  const double2 ez = v.f[B200FDTD_TM_EZ][k], ez_ghost = v.f[B200FDTD_TM_EZ][k + 1];
+  const double2 mx_old = v.f[B200FDTD_TM_MX][k], bx_old = v.f[B200FDTD_TM_BX][k];
+  const double c_mx = v.tj[B200FDTD_TMJ_C_MX * v.pitch + c], c_mxez = v.tj[B200FDTD_TMJ_C_MXEZ * v.pitch + c];
+  const double c_bx1 = v.ti[B200FDTD_TMI_C_BXMX1 * v.rows + r], c_bx0 = v.ti[B200FDTD_TMI_C_BXMX0 * v.rows + r];
+  const double2 mx = c_mx * mx_old - c_mxez * (ez_ghost - ez);
+  const double2 bx = (bx_old + c_bx1 * mx) - c_bx0 * mx_old;
+  v.peer_up_h[(size_t)r * v.peer_up_pitch + (B200_JOFF - 1)] = div_const(bx, v.mu0);
+  f.ghost_e[r] = ez_ghost;
+}
+
 // ---- the same march with the operands staged by TMA -----------------------------------
 // Blackwell form of the one-pass step.  A CTA owns a strip of 32*WARPS columns and a band of rows.
 // One producer warp streams the band through a ring of STAGES row buffers in shared memory with
@@ -593,6 +621,7 @@ __global__ void __launch_bounds__(32 * (WARPS + 1), MINB) tm_upml_fused_tma_kern
 
     double2 ez_right = shfl_down1(ez_cur);                // old Ez(r, c+1)
     if (lane == 31) ez_right = cta_right ? edge_e : ez_nb;
+    if (f.ghost_e != nullptr && c == v.c_hi) ez_right = f.ghost_e[r];   // never the live ghost column (see the edge kernel)
 
     const TmRowCoef rc = tm_row_coef(v, r);               // warp-uniform, L1-resident
     TmH h;
@@ -641,6 +670,9 @@ __global__ void __launch_bounds__(32 * (WARPS + 1), MINB) tm_upml_fused_tma_kern
       v.f[B200FDTD_TM_JZ][k] = jz;
       v.f[B200FDTD_TM_DZ][k] = dz;
       Ez[k] = ez;
+      // y-slab halo: my first owned column of Ez is the lower neighbour's high ghost column
+      if (v.peer_down_e != nullptr && c == v.c_first)
+        v.peer_down_e[(size_t)r * v.peer_down_pitch + v.peer_down_col] = ez;
       if (STORE_H) {
         v.f[B200FDTD_TM_HX][k] = h.hx;
         v.f[B200FDTD_TM_HY][k] = h.hy;
@@ -669,14 +701,15 @@ __global__ void derive_h_kernel(const double2 *__restrict__ b, double2 *h, int p
 
 }  // namespace
 
-// The one-pass TM step (fused_kernels.cu): a single unbatched double-precision slab without peer
-// halos, default pulse / point sources only; by default on grids of >= 2^22 updated cells, where
+// The one-pass TM step (fused_kernels.cu): an unbatched double-precision slab (alone, or with peer
+// halos), default pulse / point sources only; by default on grids of >= 2^22 updated cells, where
 // its 232 B per cell-update beat the two kernels' 264 (on small grids a step is launch-bound and
 // the pre-pass launches cost more than the bytes save).
 bool b200_want_fused(const b200fdtd_engine *e, const b200fdtd_step_args *a)
 {
   if (e->g.kind != B200FDTD_TM_UPML || e->fp32 || e->n_batch > 1 || e->lean_interior) return false;
-  if (e->peer.attached[0] || e->peer.attached[1]) return false;
+  if ((e->peer.attached[0] || e->peer.attached[1]) && !(e->fused_variant >= 20 && e->fused_variant <= 30))
+    return false;                                       // only the TMA-staged form speaks the peer-halo protocol
   if (a != nullptr && (a->line.enabled || a->cw[0].enabled)) return false;
   if (e->use_fused) return true;
   if (!e->fused_auto) return false;
@@ -686,6 +719,12 @@ bool b200_want_fused(const b200fdtd_engine *e, const b200fdtd_step_args *a)
 int b200_fused_prepare(b200fdtd_engine *e)
 {
   FusedState &fs = e->fused;
+  if (e->peer.attached[1] && fs.ghost_e == nullptr) {   // (a neighbour may be attached after the first prepare)
+    cudaError_t err = cudaMalloc((void **)&fs.ghost_e, (size_t)e->rows * sizeof(double2));
+    if (err != cudaSuccess) return b200_fail(B200FDTD_ERR_NOMEM, "fused ghost column: %s", cudaGetErrorString(err));
+    B200_CUDA(cudaMemsetAsync(fs.ghost_e, 0, (size_t)e->rows * sizeof(double2), e->stream));
+    e->dev_bytes += (size_t)e->rows * sizeof(double2);
+  }
   if (fs.ready) return B200FDTD_OK;
   const int n_cols = e->c_hi - e->c_lo + 1, n_rows = e->r_hi - e->r_lo + 1;
   if (n_cols < 1 || n_rows < 1) { fs.ready = true; fs.n_strips = fs.n_bands = 0; return B200FDTD_OK; }
@@ -708,7 +747,7 @@ int b200_fused_prepare(b200fdtd_engine *e)
 void b200_fused_release(b200fdtd_engine *e)
 {
   FusedState &fs = e->fused;
-  cudaFree(fs.col_e); cudaFree(fs.col_h); cudaFree(fs.row_e); cudaFree(fs.row_h);
+  cudaFree(fs.col_e); cudaFree(fs.col_h); cudaFree(fs.row_e); cudaFree(fs.row_h); cudaFree(fs.ghost_e);
   const int keep_band = fs.band_h;
   memset(&fs, 0, sizeof fs);
   fs.band_h = keep_band;
@@ -734,6 +773,7 @@ int b200_launch_upml_fused(b200fdtd_engine *e, const b200fdtd_step_args *a)
   f.col_e = fs.col_e; f.col_h = fs.col_h; f.row_e = fs.row_e; f.row_h = fs.row_h;
   f.unit_r_lo = e->lean_r_lo; f.unit_r_hi = e->lean_r_hi;       // empty (1, 0) when the tables have no such region
   f.unit_c_lo = e->lean_c_lo; f.unit_c_hi = e->lean_c_hi;
+  f.ghost_e = fs.ghost_e;
 
   const int n_cols = e->c_hi - e->c_lo + 1, n_rows = e->r_hi - e->r_lo + 1;
   const long long n_col_items = (long long)(f.n_edges + 1) * n_rows;
@@ -805,6 +845,24 @@ int b200_launch_upml_fused(b200fdtd_engine *e, const b200fdtd_step_args *a)
 #undef FUSED_TMA_LAUNCH
   e->launches += 3;
   e->h_stale = !e->store_h;
+  B200_CUDA(cudaGetLastError());
+  return B200FDTD_OK;
+}
+
+// First kernel of a one-pass step on a slab with an upper neighbour (see tm_fused_edge_kernel).
+int b200_launch_fused_edge(b200fdtd_engine *e, const b200fdtd_step_args *a)
+{
+  int rc = b200_fused_prepare(e);
+  if (rc) return rc;
+  if (e->fused.ghost_e == nullptr || e->peer.up_h == nullptr)
+    return b200_fail(B200FDTD_ERR_STATE, "fused edge kernel without an upper neighbour");
+  FusedView f;
+  memset(&f, 0, sizeof f);
+  f.u = make_view(e, a);
+  f.ghost_e = e->fused.ghost_e;
+  const int n_rows = e->r_hi - e->r_lo + 1;
+  tm_fused_edge_kernel<<<(n_rows + 127) / 128, 128, 0, e->stream>>>(f);
+  e->launches++;
   B200_CUDA(cudaGetLastError());
   return B200FDTD_OK;
 }

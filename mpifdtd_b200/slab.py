@@ -132,6 +132,8 @@ class SlabRun:
         e = self.engine
         if self.world == 1:
             e.step(self.args)
+        elif self.peer_halos and e.step_form() == 3:
+            e.step(self.args)       # one pass; b200fdtd_step runs the peer-halo protocol around it
         elif self.peer_halos:       # halo columns travel inside the phase kernels (peer stores)
             e.phase_h(self.args)
             e.phase_e(self.args)

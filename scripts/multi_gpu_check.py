@@ -2,7 +2,7 @@
 reproduce the single-GPU run: fields bit for bit, far field to summation-order noise.
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
-        --master-port 29511 scripts/multi_gpu_check.py [solver] [npx] [npy] [steps] [nccl|peer] [f64|f32] [exact|unit|lean]
+        --master-port 29511 scripts/multi_gpu_check.py [solver] [npx] [npy] [steps] [nccl|peer] [f64|f32] [exact|unit|fused|lean]
 """
 import os
 import sys
@@ -23,6 +23,8 @@ precision = sys.argv[6] if len(sys.argv) > 6 else "f64"     # "f32": the optiona
 form = sys.argv[7] if len(sys.argv) > 7 else "exact"        # "unit": bit-identical split form; "lean": tolerance form
 if form == "lean":
     os.environ["B200FDTD_LEAN_INTERIOR"] = "1"
+if form == "fused":     # the one-pass step forced on (auto would not pick it at test sizes); peer halos only
+    os.environ["B200FDTD_FUSED"] = "1"
 if form == "unit":      # unit-coefficient interior kernels forced on (auto would not pick them at test sizes)
     os.environ["B200FDTD_UNIT_SPLIT"] = "1"
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])

@@ -16,6 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     ("TE_UPML_2D", "nccl", "f64", "exact"), ("TE_UPML_2D", "peer", "f64", "exact"),
     ("TM_UPML_2D", "peer", "f32", "exact"), ("TE_UPML_2D", "nccl", "f32", "exact"),
     ("TM_UPML_2D", "peer", "f64", "unit"), ("TE_UPML_2D", "nccl", "f64", "unit"),
+    ("TM_UPML_2D", "peer", "f64", "fused"),
     ("TM_UPML_2D", "peer", "f64", "lean"), ("TE_UPML_2D", "peer", "f64", "lean"), ("TM_UPML_2D", "nccl", "f64", "lean")])
 def test_two_rank_run_matches_single_gpu(solver, halo, precision, form):
     import torch
