@@ -416,6 +416,12 @@ int b200fdtd_upml_interior(int32_t kind, const double *tab_i, int32_t n_px, cons
 /* the rectangle this engine's split forms use (global i / j of this slab's share; without row
  * r_lo / column c_lo, which stay with the frame kernels); {1,0,1,0} when no split form is active */
 int b200fdtd_get_lean_extent(b200fdtd_engine *e, int32_t out[4]);
+/* Host-only (no device needed): the launch geometry of the split forms for an updated rectangle
+ * and an interior rectangle inside it, both { r_lo, r_hi, c_lo, c_hi } inclusive.  rects receives up
+ * to 5 x 7 ints { r_lo, r_hi, c_lo, c_hi, bw_log2, nbx, blk_end }: first the interior launch, then the
+ * pieces of the frame launch (block numbering restarts; a block covers 2^bw_log2 columns x
+ * 256 >> bw_log2 rows).  For tests: together they must tile the updated rectangle exactly. */
+int b200fdtd_split_geometry(const int32_t updated[4], const int32_t interior[4], int32_t *rects, int32_t *n_rects);
 /* which form b200fdtd_step launches right now: 0 one full kernel per phase, 1 unit-coefficient
  * interior kernel + frame (bit-identical to 0), 2 lean interior + frame, 3 the one-pass step
  * (bit-identical to 0; phase_h / phase_e then still launch form 0 or 1) */

@@ -208,6 +208,7 @@ def lib():
     L.b200fdtd_upml_interior.argtypes = [i32, vp, i32, vp, i32, vp]
     L.b200fdtd_get_lean_extent.argtypes = [vp, vp]
     L.b200fdtd_get_step_form.argtypes = [vp, C.POINTER(i32)]
+    L.b200fdtd_split_geometry.argtypes = [vp, vp, vp, C.POINTER(i32)]
     L.mpifdtd_readConfig.argtypes = [C.c_char_p, vp]
     for name in ("fdtdTM_upml_getHx", "fdtdTM_upml_getHy", "fdtdTM_upml_getEz",
                  "fdtdTE_upml_getEx", "fdtdTE_upml_getEy", "fdtdTE_upml_getHz",

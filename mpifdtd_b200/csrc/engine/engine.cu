@@ -382,6 +382,22 @@ int b200fdtd_upml_interior(int32_t kind, const double *tab_i, int32_t n_px, cons
   return B200FDTD_OK;
 }
 
+int b200fdtd_split_geometry(const int32_t updated[4], const int32_t interior[4], int32_t *rects, int32_t *n_rects)
+{
+  if (!updated || !interior || !rects || !n_rects) return b200_fail(B200FDTD_ERR_ARG, "NULL argument");
+  if (updated[1] < updated[0] || updated[3] < updated[2] || interior[1] < interior[0] || interior[3] < interior[2] ||
+      interior[0] < updated[0] || interior[1] > updated[1] || interior[2] < updated[2] || interior[3] > updated[3])
+    return b200_fail(B200FDTD_ERR_ARG, "the interior rectangle must be a non-empty part of the updated one");
+  int out[5][7], n = 0;
+  const int u[4] = { updated[0], updated[1], updated[2], updated[3] };
+  const int in[4] = { interior[0], interior[1], interior[2], interior[3] };
+  int rc = b200_split_geometry(u, in, out, &n); if (rc) return rc;
+  for (int q = 0; q < n; q++)
+    for (int m = 0; m < 7; m++) rects[q * 7 + m] = out[q][m];
+  *n_rects = n;
+  return B200FDTD_OK;
+}
+
 int b200fdtd_get_step_form(b200fdtd_engine *e, int32_t *form)
 {
   if (!e || !form) return b200_fail(B200FDTD_ERR_ARG, "NULL argument");

@@ -138,7 +138,8 @@ int b200_fail(int code, const char *fmt, ...);
 
 // launchers (upml_kernels.cu)
 int b200_launch_upml_h(b200fdtd_engine *e, const b200fdtd_step_args *a);
-int b200_step_form(const b200fdtd_engine *e);   // 0 one kernel per phase, 1 unit-coefficient interior + frame, 2 lean interior + frame
+int b200_step_form(const b200fdtd_engine *e);
+int b200_split_geometry(const int updated[4], const int interior[4], int out[5][7], int *n_out);   // 0 one kernel per phase, 1 unit-coefficient interior + frame, 2 lean interior + frame
 int b200_launch_upml_e(b200fdtd_engine *e, const b200fdtd_step_args *a);
 int b200_launch_upml_pipelined(b200fdtd_engine *e, const b200fdtd_step_args *a);
 void b200_pipe_release(b200fdtd_engine *e);

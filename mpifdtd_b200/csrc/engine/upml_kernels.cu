@@ -1117,6 +1117,30 @@ int b200_launch_upml_pipelined(b200fdtd_engine *e, const b200fdtd_step_args *a)
   return e->fp32 ? launch_pipelined<float>(e, a) : launch_pipelined<double>(e, a);
 }
 
+// Host-only view of the launch geometry of the split forms, for tests: rectangle 0 is the interior
+// launch, the others the frame launch (block numbering restarts there).  7 ints per rectangle:
+// r_lo, r_hi, c_lo, c_hi, bw_log2, nbx, blk_end.
+int b200_split_geometry(const int updated[4], const int interior[4], int out[5][7], int *n_out)
+{
+  b200fdtd_engine e;
+  memset(&e, 0, sizeof e);
+  e.r_lo = updated[0]; e.r_hi = updated[1]; e.c_lo = updated[2]; e.c_hi = updated[3];
+  e.lean_r_lo = interior[0]; e.lean_r_hi = interior[1]; e.lean_c_lo = interior[2]; e.lean_c_hi = interior[3];
+  UpmlViewT<double> vi, vf;
+  memset(&vi, 0, sizeof vi); memset(&vf, 0, sizeof vf);
+  const unsigned nb_i = interior_rect(&e, vi), nb_f = frame_rects(&e, vf);
+  int n = 0;
+  auto put = [&](const LaunchRect &R) {
+    const int row[7] = { R.r_lo, R.r_hi, R.c_lo, R.c_hi, R.bw_log2, R.nbx, (int)R.blk_end };
+    memcpy(out[n++], row, sizeof row);
+  };
+  if (nb_i) put(vi.rect[0]);
+  for (int q = 0; q < 4 && nb_f; q++)
+    if (vf.rect[q].r_hi >= vf.rect[q].r_lo && (q == 0 || vf.rect[q].blk_end > vf.rect[q - 1].blk_end)) put(vf.rect[q]);
+  *n_out = n;
+  return B200FDTD_OK;
+}
+
 int b200_step_form(const b200fdtd_engine *e)
 {
   return lean_active(e) ? 2 : unit_active(e) ? 1 : 0;
