@@ -19,6 +19,8 @@
  *   TE update loops ............... fdtdTE_upml.c:168-192,252-314
  *   Gaussian-pulse source ......... field.c:224-256
  *   soft-start clock .............. field.c:312-315
+ *   MPI-variant solvers (ids 4/5) . mpiTM_UPML.c:196-217,337-374,430-520; mpiTE_UPML.c:250-400
+ *                                   (stepping at one rank; their ntff() is not restated)
  *   NTFF time-domain accumulation . ntffTM.c:279-371, ntffTE.c:57-157
  *   translate / FFT / spectrum .... ntffTM.c:161-232, ntffTE.c:20-55,160-195,
  *                                   cfft.c:104-179
@@ -315,6 +317,83 @@ void oracle_step(OracleSim *s, int n, int with_ntff)
 {
   for (int it = 0; it < n; it++) {
     if (s->kind == KIND_TM) step_tm(s, with_ntff); else step_te(s, with_ntff);
+    s->time += 1.0;                                                   /* field.c:312-315 */
+    s->ray_coef = 1.0 - exp(-pow(0.01 * s->time, 2));
+  }
+}
+
+/* ---- the "MPI" solver variants (ids 4 / 5) at one rank ---------------------------------------
+ * mpiTM_UPML.c:196-217 (update), 337-374 (scatteredWave), 430-520 (loops), 663-716 (coefficients);
+ * mpiTE_UPML.c:250-304 (scatteredWave, update), 337-400 (loops), 489-536 (coefficients).
+ * Differences from the serial solvers restated above: E phase first, then the source, then the
+ * H phase; a continuous-wave source (TE: on Ey only); and the loops cover ALL npx x npy cells
+ * (local 1..SUB_N_PX-2 <-> global 0..N-1) against a ring of ghost cells that stay zero at one
+ * rank -- here: neighbours outside the grid read as 0.  Coefficients and permittivity positions
+ * at global (x, y) are the serial solvers' at (i, j) (same sigma positions, same sig_max: with
+ * cos(pi/3) for TM, without for TE), so set_coefficients() above serves both.  The reference keeps
+ * (N+2) x (N+2) arrays; this restatement keeps N x N, i.e. the reference's arrays without the ring.
+ * Not restated: the variants' own ntff() (pinned by the live reference in tests/). */
+static inline cplx cell(const OracleSim *s, const cplx *a, int i, int j)
+{
+  return (i < 0 || j < 0 || i >= s->npx || j >= s->npy) ? 0 : a[i * s->npy + j];
+}
+
+static void step_mpi_tm(OracleSim *s)
+{
+  const int N = s->npy;
+  cplx **f = s->f; double **c = s->c;
+#define ALL for (int i = 0; i < s->npx; i++) for (int j = 0; j < s->npy; j++)
+  ALL { int k = i * N + j; cplx o = f[JZ][k];                         /* calcJD: left = i-1, bottom = j-1 */
+    f[JZ][k] = c[C_JZ][k] * f[JZ][k] + c[C_JZHXHY][k] * (+f[HY][k] - cell(s, f[HY], i - 1, j) - f[HX][k] + cell(s, f[HX], i, j - 1));
+    f[DZ][k] = c[C_DZ][k] * f[DZ][k] + c[C_DZJZ1][k] * f[JZ][k] - c[C_DZJZ0][k] * o; }
+  ALL { int k = i * N + j; f[EZ][k] = f[DZ][k] / s->eps[0][k]; }      /* calcE */
+  {                                                                  /* scatteredWave(Ez, EPS_EZ) */
+    double rad = s->angle_deg * M_PI / 180;
+    double ks_cos = cos(rad) * s->k_s, ks_sin = sin(rad) * s->k_s;
+    ALL { int k = i * N + j;
+      double kr = i * ks_cos + j * ks_sin;
+      f[EZ][k] += s->ray_coef * (EPS0 / s->eps[0][k] - 1.0) * cexp(I * (kr - s->omega_s * s->time)); }
+  }
+  ALL { int k = i * N + j; cplx o = f[MX][k];                         /* calcMB: top = j+1, right = i+1 */
+    f[MX][k] = c[C_MX][k] * f[MX][k] - c[C_MXEZ][k] * (cell(s, f[EZ], i, j + 1) - f[EZ][k]);
+    f[BX][k] = c[C_BX][k] * f[BX][k] + c[C_BXMX1][k] * f[MX][k] - c[C_BXMX0][k] * o; }
+  ALL { int k = i * N + j; cplx o = f[MY][k];
+    f[MY][k] = c[C_MY][k] * f[MY][k] - c[C_MYEZ][k] * (-cell(s, f[EZ], i + 1, j) + f[EZ][k]);
+    f[BY][k] = c[C_BY][k] * f[BY][k] + c[C_BYMY1][k] * f[MY][k] - c[C_BYMY0][k] * o; }
+  ALL { int k = i * N + j; f[HX][k] = f[BX][k] / MU0; }               /* calcH */
+  ALL { int k = i * N + j; f[HY][k] = f[BY][k] / MU0; }
+}
+
+static void step_mpi_te(OracleSim *s)
+{
+  const int N = s->npy;
+  cplx **f = s->f; double **c = s->c;
+  ALL { int k = i * N + j; cplx o = f[JX][k];                         /* calcJD */
+    f[JX][k] = c[C_JX][k] * f[JX][k] + c[C_JXHZ][k] * (f[HZ][k] - cell(s, f[HZ], i, j - 1));
+    f[DX][k] = c[C_DX][k] * f[DX][k] + c[C_DXJX1][k] * f[JX][k] - c[C_DXJX0][k] * o; }
+  ALL { int k = i * N + j; cplx o = f[JY][k];
+    f[JY][k] = c[C_JY][k] * f[JY][k] + c[C_JYHZ][k] * (-f[HZ][k] + cell(s, f[HZ], i - 1, j));
+    f[DY][k] = c[C_DY][k] * f[DY][k] + c[C_DYJY1][k] * f[JY][k] - c[C_DYJY0][k] * o; }
+  ALL { int k = i * N + j; f[EX][k] = f[DX][k] / s->eps[0][k]; }      /* calcE */
+  ALL { int k = i * N + j; f[EY][k] = f[DY][k] / s->eps[1][k]; }
+  {                                                                  /* scatteredWave(Ey, EPS_EY) */
+    double rad = s->angle_deg * M_PI / 180.0;
+    double ks_cos = cos(rad) * s->k_s, ks_sin = sin(rad) * s->k_s;
+    ALL { int k = i * N + j;
+      double ikx = i * ks_cos + j * ks_sin;
+      f[EY][k] += s->ray_coef * (EPS0 / s->eps[1][k] - 1) * (cos(ikx - s->omega_s * s->time) + I * sin(ikx - s->omega_s * s->time)); }
+  }
+  ALL { int k = i * N + j; cplx o = f[MZ][k];                         /* calcMB */
+    f[MZ][k] = c[C_MZ][k] * f[MZ][k] - c[C_MZEXEY][k] * (cell(s, f[EY], i + 1, j) - f[EY][k] - cell(s, f[EX], i, j + 1) + f[EX][k]);
+    f[BZ][k] = c[C_BZ][k] * f[BZ][k] + c[C_BZMZ1][k] * f[MZ][k] - c[C_BZMZ0][k] * o; }
+  ALL { int k = i * N + j; f[HZ][k] = f[BZ][k] / MU0; }               /* calcH */
+}
+
+/* n update() calls of solver id 4 (kind TM) / 5 (kind TE) on a sim made by oracle_create */
+void oracle_step_mpi(OracleSim *s, int n)
+{
+  for (int it = 0; it < n; it++) {
+    if (s->kind == KIND_TM) step_mpi_tm(s); else step_mpi_te(s);
     s->time += 1.0;                                                   /* field.c:312-315 */
     s->ray_coef = 1.0 - exp(-pow(0.01 * s->time, 2));
   }

@@ -160,6 +160,33 @@ def test_mpi_variant_solver_vs_live_reference(plugin_lib, kind, model, in_tmp_cw
     gpu.finish()
 
 
+@pytest.mark.parametrize("kind,model,angle", [(4, "MIE_CYLINDER", 25), (5, "MIE_CYLINDER", 25), (4, "ZIGZAG", 0),
+                                              (5, "LAYER", 60)])
+def test_mpi_variant_solver_vs_oracle(plugin_lib, oracle, kind, model, angle, in_tmp_cwd):
+    """The same ids against the plain-C restatement (oracle_step_mpi, pinned to the reference in
+    tests/test_oracle_cpu.py): needs nothing but this repository on the GPU box."""
+    npx, npy, steps = 130, 150, 300
+    gpu = B.Plugin(model, kind, npx, npy, steps=steps, angle_deg=angle)
+    L = gpu.L
+    maps = [(0.0, 0.0, B.D_XY)] if kind == 4 else [(0.5, 0.0, B.D_Y), (0.0, 0.5, B.D_X)]
+    eps = []
+    for xo, yo, mode in maps:
+        e = np.empty((npx, npy))
+        L.mpifdtd_fill_eps(e.ctypes.data, xo, yo, mode)
+        eps.append(e)
+    cpu = oracle.OracleSim(oracle.TM if kind == 4 else oracle.TE, npx, npy, steps, *eps, angle_deg=angle)
+    gpu.run()
+    cpu.step_mpi(steps)
+    for slot, f in enumerate(gpu.SLOTS[kind]):
+        want = cpu.field(slot)
+        assert np.abs(want).max() > 0, f
+        assert rel_err(gpu.any_field(slot), want) <= TOL_FIELD, f
+    ring = gpu.field(gpu.SLOTS[kind][0])                  # the getter's array carries the ghost ring
+    assert ring.shape == (npx + 2, npy + 2) and rel_err(ring[1:-1, 1:-1], cpu.field(0)) <= TOL_FIELD
+    gpu.finish()
+    cpu.close()
+
+
 UW_NAMES = {4: ["Ux", "Uy", "Wz"], 5: ["Wx", "Wy", "Uz"]}
 
 

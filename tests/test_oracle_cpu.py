@@ -109,3 +109,41 @@ def test_split_oracle_vs_reference_recorded_snapshots(oracle, kind):
     for f in oracle.SPLIT_FIELDS[kind]:
         assert rel_err(cpu.field(f), g["end_" + f]) <= 1e-13, ("end", f)
     cpu.close()
+
+
+MPI_FIELDS = {4: ["Ez", "Jz", "Dz", "Hx", "Mx", "Bx", "Hy", "My", "By"],
+              5: ["Ex", "Jx", "Dx", "Ey", "Jy", "Dy", "Hz", "Mz", "Bz"]}
+
+
+@pytest.mark.parametrize("kind,model,angle", [(4, "MIE_CYLINDER", 25), (5, "MIE_CYLINDER", 25), (4, "ZIGZAG", 0),
+                                              (5, "LAYER", 60)])
+def test_mpi_variant_restatement_vs_live_reference(oracle, plugin_lib, kind, model, angle):
+    """oracle_step_mpi (solver ids 4 / 5 at one rank: E first, CW source, every cell against a zero
+    ghost ring) against the unmodified reference, all nine arrays, and the coefficient arrays it
+    shares with the serial restatement against the reference's own (N+2) x (N+2) ones."""
+    from oracle import reflib
+    from mpifdtd_b200 import binding as B
+    if not reflib.available():
+        pytest.skip("oracle/_ref/libref.so not present")
+    npx, npy, steps = 90, 104, 240
+    cwd = os.getcwd()
+    ref = reflib.RefSim(model, kind, npx, npy, steps=steps, angle_deg=angle)
+    sub = (npx + 2) * (npy + 2)
+    grab = lambda name, real=False: (ref.darray(name, sub) if real else ref.carray(name, sub)).reshape(npx + 2, npy + 2)[1:-1, 1:-1]
+    if kind == 4:
+        sim = oracle.OracleSim(oracle.TM, npx, npy, steps, grab("EPS_EZ", True), angle_deg=angle)
+        coefs = oracle.TM_COEFS
+    else:
+        sim = oracle.OracleSim(oracle.TE, npx, npy, steps, grab("EPS_EX", True), grab("EPS_EY", True), angle_deg=angle)
+        coefs = oracle.TE_COEFS
+    for c in coefs:
+        assert bit_equal(sim.coef(c), grab(c, True)), c
+    for chunk in (steps // 3, steps - steps // 3):
+        ref.step(chunk)
+        sim.step_mpi(chunk)
+        for slot, f in enumerate(MPI_FIELDS[kind]):
+            want = grab(f)
+            assert rel_err(sim.field(slot), want) <= 1e-13, (f, chunk)
+    assert np.abs(grab(MPI_FIELDS[kind][0])).max() > 1e-3
+    os.chdir(cwd)          # (the reference's finish() for these ids calls MPI_Finalize; not needed)
+    sim.close()
