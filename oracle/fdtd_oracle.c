@@ -20,7 +20,8 @@
  *   Gaussian-pulse source ......... field.c:224-256
  *   soft-start clock .............. field.c:312-315
  *   MPI-variant solvers (ids 4/5) . mpiTM_UPML.c:196-217,337-374,430-520; mpiTE_UPML.c:250-400
- *                                   (stepping at one rank; their ntff() is not restated)
+ *                                   (stepping at one rank) and their own ntff():
+ *                                   mpiTM_UPML.c:840-1037, mpiTE_UPML.c:601-790
  *   NTFF time-domain accumulation . ntffTM.c:279-371, ntffTE.c:57-157
  *   translate / FFT / spectrum .... ntffTM.c:161-232, ntffTE.c:20-55,160-195,
  *                                   cfft.c:104-179
@@ -331,8 +332,7 @@ void oracle_step(OracleSim *s, int n, int with_ntff)
  * rank -- here: neighbours outside the grid read as 0.  Coefficients and permittivity positions
  * at global (x, y) are the serial solvers' at (i, j) (same sigma positions, same sig_max: with
  * cos(pi/3) for TM, without for TE), so set_coefficients() above serves both.  The reference keeps
- * (N+2) x (N+2) arrays; this restatement keeps N x N, i.e. the reference's arrays without the ring.
- * Not restated: the variants' own ntff() (pinned by the live reference in tests/). */
+ * (N+2) x (N+2) arrays; this restatement keeps N x N, i.e. the reference's arrays without the ring. */
 static inline cplx cell(const OracleSim *s, const cplx *a, int i, int j)
 {
   return (i < 0 || j < 0 || i >= s->npx || j >= s->npy) ? 0 : a[i * s->npy + j];
@@ -389,11 +389,137 @@ static void step_mpi_te(OracleSim *s)
   ALL { int k = i * N + j; f[HZ][k] = f[BZ][k] / MU0; }               /* calcH */
 }
 
+/* ---- the variants' own ntff(): mpiTM_UPML.c:840-1037, mpiTE_UPML.c:601-790 ------------------
+ * Same three-tap binning as ntffTM_TimeCalc, but: the time shift is evaluated directly per cell (no
+ * running subtraction), every tap is scaled by coef = 1/(4 pi C 1e6), and the NTFF box indices are
+ * used as LOCAL indices of the (N+2)^2 arrays -- local i is global i-1, so the surface sits one cell
+ * down-left of where the time shift says.  LOC() maps a local index to this file's N x N arrays. */
+#define LOC(a, li, lj) cell(s, (a), (li) - 1, (lj) - 1)
+#define TAPS(U, W, e, h) do {                                              \
+    U[stp + m_e - 1] += (e) * b_e * coef;  W[stp + m_h - 1] += (h) * b_h * coef;  \
+    U[stp + m_e]     += (e) * ab_e * coef; W[stp + m_h]     += (h) * ab_h * coef; \
+    U[stp + m_e + 1] -= (e) * a_e * coef;  W[stp + m_h + 1] -= (h) * a_h * coef;  \
+  } while (0)
+static inline void ntff_coef(double time, double shift, int *m, double *a, double *b, double *ab)
+{
+  double t = time + shift;
+  *m = floor(t + 0.5);
+  *a = (0.5 + t - *m);
+  *b = 1.0 - *a;
+  *ab = *a - *b;
+}
+static inline int imax(int a, int b) { return a > b ? a : b; }
+static inline int imin(int a, int b) { return a < b ? a : b; }
+
+static void ntff_mpi(OracleSim *s)
+{
+  const double C = C0, R = 1.0e6;
+  const double coef = 1.0 / (4 * M_PI * C * R);
+  const int spx = s->npx + 2, spy = s->npy + 2;         /* SUB_N_PX, SUB_N_PY at one rank */
+  const int cx = s->npx / 2, cy = s->npy / 2;
+  const int tp = s->top, bm = s->bottom, rt = s->right, lt = s->left;
+  const double timeE = s->time - 1, timeH = s->time - 0.5;
+  cplx **f = s->f;
+  int m_e, m_h;
+  double a_e, b_e, ab_e, a_h, b_h, ab_h;
+  for (int ang = 0; ang < 360; ang++) {
+    double rad = ang * M_PI / 180.0;
+    double r1x = cos(rad), r1y = sin(rad);
+    const int stp = ang * s->array_size;
+    if (s->kind == KIND_TM) {
+      cplx *Ux = s->uw[0], *Uy = s->uw[1], *Wz = s->uw[2];
+      if (0 < bm && bm < spy - 1)                       /* bottom: U_x += Ez, W_z += Hx */
+        for (int i = imax(1, lt); i < imin(spx, rt); i++) {
+          const double r2x = i - cx, r2y = bm - cy;
+          const double shift = -(r1x * r2x + r1y * r2y) / C + s->rf_per_c;
+          ntff_coef(timeE, shift, &m_e, &a_e, &b_e, &ab_e);
+          ntff_coef(timeH, shift, &m_h, &a_h, &b_h, &ab_h);
+          const cplx ez = LOC(f[EZ], i, bm);
+          const cplx hx = 0.5 * (LOC(f[HX], i, bm) + LOC(f[HX], i, bm - 1));
+          TAPS(Ux, Wz, ez, hx);
+        }
+      if (0 < rt && rt < spx - 1)                       /* right: U_y += Ez, W_z += Hy */
+        for (int j = imax(1, bm); j < imin(spy, tp); j++) {
+          const double r2x = rt - cx, r2y = j - cy;
+          const double shift = -(r1x * r2x + r1y * r2y) / C + s->rf_per_c;
+          ntff_coef(timeE, shift, &m_e, &a_e, &b_e, &ab_e);
+          ntff_coef(timeH, shift, &m_h, &a_h, &b_h, &ab_h);
+          const cplx ez = LOC(f[EZ], rt, j);
+          const cplx hy = 0.5 * (LOC(f[HY], rt, j) + LOC(f[HY], rt - 1, j));
+          TAPS(Uy, Wz, ez, hy);
+        }
+      if (0 < tp && tp < spy - 1)                       /* top */
+        for (int i = imax(1, lt); i < imin(spx, rt); i++) {
+          const double r2x = i - cx, r2y = tp - cy;
+          const double shift = -(r1x * r2x + r1y * r2y) / C + s->rf_per_c;
+          ntff_coef(timeE, shift, &m_e, &a_e, &b_e, &ab_e);
+          ntff_coef(timeH, shift, &m_h, &a_h, &b_h, &ab_h);
+          const cplx ez = -LOC(f[EZ], i, tp);
+          const cplx hx = -0.5 * (LOC(f[HX], i, tp) + LOC(f[HX], i, tp - 1));
+          TAPS(Ux, Wz, ez, hx);
+        }
+      if (0 < lt && lt < spx)                           /* left (the reference's own bound) */
+        for (int j = imax(1, bm); j < imin(spy, tp); j++) {
+          const double r2x = lt - cx, r2y = j - cy;
+          const double shift = -(r1x * r2x + r1y * r2y) / C + s->rf_per_c;
+          ntff_coef(timeE, shift, &m_e, &a_e, &b_e, &ab_e);
+          ntff_coef(timeH, shift, &m_h, &a_h, &b_h, &ab_h);
+          const cplx ez = -LOC(f[EZ], lt, j);
+          const cplx hy = -0.5 * (LOC(f[HY], lt, j) + LOC(f[HY], lt - 1, j));
+          TAPS(Uy, Wz, ez, hy);
+        }
+    } else {
+      cplx *Wx = s->uw[0], *Wy = s->uw[1], *Uz = s->uw[2];
+      if (0 < bm && bm < spy - 1)                       /* bottom: U_z -= Ex, W_x -= Hz */
+        for (int i = imax(1, lt); i < imin(spx, rt); i++) {
+          const double r2x = i - cx + 0.5, r2y = bm - cy;
+          double shift = -(r1x * r2x + r1y * r2y) / C0 + s->rf_per_c;
+          ntff_coef(timeE, shift, &m_e, &a_e, &b_e, &ab_e);
+          ntff_coef(timeH, shift, &m_h, &a_h, &b_h, &ab_h);
+          cplx ex = -LOC(f[EX], i, bm);
+          cplx hz = -0.5 * (LOC(f[HZ], i, bm) + LOC(f[HZ], i, bm - 1));
+          TAPS(Uz, Wx, ex, hz);
+        }
+      if (0 < rt && rt < spx - 1)                       /* right */
+        for (int j = imax(1, bm); j < imin(spy, tp); j++) {
+          double r2x = rt - cx, r2y = j - cy + 0.5;
+          double shift = -(r1x * r2x + r1y * r2y) / C0 + s->rf_per_c;
+          ntff_coef(timeE, shift, &m_e, &a_e, &b_e, &ab_e);
+          ntff_coef(timeH, shift, &m_h, &a_h, &b_h, &ab_h);
+          cplx ey = -LOC(f[EY], rt, j);
+          cplx hz = -0.5 * (LOC(f[HZ], rt, j) + LOC(f[HZ], rt - 1, j));
+          TAPS(Uz, Wy, ey, hz);
+        }
+      if (0 < tp && tp < spy - 1)                       /* top */
+        for (int i = imax(1, lt); i < imin(spx, rt); i++) {
+          const double r2x = i - cx + 0.5, r2y = tp - cy;
+          double shift = -(r1x * r2x + r1y * r2y) / C0 + s->rf_per_c;
+          ntff_coef(timeE, shift, &m_e, &a_e, &b_e, &ab_e);
+          ntff_coef(timeH, shift, &m_h, &a_h, &b_h, &ab_h);
+          cplx ex = LOC(f[EX], i, tp);
+          cplx hz = 0.5 * (LOC(f[HZ], i, tp) + LOC(f[HZ], i, tp - 1));
+          TAPS(Uz, Wx, ex, hz);
+        }
+      if (0 < lt && lt < spx)                           /* left */
+        for (int j = imax(1, bm); j < imin(spy, tp); j++) {
+          double r2x = lt - cx, r2y = j - cy + 0.5;
+          double shift = -(r1x * r2x + r1y * r2y) / C0 + s->rf_per_c;
+          ntff_coef(timeE, shift, &m_e, &a_e, &b_e, &ab_e);
+          ntff_coef(timeH, shift, &m_h, &a_h, &b_h, &ab_h);
+          cplx ey = LOC(f[EY], lt, j);
+          cplx hz = 0.5 * (LOC(f[HZ], lt, j) + LOC(f[HZ], lt - 1, j));
+          TAPS(Uz, Wy, ey, hz);
+        }
+    }
+  }
+}
+
 /* n update() calls of solver id 4 (kind TM) / 5 (kind TE) on a sim made by oracle_create */
-void oracle_step_mpi(OracleSim *s, int n)
+void oracle_step_mpi(OracleSim *s, int n, int with_ntff)
 {
   for (int it = 0; it < n; it++) {
     if (s->kind == KIND_TM) step_mpi_tm(s); else step_mpi_te(s);
+    if (with_ntff) ntff_mpi(s);
     s->time += 1.0;                                                   /* field.c:312-315 */
     s->ray_coef = 1.0 - exp(-pow(0.01 * s->time, 2));
   }

@@ -39,7 +39,7 @@ def lib():
         L.oracle_create.argtypes = [C.c_int] * 8 + [C.c_void_p, C.c_void_p]
         L.oracle_destroy.argtypes = [C.c_void_p]
         L.oracle_step.argtypes = [C.c_void_p, C.c_int, C.c_int]
-        L.oracle_step_mpi.argtypes = [C.c_void_p, C.c_int]
+        L.oracle_step_mpi.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.oracle_field.restype = C.c_void_p
         L.oracle_field.argtypes = [C.c_void_p, C.c_int]
         L.oracle_coef.restype = C.c_void_p
@@ -85,10 +85,11 @@ class OracleSim:
     def step(self, n=1, with_ntff=True):
         self.L.oracle_step(self.h, n, 1 if with_ntff else 0)
 
-    def step_mpi(self, n=1):
+    def step_mpi(self, n=1, with_ntff=True):
         """n update() calls of the MPI-variant solver of this kind (id 4 for TM, 5 for TE) at one
-        rank: E first, CW source, all cells against a zero ghost ring (mpiTM_UPML.c:196-217)."""
-        self.L.oracle_step_mpi(self.h, n)
+        rank: E first, CW source, all cells against a zero ghost ring (mpiTM_UPML.c:196-217), then
+        the variant's own ntff() into uw()."""
+        self.L.oracle_step_mpi(self.h, n, 1 if with_ntff else 0)
 
     def field(self, name_or_slot):
         slots = TM_SLOTS if self.kind == TM else TE_SLOTS

@@ -162,9 +162,11 @@ def test_mpi_variant_solver_vs_live_reference(plugin_lib, kind, model, in_tmp_cw
 
 @pytest.mark.parametrize("kind,model,angle", [(4, "MIE_CYLINDER", 25), (5, "MIE_CYLINDER", 25), (4, "ZIGZAG", 0),
                                               (5, "LAYER", 60)])
-def test_mpi_variant_solver_vs_oracle(plugin_lib, oracle, kind, model, angle, in_tmp_cwd):
-    """The same ids against the plain-C restatement (oracle_step_mpi, pinned to the reference in
-    tests/test_oracle_cpu.py): needs nothing but this repository on the GPU box."""
+def test_mpi_variant_solver_vs_oracle(plugin_lib, oracle, kind, model, angle, in_tmp_cwd, monkeypatch):
+    """The same ids -- stepping and their own ntff() (row a15) -- against the plain-C restatement
+    (oracle_step_mpi, pinned to the reference in tests/test_oracle_cpu.py): needs nothing but this
+    repository on the GPU box."""
+    monkeypatch.setenv("MPIFDTD_NTFF_FULL_BINS", "1")       # all arraySize bins, spills included
     npx, npy, steps = 130, 150, 300
     gpu = B.Plugin(model, kind, npx, npy, steps=steps, angle_deg=angle)
     L = gpu.L
@@ -183,6 +185,13 @@ def test_mpi_variant_solver_vs_oracle(plugin_lib, oracle, kind, model, angle, in
         assert rel_err(gpu.any_field(slot), want) <= TOL_FIELD, f
     ring = gpu.field(gpu.SLOTS[kind][0])                  # the getter's array carries the ghost ring
     assert ring.shape == (npx + 2, npy + 2) and rel_err(ring[1:-1, 1:-1], cpu.field(0)) <= TOL_FIELD
+    scale = max(np.abs(cpu.uw(slot)).max() for slot in range(3))
+    assert scale > 0
+    for slot in range(3):                                 # TM Ux, Uy, Wz | TE Wx, Wy, Uz
+        got = gpu.ntff_uw(slot, project=(slot == 0))
+        assert got.shape == (360, cpu.array_size)
+        assert np.abs(got - cpu.uw(slot)).max() <= 1e-10 * scale, slot
+    os.makedirs("MPI_TE_UPML", exist_ok=True)
     gpu.finish()
     cpu.close()
 

@@ -119,8 +119,9 @@ MPI_FIELDS = {4: ["Ez", "Jz", "Dz", "Hx", "Mx", "Bx", "Hy", "My", "By"],
                                               (5, "LAYER", 60)])
 def test_mpi_variant_restatement_vs_live_reference(oracle, plugin_lib, kind, model, angle):
     """oracle_step_mpi (solver ids 4 / 5 at one rank: E first, CW source, every cell against a zero
-    ghost ring) against the unmodified reference, all nine arrays, and the coefficient arrays it
-    shares with the serial restatement against the reference's own (N+2) x (N+2) ones."""
+    ghost ring, then the variants' own ntff()) against the unmodified reference: all nine arrays, the
+    U/W accumulators, and the coefficient arrays it shares with the serial restatement against the
+    reference's own (N+2) x (N+2) ones."""
     from oracle import reflib
     from mpifdtd_b200 import binding as B
     if not reflib.available():
@@ -145,5 +146,10 @@ def test_mpi_variant_restatement_vs_live_reference(oracle, plugin_lib, kind, mod
             want = grab(f)
             assert rel_err(sim.field(slot), want) <= 1e-13, (f, chunk)
     assert np.abs(grab(MPI_FIELDS[kind][0])).max() > 1e-3
+    # the variants' own ntff() (row a15): all arraySize bins of all 360 directions, spills included
+    for slot, name in enumerate(["Ux", "Uy", "Wz"] if kind == 4 else ["Wx", "Wy", "Uz"]):
+        want = ref.ntff_uw(name)
+        assert np.abs(want).max() > 0, name
+        assert rel_err(sim.uw(slot), want) <= 1e-13, name
     os.chdir(cwd)          # (the reference's finish() for these ids calls MPI_Finalize; not needed)
     sim.close()
