@@ -75,3 +75,18 @@ def test_frame_free_region_from_the_tables(plugin_lib, kind):
     L.mpifdtd_upml_tables(kind, ti.ctypes.data, tj.ctypes.data)
     assert L.b200fdtd_upml_interior(kind, ti.ctypes.data, 20, tj.ctypes.data, 20, out.ctypes.data) == 0
     assert out[0] > out[1] and out[2] > out[3]
+
+
+@pytest.mark.parametrize("npx,npy,pml", [(40, 52, 5), (100, 64, 16), (33, 47, 10), (256, 300, 12)])
+@pytest.mark.parametrize("kind", [2, 3])
+def test_frame_free_region_follows_the_pml_width(plugin_lib, kind, npx, npy, pml):
+    """field_sigmaX/Y vanish for pml <= u < N - pml - 1 at the integer and the half-cell position
+    (field.c:259-283), so the rectangle is [pml, N - pml - 1] in both directions."""
+    L = plugin_lib
+    L.models_setModel(B.MODELS["NO_MODEL"])
+    L.field_init(B.FieldInfo(npx * 10, npy * 10, 10, pml, 500, 0, 10))
+    ti, tj = np.empty((6, npx)), np.empty((6, npy))
+    L.mpifdtd_upml_tables(kind, ti.ctypes.data, tj.ctypes.data)
+    out = np.zeros(4, dtype=np.int32)
+    assert L.b200fdtd_upml_interior(kind, ti.ctypes.data, npx, tj.ctypes.data, npy, out.ctypes.data) == 0
+    assert tuple(int(v) for v in out) == (pml, npx - pml - 1, pml, npy - pml - 1)
