@@ -19,6 +19,7 @@
  *   TE update loops ............... fdtdTE_upml.c:168-192,252-314
  *   Gaussian-pulse source ......... field.c:224-256
  *   soft-start clock .............. field.c:312-315
+ *   opt-in sources ................ field.c:145-152,202-218; mpiTM_UPML.c:377-403
  *   MPI-variant solvers (ids 4/5) . mpiTM_UPML.c:196-217,337-374,430-520; mpiTE_UPML.c:250-400
  *                                   (stepping at one rank) and their own ntff():
  *                                   mpiTM_UPML.c:840-1037, mpiTE_UPML.c:601-790
@@ -58,6 +59,7 @@ enum { N_ANG = 360, N_FFT = 8192, LAM_FIRST = 380, LAM_LAST = 700 };
 typedef struct OracleSim {
   int kind, npx, npy, npml, nx, ny, ncell;
   int h_u_nm, steps, point_source;
+  int source_form;              /* 0 the solver's own source; 1 CW instead (id 2); 2 plane-wave line source added (ids 2, 4) */
   double lambda_s, k_s, omega_s, angle_deg;
   double time, ray_coef;
   /* NTFF box */
@@ -192,6 +194,7 @@ void oracle_destroy(OracleSim *s)
 }
 
 void oracle_set_point_source(OracleSim *s, int on) { s->point_source = on; }
+void oracle_set_source_form(OracleSim *s, int form) { s->source_form = form; }
 void oracle_set_angle(OracleSim *s, int deg) { s->angle_deg = deg; }
 
 /* ---- field.c:224-256 ------------------------------------------------------- */
@@ -266,6 +269,31 @@ static void ntff_accumulate(OracleSim *s)
   }
 }
 
+/* ---- opt-in source forms (row a10), as oracle/refbuild/wrap_*.c compose them from the reference ----
+ * field_scatteredWave (field.c:202-218; the commented alternative at fdtdTM_upml.c:62) */
+static void cw_wave(OracleSim *s, cplx *p, const double *eps, double gx, double gy)
+{
+  double rad = s->angle_deg * M_PI / 180.0;
+  double ks_cos = cos(rad) * s->k_s, ks_sin = sin(rad) * s->k_s;
+  for (int i = 1; i < s->npx - 1; i++)
+    for (int j = 1; j < s->npy - 1; j++) {
+      int k = i * s->npy + j;
+      double kr = (i + gx) * ks_cos + (j + gy) * ks_sin;
+      p[k] += s->ray_coef * (EPS0 / eps[k] - 1.0) * cexp(I * (kr - s->omega_s * s->time));
+    }
+}
+/* planeWave (mpiTM_UPML.c:377-403; commented call at :204): a line source on grid row x, columns
+ * y_lo..y_hi */
+static void plane_line(OracleSim *s, cplx *p, int x, int y_lo, int y_hi)
+{
+  const double rad = s->angle_deg * M_PI / 180;
+  const double ks_cos = cos(rad) * s->k_s, ks_sin = sin(rad) * s->k_s;
+  for (int y = y_lo; y <= y_hi; y++) {
+    double kr = (x * ks_cos + y * ks_sin) - s->time;
+    p[x * s->npy + y] += s->ray_coef * cexp(I * kr * s->omega_s);
+  }
+}
+
 static void step_tm(OracleSim *s, int with_ntff)
 {
   const int N = s->npy;
@@ -283,7 +311,9 @@ static void step_tm(OracleSim *s, int with_ntff)
     f[JZ][k] = c[C_JZ][k] * f[JZ][k] + c[C_JZHXHY][k] * (+f[HY][k] - f[HY][k - N] - f[HX][k] + f[HX][k - 1]);
     f[DZ][k] = c[C_DZ][k] * f[DZ][k] + c[C_DZJZ1][k] * f[JZ][k] - c[C_DZJZ0][k] * o; }
   INTERIOR { int k = i * N + j; f[EZ][k] = f[DZ][k] / s->eps[0][k]; } /* calcE  */
-  pulse(s, f[EZ], s->eps[0], 0, 0, 1.0);
+  if (s->source_form == 1) cw_wave(s, f[EZ], s->eps[0], 0, 0);
+  else pulse(s, f[EZ], s->eps[0], 0, 0, 1.0);
+  if (s->source_form == 2) plane_line(s, f[EZ], s->left, 1, s->npy - 2);   /* serial grid: x = NTFF left edge */
   if (s->point_source)
     f[EZ][(s->npx / 2) * N + s->npy / 2] += s->ray_coef * cexp(I * s->omega_s * s->time);
   if (with_ntff) ntff_accumulate(s);
@@ -353,6 +383,8 @@ static void step_mpi_tm(OracleSim *s)
     ALL { int k = i * N + j;
       double kr = i * ks_cos + j * ks_sin;
       f[EZ][k] += s->ray_coef * (EPS0 / s->eps[0][k] - 1.0) * cexp(I * (kr - s->omega_s * s->time)); }
+    if (s->source_form == 2)                                         /* planeWave(Ez, EPS_EZ): local i = left */
+      plane_line(s, f[EZ], s->left - 1, 0, s->npy - 1);
   }
   ALL { int k = i * N + j; cplx o = f[MX][k];                         /* calcMB: top = j+1, right = i+1 */
     f[MX][k] = c[C_MX][k] * f[MX][k] - c[C_MXEZ][k] * (cell(s, f[EZ], i, j + 1) - f[EZ][k]);

@@ -40,6 +40,7 @@ def lib():
         L.oracle_destroy.argtypes = [C.c_void_p]
         L.oracle_step.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.oracle_step_mpi.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.oracle_set_source_form.argtypes = [C.c_void_p, C.c_int]
         L.oracle_field.restype = C.c_void_p
         L.oracle_field.argtypes = [C.c_void_p, C.c_int]
         L.oracle_coef.restype = C.c_void_p
@@ -69,7 +70,7 @@ def lib():
 
 class OracleSim:
     def __init__(self, kind, n_px, n_py, steps, eps0, eps1=None, h_u_nm=10, pml=10, lambda_nm=500,
-                 angle_deg=0, point_source=False):
+                 angle_deg=0, point_source=False, source_form=0):
         self.L = lib()
         self.kind, self.n_px, self.n_py, self.steps = kind, n_px, n_py, steps
         e0 = np.ascontiguousarray(eps0, dtype=np.float64)
@@ -80,6 +81,8 @@ class OracleSim:
                                       None if e1 is None else e1.ctypes.data)
         if point_source:
             self.L.oracle_set_point_source(self.h, 1)
+        if source_form:       # 1 "CW": field_scatteredWave instead of the pulse; 2 "PLANE": planeWave added
+            self.L.oracle_set_source_form(self.h, {"CW": 1, "PLANE": 2}.get(source_form, source_form))
         self.array_size = self.L.oracle_array_size(self.h)
 
     def step(self, n=1, with_ntff=True):

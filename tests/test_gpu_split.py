@@ -280,6 +280,37 @@ def test_optional_source_forms_vs_live_reference(plugin_lib, kind, model, form, 
         B.lib().mpifdtd_setSourceForm(0)
 
 
+@pytest.mark.parametrize("kind,model,form", [(2, "MIE_CYLINDER", "CW"), (2, "NO_MODEL", "PLANE"),
+                                             (4, "NO_MODEL", "PLANE"), (4, "ZIGZAG", "PLANE")])
+def test_optional_source_forms_vs_oracle(plugin_lib, oracle, kind, model, form, in_tmp_cwd, monkeypatch):
+    """The same forms against the plain-C restatement (pinned to the reference's functions in
+    tests/test_oracle_cpu.py::test_optional_source_restatements_vs_live_reference)."""
+    monkeypatch.setenv("MPIFDTD_NTFF_FULL_BINS", "1")
+    npx, npy, steps = (256, 256, 300) if model == "NO_MODEL" else (120, 140, 360)
+    gpu = B.Plugin(model, kind, npx, npy, steps=steps, angle_deg=20, source_form=form)
+    try:
+        eps = np.empty((npx, npy))
+        gpu.L.mpifdtd_fill_eps(eps.ctypes.data, 0.0, 0.0, B.D_XY)
+        cpu = oracle.OracleSim(oracle.TM, npx, npy, steps, eps, angle_deg=20, source_form=form)
+        gpu.run()
+        if kind == 4:
+            cpu.step_mpi(steps)
+        else:
+            cpu.step(steps)
+        assert np.abs(cpu.field(0)).max() > 1e-3
+        for slot in (0, 3, 6):                            # Ez, Hx, Hy
+            assert rel_err(gpu.any_field(slot), cpu.field(slot)) <= TOL_FIELD, slot
+        scale = max(np.abs(cpu.uw(slot)).max() for slot in range(3))
+        for slot in range(3):
+            got = gpu.ntff_uw(slot, project=(slot == 0))
+            assert np.abs(got - cpu.uw(slot)).max() <= 1e-10 * scale, slot
+        os.makedirs("MPI_TE_UPML", exist_ok=True)
+        gpu.finish()
+        cpu.close()
+    finally:
+        B.lib().mpifdtd_setSourceForm(0)
+
+
 # ---------------------------------------------------------------- frequency-domain NTFF
 def test_frequency_ntff_tm_upml_vs_oracle(plugin_lib, oracle, in_tmp_cwd):
     """ntffTM_Frequency (ntffTM.c:72-158) on the GPU fields of the serial TM UPML solver."""

@@ -153,3 +153,40 @@ def test_mpi_variant_restatement_vs_live_reference(oracle, plugin_lib, kind, mod
         assert rel_err(sim.uw(slot), want) <= 1e-13, name
     os.chdir(cwd)          # (the reference's finish() for these ids calls MPI_Finalize; not needed)
     sim.close()
+
+
+@pytest.mark.parametrize("kind,model,form,hook", [
+    (2, "MIE_CYLINDER", "CW", "refhook_tm_upml_update_cw"),
+    (2, "NO_MODEL", "PLANE", "refhook_tm_upml_update_plane_wave"),
+    (4, "NO_MODEL", "PLANE", "refhook_mpi_tm_upml_update_plane_wave"),
+    (4, "ZIGZAG", "PLANE", "refhook_mpi_tm_upml_update_plane_wave")])
+def test_optional_source_restatements_vs_live_reference(oracle, kind, model, form, hook):
+    """Row a10's opt-in sources (field_scatteredWave, planeWave) in the C restatement against the
+    reference's own static functions as oracle/refbuild/wrap_*.c compose them."""
+    from oracle import reflib
+    if not reflib.available():
+        pytest.skip("oracle/_ref/libref.so not present")
+    npx, npy, steps = (128, 128, 200) if model == "NO_MODEL" else (90, 104, 240)
+    cwd = os.getcwd()
+    ref = reflib.RefSim(model, kind, npx, npy, steps=steps, angle_deg=20)
+    ring = 1 if kind == 4 else 0
+    sub = (npx + 2 * ring) * (npy + 2 * ring)
+
+    def grab(name, real=False):
+        a = (ref.darray(name, sub) if real else ref.carray(name, sub)).reshape(npx + 2 * ring, npy + 2 * ring)
+        return a[1:-1, 1:-1] if ring else a
+
+    sim = oracle.OracleSim(oracle.TM, npx, npy, steps, grab("EPS_EZ", True), angle_deg=20, source_form=form)
+    ref.step_fn(hook, steps)
+    if kind == 4:
+        sim.step_mpi(steps)
+    else:
+        sim.step(steps)
+    assert np.abs(grab("Ez")).max() > 1e-3
+    for slot, f in ((0, "Ez"), (3, "Hx"), (6, "Hy")):
+        assert rel_err(sim.field(slot), grab(f)) <= 1e-13, f
+    for slot, name in enumerate(("Ux", "Uy", "Wz")):
+        want = ref.ntff_uw(name)
+        assert rel_err(sim.uw(slot), want) <= 1e-13, name
+    os.chdir(cwd)
+    sim.close()
