@@ -7,7 +7,8 @@
  *
  * Parity status: PINNED.  tests/test_oracle_cpu.py checks this file against
  * (a) the golden vectors under tests/golden/ generated from the unmodified
- * reference by tests/golden/make_golden.py, and (b) oracle/_ref/libref.so (the
+ * reference by tests/golden/make_golden.py (serial UPML runs, and the MPI-variant
+ * ids incl. the plane-wave source), and (b) oracle/_ref/libref.so (the
  * reference compiled in place) whenever that library is present.
  *
  * What is restated, with the reference lines each block follows:

@@ -161,3 +161,39 @@ def split_fixtures():
 
 if __name__ == "__main__" and "split" in sys.argv[1:]:
     split_fixtures()
+
+
+def mpi_fixtures():
+    """The "MPI" solver ids 4 / 5 at one rank (stub single-rank MPI): eps maps, the three main
+    fields after 150 and 300 steps, U/W rows of their own ntff() (all arraySize bins); and the
+    opt-in plane-wave source on id 4.  Arrays are stored WITHOUT the ghost ring."""
+    cases = [("mpi_kind4_mie", "MIE_CYLINDER", 4, None), ("mpi_kind5_mie", "MIE_CYLINDER", 5, None),
+             ("mpi_kind4_zigzag_plane", "ZIGZAG", 4, "refhook_mpi_tm_upml_update_plane_wave")]
+    fields = {4: ["Ez", "Hx", "Hy"], 5: ["Ex", "Ey", "Hz"]}
+    eps = {4: ["EPS_EZ"], 5: ["EPS_EX", "EPS_EY"]}
+    uws = {4: ["Ux", "Uy", "Wz"], 5: ["Wx", "Wy", "Uz"]}
+    npx, npy, hu, steps, angle = 80, 92, 20, 300, 25
+    sub = (npx + 2) * (npy + 2)
+    cwd = os.getcwd()
+    for tag, model, kind, hook in cases:
+        sim = reflib.RefSim(model, kind, npx, npy, steps=steps, h_u_nm=hu, angle_deg=angle)
+        inner = lambda a: a.reshape(npx + 2, npy + 2)[1:-1, 1:-1].copy()
+        out = {"meta": np.array([npx, npy, hu, steps, angle, kind, reflib.MODELS[model], 1 if hook else 0])}
+        for e in eps[kind]:
+            out[e] = inner(sim.darray(e, sub))
+        for label, n in (("mid_", steps // 2), ("end_", steps - steps // 2)):
+            if hook:
+                sim.step_fn(hook, n)
+            else:
+                sim.step(n)
+            for f in fields[kind]:
+                out[label + f] = inner(sim.carray(f, sub))
+        for u in uws[kind]:
+            out["uw_" + u] = sim.ntff_uw(u)[ANGLE_ROWS, :]
+        os.chdir(cwd)          # (finish() of these ids calls MPI_Finalize: not called)
+        np.savez_compressed(os.path.join(HERE, tag + ".npz"), **out)
+        print(tag, "max |E|", float(np.abs(out["end_" + fields[kind][0]]).max()))
+
+
+if __name__ == "__main__" and "mpi" in sys.argv[1:]:
+    mpi_fixtures()

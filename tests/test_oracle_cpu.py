@@ -190,3 +190,27 @@ def test_optional_source_restatements_vs_live_reference(oracle, kind, model, for
         assert rel_err(sim.uw(slot), want) <= 1e-13, name
     os.chdir(cwd)
     sim.close()
+
+
+@pytest.mark.parametrize("name", ["mpi_kind4_mie", "mpi_kind5_mie", "mpi_kind4_zigzag_plane"])
+def test_mpi_variant_restatement_matches_reference_recording(oracle, name):
+    """oracle_step_mpi against arrays recorded from the unmodified reference (ids 4 / 5 at one rank,
+    tests/golden/make_golden.py mpi): pins the restatement where libref.so is absent."""
+    g = golden(name + ".npz")
+    npx, npy, hu, steps, angle, kind, _model, plane = (int(v) for v in g["meta"])
+    if kind == 4:
+        sim = oracle.OracleSim(oracle.TM, npx, npy, steps, g["EPS_EZ"], h_u_nm=hu, angle_deg=angle,
+                               source_form="PLANE" if plane else 0)
+        fields, uws = {"Ez": 0, "Hx": 3, "Hy": 6}, ["Ux", "Uy", "Wz"]
+    else:
+        sim = oracle.OracleSim(oracle.TE, npx, npy, steps, g["EPS_EX"], g["EPS_EY"], h_u_nm=hu, angle_deg=angle)
+        fields, uws = {"Ex": 0, "Ey": 3, "Hz": 6}, ["Wx", "Wy", "Uz"]
+    sim.step_mpi(steps // 2)
+    for f, slot in fields.items():
+        assert rel_err(sim.field(slot), g["mid_" + f]) <= 1e-13, f
+    sim.step_mpi(steps - steps // 2)
+    for f, slot in fields.items():
+        assert rel_err(sim.field(slot), g["end_" + f]) <= 1e-13, f
+    for slot, u in enumerate(uws):
+        assert rel_err(sim.uw(slot)[ANGLE_ROWS, :], g["uw_" + u]) <= 1e-13, u
+    sim.close()
