@@ -29,3 +29,15 @@ def test_nonzero_rank_of_reference_arm_is_silent():
     p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
                        capture_output=True, text=True, env=env, timeout=120)
     assert p.returncode == 0 and p.stdout.strip() == ""
+
+
+def test_stdout_carries_the_json_line_only():
+    """quiet_stdout() points fd 1 at stderr for the run (NCCL prints its banner on stdout at
+    N > 1) and emit() writes the line on the original stdout."""
+    code = ("import os, sys; sys.path.insert(0, %r); import bench; bench.quiet_stdout(); "
+            "os.write(1, b'NCCL version 2.28.9+cuda12.9\\n'); print('library chatter'); "
+            "bench.emit('{\"metric\": \"x\"}')" % ROOT)
+    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert p.returncode == 0, p.stderr[-2000:]
+    assert p.stdout == '{"metric": "x"}\n'
+    assert "NCCL version" in p.stderr and "library chatter" in p.stderr
