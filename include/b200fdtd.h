@@ -337,6 +337,11 @@ int b200fdtd_set_field(b200fdtd_engine *e, int32_t slot, const double *host_comp
 int b200fdtd_get_field_ld(b200fdtd_engine *e, int32_t slot, double *host_first_cell, int64_t ld_complex);
 /* slab-shaped variant: host array is [n_px][nj] complex (what one rank mirrors) */
 int b200fdtd_get_field_slab(b200fdtd_engine *e, int32_t slot, double *slab_complex);
+/* Order-independent 64-bit digest of the owned cells of a field plane (every 64-bit word mixed
+ * with its GLOBAL cell position, summed mod 2^64): equal digests <=> equal bits in equal cells,
+ * and the digests of the y-slabs of a split run add up (mod 2^64) to the single-slab digest.
+ * Lets a multi-GPU run or a stress loop prove bit-identity without moving the planes. */
+int b200fdtd_field_digest(b200fdtd_engine *e, int32_t slot, uint64_t *digest);
 int b200fdtd_zero_state(b200fdtd_engine *e);        /* the memsets of reset(), fdtdTM_upml.c:98-113 */
 
 /* ---- NTFF ---------------------------------------------------------------- */

@@ -150,6 +150,7 @@ def lib():
     L.mpifdtd_split_step_args.argtypes = [C.c_int, C.POINTER(StepArgs)]
     L.b200fdtd_selftest_division.argtypes = [dbl, C.c_uint64, C.POINTER(C.c_uint64)]
     L.b200fdtd_zero_state.argtypes = [vp]
+    L.b200fdtd_field_digest.argtypes = [vp, i32, C.POINTER(C.c_uint64)]
     L.b200fdtd_ntff_project.argtypes = [vp]
     L.b200fdtd_ntff_get_uw.argtypes = [vp, i32, vp]
     L.b200fdtd_ntff_uw_device.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_uint64)]
@@ -479,6 +480,12 @@ class Engine:
 
     def zero(self):
         check(self.L.b200fdtd_zero_state(self.h), "zero_state")
+
+    def digest(self, slot):
+        """64-bit position-mixed digest of this slab's cells of a field (sums over slabs mod 2^64)."""
+        d = C.c_uint64(0)
+        check(self.L.b200fdtd_field_digest(self.h, slot, C.byref(d)), "field_digest")
+        return d.value
 
     def set_option(self, option, value):
         check(self.L.b200fdtd_set_option(self.h, option, value), "set_option")

@@ -53,6 +53,34 @@ __global__ void fill_double_kernel(double *dst, size_t n, double value)
     dst[k] = value;
 }
 
+// Order-independent 64-bit digest of the owned cells of one field plane: every 64-bit word is
+// mixed with its GLOBAL position (i * n_py + j, word index), the mixes are summed mod 2^64.  Two
+// planes have the same digest iff (up to 2^-64) they hold the same bits in the same cells, and the
+// digests of the y-slabs of a split run add up to the digest of the single-slab plane.
+__device__ __forceinline__ unsigned long long mix64(unsigned long long x)
+{
+  x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull;
+  x ^= x >> 27; x *= 0x94d049bb133111ebull;
+  return x ^ (x >> 31);
+}
+
+template <int WORDS>      // 64-bit words per element: 2 (double2) or 1 (float2)
+__global__ void digest_kernel(const unsigned long long *plane, int pitch, int n_px, int nj, long long n_py,
+                              long long j0, unsigned long long *out)
+{
+  unsigned long long acc = 0;
+  const size_t n = (size_t)n_px * nj;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) {
+    const size_t i = t / nj, c = t - i * nj;
+    const unsigned long long *cell = plane + ((i + 1) * pitch + c + B200_JOFF) * WORDS;
+    const unsigned long long g = ((unsigned long long)i * n_py + j0 + c) * WORDS;
+#pragma unroll
+    for (int w = 0; w < WORDS; w++) acc += mix64(cell[w] ^ mix64(g + w + 0x9e3779b97f4a7c15ull));
+  }
+  for (int d = 16; d > 0; d >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, d);
+  if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
+}
+
 void free_ntff(b200fdtd_engine *e)
 {
   NtffState &n = e->ntff;
@@ -972,6 +1000,29 @@ int b200fdtd_set_field(b200fdtd_engine *e, int32_t slot, const double *host)
   cudaFree(temp);
   if (err != cudaSuccess) return b200_fail(B200FDTD_ERR_CUDA, "field upload: %s", cudaGetErrorString(err));
   return rc;
+}
+
+int b200fdtd_field_digest(b200fdtd_engine *e, int32_t slot, uint64_t *digest)
+{
+  if (!e || !digest || slot < 0 || slot >= e->n_fields) return b200_fail(B200FDTD_ERR_ARG, "bad field slot %d", slot);
+  int rc = select_device(e); if (rc) return rc;
+  rc = b200_refresh_h(e); if (rc) return rc;
+  unsigned long long *acc = nullptr;
+  cudaError_t err = cudaMalloc((void **)&acc, sizeof *acc);
+  if (err != cudaSuccess) return b200_fail(B200FDTD_ERR_NOMEM, "digest accumulator: %s", cudaGetErrorString(err));
+  cudaMemsetAsync(acc, 0, sizeof *acc, e->stream);
+  const unsigned long long *plane =
+      (const unsigned long long *)((const char *)e->field[slot] + (size_t)e->sel * e->plane * e->csize);
+  if (e->fp32) digest_kernel<1><<<1184, 256, 0, e->stream>>>(plane, e->pitch, e->g.n_px, e->g.nj, e->g.n_py, e->g.j0, acc);
+  else         digest_kernel<2><<<1184, 256, 0, e->stream>>>(plane, e->pitch, e->g.n_px, e->g.nj, e->g.n_py, e->g.j0, acc);
+  e->launches++;
+  unsigned long long host = 0;
+  err = cudaMemcpyAsync(&host, acc, sizeof host, cudaMemcpyDeviceToHost, e->stream);
+  if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
+  cudaFree(acc);
+  if (err != cudaSuccess) return b200_fail(B200FDTD_ERR_CUDA, "field digest: %s", cudaGetErrorString(err));
+  *digest = host;
+  return B200FDTD_OK;
 }
 
 int b200fdtd_zero_state(b200fdtd_engine *e)
