@@ -289,13 +289,17 @@ int b200fdtd_set_dense(b200fdtd_engine *e, int32_t slot, const double *host_map)
 /* One update() (fdtdTM_upml.c:54-66 / fdtdTE_upml.c:168-192): H phase, E phase
  * with source, NTFF surface sample.  Asynchronous on the engine's stream. */
 int b200fdtd_step(b200fdtd_engine *e, const b200fdtd_step_args *args);
-/* The same, split so a multi-GPU driver can exchange halos between phases. */
+/* The same, split so a multi-GPU driver can exchange halos between phases.  With peer halos
+ * attached AND an NTFF plan set, b200fdtd_phase_sample completes the step: it publishes the
+ * E-phase flag that b200fdtd_phase_e holds back until the surface has been sampled (the lower
+ * neighbour's next H phase overwrites a ghost column the sample reads).  b200fdtd_step runs
+ * the same protocol itself whenever peers are attached, whatever form the step takes. */
 int b200fdtd_phase_h(b200fdtd_engine *e, const b200fdtd_step_args *args);
 int b200fdtd_phase_e(b200fdtd_engine *e, const b200fdtd_step_args *args);
 int b200fdtd_phase_sample(b200fdtd_engine *e, const b200fdtd_step_args *args);
-/* H and E phase of the serial TM kind in ONE pass (what b200fdtd_step launches when
- * b200fdtd_get_step_form says 3): edge pre-pass + the TMA-staged marching kernel; an error if the
- * engine / source is not served by it (see B200FDTD_OPT_FUSED). */
+/* H and E phase of the serial UPML kinds in ONE pass (what b200fdtd_step launches when
+ * b200fdtd_get_step_form says 3 or 4): edge pre-pass + the TMA-staged marching kernel; an error if
+ * the engine / source is not served by it (see B200FDTD_OPT_FUSED). */
 int b200fdtd_phase_fused(b200fdtd_engine *e, const b200fdtd_step_args *args);
 int b200fdtd_sync(b200fdtd_engine *e);
 /* n_steps consecutive update() calls starting at time0, replayed from a CUDA graph: the step's
@@ -325,6 +329,11 @@ int b200fdtd_halo_unpack(b200fdtd_engine *e, int32_t which, const void *dev_buf)
 #define B200FDTD_PEER_BLOB_BYTES 256
 int b200fdtd_peer_export(b200fdtd_engine *e, void *blob);
 int b200fdtd_peer_attach(b200fdtd_engine *e, int32_t which_neighbour, const void *blob);
+/* The same between two engines of ONE process (several devices driven by one host thread -- the
+ * C plugin's multi-GPU mode -- or several slabs on one device): plain pointers, CUDA peer access
+ * enabled on demand; no IPC, no NCCL.  Attach both directions: lower.attach(1, upper) and
+ * upper.attach(0, lower). */
+int b200fdtd_peer_attach_engine(b200fdtd_engine *e, int32_t which_neighbour, b200fdtd_engine *neighbour);
 /* Launch everything on this CUDA stream (a cudaStream_t) from now on. */
 int b200fdtd_set_stream(b200fdtd_engine *e, void *cuda_stream);
 
@@ -350,6 +359,9 @@ int b200fdtd_zero_state(b200fdtd_engine *e);        /* the memsets of reset(), f
  * Ux,Uy,Wz; TE Wx,Wy,Uz. */
 int b200fdtd_ntff_project(b200fdtd_engine *e);
 int b200fdtd_ntff_get_uw(b200fdtd_engine *e, int32_t slot, double *host_complex);
+/* dst.U/W += src.U/W after both have been projected: the end-of-run sum over the y-slabs of one
+ * process (peer copy + one kernel; the reference's MPI solvers never reduce) */
+int b200fdtd_ntff_add_uw(b200fdtd_engine *dst, b200fdtd_engine *src);
 /* device pointer + element count of the whole U/W block, for an NCCL reduce */
 int b200fdtd_ntff_uw_device(b200fdtd_engine *e, void **dev_ptr, uint64_t *n_doubles);
 /* out[(lambda-lambda_first)*n_angles + ang], the table ntff_outputEnormBin writes */
@@ -370,24 +382,20 @@ int b200fdtd_ntff_frequency(b200fdtd_engine *e, const b200fdtd_freq_args *args, 
 
 /* ---- tuning switches ------------------------------------------------------ */
 enum {
-  B200FDTD_OPT_FUSED = 1,     /* the one-pass H+E step of the serial TM kind (one unbatched double-
-                                 precision slab without peer halos; 232 instead of 264 B per
-                                 cell-update, bit-identical): 1 wherever it can run, 0 never,
-                                 2 (default) on grids of >= 2^22 updated cells                   */
-  B200FDTD_OPT_STORE_H = 2,   /* 1: the fused kernel also writes Hx/Hy every step (264 B/cell);
+  B200FDTD_OPT_FUSED = 1,     /* the one-pass H+E step (fused_kernels.cu) of the serial UPML kinds (2 TM,
+                                 3 TE; one unbatched double-precision slab, alone or with peer halos):
+                                 TM 232 instead of 264 B per cell-update, TE 272 instead of 288,
+                                 bit-identical to the two-kernel step; with OPT_LEAN_INTERIOR TM 136
+                                 instead of 168, TE 176 instead of 192, bit-identical to the two-kernel
+                                 lean step.  1 wherever it can run, 0 never, 2 (default) on grids of
+                                 >= 2^22 updated cells                                           */
+  B200FDTD_OPT_STORE_H = 2,   /* 1: the one-pass kernel also writes H every step (+32 / +16 B/cell);
                                  0 (default): H is derived from B on demand (getters, NTFF,
-                                 halo) -- Hx == Bx/mu0 holds after every H phase (232 B/cell)    */
-  B200FDTD_OPT_BAND_ROWS = 3, /* rows a warp marches per band in the fused kernel (default 32 for
-                                 the TMA-staged forms, 256 for the others)                       */
-  B200FDTD_OPT_FUSED_SHAPE = 4, /* form of the fused kernel: 20 (default) .. 30 operands staged by
-                                 TMA bulk copies behind an mbarrier ring, 10..15 by cp.async,
-                                 0..5 prefetched in registers (see fused_kernels.cu)             */
-  B200FDTD_OPT_PIPELINED = 5,  /* 1: b200fdtd_step of an unbatched, peer-less UPML engine runs ONE
-                                  persistent kernel per step that overlaps the H phase of row band
-                                  k+1 with the E phase of band k, so the E phase finds Bx/By (Bz) in
-                                  L2: 232 instead of 264 B/cell of DRAM traffic (TM).  Bit-identical
-                                  to the two-kernel step.  0: two kernels.                        */
-  B200FDTD_OPT_PIPE_BAND_ROWS = 6, /* rows per band of the pipelined step (default 4)            */
+                                 halo) -- Hx == Bx/mu0 holds after every H phase                 */
+  B200FDTD_OPT_BAND_ROWS = 3, /* rows a CTA marches per band in the one-pass kernel (default 32)  */
+  B200FDTD_OPT_FUSED_SHAPE = 4, /* launch shape of the one-pass kernel, consumer warps x row buffers:
+                                 20 (default) 8 x 4, 21 8 x 6, 22 16 x 3 (TM only), 23 4 x 8, 24 8 x 3 */
+  /* 5, 6: retired (the pipelined persistent step of round 1) */
   B200FDTD_OPT_F32_PAIRS = 7,  /* single-precision engines: 1 (default) two cells per thread with
                                   128-bit accesses, 0 the one-cell-per-thread kernels; identical bits */
   B200FDTD_OPT_UNIT_SPLIT = 9,  /* UPML kinds, double precision, two-kernel step.  Inside the frame-free
@@ -429,7 +437,8 @@ int b200fdtd_get_lean_extent(b200fdtd_engine *e, int32_t out[4]);
 int b200fdtd_split_geometry(const int32_t updated[4], const int32_t interior[4], int32_t *rects, int32_t *n_rects);
 /* which form b200fdtd_step launches right now: 0 one full kernel per phase, 1 unit-coefficient
  * interior kernel + frame (bit-identical to 0), 2 lean interior + frame, 3 the one-pass step
- * (bit-identical to 0; phase_h / phase_e then still launch form 0 or 1) */
+ * (bit-identical to 0; phase_h / phase_e then still launch form 0 or 1), 4 the one-pass step in
+ * the lean form (bit-identical to 2) */
 int b200fdtd_get_step_form(b200fdtd_engine *e, int32_t *form);
 
 /* Device self-test: the kernels replace `x / d` (d loop-invariant, e.g. MU_0_S) by a

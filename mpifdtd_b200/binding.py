@@ -25,7 +25,7 @@ SOLVERS = dict(TM_2D=0, TE_2D=1, TM_UPML_2D=2, TE_UPML_2D=3,
                MPI_TM_UPML_2D=4, MPI_TE_UPML_2D=5, NS_TM_2D=6, NS_TE_2D=7)
 D_X, D_Y, D_XY = 0, 1, 2
 UPML_TABS = 6
-OPT_FUSED, OPT_STORE_H, OPT_BAND_ROWS, OPT_FUSED_SHAPE, OPT_PIPELINED, OPT_PIPE_BAND_ROWS, OPT_F32_PAIRS = 1, 2, 3, 4, 5, 6, 7
+OPT_FUSED, OPT_STORE_H, OPT_BAND_ROWS, OPT_FUSED_SHAPE, OPT_F32_PAIRS = 1, 2, 3, 4, 7
 OPT_LEAN_INTERIOR = 8
 OPT_UNIT_SPLIT = 9
 
@@ -139,6 +139,8 @@ def lib():
     L.b200fdtd_set_dense.argtypes = [vp, i32, vp]
     L.b200fdtd_peer_export.argtypes = [vp, vp]
     L.b200fdtd_peer_attach.argtypes = [vp, i32, vp]
+    L.b200fdtd_peer_attach_engine.argtypes = [vp, i32, vp]
+    L.b200fdtd_ntff_add_uw.argtypes = [vp, vp]
     L.mpifdtd_ntffFrequency.argtypes = [C.c_int, vp]
     L.mpifdtd_split_prepare_host.argtypes = [C.c_int]
     L.mpifdtd_split_prepare_host_lean.argtypes = [C.c_int]
@@ -456,6 +458,13 @@ class Engine:
         buf = C.create_string_buffer(blob, 256)
         check(self.L.b200fdtd_peer_attach(self.h, which_neighbour, buf), "peer_attach")
 
+    def peer_attach_engine(self, which_neighbour, other):
+        """Same-process attachment (several slabs / devices under one host thread)."""
+        check(self.L.b200fdtd_peer_attach_engine(self.h, which_neighbour, other.h), "peer_attach_engine")
+
+    def add_uw(self, other):
+        check(self.L.b200fdtd_ntff_add_uw(self.h, other.h), "ntff_add_uw")
+
     def halo_pack(self, which, dev_ptr):
         check(self.L.b200fdtd_halo_pack(self.h, which, C.c_void_p(dev_ptr)), "halo_pack")
 
@@ -492,7 +501,7 @@ class Engine:
 
     def step_form(self):
         """0 one full kernel per phase, 1 unit-coefficient interior + frame, 2 lean interior + frame,
-        3 the one-pass step (phase_h / phase_e then still launch form 0 or 1)."""
+        3 the one-pass step (phase_h / phase_e then still launch form 0 or 1), 4 one pass, lean form."""
         form = C.c_int32(-1)
         check(self.L.b200fdtd_get_step_form(self.h, C.byref(form)), "get_step_form")
         return form.value

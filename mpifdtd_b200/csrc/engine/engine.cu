@@ -81,6 +81,12 @@ __global__ void digest_kernel(const unsigned long long *plane, int pitch, int n_
   if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
 }
 
+__global__ void axpy_double_kernel(double *dst, const double *src, size_t n)
+{
+  for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x)
+    dst[k] += src[k];
+}
+
 void free_ntff(b200fdtd_engine *e)
 {
   NtffState &n = e->ntff;
@@ -192,19 +198,17 @@ int b200fdtd_create(const b200fdtd_grid *grid, b200fdtd_engine **out)
   e->rsize = e->fp32 ? sizeof(float) : sizeof(double);
   e->use_fused = false;     // the one-pass kernel: everywhere it can run (B200FDTD_OPT_FUSED = 1) ...
   e->fused_auto = true;     // ... or, by default, on large single-slab TM grids (2 = auto)
-  e->fused_variant = 20;    // TMA-staged form, 256 columns x 4 row buffers
+  e->fused_variant = 20;    // 8 consumer warps (256 columns) x 4 row buffers
   e->store_h = false;
   e->h_stale = false;
   if (const char *v = getenv("B200FDTD_FUSED")) {
-    e->use_fused = atoi(v) == 1 && grid->kind == B200FDTD_TM_UPML && !e->fp32 && n_batch == 1;
+    e->use_fused = atoi(v) == 1 && (grid->kind == B200FDTD_TM_UPML || grid->kind == B200FDTD_TE_UPML) && !e->fp32 &&
+                   n_batch == 1;
     e->fused_auto = atoi(v) == 2;
   }
   if (const char *v = getenv("B200FDTD_STORE_H")) e->store_h = atoi(v) != 0;
   e->f32_pairs = true;
   if (const char *v = getenv("B200FDTD_F32_PAIRS")) e->f32_pairs = atoi(v) != 0;
-  e->use_pipelined = false;
-  if (const char *v = getenv("B200FDTD_PIPELINED")) e->use_pipelined = atoi(v) != 0;
-  if (const char *v = getenv("B200FDTD_PIPE_BAND_ROWS")) e->pipe.band_rows = atoi(v);
   if (const char *v = getenv("B200FDTD_FUSED_SHAPE")) e->fused_variant = atoi(v);
   if (const char *v = getenv("B200FDTD_BAND_ROWS")) e->fused.band_h = atoi(v);
   e->unit_split = 2;
@@ -263,7 +267,6 @@ int b200fdtd_destroy(b200fdtd_engine *e)
   for (int s = 0; s < B200FDTD_MAX_DENSE; s++) cudaFree(e->dense[s]);
   free_ntff(e);
   b200_fused_release(e);
-  b200_pipe_release(e);
   peer_release(e);
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
@@ -337,6 +340,50 @@ int b200fdtd_peer_attach(b200fdtd_engine *e, int32_t which, const void *blob)
     e->peer.opened[0] = p_e; e->peer.opened[1] = p_f;
   }
   e->peer.attached[which] = true;
+  return B200FDTD_OK;
+}
+
+// The same attachment between two engines of ONE process (one host thread driving several
+// devices, or several slabs on one device): plain pointers, peer access enabled on demand.
+int b200fdtd_peer_attach_engine(b200fdtd_engine *e, int32_t which, b200fdtd_engine *nb)
+{
+  if (!e || !nb || e == nb || which < 0 || which > 1) return b200_fail(B200FDTD_ERR_ARG, "bad peer argument");
+  if (!kind_is_upml(e->g.kind) || e->n_batch > 1 || nb->n_batch > 1)
+    return b200_fail(B200FDTD_ERR_ARG, "peer halos serve unbatched engines of the UPML kinds");
+  if (nb->rows != e->rows || nb->g.kind != e->g.kind || nb->fp32 != e->fp32)
+    return b200_fail(B200FDTD_ERR_ARG, "neighbour slab has another shape, solver kind or precision");
+  b200fdtd_engine *both[2] = { e, nb };
+  for (int n = 0; n < 2; n++) {
+    int rc = select_device(both[n]); if (rc) return rc;
+    if (!both[n]->peer.flags) {
+      rc = dev_alloc_zero(both[n], (void **)&both[n]->peer.flags, 2 * sizeof(unsigned long long));
+      if (rc) return rc;
+      B200_CUDA(cudaStreamSynchronize(both[n]->stream));
+    }
+  }
+  int rc = select_device(e); if (rc) return rc;
+  if (nb->device != e->device) {
+    int can = 0;
+    B200_CUDA(cudaDeviceCanAccessPeer(&can, e->device, nb->device));
+    if (!can) return b200_fail(B200FDTD_ERR_STATE, "device %d cannot access device %d", e->device, nb->device);
+    cudaError_t err = cudaDeviceEnablePeerAccess(nb->device, 0);
+    if (err == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+    else if (err != cudaSuccess) return b200_fail(B200FDTD_ERR_CUDA, "enable peer access: %s", cudaGetErrorString(err));
+  }
+  int es, hs;
+  peer_slots(e, &es, &hs);
+  if (which == 1) {                     // upper neighbour: I store H into its low ghost column
+    e->peer.up_h = nb->field[hs];
+    e->peer.up_pitch = nb->pitch;
+    e->peer.up_flag = nb->peer.flags + 0;
+  } else {                              // lower neighbour: I store E into its high ghost column
+    e->peer.down_e = nb->field[es];
+    e->peer.down_pitch = nb->pitch;
+    e->peer.down_nj = nb->g.nj;
+    e->peer.down_flag = nb->peer.flags + 1;
+  }
+  e->peer.attached[which] = true;
+  e->graph_epoch++;
   return B200FDTD_OK;
 }
 
@@ -430,7 +477,7 @@ int b200fdtd_get_step_form(b200fdtd_engine *e, int32_t *form)
 {
   if (!e || !form) return b200_fail(B200FDTD_ERR_ARG, "NULL argument");
   *form = kind_is_upml(e->g.kind) && e->have_tabs ? b200_step_form(e) : 0;
-  if (kind_is_upml(e->g.kind) && e->have_tabs && b200_want_fused(e, nullptr)) *form = 3;
+  if (kind_is_upml(e->g.kind) && e->have_tabs && b200_want_fused(e, nullptr)) *form = (*form == 2) ? 4 : 3;
   return B200FDTD_OK;
 }
 
@@ -718,7 +765,13 @@ int b200fdtd_phase_e(b200fdtd_engine *e, const b200fdtd_step_args *a)
   // my low ghost column (Hx / Hz) is written by the lower neighbour's H phase of this step
   if (e->peer.attached[0]) { rc = b200_peer_wait(e, 0, step + 1); if (rc) return rc; }
   rc = b200_launch_upml_e(e, a);                // reads B/mu0 when the H arrays are stale; halo column downward
-  if (!rc && e->peer.attached[0]) rc = b200_peer_signal(e, e->peer.down_flag, step + 1);
+  // Once told, the lower neighbour may run its next H phase and overwrite my low ghost column of H,
+  // which the NTFF sample of THIS step still reads for surface points on my first owned column: with
+  // an NTFF plan the signal is left to b200fdtd_phase_sample, which completes the step.
+  if (!rc && e->peer.attached[0]) {
+    if (e->ntff.ready) e->peer.pending_down = step + 1;
+    else rc = b200_peer_signal(e, e->peer.down_flag, step + 1);
+  }
   return rc;
 }
 
@@ -729,8 +782,9 @@ int b200fdtd_set_option(b200fdtd_engine *e, int32_t option, int32_t value)
   e->graph_epoch++;
   switch (option) {
   case B200FDTD_OPT_FUSED:
-    if (value && (e->g.kind != B200FDTD_TM_UPML || e->fp32 || e->n_batch > 1))
-      return b200_fail(B200FDTD_ERR_ARG, "the fused step serves the serial TM kind in double precision only");
+    if (value == 1 && ((e->g.kind != B200FDTD_TM_UPML && e->g.kind != B200FDTD_TE_UPML) || e->fp32 || e->n_batch > 1))
+      return b200_fail(B200FDTD_ERR_ARG, "the one-pass step serves the serial UPML kinds (2, 3), unbatched, in double "
+                                         "precision");
     e->use_fused = value == 1;
     e->fused_auto = value == 2;
     return B200FDTD_OK;
@@ -745,21 +799,12 @@ int b200fdtd_set_option(b200fdtd_engine *e, int32_t option, int32_t value)
     e->fused.band_h = value;
     return B200FDTD_OK;
   case B200FDTD_OPT_FUSED_SHAPE:
+    if (value < 20 || value > 24) return b200_fail(B200FDTD_ERR_ARG, "one-pass launch shapes are 20..24");
+    B200_CUDA(cudaStreamSynchronize(e->stream));
     e->fused_variant = value;
-    return B200FDTD_OK;
-  case B200FDTD_OPT_PIPELINED:
-    if (value && !kind_is_upml(e->g.kind))
-      return b200_fail(B200FDTD_ERR_ARG, "the pipelined step serves the UPML kinds");
-    e->use_pipelined = value != 0;
     return B200FDTD_OK;
   case B200FDTD_OPT_F32_PAIRS:
     e->f32_pairs = value != 0;
-    return B200FDTD_OK;
-  case B200FDTD_OPT_PIPE_BAND_ROWS:
-    if (value < 1) return b200_fail(B200FDTD_ERR_ARG, "band rows must be >= 1");
-    B200_CUDA(cudaStreamSynchronize(e->stream));
-    b200_pipe_release(e);
-    e->pipe.band_rows = value;
     return B200FDTD_OK;
   case B200FDTD_OPT_UNIT_SPLIT:
     if (value < 0 || value > 2) return b200_fail(B200FDTD_ERR_ARG, "unit split: 0 off, 1 on, 2 auto");
@@ -785,7 +830,12 @@ int b200fdtd_phase_fused(b200fdtd_engine *e, const b200fdtd_step_args *a)
 int b200fdtd_phase_sample(b200fdtd_engine *e, const b200fdtd_step_args *a)
 {
   int rc = check_ready(e, a); if (rc) return rc;
-  return b200_launch_ntff_sample(e, a);
+  rc = b200_launch_ntff_sample(e, a);
+  if (!rc && e->peer.pending_down) {            // the E-phase signal b200fdtd_phase_e held back
+    rc = b200_peer_signal(e, e->peer.down_flag, e->peer.pending_down);
+    e->peer.pending_down = 0;
+  }
+  return rc;
 }
 
 int b200fdtd_step(b200fdtd_engine *e, const b200fdtd_step_args *a)
@@ -793,11 +843,18 @@ int b200fdtd_step(b200fdtd_engine *e, const b200fdtd_step_args *a)
   int rc = check_ready(e, a); if (rc) return rc;
   if (kind_is_split(e->g.kind)) return b200_launch_split_step(e, a);
   const bool e_first = (e->g.kind == B200FDTD_MPI_TM_UPML || e->g.kind == B200FDTD_MPI_TE_UPML);
-  const bool can_pipeline = e->use_pipelined && !e_first && e->n_batch == 1 && !e->store_h &&
-                            !e->peer.attached[0] && !e->peer.attached[1];
-  if (can_pipeline) {
-    rc = b200_launch_upml_pipelined(e, a);      // H and E of one step in one persistent kernel
-  } else if (b200_want_fused(e, a)) {
+  const bool peers = e->peer.attached[0] || e->peer.attached[1];
+  if (peers && e_first)
+    return b200_fail(B200FDTD_ERR_STATE, "peer halos serve the H-first UPML kinds (2, 3)");
+  if (peers && !b200_want_fused(e, a)) {
+    // two-kernel forms on a slab with neighbours: the phase entry points carry the flag protocol
+    // (wait for the neighbour's halo, launch, signal) -- never a bare launch next to a peer store
+    rc = b200fdtd_phase_h(e, a);
+    if (!rc) rc = b200fdtd_phase_e(e, a);
+    if (!rc) rc = b200fdtd_phase_sample(e, a);
+    return rc;
+  }
+  if (b200_want_fused(e, a)) {
     // H and E in one pass.  On a y-slab with peer halos: my last column's Hx goes up first (edge
     // kernel; it also saves the old ghost Ez the pass needs), the pass waits for the lower
     // neighbour's, and stores my first column's Ez downward itself.
@@ -809,7 +866,12 @@ int b200fdtd_step(b200fdtd_engine *e, const b200fdtd_step_args *a)
     }
     if (!rc && e->peer.attached[0]) rc = b200_peer_wait(e, 0, step + 1);   // lower neighbour's Hx of this step
     if (!rc) rc = b200_launch_upml_fused(e, a);
-    if (!rc && e->peer.attached[0]) rc = b200_peer_signal(e, e->peer.down_flag, step + 1);
+    // (the surface sample goes before the signal: see b200fdtd_phase_e)
+    if (!rc && e->peer.attached[0]) {
+      rc = b200_launch_ntff_sample(e, a);
+      if (!rc) rc = b200_peer_signal(e, e->peer.down_flag, step + 1);
+      return rc;
+    }
   } else if (e_first) {              // mpiTM_UPML.c:196-217: E, source, H, NTFF
     rc = b200_launch_upml_e(e, a);
     if (!rc) rc = b200_launch_upml_h(e, a);
@@ -825,8 +887,6 @@ int b200fdtd_step(b200fdtd_engine *e, const b200fdtd_step_args *a)
 // sequence depends on the step number).
 static int launch_clocked_step(b200fdtd_engine *e, const b200fdtd_step_args *a)
 {
-  // (never the pipelined kernel: its queue base and epoch change per launch, which a replayed
-  // graph cannot express)
   int rc;
   if (b200_want_fused(e, a)) {
     rc = b200_launch_upml_fused(e, a);
@@ -1035,6 +1095,7 @@ int b200fdtd_zero_state(b200fdtd_engine *e)
   // peer-halo flags restart with the step counter; a multi-rank reset must be bracketed by
   // the driver's own barrier (no rank may be mid-step while another zeroes)
   if (e->peer.flags) B200_CUDA(cudaMemsetAsync(e->peer.flags, 0, 2 * sizeof(unsigned long long), e->stream));
+  e->peer.pending_down = 0;
   NtffState &n = e->ntff;
   if (n.ready) {
     const size_t nb = (size_t)e->n_batch;
@@ -1063,6 +1124,31 @@ int b200fdtd_ntff_get_uw(b200fdtd_engine *e, int32_t slot, double *host)
   B200_CUDA(cudaMemcpyAsync(host, n.uw + ((size_t)e->sel * 3 + (size_t)slot) * count, sizeof(double2) * count,
                             cudaMemcpyDeviceToHost, e->stream));
   B200_CUDA(cudaStreamSynchronize(e->stream));
+  return B200FDTD_OK;
+}
+
+// dst.U/W += src.U/W (both projected): the end-of-run sum over the slabs of one process
+int b200fdtd_ntff_add_uw(b200fdtd_engine *dst, b200fdtd_engine *src)
+{
+  if (!dst || !src || !dst->ntff.ready || !src->ntff.ready || dst->ntff.n_angles != src->ntff.n_angles ||
+      dst->ntff.n_bins != src->ntff.n_bins || dst->n_batch != src->n_batch)
+    return b200_fail(B200FDTD_ERR_ARG, "U/W blocks of different shape");
+  const size_t n = 2ull * 3ull * (size_t)dst->ntff.n_angles * (size_t)dst->ntff.n_bins * (size_t)dst->n_batch;
+  int rc = select_device(src); if (rc) return rc;
+  B200_CUDA(cudaStreamSynchronize(src->stream));
+  rc = select_device(dst); if (rc) return rc;
+  double *tmp = nullptr;
+  cudaError_t err = cudaMalloc((void **)&tmp, n * sizeof(double));
+  if (err != cudaSuccess) return b200_fail(B200FDTD_ERR_NOMEM, "U/W staging: %s", cudaGetErrorString(err));
+  err = cudaMemcpyPeerAsync(tmp, dst->device, src->ntff.uw, src->device, n * sizeof(double), dst->stream);
+  if (err == cudaSuccess) {
+    axpy_double_kernel<<<592, 256, 0, dst->stream>>>((double *)dst->ntff.uw, tmp, n);
+    dst->launches++;
+    err = cudaGetLastError();
+  }
+  if (err == cudaSuccess) err = cudaStreamSynchronize(dst->stream);
+  cudaFree(tmp);
+  if (err != cudaSuccess) return b200_fail(B200FDTD_ERR_CUDA, "U/W sum: %s", cudaGetErrorString(err));
   return B200FDTD_OK;
 }
 

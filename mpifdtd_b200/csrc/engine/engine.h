@@ -43,23 +43,11 @@ struct NtffState {
   int sp_n_fft, sp_n_lam;
 };
 
-struct FusedState {          // side buffers of the fused step (fused_kernels.cu)
+struct FusedState {          // side buffers of the one-pass step (fused_kernels.cu)
   bool ready;
   int n_strips, n_bands, band_h;
-  double2 *col_e, *col_h, *row_e, *row_h;
+  double2 *col_e, *col_h, *row_e, *row_h;   // old E / new B at strip and band edges
   double2 *ghost_e;          // y-slab with an upper neighbour: old Ez of the high ghost column (see fused_kernels.cu)
-};
-
-// Pipelined step (upml_kernels.cu): one persistent kernel per time step that runs the H phase
-// of row band k+1 and the E phase of band k side by side, so the B arrays the E phase reads
-// are still in the 126 MB L2 when it gets to them.
-struct PipeState {
-  bool ready;
-  int band_rows, n_bands, n_ctas;
-  unsigned long long *queue;         // device: task counter, monotonic across launches
-  unsigned int *done_h;              // device [n_bands]: finished H tasks per band, monotonic
-  unsigned long long queue_value;    // host copy of *queue at the next launch
-  unsigned int epoch;                // launches so far
 };
 
 // Peer (NVLink) halo state of a y-slab engine: the neighbours' field arrays and flag words,
@@ -74,6 +62,7 @@ struct PeerState {
   unsigned long long *down_flag;     // the lower neighbour's flags[1]
   void *opened[6];                   // IPC mappings to close
   int up_pitch, down_pitch, down_nj;
+  unsigned long long pending_down;   // E-phase signal held back until the NTFF sample of the step has run (0 = none)
 };
 
 struct b200fdtd_engine {
@@ -101,7 +90,6 @@ struct b200fdtd_engine {
   NtffState ntff;
   FusedState fused;
   PeerState peer;
-  PipeState pipe;
   // multi-step replay (b200fdtd_run_steps): device clock {time} and the cached graph of a chunk
   double *clock_dev;        // device: [0] = time of the step being computed
   bool clock_mode;          // launchers build views that read the time from clock_dev
@@ -110,8 +98,7 @@ struct b200fdtd_engine {
   uint64_t graph_launches;  // kernels one replay of the cached graph launches
   unsigned graph_epoch, graph_built_epoch;   // bumped by anything that changes what a step launches
   bool f32_pairs;           // single precision: two cells per thread (default on)
-  bool use_pipelined;       // b200fdtd_step runs the pipelined persistent kernel (serial UPML kinds, one slab)
-  bool use_fused;           // b200fdtd_step runs the one-pass kernel (serial TM kind) wherever it can
+  bool use_fused;           // b200fdtd_step runs the one-pass kernel (serial UPML kinds) wherever it can
   bool fused_auto;          // ... or on large grids only (default)
   bool store_h;             // the fused kernel also writes Hx/Hy (264 instead of 232 B/cell)
   bool h_stale;             // Hx/Hy arrays lag Bx/By (fused step without store_h)
@@ -141,8 +128,6 @@ int b200_launch_upml_h(b200fdtd_engine *e, const b200fdtd_step_args *a);
 int b200_step_form(const b200fdtd_engine *e);
 int b200_split_geometry(const int updated[4], const int interior[4], int out[5][7], int *n_out);   // 0 one kernel per phase, 1 unit-coefficient interior + frame, 2 lean interior + frame
 int b200_launch_upml_e(b200fdtd_engine *e, const b200fdtd_step_args *a);
-int b200_launch_upml_pipelined(b200fdtd_engine *e, const b200fdtd_step_args *a);
-void b200_pipe_release(b200fdtd_engine *e);
 int b200_launch_halo(b200fdtd_engine *e, int which, void *buf, bool pack);
 int b200_peer_wait(b200fdtd_engine *e, int which, unsigned long long value);
 int b200_peer_signal(b200fdtd_engine *e, unsigned long long *peer_flag, unsigned long long value);

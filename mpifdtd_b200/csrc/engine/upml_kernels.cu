@@ -74,14 +74,8 @@ __device__ __forceinline__ bool locate_rect(const UpmlViewT<T> &v, int &r, int &
   return r <= R.r_hi && c <= R.c_hi;
 }
 
-// B loads of the E phase.  In the pipelined step another SM may have written these values
-// moments ago while this SM's L1 can still hold the line from its own H-phase reads of the
-// neighbouring cells, so there they are read at L2 (ld.global.cg); otherwise a plain load.
-template <bool L2_ONLY, typename C>
-__device__ __forceinline__ C ld_b(const C *p) { return L2_ONLY ? __ldcg(p) : *p; }
-
-// ---- the arithmetic of one cell, shared by the one-cell-per-thread kernels, the pipelined
-// step and the two-cells-per-thread single-precision kernels.  Expression order is the
+// ---- the arithmetic of one cell, shared by the one-cell-per-thread kernels and the
+// two-cells-per-thread single-precision kernels.  Expression order is the
 // reference's (see the citations); compiled with -fmad=false.
 template <typename T, typename C = typename Cx<T>::type>
 __device__ __forceinline__ void tm_h_math(C ez, C ez_j1, C ez_i1, C mx_old, C bx_old, C my_old, C by_old, T c_mx,
@@ -252,7 +246,7 @@ __global__ void __launch_bounds__(kBlock, B200_H_MIN_BLOCKS) tm_upml_h_kernel(co
 // FROM_B = true: H is formed on the fly as B/mu0.  Cells just outside the updated range
 // (the ring, or a neighbour slab's halo column) are not derived state: there the H array
 // itself is read, exactly like the STORE_H form does.
-template <typename T, bool FROM_B, bool L2_B = false>
+template <typename T, bool FROM_B>
 __device__ __forceinline__ void tm_upml_e_cell(const UpmlViewT<T> &v, int r, int c, size_t k, size_t k0)
 {
   using C = typename Cx<T>::type;
@@ -262,8 +256,8 @@ __device__ __forceinline__ void tm_upml_e_cell(const UpmlViewT<T> &v, int r, int
     const C *__restrict__ By = v.f[B200FDTD_TM_BY];
     // all four loads are issued unconditionally; the (block-uniform, rare) edge cases
     // then replace the derived value by the stored one
-    const C by = ld_b<L2_B>(By + k), bx = ld_b<L2_B>(Bx + k), by_i0 = ld_b<L2_B>(By + k - v.pitch),
-            bx_j0 = ld_b<L2_B>(Bx + k - 1);
+    const C by = By[k], bx = Bx[k], by_i0 = By[k - v.pitch],
+            bx_j0 = Bx[k - 1];
     hy = div_const(by, v.mu0);
     hx = div_const(bx, v.mu0);
     hy_i0 = div_const(by_i0, v.mu0);
@@ -346,7 +340,7 @@ __global__ void __launch_bounds__(kBlock, B200_TE_H_MIN_BLOCKS) te_upml_h_kernel
   te_upml_h_cell<T, STORE_H>(v, r, c, k, k0);
 }
 
-template <typename T, bool FROM_B, bool L2_B = false>
+template <typename T, bool FROM_B>
 __device__ __forceinline__ void te_upml_e_cell(const UpmlViewT<T> &v, int r, int c, size_t k, size_t k0)
 {
   using C = typename Cx<T>::type;
@@ -354,7 +348,7 @@ __device__ __forceinline__ void te_upml_e_cell(const UpmlViewT<T> &v, int r, int
   C hz, hz_j0, hz_i0;
   if (FROM_B) {                               // Hz == Bz/mu0 (fdtdTE_upml.c:312), formed on the fly
     const C *__restrict__ Bz = v.f[B200FDTD_TE_BZ];
-    const C bz = ld_b<L2_B>(Bz + k), bz_j0 = ld_b<L2_B>(Bz + k - 1), bz_i0 = ld_b<L2_B>(Bz + k - v.pitch);
+    const C bz = Bz[k], bz_j0 = Bz[k - 1], bz_i0 = Bz[k - v.pitch];
     hz = div_const(bz, v.mu0);
     hz_j0 = div_const(bz_j0, v.mu0);
     hz_i0 = div_const(bz_i0, v.mu0);
@@ -656,85 +650,6 @@ __global__ void __launch_bounds__(kBlock, B200_LEAN_MIN_BLOCKS) te_lean_e_kernel
 }
 
 #include "upml_pairs_f32.cuh"
-
-// ------------------------------------------------------------------ pipelined step -----
-// One persistent kernel per time step.  The grid is cut into bands of `band_rows` rows; a task
-// is (phase, band, block of kBlock columns) and CTAs pull tasks from a global counter in the
-// order H(0), H(1), E(0), H(2), E(1), ...  E(k) needs every H task of bands k and k-1 to have
-// finished (it reads their B, and it overwrites the Ez they read); finished H tasks are
-// counted per band and E tasks wait on those counters (they were dequeued earlier, so they
-// are running or done: no deadlock, no co-residency requirement).  Between H(k) writing Bx/By
-// and E(k) reading them lie about two bands of traffic (a few MB), so the reads hit L2 and the
-// step moves 232 B/cell of DRAM traffic instead of 264 (TM; TE 272 instead of 288), with the
-// same per-cell code and therefore bit-identical results.
-// Status: opt-in (B200FDTD_OPT_PIPELINED).  ncu confirms the traffic (231.6 B/cell at 8192^2,
-// band_rows 8) but the kernel is not DRAM-bound: the 444 tasks in flight span three stages, so
-// E tasks wait on H tasks that are still running, and per-task bookkeeping (dequeue, barriers,
-// fence + count) is paid every 2048 cells: 21.4 Gcell/s against 23.9 for the two-kernel step at
-// 16384^2.  Finer tasks shrink the window but multiply the bookkeeping; larger ones overflow L2.
-struct PipeArgs {
-  unsigned long long *queue;
-  unsigned long long queue_base;
-  unsigned int *done_h;
-  unsigned int done_target;
-  int band_rows, n_bands, nbx;
-};
-
-#ifndef B200_PIPE_MIN_BLOCKS
-#define B200_PIPE_MIN_BLOCKS 3
-#endif
-
-template <typename T, bool TM>
-__global__ void __launch_bounds__(kBlock, B200_PIPE_MIN_BLOCKS) upml_pipelined_kernel(const __grid_constant__ UpmlViewT<T> v, const PipeArgs p)
-{
-  __shared__ unsigned long long s_task;
-  const long long per_stage = 2LL * p.nbx;
-  const long long total = (long long)(p.n_bands + 1) * per_stage;
-  // (Dequeuing one task ahead was tried and is much slower: a CTA then sits on an H task that
-  // E tasks of other CTAs are already waiting for -- 10 instead of 21 Gcell/s.)
-  for (;;) {
-    __syncthreads();                                   // s_task of the previous round has been read
-    if (threadIdx.x == 0) s_task = atomicAdd(p.queue, 1ull) - p.queue_base;
-    __syncthreads();
-    const long long task = (long long)s_task;
-    if (task >= total) return;
-    const int stage = (int)(task / per_stage);
-    const int w = (int)(task - (long long)stage * per_stage);
-    const bool is_h = w < p.nbx;
-    const int band = is_h ? stage : stage - 1;
-    const bool exists = band >= 0 && band < p.n_bands;  // H of the last stage / E of the first: no such band
-    const int c = v.c_lo + (is_h ? w : w - p.nbx) * kBlock + (int)threadIdx.x;
-    const int r0 = v.r_lo + band * p.band_rows;
-    const int r1 = min(r0 + p.band_rows - 1, v.r_hi);
-    if (!exists) {
-    } else if (is_h) {
-      if (c <= v.c_hi)
-        for (int r = r0; r <= r1; r++) {
-          const size_t k = (size_t)r * (size_t)v.pitch + (size_t)c;
-          if (TM) tm_upml_h_cell<T, false>(v, r, c, k, k);
-          else    te_upml_h_cell<T, false>(v, r, c, k, k);
-        }
-      __syncthreads();                                 // the whole CTA's stores precede the count
-      if (threadIdx.x == 0) { __threadfence(); atomicAdd(p.done_h + band, 1u); }
-    } else {
-      if (threadIdx.x == 0) {
-        for (int b = band; b >= band - 1 && b >= 0; b--) {
-          unsigned int seen;
-          do {
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.done_h + b) : "memory");
-          } while ((int)(seen - p.done_target) < 0);
-        }
-      }
-      __syncthreads();
-      if (c <= v.c_hi)
-        for (int r = r0; r <= r1; r++) {
-          const size_t k = (size_t)r * (size_t)v.pitch + (size_t)c;
-          if (TM) tm_upml_e_cell<T, true, true>(v, r, c, k, k);
-          else    te_upml_e_cell<T, true, true>(v, r, c, k, k);
-        }
-    }
-  }
-}
 
 // One halo column <-> a contiguous buffer of n_px complex values (always double complex on
 // the wire, whatever the engine's precision).
@@ -1061,60 +976,6 @@ static int launch_e(b200fdtd_engine *e, const b200fdtd_step_args *a)
   e->launches++;
   B200_CUDA(cudaGetLastError());
   return B200FDTD_OK;
-}
-
-void b200_pipe_release(b200fdtd_engine *e)
-{
-  cudaFree(e->pipe.queue);
-  cudaFree(e->pipe.done_h);
-  const int rows = e->pipe.band_rows;
-  memset(&e->pipe, 0, sizeof e->pipe);
-  e->pipe.band_rows = rows;
-}
-
-template <typename T>
-static int launch_pipelined(b200fdtd_engine *e, const b200fdtd_step_args *a)
-{
-  PipeState &ps = e->pipe;
-  const bool tm = is_tm(e->g.kind);
-  const int n_rows = e->r_hi - e->r_lo + 1;
-  if (!ps.ready) {
-    if (ps.band_rows <= 0) ps.band_rows = 4;
-    ps.n_bands = (n_rows + ps.band_rows - 1) / ps.band_rows;
-    B200_CUDA(cudaMalloc(&ps.queue, sizeof(unsigned long long)));
-    B200_CUDA(cudaMalloc(&ps.done_h, sizeof(unsigned int) * (size_t)ps.n_bands));
-    B200_CUDA(cudaMemsetAsync(ps.queue, 0, sizeof(unsigned long long), e->stream));
-    B200_CUDA(cudaMemsetAsync(ps.done_h, 0, sizeof(unsigned int) * (size_t)ps.n_bands, e->stream));
-    int per_sm = 0, sms = 0;
-    if (tm) B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, upml_pipelined_kernel<T, true>, kBlock, 0));
-    else    B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, upml_pipelined_kernel<T, false>, kBlock, 0));
-    B200_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->device));
-    ps.n_ctas = (per_sm > 0 ? per_sm : 1) * (sms > 0 ? sms : 1);
-    ps.queue_value = 0;
-    ps.epoch = 0;
-    ps.ready = true;
-  }
-  const UpmlViewT<T> v = make_view_t<T>(e, a);
-  const unsigned long long total = (unsigned long long)(ps.n_bands + 1) * 2ull * (unsigned long long)v.nbx;
-  const unsigned grid = (unsigned)(total < (unsigned long long)ps.n_ctas ? total : (unsigned long long)ps.n_ctas);
-  ps.epoch++;
-  PipeArgs p;
-  p.queue = ps.queue;  p.queue_base = ps.queue_value;
-  p.done_h = ps.done_h;  p.done_target = ps.epoch * (unsigned)v.nbx;
-  p.band_rows = ps.band_rows;  p.n_bands = ps.n_bands;  p.nbx = v.nbx;
-  if (tm) upml_pipelined_kernel<T, true><<<grid, kBlock, 0, e->stream>>>(v, p);
-  else    upml_pipelined_kernel<T, false><<<grid, kBlock, 0, e->stream>>>(v, p);
-  ps.queue_value += total + grid;           // every CTA leaves on its first dequeue past the end
-  e->h_stale = true;                        // H arrays are not written (H == B/mu0 on demand)
-  e->launches++;
-  B200_CUDA(cudaGetLastError());
-  return B200FDTD_OK;
-}
-
-int b200_launch_upml_pipelined(b200fdtd_engine *e, const b200fdtd_step_args *a)
-{
-  if (e->r_hi < e->r_lo || e->c_hi < e->c_lo) return B200FDTD_OK;
-  return e->fp32 ? launch_pipelined<float>(e, a) : launch_pipelined<double>(e, a);
 }
 
 // Host-only view of the launch geometry of the split forms, for tests: rectangle 0 is the interior

@@ -132,13 +132,10 @@ class SlabRun:
         e = self.engine
         if self.world == 1:
             e.step(self.args)
-        elif self.peer_halos and e.step_form() == 3:
-            e.step(self.args)       # one pass; b200fdtd_step runs the peer-halo protocol around it
-        elif self.peer_halos:       # halo columns travel inside the phase kernels (peer stores)
-            e.phase_h(self.args)
-            e.phase_e(self.args)
-            if self.with_ntff:
-                e.phase_sample(self.args)
+        elif self.peer_halos:
+            # halo columns travel as peer stores inside the kernels; b200fdtd_step runs the flag
+            # protocol around whatever form the step takes (one pass, or H phase / E phase)
+            e.step(self.args)
         else:
             e.phase_h(self.args)
             self._exchange(0)

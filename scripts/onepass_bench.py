@@ -1,0 +1,38 @@
+"""Kernel-level timing of the one-pass step (pre-pass + marching kernel, b200fdtd_phase_fused) at
+benchmark scale: TM / TE x exact / lean x launch shapes x band heights.  CUDA events on the engine's
+stream.  `python scripts/onepass_bench.py [n] [model]` prints one line per configuration."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from mpifdtd_b200 import binding as B
+from mpifdtd_b200.slab import SlabRun
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
+model = sys.argv[2] if len(sys.argv) > 2 else "ZIGZAG"
+solvers = sys.argv[3].split(",") if len(sys.argv) > 3 else ["TM_UPML_2D", "TE_UPML_2D"]
+BYTES = {("TM_UPML_2D", 0): 232, ("TM_UPML_2D", 1): 136, ("TE_UPML_2D", 0): 272, ("TE_UPML_2D", 1): 176}
+reps = 10
+for solver in solvers:
+    run = SlabRun(model, solver, n, n, 64, with_ntff=False)
+    e = run.engine
+    run.L.mpifdtd_upml_step_args(run.kind, 0, B.C.byref(run.args))
+    for lean in (0, 1):
+        e.set_option(B.OPT_LEAN_INTERIOR, lean)
+        for shape, band in ((20, 32), (21, 32), (24, 32), (23, 32), (20, 64), (21, 64), (20, 16), (22, 32)):
+            e.set_option(B.OPT_FUSED_SHAPE, shape)
+            e.set_option(B.OPT_BAND_ROWS, band)
+            try:
+                e.phase_fused(run.args); e.phase_fused(run.args); e.sync()
+            except B.EngineError as err:
+                print(solver, "lean" if lean else "exact", "shape", shape, "band", band, "unavailable:", str(err)[:80])
+                continue
+            e.timer_start()
+            for _ in range(reps):
+                e.phase_fused(run.args)
+            ms = e.timer_stop() / reps
+            by = BYTES[(solver, lean)]
+            print("%s %-5s shape %d band %3d: %7.3f ms  %6.2f Gcell/s  %6.0f GB/s (%d B/cell)"
+                  % (solver, "lean" if lean else "exact", shape, band, ms, n * n / ms / 1e6, by * n * n / ms / 1e6, by),
+                  flush=True)
+    run.close()

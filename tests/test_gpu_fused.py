@@ -1,15 +1,17 @@
-"""Every form of the TM step must produce identical bits:
+"""Every form of a UPML step must produce identical bits:
 
-  * two-kernel step that stores Hx/Hy (the literal restatement of the reference's passes),
+  * two-kernel step that stores H (the literal restatement of the reference's passes),
   * two-kernel step that does NOT store H and forms it as B/mu0 in the E phase (default),
-  * the one-pass "warp-strip marching" kernel, with and without H stores (opt-in), with its
-    operands prefetched in registers, staged by cp.async, or staged by TMA bulk copies behind
-    an mbarrier ring (producer warp + consumer warps).
+  * the one-pass kernel (fused_kernels.cu: H and E phase of a row band in one march, operands
+    staged by TMA bulk copies behind an mbarrier ring, producer warp + consumer warps), with and
+    without H stores, in every launch shape -- for TM (fdtdTM_upml.c:155-219) and TE
+    (fdtdTE_upml.c:252-314).
 
 All evaluate the same expressions in the same order (-fmad=false), so after any number of
 steps from any state each of the nine arrays and the NTFF history must agree bit for bit
 -- including ragged strips (columns not a multiple of 32), bands of any height and strips
-narrower than a warp."""
+narrower than a warp.  The lean (tolerance) form has the same property between ITS two-kernel
+and one-pass realisations."""
 import ctypes as C
 
 import numpy as np
@@ -20,22 +22,26 @@ from mpifdtd_b200 import binding as B
 
 pytestmark = pytest.mark.gpu
 
+H_OF_B = {2: ((3, 5), (6, 8)), 3: ((6, 8),)}          # slots (H, B) tied by H == B/mu0 after any H phase
 
-def make_engine(L, npx, npy, steps, eps, fused, store_h=0, band=None, j0=0, nj=None, shape=0):
-    eng = B.Engine(2, npx, npy, 10, j0=j0, nj=nj)
+
+def make_engine(L, npx, npy, steps, eps, fused, store_h=0, band=None, j0=0, nj=None, shape=20, kind=2, lean=0):
+    eng = B.Engine(kind, npx, npy, 10, j0=j0, nj=nj)
     ti, tj = np.empty((6, npx)), np.empty((6, npy))
-    L.mpifdtd_upml_tables(2, ti.ctypes.data, tj.ctypes.data)
+    L.mpifdtd_upml_tables(kind, ti.ctypes.data, tj.ctypes.data)
     eng.set_tables(ti, tj)
-    eng.set_eps(0, eps)
+    for slot, e in enumerate(eps if isinstance(eps, (list, tuple)) else [eps]):
+        eng.set_eps(slot, e)
     box = L.field_getNTFFInfo()
     n_local = L.mpifdtd_ntff_local_count(C.byref(box), eng.j0, eng.nj)
-    ptr = L.mpifdtd_ntff_time_shift(C.byref(box), 360, 0.0, eng.j0, eng.nj)
+    ptr = L.mpifdtd_ntff_time_shift(C.byref(box), 360, 0.0 if kind == 2 else 0.5, eng.j0, eng.nj)
     plan = B.NtffPlan(box.top, box.bottom, box.left, box.right,
                       L.mpifdtd_ntff_point_count(C.byref(box)), n_local, steps, steps, 360,
                       box.arraySize, ptr)
     B.check(L.b200fdtd_set_ntff_plan(eng.h, C.byref(plan)), "plan")
     L.free(ptr)
     eng.n_bins = steps
+    eng.set_option(B.OPT_LEAN_INTERIOR, lean)
     eng.set_option(B.OPT_FUSED, fused)
     eng.set_option(B.OPT_STORE_H, store_h)
     if fused and band:
@@ -45,36 +51,26 @@ def make_engine(L, npx, npy, steps, eps, fused, store_h=0, band=None, j0=0, nj=N
     return eng
 
 
-@pytest.mark.parametrize("npx,npy,band", [(70, 96, 256), (45, 47, 7), (131, 200, 64), (300, 41, 33),
-                                          (64, 1030, 1), (257, 66, 256), (300, 700, 48)])
-def test_fused_step_is_bit_identical_to_two_kernel_step(plugin_lib, npx, npy, band):
-    L = plugin_lib
-    steps = 6
-    L.models_setModel(B.MODELS["NO_MODEL"])
-    L.field_init(B.FieldInfo(npx * 10, npy * 10, 10, 10, 500, 30, steps))
-    rng = np.random.default_rng(npx * 1000 + npy)
-    eps = np.where(rng.random((npx, npy)) < 0.5, 1.0, 1.0 + 2.0 * rng.random((npx, npy)))
+def random_case(npx, npy, kind):
+    rng = np.random.default_rng(npx * 1000 + npy + kind)
+    eps = [np.where(rng.random((npx, npy)) < 0.5, 1.0, 1.0 + 2.0 * rng.random((npx, npy)))
+           for _ in range(1 if kind == 2 else 2)]
     state = [rng.standard_normal((npx, npy)) + 1j * rng.standard_normal((npx, npy)) for _ in range(9)]
-    # H arrays must satisfy the solver's invariant Hx == Bx/mu0 (true after any H phase)
+    # H arrays must satisfy the solver's invariant H == B/mu0 (true after any H phase)
     mu0 = B.MU_0_S
-    state[3] = (state[5].real / mu0) + 1j * (state[5].imag / mu0)
-    state[6] = (state[8].real / mu0) + 1j * (state[8].imag / mu0)
-    engines = [make_engine(L, npx, npy, steps, eps, 0, store_h=1),
-               make_engine(L, npx, npy, steps, eps, 0, store_h=0),
-               make_engine(L, npx, npy, steps, eps, 1, store_h=0, band=band),
-               make_engine(L, npx, npy, steps, eps, 1, store_h=1, band=band),
-               make_engine(L, npx, npy, steps, eps, 1, store_h=0, band=band, shape=10),    # cp.async staged
-               make_engine(L, npx, npy, steps, eps, 1, store_h=1, band=band, shape=13),
-               make_engine(L, npx, npy, steps, eps, 1, store_h=0, band=band, shape=20),    # TMA staged, 256 columns
-               make_engine(L, npx, npy, steps, eps, 1, store_h=1, band=band, shape=24),    # 256 columns, 3 stages
-               make_engine(L, npx, npy, steps, eps, 1, store_h=0, band=band, shape=22)]    # 512 columns, 3 stages
+    for h, b in H_OF_B[kind]:
+        state[h] = (state[b].real / mu0) + 1j * (state[b].imag / mu0)
+    return eps, state
+
+
+def run_and_compare(L, kind, engines, state, steps):
     for eng in engines:
         for slot in range(9):
             eng.set_field(slot, state[slot])
     args = B.StepArgs()
     L.field_reset()
     for _ in range(steps):
-        L.mpifdtd_upml_step_args(2, 1, C.byref(args))       # pulse + point source both on
+        L.mpifdtd_upml_step_args(kind, 1, C.byref(args))       # pulse + point source both on
         for eng in engines:
             eng.step(args)
         L.field_nextStep()
@@ -96,6 +92,49 @@ def test_fused_step_is_bit_identical_to_two_kernel_step(plugin_lib, npx, npy, ba
     assert engines[1].launches() > 0
     for eng in engines:
         eng.close()
+
+
+CASES = [(70, 96, 256), (45, 47, 7), (131, 200, 64), (300, 41, 33), (64, 1030, 1), (257, 66, 256), (300, 700, 48)]
+
+
+@pytest.mark.parametrize("kind", [2, 3])
+@pytest.mark.parametrize("npx,npy,band", CASES)
+def test_fused_step_is_bit_identical_to_two_kernel_step(plugin_lib, npx, npy, band, kind):
+    L = plugin_lib
+    steps = 6
+    L.models_setModel(B.MODELS["NO_MODEL"])
+    L.field_init(B.FieldInfo(npx * 10, npy * 10, 10, 10, 500, 30, steps))
+    eps, state = random_case(npx, npy, kind)
+    mk = lambda *a, **kw: make_engine(L, npx, npy, steps, eps, *a, kind=kind, **kw)
+    engines = [mk(0, store_h=1), mk(0, store_h=0),
+               mk(1, store_h=0, band=band, shape=20),      # 256 columns x 4 row buffers: the default
+               mk(1, store_h=1, band=band, shape=20),
+               mk(1, store_h=1, band=band, shape=23),      # 128 columns x 8 row buffers
+               mk(1, store_h=0, band=band, shape=23),
+               mk(1, store_h=1, band=band, shape=24),      # 256 columns x 3
+               mk(1, store_h=0, band=band, shape=21),      # 256 columns x 6
+               mk(1, store_h=0, band=band, shape=22)]      # 512 columns x 3
+    run_and_compare(L, kind, engines, state, steps)
+
+
+@pytest.mark.parametrize("kind", [2, 3])
+@pytest.mark.parametrize("npx,npy,band", CASES)
+def test_lean_one_pass_is_bit_identical_to_lean_two_kernel_step(plugin_lib, npx, npy, band, kind):
+    """The tolerance form: cells of the frame-free rectangle advance B / D directly, in two
+    kernels (upml_kernels.cu) or in one pass -- same expressions, same bits; M / J of those cells
+    are touched by neither."""
+    L = plugin_lib
+    steps = 6
+    L.models_setModel(B.MODELS["NO_MODEL"])
+    L.field_init(B.FieldInfo(npx * 10, npy * 10, 10, 10, 500, 30, steps))
+    eps, state = random_case(npx, npy, kind)
+    mk = lambda *a, **kw: make_engine(L, npx, npy, steps, eps, *a, kind=kind, lean=1, **kw)
+    engines = [mk(0, store_h=1), mk(0, store_h=0),
+               mk(1, store_h=0, band=band, shape=20), mk(1, store_h=1, band=band, shape=20),
+               mk(1, store_h=0, band=band, shape=23), mk(1, store_h=1, band=band, shape=21),
+               mk(1, store_h=0, band=band, shape=22)]
+    assert engines[0].step_form() == 2 and engines[2].step_form() == 4
+    run_and_compare(L, kind, engines, state, steps)
 
 
 def test_launches_per_step(plugin_lib, in_tmp_cwd, monkeypatch):
@@ -121,7 +160,8 @@ def test_constant_division_shortcut_is_exactly_ieee(plugin_lib, divisor):
     assert bad.value == 0
 
 
-def test_one_pass_step_is_the_default_on_large_grids(plugin_lib, in_tmp_cwd, monkeypatch):
+@pytest.mark.parametrize("solver", ["TM_UPML_2D", "TE_UPML_2D"])
+def test_one_pass_step_is_the_default_on_large_grids(plugin_lib, in_tmp_cwd, monkeypatch, solver):
     """auto (default): grids of >= 2^22 updated cells take the TMA-staged one-pass step -- through
     b200fdtd_step and through the plugin's deferred multi-step replay (device clock, CUDA graph) --
     and produce the bits of the two-kernel step on all nine arrays and the NTFF history."""
@@ -129,7 +169,7 @@ def test_one_pass_step_is_the_default_on_large_grids(plugin_lib, in_tmp_cwd, mon
     res = {}
     for mode in ("2", "0"):
         monkeypatch.setenv("B200FDTD_FUSED", mode)
-        gpu = B.Plugin("MIE_CYLINDER", "TM_UPML_2D", npx, npy, steps=steps, h_u_nm=10, angle_deg=20)
+        gpu = B.Plugin("MIE_CYLINDER", solver, npx, npy, steps=steps, h_u_nm=10, angle_deg=20)
         form = C.c_int32(-1)
         B.check(gpu.L.b200fdtd_get_step_form(gpu.engine_handle(), C.byref(form)), "get_step_form")
         assert form.value == (3 if mode == "2" else 1)
@@ -145,7 +185,7 @@ def test_one_pass_step_is_the_default_on_large_grids(plugin_lib, in_tmp_cwd, mon
         assert bit_equal(a, b), n
     # small grids keep one kernel per phase
     monkeypatch.setenv("B200FDTD_FUSED", "2")
-    small = B.Plugin("MIE_CYLINDER", "TM_UPML_2D", 256, 256, steps=8, h_u_nm=10)
+    small = B.Plugin("MIE_CYLINDER", solver, 256, 256, steps=8, h_u_nm=10)
     B.check(small.L.b200fdtd_get_step_form(small.engine_handle(), C.byref(form)), "get_step_form")
     assert form.value == 0
     small.finish()

@@ -1,5 +1,5 @@
-"""Multi-GPU y-slab run under torchrun (NCCL halos + NTFF reduce) == single-GPU run.
-Needs >= 2 GPUs; skipped on a one-GPU box (the same data path is covered there by
+"""Multi-GPU y-slab run under torchrun (peer or NCCL halos + NTFF reduce) == single-GPU run, all
+nine arrays bit for bit.  Needs >= 2 GPUs (4 for the middle-rank cases); skipped on a one-GPU box (the same data path is covered there by
 test_gpu_parity.py::test_slab_split_equals_single_engine with device-buffer halos)."""
 import os
 import subprocess
@@ -16,15 +16,22 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     ("TE_UPML_2D", "nccl", "f64", "exact"), ("TE_UPML_2D", "peer", "f64", "exact"),
     ("TM_UPML_2D", "peer", "f32", "exact"), ("TE_UPML_2D", "nccl", "f32", "exact"),
     ("TM_UPML_2D", "peer", "f64", "unit"), ("TE_UPML_2D", "nccl", "f64", "unit"),
-    ("TM_UPML_2D", "peer", "f64", "fused"),
+    ("TM_UPML_2D", "peer", "f64", "fused"), ("TE_UPML_2D", "peer", "f64", "fused"),
+    ("TM_UPML_2D", "peer", "f64", "leanfused"), ("TE_UPML_2D", "peer", "f64", "leanfused"),
     ("TM_UPML_2D", "peer", "f64", "lean"), ("TE_UPML_2D", "peer", "f64", "lean"), ("TM_UPML_2D", "nccl", "f64", "lean")])
-def test_two_rank_run_matches_single_gpu(solver, halo, precision, form):
+@pytest.mark.parametrize("nproc", [2, 4])
+def test_multi_rank_run_matches_single_gpu(solver, halo, precision, form, nproc):
+    """nproc = 4: ranks 1 and 2 have BOTH neighbours attached (the protocol a middle rank of the
+    8-GPU run executes).  Skipped where the box has fewer GPUs; the same protocol runs on one GPU in
+    tests/test_gpu_peer_local.py."""
     import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+    if torch.cuda.device_count() < nproc:
+        pytest.skip("needs %d GPUs" % nproc)
+    if nproc == 4 and (precision == "f32" or (halo == "nccl" and form != "exact")):
+        pytest.skip("4-rank runs cover the f64 peer forms and the exact NCCL form")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc),
            "--master-addr", "127.0.0.1", "--master-port", "29517",
-           os.path.join(ROOT, "scripts", "multi_gpu_check.py"), solver, "128", "200", "420", halo, precision, form]
+           os.path.join(ROOT, "scripts", "multi_gpu_check.py"), solver, "128", "260", "420", halo, precision, form]
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
-    assert "MULTI_GPU_CHECK %s OK" % halo in p.stdout
+    assert "MULTI_GPU_CHECK %s world %d OK" % (halo, nproc) in p.stdout

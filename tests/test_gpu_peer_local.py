@@ -1,0 +1,24 @@
+"""The peer-halo protocol (direct stores into the neighbours' ghost columns + device flags) with
+3 and 4 slabs inside ONE process, on whatever GPUs the box has -- one is enough.  A middle slab
+runs exactly what ranks 1..N-2 of an 8-GPU run do (wait-up, edge kernel, signal-up, wait-down,
+pass, sample, signal-down; engine.cu b200fdtd_step).  Replaces mpiTM_UPML.c:252-334 halos."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("solver,world,form", [
+    ("TM_UPML_2D", 3, "exact"), ("TE_UPML_2D", 4, "exact"),
+    ("TM_UPML_2D", 4, "fused"), ("TE_UPML_2D", 4, "fused"), ("TM_UPML_2D", 3, "unit"), ("TE_UPML_2D", 3, "unit"),
+    ("TM_UPML_2D", 4, "lean"), ("TM_UPML_2D", 4, "leanfused"), ("TE_UPML_2D", 3, "leanfused")])
+def test_slabs_with_peer_halos_match_single_engine(solver, world, form):
+    cmd = [sys.executable, os.path.join(ROOT, "scripts", "peer_local_check.py"), solver, "128", "260", "420",
+           str(world), form, "spread"]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
+    assert "PEER_LOCAL_CHECK %s %s world %d spread OK" % (solver, form, world) in p.stdout
