@@ -225,6 +225,19 @@ extern void mpifdtd_setAngleBatch(const int *angles_deg, int n);
 extern void mpifdtd_selectAngle(int index);
 extern int mpifdtd_runAngleSweep(FieldInfo field_info, int start_deg, int end_deg, int delta_deg, int max_batch);
 
+/* ---- multi-GPU mode of the serial UPML solvers, host code staying C (extension; replaces
+ * init_mpi + the per-step halo Sendrecv of mpiTM_UPML.c:196-217,252-334,718-748) ---------------
+ * mpifdtd_setDevices(n): the next init() of solver ids 2 / 3 cuts the grid into n y-slabs, one
+ * engine per slab, slab g on CUDA device g modulo the visible devices; one process, one host
+ * thread; halos are direct NVLink peer stores ordered by device flags; reset()/finish() sum the
+ * slabs' NTFF partial sums and write the same files; getters gather the slabs.  n <= 1: one
+ * engine (default).  Environment MPIFDTD_DEVICES=n does the same for an unmodified main.c.
+ * mpifdtd_upml_slab_count / _slab_engine: how many slabs the active solver (kind 2 / 3) runs and
+ * the engine handle of slab g (harness use: device timers, digests). */
+extern void mpifdtd_setDevices(int n);
+extern int mpifdtd_upml_slab_count(int kind);
+extern struct b200fdtd_engine *mpifdtd_upml_slab_engine(int kind, int g);
+
 /* ---- config.txt (parser.h:5, configSample.txt:6-22, main.c:319-366) ------ */
 extern bool parser_nextLine(FILE *fp, char buf[]);            /* parser.c:3 */
 typedef struct MpifdtdConfig {

@@ -252,6 +252,24 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
       "bra WAIT_%=;\n\t"
       "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+// A consumer warp hands a ring slot back.  Its ld.shared reads of the slot are GENERIC-proxy
+// accesses, the refill is an ASYNC-proxy write (cp.async.bulk), and nothing in `ld.shared ...;
+// mbarrier.arrive` makes the arrive wait for the loads: ptxas issues SYNCS.ARRIVE right behind the
+// last LDS without a scoreboard wait.  When this warp's arrival is the one that completes the
+// phase, the producer refills at once and its first bulk copy can land in the array the warp
+// loaded last while that load is still in flight.  Observed exactly so (profiles/r02_onepass_race.md):
+// 16/32-byte-granular chunks of the NEXT refill's Ez in the columns of the slowest warp -- the
+// frame-strip warp next to unit-coefficient warps --, 64 of 150 fresh-engine runs of the 16-warp x
+// 3-buffer shape, and the one-off mismatch of round 1.  The cross-proxy fence (SASS: MEMBAR.ALL.CTA
+// + FENCE.VIEW.ASYNC.S) makes every lane's loads complete first; the warp barrier orders the lanes;
+// one lane arrives.  0 of 350 runs since.  (Forcing completion with a register dependency -- an
+// st.shared of a fold of everything loaded -- cures it too, but measured 1-3 % slower.)
+__device__ __forceinline__ void release_slot(unsigned long long *empty_bar, int lane)
+{
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncwarp();
+  if (lane == 0) mbar_arrive(empty_bar);
+}
 __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, unsigned bytes, unsigned long long *bar)
 {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -426,8 +444,7 @@ __global__ void __launch_bounds__(32 * (WARPS + 1), 1) tm_onepass_kernel(const _
       ez_nb_nxt = st.ez[t - 1]; l_bx = st.bx[t - 1];
       if (!lean_tile) l_mx = st.mx[t - 1];
     }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&empty[s]);                // the slot may be refilled
+    release_slot(&empty[s], lane);                        // the slot may be refilled
     if (++s == STAGES) { s = 0; ph ^= 1u; }
 
     double2 ez_right = shfl_down1(ez_cur);                // old Ez(r, c+1)
@@ -642,8 +659,7 @@ __global__ void __launch_bounds__(32 * (WARPS + 1), 1) te_onepass_kernel(const _
       l_ey_below = st.ey[t - 1]; l_ex = st.ex[t - 1]; l_bz = st.bz[t - 1];
       if (!lean_tile) l_mz = st.mz[t - 1];
     }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&empty[s]);
+    release_slot(&empty[s], lane);
     if (++s == STAGES) { s = 0; ph ^= 1u; }
 
     double2 ex_right = shfl_down1(ex_old);                // old Ex(r, c+1)

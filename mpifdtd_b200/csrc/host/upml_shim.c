@@ -33,10 +33,13 @@
 #define N_ANGLES 360
 
 #define MPIFDTD_MAX_ANGLE_BATCH 4096
+#define MPIFDTD_MAX_SLABS 16
 
 typedef struct UpmlSolver {
   int kind;                       /* B200FDTD_TM_UPML or B200FDTD_TE_UPML          */
-  b200fdtd_engine *engine;
+  b200fdtd_engine *engine;        /* slab 0: the whole grid unless n_slabs > 1      */
+  b200fdtd_engine *slab[MPIFDTD_MAX_SLABS];   /* y-slabs, one engine each (slab[0] == engine) */
+  int n_slabs;
   double *eps[3];                 /* host maps: TM EZ,HX,HY (HX/HY lazily) | TE EX,EY,HZ */
   dcomplex *mirror[3];            /* pinned mirrors for the X, Y, Z getters (lazy)  */
   size_t mirror_cells;
@@ -67,6 +70,7 @@ static int is_tm_kind(int kind)  { return kind == B200FDTD_TM_UPML || kind == B2
 static int point_source_requested;
 static int source_form_requested;      /* MPIFDTD_SRC_* */
 static int precision_requested;        /* B200FDTD_F64 / B200FDTD_F32 */
+static int slabs_requested;            /* y-slabs (GPUs) of the next init(), 0 = ask MPIFDTD_DEVICES, else 1 */
 static int batch_requested;            /* number of angles of the next init(), 0 = unbatched */
 static int batch_angles_requested[MPIFDTD_MAX_ANGLE_BATCH];
 
@@ -122,6 +126,45 @@ void mpifdtd_setPrecision(int precision)
     exit(2);
   }
   precision_requested = precision;
+}
+
+/* Multi-GPU mode of the serial UPML solvers (ids 2, 3), host code staying C: the next init()
+ * cuts the grid into n y-slabs, one engine per slab, slab g on CUDA device g modulo the number
+ * of visible devices (so a one-GPU box can still run -- and test -- several slabs).  ONE process,
+ * ONE host thread: update() issues the step on every engine, the slabs exchange their one-column
+ * halos as direct stores into the neighbour's ghost columns over NVLink (CUDA peer access) and
+ * order themselves with device-side flags; reset()/finish() sum the slabs' NTFF partial sums
+ * onto slab 0 and write the files; the getters gather the slabs into the [N_PX][N_PY] mirror.
+ * Replaces init_mpi + Connection_ISend_IRecvH/E of the MPI solvers (mpiTM_UPML.c:196-217,
+ * 252-334, 718-748) and adds the far-field reduce they never do.
+ * n <= 1 (default): one engine.  Environment MPIFDTD_DEVICES=n does the same for an unmodified
+ * main.c.  Not combined with an angle batch (a batch already fills the GPU). */
+void mpifdtd_setDevices(int n)
+{
+  if (n < 0 || n > MPIFDTD_MAX_SLABS) {
+    printf("mpifdtd_setDevices: %d slabs (max %d)\n", n, MPIFDTD_MAX_SLABS);
+    exit(2);
+  }
+  slabs_requested = n;
+}
+
+static int slabs_for_next_init(void)
+{
+  int n = slabs_requested;
+  if (n == 0) {
+    const char *v = getenv("MPIFDTD_DEVICES");
+    if (v != NULL) n = atoi(v);
+  }
+  if (n > MPIFDTD_MAX_SLABS) n = MPIFDTD_MAX_SLABS;
+  return n > 1 ? n : 1;
+}
+
+/* contiguous, near-equal column ranges; the first slabs take the remainder (slab.py agrees) */
+static void slab_columns(int n_py, int n_slabs, int g, int *j0, int *nj)
+{
+  const int base = n_py / n_slabs, extra = n_py % n_slabs;
+  *j0 = g * base + (g < extra ? g : extra);
+  *nj = base + (g < extra ? 1 : 0);
 }
 
 /* Angle batch.  The reference sweeps incidence angles one simulation at a
@@ -288,6 +331,9 @@ static void solver_init(UpmlSolver *s)
     s->n_batch = batch_requested;
     memcpy(s->batch_angles, batch_angles_requested, sizeof(int) * (size_t)batch_requested);
   }
+  s->n_slabs = (mpi || s->n_batch > 1) ? 1 : slabs_for_next_init();
+  if (s->n_slabs > g.N_PY / 4) s->n_slabs = g.N_PY / 4 > 0 ? g.N_PY / 4 : 1;
+  if (s->n_slabs > 1) s->defer = 0;     /* multi-step replay is a single-engine feature */
 
   b200fdtd_grid grid;
   memset(&grid, 0, sizeof grid);
@@ -305,7 +351,21 @@ static void solver_init(UpmlSolver *s)
   grid.mu0 = MU_0_S;
   grid.n_batch = s->n_batch;
   double t_lap = now_s();
-  die_on(b200fdtd_create(&grid, &s->engine), "b200fdtd_create");
+  int n_dev = 1;
+  if (s->n_slabs > 1) die_on(b200fdtd_device_count(&n_dev), "b200fdtd_device_count");
+  for (int k = 0; k < s->n_slabs; k++) {
+    if (s->n_slabs > 1) {
+      int j0, nj;
+      slab_columns(g.N_PY, s->n_slabs, k, &j0, &nj);
+      grid.j0 = j0;  grid.nj = nj;  grid.device = k % n_dev;
+    }
+    die_on(b200fdtd_create(&grid, &s->slab[k]), "b200fdtd_create");
+  }
+  s->engine = s->slab[0];
+  for (int k = 0; k + 1 < s->n_slabs; k++) {        /* neighbours along y */
+    die_on(b200fdtd_peer_attach_engine(s->slab[k], 1, s->slab[k + 1]), "b200fdtd_peer_attach_engine");
+    die_on(b200fdtd_peer_attach_engine(s->slab[k + 1], 0, s->slab[k]), "b200fdtd_peer_attach_engine");
+  }
   lap("init: engine create", &t_lap);
   if (s->n_batch > 1) {
     b200fdtd_batch_source *src = (b200fdtd_batch_source *)malloc(sizeof *src * (size_t)s->n_batch);
@@ -328,14 +388,16 @@ static void solver_init(UpmlSolver *s)
     mpifdtd_fill_eps(s->eps[1], 0, 0.5, D_X);
   }
   lap("init: eps maps (host)", &t_lap);
-  for (int m = 0; m < n_eps; m++)
-    die_on(b200fdtd_set_eps(s->engine, m, s->eps[m]), "b200fdtd_set_eps");
+  for (int k = 0; k < s->n_slabs; k++)
+    for (int m = 0; m < n_eps; m++)
+      die_on(b200fdtd_set_eps(s->slab[k], m, s->eps[m]), "b200fdtd_set_eps");     /* each engine takes its columns */
   lap("init: eps upload", &t_lap);
 
   double *ti = (double *)malloc(sizeof(double) * B200FDTD_UPML_TABS * g.N_PX);
   double *tj = (double *)malloc(sizeof(double) * B200FDTD_UPML_TABS * g.N_PY);
   build_tables(s, ti, tj);
-  die_on(b200fdtd_set_upml_tables(s->engine, ti, tj), "b200fdtd_set_upml_tables");
+  for (int k = 0; k < s->n_slabs; k++)
+    die_on(b200fdtd_set_upml_tables(s->slab[k], ti, tj), "b200fdtd_set_upml_tables");
   free(ti); free(tj);
 
   s->mirror_cells = sub_cells;          /* the pinned mirrors are allocated by the first getter call */
@@ -381,13 +443,17 @@ static void solver_init(UpmlSolver *s)
   plan.n_angles = N_ANGLES;
   plan.array_size = box.arraySize;
   lap("init: tables", &t_lap);
-  double *shift = mpifdtd_ntff_time_shift(&box, N_ANGLES, tm ? 0.0 : 0.5, 0, g.N_PY);
-  plan.time_shift = shift;
-  lap("init: ntff time shifts", &t_lap);
-  if (plan.n_points > 0 && plan.max_time > 0)
-    die_on(b200fdtd_set_ntff_plan(s->engine, &plan), "b200fdtd_set_ntff_plan");
-  free(shift);
-  lap("init: ntff plan upload", &t_lap);
+  for (int k = 0; k < s->n_slabs; k++) {            /* each slab samples the surface points it owns */
+    int j0 = 0, nj = g.N_PY;
+    if (s->n_slabs > 1) slab_columns(g.N_PY, s->n_slabs, k, &j0, &nj);
+    plan.n_local = mpifdtd_ntff_local_count(&box, j0, nj);
+    double *shift = mpifdtd_ntff_time_shift(&box, N_ANGLES, tm ? 0.0 : 0.5, j0, nj);
+    plan.time_shift = shift;
+    if (plan.n_points > 0 && plan.max_time > 0)
+      die_on(b200fdtd_set_ntff_plan(s->slab[k], &plan), "b200fdtd_set_ntff_plan");
+    free(shift);
+  }
+  lap("init: ntff plans", &t_lap);
 }
 
 /* ---- update ------------------------------------------------------------------ */
@@ -542,7 +608,10 @@ static void solver_update(UpmlSolver *s)
   }
   b200fdtd_step_args a;
   mpifdtd_upml_step_args_form(s->kind, s->point_source, s->source_form, &a);
-  die_on(b200fdtd_step(s->engine, &a), "b200fdtd_step");
+  /* asynchronous launches: with several slabs the engines order themselves across GPUs through
+   * the peer-halo flags, the host never waits */
+  for (int k = 0; k < s->n_slabs; k++)
+    die_on(b200fdtd_step(s->slab[k], &a), "b200fdtd_step");
 }
 
 /* ---- reset / finish ------------------------------------------------------------ */
@@ -591,13 +660,18 @@ static void write_far_field(UpmlSolver *s)
   const int n = s->n_batch > 1 ? s->n_batch : 1;
   flush_pending(s);
   double t_lap = now_s(), t_gpu = 0, t_txt = 0, t_bin = 0;
-  die_on(b200fdtd_sync(s->engine), "b200fdtd_sync");
+  for (int k = 0; k < s->n_slabs; k++) die_on(b200fdtd_sync(s->slab[k]), "b200fdtd_sync");
   lap("finish: drain the stepping", &t_lap);
+  if (s->n_slabs > 1) {                 /* partial sums of the slabs -> slab 0, in slab order */
+    for (int k = 0; k < s->n_slabs; k++) die_on(b200fdtd_ntff_project(s->slab[k]), "b200fdtd_ntff_project");
+    for (int k = 1; k < s->n_slabs; k++) die_on(b200fdtd_ntff_add_uw(s->slab[0], s->slab[k]), "b200fdtd_ntff_add_uw");
+    lap("finish: ntff projection + sum over slabs", &t_lap);
+  }
   for (int k = 0; k < n; k++) {
     const int angle = s->n_batch > 1 ? s->batch_angles[k] : (int)field_getWaveAngle();
     if (s->n_batch > 1) die_on(b200fdtd_select_batch(s->engine, k), "b200fdtd_select_batch");
     double t0 = now_s();
-    mpifdtd_upml_far_field(s->engine, s->kind, k == 0, table);
+    mpifdtd_upml_far_field(s->engine, s->kind, k == 0 && s->n_slabs == 1, table);
     double t1 = now_s();
     sprintf(name, "%d[deg].txt", angle);
     ntff_outputEnormTxt(by_row, name);
@@ -714,7 +788,9 @@ static void solver_reset(UpmlSolver *s)
   flush_pending(s);
   if (!is_mpi_kind(s->kind))                        /* mpiTM_UPML.c:219-232: reset only zeroes */
     write_far_field(s);
-  die_on(b200fdtd_zero_state(s->engine), "b200fdtd_zero_state");
+  /* nobody may be in mid-step while a neighbour's flags are zeroed */
+  for (int k = 0; k < s->n_slabs; k++) die_on(b200fdtd_sync(s->slab[k]), "b200fdtd_sync");
+  for (int k = 0; k < s->n_slabs; k++) die_on(b200fdtd_zero_state(s->slab[k]), "b200fdtd_zero_state");
 }
 
 static void solver_finish(UpmlSolver *s)
@@ -724,8 +800,12 @@ static void solver_finish(UpmlSolver *s)
    * call is commented out (mpiTM_UPML.c:240), so id 4 writes nothing */
   if (s->kind == B200FDTD_MPI_TE_UPML) write_mpi_te_far_field();
   solver_reset(s);
-  die_on(b200fdtd_destroy(s->engine), "b200fdtd_destroy");
+  for (int k = 0; k < s->n_slabs; k++) {
+    die_on(b200fdtd_destroy(s->slab[k]), "b200fdtd_destroy");
+    s->slab[k] = NULL;
+  }
   s->engine = NULL;
+  s->n_slabs = 0;
   free(s->eps_ringed); s->eps_ringed = NULL;
   for (int m = 0; m < 3; m++) {
     b200fdtd_host_free(s->eps[m]);    s->eps[m] = NULL;
@@ -745,7 +825,8 @@ static dcomplex *solver_field(UpmlSolver *s, int mirror, int slot)
     die_on(b200fdtd_get_field_ld(s->engine, slot, first, g.N_PY + 2), "b200fdtd_get_field_ld");
     return s->mirror[mirror];
   }
-  die_on(b200fdtd_get_field(s->engine, slot, (double *)s->mirror[mirror]), "b200fdtd_get_field");
+  for (int k = 0; k < s->n_slabs; k++)               /* every slab lands in its own columns of the mirror */
+    die_on(b200fdtd_get_field(s->slab[k], slot, (double *)s->mirror[mirror]), "b200fdtd_get_field");
   return s->mirror[mirror];
 }
 
@@ -815,6 +896,19 @@ int mpi_fdtdTE_upml_getSubNcell(void) { return (N_PX + 2) * (N_PY + 2); }
 
 /* engine handle of the active serial UPML solver, for harnesses that want device
  * timers or the U/W arrays (not part of the reference surface) */
+/* slab g of the active serial UPML solver (NULL past the end), and how many there are */
+b200fdtd_engine *mpifdtd_upml_slab_engine(int kind, int g)
+{
+  UpmlSolver *s = kind == B200FDTD_TM_UPML ? &tm_solver : kind == B200FDTD_TE_UPML ? &te_solver : NULL;
+  if (s == NULL || g < 0 || g >= s->n_slabs) return NULL;
+  flush_pending(s);
+  return s->slab[g];
+}
+int mpifdtd_upml_slab_count(int kind)
+{
+  return kind == B200FDTD_TM_UPML ? tm_solver.n_slabs : kind == B200FDTD_TE_UPML ? te_solver.n_slabs : 0;
+}
+
 b200fdtd_engine *mpifdtd_upml_engine(int kind)
 {
   switch (kind) {                          /* whoever takes the handle sees every update() so far */
