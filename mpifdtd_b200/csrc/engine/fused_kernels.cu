@@ -320,63 +320,33 @@ __device__ __forceinline__ Tile make_tile(const OnePassView &f)
 }
 
 // =========================================================================================== TM =====
-template <bool LEAN, bool STORE_H, int WARPS, int STAGES>
-__global__ void __launch_bounds__(32 * (WARPS + 1), 1) tm_onepass_kernel(const __grid_constant__ OnePassView f)
+// The consumer side of the TM kernel, compiled three times (MODE): the hot loops -- a warp tile inside
+// the frame-free rectangle in the exact form (ROW_UNIT), a CTA tile inside it in the lean form
+// (ROW_LEAN) -- carry none of the frame's table reads, quotients and per-cell case distinctions;
+// everything else (frame and mixed tiles) runs ROW_GENERAL.  Same expressions, same bits.
+enum { ROW_GENERAL = 0, ROW_UNIT = 1, ROW_LEAN = 2 };
+
+// rare work of the hot loops, out of line: material cells (division by eps, the pulse's exp / sincos)
+// and the opt-in point source
+static __device__ __noinline__ double2 tm_material_cell(const UpmlView *v, int r, int c, size_t k, double eps, double2 dz)
 {
-  constexpr int W = 32 * WARPS;
-  extern __shared__ __align__(128) unsigned char op_smem[];
-  TmRow<W> *ring = reinterpret_cast<TmRow<W> *>(op_smem);
-  double2 *ez_first = reinterpret_cast<double2 *>(op_smem + sizeof(TmRow<W>) * STAGES);   // Ez(r0, strip)
-  unsigned long long *full = reinterpret_cast<unsigned long long *>(ez_first + W);
-  unsigned long long *empty = full + STAGES;
-  unsigned long long *first_bar = empty + STAGES;
+  double2 ez = div_eps(dz, eps);
+  const b200fdtd_pulse pulse = onepass_pulse(*v, 0);
+  if (pulse.enabled && eps != 1.0) ez = ez + pulse_term(pulse, r - 1, v->j_base + c, eps);
+  if ((long long)k == v->point_k) ez = ez + make_double2(v->point_re, v->point_im);
+  return ez;
+}
 
+template <int MODE, bool LEAN, bool STORE_H, int W, int STAGES>
+__device__ __forceinline__ void tm_consume(const OnePassView &f, const Tile &T, TmRow<W> *ring, const double2 *ez_first,
+                                           unsigned long long *full, unsigned long long *empty,
+                                           unsigned long long *first_bar)
+{
+  constexpr bool lean_tile = MODE == ROW_LEAN;
+  constexpr bool unit = MODE == ROW_UNIT;
   const UpmlView &v = f.u;
-  const Tile T = make_tile<LEAN, WARPS>(f);
   const int lane = T.lane, warp = T.warp, c0 = T.c0, r0 = T.r0, r1 = T.r1, wcopy = T.wcopy;
-  const bool lean_tile = T.lean_tile;
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], (unsigned)T.live_warps); }
-    mbar_init(first_bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-
   double2 *Ez = v.f[B200FDTD_TM_EZ];
-  if (warp == WARPS) {
-    // ---- producer: one lane streams the band, STAGES rows ahead of the slowest consumer ----
-    if (lane != 0) return;
-    const unsigned seg = (unsigned)(wcopy * sizeof(double2));
-    const unsigned tx = (lean_tile ? 4u : 7u) * seg + (unsigned)(T.n_eps * sizeof(double));
-    const double2 *row_e_next = f.row_e + (size_t)(blockIdx.y + 1) * v.pitch;
-    // the band's first Ez row: nobody has written it yet (only this CTA's consumers will, and they
-    // wait for this copy), so every consumer sees the OLD values of its own and its neighbours' cells
-    mbar_expect_tx(first_bar, seg);
-    bulk_g2s(ez_first, &Ez[(size_t)r0 * v.pitch + c0], seg, first_bar);
-    int s = 0; unsigned ph = 0;
-    for (int r = r0; r < r1; r++) {
-      if (r - r0 >= STAGES) mbar_wait(&empty[s], ph ^ 1u);   // every consumer has handed the slot back
-      TmRow<W> &st = ring[s];
-      const size_t k = (size_t)r * v.pitch + c0;
-      mbar_expect_tx(&full[s], tx);
-      bulk_g2s(st.ez, (r + 1 < r1) ? &Ez[k + v.pitch] : &row_e_next[c0], seg, &full[s]);
-      bulk_g2s(st.bx, &v.f[B200FDTD_TM_BX][k], seg, &full[s]);
-      bulk_g2s(st.by, &v.f[B200FDTD_TM_BY][k], seg, &full[s]);
-      bulk_g2s(st.dz, &v.f[B200FDTD_TM_DZ][k], seg, &full[s]);
-      if (!lean_tile) {
-        bulk_g2s(st.mx, &v.f[B200FDTD_TM_MX][k], seg, &full[s]);
-        bulk_g2s(st.my, &v.f[B200FDTD_TM_MY][k], seg, &full[s]);
-        bulk_g2s(st.jz, &v.f[B200FDTD_TM_JZ][k], seg, &full[s]);
-      }
-      bulk_g2s(st.eps, &v.eps0[k - T.eps_off], (unsigned)(T.n_eps * sizeof(double)), &full[s]);
-      if (++s == STAGES) { s = 0; ph ^= 1u; }
-    }
-    return;
-  }
-
-  // ---- consumers ------------------------------------------------------------------------
-  if (warp >= T.live_warps) return;
   const int t = 32 * warp + lane;
   const int c = c0 + t;
   const bool active = c <= v.c_hi;
@@ -388,9 +358,6 @@ __global__ void __launch_bounds__(32 * (WARPS + 1), 1) tm_onepass_kernel(const _
   const bool first_strip = blockIdx.x == 0, first_band = blockIdx.y == 0;
   const double2 *col_e_next = f.col_e + (size_t)(blockIdx.x + 1) * v.rows;   // old Ez(r, c0 + W)
   const double2 *col_b_mine = f.col_b + (size_t)blockIdx.x * v.rows;         // new Bx(r, c0 - 1)
-  // exact form: this warp's tile inside the frame-free rectangle -> unit-coefficient expressions
-  const bool unit = !LEAN && r0 >= f.in_r_lo && r1 - 1 <= f.in_r_hi && c0 + 32 * warp >= f.in_c_lo &&
-                    c0 + 32 * warp + 31 <= f.in_c_hi;
   // lean form: which of this lane's / its left neighbour's cells advance B and D directly
   const bool col_in = LEAN && c >= f.in_c_lo && c <= f.in_c_hi;
   const bool left_col_in = LEAN && c - 1 >= f.in_c_lo && c - 1 <= f.in_c_hi;
@@ -401,7 +368,8 @@ __global__ void __launch_bounds__(32 * (WARPS + 1), 1) tm_onepass_kernel(const _
     c_dzjz = v.tj[B200FDTD_TMJ_C_DZJZ * v.pitch + c];
   }
 
-  const b200fdtd_pulse pulse = onepass_pulse(v, 0);
+  b200fdtd_pulse pulse;
+  if (MODE == ROW_GENERAL) pulse = onepass_pulse(v, 0);
   size_t k = (size_t)r0 * v.pitch + c;
   // new B of the previous row (by_prev) and, for exact cells, its quotient by mu0 (hy_prev)
   double2 by_prev = zero, hy_prev = zero;
@@ -486,6 +454,10 @@ __global__ void __launch_bounds__(32 * (WARPS + 1), 1) tm_onepass_kernel(const _
       // fdtdTM_upml.c:188-189 for cell (r, c-1), as its owner evaluates them
       double2 m_unused;
       if (LEAN && (lean_tile || (row_in && left_col_in))) bx_left = l_bx - (ez_cur - ez_nb);
+      else if (unit && c - 1 >= f.in_c_lo) {              // the neighbour is a unit-coefficient cell too
+        const double2 l_m = l_mx - (ez_cur - ez_nb);
+        bx_left = (l_bx + l_m) - l_mx;
+      }
       else bx_left = tm_bx_full(v, r, c - 1, ez_nb, ez_cur, l_mx, l_bx, &m_unused);
       if (!lean_tile) hx_left = div_const(bx_left, v.mu0);
     }
@@ -504,11 +476,16 @@ __global__ void __launch_bounds__(32 * (WARPS + 1), 1) tm_onepass_kernel(const _
         jz = c_jz * jz_old + c_jzh * (((hy - hy_prev) - hx) + hx_left);
         dz = (c_dz * dz_old + c_dzjz * jz) - c_dzjz * jz_old;
       }
-      double2 ez = div_eps(dz, eps);
-      if (pulse.enabled && eps != 1.0)
-        ez = ez + pulse_term(pulse, r - 1, v.j_base + c, eps);
-      if ((long long)k == v.point_k)
-        ez = ez + make_double2(v.point_re, v.point_im);
+      double2 ez = dz;
+      if (MODE == ROW_GENERAL) {
+        ez = div_eps(dz, eps);
+        if (pulse.enabled && eps != 1.0)
+          ez = ez + pulse_term(pulse, r - 1, v.j_base + c, eps);
+        if ((long long)k == v.point_k)
+          ez = ez + make_double2(v.point_re, v.point_im);
+      } else if (eps != 1.0 || (long long)k == v.point_k) {
+        ez = tm_material_cell(&v, r, c, k, eps, dz);
+      }
       if (!(LEAN && lean_cell)) {
         v.f[B200FDTD_TM_MX][k] = mx;
         v.f[B200FDTD_TM_MY][k] = my;
@@ -535,18 +512,15 @@ __global__ void __launch_bounds__(32 * (WARPS + 1), 1) tm_onepass_kernel(const _
   }
 }
 
-// =========================================================================================== TE =====
-// slots: 0 Ex 1 Jx 2 Dx 3 Ey 4 Jy 5 Dy 6 Hz 7 Mz 8 Bz.  Hz(i,j) needs Ey(i+1,j) (next row: carried like
-// TM's Ez) and Ex(i,j+1) (right lane: staged per row); Ex(i,j) needs the new Hz(i,j-1) (left lane),
-// Ey(i,j) the new Hz(i-1,j) (previous row, carried).  fdtdTE_upml.c:252-314.
+
 template <bool LEAN, bool STORE_H, int WARPS, int STAGES>
-__global__ void __launch_bounds__(32 * (WARPS + 1), 1) te_onepass_kernel(const __grid_constant__ OnePassView f)
+__global__ void __launch_bounds__(32 * (WARPS + 1), 1) tm_onepass_kernel(const __grid_constant__ OnePassView f)
 {
   constexpr int W = 32 * WARPS;
   extern __shared__ __align__(128) unsigned char op_smem[];
-  TeRow<W> *ring = reinterpret_cast<TeRow<W> *>(op_smem);
-  double2 *ey_first = reinterpret_cast<double2 *>(op_smem + sizeof(TeRow<W>) * STAGES);   // Ey(r0, strip)
-  unsigned long long *full = reinterpret_cast<unsigned long long *>(ey_first + W);
+  TmRow<W> *ring = reinterpret_cast<TmRow<W> *>(op_smem);
+  double2 *ez_first = reinterpret_cast<double2 *>(op_smem + sizeof(TmRow<W>) * STAGES);   // Ez(r0, strip)
+  unsigned long long *full = reinterpret_cast<unsigned long long *>(ez_first + W);
   unsigned long long *empty = full + STAGES;
   unsigned long long *first_bar = empty + STAGES;
 
@@ -562,39 +536,79 @@ __global__ void __launch_bounds__(32 * (WARPS + 1), 1) te_onepass_kernel(const _
   }
   __syncthreads();
 
-  double2 *Ex = v.f[B200FDTD_TE_EX], *Ey = v.f[B200FDTD_TE_EY];
+  double2 *Ez = v.f[B200FDTD_TM_EZ];
   if (warp == WARPS) {
+    // ---- producer: one lane streams the band, STAGES rows ahead of the slowest consumer ----
     if (lane != 0) return;
     const unsigned seg = (unsigned)(wcopy * sizeof(double2));
-    const unsigned eps_bytes = (unsigned)(T.n_eps * sizeof(double));
-    const unsigned tx = (lean_tile ? 5u : 8u) * seg + 2u * eps_bytes;
+    const unsigned tx = (lean_tile ? 4u : 7u) * seg + (unsigned)(T.n_eps * sizeof(double));
     const double2 *row_e_next = f.row_e + (size_t)(blockIdx.y + 1) * v.pitch;
+    // the band's first Ez row: nobody has written it yet (only this CTA's consumers will, and they
+    // wait for this copy), so every consumer sees the OLD values of its own and its neighbours' cells
     mbar_expect_tx(first_bar, seg);
-    bulk_g2s(ey_first, &Ey[(size_t)r0 * v.pitch + c0], seg, first_bar);
+    bulk_g2s(ez_first, &Ez[(size_t)r0 * v.pitch + c0], seg, first_bar);
     int s = 0; unsigned ph = 0;
     for (int r = r0; r < r1; r++) {
-      if (r - r0 >= STAGES) mbar_wait(&empty[s], ph ^ 1u);
-      TeRow<W> &st = ring[s];
+      if (r - r0 >= STAGES) mbar_wait(&empty[s], ph ^ 1u);   // every consumer has handed the slot back
+      TmRow<W> &st = ring[s];
       const size_t k = (size_t)r * v.pitch + c0;
       mbar_expect_tx(&full[s], tx);
-      bulk_g2s(st.ey, (r + 1 < r1) ? &Ey[k + v.pitch] : &row_e_next[c0], seg, &full[s]);
-      bulk_g2s(st.ex, &Ex[k], seg, &full[s]);
-      bulk_g2s(st.bz, &v.f[B200FDTD_TE_BZ][k], seg, &full[s]);
-      bulk_g2s(st.dx, &v.f[B200FDTD_TE_DX][k], seg, &full[s]);
-      bulk_g2s(st.dy, &v.f[B200FDTD_TE_DY][k], seg, &full[s]);
+      bulk_g2s(st.ez, (r + 1 < r1) ? &Ez[k + v.pitch] : &row_e_next[c0], seg, &full[s]);
+      bulk_g2s(st.bx, &v.f[B200FDTD_TM_BX][k], seg, &full[s]);
+      bulk_g2s(st.by, &v.f[B200FDTD_TM_BY][k], seg, &full[s]);
+      bulk_g2s(st.dz, &v.f[B200FDTD_TM_DZ][k], seg, &full[s]);
       if (!lean_tile) {
-        bulk_g2s(st.mz, &v.f[B200FDTD_TE_MZ][k], seg, &full[s]);
-        bulk_g2s(st.jx, &v.f[B200FDTD_TE_JX][k], seg, &full[s]);
-        bulk_g2s(st.jy, &v.f[B200FDTD_TE_JY][k], seg, &full[s]);
+        bulk_g2s(st.mx, &v.f[B200FDTD_TM_MX][k], seg, &full[s]);
+        bulk_g2s(st.my, &v.f[B200FDTD_TM_MY][k], seg, &full[s]);
+        bulk_g2s(st.jz, &v.f[B200FDTD_TM_JZ][k], seg, &full[s]);
       }
-      bulk_g2s(st.epx, &v.eps0[k - T.eps_off], eps_bytes, &full[s]);
-      bulk_g2s(st.epy, &v.eps1[k - T.eps_off], eps_bytes, &full[s]);
+      bulk_g2s(st.eps, &v.eps0[k - T.eps_off], (unsigned)(T.n_eps * sizeof(double)), &full[s]);
       if (++s == STAGES) { s = 0; ph ^= 1u; }
     }
     return;
   }
 
+  // ---- consumers ------------------------------------------------------------------------
   if (warp >= T.live_warps) return;
+  if constexpr (LEAN) {
+    if (lean_tile) tm_consume<ROW_LEAN, true, STORE_H, W, STAGES>(f, T, ring, ez_first, full, empty, first_bar);
+    else           tm_consume<ROW_GENERAL, true, STORE_H, W, STAGES>(f, T, ring, ez_first, full, empty, first_bar);
+  } else {
+    // exact form: this warp's tile inside the frame-free rectangle -> unit-coefficient expressions
+    const bool unit = r0 >= f.in_r_lo && r1 - 1 <= f.in_r_hi && c0 + 32 * warp >= f.in_c_lo &&
+                      c0 + 32 * warp + 31 <= f.in_c_hi;
+    if (unit) tm_consume<ROW_UNIT, false, STORE_H, W, STAGES>(f, T, ring, ez_first, full, empty, first_bar);
+    else      tm_consume<ROW_GENERAL, false, STORE_H, W, STAGES>(f, T, ring, ez_first, full, empty, first_bar);
+  }
+}
+
+// =========================================================================================== TE =====
+// slots: 0 Ex 1 Jx 2 Dx 3 Ey 4 Jy 5 Dy 6 Hz 7 Mz 8 Bz.  Hz(i,j) needs Ey(i+1,j) (next row: carried like
+// TM's Ez) and Ex(i,j+1) (right lane: staged per row); Ex(i,j) needs the new Hz(i,j-1) (left lane),
+// Ey(i,j) the new Hz(i-1,j) (previous row, carried).  fdtdTE_upml.c:252-314.
+static __device__ __noinline__ void te_material_cell(const UpmlView *v, int r, int c, size_t k, double eps_x, double eps_y,
+                                                     double2 dx, double2 dy, double2 *ex_out, double2 *ey_out)
+{
+  double2 ex = div_eps(dx, eps_x), ey = div_eps(dy, eps_y);
+  const b200fdtd_pulse pulse_x = onepass_pulse(*v, 0), pulse_y = onepass_pulse(*v, 1);
+  if (pulse_x.enabled && eps_x != 1.0) ex = ex + pulse_term(pulse_x, r - 1, v->j_base + c, eps_x);
+  if (pulse_y.enabled && eps_y != 1.0) ey = ey + pulse_term(pulse_y, r - 1, v->j_base + c, eps_y);
+  if ((long long)k == v->point_k) ex = ex + make_double2(v->point_re, v->point_im);
+  *ex_out = ex;
+  *ey_out = ey;
+}
+
+// consumer side of the TE kernel, compiled per MODE like tm_consume
+template <int MODE, bool LEAN, bool STORE_H, int W, int STAGES>
+__device__ __forceinline__ void te_consume(const OnePassView &f, const Tile &T, TeRow<W> *ring, const double2 *ey_first,
+                                           unsigned long long *full, unsigned long long *empty,
+                                           unsigned long long *first_bar)
+{
+  constexpr bool lean_tile = MODE == ROW_LEAN;
+  constexpr bool unit = MODE == ROW_UNIT;
+  const UpmlView &v = f.u;
+  const int lane = T.lane, warp = T.warp, c0 = T.c0, r0 = T.r0, r1 = T.r1, wcopy = T.wcopy;
+  double2 *Ex = v.f[B200FDTD_TE_EX], *Ey = v.f[B200FDTD_TE_EY];
   const int t = 32 * warp + lane;
   const int c = c0 + t;
   const bool active = c <= v.c_hi;
@@ -604,8 +618,6 @@ __global__ void __launch_bounds__(32 * (WARPS + 1), 1) te_onepass_kernel(const _
   const bool first_strip = blockIdx.x == 0, first_band = blockIdx.y == 0;
   const double2 *col_e_next = f.col_e + (size_t)(blockIdx.x + 1) * v.rows;   // old Ex(r, c0 + W)
   const double2 *col_b_mine = f.col_b + (size_t)blockIdx.x * v.rows;         // new Bz(r, c0 - 1)
-  const bool unit = !LEAN && r0 >= f.in_r_lo && r1 - 1 <= f.in_r_hi && c0 + 32 * warp >= f.in_c_lo &&
-                    c0 + 32 * warp + 31 <= f.in_c_hi;
   const bool col_in = LEAN && c >= f.in_c_lo && c <= f.in_c_hi;
   const bool left_col_in = LEAN && c - 1 >= f.in_c_lo && c - 1 <= f.in_c_hi;
 
@@ -618,7 +630,8 @@ __global__ void __launch_bounds__(32 * (WARPS + 1), 1) te_onepass_kernel(const _
     num0 = v.tj[B200FDTD_TEJ_NUM_DYJY0 * v.pitch + c];
   }
 
-  const b200fdtd_pulse pulse_x = onepass_pulse(v, 0), pulse_y = onepass_pulse(v, 1);
+  b200fdtd_pulse pulse_x, pulse_y;
+  if (MODE == ROW_GENERAL) { pulse_x = onepass_pulse(v, 0); pulse_y = onepass_pulse(v, 1); }
   size_t k = (size_t)r0 * v.pitch + c;
   double2 bz_prev = zero, hz_prev = zero;                 // new Bz(r-1, c) and its quotient by mu0
   if (active) {
@@ -692,6 +705,10 @@ __global__ void __launch_bounds__(32 * (WARPS + 1), 1) te_onepass_kernel(const _
     if (inner_left) {
       double2 m_unused;
       if (LEAN && (lean_tile || (row_in && left_col_in))) bz_left = l_bz - (((l_ey_below - ey_nb) - ex_old) + l_ex);
+      else if (unit && c - 1 >= f.in_c_lo) {              // the neighbour is a unit-coefficient cell too
+        const double2 l_m = l_mz - (((l_ey_below - ey_nb) - ex_old) + l_ex);
+        bz_left = (l_bz + l_m) - l_mz;
+      }
       else bz_left = te_bz_full(v, r, c - 1, l_ey_below, ey_nb, ex_old, l_ex, l_mz, l_bz, &m_unused);
       if (!lean_tile) hz_left = div_const(bz_left, v.mu0);
     }
@@ -716,10 +733,15 @@ __global__ void __launch_bounds__(32 * (WARPS + 1), 1) te_onepass_kernel(const _
         const double c_dy1 = quotient_or_one(num1, den), c_dy0 = quotient_or_one(num0, den);
         dy = (c_dy * dy_old + c_dy1 * jy) - c_dy0 * jy_old;
       }
-      double2 ex = div_eps(dx, eps_x), ey = div_eps(dy, eps_y);
-      if (pulse_x.enabled && eps_x != 1.0) ex = ex + pulse_term(pulse_x, r - 1, v.j_base + c, eps_x);
-      if (pulse_y.enabled && eps_y != 1.0) ey = ey + pulse_term(pulse_y, r - 1, v.j_base + c, eps_y);
-      if ((long long)k == v.point_k) ex = ex + make_double2(v.point_re, v.point_im);
+      double2 ex = dx, ey = dy;
+      if (MODE == ROW_GENERAL) {
+        ex = div_eps(dx, eps_x); ey = div_eps(dy, eps_y);
+        if (pulse_x.enabled && eps_x != 1.0) ex = ex + pulse_term(pulse_x, r - 1, v.j_base + c, eps_x);
+        if (pulse_y.enabled && eps_y != 1.0) ey = ey + pulse_term(pulse_y, r - 1, v.j_base + c, eps_y);
+        if ((long long)k == v.point_k) ex = ex + make_double2(v.point_re, v.point_im);
+      } else if (eps_x != 1.0 || eps_y != 1.0 || (long long)k == v.point_k) {
+        te_material_cell(&v, r, c, k, eps_x, eps_y, dx, dy, &ex, &ey);
+      }
       if (!(LEAN && lean_cell)) {
         v.f[B200FDTD_TE_MZ][k] = mz;
         v.f[B200FDTD_TE_JX][k] = jx;
@@ -740,6 +762,73 @@ __global__ void __launch_bounds__(32 * (WARPS + 1), 1) te_onepass_kernel(const _
     ey_nb = l_ey_below;
     edge_e = edge_e_nxt;
     edge_b = edge_b_nxt;
+  }
+}
+
+template <bool LEAN, bool STORE_H, int WARPS, int STAGES>
+__global__ void __launch_bounds__(32 * (WARPS + 1), 1) te_onepass_kernel(const __grid_constant__ OnePassView f)
+{
+  constexpr int W = 32 * WARPS;
+  extern __shared__ __align__(128) unsigned char op_smem[];
+  TeRow<W> *ring = reinterpret_cast<TeRow<W> *>(op_smem);
+  double2 *ey_first = reinterpret_cast<double2 *>(op_smem + sizeof(TeRow<W>) * STAGES);   // Ey(r0, strip)
+  unsigned long long *full = reinterpret_cast<unsigned long long *>(ey_first + W);
+  unsigned long long *empty = full + STAGES;
+  unsigned long long *first_bar = empty + STAGES;
+
+  const UpmlView &v = f.u;
+  const Tile T = make_tile<LEAN, WARPS>(f);
+  const int lane = T.lane, warp = T.warp, c0 = T.c0, r0 = T.r0, r1 = T.r1, wcopy = T.wcopy;
+  const bool lean_tile = T.lean_tile;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], (unsigned)T.live_warps); }
+    mbar_init(first_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  double2 *Ex = v.f[B200FDTD_TE_EX], *Ey = v.f[B200FDTD_TE_EY];
+  if (warp == WARPS) {
+    if (lane != 0) return;
+    const unsigned seg = (unsigned)(wcopy * sizeof(double2));
+    const unsigned eps_bytes = (unsigned)(T.n_eps * sizeof(double));
+    const unsigned tx = (lean_tile ? 5u : 8u) * seg + 2u * eps_bytes;
+    const double2 *row_e_next = f.row_e + (size_t)(blockIdx.y + 1) * v.pitch;
+    mbar_expect_tx(first_bar, seg);
+    bulk_g2s(ey_first, &Ey[(size_t)r0 * v.pitch + c0], seg, first_bar);
+    int s = 0; unsigned ph = 0;
+    for (int r = r0; r < r1; r++) {
+      if (r - r0 >= STAGES) mbar_wait(&empty[s], ph ^ 1u);
+      TeRow<W> &st = ring[s];
+      const size_t k = (size_t)r * v.pitch + c0;
+      mbar_expect_tx(&full[s], tx);
+      bulk_g2s(st.ey, (r + 1 < r1) ? &Ey[k + v.pitch] : &row_e_next[c0], seg, &full[s]);
+      bulk_g2s(st.ex, &Ex[k], seg, &full[s]);
+      bulk_g2s(st.bz, &v.f[B200FDTD_TE_BZ][k], seg, &full[s]);
+      bulk_g2s(st.dx, &v.f[B200FDTD_TE_DX][k], seg, &full[s]);
+      bulk_g2s(st.dy, &v.f[B200FDTD_TE_DY][k], seg, &full[s]);
+      if (!lean_tile) {
+        bulk_g2s(st.mz, &v.f[B200FDTD_TE_MZ][k], seg, &full[s]);
+        bulk_g2s(st.jx, &v.f[B200FDTD_TE_JX][k], seg, &full[s]);
+        bulk_g2s(st.jy, &v.f[B200FDTD_TE_JY][k], seg, &full[s]);
+      }
+      bulk_g2s(st.epx, &v.eps0[k - T.eps_off], eps_bytes, &full[s]);
+      bulk_g2s(st.epy, &v.eps1[k - T.eps_off], eps_bytes, &full[s]);
+      if (++s == STAGES) { s = 0; ph ^= 1u; }
+    }
+    return;
+  }
+
+  if (warp >= T.live_warps) return;
+  if constexpr (LEAN) {
+    if (lean_tile) te_consume<ROW_LEAN, true, STORE_H, W, STAGES>(f, T, ring, ey_first, full, empty, first_bar);
+    else           te_consume<ROW_GENERAL, true, STORE_H, W, STAGES>(f, T, ring, ey_first, full, empty, first_bar);
+  } else {
+    const bool unit = r0 >= f.in_r_lo && r1 - 1 <= f.in_r_hi && c0 + 32 * warp >= f.in_c_lo &&
+                      c0 + 32 * warp + 31 <= f.in_c_hi;
+    if (unit) te_consume<ROW_UNIT, false, STORE_H, W, STAGES>(f, T, ring, ey_first, full, empty, first_bar);
+    else      te_consume<ROW_GENERAL, false, STORE_H, W, STAGES>(f, T, ring, ey_first, full, empty, first_bar);
   }
 }
 
