@@ -8,34 +8,46 @@ rank per GPU.
 Workload (BASELINE.json configs[4], the one the 1/2/4/8-GPU metric is quoted on):
 zigzagModel, TM UPML (solver id 2), 16384 x 16384 cells PER GPU, stacked along y
 (global grid 16384 x 16384*N), h_u = 10 nm, pml = 10, lambda = 500 nm, angle 0.
-A "step" is one update(): H phase, E phase + source, NTFF surface sample; the
-deferred NTFF projection of the K timed steps is inside the timed region too.
-9 complex fields x 4 GiB per GPU -- far larger than the 126 MB L2, so no flush is
-needed between iterations.
+A "step" is one update(): H phase + E phase + source (ONE pass of the one-pass kernel,
+fused_kernels.cu) and the NTFF surface sample; the deferred NTFF projection of the K
+timed steps is inside the timed region too.  9 complex fields x 4 GiB per GPU -- far
+larger than the 126 MB L2, so no flush is needed between iterations.
 
   value      whole-job Gcell-updates/s, state resident in HBM, CUDA-event timed on
              the engine's stream, max over ranks.
-  e2e        the same metric through the host-facing C API with HOST buffers in
-             the timed region: eps map H2D from pinned memory, K x update(), Ez
-             D2H into the pinned mirror the getter hands out.
-  roofline   H-phase kernel alone (the dominant kernel): algorithmic bytes
-             (144 B/cell: reads Ez,Mx,Bx,My,By, writes Mx,Bx,My,By; Hx/Hy are not stored,
-             the E phase forms them as B/mu0) over its mean duration, against
-             MEASURED_PEAKS.json hbm_gbs.  `e_phase` is the other kernel (120 B/cell);
-             `step` carries the contract figure of SURVEY 8(d): 264 B/cell-update x rate,
-             which is exactly what the two kernels move.
+  roofline   the one-pass kernel (+ its edge pre-pass, timed together, live, CUDA
+             events): algorithmic bytes per launch (TM 232 B per cell-update: reads
+             Ez,Mx,Bx,My,By,Jz,Dz + eps, writes Mx,Bx,My,By,Jz,Dz,Ez; TE 272) over its
+             mean duration, against MEASURED_PEAKS.json hbm_gbs.  `step` carries SURVEY
+             8(d)'s contract figure (264 / 288 B) for comparison; `two_kernel_form` the two
+             phase kernels the step would otherwise launch.
+  e2e        the same metric with HOST buffers inside the timed region: eps map H2D from
+             pinned (NUMA-local) memory, K x update(), NTFF projection, Ez D2H into a
+             pinned mirror -- wall clock, max over ranks.  `e2e_plugin` (N = 1) is the
+             reference-facing call sequence itself -- simulator_init / K x simulator_calc /
+             fdtdTM_upml_getEz / simulator_finish -- at a size whose host-side permittivity
+             build fits the bench budget, with `init_s` reported beside it.
   lean_interior
              the same K steps with B200FDTD_OPT_LEAN_INTERIOR (opt-in tolerance form: cells
-             outside the absorbing frame advance B / D directly, 168 instead of 264 B per TM
+             outside the absorbing frame advance B / D directly; one pass, 136 B per TM
              cell-update; fields within 1e-12 of the reference instead of bit-identical).
-             Reported BESIDE `value`, which stays the reference's arithmetic in every cell;
-             `--lean` makes it the measured form of the whole line instead.
+             Reported BESIDE `value`, which stays the reference's arithmetic in every cell.
+  dense      `value` again on a material-dense structure (--fill, default 0.35 of the
+             cells with eps != 1, every one of them firing the pulse's exp / sincos): the
+             regime the vacuum-dominated zigzag workload does not show.
+  parity_check
+             N > 1: before anything is timed, a 512 x (512 N) random-state, random-eps case
+             runs on the SAME ranks, peer halos and step form, and every one of the nine
+             arrays is compared bit for bit (position-mixed 64-bit digests summed over the
+             slabs) with a single-slab run on rank 0; U/W after the reduce within 1e-12.
   cpu_baseline / --impl reference
              the UNMODIFIED reference (oracle/_ref/libref.so, built from
              /root/reference) on the host cores, one serial solver instance per
-             core (how main.c uses its MPI ranks), on a bounded sample.
+             core (how main.c uses its MPI ranks), on a bounded sample whose size is
+             stated in config.workload.
 """
 import argparse
+import ctypes
 import json
 import os
 import statistics
@@ -48,10 +60,12 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, HERE)
 
 N_PER_GPU = 16384
-BYTES_STEP_TM = 264          # SURVEY 8(d) contract figure = what the step moves: 144 + 120
-BYTES_H_TM = 144             # H-phase kernel: reads Ez,Mx,Bx,My,By (80) + writes Mx,Bx,My,By (64)
-BYTES_E_TM = 120             # E-phase kernel: reads Bx,By,Jz,Dz (64) + eps (8) + writes Jz,Dz,Ez (48)
 FALLBACK_HBM_GBS = 6650.0    # B200_PROFILING.md fallback
+# algorithmic bytes per cell-update: one-pass forms, two-kernel phases, SURVEY 8(d)
+BYTES = {"TM_UPML_2D": {"one_pass": 232, "one_pass_lean": 136, "h": 144, "e": 120, "contract": 264,
+                        "lean_h": 80, "lean_e": 88},
+         "TE_UPML_2D": {"one_pass": 272, "one_pass_lean": 176, "h": 96, "e": 192, "contract": 288,
+                        "lean_h": 64, "lean_e": 128}}
 
 
 def ncu_traffic(kernel_substr, cells):
@@ -62,7 +76,7 @@ def ncu_traffic(kernel_substr, cells):
     for path in sorted(glob.glob(os.path.join(HERE, "profiles", "*_full.json")), reverse=True):
         try:
             for rec in json.load(open(path))["launches"]:
-                name = rec["kernel"].replace("double, ", "").replace(" ", "")      # "<double, 0>" == "<0>"
+                name = rec["kernel"].replace("double, ", "").replace(" ", "").replace("(bool)", "").replace("(int)", "")
                 if kernel_substr in name and abs(rec.get("cells", 0) - cells) < 0.01 * cells:
                     return rec["traffic_bytes"], os.path.relpath(path, HERE)
         except Exception:
@@ -134,8 +148,15 @@ def run_cpu_reference(n, steps, warm, with_ntff=True, max_workers=None):
             "max_loop_s": max(times)}
 
 
+def cpu_sample_text(res, n, steps, warm):
+    return ("%d concurrent serial TM_UPML instances of the unmodified reference (oracle/_ref/libref.so, one per "
+            "host core, as main.c uses its MPI ranks), each zigzagModel %dx%d, %d timed steps after %d warm-up, "
+            "NTFF included" % (res["cores"], n, n, steps, warm))
+
+
 def reference_arm(args):
-    """bench.py --impl reference: the reference's own CPU path, same metric/config."""
+    """bench.py --impl reference: the reference's own CPU path, same metric; the workload string
+    states the bounded sample that was actually run."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
@@ -148,15 +169,20 @@ def reference_arm(args):
                           "oracle/_ref/libref.so missing (built only where /root/reference exists)"}))
         return 0
     value = res["rate"] / 1e9
-    sample = ("%d concurrent serial TM_UPML instances (one per host core, as main.c uses MPI "
-              "ranks), each zigzagModel %dx%d, %d timed steps after %d warm-up, NTFF included"
-              % (res["cores"], n, n, args.steps, args.warmup))
+    sample = cpu_sample_text(res, n, args.steps, args.warmup)
+    cfg = workload_config(args.gpus, n=args.n)
+    cfg["workload"] = ("CPU SAMPLE of that workload: %d x zigzagModel TM_UPML_2D %d x %d (one reference instance per "
+                       "host core); the GPU arm runs %s" % (res["cores"], n, n, cfg["workload"]))
+    cfg["cpu_sample_cells_per_instance"] = n * n
+    cfg["note"] = ("bounded sample (BASELINE.md 4.5): the reference's layout needs 78 GiB per 16384^2 instance; its "
+                   "per-core rate falls with grid size (survey: -35 % from 1024^2 to 4096^2), so the sample flatters "
+                   "the CPU")
     line = {
         "impl": "reference", "metric": "Gcell-updates/s", "value": value, "unit": "Gcell-updates/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * res["max_loop_s"] / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args.gpus, sample_note="CPU arm runs a bounded sample: " + sample, n=args.n),
+        "config": cfg,
         "cpu_baseline": {"value": value, "unit": "Gcell-updates/s", "cores": res["cores"],
                          "kind": "reference", "sample": sample},
         "e2e": {"value": value, "unit": "Gcell-updates/s", "h2d_bytes_per_step": 0,
@@ -171,8 +197,7 @@ MODEL_NAMES = {"ZIGZAG": "zigzagModel", "LAYER": "multiLayerModel", "MORPHO_SCAL
                "MIE_CYLINDER": "MieCylinderModel", "NO_MODEL": "noModel"}
 
 
-def workload_config(n_gpus, sample_note=None, n=N_PER_GPU, solver="TM_UPML_2D", halo="peer", model="ZIGZAG",
-                    strong=False):
+def workload_config(n_gpus, n=N_PER_GPU, solver="TM_UPML_2D", halo="peer", model="ZIGZAG", strong=False):
     n_py = n if strong else n * n_gpus
     per_gpu = n * n_py // n_gpus
     cfg = {"workload": "%s %s %s scaling, %d x %d cells per GPU, global %d x %d, y-slabs"
@@ -184,9 +209,43 @@ def workload_config(n_gpus, sample_note=None, n=N_PER_GPU, solver="TM_UPML_2D", 
            "parallelism": "y-slab x%d" % n_gpus}
     if n_gpus > 1:
         cfg["halo"] = halo
-    if sample_note:
-        cfg["note"] = sample_note
     return cfg
+
+
+# ----------------------------------------------------------------------------
+# host placement: this rank's threads and pinned buffers next to its GPU
+# ----------------------------------------------------------------------------
+def bind_near_gpu(local_rank):
+    """CPU affinity + memory policy (MPOL_PREFERRED) of this process on the NUMA node its GPU hangs
+    off, so the pinned eps / Ez buffers of the e2e leg are node-local: at 8 ranks the host copies
+    otherwise cross the socket interconnect (round 1: 50 -> 13 GB/s per GPU).  Best effort."""
+    info = {"numa_node": None, "bound": False}
+    try:
+        out = subprocess.run(["nvidia-smi", "-i", str(local_rank), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=20).stdout.strip()
+        bdf = out.lower()
+        if bdf.startswith("0000"):
+            bdf = bdf[4:]                  # nvidia-smi prints an 8-digit domain, sysfs a 4-digit one
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read())
+        info["numa_node"] = node
+        if node < 0:
+            return info
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        mask = ctypes.c_ulong(1 << node)
+        libc = ctypes.CDLL(None, use_errno=True)
+        # set_mempolicy(MPOL_PREFERRED = 1, &mask, maxnode): x86-64 syscall 238
+        rc = libc.syscall(238, 1, ctypes.byref(mask), ctypes.c_ulong(8 * ctypes.sizeof(mask)))
+        info["bound"] = bool(allowed) and rc == 0
+        info["cpus"] = len(allowed)
+    except Exception as err:            # no sysfs entry, container without the syscall, ...
+        info["error"] = str(err)[:80]
+    return info
 
 
 # ----------------------------------------------------------------------------
@@ -238,17 +297,101 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------
+# multi-GPU parity check on the communicator the benchmark uses
+# ----------------------------------------------------------------------------
+def parity_check(B, SlabRun, solver, world, rank, local_rank, comm, stream, dist, torch, steps=48, n=512):
+    """A 512 x (512 * world) case from a random state with a random permittivity map (one cell in
+    three a material cell) and the pulse on, stepped on all ranks with peer halos in the one-pass
+    form the benchmark runs; then the same global case as ONE slab on rank 0.  Every one of the
+    nine arrays must agree bit for bit: the position-mixed digests of the slabs add up (mod 2^64) to
+    the single-slab digest.  U/W after the NCCL reduce against the single slab's: <= 1e-12."""
+    import numpy as np
+    kind = 2 if solver == "TM_UPML_2D" else 3
+    npx, npy = n, n * world
+    rng = np.random.default_rng(20261017)
+    n_eps = 1 if kind == 2 else 2
+    eps = [np.where(rng.random((npx, npy), dtype=np.float32) < 0.67, 1.0, 1.5 + rng.random((npx, npy), dtype=np.float32))
+           for _ in range(n_eps)]
+    state = [rng.standard_normal((npx, npy), dtype=np.float32).astype(np.float64) +
+             1j * rng.standard_normal((npx, npy), dtype=np.float32).astype(np.float64) for _ in range(9)]
+    for h, b in (((3, 5), (6, 8)) if kind == 2 else ((6, 8),)):      # H == B/mu0, the solver's invariant
+        state[h] = (state[b].real / B.MU_0_S) + 1j * (state[b].imag / B.MU_0_S)
+
+    def run_case(r, w, communicator):
+        run = SlabRun("NO_MODEL", solver, npx, npy, steps, rank=r, world=w, device=local_rank, comm=communicator,
+                      angle_deg=30)
+        run.engine.set_stream(stream.cuda_stream)
+        run.engine.set_option(B.OPT_FUSED, 1)                 # the benchmark's form, forced at this size
+        for slot, e in enumerate(eps):
+            run.engine.set_eps(slot, e)
+        for slot in range(9):
+            run.engine.set_field(slot, state[slot])
+        if communicator is not None and w > 1:
+            run.enable_peer_halos(communicator.gather_blobs)
+        form = run.engine.step_form()
+        for _ in range(steps):
+            run.step()
+        run.engine.sync()
+        digests = [run.engine.digest(s) for s in range(9)]
+        run.project()
+        uw = None
+        ptr, count = run.engine.uw_device()
+        if communicator is not None and w > 1:
+            communicator.reduce_sum_to_root(ptr, count)
+        if r == 0:
+            uw = np.stack([run.engine.uw(s) for s in range(3)])
+        torch.cuda.synchronize()
+        if communicator is not None and w > 1:
+            dist.barrier()                 # nobody frees a slab a neighbour may still store into
+        run.close()
+        return digests, uw, form
+
+    mine, uw_multi, form = run_case(rank, world, comm)
+    t = torch.tensor([d - (1 << 64) if d >= (1 << 63) else d for d in mine], dtype=torch.int64, device="cuda")
+    gathered = [torch.zeros_like(t) for _ in range(world)]
+    dist.all_gather(gathered, t)
+    out = None
+    if rank == 0:
+        total = [sum(int(g[s].item()) for g in gathered) & ((1 << 64) - 1) for s in range(9)]
+        want, uw_single, _ = run_case(0, 1, None)
+        bad = [s for s in range(9) if total[s] != want[s]]
+        err = float(np.abs(uw_multi - uw_single).max() / np.abs(uw_single).max())
+        ok = not bad and err <= 1e-12
+        out = {"result": "bit-identical" if ok else "MISMATCH",
+               "grid": "%d x %d, %d y-slabs of %d columns" % (npx, npy, world, n), "steps": steps,
+               "arrays_compared": 9, "mismatching_arrays": bad, "step_form": form,
+               "ntff_uw_rel_err_after_reduce": err,
+               "how": "random state + random eps (1/3 material cells) + pulse; digests of the slabs summed mod 2^64 "
+                      "vs a single-slab run of the same global case on rank 0"}
+    dist.barrier()
+    return out
+
+
+def dense_eps(np, n_px, nj, fill, seed):
+    """Material-dense permittivity map: square blocks of 8 x 8 cells, a fraction `fill` of them
+    dielectric (eps 2.56, the reference's n = 1.6) -- every such cell divides by eps and fires the
+    pulse's exp / sincos each step."""
+    rng = np.random.default_rng(seed)
+    blocks = rng.random(((n_px + 7) // 8, (nj + 7) // 8), dtype=np.float32) < fill
+    eps = np.where(np.repeat(np.repeat(blocks, 8, axis=0), 8, axis=1)[:n_px, :nj], 2.56, 1.0)
+    eps[:12, :] = 1.0; eps[-12:, :] = 1.0                      # keep the absorbing frame in vacuum
+    return np.ascontiguousarray(eps)
+
+
+# ----------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------
 def gpu_arm(args):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    placement = bind_near_gpu(local_rank)          # before anything allocates host memory
+
     import numpy as np
     import torch
     from mpifdtd_b200 import binding as B
     from mpifdtd_b200.slab import SlabRun, TorchHaloComm
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if world != args.gpus and world > 1:
         raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
     if B.device_count() < 1:
@@ -261,12 +404,12 @@ def gpu_arm(args):
         res_stencil = run_cpu_reference(args.cpu_n, args.cpu_steps, 2, with_ntff=False)
         if res is not None:
             cpu = {"value": res["rate"] / 1e9, "unit": "Gcell-updates/s", "cores": res["cores"],
-                   "kind": "reference",
-                   "sample": "%d concurrent serial TM_UPML instances of oracle/_ref/libref.so (one per "
-                             "host core), zigzagModel %dx%d, %d timed steps, NTFF included"
-                             % (res["cores"], args.cpu_n, args.cpu_n, args.cpu_steps),
+                   "kind": "reference", "sample": cpu_sample_text(res, args.cpu_n, args.cpu_steps, 2),
                    "per_core_mcells": res["per_core"] / 1e6,
-                   "stencil_only_value": (res_stencil["rate"] / 1e9) if res_stencil else None}
+                   "stencil_only_value": (res_stencil["rate"] / 1e9) if res_stencil else None,
+                   "note": "the GPU's NTFF cost in a run this short is the surface sample only (the deferred "
+                           "projection finds few taps inside K steps), so `stencil_only_value` is the like-for-like "
+                           "CPU figure for `value`"}
         else:
             cpu = {"value": None, "unit": "Gcell-updates/s", "cores": 0, "kind": "reference",
                    "sample": "unavailable: oracle/_ref/libref.so not shipped to this box"}
@@ -282,11 +425,31 @@ def gpu_arm(args):
     n_px, n_py = args.n, (args.n if args.strong else args.n * world)
     K, W = args.steps, args.warmup
     total_steps = W + K
+    tm = args.solver == "TM_UPML_2D"
+    by = BYTES[args.solver]
     stream = torch.cuda.Stream()
     comm = None
     with torch.cuda.stream(stream):
         if world > 1:
             comm = TorchHaloComm(n_px, torch.device("cuda", local_rank))
+
+        def barrier():
+            torch.cuda.synchronize()
+            if dist is not None:
+                dist.barrier()
+            torch.cuda.synchronize()
+
+        def max_over_ranks(x):
+            t = torch.tensor([x], dtype=torch.float64, device="cuda")
+            if dist is not None:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+
+        # ---- correctness of the multi-GPU path, on this communicator, before anything is timed
+        parity = None
+        if world > 1 and args.halo == "peer" and args.precision == "f64" and not args.no_parity_check:
+            parity = parity_check(B, SlabRun, args.solver, world, rank, local_rank, comm, stream, dist, torch)
+
         run = SlabRun(args.model, args.solver, n_px, n_py, total_steps, rank=rank, world=world,
                       device=local_rank, comm=comm, precision=args.precision)
         run.engine.set_stream(stream.cuda_stream)
@@ -297,157 +460,180 @@ def gpu_arm(args):
             if args.halo == "peer":
                 run.enable_peer_halos(comm.gather_blobs)
 
-        def barrier():
-            torch.cuda.synchronize()
-            if dist is not None:
-                dist.barrier()
-            torch.cuda.synchronize()
-
-        # 0 full kernels, 1 unit-coefficient interior + frame, 2 lean interior + frame, 3 one-pass step
+        # 0 full kernels, 1 unit-coefficient interior + frame, 2 lean interior + frame, 3 one pass, 4 one pass lean
         form = run.engine.step_form()
-        two_kernel_form = form
-        if form == 3 and world > 1 and args.halo != "peer":
-            form = -1       # NCCL send/recv halos run between the two phase kernels: no one-pass step there
-        if form in (3, -1):       # phase_h / phase_e (timed separately below, for reference) use this form:
-            run.engine.set_option(B.OPT_FUSED, 0)
-            two_kernel_form = run.engine.step_form()
-            run.engine.set_option(B.OPT_FUSED, 2)
-            if form == -1:
-                form = two_kernel_form
-
-        # ---- value: device-resident K steps + deferred projection ----------------
-        for _ in range(W):
-            run.step()
-        barrier()
-        sampler = ClockSampler(local_rank)
-        if rank == 0:
-            sampler.start()
-        launches0 = run.engine.launches()
-        run.engine.timer_start()
-        for _ in range(K):
-            run.step()
-        run.project()
-        ms = run.engine.timer_stop()
-        launches = run.engine.launches() - launches0
-        barrier()
-        clocks = sampler.stop() if rank == 0 else None
-        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        if dist is not None:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_max = float(t.item())
+        one_pass = form in (3, 4) and not (world > 1 and args.halo != "peer")
         cells = float(n_px) * float(n_py)
-        value = cells * K / (ms_max * 1e-3) / 1e9
+        cells_rank = float(n_px) * float(run.nj)
 
-        # ---- per-kernel timing for the roofline (rank-local, same state) ----------
-        reps = max(3, min(K, 20))
-        run.engine.phase_h(run.args); run.engine.sync()
-        run.engine.timer_start()
-        for _ in range(reps):
-            run.engine.phase_h(run.args)
-        ms_h = run.engine.timer_stop() / reps
-        run.engine.phase_e(run.args); run.engine.sync()
-        run.engine.timer_start()
-        for _ in range(reps):
-            run.engine.phase_e(run.args)
-        ms_e = run.engine.timer_stop() / reps
-        ms_fused = None
-        if form == 3:        # the step is ONE pass: edge pre-pass + TMA-staged marching kernel
-            run.engine.phase_fused(run.args); run.engine.sync()
-            run.engine.timer_start()
-            for _ in range(reps):
-                run.engine.phase_fused(run.args)
-            ms_fused = run.engine.timer_stop() / reps
-        barrier()
-
-        # ---- the opt-in lean-interior form, same state, same K steps (reported beside `value`)
-        lean = None
-        if not args.lean and not args.no_lean_leg:
-            run.engine.zero()
-            run.L.field_reset()
-            run.engine.set_option(B.OPT_LEAN_INTERIOR, 1)
-            barrier()
+        def timed_steps():
             for _ in range(W):
                 run.step()
             barrier()
+            launches0 = run.engine.launches()
             run.engine.timer_start()
             for _ in range(K):
                 run.step()
             run.project()
-            t = torch.tensor([run.engine.timer_stop()], dtype=torch.float64, device="cuda")
-            if dist is not None:
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms_lean = float(t.item())
-            run.engine.phase_h(run.args); run.engine.sync()
+            ms = run.engine.timer_stop()
+            launches = run.engine.launches() - launches0
+            barrier()
+            return max_over_ranks(ms), launches
+
+        def restart():
+            run.engine.zero()
+            run.L.field_reset()
+            barrier()
+
+        # ---- value: device-resident K steps + deferred projection ----------------
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        ms_max, launches = timed_steps()
+        clocks = sampler.stop() if rank == 0 else None
+        value = cells * K / (ms_max * 1e-3) / 1e9
+
+        # ---- per-kernel timing for the roofline (rank-local, same state, CUDA events) -------
+        def time_phase(fn, reps):
+            fn(run.args); run.engine.sync()
             run.engine.timer_start()
             for _ in range(reps):
-                run.engine.phase_h(run.args)
-            ms_h_lean = run.engine.timer_stop() / reps
-            run.engine.phase_e(run.args); run.engine.sync()
-            run.engine.timer_start()
-            for _ in range(reps):
-                run.engine.phase_e(run.args)
-            ms_e_lean = run.engine.timer_stop() / reps
+                fn(run.args)
+            return run.engine.timer_stop() / reps
+
+        reps = max(3, min(K, 20))
+        ms_one = time_phase(run.engine.phase_fused, reps) if form in (3, 4) else None
+        if form in (3, 4):             # phase_h / phase_e time the two-kernel form the step would otherwise take
+            run.engine.set_option(B.OPT_FUSED, 0)
+        two_form = run.engine.step_form()
+        ms_h = time_phase(run.engine.phase_h, reps)
+        ms_e = time_phase(run.engine.phase_e, reps)
+        if form in (3, 4):
+            run.engine.set_option(B.OPT_FUSED, 2)
+        barrier()
+
+        # ---- the opt-in lean-interior form, same K steps (reported beside `value`) --------------
+        lean = None
+        if not args.lean and not args.no_lean_leg:
+            restart()
+            run.engine.set_option(B.OPT_LEAN_INTERIOR, 1)
+            barrier()
+            lean_form = run.engine.step_form()
+            ms_lean, _ = timed_steps()
+            ms_lean_kernel = time_phase(run.engine.phase_fused, reps) if lean_form == 4 else None
             run.engine.sync()
             run.engine.set_option(B.OPT_LEAN_INTERIOR, 0)
             barrier()
-            lean = (ms_lean, ms_h_lean, ms_e_lean)
+            lean = (ms_lean, ms_lean_kernel, lean_form)
 
-        # ---- e2e: host buffers inside the timed region ------------------------------
-        run.engine.zero()
-        run.L.field_reset()
-        barrier()            # every rank has zeroed (peer-halo flags included) before anyone steps
-        eps_pinned = torch.from_numpy(run.eps_host[0]).pin_memory()
-        ez_pinned = torch.empty((n_px, run.nj, 2), dtype=torch.float64).pin_memory()
+        # ---- material-dense structure: same engine, another permittivity map --------------------
+        dense = None
+        if args.fill > 0 and tm and args.precision == "f64":
+            restart()
+            d_eps = dense_eps(np, n_px, run.nj, args.fill, 7 + rank)
+            frac = float((d_eps != 1.0).mean())
+            B.check(run.L.b200fdtd_set_eps_slab(run.engine.h, 0, d_eps.ctypes.data), "set_eps_slab")
+            del d_eps
+            ms_dense, _ = timed_steps()
+            ms_dense_kernel = time_phase(run.engine.phase_fused, reps) if form in (3, 4) else None
+            B.check(run.L.b200fdtd_set_eps_slab(run.engine.h, 0, run.eps_host[0].ctypes.data), "set_eps_slab")
+            dense = (ms_dense, ms_dense_kernel, frac)
+
+        # ---- e2e: host buffers inside the timed region ------------------------------------------
+        restart()
+        pinned = []                        # pinned by the library (cudaHostAlloc), node-local after bind_near_gpu()
+
+        def host_alloc(nbytes):
+            p = ctypes.c_void_p()
+            B.check(run.L.b200fdtd_host_alloc(ctypes.byref(p), nbytes), "host_alloc")
+            pinned.append(p)
+            return p
+
+        n_eps = len(run.eps_host)
+        eps_pinned = [host_alloc(e.nbytes) for e in run.eps_host]
+        for p, e in zip(eps_pinned, run.eps_host):
+            ctypes.memmove(p, e.ctypes.data, e.nbytes)
+        field_bytes = n_px * run.nj * 16
+        ez_pinned = host_alloc(field_bytes)
         for _ in range(min(W, 3)):
             run.step()
         barrier()
         t0 = time.perf_counter()
-        B.check(run.L.b200fdtd_set_eps_slab(run.engine.h, 0, eps_pinned.data_ptr()), "set_eps_slab")
+        for slot in range(n_eps):
+            B.check(run.L.b200fdtd_set_eps_slab(run.engine.h, slot, eps_pinned[slot]), "set_eps_slab")
         for _ in range(K):
             run.step()
-        B.check(run.L.b200fdtd_get_field_slab(run.engine.h, 0, ez_pinned.data_ptr()), "get_field_slab")
+        run.project()
+        B.check(run.L.b200fdtd_get_field_slab(run.engine.h, 0, ez_pinned), "get_field_slab")
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
-        t = torch.tensor([dt], dtype=torch.float64, device="cuda")
-        if dist is not None:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_value = cells * K / float(t.item()) / 1e9
-        h2d = run.eps_host[0].nbytes / K
-        d2h = n_px * run.nj * 16 / K
+        e2e_value = cells * K / max_over_ranks(dt) / 1e9
+        h2d = sum(e.nbytes for e in run.eps_host) / K
+        d2h = field_bytes / K
+        for p in pinned:
+            run.L.b200fdtd_host_free(p)
+
+    # ---- e2e through the plugin surface itself (N = 1) ----------------------------------------------
+    device_bytes = run.engine.device_bytes()
+    e2e_plugin = None
+    if rank == 0 and world == 1 and not args.no_plugin_leg and args.precision == "f64" and not args.lean:
+        run.close()
+        run = None
+        e2e_plugin = plugin_leg(B, args, K)
 
     if rank == 0:
         peak, peak_kind = measured_hbm_peak()
-        cells_rank = float(n_px) * float(run.nj)
-        tm = args.solver == "TM_UPML_2D"
-        # TE: H phase reads Ex,Ey,Mz,Bz (64) + writes Mz,Bz (32); E phase reads Bz,Jx,Dx,Jy,Dy (80) +
-        # eps x2 (16) + writes Jx,Dx,Jy,Dy,Ex,Ey (96); step = SURVEY 8(d)'s 288 B
-        bytes_h, bytes_e, bytes_step = (BYTES_H_TM, BYTES_E_TM, BYTES_STEP_TM) if tm else (96, 192, 288)
-        # lean interior: H reads Ez,Bx,By + writes Bx,By (TE: Ex,Ey,Bz + Bz); E reads Bx,By,Dz,eps +
-        # writes Dz,Ez (TE: Bz,Dx,Dy,2 eps + Dx,Dy,Ex,Ey); the 10-cell frame adds < 0.3 % at 16384^2
-        lean_h, lean_e = (80, 88) if tm else (64, 128)
-        if args.lean:
-            bytes_h, bytes_e = lean_h, lean_e
-        if args.precision == "f32":     # complex64 fields, f32 eps: every array element is half as wide
-            bytes_h, bytes_e, bytes_step = bytes_h // 2, bytes_e // 2, bytes_step // 2
-            lean_h, lean_e = lean_h // 2, lean_e // 2
         kname = "tm" if tm else "te"
-        ach_h = bytes_h * cells_rank / (ms_h * 1e-3) / 1e9
-        ach_e = bytes_e * cells_rank / (ms_e * 1e-3) / 1e9
-        step_gbs = bytes_step * (value / world) * 1e9 / 1e9
-        # ncu prints the kernel as <double, STORE_H, LEAN>: "<0,0>" default form, "<0,1>" lean
-        # kernel names as ncu prints them, minus "double, " and blanks: the full kernels are
-        # <STORE_H, RECTS> ("<0>" in captures older than the RECTS parameter), the lean ones <STORE_H>
-        traffic, traffic_src = None, None
-        if args.precision == "f64":
-            tags = {0: [kname + "_upml_h_kernel<0,0>", kname + "_upml_h_kernel<0>"],
-                    1: [kname + "_unit_h_kernel<0>"], 2: [kname + "_lean_h_kernel<0>"],
-                    3: [kname + "_upml_fused_tma_kernel<0"]}[form]
-            for tag in tags:
-                traffic, traffic_src = ncu_traffic(tag, cells_rank)
-                if traffic is not None:
-                    break
-        stem = kname + {0: "_upml", 1: "_unit", 2: "_lean"}[two_kernel_form]
-        h_name, e_name = stem + "_h_kernel<STORE_H=false>", stem + "_e_kernel<FROM_B=true>"
+        scale = 1 if args.precision == "f64" else 0.5          # complex64 / f32 eps: every element half as wide
+        step_gbs = by["contract"] * scale * (value / world)
+        stems = {0: "_upml", 1: "_unit", 2: "_lean"}
+        two = {"h_phase": {"kernel": kname + stems[two_form] + "_h_kernel<STORE_H=false>", "ms_per_launch": ms_h,
+                           "algorithmic_bytes_per_cell": by["h"] * scale,
+                           "achieved": by["h"] * scale * cells_rank / (ms_h * 1e-3) / 1e9},
+               "e_phase": {"kernel": kname + stems[two_form] + "_e_kernel<FROM_B=true>", "ms_per_launch": ms_e,
+                           "algorithmic_bytes_per_cell": by["e"] * scale,
+                           "achieved": by["e"] * scale * cells_rank / (ms_e * 1e-3) / 1e9}}
+        for ph in two.values():
+            ph["frac"] = ph["achieved"] / peak
+        if one_pass:
+            b_one = by["one_pass_lean" if form == 4 else "one_pass"]
+            ach = b_one * cells_rank / (ms_one * 1e-3) / 1e9
+            traffic, traffic_src = ncu_traffic(kname + "_onepass_kernel<%d,0" % (1 if form == 4 else 0), cells_rank)
+            roof = {"bound": "hbm",
+                    "kernel": "%s_onepass_kernel<LEAN=%s, STORE_H=false, 8 warps, 4 row buffers> (+ its edge pre-pass, "
+                              "timed together)" % (kname, "true" if form == 4 else "false"),
+                    "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": peak_kind,
+                    "traffic": traffic, "traffic_source": traffic_src,
+                    "algorithmic_bytes_per_launch": b_one * cells_rank, "ms_per_launch": ms_one,
+                    "algorithmic_bytes_per_cell": b_one,
+                    "note": ("one pass reads Ez,Mx,Bx,My,By,Jz,Dz + eps (120 B) and writes Mx,Bx,My,By,Jz,Dz,Ez (112 B): "
+                             "232 B per cell-update against SURVEY 8(d)'s 264 B contract figure for two passes"
+                             if tm and form == 3 else "see DESIGN.md section 4 for the byte count of this form"),
+                    "step": {"algorithmic_bytes_per_cell_update": by["contract"], "achieved": step_gbs,
+                             "frac": step_gbs / peak, "frac_of_nominal_8TBs": step_gbs / 8000.0,
+                             "moved_bytes_per_cell_update": b_one, "moved": b_one * (value / world),
+                             "moved_frac": b_one * (value / world) / peak},
+                    "two_kernel_form": two}
+        else:
+            bh = (by["lean_h"] if form == 2 else by["h"]) * scale
+            be = (by["lean_e"] if form == 2 else by["e"]) * scale
+            ach = bh * cells_rank / (ms_h * 1e-3) / 1e9
+            roof = {"bound": "hbm", "kernel": two["h_phase"]["kernel"], "achieved": ach, "peak": peak, "unit": "GB/s",
+                    "frac": ach / peak, "peak_source": peak_kind, "traffic": None, "traffic_source": None,
+                    "algorithmic_bytes_per_launch": bh * cells_rank, "ms_per_launch": ms_h,
+                    "algorithmic_bytes_per_cell": bh,
+                    "e_phase": dict(two["e_phase"], algorithmic_bytes_per_cell=be,
+                                    achieved=be * cells_rank / (ms_e * 1e-3) / 1e9),
+                    "step": {"algorithmic_bytes_per_cell_update": by["contract"] * scale, "achieved": step_gbs,
+                             "frac": step_gbs / peak, "frac_of_nominal_8TBs": step_gbs / 8000.0,
+                             "moved_bytes_per_cell_update": bh + be, "moved": (bh + be) * (value / world),
+                             "moved_frac": (bh + be) * (value / world) / peak}}
+        forms = {3: "one pass: edge pre-pass + TMA-staged marching kernel (H and E fused; bit-identical to the "
+                    "two-kernel forms; B200FDTD_OPT_FUSED, default on grids of >= 2^22 cells)",
+                 4: "one pass, lean interior (tolerance form)",
+                 0: "one full kernel per phase",
+                 1: "unit-coefficient interior kernel + frame kernel per phase (bit-identical to the one-kernel form)",
+                 2: "lean interior kernel + frame kernel per phase (tolerance form)"}
         line = {
             "metric": "Gcell-updates/s", "value": value, "unit": "Gcell-updates/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_max / K,
@@ -456,83 +642,99 @@ def gpu_arm(args):
             "config": workload_config(world, n=args.n, solver=args.solver, model=args.model, strong=args.strong,
                                       halo={"peer": "direct NVLink peer stores + device flags",
                                             "nccl": "NCCL send/recv"}[args.halo]),
-            "roofline": {"bound": "hbm", "kernel": h_name, "achieved": ach_h,
-                         "peak": peak, "unit": "GB/s", "frac": ach_h / peak, "peak_source": peak_kind,
-                         "traffic": traffic, "traffic_source": traffic_src,
-                         "algorithmic_bytes_per_launch": bytes_h * cells_rank, "ms_per_launch": ms_h,
-                         "algorithmic_bytes_per_cell": bytes_h,
-                         "e_phase": {"kernel": e_name, "achieved": ach_e,
-                                     "frac": ach_e / peak, "ms_per_launch": ms_e,
-                                     "algorithmic_bytes_per_cell": bytes_e},
-                         "step": {"algorithmic_bytes_per_cell_update": bytes_step,
-                                  "achieved": step_gbs, "frac": step_gbs / peak,
-                                  "frac_of_nominal_8TBs": step_gbs / 8000.0}},
+            "roofline": roof,
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "Gcell-updates/s",
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "path": "b200fdtd_set_eps_slab(pinned host eps) + K x [mpifdtd_upml_step_args + "
-                            "b200fdtd_step + field_nextStep] + b200fdtd_get_field_slab(Ez -> pinned host)"},
+                    "path": "b200fdtd_set_eps_slab(pinned host eps) + K x [mpifdtd_upml_step_args + b200fdtd_step + "
+                            "field_nextStep] + b200fdtd_ntff_project + b200fdtd_get_field_slab(%s -> pinned host)"
+                            % ("Ez" if tm else "Ex"),
+                    "host_placement": placement},
             "gpu_launches": int(launches),
-            "step_form": {3: "one pass: edge pre-pass + TMA-staged marching kernel (H and E fused, 232 B per "
-                             "cell-update, bit-identical to the two-kernel forms; B200FDTD_OPT_FUSED, default on "
-                             "large single-slab TM grids)",
-                          0: "one full kernel per phase",
-                          1: "unit-coefficient interior kernel + frame kernel per phase (bit-identical to the "
-                             "one-kernel form; B200FDTD_OPT_UNIT_SPLIT, default on large grids)",
-                          2: "lean interior kernel + frame kernel per phase (tolerance form)"}[form],
+            "step_form": forms[form if one_pass or form < 3 else two_form],
             "clocks": clocks,
-            "device_bytes": run.engine.device_bytes(),
+            "device_bytes": device_bytes,
         }
-        if form == 3:
-            bytes_fused = 232 if args.precision == "f64" else 116
-            ach_f = bytes_fused * cells_rank / (ms_fused * 1e-3) / 1e9
-            two = dict(line["roofline"])
-            line["roofline"] = {
-                "bound": "hbm", "kernel": kname + "_upml_fused_tma_kernel<STORE_H=false, 8 warps, 4 stages> (+ its "
-                                          "edge pre-pass, timed together)",
-                "achieved": ach_f, "peak": peak, "unit": "GB/s", "frac": ach_f / peak, "peak_source": peak_kind,
-                "traffic": traffic, "traffic_source": traffic_src,
-                "algorithmic_bytes_per_launch": bytes_fused * cells_rank, "ms_per_launch": ms_fused,
-                "algorithmic_bytes_per_cell": bytes_fused,
-                "note": "one pass reads Ez,Mx,Bx,My,By,Jz,Dz + eps (120 B) and writes Mx,Bx,My,By,Jz,Dz,Ez (112 B): "
-                        "232 B per cell-update against SURVEY 8(d)'s 264 B contract figure for two passes",
-                "step": {"algorithmic_bytes_per_cell_update": bytes_step,
-                         "achieved": step_gbs, "frac": step_gbs / peak, "frac_of_nominal_8TBs": step_gbs / 8000.0,
-                         "moved_bytes_per_cell_update": bytes_fused,
-                         "moved": bytes_fused * (value / world), "moved_frac": bytes_fused * (value / world) / peak},
-                "two_kernel_form": {"h_phase": {k: two[k] for k in ("kernel", "achieved", "frac", "ms_per_launch",
-                                                                    "algorithmic_bytes_per_cell")},
-                                    "e_phase": two["e_phase"]}}
+        if e2e_plugin is not None:
+            line["e2e_plugin"] = e2e_plugin
+        if parity is not None:
+            line["parity_check"] = parity["result"]
+            line["parity_detail"] = parity
         if args.lean:
-            line["config"]["form"] = ("lean interior (B200FDTD_OPT_LEAN_INTERIOR): tolerance form, fields within "
-                                      "1e-12 of the reference; moves %d B per cell-update" % (bytes_h + bytes_e))
-            line["roofline"]["step"]["moved_bytes_per_cell_update"] = bytes_h + bytes_e
-            line["roofline"]["step"]["moved"] = (bytes_h + bytes_e) * (value / world)
-            line["roofline"]["step"]["moved_frac"] = (bytes_h + bytes_e) * (value / world) / peak
+            line["config"]["form"] = "lean interior (B200FDTD_OPT_LEAN_INTERIOR): tolerance form, fields within 1e-12"
         if lean is not None:
-            ms_lean, ms_h_lean, ms_e_lean = lean
+            ms_lean, ms_lean_kernel, lean_form = lean
             v_lean = cells * K / (ms_lean * 1e-3) / 1e9
-            moved = (lean_h + lean_e) * (v_lean / world)
+            b_lean = by["one_pass_lean"] if lean_form == 4 else by["lean_h"] + by["lean_e"]
             line["lean_interior"] = {
                 "value": v_lean, "unit": "Gcell-updates/s", "ms_per_step": ms_lean / K,
-                "speedup_vs_value": v_lean / value,
+                "speedup_vs_value": v_lean / value, "step_form": forms[lean_form],
                 "note": "opt-in B200FDTD_OPT_LEAN_INTERIOR: cells outside the absorbing frame skip the M / J "
                         "recurrences (all coefficients exactly 1 there); tolerance form, fields within 1e-12 of "
                         "the reference (tests/test_gpu_lean.py); `value` above is the bit-exact default",
-                "moved_bytes_per_cell_update": lean_h + lean_e,
-                "moved": moved, "moved_frac": moved / peak,
-                "h_phase": {"ms_per_launch": ms_h_lean, "bytes_per_cell": lean_h,
-                            "achieved": lean_h * cells_rank / (ms_h_lean * 1e-3) / 1e9,
-                            "frac": lean_h * cells_rank / (ms_h_lean * 1e-3) / 1e9 / peak},
-                "e_phase": {"ms_per_launch": ms_e_lean, "bytes_per_cell": lean_e,
-                            "achieved": lean_e * cells_rank / (ms_e_lean * 1e-3) / 1e9,
-                            "frac": lean_e * cells_rank / (ms_e_lean * 1e-3) / 1e9 / peak}}
+                "moved_bytes_per_cell_update": b_lean, "moved": b_lean * (v_lean / world),
+                "moved_frac": b_lean * (v_lean / world) / peak}
+            if ms_lean_kernel:
+                ach = b_lean * cells_rank / (ms_lean_kernel * 1e-3) / 1e9
+                line["lean_interior"]["kernel"] = {"ms_per_launch": ms_lean_kernel, "achieved": ach, "frac": ach / peak}
+        if dense is not None:
+            ms_dense, ms_dense_kernel, frac = dense
+            v_dense = cells * K / (ms_dense * 1e-3) / 1e9
+            line["dense"] = {"value": v_dense, "unit": "Gcell-updates/s", "ms_per_step": ms_dense / K,
+                             "material_cell_fraction": frac, "ratio_to_value": v_dense / value,
+                             "structure": "8 x 8-cell dielectric blocks (eps 2.56) on %.0f %% of the grid; every "
+                                          "material cell divides by eps and evaluates the pulse's exp / sincos each "
+                                          "step (field.c:224-256)" % (100 * frac)}
+            if ms_dense_kernel:
+                ach = by["one_pass"] * cells_rank / (ms_dense_kernel * 1e-3) / 1e9
+                line["dense"]["roofline"] = {"ms_per_launch": ms_dense_kernel, "achieved": ach, "frac": ach / peak,
+                                             "algorithmic_bytes_per_cell": by["one_pass"]}
         emit(json.dumps(line))
-    run.close()
+    if run is not None:
+        run.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def plugin_leg(B, args, K):
+    """The reference-facing call sequence itself, timed with the host clock: simulator_init (host
+    permittivity build + uploads + NTFF plan: `init_s`), K x simulator_calc (deferred CUDA-graph
+    replay), the borrowed-pointer getter (D2H into the pinned mirror) and simulator_finish (NTFF
+    projection, spectrum, the two far-field files).  Size: the largest square grid whose init stays
+    within a few seconds of host work."""
+    import numpy as np
+    n = args.plugin_n
+    cwd = os.getcwd()
+    work = tempfile.mkdtemp(prefix="bench_plugin_")
+    os.chdir(work)
+    try:
+        L = B.lib()
+        t0 = time.perf_counter()
+        gpu = B.Plugin(args.model, args.solver, n, n, steps=K + 3, h_u_nm=10)
+        gpu.sync()
+        init_s = time.perf_counter() - t0
+        gpu.step(3)
+        gpu.sync()
+        t1 = time.perf_counter()
+        gpu.step(K)
+        getter = "fdtdTM_upml_getEz" if args.solver == "TM_UPML_2D" else "fdtdTE_upml_getEx"
+        ptr = getattr(L, getter)()
+        t2 = time.perf_counter()
+        peak = float(np.abs(np.frombuffer((ctypes.c_double * 64).from_address(ptr), dtype=np.float64)).max())
+        gpu.finish()
+        t3 = time.perf_counter()
+        return {"value": n * n * K / (t2 - t1) / 1e9, "unit": "Gcell-updates/s",
+                "grid": "%d x %d" % (n, n), "steps": K,
+                "init_s": init_s, "calc_plus_getter_s": t2 - t1, "finish_s": t3 - t2,
+                "value_including_finish": n * n * K / (t3 - t1) / 1e9,
+                "d2h_bytes_per_step": n * n * 16 / K,
+                "path": "simulator_init | timed: K x simulator_calc + %s() (pinned mirror) | simulator_finish "
+                        "(projection, spectrum, .txt + .dat)" % getter,
+                "first_values_abs_max": peak}
+    finally:
+        os.chdir(cwd)
 
 
 _json_out = None
@@ -548,7 +750,7 @@ def emit(text):
 
 def quiet_stdout():
     """stdout carries the JSON line only: whatever libraries print to fd 1 during the run (the NCCL
-    version banner, ...) goes to stderr instead."""
+    version banner, the plugin's own printf()s, ...) goes to stderr instead."""
     global _json_out
     sys.stdout.flush()
     _json_out = os.dup(1)
@@ -563,8 +765,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", "--size", dest="n", type=int, default=N_PER_GPU,
                     help="cells per side per GPU (use --size under torchrun, whose own parser trips over --n)")
-    ap.add_argument("--cpu-n", type=int, default=1024, help="grid side of the CPU sample")
-    ap.add_argument("--cpu-steps", type=int, default=10)
+    ap.add_argument("--cpu-n", type=int, default=2048, help="grid side of the CPU sample (one instance per core)")
+    ap.add_argument("--cpu-steps", type=int, default=6)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--halo", default="peer", choices=["peer", "nccl"],
                     help="multi-GPU halo transport: direct NVLink peer stores (default) or NCCL send/recv")
@@ -580,6 +782,11 @@ def main():
                     help="measure the whole line in the opt-in lean-interior form (tolerance form, not the "
                          "bit-exact default)")
     ap.add_argument("--no-lean-leg", action="store_true", help="skip the extra lean_interior measurement")
+    ap.add_argument("--fill", type=float, default=0.35,
+                    help="material-cell fraction of the extra `dense` measurement (0 = skip)")
+    ap.add_argument("--no-parity-check", action="store_true", help="N > 1: skip the bit-identity check")
+    ap.add_argument("--no-plugin-leg", action="store_true", help="N = 1: skip the e2e_plugin measurement")
+    ap.add_argument("--plugin-n", type=int, default=4096, help="grid side of the e2e_plugin leg")
     ap.add_argument("--solver", default="TM_UPML_2D", choices=["TM_UPML_2D", "TE_UPML_2D"],
                     help="TM_UPML_2D is the BASELINE workload; TE_UPML_2D is reported for information")
     args = ap.parse_args()
