@@ -250,6 +250,19 @@ typedef struct MpifdtdConfig {
  * success; on a missing file or a short file prints and exit(2)s like the
  * reference's readConfig (main.c:319-366, commented out upstream). */
 extern int mpifdtd_readConfig(const char *path, MpifdtdConfig *out);
+/* initConfigFromText (main.c:368-394): rank 0 reads config.txt, prints the FieldSetting banner and
+ * sends the struct -- sizeof(MpifdtdConfig)/sizeof(int) ints, as upstream's MPI_Send of MPI_INTs --
+ * to every other rank, which receive it from rank 0.  The transport is the caller's (thin wrappers
+ * of MPI_Send / MPI_Recv, or any other message layer); with send == recv == NULL a built-in one
+ * for ranks on one node: a file under /dev/shm keyed by MPIFDTD_JOB_ID (default: the launcher's
+ * pid), published atomically by rank 0 and polled by the others (MPIFDTD_BCAST_TIMEOUT_S, default
+ * 120).  Callbacks return 0 on success.  Errors: message + exit(2).  mpifdtd_configBroadcastDone()
+ * removes the published file (rank 0, once everybody has read). */
+typedef int (*mpifdtd_send_ints)(const int *buf, int count, int dest, void *ctx);
+typedef int (*mpifdtd_recv_ints)(int *buf, int count, int src, void *ctx);
+extern int mpifdtd_initConfigFromText(const char *path, int rank, int n_ranks, MpifdtdConfig *cfg,
+                                      mpifdtd_send_ints send, mpifdtd_recv_ints recv, void *ctx);
+extern void mpifdtd_configBroadcastDone(void);
 
 /* ---- small utilities main.c / drawer.c pull in (function.h, myComplex.h) -- */
 extern double *newDouble(int size);

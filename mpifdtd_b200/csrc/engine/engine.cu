@@ -251,6 +251,23 @@ int b200fdtd_create(const b200fdtd_grid *grid, b200fdtd_engine **out)
     b200fdtd_destroy(e);
     return b200_fail(B200FDTD_ERR_CUDA, "initial memset failed");
   }
+  // The kernels replace x / mu0 by a reciprocal multiply with one FMA correction (div_const,
+  // upml_common.cuh), bit-identical to IEEE division for the reference's MU_0_S (2^31 operands in
+  // tests/test_gpu_fused.py).  The identity is a property of the divisor: a caller-supplied mu0 is
+  // checked once per distinct value here, and an engine whose divisor breaks it is refused.
+  if (kind_is_upml(grid->kind) && !e->fp32) {
+    static double checked_mu0 = 0.0;
+    if (grid->mu0 != checked_mu0) {
+      unsigned long long bad = 0;
+      rc = (grid->mu0 > 0.0) ? b200_selftest_division(grid->mu0, 1ull << 22, &bad) : B200FDTD_ERR_ARG;
+      if (rc || bad) {
+        b200fdtd_destroy(e);
+        return b200_fail(rc ? rc : B200FDTD_ERR_STATE, "mu0 = %.17g: the exact-division shortcut disagrees with IEEE "
+                         "division for %llu of 2^22 operands", grid->mu0, bad);
+      }
+      checked_mu0 = grid->mu0;
+    }
+  }
   *out = e;
   return B200FDTD_OK;
 }

@@ -45,3 +45,97 @@ int mpifdtd_readConfig(const char *path, MpifdtdConfig *out)
   out->field_info.angle_deg = out->startAngle;
   return 0;
 }
+
+/* ---- initConfigFromText (main.c:368-394, commented out upstream) -----------------------------
+ * "It would be bad if everybody read the file at once, so only rank 0 reads and then the config
+ * is synchronised": rank 0 parses config.txt, prints the FieldSetting banner and sends the struct
+ * -- all ints -- to every other rank; the others receive it.  Upstream's transport is
+ * MPI_Send / MPI_Recv of sizeof(Config)/sizeof(int) MPI_INTs with tag 1.  Here the transport is a
+ * pair of callbacks (an MPI build passes thin wrappers of MPI_Send / MPI_Recv; the Python harness
+ * passes torch.distributed send / recv), and with send == recv == NULL a built-in one for
+ * processes on ONE node that were started without any message layer (one `mpifdtd_sweep` per GPU
+ * with RANK / WORLD_SIZE in the environment): rank 0 publishes the ints in a file under /dev/shm
+ * (written under a temporary name, then renamed: readers never see a partial file), the other
+ * ranks poll for it.  The file is keyed by MPIFDTD_JOB_ID, or by the parent process id when that
+ * is not set (ranks started by one launcher share it). */
+#include <errno.h>
+#include <sys/stat.h>
+#include <time.h>
+#include <unistd.h>
+
+#define CONFIG_INTS ((int)(sizeof(MpifdtdConfig) / sizeof(int)))
+
+static void bcast_path(char *dst, size_t n)
+{
+  const char *job = getenv("MPIFDTD_JOB_ID");
+  if (job != NULL && job[0] != '\0') snprintf(dst, n, "/dev/shm/mpifdtd_config_%s", job);
+  else snprintf(dst, n, "/dev/shm/mpifdtd_config_ppid%ld", (long)getppid());
+}
+
+static void print_banner(const MpifdtdConfig *c)                 /* main.c:373-381 */
+{
+  printf("===========FieldSetting=======\n");
+  printf("fieldSize(nm) = (%d, %d) \nh_u = %d \npml = %d\n", c->field_info.width_nm, c->field_info.height_nm,
+         c->field_info.h_u_nm, c->field_info.pml);
+  printf("lambda(nm) = %d  \nstep = %d\n", c->field_info.lambda_nm, c->field_info.stepNum);
+  printf("angle = %d .. %d (delta = %d)\n", c->startAngle, c->endAngle, c->deltaAngle);
+  printf("==============================\n");
+}
+
+int mpifdtd_initConfigFromText(const char *path, int rank, int n_ranks, MpifdtdConfig *cfg,
+                               mpifdtd_send_ints send, mpifdtd_recv_ints recv, void *ctx)
+{
+  if (cfg == NULL || rank < 0 || n_ranks < 1 || rank >= n_ranks || (send == NULL) != (recv == NULL)) {
+    printf("mpifdtd_initConfigFromText: bad rank %d of %d or half a transport\n", rank, n_ranks);
+    exit(2);
+  }
+  char shm[256];
+  bcast_path(shm, sizeof shm);
+  if (rank == 0) {
+    mpifdtd_readConfig(path, cfg);                                /* exit(2) on a missing / short file */
+    print_banner(cfg);
+    if (send != NULL) {
+      for (int i = 1; i < n_ranks; i++)
+        if (send((const int *)cfg, CONFIG_INTS, i, ctx) != 0) { printf("config broadcast: send to rank %d failed\n", i); exit(2); }
+    } else if (n_ranks > 1) {
+      char tmp[300];
+      snprintf(tmp, sizeof tmp, "%s.tmp%ld", shm, (long)getpid());
+      FILE *fp = fopen(tmp, "wb");
+      if (fp == NULL || fwrite(cfg, sizeof(int), CONFIG_INTS, fp) != (size_t)CONFIG_INTS || fclose(fp) != 0 ||
+          rename(tmp, shm) != 0) {
+        printf("config broadcast: cannot publish %s\n", shm);
+        exit(2);
+      }
+    }
+    return 0;
+  }
+  if (recv != NULL) {
+    if (recv((int *)cfg, CONFIG_INTS, 0, ctx) != 0) { printf("config broadcast: receive from rank 0 failed\n"); exit(2); }
+    return 0;
+  }
+  double waited = 0, limit = 120;
+  if (getenv("MPIFDTD_BCAST_TIMEOUT_S") != NULL) limit = atof(getenv("MPIFDTD_BCAST_TIMEOUT_S"));
+  const time_t not_before = time(NULL) - 120;           /* a leftover of an earlier job under the same key is not ours */
+  for (;;) {
+    struct stat st;
+    FILE *fp = (stat(shm, &st) == 0 && st.st_mtime >= not_before) ? fopen(shm, "rb") : NULL;
+    if (fp != NULL) {
+      size_t got = fread(cfg, sizeof(int), CONFIG_INTS, fp);
+      fclose(fp);
+      if (got == (size_t)CONFIG_INTS) return 0;
+    }
+    if (waited >= limit) { printf("config broadcast: rank 0 never published %s\n", shm); exit(2); }
+    struct timespec ts = { 0, 20 * 1000 * 1000 };
+    nanosleep(&ts, NULL);
+    waited += 0.02;
+  }
+}
+
+/* rank 0 removes the published file once every rank has its copy (after the job's first barrier,
+ * or at exit); harmless when nothing was published */
+void mpifdtd_configBroadcastDone(void)
+{
+  char shm[256];
+  bcast_path(shm, sizeof shm);
+  unlink(shm);
+}

@@ -14,7 +14,8 @@
  * initParameter() with MIE_CYLINDER / TM_UPML_2D.  Several GPUs: start one process per GPU
  * with RANK / WORLD_SIZE (or OMPI_COMM_WORLD_RANK / _SIZE) set and CUDA_VISIBLE_DEVICES
  * selecting the device; rank r takes angles start + r*delta, step delta*world -- the
- * reference's rank striding (main.c:126-138).  Errors: message + exit(2), as everywhere.
+ * reference's rank striding (main.c:126-138) -- and only rank 0 opens config.txt: the others
+ * receive the struct from it (initConfigFromText, main.c:368-394).  Errors: message + exit(2), as everywhere.
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -59,8 +60,11 @@ int main(int argc, char **argv)
     if (strcmp(argv[a], "--max-batch") == 0 && a + 1 < argc) max_batch = atoi(argv[++a]);
     else config_path = argv[a];
   }
+  const int rank = env_int("RANK", "OMPI_COMM_WORLD_RANK", 0);
+  const int world = env_int("WORLD_SIZE", "OMPI_COMM_WORLD_SIZE", 1);
   if (config_path != NULL) {
-    mpifdtd_readConfig(config_path, &cfg);             /* exits 2 on a missing / short file */
+    /* main.c:368-394: only rank 0 reads the file, the others get the struct from it */
+    mpifdtd_initConfigFromText(config_path, rank, world, &cfg, NULL, NULL, NULL);
     have_config = 1;
   } else {                                             /* initParameter(), main.c:90-108 */
     memset(&cfg, 0, sizeof cfg);
@@ -72,8 +76,6 @@ int main(int argc, char **argv)
     cfg.ModelType = MIE_CYLINDER;
     cfg.SolverType = TM_UPML_2D;
   }
-  const int rank = env_int("RANK", "OMPI_COMM_WORLD_RANK", 0);
-  const int world = env_int("WORLD_SIZE", "OMPI_COMM_WORLD_SIZE", 1);
   if (world < 1 || rank < 0 || rank >= world || cfg.deltaAngle <= 0) {
     printf("mpifdtd_sweep: bad rank %d of %d or angle step %d\n", rank, world, cfg.deltaAngle);
     exit(2);

@@ -69,6 +69,10 @@ class SlabRun:
         self.L.models_initModel()
         self.j0, self.nj = split_columns(n_py, world, rank)
         self.engine = B.Engine(self.kind, n_px, n_py, pml, self.j0, self.nj, device, precision=precision)
+        if comm is not None and hasattr(comm, "torch") and str(getattr(comm, "device", "")).startswith("cuda"):
+            # NCCL send/recv runs on torch's current stream: the engine's pack / unpack kernels must be
+            # ordered with it, so the engine launches there too
+            self.engine.set_stream(comm.torch.cuda.current_stream().cuda_stream)
 
         ti = np.empty((B.UPML_TABS, n_px))
         tj = np.empty((B.UPML_TABS, n_py))
@@ -190,6 +194,8 @@ class TorchHaloComm:
         return out
 
     def exchange(self, send_ptr, recv_ptr, n_complex, send_to, recv_from):
+        """send_ptr / recv_ptr are this object's own buffers (pointers()); kept in the signature so other
+        communicators (the gloo protocol test) can take raw pointers"""
         dist = self.dist
         ops = []
         if send_to is not None:
