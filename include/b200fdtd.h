@@ -446,6 +446,9 @@ int b200fdtd_get_step_form(b200fdtd_engine *e, int32_t *form);
  * correctly rounded quotient.  Counts disagreements with IEEE division over `samples`
  * pseudo-random operands (raw bit patterns and field-like magnitudes); must be 0. */
 int b200fdtd_selftest_division(double divisor, uint64_t samples, uint64_t *mismatches);
+/* divisor == 0: the per-cell division by the permittivity instead -- every sample its own divisor
+ * (random significands, short decimals, all-ones significands, 2^-4 .. 2^8), through the reciprocal
+ * + two correction steps the material cells use (div_eps, upml_common.cuh); must be 0 as well. */
 
 /* ---- introspection -------------------------------------------------------- */
 /* kernels launched by this engine since creation (bench.py's gpu_launches) */

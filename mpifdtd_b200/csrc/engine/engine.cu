@@ -1187,7 +1187,7 @@ int b200fdtd_ntff_spectrum(b200fdtd_engine *e, const b200fdtd_spectrum_args *arg
 
 int b200fdtd_selftest_division(double divisor, uint64_t samples, uint64_t *mismatches)
 {
-  if (!mismatches || !(divisor > 0.0)) return b200_fail(B200FDTD_ERR_ARG, "bad argument");
+  if (!mismatches || !(divisor >= 0.0)) return b200_fail(B200FDTD_ERR_ARG, "bad argument");
   unsigned long long bad = 0;
   int rc = b200_selftest_division(divisor, samples, &bad);
   *mismatches = bad;

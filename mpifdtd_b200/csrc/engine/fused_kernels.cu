@@ -328,11 +328,48 @@ enum { ROW_GENERAL = 0, ROW_UNIT = 1, ROW_LEAN = 2 };
 
 // rare work of the hot loops, out of line: material cells (division by eps, the pulse's exp / sincos)
 // and the opt-in point source
-static __device__ __noinline__ double2 tm_material_cell(const UpmlView *v, int r, int c, size_t k, double eps, double2 dz)
+// true: pulse m adds a signed zero (or nothing) to cell (i, j) this step -- see pulse_add()
+__device__ __forceinline__ bool pulse_is_far(const UpmlView &v, int m, int i, int j)
 {
-  double2 ez = div_eps(dz, eps);
+  const b200fdtd_pulse *p = &v.pulse[m];
+  double tm0 = p->time_minus_t0;
+  if (v.batch != nullptr) {
+    p = &v.batch[0].pulse[m];
+    tm0 = (v.time_ptr != nullptr ? *v.time_ptr : v.time) - v.batch[0].t0[m];
+  }
+  if (!p->enabled) return true;
+  const double r = ((i + p->gap_x) * p->cos_per_c + (j + p->gap_y) * p->sin_per_c) - tm0;
+  return fabs(r) > 28.3 * p->beam_width;
+}
+static __device__ __noinline__ double2 tm_pulse_cell(const UpmlView *v, int r, int c, double eps, double2 ez)
+{
   const b200fdtd_pulse pulse = onepass_pulse(*v, 0);
-  if (pulse.enabled && eps != 1.0) ez = ez + pulse_term(pulse, r - 1, v->j_base + c, eps);
+  if (pulse.enabled) ez = pulse_add(ez, pulse, r - 1, v->j_base + c, eps);
+  return ez;
+}
+// material cell of a hot loop: the division inline (a reciprocal and six FMAs per component pair),
+// the pulse's exp / sincos out of line and only where the pulse is
+// A lane marches down one column, where consecutive cells mostly share their permittivity: the
+// reciprocal of the last one is kept (inv == 0: a permittivity outside the plain range, IEEE path).
+struct EpsCache { double eps, inv; };
+__device__ __forceinline__ double2 div_eps_cached(double2 z, double eps, EpsCache &cache)
+{
+  if (eps != cache.eps) {
+    cache.eps = eps;
+    cache.inv = eps_is_plain(eps) ? __drcp_rn(eps) : 0.0;
+  }
+  if (cache.inv != 0.0) return div_eps(z, eps, cache.inv);
+  return make_double2(ieee_div(z.x, eps), ieee_div(z.y, eps));
+}
+__device__ __forceinline__ double2 tm_material_cell(const UpmlView *v, int r, int c, size_t k, double eps, double2 dz,
+                                                    EpsCache &cache)
+{
+  double2 ez = dz;
+  if (eps != 1.0) {
+    ez = div_eps_cached(dz, eps, cache);
+    if (!pulse_is_far(*v, 0, r - 1, v->j_base + c) || neg_zero(ez.x) || neg_zero(ez.y))
+      ez = tm_pulse_cell(v, r, c, eps, ez);
+  }
   if ((long long)k == v->point_k) ez = ez + make_double2(v->point_re, v->point_im);
   return ez;
 }
@@ -370,6 +407,7 @@ __device__ __forceinline__ void tm_consume(const OnePassView &f, const Tile &T, 
 
   b200fdtd_pulse pulse;
   if (MODE == ROW_GENERAL) pulse = onepass_pulse(v, 0);
+  EpsCache eps_cache = { 1.0, 1.0 };
   size_t k = (size_t)r0 * v.pitch + c;
   // new B of the previous row (by_prev) and, for exact cells, its quotient by mu0 (hy_prev)
   double2 by_prev = zero, hy_prev = zero;
@@ -480,11 +518,11 @@ __device__ __forceinline__ void tm_consume(const OnePassView &f, const Tile &T, 
       if (MODE == ROW_GENERAL) {
         ez = div_eps(dz, eps);
         if (pulse.enabled && eps != 1.0)
-          ez = ez + pulse_term(pulse, r - 1, v.j_base + c, eps);
+          ez = pulse_add(ez, pulse, r - 1, v.j_base + c, eps);
         if ((long long)k == v.point_k)
           ez = ez + make_double2(v.point_re, v.point_im);
       } else if (eps != 1.0 || (long long)k == v.point_k) {
-        ez = tm_material_cell(&v, r, c, k, eps, dz);
+        ez = tm_material_cell(&v, r, c, k, eps, dz, eps_cache);
       }
       if (!(LEAN && lean_cell)) {
         v.f[B200FDTD_TM_MX][k] = mx;
@@ -586,13 +624,27 @@ __global__ void __launch_bounds__(32 * (WARPS + 1), 1) tm_onepass_kernel(const _
 // slots: 0 Ex 1 Jx 2 Dx 3 Ey 4 Jy 5 Dy 6 Hz 7 Mz 8 Bz.  Hz(i,j) needs Ey(i+1,j) (next row: carried like
 // TM's Ez) and Ex(i,j+1) (right lane: staged per row); Ex(i,j) needs the new Hz(i,j-1) (left lane),
 // Ey(i,j) the new Hz(i-1,j) (previous row, carried).  fdtdTE_upml.c:252-314.
-static __device__ __noinline__ void te_material_cell(const UpmlView *v, int r, int c, size_t k, double eps_x, double eps_y,
-                                                     double2 dx, double2 dy, double2 *ex_out, double2 *ey_out)
+static __device__ __noinline__ double2 te_pulse_cell(const UpmlView *v, int m, int r, int c, double eps, double2 e)
 {
-  double2 ex = div_eps(dx, eps_x), ey = div_eps(dy, eps_y);
-  const b200fdtd_pulse pulse_x = onepass_pulse(*v, 0), pulse_y = onepass_pulse(*v, 1);
-  if (pulse_x.enabled && eps_x != 1.0) ex = ex + pulse_term(pulse_x, r - 1, v->j_base + c, eps_x);
-  if (pulse_y.enabled && eps_y != 1.0) ey = ey + pulse_term(pulse_y, r - 1, v->j_base + c, eps_y);
+  const b200fdtd_pulse pulse = onepass_pulse(*v, m);
+  if (pulse.enabled) e = pulse_add(e, pulse, r - 1, v->j_base + c, eps);
+  return e;
+}
+__device__ __forceinline__ void te_material_cell(const UpmlView *v, int r, int c, size_t k, double eps_x, double eps_y,
+                                                 double2 dx, double2 dy, double2 *ex_out, double2 *ey_out,
+                                                 EpsCache &cache_x, EpsCache &cache_y)
+{
+  double2 ex = dx, ey = dy;
+  if (eps_x != 1.0) {
+    ex = div_eps_cached(dx, eps_x, cache_x);
+    if (!pulse_is_far(*v, 0, r - 1, v->j_base + c) || neg_zero(ex.x) || neg_zero(ex.y))
+      ex = te_pulse_cell(v, 0, r, c, eps_x, ex);
+  }
+  if (eps_y != 1.0) {
+    ey = div_eps_cached(dy, eps_y, cache_y);
+    if (!pulse_is_far(*v, 1, r - 1, v->j_base + c) || neg_zero(ey.x) || neg_zero(ey.y))
+      ey = te_pulse_cell(v, 1, r, c, eps_y, ey);
+  }
   if ((long long)k == v->point_k) ex = ex + make_double2(v->point_re, v->point_im);
   *ex_out = ex;
   *ey_out = ey;
@@ -632,6 +684,7 @@ __device__ __forceinline__ void te_consume(const OnePassView &f, const Tile &T, 
 
   b200fdtd_pulse pulse_x, pulse_y;
   if (MODE == ROW_GENERAL) { pulse_x = onepass_pulse(v, 0); pulse_y = onepass_pulse(v, 1); }
+  EpsCache eps_cache_x = { 1.0, 1.0 }, eps_cache_y = { 1.0, 1.0 };
   size_t k = (size_t)r0 * v.pitch + c;
   double2 bz_prev = zero, hz_prev = zero;                 // new Bz(r-1, c) and its quotient by mu0
   if (active) {
@@ -736,11 +789,11 @@ __device__ __forceinline__ void te_consume(const OnePassView &f, const Tile &T, 
       double2 ex = dx, ey = dy;
       if (MODE == ROW_GENERAL) {
         ex = div_eps(dx, eps_x); ey = div_eps(dy, eps_y);
-        if (pulse_x.enabled && eps_x != 1.0) ex = ex + pulse_term(pulse_x, r - 1, v.j_base + c, eps_x);
-        if (pulse_y.enabled && eps_y != 1.0) ey = ey + pulse_term(pulse_y, r - 1, v.j_base + c, eps_y);
+        if (pulse_x.enabled && eps_x != 1.0) ex = pulse_add(ex, pulse_x, r - 1, v.j_base + c, eps_x);
+        if (pulse_y.enabled && eps_y != 1.0) ey = pulse_add(ey, pulse_y, r - 1, v.j_base + c, eps_y);
         if ((long long)k == v.point_k) ex = ex + make_double2(v.point_re, v.point_im);
       } else if (eps_x != 1.0 || eps_y != 1.0 || (long long)k == v.point_k) {
-        te_material_cell(&v, r, c, k, eps_x, eps_y, dx, dy, &ex, &ey);
+        te_material_cell(&v, r, c, k, eps_x, eps_y, dx, dy, &ex, &ey, eps_cache_x, eps_cache_y);
       }
       if (!(LEAN && lean_cell)) {
         v.f[B200FDTD_TE_MZ][k] = mz;

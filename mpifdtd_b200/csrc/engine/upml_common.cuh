@@ -115,10 +115,42 @@ __device__ __forceinline__ double quotient_or_one(double num, double den)
   if (num != den) q = ieee_div(num, den);
   return q;
 }
-// z / eps where eps is usually exactly 1 (vacuum)
+// x / d for an ARBITRARY divisor (a cell's permittivity), exactly, given y = RN(1/d) -- which the
+// caller forms once per cell with the correctly rounded reciprocal __drcp_rn and shares between the
+// two components and the source term's 1/eps.  Two Markstein steps: q0 = RN(x*y) is within 1.5 ulp
+// of x/d, the first correction makes it faithful (its error before rounding is ~1e-16 ulp), and from
+// a faithful quotient the second is the correctly rounded one (Markstein 1990, Cornea et al.); a
+// zero residual means the quotient is already exact (and keeps the sign of a zero).  Operands whose
+// products could leave the normal range take the IEEE path, as in div_const.  Checked against `/`
+// on the device over 2^31 random (x, d) pairs: b200fdtd_selftest_division with divisor 0.
+__device__ __forceinline__ double div_exact(double x, double d, double y)
+{
+  const double q0 = x * y;
+  const double r0 = fma(-q0, d, x);
+  double res = q0;
+  if (r0 != 0.0) {
+    const double q1 = fma(r0, y, q0);
+    const double r1 = fma(-q1, d, x);
+    res = (r1 == 0.0) ? q1 : fma(r1, y, q1);
+  }
+  const unsigned hi = (unsigned)__double2hiint(x) & 0x7fffffffu;
+  const bool exotic = (hi - 0x05d00000u) >= (0x7a100000u - 0x05d00000u);
+  if (exotic && x != 0.0) res = ieee_div(x, d);
+  return res;
+}
+// z / eps where eps is usually exactly 1 (vacuum); material cells: permittivities are O(1..100),
+// anything outside [2^-20, 2^20] goes through the IEEE division
+__device__ __forceinline__ double2 div_eps(double2 z, double eps, double inv_eps)
+{
+  return make_double2(div_exact(z.x, eps, inv_eps), div_exact(z.y, eps, inv_eps));
+}
+__device__ __forceinline__ bool eps_is_plain(double eps) { return eps > 9.5367431640625e-07 && eps < 1048576.0; }
 __device__ __forceinline__ double2 div_eps(double2 z, double eps)
 {
-  if (eps != 1.0) z = make_double2(ieee_div(z.x, eps), ieee_div(z.y, eps));
+  if (eps != 1.0) {
+    if (eps_is_plain(eps)) z = div_eps(z, eps, __drcp_rn(eps));
+    else z = make_double2(ieee_div(z.x, eps), ieee_div(z.y, eps));
+  }
   return z;
 }
 
@@ -145,6 +177,21 @@ __device__ __forceinline__ double2 pulse_term(const b200fdtd_pulse &s, int i, in
   double sn, cs;
   sincos(r * s.omega, &sn, &cs);
   return make_double2(amp * cs, amp * sn);
+}
+
+// Adding the pulse to a field component, with the shortcut the pulse's own shape offers:
+// exp(-(r/w)^2) is EXACTLY +0 once |r| > 28.3 w (the true value lies below half the smallest
+// subnormal), the term is then a signed zero, and x + (+-0) == x for every x except x == -0.  So far
+// from the pulse -- most material cells at any given step -- the exp, the sincos and the 1/eps are
+// skipped and the bits stay what field.c:248-253 produces; a component that IS -0 takes the full path.
+__device__ __forceinline__ bool neg_zero(double v) { return __double_as_longlong(v) == (long long)0x8000000000000000ull; }
+__device__ __forceinline__ bool neg_zero(float v) { return __float_as_int(v) == (int)0x80000000u; }
+template <typename C>
+__device__ __forceinline__ C pulse_add(C e, const b200fdtd_pulse &s, int i, int j, double eps)
+{
+  const double r = ((i + s.gap_x) * s.cos_per_c + (j + s.gap_y) * s.sin_per_c) - s.time_minus_t0;
+  if (fabs(r) > 28.3 * s.beam_width && !neg_zero(e.x) && !neg_zero(e.y)) return e;
+  return add_source(e, pulse_term(s, i, j, eps));
 }
 
 // The pulse of source slot m for this block's simulation: the step's own parameters, or -- in a

@@ -96,7 +96,7 @@ template <typename T, typename C = typename Cx<T>::type>
 __device__ __forceinline__ void tm_e_sources(const UpmlViewT<T> &v, int r, int c, size_t k0, T eps, C &ez)
 {
   if (eps != (T)1 && pulse_on(v, 0))       // field.c:248
-    ez = add_source(ez, pulse_term(pulse_of(v, 0), r - 1, v.j_base + c, (double)eps));
+    ez = pulse_add(ez, pulse_of(v, 0), r - 1, v.j_base + c, (double)eps);
   if (v.cw[0].enabled && eps != (T)1)          // mpiTM_UPML.c:370
     ez = add_source(ez, cw_eps_term(v.cw[0], r - 1, v.j_base + c, (double)eps));
   if ((long long)k0 == v.point_k)
@@ -161,9 +161,9 @@ __device__ __forceinline__ void te_e_sources(const UpmlViewT<T> &v, int r, int c
 {
   const int i = r - 1, j = v.j_base + c;
   if (eps_x != (T)1 && pulse_on(v, 0))     // fdtdTE_upml.c:186-187
-    ex = add_source(ex, pulse_term(pulse_of(v, 0), i, j, (double)eps_x));
+    ex = pulse_add(ex, pulse_of(v, 0), i, j, (double)eps_x);
   if (eps_y != (T)1 && pulse_on(v, 1))     // fdtdTE_upml.c:188-189
-    ey = add_source(ey, pulse_term(pulse_of(v, 1), i, j, (double)eps_y));
+    ey = pulse_add(ey, pulse_of(v, 1), i, j, (double)eps_y);
   if (v.cw[0].enabled && eps_x != (T)1) ex = add_source(ex, cw_eps_term(v.cw[0], i, j, (double)eps_x));
   if (v.cw[1].enabled && eps_y != (T)1) ey = add_source(ey, cw_eps_term(v.cw[1], i, j, (double)eps_y));   // mpiTE_UPML.c:278
   if ((long long)k0 == v.point_k)
@@ -761,6 +761,7 @@ __global__ void division_selftest_kernel(unsigned long long seed, unsigned long 
                                          unsigned long long *mismatches)
 {
   ConstDivisor c; c.d = d; c.r = 1.0 / d;
+  const bool any_divisor = d == 0.0;     // every sample its own divisor, through div_eps (permittivity-like values)
   unsigned long long x = seed + 0x9E3779B97F4A7C15ull * (blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x + 1);
   unsigned long long bad = 0;
   for (unsigned long long n = 0; n < per_thread; n++) {
@@ -768,6 +769,21 @@ __global__ void division_selftest_kernel(unsigned long long seed, unsigned long 
     // alternate between raw bit patterns (all exponents, subnormals, inf/nan) and field-like magnitudes
     double v = (n & 1) ? __longlong_as_double((long long)x)
                        : ((double)(long long)x) * ((n & 2) ? 1.0e-19 : 1.0e-31);
+    if (any_divisor) {
+      unsigned long long y = x * 0x2545F4914F6CDD1Dull;
+      // a random 52-bit significand in [1, 2), scaled into [2^-4, 2^8): 1.0 itself, all-ones
+      // significands and short decimals like 2.56 are among the patterns
+      double dd = __longlong_as_double((long long)((y >> 12) | 0x3ff0000000000000ull));
+      if ((n & 12) == 4) dd = 1.0 + (double)((y >> 40) % 2000) * 0.01;
+      if ((n & 12) == 8) dd = __longlong_as_double((long long)(0x3fffffffffffffffull - ((y >> 58) & 7)));
+      dd = ldexp(dd, (int)((y >> 3) % 12) - 4);
+      const double2 got2 = div_eps(make_double2(v, -v), dd);
+      const double want = v / dd, want2 = (-v) / dd;
+      const bool ok = ((__double_as_longlong(want) == __double_as_longlong(got2.x)) || (want != want && got2.x != got2.x)) &&
+                      ((__double_as_longlong(want2) == __double_as_longlong(got2.y)) || (want2 != want2 && got2.y != got2.y));
+      if (!ok) bad++;
+      continue;
+    }
     const double want = v / d, got = div_const(v, c);
     const bool same = (__double_as_longlong(want) == __double_as_longlong(got)) || (want != want && got != got);
     if (!same) bad++;

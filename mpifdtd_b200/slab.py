@@ -96,7 +96,9 @@ class SlabRun:
             ptr = self.L.mpifdtd_ntff_time_shift(C.byref(self.box), 360,
                                                  0.0 if self.kind == 2 else 0.5, self.j0, self.nj)
             n_points = self.L.mpifdtd_ntff_point_count(C.byref(self.box))
-            self.engine.n_bins = steps if n_bins is None else n_bins
+            # bins kept: the first `steps` (all the far field reads, ntffTM.c:181), a number, or "full" =
+            # the reference's whole arraySize (every tap of a short run lands somewhere)
+            self.engine.n_bins = steps if n_bins is None else (self.box.arraySize if n_bins == "full" else n_bins)
             plan = B.NtffPlan(self.box.top, self.box.bottom, self.box.left, self.box.right,
                               n_points, n_local, steps, self.engine.n_bins, 360,
                               self.box.arraySize, ptr)

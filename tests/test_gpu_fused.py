@@ -154,6 +154,14 @@ def test_launches_per_step(plugin_lib, in_tmp_cwd, monkeypatch):
     gpu.finish()
 
 
+def test_permittivity_division_is_exactly_ieee(plugin_lib):
+    """div_eps(z, eps) -- correctly rounded reciprocal + two Markstein corrections, one reciprocal
+    per cell -- must equal z / eps bit for bit: 2^31 operand pairs with a fresh divisor each."""
+    bad = C.c_uint64(123)
+    B.check(plugin_lib.b200fdtd_selftest_division(0.0, 1 << 31, C.byref(bad)), "selftest")
+    assert bad.value == 0
+
+
 @pytest.mark.parametrize("divisor", [B.MU_0_S, 2.56, 1.0 / 3.0, 1.5625, 15.069924])
 def test_constant_division_shortcut_is_exactly_ieee(plugin_lib, divisor):
     """div_const(x, d) must equal x / d bit for bit (upml_common.cuh): 2^31 operands per

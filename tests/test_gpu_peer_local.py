@@ -21,4 +21,16 @@ def test_slabs_with_peer_halos_match_single_engine(solver, world, form):
            str(world), form, "spread"]
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
-    assert "PEER_LOCAL_CHECK %s %s world %d spread OK" % (solver, form, world) in p.stdout
+    assert "PEER_LOCAL_CHECK %s %s world %d spread model OK" % (solver, form, world) in p.stdout
+
+
+@pytest.mark.parametrize("solver,world,form", [("TM_UPML_2D", 4, "fused"), ("TE_UPML_2D", 3, "fused"),
+                                               ("TM_UPML_2D", 3, "exact")])
+def test_slabs_from_a_random_state(solver, world, form):
+    """Every cell non-zero from the first step (random fields, one cell in three a material cell):
+    what bench.py's parity_check runs across real ranks."""
+    cmd = [sys.executable, os.path.join(ROOT, "scripts", "peer_local_check.py"), solver, "150", "330", "40",
+           str(world), form, "spread", "random"]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
+    assert "PEER_LOCAL_CHECK %s %s world %d spread random OK" % (solver, form, world) in p.stdout
