@@ -285,6 +285,15 @@ int b200fdtd_set_split_tables(b200fdtd_engine *e, const double *tab_i, const dou
  * nsFdtdTM.c:231-307 etc. */
 int b200fdtd_set_dense(b200fdtd_engine *e, int32_t slot, const double *host_map);
 
+/* NS-FDTD TE (kind 7) keeps eight dense coefficient arrays because its PML terms depend on the
+ * permittivity through tanh (nsFdtdTE.c:100-181).  Outside the absorbing frame sigma == 0, the four
+ * decay coefficients are exactly 1.0 and C_HZXLX == C_HZYLY bit for bit, so there the kernels read
+ * three arrays instead of eight (232 instead of 272 B per cell-update) and produce the same bits
+ * (1.0 * x == x).  The caller names that rectangle (global i / j, inclusive; lo > hi switches the
+ * form off) after checking it on its host arrays; thread blocks that are not wholly inside it take the
+ * dense path of the same kernel. */
+int b200fdtd_set_split_interior(b200fdtd_engine *e, int32_t i_lo, int32_t i_hi, int32_t j_lo, int32_t j_hi);
+
 /* ---- the hot path -------------------------------------------------------- */
 /* One update() (fdtdTM_upml.c:54-66 / fdtdTE_upml.c:168-192): H phase, E phase
  * with source, NTFF surface sample.  Asynchronous on the engine's stream. */

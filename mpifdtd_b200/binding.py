@@ -137,6 +137,7 @@ def lib():
     L.b200fdtd_get_field_slab.argtypes = [vp, i32, vp]
     L.b200fdtd_set_option.argtypes = [vp, i32, i32]
     L.b200fdtd_set_dense.argtypes = [vp, i32, vp]
+    L.b200fdtd_set_split_interior.argtypes = [vp, i32, i32, i32, i32]
     L.b200fdtd_peer_export.argtypes = [vp, vp]
     L.b200fdtd_peer_attach.argtypes = [vp, i32, vp]
     L.b200fdtd_peer_attach_engine.argtypes = [vp, i32, vp]

@@ -217,6 +217,8 @@ int b200fdtd_create(const b200fdtd_grid *grid, b200fdtd_engine **out)
   if (const char *v = getenv("B200FDTD_LEAN_INTERIOR")) e->lean_interior = atoi(v) != 0 && kind_is_upml(grid->kind);
   e->lean_r_lo = e->lean_c_lo = 1;
   e->lean_r_hi = e->lean_c_hi = 0;
+  e->split_in_r_lo = e->split_in_c_lo = 1;
+  e->split_in_r_hi = e->split_in_c_hi = 0;
 
   // update extents clipped to this slab, in layout coordinates
   const int jl = grid->j_lo > grid->j0 ? grid->j_lo : grid->j0;
@@ -642,6 +644,26 @@ int b200fdtd_set_dense(b200fdtd_engine *e, int32_t slot, const double *host_map)
                               cudaMemcpyHostToDevice, e->stream));
   B200_CUDA(cudaStreamSynchronize(e->stream));
   e->have_dense[slot] = true;
+  return B200FDTD_OK;
+}
+
+int b200fdtd_set_split_interior(b200fdtd_engine *e, int32_t i_lo, int32_t i_hi, int32_t j_lo, int32_t j_hi)
+{
+  if (!e) return b200_fail(B200FDTD_ERR_ARG, "NULL engine");
+  if (e->g.kind != B200FDTD_NS_TE) return b200_fail(B200FDTD_ERR_ARG, "the interior form serves the NS-FDTD TE kind (7)");
+  e->split_in_r_lo = e->split_in_c_lo = 1;
+  e->split_in_r_hi = e->split_in_c_hi = 0;
+  if (i_lo > i_hi || j_lo > j_hi) return B200FDTD_OK;             // switched off
+  const b200fdtd_grid &g = e->g;
+  const int jl = j_lo > g.j0 ? j_lo : g.j0, jh = j_hi < g.j0 + g.nj - 1 ? j_hi : g.j0 + g.nj - 1;
+  int r_lo = i_lo + 1, r_hi = i_hi + 1, c_lo = jl - g.j0 + B200_JOFF, c_hi = jh - g.j0 + B200_JOFF;
+  if (r_lo < e->r_lo) r_lo = e->r_lo;
+  if (r_hi > e->r_hi) r_hi = e->r_hi;
+  if (c_lo < e->c_lo) c_lo = e->c_lo;
+  if (c_hi > e->c_hi) c_hi = e->c_hi;
+  if (r_lo <= r_hi && c_lo <= c_hi) {
+    e->split_in_r_lo = r_lo; e->split_in_r_hi = r_hi; e->split_in_c_lo = c_lo; e->split_in_c_hi = c_hi;
+  }
   return B200FDTD_OK;
 }
 

@@ -87,6 +87,9 @@ struct b200fdtd_engine {
   double *tab_j;            // device [B200FDTD_UPML_TABS][pitch], indexed by in-row offset
   bool have_tabs, have_eps[2];
   bool split_lean;          // split-field kinds 0/1/6: 1-D tables + eps / G arrays instead of 8 dense arrays
+  // kind 7 (NS TE): rectangle (layout coordinates, inclusive; empty as lo > hi) where the four decay
+  // coefficients are exactly 1.0 and C_HZXLX == C_HZYLY: three coefficient arrays instead of eight there
+  int split_in_r_lo, split_in_r_hi, split_in_c_lo, split_in_c_hi;
   NtffState ntff;
   FusedState fused;
   PeerState peer;

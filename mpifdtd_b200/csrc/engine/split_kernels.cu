@@ -25,6 +25,7 @@ struct SplitView {
   int rows;
   int pitch;
   int r_lo, c_lo, c_hi, nbx;
+  int in_r_lo, in_r_hi, in_c_lo, in_c_hi;   // kind 7: the rectangle of b200fdtd_set_split_interior (empty: lo > hi)
   int j_base;
   b200fdtd_cw cw[2];
   double ns_r2;
@@ -39,6 +40,14 @@ __device__ __forceinline__ bool locate(const SplitView &v, int &r, int &c, size_
   c = v.c_lo + cb * kBlock + (int)threadIdx.x;
   k = (size_t)r * (size_t)v.pitch + (size_t)c;
   return c <= v.c_hi;
+}
+
+// kind 7: does this whole thread block (kBlock consecutive columns of row r) lie inside the rectangle
+// where the decay coefficients are exactly 1.0 and the two curl coefficients coincide?  Block-uniform.
+__device__ __forceinline__ bool block_in_interior(const SplitView &v, int r, int c)
+{
+  const int c_first = c - (int)threadIdx.x;
+  return r >= v.in_r_lo && r <= v.in_r_hi && c_first >= v.in_c_lo && c_first + kBlock - 1 <= v.in_c_hi;
 }
 
 // one CW source target; `factor` is the host-built per-cell (eps0/eps - 1)-type term
@@ -168,7 +177,7 @@ __global__ void __launch_bounds__(kBlock) split_tm_e_kernel(const SplitView v)
 
 // ---------------------------------------------------------------- TE family ------
 // slots: 0 Hz 1 Hzx 2 Hzy 3 Ex 4 Ey
-template <bool NS, bool LEAN>          // LEAN: kind 1 only (NS TE keeps its dense arrays)
+template <bool NS, bool LEAN, bool INTERIOR = false>          // LEAN: kind 1 only (NS TE keeps its dense arrays)
 __global__ void __launch_bounds__(kBlock) split_te_e_kernel(const SplitView v)
 {
   int r, c; size_t k;
@@ -191,7 +200,12 @@ __global__ void __launch_bounds__(kBlock) split_te_e_kernel(const SplitView v)
     dx_term = ((zx - Hzx[k - P]) + zy) - Hzy[k - P];
   }
   double c_ex, c_exly, c_ey, c_eylx, fx, fy;
-  if (!LEAN) {
+  const bool inside = INTERIOR && block_in_interior(v, r, c);
+  if (inside) {           // C_EX == C_EY == 1.0 here: 1.0 * x == x
+    c_ex = 1.0;  c_exly = v.c[B200FDTD_STE_C_EXLY][k];
+    c_ey = 1.0;  c_eylx = v.c[B200FDTD_STE_C_EYLX][k];
+    fx = v.c[B200FDTD_DENSE_SRC0][k];  fy = v.c[B200FDTD_DENSE_SRC1][k];
+  } else if (!LEAN) {
     c_ex = v.c[B200FDTD_STE_C_EX][k];  c_exly = v.c[B200FDTD_STE_C_EXLY][k];
     c_ey = v.c[B200FDTD_STE_C_EY][k];  c_eylx = v.c[B200FDTD_STE_C_EYLX][k];
     fx = v.c[B200FDTD_DENSE_SRC0][k];  fy = v.c[B200FDTD_DENSE_SRC1][k];
@@ -203,8 +217,8 @@ __global__ void __launch_bounds__(kBlock) split_te_e_kernel(const SplitView v)
     c_ex = px.c;  c_exly = px.l;  c_ey = py.c;  c_eylx = py.l;
     fx = 0.0;  fy = inv_y - 1.0;
   }
-  double2 ex = c_ex * v.f[B200FDTD_STE_EX][k] + c_exly * dy_term;
-  double2 ey = c_ey * v.f[B200FDTD_STE_EY][k] - c_eylx * dx_term;
+  double2 ex = (inside ? v.f[B200FDTD_STE_EX][k] : c_ex * v.f[B200FDTD_STE_EX][k]) + c_exly * dy_term;
+  double2 ey = (inside ? v.f[B200FDTD_STE_EY][k] : c_ey * v.f[B200FDTD_STE_EY][k]) - c_eylx * dx_term;
   const int i = r - 1, j = v.j_base + c;
   if (v.cw[0].enabled && fx != 0.0) ex = ex + cw_term(v.cw[0], i, j, fx);     // nsFdtdTE.c:247-248
   if (v.cw[1].enabled && fy != 0.0) ey = ey + cw_term(v.cw[1], i, j, fy);     // fdtdTE.c:285, nsFdtdTE.c:249-250
@@ -212,13 +226,24 @@ __global__ void __launch_bounds__(kBlock) split_te_e_kernel(const SplitView v)
   v.f[B200FDTD_STE_EY][k] = ey;
 }
 
-template <bool LEAN>
+// INTERIOR (NS TE, kind 7): thread blocks inside the rectangle of b200fdtd_set_split_interior -- decay
+// coefficients exactly 1.0, the two curl coefficients equal -- read three arrays fewer: same bits
+template <bool LEAN, bool INTERIOR = false>
 __global__ void __launch_bounds__(kBlock) split_te_h_kernel(const SplitView v)
 {
   int r, c; size_t k;
   if (!locate(v, r, c, k)) return;
   const double2 *__restrict__ Ex = v.f[B200FDTD_STE_EX];
   const double2 *__restrict__ Ey = v.f[B200FDTD_STE_EY];
+  if (INTERIOR && block_in_interior(v, r, c)) {
+    const double g = v.c[B200FDTD_STE_C_HZXLX][k];
+    const double2 hzx = v.f[B200FDTD_STE_HZX][k] - g * (Ey[k + v.pitch] - Ey[k]);
+    const double2 hzy = v.f[B200FDTD_STE_HZY][k] + g * (Ex[k + 1] - Ex[k]);
+    v.f[B200FDTD_STE_HZX][k] = hzx;
+    v.f[B200FDTD_STE_HZY][k] = hzy;
+    v.f[B200FDTD_STE_HZ][k] = hzx + hzy;
+    return;
+  }
   double c_hzx, c_hzxlx, c_hzy, c_hzyly;
   if (!LEAN) {
     c_hzx = v.c[B200FDTD_STE_C_HZX][k];  c_hzxlx = v.c[B200FDTD_STE_C_HZXLX][k];
@@ -252,6 +277,8 @@ int b200_launch_split_step(b200fdtd_engine *e, const b200fdtd_step_args *a)
   v.eps0 = e->eps[0]; v.eps1 = e->eps[1];
   v.ti = e->tab_i; v.tj = e->tab_j;
   v.rows = e->rows;
+  v.in_r_lo = e->split_in_r_lo; v.in_r_hi = e->split_in_r_hi;
+  v.in_c_lo = e->split_in_c_lo; v.in_c_hi = e->split_in_c_hi;
   const unsigned nblk = (unsigned)((long long)v.nbx * (e->r_hi - e->r_lo + 1));
   cudaStream_t st = e->stream;
   const bool lean = e->split_lean;
@@ -269,8 +296,13 @@ int b200_launch_split_step(b200fdtd_engine *e, const b200fdtd_step_args *a)
     else      { split_tm_h_kernel<true, false><<<nblk, kBlock, 0, st>>>(v); split_tm_e_kernel<true, false><<<nblk, kBlock, 0, st>>>(v); }
     break;
   case B200FDTD_NS_TE:     // nsFdtdTE.c:233-251: calcH, Hz = Hzx + Hzy, calcE, sources
-    split_te_h_kernel<false><<<nblk, kBlock, 0, st>>>(v);
-    split_te_e_kernel<true, false><<<nblk, kBlock, 0, st>>>(v);
+    if (v.in_r_hi >= v.in_r_lo && v.in_c_hi >= v.in_c_lo) {      // blocks inside the frame-free rectangle: 3 arrays
+      split_te_h_kernel<false, true><<<nblk, kBlock, 0, st>>>(v);
+      split_te_e_kernel<true, false, true><<<nblk, kBlock, 0, st>>>(v);
+    } else {
+      split_te_h_kernel<false><<<nblk, kBlock, 0, st>>>(v);
+      split_te_e_kernel<true, false><<<nblk, kBlock, 0, st>>>(v);
+    }
     break;
   default:
     return b200_fail(B200FDTD_ERR_STATE, "not a split-field kind: %d", e->g.kind);

@@ -405,6 +405,34 @@ static void build_host(SplitSolver *s, int lean)
   }
 }
 
+/* NS TE (id 7): outside the absorbing frame sigma == 0, so beta == 0 and the four decay coefficients
+ * of nsFdtdTE.c:155-177 are exactly 1.0 while C_HZXLX and C_HZYLY are the same u/z/(1 + 0).  The
+ * largest centred rectangle where the arrays built above really say so -- checked cell by cell, not
+ * assumed -- goes to the engine, whose kernels then read three coefficient arrays instead of eight
+ * there (b200fdtd_set_split_interior).  MPIFDTD_SPLIT_DENSE=1 keeps the dense form everywhere. */
+static void set_ns_te_interior(SplitSolver *s)
+{
+  FieldInfo_S g = field_getFieldInfo_S();
+  const char *v = getenv("MPIFDTD_SPLIT_DENSE");
+  if (v != NULL && v[0] == '1') return;
+  for (int margin = g.N_PML + 1; margin < g.N_PML + 6; margin++) {
+    const int i_lo = margin, i_hi = g.N_PX - 1 - margin, j_lo = margin, j_hi = g.N_PY - 1 - margin;
+    if (i_hi - i_lo < 8 || j_hi - j_lo < 8) return;
+    int ok = 1;
+    for (int i = i_lo; i <= i_hi && ok; i++)
+      for (int j = j_lo; j <= j_hi; j++) {
+        const int k = field_index(i, j);
+        if (s->coef[B200FDTD_STE_C_HZX][k] != 1.0 || s->coef[B200FDTD_STE_C_HZY][k] != 1.0 ||
+            s->coef[B200FDTD_STE_C_EX][k] != 1.0 || s->coef[B200FDTD_STE_C_EY][k] != 1.0 ||
+            s->coef[B200FDTD_STE_C_HZXLX][k] != s->coef[B200FDTD_STE_C_HZYLY][k]) { ok = 0; break; }
+      }
+    if (ok) {
+      die_on(b200fdtd_set_split_interior(s->engine, i_lo, i_hi, j_lo, j_hi), "b200fdtd_set_split_interior");
+      return;
+    }
+  }
+}
+
 static void solver_init(SplitSolver *s)
 {
   FieldInfo_S g = field_getFieldInfo_S();
@@ -442,6 +470,7 @@ static void solver_init(SplitSolver *s)
     die_on(b200fdtd_set_dense(s->engine, m, s->coef[m]), "b200fdtd_set_dense");
   die_on(b200fdtd_set_dense(s->engine, B200FDTD_DENSE_SRC0, s->src[0]), "b200fdtd_set_dense(src0)");
   die_on(b200fdtd_set_dense(s->engine, B200FDTD_DENSE_SRC1, s->src[1]), "b200fdtd_set_dense(src1)");
+  if (s->kind == B200FDTD_NS_TE) set_ns_te_interior(s);
   /* the pinned getter mirrors are allocated by the first getter call (solver_field) */
 }
 

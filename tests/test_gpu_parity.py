@@ -154,6 +154,29 @@ def test_mie_1024_short_run_vs_oracle(plugin_lib, oracle, solver, field):
     gpu.finish()
 
 
+def test_one_pass_default_at_4096_vs_oracle(plugin_lib, oracle, monkeypatch, in_tmp_cwd):
+    """A grid where the auto rule itself picks the one-pass step (form 3), with a material model and
+    the NTFF box, compared DIRECTLY with the oracle -- all nine arrays and every bin of U/W -- instead
+    of by transitivity through the two-kernel form (VERDICT r01, weak #12)."""
+    monkeypatch.setenv("MPIFDTD_NTFF_FULL_BINS", "1")
+    n, steps = 4096, 50
+    gpu = B.Plugin("MIE_CYLINDER", "TM_UPML_2D", n, steps=steps)
+    form = B.C.c_int32(-1)
+    B.check(gpu.L.b200fdtd_get_step_form(gpu.engine_handle(), B.C.byref(form)), "get_step_form")
+    assert form.value == 3
+    cpu = oracle_for(oracle, gpu, steps)
+    gpu.run()
+    cpu.step(steps)
+    assert np.abs(cpu.field(0)).max() > 0
+    for slot in range(9):
+        assert rel_err(gpu.any_field(slot), cpu.field(slot)) <= TOL_FIELD, slot
+    for slot in range(3):
+        want = cpu.uw(slot)
+        assert np.abs(want).max() > 0, slot
+        assert rel_err(gpu.ntff_uw(slot, project=(slot == 0)), want) <= TOL_FARFIELD, slot
+    gpu.finish()
+
+
 # ---------------------------------------------------------------- lifecycle
 def test_reset_then_new_angle_matches_fresh_run(plugin_lib, oracle):
     """main.c:207-209: simulator_reset() writes the far field, zeroes state, then the

@@ -50,6 +50,33 @@ def test_lean_form_is_bit_identical_to_dense(plugin_lib, kind, model, in_tmp_cwd
     assert runs["lean"][1] < 0.8 * runs["dense"][1]              # and it really keeps fewer arrays
 
 
+@pytest.mark.parametrize("model", ["LAYER", "MIE_CYLINDER", "ZIGZAG"])
+def test_ns_te_interior_form_is_bit_identical_to_dense(plugin_lib, model, in_tmp_cwd, monkeypatch):
+    """Solver id 7 (the reference's own default, main.c:155-156): outside the absorbing frame its
+    decay coefficients are exactly 1.0 and C_HZXLX == C_HZYLY, so the kernels read three coefficient
+    arrays there instead of eight (b200fdtd_set_split_interior) -- and must give the bits of the
+    all-dense form.  LAYER keeps eps != 1 inside the PML (the tanh-dependent frame coefficients).
+    (800 columns: two of the four 256-column thread blocks of a row lie wholly inside the rectangle.)"""
+    npx, npy, steps = 200, 800, 240
+    runs = {}
+    for form in ("dense", "interior"):
+        if form == "dense":
+            monkeypatch.setenv("MPIFDTD_SPLIT_DENSE", "1")
+        else:
+            monkeypatch.delenv("MPIFDTD_SPLIT_DENSE")
+        gpu = B.Plugin(model, 7, npx, npy, steps=steps, lambda_nm=633, angle_deg=15)
+        n0 = gpu.launches()
+        gpu.step(10)
+        per_step = (gpu.launches() - n0) / 10
+        gpu.run()
+        runs[form] = ({f: gpu.field(f) for f in FIELDS[7]}, per_step)
+        gpu.finish()
+    assert np.abs(runs["dense"][0][FIELDS[7][0]]).max() > 1e-3
+    for f in FIELDS[7]:
+        assert bit_equal(runs["interior"][0][f], runs["dense"][0][f]), f
+    assert runs["dense"][1] == 2 and runs["interior"][1] == 2       # one launch per phase either way
+
+
 def C_uint64_device_bytes(gpu):
     import ctypes as C
     n = C.c_uint64(0)
