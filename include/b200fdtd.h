@@ -134,8 +134,12 @@ typedef struct b200fdtd_grid {
                             /* (incidence angle): the angle sweep of main.c:114-211  */
                             /* as ONE engine.  0 or 1 = a single simulation.  Serial */
                             /* UPML kinds (2, 3), whole grid on one engine.          */
-  int32_t reserved2;
+  int32_t flags;            /* B200FDTD_GRID_* bits, 0 by default                     */
 } b200fdtd_grid;
+/* An engine without field arrays: only the NTFF machinery (history, projection, spectrum), fed with
+ * surface samples the caller gathered from its OWN host-side fields (b200fdtd_ntff_push_samples) --
+ * what the exported ntffTM_* / ntffTE_* entry points run on.  Stepping such an engine is an error. */
+#define B200FDTD_GRID_NTFF_ONLY 1
 
 /* Scattered-field Gaussian pulse, field_scatteredPulse (field.c:224-256):
  * p[k] += dot*exp(-(r/beam_width)^2)*(eps0/eps[k]-1)*cexp(i*r*omega) on cells with
@@ -371,6 +375,13 @@ int b200fdtd_ntff_get_uw(b200fdtd_engine *e, int32_t slot, double *host_complex)
 /* dst.U/W += src.U/W after both have been projected: the end-of-run sum over the y-slabs of one
  * process (peer copy + one kernel; the reference's MPI solvers never reduce) */
 int b200fdtd_ntff_add_uw(b200fdtd_engine *dst, b200fdtd_engine *src);
+/* The surface sample of step t as the caller gathered it (n_local complex E values and n_local
+ * complex H values in the perimeter order of b200fdtd_set_ntff_plan, signs and the two-cell H average
+ * already applied: what ntff_sample_kernel records).  Replaces the per-step field reads of
+ * ntffTM_TimeCalc / ntffTE_TimeCalc for hosts that keep their fields on the CPU. */
+int b200fdtd_ntff_push_samples(b200fdtd_engine *e, int32_t t, const double *e_complex, const double *h_complex);
+/* overwrite one U/W slot ([n_angles][n_bins] complex) from the host */
+int b200fdtd_ntff_set_uw(b200fdtd_engine *e, int32_t slot, const double *host_complex);
 /* device pointer + element count of the whole U/W block, for an NCCL reduce */
 int b200fdtd_ntff_uw_device(b200fdtd_engine *e, void **dev_ptr, uint64_t *n_doubles);
 /* out[(lambda-lambda_first)*n_angles + ang], the table ntff_outputEnormBin writes */

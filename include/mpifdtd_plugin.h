@@ -225,6 +225,29 @@ extern void mpifdtd_setAngleBatch(const int *angles_deg, int n);
 extern void mpifdtd_selectAngle(int index);
 extern int mpifdtd_runAngleSweep(FieldInfo field_info, int start_deg, int end_deg, int delta_deg, int max_batch);
 
+/* ---- the reference's public NTFF entry points (ntffTM.h:7-28, ntffTE.h:5-15), for a solver file of
+ * the maintainer's own that keeps its fields on the host.  Same signatures.  TimeCalc gathers the
+ * surface samples of the step from the host arrays (the reference's reads, signs and H averages) and
+ * appends them to a GPU-side history; the 360-direction binning of ntffTM.c:279-371 runs on the GPU
+ * when the accumulators are needed: TimeTranslate / TimeOutput (and mpifdtd_ntffSync) first store
+ * them into the arrays they are given -- all arraySize bins, within 1e-13 of the reference's -- so
+ * U / W are current from then on, not after every TimeCalc.  TimeOutput writes "<ang>[deg].txt" and
+ * "<ang>[deg]_380nm_700nm_b.dat" into cwd like upstream.  ntff?_init (re)creates the accumulators for
+ * the current field_init() state; ntff?_finish releases them. */
+extern void ntffTM_init(void);
+extern void ntffTM_finish(void);
+extern void ntffTM_TimeCalc(dcomplex *Hx, dcomplex *Hy, dcomplex *Ez, dcomplex *Ux, dcomplex *Uy, dcomplex *Wz);
+extern void ntffTM_TimeTranslate(dcomplex *Ux, dcomplex *Uy, dcomplex *Wz, dcomplex *Eth, dcomplex *Eph);
+extern void ntffTM_TimeOutput(dcomplex *Ux, dcomplex *Uy, dcomplex *Wz);
+extern void ntffTM_Frequency(dcomplex *Hx, dcomplex *Hy, dcomplex *Ez, dcomplex resEz[360]);
+extern void ntffTE_init(void);
+extern void ntffTE_finish(void);
+extern void ntffTE_TimeCalc(dcomplex *Ex, dcomplex *Ey, dcomplex *Hz, dcomplex *Wx, dcomplex *Wy, dcomplex *Uz);
+extern void ntffTE_TimeTranslate(dcomplex *Wx, dcomplex *Wy, dcomplex *Uz, dcomplex *Eth, dcomplex *Eph);
+extern void ntffTE_TimeOutput(dcomplex *Wx, dcomplex *Wy, dcomplex *Uz);
+/* store the accumulators now (tm != 0: Ux, Uy, Wz; else Wx, Wy, Uz; NULL skips one) */
+extern void mpifdtd_ntffSync(int tm, dcomplex *a0, dcomplex *a1, dcomplex *a2);
+
 /* ---- multi-GPU mode of the serial UPML solvers, host code staying C (extension; replaces
  * init_mpi + the per-step halo Sendrecv of mpiTM_UPML.c:196-217,252-334,718-748) ---------------
  * mpifdtd_setDevices(n): the next init() of solver ids 2 / 3 cuts the grid into n y-slabs, one

@@ -51,7 +51,7 @@ class Grid(C.Structure):
                 ("j0", C.c_int32), ("nj", C.c_int32), ("i_lo", C.c_int32), ("i_hi", C.c_int32),
                 ("j_lo", C.c_int32), ("j_hi", C.c_int32), ("device", C.c_int32),
                 ("precision", C.c_int32), ("mu0", C.c_double),
-                ("n_batch", C.c_int32), ("reserved2", C.c_int32)]
+                ("n_batch", C.c_int32), ("flags", C.c_int32)]
 
 
 class Pulse(C.Structure):

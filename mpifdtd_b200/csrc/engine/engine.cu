@@ -192,6 +192,8 @@ int b200fdtd_create(const b200fdtd_grid *grid, b200fdtd_engine **out)
   e->pitch = ((B200_JOFF + grid->nj + 1) + 7) / 8 * 8;
   e->plane = (size_t)e->rows * e->pitch;
   e->n_fields = kind_is_split(grid->kind) ? 5 : 9;
+  const bool ntff_only = (grid->flags & B200FDTD_GRID_NTFF_ONLY) != 0;
+  if (ntff_only) e->n_fields = 0;                 // history, projection and spectrum only: no field arrays
   e->n_batch = n_batch;
   e->fp32 = grid->precision == B200FDTD_F32;
   e->csize = e->fp32 ? sizeof(float2) : sizeof(double2);
@@ -230,7 +232,9 @@ int b200fdtd_create(const b200fdtd_grid *grid, b200fdtd_engine **out)
 
   for (int s = 0; s < e->n_fields && !rc; s++)
     rc = dev_alloc_zero(e, (void **)&e->field[s], e->plane * e->csize * (size_t)n_batch);
-  if (kind_is_split(grid->kind)) {
+  if (ntff_only) {
+    if (!kind_is_upml(grid->kind) || n_batch > 1) rc = b200_fail(B200FDTD_ERR_ARG, "NTFF-only engines: an unbatched UPML kind");
+  } else if (kind_is_split(grid->kind)) {
     // dense coefficient arrays and eps maps are allocated by the first set_dense / set_eps
     // call for their slot: the lean form needs only a few of them
     rc = dev_alloc_zero(e, (void **)&e->tab_i, sizeof(double) * B200FDTD_SPLIT_TABS * e->rows);
@@ -757,6 +761,7 @@ int b200fdtd_set_ntff_plan(b200fdtd_engine *e, const b200fdtd_ntff_plan *p)
 static int check_ready(b200fdtd_engine *e, const b200fdtd_step_args *a)
 {
   if (!e || !a) return b200_fail(B200FDTD_ERR_ARG, "NULL argument");
+  if (e->n_fields == 0) return b200_fail(B200FDTD_ERR_STATE, "an NTFF-only engine has no fields to step");
   if (kind_is_split(e->g.kind)) {
     if (e->split_lean) {            // 1-D tables + eps (kinds 0, 1) or G arrays + source factor (kind 6)
       const int k = e->g.kind;
@@ -1188,6 +1193,36 @@ int b200fdtd_ntff_add_uw(b200fdtd_engine *dst, b200fdtd_engine *src)
   if (err == cudaSuccess) err = cudaStreamSynchronize(dst->stream);
   cudaFree(tmp);
   if (err != cudaSuccess) return b200_fail(B200FDTD_ERR_CUDA, "U/W sum: %s", cudaGetErrorString(err));
+  return B200FDTD_OK;
+}
+
+int b200fdtd_ntff_push_samples(b200fdtd_engine *e, int32_t t, const double *e_complex, const double *h_complex)
+{
+  if (!e || !e_complex || !h_complex || !e->ntff.ready) return b200_fail(B200FDTD_ERR_ARG, "bad sample push");
+  NtffState &n = e->ntff;
+  if (t < 0 || t >= n.max_time || e->n_batch > 1)
+    return b200_fail(B200FDTD_ERR_ARG, "step %d outside the NTFF history [0, %d)", t, n.max_time);
+  int rc = select_device(e); if (rc) return rc;
+  if (n.n_local > 0) {            // hist[p][t]: one element per point, max_time elements apart
+    B200_CUDA(cudaMemcpy2DAsync(n.hist_e + t, sizeof(double2) * (size_t)n.max_time, e_complex, sizeof(double2),
+                                sizeof(double2), (size_t)n.n_local, cudaMemcpyHostToDevice, e->stream));
+    B200_CUDA(cudaMemcpy2DAsync(n.hist_h + t, sizeof(double2) * (size_t)n.max_time, h_complex, sizeof(double2),
+                                sizeof(double2), (size_t)n.n_local, cudaMemcpyHostToDevice, e->stream));
+    B200_CUDA(cudaStreamSynchronize(e->stream));      // the caller's buffers are free again
+  }
+  if (t + 1 > n.steps_recorded) n.steps_recorded = t + 1;
+  return B200FDTD_OK;
+}
+
+int b200fdtd_ntff_set_uw(b200fdtd_engine *e, int32_t slot, const double *host)
+{
+  if (!e || !host || slot < 0 || slot > 2 || !e->ntff.ready) return b200_fail(B200FDTD_ERR_ARG, "bad U/W request");
+  int rc = select_device(e); if (rc) return rc;
+  const NtffState &n = e->ntff;
+  const size_t count = (size_t)n.n_angles * n.n_bins;
+  B200_CUDA(cudaMemcpyAsync(n.uw + ((size_t)e->sel * 3 + (size_t)slot) * count, host, sizeof(double2) * count,
+                            cudaMemcpyHostToDevice, e->stream));
+  B200_CUDA(cudaStreamSynchronize(e->stream));
   return B200FDTD_OK;
 }
 

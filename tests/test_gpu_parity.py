@@ -170,10 +170,10 @@ def test_one_pass_default_at_4096_vs_oracle(plugin_lib, oracle, monkeypatch, in_
     assert np.abs(cpu.field(0)).max() > 0
     for slot in range(9):
         assert rel_err(gpu.any_field(slot), cpu.field(slot)) <= TOL_FIELD, slot
+    # (50 steps do not carry the scattered field from the cylinder to the NTFF box 2000 cells away: the
+    # surface history, and with it U/W, must be exactly as empty as the oracle's)
     for slot in range(3):
-        want = cpu.uw(slot)
-        assert np.abs(want).max() > 0, slot
-        assert rel_err(gpu.ntff_uw(slot, project=(slot == 0)), want) <= TOL_FARFIELD, slot
+        assert rel_err(gpu.ntff_uw(slot, project=(slot == 0)), cpu.uw(slot)) <= TOL_FARFIELD, slot
     gpu.finish()
 
 
