@@ -564,16 +564,25 @@ def gpu_arm(args):
         barrier()
         t0 = time.perf_counter()
         for slot in range(n_eps):
-            B.check(run.L.b200fdtd_set_eps_slab(run.engine.h, slot, eps_pinned[slot]), "set_eps_slab")
+            B.check(run.L.b200fdtd_set_eps_slab(run.engine.h, slot, eps_pinned[slot]), "set_eps_slab")   # synchronous
+        t1 = time.perf_counter()
         for _ in range(K):
             run.step()
         run.project()
+        run.engine.sync()
+        t2 = time.perf_counter()
         B.check(run.L.b200fdtd_get_field_slab(run.engine.h, 0, ez_pinned), "get_field_slab")
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         e2e_value = cells * K / max_over_ranks(dt) / 1e9
         h2d = sum(e.nbytes for e in run.eps_host) / K
         d2h = field_bytes / K
+        # where the wall time went on the slowest rank of each part: the two copies can overlap nothing (the
+        # first step needs all of eps, the field is final only after the last step)
+        e2e_parts = {"h2d_s": max_over_ranks(t1 - t0), "steps_s": max_over_ranks(t2 - t1),
+                     "d2h_s": max_over_ranks(dt - (t2 - t0)),
+                     "h2d_gbs_per_rank": h2d * K / max_over_ranks(t1 - t0) / 1e9,
+                     "d2h_gbs_per_rank": d2h * K / max_over_ranks(dt - (t2 - t0)) / 1e9}
         for p in pinned:
             run.L.b200fdtd_host_free(p)
 
@@ -653,7 +662,7 @@ def gpu_arm(args):
                     "path": "b200fdtd_set_eps_slab(pinned host eps) + K x [mpifdtd_upml_step_args + b200fdtd_step + "
                             "field_nextStep] + b200fdtd_ntff_project + b200fdtd_get_field_slab(%s -> pinned host)"
                             % ("Ez" if tm else "Ex"),
-                    "host_placement": placement},
+                    "host_placement": placement, "where_the_time_goes": e2e_parts},
             "gpu_launches": int(launches),
             "step_form": forms[form if one_pass or form < 3 else two_form],
             "clocks": clocks,

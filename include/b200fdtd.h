@@ -265,6 +265,11 @@ int b200fdtd_destroy(b200fdtd_engine *e);                                /* free
 /* Pinned host memory for mirrors the getters hand out (cudaHostAlloc). */
 int b200fdtd_host_alloc(void **ptr, uint64_t bytes);
 int b200fdtd_host_free(void *ptr);
+/* Getter mirrors: page-aligned pageable memory that is pinned in place (cudaHostRegister, the pointer
+ * does not change) once the caller has refreshed it a few times; see engine.cu. */
+int b200fdtd_mirror_alloc(void **ptr, uint64_t bytes);
+int b200fdtd_mirror_pin(void *ptr, uint64_t bytes);
+int b200fdtd_mirror_free(void *ptr, int32_t pinned);
 
 /* ---- init-time uploads --------------------------------------------------- */
 /* setCoefficient (fdtdTM_upml.c:224-274, fdtdTE_upml.c:361-412) */

@@ -147,6 +147,38 @@ int b200fdtd_host_free(void *ptr)
   return B200FDTD_OK;
 }
 
+// Getter mirrors.  Pinning 256 MB costs ~100 ms, a one-off download of it through pageable memory
+// ~20 ms: a mirror starts as plain page-aligned memory and is pinned IN PLACE (same pointer, so the
+// borrowed pointers callers hold stay valid) once it has been refreshed a few times -- the viewer's
+// per-frame getter then runs at full PCIe speed, a batch run that looks once never pays for pinning.
+int b200fdtd_mirror_alloc(void **ptr, uint64_t bytes)
+{
+  if (!ptr) return b200_fail(B200FDTD_ERR_ARG, "ptr is NULL");
+  void *p = nullptr;
+  if (posix_memalign(&p, 4096, bytes ? bytes : 4096) != 0 || p == nullptr)
+    return b200_fail(B200FDTD_ERR_NOMEM, "host mirror of %llu bytes", (unsigned long long)bytes);
+  memset(p, 0, bytes);
+  *ptr = p;
+  return B200FDTD_OK;
+}
+
+int b200fdtd_mirror_pin(void *ptr, uint64_t bytes)
+{
+  if (!ptr) return b200_fail(B200FDTD_ERR_ARG, "ptr is NULL");
+  cudaError_t err = cudaHostRegister(ptr, bytes, cudaHostRegisterDefault);
+  if (err == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return B200FDTD_OK; }
+  if (err != cudaSuccess) { cudaGetLastError(); return b200_fail(B200FDTD_ERR_CUDA, "cudaHostRegister: %s", cudaGetErrorString(err)); }
+  return B200FDTD_OK;
+}
+
+int b200fdtd_mirror_free(void *ptr, int32_t pinned)
+{
+  if (!ptr) return B200FDTD_OK;
+  if (pinned && cudaHostUnregister(ptr) != cudaSuccess) cudaGetLastError();
+  free(ptr);
+  return B200FDTD_OK;
+}
+
 int b200fdtd_create(const b200fdtd_grid *grid, b200fdtd_engine **out)
 {
   if (!grid || !out) return b200_fail(B200FDTD_ERR_ARG, "NULL argument");

@@ -1055,8 +1055,11 @@ int b200_launch_upml_fused(b200fdtd_engine *e, const b200fdtd_step_args *a)
     onepass_prepass_rows_kernel<false><<<(unsigned)((n_row_items + 255) / 256), 256, 0, e->stream>>>(f);
   }
   const dim3 grid((fs.n_strips + sh.warps - 1) / sh.warps, fs.n_bands);
-  const cudaError_t err = tm ? launch_variant<true>(e->fused_variant, f, grid, e->stream, f.lean != 0, e->store_h)
-                             : launch_variant<false>(e->fused_variant, f, grid, e->stream, f.lean != 0, e->store_h);
+  // the default shape keeps 4 row buffers in flight; the TM lean form stages 18 KB per row instead of 30 and
+  // runs ~1.5 % faster with 6 (same strip width, so the pre-pass geometry is unchanged)
+  const int variant = (e->fused_variant == 20 && tm && f.lean) ? 21 : e->fused_variant;
+  const cudaError_t err = tm ? launch_variant<true>(variant, f, grid, e->stream, f.lean != 0, e->store_h)
+                             : launch_variant<false>(variant, f, grid, e->stream, f.lean != 0, e->store_h);
   if (err != cudaSuccess)
     return b200_fail(B200FDTD_ERR_CUDA, "one-pass kernel (shape %d): %s", e->fused_variant, cudaGetErrorString(err));
   e->launches += 3;

@@ -30,6 +30,7 @@ typedef struct SplitSolver {
   double *coef[8];
   double *src[2];
   dcomplex *mirror[5];            /* host mirrors of the five fields              */
+  int mirror_reads[5];            /* refreshes so far; pinned in place at the third */
 } SplitSolver;
 
 static SplitSolver tm_plain = { .kind = B200FDTD_TM }, te_plain = { .kind = B200FDTD_TE };
@@ -537,9 +538,12 @@ static void solver_update(SplitSolver *s)
 static dcomplex *solver_field(SplitSolver *s, int slot)
 {
   if (s->engine == NULL) return NULL;
-  if (s->mirror[slot] == NULL)          /* pinned allocation is slow: only if somebody looks */
-    die_on(b200fdtd_host_alloc((void **)&s->mirror[slot], sizeof(dcomplex) * (size_t)field_getFieldInfo_S().N_CELL),
-           "host_alloc(mirror)");
+  const size_t mirror_bytes = sizeof(dcomplex) * (size_t)field_getFieldInfo_S().N_CELL;
+  if (s->mirror[slot] == NULL) {        /* only if somebody looks; pageable first, pinned in place once it is read often */
+    die_on(b200fdtd_mirror_alloc((void **)&s->mirror[slot], mirror_bytes), "mirror_alloc");
+    s->mirror_reads[slot] = 0;
+  }
+  if (++s->mirror_reads[slot] == 3) die_on(b200fdtd_mirror_pin(s->mirror[slot], mirror_bytes), "mirror_pin");
   die_on(b200fdtd_get_field(s->engine, slot, (double *)s->mirror[slot]), "b200fdtd_get_field");
   return s->mirror[slot];
 }
@@ -565,7 +569,10 @@ static void solver_finish(SplitSolver *s)
   die_on(b200fdtd_destroy(s->engine), "b200fdtd_destroy");
   s->engine = NULL;
   free_host(s);
-  for (int m = 0; m < 5; m++) { b200fdtd_host_free(s->mirror[m]); s->mirror[m] = NULL; }
+  for (int m = 0; m < 5; m++) {
+    b200fdtd_mirror_free(s->mirror[m], s->mirror_reads[m] >= 3);
+    s->mirror[m] = NULL;  s->mirror_reads[m] = 0;
+  }
 }
 
 /* test hooks: host-built dense arrays and the engine of a split solver */

@@ -41,7 +41,8 @@ typedef struct UpmlSolver {
   b200fdtd_engine *slab[MPIFDTD_MAX_SLABS];   /* y-slabs, one engine each (slab[0] == engine) */
   int n_slabs;
   double *eps[3];                 /* host maps: TM EZ,HX,HY (HX/HY lazily) | TE EX,EY,HZ */
-  dcomplex *mirror[3];            /* pinned mirrors for the X, Y, Z getters (lazy)  */
+  dcomplex *mirror[3];            /* host mirrors for the X, Y, Z getters (lazy)    */
+  int mirror_reads[3];            /* refreshes so far; pinned in place at the third  */
   size_t mirror_cells;
   int n_cell;
   int point_source;               /* opt-in, see mpifdtd_enablePointSource         */
@@ -380,7 +381,7 @@ static void solver_init(UpmlSolver *s)
    * along x (fdtdTE_upml.c:374-375); EPS_HZ likewise unused. */
   const int n_eps = tm ? 1 : 2;
   for (int m = 0; m < n_eps; m++)
-    die_on(b200fdtd_host_alloc((void **)&s->eps[m], sizeof(double) * (size_t)g.N_CELL), "host_alloc(eps)");
+    die_on(b200fdtd_mirror_alloc((void **)&s->eps[m], sizeof(double) * (size_t)g.N_CELL), "mirror_alloc(eps)");   /* uploaded once: not worth pinning */
   if (tm) {
     mpifdtd_fill_eps(s->eps[0], 0, 0, D_XY);
   } else {
@@ -808,8 +809,9 @@ static void solver_finish(UpmlSolver *s)
   s->n_slabs = 0;
   free(s->eps_ringed); s->eps_ringed = NULL;
   for (int m = 0; m < 3; m++) {
-    b200fdtd_host_free(s->eps[m]);    s->eps[m] = NULL;
-    b200fdtd_host_free(s->mirror[m]); s->mirror[m] = NULL;
+    b200fdtd_mirror_free(s->eps[m], 0); s->eps[m] = NULL;
+    b200fdtd_mirror_free(s->mirror[m], s->mirror_reads[m] >= 3);
+    s->mirror[m] = NULL;  s->mirror_reads[m] = 0;
   }
 }
 
@@ -817,8 +819,14 @@ static dcomplex *solver_field(UpmlSolver *s, int mirror, int slot)
 {
   if (s->engine == NULL) return NULL;                         /* upstream returns its NULL static */
   flush_pending(s);
-  if (s->mirror[mirror] == NULL)        /* pinned allocation is slow (~30 ms per 16 MB): only if somebody looks */
-    die_on(b200fdtd_host_alloc((void **)&s->mirror[mirror], sizeof(dcomplex) * s->mirror_cells), "host_alloc(mirror)");
+  if (s->mirror[mirror] == NULL) {      /* only if somebody looks */
+    die_on(b200fdtd_mirror_alloc((void **)&s->mirror[mirror], sizeof(dcomplex) * s->mirror_cells), "mirror_alloc");
+    s->mirror_reads[mirror] = 0;
+  }
+  /* pinning is slow (~30 ms per 16 MB): a caller that looks once (batch mode) gets a pageable copy,
+   * one that keeps looking (the viewer's display()) a pinned mirror -- same pointer either way */
+  if (++s->mirror_reads[mirror] == 3)
+    die_on(b200fdtd_mirror_pin(s->mirror[mirror], sizeof(dcomplex) * s->mirror_cells), "mirror_pin");
   if (is_mpi_kind(s->kind)) {                                 /* (N+2) x (N+2) with a zero ring */
     FieldInfo_S g = field_getFieldInfo_S();
     double *first = (double *)(s->mirror[mirror] + (size_t)(g.N_PY + 2) + 1);
