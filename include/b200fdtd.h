@@ -279,6 +279,14 @@ int b200fdtd_set_upml_tables(b200fdtd_engine *e, const double *tab_i, const doub
 int b200fdtd_set_eps(b200fdtd_engine *e, int32_t eps_slot, const double *host_eps);
 /* the same from a slab-shaped map [n_px][nj] (what a rank of a multi-GPU run builds) */
 int b200fdtd_set_eps_slab(b200fdtd_engine *e, int32_t eps_slot, const double *slab_eps);
+/* The same map as a palette: a permittivity map holds few distinct values (vacuum, the materials,
+ * the area-averaged boundary cells), so the host can ship 16-bit indices into a table of at most
+ * 65536 doubles -- 2 instead of 8 bytes per cell over PCIe -- and the device expands them into the
+ * dense map the kernels read (north_star: "per-cell material indices resolved from the model at
+ * init").  index_first points at (i = 0, first owned column), rows are ld elements apart (ld = n_py
+ * for a whole-grid map, nj for a slab-shaped one).  Bit-identical to b200fdtd_set_eps. */
+int b200fdtd_set_eps_palette(b200fdtd_engine *e, int32_t eps_slot, const uint16_t *index_first, int64_t ld,
+                             const double *table, int32_t n_values);
 int b200fdtd_set_ntff_plan(b200fdtd_engine *e, const b200fdtd_ntff_plan *plan);   /* ntffTM_init */
 /* batched engines: the n_batch per-simulation sources (host array) */
 int b200fdtd_set_batch_sources(b200fdtd_engine *e, const b200fdtd_batch_source *sources);

@@ -189,6 +189,8 @@ def lib():
     L.mpifdtd_fill_eps_slab.argtypes = [vp, dbl, dbl, C.c_int, C.c_int, C.c_int]
     L.mpifdtd_upml_tables.argtypes = [C.c_int, vp, vp]
     L.b200fdtd_set_eps_slab.argtypes = [vp, i32, vp]
+    L.b200fdtd_set_eps_palette.argtypes = [vp, i32, vp, C.c_int64, vp, i32]
+    L.mpifdtd_eps_palette.argtypes = [vp, C.c_size_t, vp, vp]
     L.mpifdtd_upml_step_args.argtypes = [C.c_int, C.c_int, C.POINTER(StepArgs)]
     L.mpifdtd_upml_far_field.argtypes = [vp, C.c_int, C.c_int, vp]
     L.mpifdtd_ntff_time_shift.restype = vp

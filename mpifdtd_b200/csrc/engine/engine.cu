@@ -1,9 +1,11 @@
 // engine.cu -- lifetime, uploads, state access and the C ABI of include/b200fdtd.h.
+#include <algorithm>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <sys/mman.h>
 #include <vector>
 #include "engine.h"
 
@@ -87,6 +89,20 @@ __global__ void axpy_double_kernel(double *dst, const double *src, size_t n)
     dst[k] += src[k];
 }
 
+// eps[k] = table[index[k]] over rows [i0, i0 + n_rows) of the owned cells (ghosts and padding keep
+// the vacuum 1.0); `index` holds just those rows
+template <typename T>
+__global__ void expand_palette_kernel(const unsigned short *__restrict__ index, const double *__restrict__ table,
+                                      int n_values, T *eps, int pitch, int i0, int n_rows, int nj)
+{
+  const size_t n = (size_t)n_rows * nj;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) {
+    const size_t i = t / nj, c = t - i * nj;
+    const int v = index[t];
+    eps[(i0 + i + 1) * pitch + B200_JOFF + c] = (T)table[v < n_values ? v : 0];
+  }
+}
+
 void free_ntff(b200fdtd_engine *e)
 {
   NtffState &n = e->ntff;
@@ -147,35 +163,60 @@ int b200fdtd_host_free(void *ptr)
   return B200FDTD_OK;
 }
 
-// Getter mirrors.  Pinning 256 MB costs ~100 ms, a one-off download of it through pageable memory
-// ~20 ms: a mirror starts as plain page-aligned memory and is pinned IN PLACE (same pointer, so the
-// borrowed pointers callers hold stay valid) once it has been refreshed a few times -- the viewer's
-// per-frame getter then runs at full PCIe speed, a batch run that looks once never pays for pinning.
+// Getter mirrors.  Pinning 256 MB of 4 KB pages costs ~100 ms, a one-off download of it through
+// pageable memory about as much.  A mirror is an anonymous mapping aligned to 2 MB with transparent
+// huge pages requested (zero-filled by the kernel, 128 faults instead of 65536), and it is pinned IN
+// PLACE (cudaHostRegister: same pointer, so the borrowed pointers callers hold stay valid).
+namespace {
+struct MirrorRec { void *ptr; size_t bytes; bool pinned; };
+MirrorRec g_mirrors[256];
+MirrorRec *find_mirror(void *ptr)
+{
+  for (MirrorRec &m : g_mirrors)
+    if (m.ptr == ptr) return &m;
+  return nullptr;
+}
+}  // namespace
+
 int b200fdtd_mirror_alloc(void **ptr, uint64_t bytes)
 {
   if (!ptr) return b200_fail(B200FDTD_ERR_ARG, "ptr is NULL");
-  void *p = nullptr;
-  if (posix_memalign(&p, 4096, bytes ? bytes : 4096) != 0 || p == nullptr)
-    return b200_fail(B200FDTD_ERR_NOMEM, "host mirror of %llu bytes", (unsigned long long)bytes);
-  memset(p, 0, bytes);
+  MirrorRec *rec = find_mirror(nullptr);
+  if (!rec) return b200_fail(B200FDTD_ERR_NOMEM, "too many host mirrors");
+  const size_t huge = 2u << 20;
+  const size_t len = ((bytes ? bytes : 1) + huge - 1) / huge * huge;
+  // over-map by one huge page so the start can be aligned; the unused head and tail are unmapped again
+  char *raw = (char *)mmap(nullptr, len + huge, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+  if (raw == (char *)MAP_FAILED) return b200_fail(B200FDTD_ERR_NOMEM, "host mirror of %llu bytes", (unsigned long long)bytes);
+  char *p = (char *)(((uintptr_t)raw + huge - 1) / huge * huge);
+  if (p > raw) munmap(raw, (size_t)(p - raw));
+  if (p + len < raw + len + huge) munmap(p + len, (size_t)(raw + len + huge - (p + len)));
+  madvise(p, len, MADV_HUGEPAGE);
+  rec->ptr = p; rec->bytes = len; rec->pinned = false;
   *ptr = p;
   return B200FDTD_OK;
 }
 
 int b200fdtd_mirror_pin(void *ptr, uint64_t bytes)
 {
-  if (!ptr) return b200_fail(B200FDTD_ERR_ARG, "ptr is NULL");
-  cudaError_t err = cudaHostRegister(ptr, bytes, cudaHostRegisterDefault);
-  if (err == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return B200FDTD_OK; }
+  MirrorRec *rec = ptr ? find_mirror(ptr) : nullptr;
+  if (!rec) return b200_fail(B200FDTD_ERR_ARG, "not a mirror");
+  (void)bytes;
+  if (rec->pinned) return B200FDTD_OK;
+  cudaError_t err = cudaHostRegister(ptr, rec->bytes, cudaHostRegisterDefault);
   if (err != cudaSuccess) { cudaGetLastError(); return b200_fail(B200FDTD_ERR_CUDA, "cudaHostRegister: %s", cudaGetErrorString(err)); }
+  rec->pinned = true;
   return B200FDTD_OK;
 }
 
 int b200fdtd_mirror_free(void *ptr, int32_t pinned)
 {
-  if (!ptr) return B200FDTD_OK;
-  if (pinned && cudaHostUnregister(ptr) != cudaSuccess) cudaGetLastError();
-  free(ptr);
+  (void)pinned;
+  MirrorRec *rec = ptr ? find_mirror(ptr) : nullptr;
+  if (!rec) return B200FDTD_OK;
+  if (rec->pinned && cudaHostUnregister(ptr) != cudaSuccess) cudaGetLastError();
+  munmap(ptr, rec->bytes);
+  rec->ptr = nullptr; rec->bytes = 0; rec->pinned = false;
   return B200FDTD_OK;
 }
 
@@ -666,6 +707,47 @@ static int upload_eps(b200fdtd_engine *e, int32_t slot, const double *src, size_
   B200_CUDA(cudaStreamSynchronize(e->stream));
   e->have_eps[slot] = true;
   return B200FDTD_OK;
+}
+
+int b200fdtd_set_eps_palette(b200fdtd_engine *e, int32_t slot, const uint16_t *index_first, int64_t ld,
+                             const double *table, int32_t n_values)
+{
+  if (!e || !index_first || !table || n_values < 1 || n_values > 65536 || ld < e->g.nj)
+    return b200_fail(B200FDTD_ERR_ARG, "bad palette (%d values)", n_values);
+  if (slot < 0 || slot > 1 || (!e->eps[slot] && !kind_is_split(e->g.kind)))
+    return b200_fail(B200FDTD_ERR_ARG, "bad eps slot %d", slot);
+  int rc = select_device(e); if (rc) return rc;
+  if (!e->eps[slot]) { rc = dev_alloc_zero(e, (void **)&e->eps[slot], e->plane * e->rsize); if (rc) return rc; }
+  const b200fdtd_grid &g = e->g;
+  // the indices travel in row blocks through a small staging buffer (a 512 MB cudaMalloc / cudaFree
+  // pair costs more than the copy it would serve)
+  const int rows_per_chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)g.n_px, ((size_t)16 << 20) / (size_t)g.nj));
+  unsigned short *d_index = nullptr;
+  double *d_table = nullptr;
+  cudaError_t err = cudaMalloc((void **)&d_index, (size_t)rows_per_chunk * g.nj * sizeof(unsigned short));
+  if (err == cudaSuccess) err = cudaMalloc((void **)&d_table, sizeof(double) * (size_t)n_values);
+  if (err != cudaSuccess) { cudaFree(d_index); return b200_fail(B200FDTD_ERR_NOMEM, "palette staging: %s", cudaGetErrorString(err)); }
+  if (e->fp32) rc = b200_fill_float(e, (float *)e->eps[slot], e->plane, 1.0f);
+  else { fill_double_kernel<<<1184, 256, 0, e->stream>>>(e->eps[slot], e->plane, 1.0); e->launches++; }
+  if (!rc) {
+    err = cudaMemcpyAsync(d_table, table, sizeof(double) * (size_t)n_values, cudaMemcpyHostToDevice, e->stream);
+    for (int i0 = 0; i0 < g.n_px && err == cudaSuccess; i0 += rows_per_chunk) {
+      const int n_rows = std::min(rows_per_chunk, g.n_px - i0);
+      err = cudaMemcpy2DAsync(d_index, sizeof(unsigned short) * g.nj, index_first + (size_t)i0 * (size_t)ld,
+                              sizeof(unsigned short) * (size_t)ld, sizeof(unsigned short) * g.nj, n_rows,
+                              cudaMemcpyHostToDevice, e->stream);
+      if (err != cudaSuccess) break;
+      if (e->fp32) expand_palette_kernel<float><<<592, 256, 0, e->stream>>>(d_index, d_table, n_values, (float *)e->eps[slot], e->pitch, i0, n_rows, g.nj);
+      else         expand_palette_kernel<double><<<592, 256, 0, e->stream>>>(d_index, d_table, n_values, e->eps[slot], e->pitch, i0, n_rows, g.nj);
+      e->launches++;
+      err = cudaGetLastError();
+    }
+    if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
+    if (err != cudaSuccess) rc = b200_fail(B200FDTD_ERR_CUDA, "palette upload: %s", cudaGetErrorString(err));
+  }
+  cudaFree(d_index); cudaFree(d_table);
+  if (!rc) e->have_eps[slot] = true;
+  return rc;
 }
 
 int b200fdtd_set_dense(b200fdtd_engine *e, int32_t slot, const double *host_map)

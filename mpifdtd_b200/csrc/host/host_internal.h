@@ -11,6 +11,12 @@ extern void mpifdtd_fill_eps(double *dst, double xoff, double yoff, enum MODE mo
 extern void mpifdtd_fill_eps_slab(double *dst, double xoff, double yoff, enum MODE mode, int j0, int nj);
 
 
+/* map[n] -> 16-bit indices into a table of its distinct values (table: room for 65536 doubles);
+ * returns the number of distinct values, -1 if there are more than 65536 */
+#include <stddef.h>
+#include <stdint.h>
+extern int mpifdtd_eps_palette(const double *map, size_t n, uint16_t *index, double *table);
+
 /* farfield.c: NTFF sampling plan and post-processing constants (host libm) */
 extern int mpifdtd_ntff_point_count(const NTFFInfo *box);
 extern int mpifdtd_ntff_local_count(const NTFFInfo *box, int j0, int nj);

@@ -107,3 +107,46 @@ void mpifdtd_fill_eps_slab(double *dst, double xoff, double yoff, enum MODE mode
     if (!pthread_equal(tid[t], pthread_self()))
       pthread_join(tid[t], NULL);
 }
+
+/* ---- permittivity map as a palette ----------------------------------------------------------------
+ * A map holds few distinct values: vacuum, the materials, and the area-averaged cells along the
+ * material boundaries.  index[k] = position of map[k] in `table` (distinct bit patterns in order of
+ * first appearance, table[0] = the first cell's value); returns the number of distinct values, or -1
+ * when there are more than 65536 (the caller then uploads the dense map).  Open addressing on the
+ * 64-bit pattern; runs of equal neighbours -- almost every cell -- skip the table. */
+#include <stdint.h>
+#include <string.h>
+int mpifdtd_eps_palette(const double *map, size_t n, uint16_t *index, double *table)
+{
+  enum { SLOTS = 1 << 18 };                       /* 4 x the largest palette */
+  int32_t *slot = (int32_t *)malloc(sizeof(int32_t) * SLOTS);
+  if (slot == NULL) return -1;
+  memset(slot, 0xff, sizeof(int32_t) * SLOTS);
+  int n_values = 0;
+  uint64_t last_bits = 0;
+  int last_index = -1;
+  for (size_t k = 0; k < n; k++) {
+    uint64_t bits;
+    memcpy(&bits, &map[k], sizeof bits);
+    if (last_index >= 0 && bits == last_bits) { index[k] = (uint16_t)last_index; continue; }
+    uint64_t h = bits * 0x9e3779b97f4a7c15ull;
+    uint32_t at = (uint32_t)(h >> 46) & (SLOTS - 1);
+    for (;;) {
+      if (slot[at] < 0) {
+        if (n_values == 65536) { free(slot); return -1; }
+        slot[at] = n_values;
+        table[n_values++] = map[k];
+        break;
+      }
+      uint64_t have;
+      memcpy(&have, &table[slot[at]], sizeof have);
+      if (have == bits) break;
+      at = (at + 1) & (SLOTS - 1);
+    }
+    last_bits = bits;
+    last_index = slot[at];
+    index[k] = (uint16_t)last_index;
+  }
+  free(slot);
+  return n_values;
+}

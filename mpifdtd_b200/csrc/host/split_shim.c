@@ -30,7 +30,7 @@ typedef struct SplitSolver {
   double *coef[8];
   double *src[2];
   dcomplex *mirror[5];            /* host mirrors of the five fields              */
-  int mirror_reads[5];            /* refreshes so far; pinned in place at the third */
+  int mirror_reads[5];            /* refreshes so far; pinned in place at the first */
 } SplitSolver;
 
 static SplitSolver tm_plain = { .kind = B200FDTD_TM }, te_plain = { .kind = B200FDTD_TE };
@@ -539,11 +539,11 @@ static dcomplex *solver_field(SplitSolver *s, int slot)
 {
   if (s->engine == NULL) return NULL;
   const size_t mirror_bytes = sizeof(dcomplex) * (size_t)field_getFieldInfo_S().N_CELL;
-  if (s->mirror[slot] == NULL) {        /* only if somebody looks; pageable first, pinned in place once it is read often */
+  if (s->mirror[slot] == NULL) {        /* only if somebody looks */
     die_on(b200fdtd_mirror_alloc((void **)&s->mirror[slot], mirror_bytes), "mirror_alloc");
     s->mirror_reads[slot] = 0;
   }
-  if (++s->mirror_reads[slot] == 3) die_on(b200fdtd_mirror_pin(s->mirror[slot], mirror_bytes), "mirror_pin");
+  if (++s->mirror_reads[slot] == 1) die_on(b200fdtd_mirror_pin(s->mirror[slot], mirror_bytes), "mirror_pin");
   die_on(b200fdtd_get_field(s->engine, slot, (double *)s->mirror[slot]), "b200fdtd_get_field");
   return s->mirror[slot];
 }
@@ -570,7 +570,7 @@ static void solver_finish(SplitSolver *s)
   s->engine = NULL;
   free_host(s);
   for (int m = 0; m < 5; m++) {
-    b200fdtd_mirror_free(s->mirror[m], s->mirror_reads[m] >= 3);
+    b200fdtd_mirror_free(s->mirror[m], s->mirror_reads[m] >= 1);
     s->mirror[m] = NULL;  s->mirror_reads[m] = 0;
   }
 }

@@ -42,7 +42,7 @@ typedef struct UpmlSolver {
   int n_slabs;
   double *eps[3];                 /* host maps: TM EZ,HX,HY (HX/HY lazily) | TE EX,EY,HZ */
   dcomplex *mirror[3];            /* host mirrors for the X, Y, Z getters (lazy)    */
-  int mirror_reads[3];            /* refreshes so far; pinned in place at the third  */
+  int mirror_reads[3];            /* refreshes so far; pinned in place at the first   */
   size_t mirror_cells;
   int n_cell;
   int point_source;               /* opt-in, see mpifdtd_enablePointSource         */
@@ -389,9 +389,28 @@ static void solver_init(UpmlSolver *s)
     mpifdtd_fill_eps(s->eps[1], 0, 0.5, D_X);
   }
   lap("init: eps maps (host)", &t_lap);
-  for (int k = 0; k < s->n_slabs; k++)
-    for (int m = 0; m < n_eps; m++)
-      die_on(b200fdtd_set_eps(s->slab[k], m, s->eps[m]), "b200fdtd_set_eps");     /* each engine takes its columns */
+  /* upload: as 16-bit indices into the table of the map's distinct values where there are at most
+   * 65536 of them (2 instead of 8 bytes per cell over PCIe; MPIFDTD_EPS_DENSE=1 or a richer map: the
+   * dense doubles); each engine takes its columns */
+  {
+    const char *dense_env = getenv("MPIFDTD_EPS_DENSE");
+    const int want_palette = !(dense_env != NULL && dense_env[0] == '1');
+    uint16_t *index = want_palette ? (uint16_t *)malloc(sizeof(uint16_t) * (size_t)g.N_CELL) : NULL;
+    double *table = want_palette ? (double *)malloc(sizeof(double) * 65536) : NULL;
+    for (int m = 0; m < n_eps; m++) {
+      const int n_values = (index != NULL && table != NULL) ? mpifdtd_eps_palette(s->eps[m], (size_t)g.N_CELL, index, table) : -1;
+      for (int k = 0; k < s->n_slabs; k++) {
+        if (n_values > 0) {
+          int j0 = 0, nj = g.N_PY;
+          if (s->n_slabs > 1) slab_columns(g.N_PY, s->n_slabs, k, &j0, &nj);
+          die_on(b200fdtd_set_eps_palette(s->slab[k], m, index + j0, g.N_PY, table, n_values), "b200fdtd_set_eps_palette");
+        } else {
+          die_on(b200fdtd_set_eps(s->slab[k], m, s->eps[m]), "b200fdtd_set_eps");
+        }
+      }
+    }
+    free(index); free(table);
+  }
   lap("init: eps upload", &t_lap);
 
   double *ti = (double *)malloc(sizeof(double) * B200FDTD_UPML_TABS * g.N_PX);
@@ -810,7 +829,7 @@ static void solver_finish(UpmlSolver *s)
   free(s->eps_ringed); s->eps_ringed = NULL;
   for (int m = 0; m < 3; m++) {
     b200fdtd_mirror_free(s->eps[m], 0); s->eps[m] = NULL;
-    b200fdtd_mirror_free(s->mirror[m], s->mirror_reads[m] >= 3);
+    b200fdtd_mirror_free(s->mirror[m], s->mirror_reads[m] >= 1);
     s->mirror[m] = NULL;  s->mirror_reads[m] = 0;
   }
 }
@@ -823,9 +842,8 @@ static dcomplex *solver_field(UpmlSolver *s, int mirror, int slot)
     die_on(b200fdtd_mirror_alloc((void **)&s->mirror[mirror], sizeof(dcomplex) * s->mirror_cells), "mirror_alloc");
     s->mirror_reads[mirror] = 0;
   }
-  /* pinning is slow (~30 ms per 16 MB): a caller that looks once (batch mode) gets a pageable copy,
-   * one that keeps looking (the viewer's display()) a pinned mirror -- same pointer either way */
-  if (++s->mirror_reads[mirror] == 3)
+  /* a huge-page mapping, pinned in place the first time somebody looks (b200fdtd_mirror_alloc) */
+  if (++s->mirror_reads[mirror] == 1)
     die_on(b200fdtd_mirror_pin(s->mirror[mirror], sizeof(dcomplex) * s->mirror_cells), "mirror_pin");
   if (is_mpi_kind(s->kind)) {                                 /* (N+2) x (N+2) with a zero ring */
     FieldInfo_S g = field_getFieldInfo_S();

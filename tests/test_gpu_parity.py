@@ -177,6 +177,25 @@ def test_one_pass_default_at_4096_vs_oracle(plugin_lib, oracle, monkeypatch, in_
     gpu.finish()
 
 
+@pytest.mark.parametrize("solver,model", [("TM_UPML_2D", "MIE_CYLINDER"), ("TE_UPML_2D", "LAYER"),
+                                          ("TM_UPML_2D", "MORPHO_SCALE")])
+def test_palette_upload_equals_dense_upload(plugin_lib, monkeypatch, in_tmp_cwd, solver, model):
+    """simulator_init ships the permittivity map as 16-bit indices + a table of its distinct values
+    (b200fdtd_set_eps_palette) unless told otherwise: the device map, and with it every field, must
+    be what the dense upload gives, bit for bit."""
+    runs = {}
+    for form in ("palette", "dense"):
+        if form == "dense":
+            monkeypatch.setenv("MPIFDTD_EPS_DENSE", "1")
+        gpu = B.Plugin(model, solver, 150, 170, steps=300, h_u_nm=20, angle_deg=25)
+        gpu.run()
+        runs[form] = [gpu.any_field(s) for s in range(9)]
+        gpu.finish()
+    assert np.abs(runs["dense"][0]).max() > 0
+    for a, b in zip(runs["palette"], runs["dense"]):
+        assert bit_equal(a, b)
+
+
 # ---------------------------------------------------------------- lifecycle
 def test_reset_then_new_angle_matches_fresh_run(plugin_lib, oracle):
     """main.c:207-209: simulator_reset() writes the far field, zeroes state, then the

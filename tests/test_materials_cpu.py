@@ -101,3 +101,25 @@ def test_eps_map_bit_exact_vs_live_reference(plugin_lib, model):
             want = reflib.eps_map(model, npx, npy, xo, yo, mode, h_u_nm=hu)
             mine = product_eps(plugin_lib, model, npx, npy, hu, xo, yo, mode)
             assert bit_equal(mine, want)
+
+
+def test_eps_palette_round_trips_every_model(plugin_lib):
+    """mpifdtd_eps_palette: 16-bit indices into the table of a map's distinct values reproduce the map
+    bit for bit (what b200fdtd_set_eps_palette ships over PCIe instead of the doubles); a map with more
+    than 65536 distinct values is refused (-1: the dense upload is used)."""
+    import ctypes as C
+    L = plugin_lib
+    n = 160
+    for model in ("MIE_CYLINDER", "LAYER", "ZIGZAG", "MORPHO_SCALE", "NO_MODEL"):
+        L.models_setModel(B.MODELS[model])
+        L.field_init(B.FieldInfo(n * 10, n * 10, 10, 10, 500, 0, 10))
+        L.models_initModel()
+        eps = np.empty((n, n))
+        L.mpifdtd_fill_eps(eps.ctypes.data, 0.0, 0.0, B.D_XY)
+        index, table = np.zeros((n, n), dtype=np.uint16), np.zeros(65536)
+        count = L.mpifdtd_eps_palette(eps.ctypes.data, eps.size, index.ctypes.data, table.ctypes.data)
+        assert 1 <= count <= 65536 and count == len(np.unique(eps)), model
+        assert np.array_equal(table[index].view(np.uint64), eps.view(np.uint64)), model
+    rich = np.random.default_rng(0).random((300, 300))
+    index, table = np.zeros(rich.shape, dtype=np.uint16), np.zeros(65536)
+    assert L.mpifdtd_eps_palette(rich.ctypes.data, rich.size, index.ctypes.data, table.ctypes.data) == -1
