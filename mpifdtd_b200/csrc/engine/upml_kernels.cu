@@ -405,7 +405,7 @@ __global__ void __launch_bounds__(kBlock, B200_TE_E_MIN_BLOCKS) te_upml_e_kernel
 // Same arrays, same 264 / 288 B per cell-update, bit-identical to the one-kernel-per-phase form
 // (tests/test_gpu_unit.py); what it buys is registers (more blocks per SM, more loads in flight).
 // The frame goes through the full kernels (RECTS = true), exactly as in the lean form below.
-// blocks/SM measured at 16384^2 (scripts/variant_bench.sh): TM H 4/5/6/7/8 -> 5.60/5.60/5.58/5.67/5.67 ms,
+// blocks/SM measured at 16384^2 (round 1, A/B builds): TM H 4/5/6/7/8 -> 5.60/5.60/5.58/5.67/5.67 ms,
 // TM E 4/5/6/7 -> 5.41/4.93/5.00/5.03 ms, TE E 4/5/6/7/8 -> 8.65/8.68/8.60/10.0/10.0 ms
 #ifndef B200_UNIT_H_MIN_BLOCKS
 #define B200_UNIT_H_MIN_BLOCKS 6
