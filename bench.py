@@ -610,9 +610,18 @@ def gpu_arm(args):
     device_bytes = run.engine.device_bytes()
     e2e_plugin = None
     if rank == 0 and world == 1 and not args.no_plugin_leg and args.precision == "f64" and not args.lean:
-        run.close()
-        run = None
+        if run is not None:
+            run.close()
+            run = None
         e2e_plugin = plugin_leg(B, args, K)
+
+    # ---- the deferred NTFF projection over a history of realistic length (N = 1) -----------------------
+    ntff_leg = None
+    if rank == 0 and world == 1 and not args.no_ntff_leg:
+        if run is not None:
+            run.close()
+            run = None
+        ntff_leg = ntff_projection_leg(B, args, local_rank)
 
     if rank == 0:
         peak, peak_kind = measured_hbm_peak()
@@ -695,6 +704,10 @@ def gpu_arm(args):
         }
         if e2e_plugin is not None:
             line["e2e_plugin"] = e2e_plugin
+        if ntff_leg is not None:
+            ntff_leg["value_with_amortised_projection"] = (
+                cells / ((ms_max / K + ntff_leg["ms_per_step_amortised"]) * 1e-3) / 1e9)
+            line["ntff_projection"] = ntff_leg
         if parity is not None:
             line["parity_check"] = parity["result"]
             line["parity_detail"] = parity
@@ -734,6 +747,48 @@ def gpu_arm(args):
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def ntff_projection_leg(B, args, device, history=2048):
+    """The K timed steps of `value` record K surface samples, and the deferred projection over so
+    short a history finds few taps -- the reference, by contrast, pays its 360-direction binning every
+    step.  This leg prices the GPU's share honestly: the projection kernel over a FULL history of
+    `history` steps on the benchmark's surface (65 k points at 16384^2), on an engine that holds only
+    the NTFF machinery (B200FDTD_GRID_NTFF_ONLY), amortised per step."""
+    import numpy as np
+    L = B.lib()
+    n = args.n
+    kind = 2 if args.solver == "TM_UPML_2D" else 3
+    L.models_setModel(B.MODELS["NO_MODEL"])
+    L.field_init(B.FieldInfo(n * 10, n * 10, 10, 10, 500, 0, history))
+    grid = B.Grid(kind, n, n, 10, 0, n, 1, n - 2, 1, n - 2, device, 0, B.MU_0_S, 1, 1)      # flags = NTFF only
+    h = ctypes.c_void_p()
+    B.check(L.b200fdtd_create(ctypes.byref(grid), ctypes.byref(h)), "create")
+    try:
+        box = L.field_getNTFFInfo()
+        n_points = L.mpifdtd_ntff_point_count(ctypes.byref(box))
+        ptr = L.mpifdtd_ntff_time_shift(ctypes.byref(box), 360, 0.0 if kind == 2 else 0.5, 0, n)
+        plan = B.NtffPlan(box.top, box.bottom, box.left, box.right, n_points, n_points, history, history, 360,
+                          box.arraySize, ptr)
+        B.check(L.b200fdtd_set_ntff_plan(h, ctypes.byref(plan)), "set_ntff_plan")
+        L.free(ptr)
+        rng = np.random.default_rng(3)
+        samples = rng.standard_normal(2 * n_points) + 0.0
+        L.b200fdtd_ntff_push_samples.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p]
+        for t in (0, history // 2, history - 1):          # the last one marks the whole history as recorded
+            B.check(L.b200fdtd_ntff_push_samples(h, t, samples.ctypes.data, samples.ctypes.data), "push_samples")
+        B.check(L.b200fdtd_ntff_project(h), "project")      # warm-up
+        B.check(L.b200fdtd_sync(h), "sync")
+        ms = ctypes.c_float(0)
+        B.check(L.b200fdtd_timer_start(h), "timer_start")
+        B.check(L.b200fdtd_ntff_project(h), "project")
+        B.check(L.b200fdtd_timer_stop(h, ctypes.byref(ms)), "timer_stop")
+        return {"history_steps": history, "surface_points": n_points, "directions": 360,
+                "project_ms": ms.value, "ms_per_step_amortised": ms.value / history,
+                "note": "ntff_project_kernel over a full %d-step history of the benchmark's surface; the reference "
+                        "scatters 360 x points x 6 taps EVERY step (ntffTM.c:279-371), ~85 %% of its step" % history}
+    finally:
+        L.b200fdtd_destroy(h)
 
 
 def plugin_leg(B, args, K):
@@ -824,6 +879,7 @@ def main():
                     help="material-cell fraction of the extra `dense` measurement (0 = skip)")
     ap.add_argument("--no-parity-check", action="store_true", help="N > 1: skip the bit-identity check")
     ap.add_argument("--no-plugin-leg", action="store_true", help="N = 1: skip the e2e_plugin measurement")
+    ap.add_argument("--no-ntff-leg", action="store_true", help="N = 1: skip the NTFF projection measurement")
     ap.add_argument("--plugin-n", type=int, default=4096, help="grid side of the e2e_plugin leg")
     ap.add_argument("--solver", default="TM_UPML_2D", choices=["TM_UPML_2D", "TE_UPML_2D"],
                     help="TM_UPML_2D is the BASELINE workload; TE_UPML_2D is reported for information")

@@ -13,6 +13,12 @@
 // cell, 128-bit accesses; arithmetic keeps the reference's operand order (-fmad=false).
 #include "upml_common.cuh"
 
+// Resident blocks per SM the kernels are compiled for (register cap 65536 / (256 * n)).  A/B at 4096^2
+// (scripts/gpu_jobs/r02_j22.sh): the TE pair and the NS-FDTD TM pair gain 4-7 % at 6 blocks (id 1 27.7 ->
+// 29.6, id 6 25.7 -> 26.7 Gcell-updates/s, id 7 unchanged), the Berenger TM pair loses 5 %; 8 blocks spill.
+#define B200_SPLIT_TE_MIN_BLOCKS 6
+#define B200_SPLIT_TM_MIN_BLOCKS(NS) ((NS) ? 6 : 1)
+
 namespace {
 
 using namespace upml;
@@ -96,7 +102,7 @@ __device__ __forceinline__ double over_den(double g, double den) { return den ==
 // LEAN: see b200fdtd.h "lean form".  Kind 0 (Berenger): the four H coefficients are 1-D tables.
 // Kind 6 (NS): decay coefficients 1-D, curl coefficients G[k] / DEN (1-D).
 template <bool NS, bool LEAN>
-__global__ void __launch_bounds__(kBlock) split_tm_h_kernel(const SplitView v)
+__global__ void __launch_bounds__(kBlock, B200_SPLIT_TM_MIN_BLOCKS(NS)) split_tm_h_kernel(const SplitView v)
 {
   int r, c; size_t k;
   if (!locate(v, r, c, k)) return;
@@ -135,7 +141,7 @@ __global__ void __launch_bounds__(kBlock) split_tm_h_kernel(const SplitView v)
 }
 
 template <bool NS, bool LEAN>
-__global__ void __launch_bounds__(kBlock) split_tm_e_kernel(const SplitView v)
+__global__ void __launch_bounds__(kBlock, B200_SPLIT_TM_MIN_BLOCKS(NS)) split_tm_e_kernel(const SplitView v)
 {
   int r, c; size_t k;
   if (!locate(v, r, c, k)) return;
@@ -178,7 +184,7 @@ __global__ void __launch_bounds__(kBlock) split_tm_e_kernel(const SplitView v)
 // ---------------------------------------------------------------- TE family ------
 // slots: 0 Hz 1 Hzx 2 Hzy 3 Ex 4 Ey
 template <bool NS, bool LEAN, bool INTERIOR = false>          // LEAN: kind 1 only (NS TE keeps its dense arrays)
-__global__ void __launch_bounds__(kBlock) split_te_e_kernel(const SplitView v)
+__global__ void __launch_bounds__(kBlock, B200_SPLIT_TE_MIN_BLOCKS) split_te_e_kernel(const SplitView v)
 {
   int r, c; size_t k;
   if (!locate(v, r, c, k)) return;
@@ -229,7 +235,7 @@ __global__ void __launch_bounds__(kBlock) split_te_e_kernel(const SplitView v)
 // INTERIOR (NS TE, kind 7): thread blocks inside the rectangle of b200fdtd_set_split_interior -- decay
 // coefficients exactly 1.0, the two curl coefficients equal -- read three arrays fewer: same bits
 template <bool LEAN, bool INTERIOR = false>
-__global__ void __launch_bounds__(kBlock) split_te_h_kernel(const SplitView v)
+__global__ void __launch_bounds__(kBlock, B200_SPLIT_TE_MIN_BLOCKS) split_te_h_kernel(const SplitView v)
 {
   int r, c; size_t k;
   if (!locate(v, r, c, k)) return;
