@@ -1002,8 +1002,26 @@ int b200fdtd_step(b200fdtd_engine *e, const b200fdtd_step_args *a)
   if (kind_is_split(e->g.kind)) return b200_launch_split_step(e, a);
   const bool e_first = (e->g.kind == B200FDTD_MPI_TM_UPML || e->g.kind == B200FDTD_MPI_TE_UPML);
   const bool peers = e->peer.attached[0] || e->peer.attached[1];
-  if (peers && e_first)
-    return b200_fail(B200FDTD_ERR_STATE, "peer halos serve the H-first UPML kinds (2, 3)");
+  if (peers && e_first) {
+    // mpiTM_UPML.c:196-217 on a y-slab: E, source, [Ez/Ex column down], H, [Hx/Hz column up], NTFF --
+    // the reference's two MPI_Sendrecv exchanges as peer stores behind the same two flags.
+    const unsigned long long step = (unsigned long long)a->time;
+    // my low ghost column of H: the lower neighbour's H phase of step-1.  Its signal also says that
+    // phase has finished reading the high ghost column my E phase is about to overwrite.
+    if (e->peer.attached[0] && step > 0) { rc = b200_peer_wait(e, 0, step); if (rc) return rc; }
+    rc = b200_launch_upml_e(e, a);
+    if (!rc && e->peer.attached[0]) rc = b200_peer_signal(e, e->peer.down_flag, step + 1);
+    // my high ghost column of E: the upper neighbour's E phase of this step (which has also finished
+    // reading the low ghost column my H phase overwrites, as has its NTFF sample of step-1)
+    if (!rc && e->peer.attached[1]) rc = b200_peer_wait(e, 1, step + 1);
+    if (!rc) rc = b200_launch_upml_h(e, a);
+    if (!rc && e->peer.attached[1]) rc = b200_peer_signal(e, e->peer.up_flag, step + 1);
+    // the surface sample averages H over columns j-1 and j: on my first owned column that is the
+    // lower neighbour's H of THIS step
+    if (!rc && e->ntff.ready && e->peer.attached[0]) rc = b200_peer_wait(e, 0, step + 1);
+    if (!rc) rc = b200_launch_ntff_sample(e, a);
+    return rc;
+  }
   if (peers && !b200_want_fused(e, a)) {
     // two-kernel forms on a slab with neighbours: the phase entry points carry the flag protocol
     // (wait for the neighbour's halo, launch, signal) -- never a bare launch next to a peer store

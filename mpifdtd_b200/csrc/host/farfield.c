@@ -87,11 +87,21 @@ double *mpifdtd_ntff_time_shift(const NTFFInfo *box, int n_angles, double stagge
 /* The MPI-variant solvers' ntff() (mpiTM_UPML.c:849-1037, mpiTE_UPML.c:602-794) evaluates
  * timeShift = -(r1x*r2x + r1y*r2y)/C + RFperC afresh at every surface point, with
  * r1 = (cos, sin) NOT pre-divided by C, and (TE) the half-cell stagger added to the integer
- * difference: r2x = i - cx + 0.5.  Same point order as above; whole surface (one rank). */
-double *mpifdtd_ntff_time_shift_direct(const NTFFInfo *box, int n_angles, double stagger)
+ * difference: r2x = i - cx + 0.5.  Same point order as above.  A y-slab keeps the points whose
+ * SAMPLED cell column j + sample_dj lies in [j0, j0+nj) (these solvers read one cell down-left of
+ * where r2 says); the whole surface with j0 = 0, nj = N_PY. */
+int mpifdtd_ntff_local_count_shifted(const NTFFInfo *box, int sample_dj, int j0, int nj)
+{
+  NTFFInfo moved = *box;
+  moved.bottom += sample_dj;
+  moved.top += sample_dj;
+  return mpifdtd_ntff_local_count(&moved, j0, nj);
+}
+
+double *mpifdtd_ntff_time_shift_direct(const NTFFInfo *box, int n_angles, double stagger, int sample_dj, int j0, int nj)
 {
   const int nx = box->right - box->left, ny = box->top - box->bottom;
-  const int P = 2 * nx + 2 * ny;
+  const int P = mpifdtd_ntff_local_count_shifted(box, sample_dj, j0, nj);
   double *table = (double *)malloc(sizeof(double) * (size_t)n_angles * (size_t)(P > 0 ? P : 1));
   if (table == NULL) { printf("cannot allocate NTFF time-shift table\n"); exit(2); }
   const int cx = box->cx, cy = box->cy;          /* N_PX/2 - offsetX with offset 0 */
@@ -112,6 +122,8 @@ double *mpifdtd_ntff_time_shift_direct(const NTFFInfo *box, int n_angles, double
           const int i = (edge == 1) ? box->right : box->left, j = box->bottom + n;
           r2x = i - cx;            r2y = j - cy + stagger;
         }
+        const int j_point = along_x ? ((edge == 0) ? box->bottom : box->top) : box->bottom + n;
+        if (j_point + sample_dj < j0 || j_point + sample_dj >= j0 + nj) continue;
         row[q++] = -(r1x * r2x + r1y * r2y) / C_0_S + box->RFperC;
       }
     }

@@ -332,7 +332,7 @@ static void solver_init(UpmlSolver *s)
     s->n_batch = batch_requested;
     memcpy(s->batch_angles, batch_angles_requested, sizeof(int) * (size_t)batch_requested);
   }
-  s->n_slabs = (mpi || s->n_batch > 1) ? 1 : slabs_for_next_init();
+  s->n_slabs = s->n_batch > 1 ? 1 : slabs_for_next_init();
   if (s->n_slabs > g.N_PY / 4) s->n_slabs = g.N_PY / 4 > 0 ? g.N_PY / 4 : 1;
   if (s->n_slabs > 1) s->defer = 0;     /* multi-step replay is a single-engine feature */
 
@@ -436,18 +436,25 @@ static void solver_init(UpmlSolver *s)
     memset(&mp, 0, sizeof mp);
     mp.top = box.top; mp.bottom = box.bottom; mp.left = box.left; mp.right = box.right;
     mp.n_points = mpifdtd_ntff_point_count(&box);
-    mp.n_local = mp.n_points;
     mp.max_time = (int)field_getMaxTime();
     mp.n_bins = getenv("MPIFDTD_NTFF_FULL_BINS") ? box.arraySize : mp.max_time;
     mp.n_angles = N_ANGLES;
     mp.array_size = box.arraySize;
     mp.tap_scale = 1.0 / (4 * M_PI * C_0_S * 1.0e6);
     mp.sample_di = -1; mp.sample_dj = -1;
-    double *direct = mpifdtd_ntff_time_shift_direct(&box, N_ANGLES, tm ? 0.0 : 0.5);
-    mp.time_shift = direct;
-    if (mp.n_points > 0 && mp.max_time > 0)
-      die_on(b200fdtd_set_ntff_plan(s->engine, &mp), "b200fdtd_set_ntff_plan");
-    free(direct);
+    /* Several slabs: ONE surface over the whole grid (the single-rank meaning of the reference's
+     * ntff(); with more ranks upstream integrates every rank's own sub-grid over the same local
+     * indices and never sums the pieces), each slab sampling the cells it owns. */
+    for (int k = 0; k < s->n_slabs; k++) {
+      int j0 = 0, nj = g.N_PY;
+      if (s->n_slabs > 1) slab_columns(g.N_PY, s->n_slabs, k, &j0, &nj);
+      mp.n_local = mpifdtd_ntff_local_count_shifted(&box, mp.sample_dj, j0, nj);
+      double *direct = mpifdtd_ntff_time_shift_direct(&box, N_ANGLES, tm ? 0.0 : 0.5, mp.sample_dj, j0, nj);
+      mp.time_shift = direct;
+      if (mp.n_points > 0 && mp.max_time > 0)
+        die_on(b200fdtd_set_ntff_plan(s->slab[k], &mp), "b200fdtd_set_ntff_plan");
+      free(direct);
+    }
     return;
   }
 
@@ -761,7 +768,10 @@ int mpifdtd_mpi_te_far_series(dcomplex *eth, dcomplex *eph)
   const int n_bins = getenv("MPIFDTD_NTFF_FULL_BINS") ? field_getNTFFInfo().arraySize : max_time;
   const size_t count = (size_t)N_ANGLES * (size_t)n_bins;
   dcomplex *uw[3];
-  die_on(b200fdtd_ntff_project(s->engine), "b200fdtd_ntff_project");
+  for (int k = 0; k < s->n_slabs; k++) die_on(b200fdtd_sync(s->slab[k]), "b200fdtd_sync");
+  for (int k = 0; k < s->n_slabs; k++) die_on(b200fdtd_ntff_project(s->slab[k]), "b200fdtd_ntff_project");
+  for (int k = 1; k < s->n_slabs; k++)   /* partial sums of the slabs -> slab 0, in slab order */
+    die_on(b200fdtd_ntff_add_uw(s->slab[0], s->slab[k]), "b200fdtd_ntff_add_uw");
   for (int m = 0; m < 3; m++) {
     uw[m] = (dcomplex *)malloc(sizeof(dcomplex) * count);
     die_on(b200fdtd_ntff_get_uw(s->engine, m, (double *)uw[m]), "b200fdtd_ntff_get_uw");
@@ -847,8 +857,12 @@ static dcomplex *solver_field(UpmlSolver *s, int mirror, int slot)
     die_on(b200fdtd_mirror_pin(s->mirror[mirror], sizeof(dcomplex) * s->mirror_cells), "mirror_pin");
   if (is_mpi_kind(s->kind)) {                                 /* (N+2) x (N+2) with a zero ring */
     FieldInfo_S g = field_getFieldInfo_S();
-    double *first = (double *)(s->mirror[mirror] + (size_t)(g.N_PY + 2) + 1);
-    die_on(b200fdtd_get_field_ld(s->engine, slot, first, g.N_PY + 2), "b200fdtd_get_field_ld");
+    for (int k = 0; k < s->n_slabs; k++) {
+      int j0 = 0, nj = g.N_PY;
+      if (s->n_slabs > 1) slab_columns(g.N_PY, s->n_slabs, k, &j0, &nj);
+      double *first = (double *)(s->mirror[mirror] + (size_t)(g.N_PY + 2) + 1 + j0);
+      die_on(b200fdtd_get_field_ld(s->slab[k], slot, first, g.N_PY + 2), "b200fdtd_get_field_ld");
+    }
     return s->mirror[mirror];
   }
   for (int k = 0; k < s->n_slabs; k++)               /* every slab lands in its own columns of the mirror */
@@ -920,19 +934,31 @@ int mpi_fdtdTE_upml_getSubNpx(void)   { return N_PX + 2; }
 int mpi_fdtdTE_upml_getSubNpy(void)   { return N_PY + 2; }
 int mpi_fdtdTE_upml_getSubNcell(void) { return (N_PX + 2) * (N_PY + 2); }
 
+static UpmlSolver *solver_of_kind(int kind)
+{
+  switch (kind) {
+  case B200FDTD_TM_UPML:     return &tm_solver;
+  case B200FDTD_TE_UPML:     return &te_solver;
+  case B200FDTD_MPI_TM_UPML: return &mpi_tm_solver;
+  case B200FDTD_MPI_TE_UPML: return &mpi_te_solver;
+  default:                   return NULL;
+  }
+}
+
 /* engine handle of the active serial UPML solver, for harnesses that want device
  * timers or the U/W arrays (not part of the reference surface) */
 /* slab g of the active serial UPML solver (NULL past the end), and how many there are */
 b200fdtd_engine *mpifdtd_upml_slab_engine(int kind, int g)
 {
-  UpmlSolver *s = kind == B200FDTD_TM_UPML ? &tm_solver : kind == B200FDTD_TE_UPML ? &te_solver : NULL;
+  UpmlSolver *s = solver_of_kind(kind);
   if (s == NULL || g < 0 || g >= s->n_slabs) return NULL;
   flush_pending(s);
   return s->slab[g];
 }
 int mpifdtd_upml_slab_count(int kind)
 {
-  return kind == B200FDTD_TM_UPML ? tm_solver.n_slabs : kind == B200FDTD_TE_UPML ? te_solver.n_slabs : 0;
+  UpmlSolver *s = solver_of_kind(kind);
+  return s != NULL ? s->n_slabs : 0;
 }
 
 b200fdtd_engine *mpifdtd_upml_engine(int kind)

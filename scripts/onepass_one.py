@@ -14,6 +14,7 @@ model = sys.argv[7] if len(sys.argv) > 7 else "ZIGZAG"
 run = SlabRun(model, solver, n, n, 64, with_ntff=False)
 e = run.engine
 run.L.mpifdtd_upml_step_args(run.kind, 0, B.C.byref(run.args))
+e.set_option(B.OPT_FUSED, 1)
 e.set_option(B.OPT_LEAN_INTERIOR, lean)
 e.set_option(B.OPT_FUSED_SHAPE, shape)
 e.set_option(B.OPT_BAND_ROWS, band)

@@ -58,6 +58,46 @@ def test_plugin_with_several_slabs_matches_single_engine(plugin_lib, in_tmp_cwd,
     assert rel_err(res[n_slabs][2], res[1][2]) <= 1e-12
 
 
+@pytest.mark.parametrize("solver,names", [("MPI_TM_UPML_2D", ("Ez", "Hx", "Hy")), ("MPI_TE_UPML_2D", ("Ex", "Ey", "Hz"))])
+@pytest.mark.parametrize("n_slabs", [2, 5])
+def test_mpi_variant_solvers_with_several_slabs(plugin_lib, in_tmp_cwd, monkeypatch, solver, names, n_slabs):
+    """Ids 4/5 -- the reference's own domain-decomposed solvers (E phase first, CW source, all N x N cells
+    updated, getters with a ghost ring: mpiTM_UPML.c:196-217,674-743) -- over several slabs: the two
+    MPI_Sendrecv exchanges become peer stores.  Fields, state arrays and the projected U/W partial
+    sums must reproduce the single-engine run (fields bit for bit, U/W to summation order)."""
+    monkeypatch.setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+    monkeypatch.setenv("MPIFDTD_NTFF_FULL_BINS", "1")
+    npx, npy, steps = 110, 230, 300
+    L = plugin_lib
+    res = {}
+    for n in (1, n_slabs):
+        L.mpifdtd_setDevices(n)
+        try:
+            gpu = B.Plugin("MIE_CYLINDER", solver, npx, npy, steps=steps, h_u_nm=20, angle_deg=35)
+            assert L.mpifdtd_upml_slab_count(gpu.solver) == n
+            gpu.run()
+            getters = [gpu.field(f).copy() for f in names]
+            assert getters[0].shape == (npx + 2, npy + 2)
+            state = [gather(gpu, s) for s in range(9)]
+            uw = []
+            if solver == "MPI_TE_UPML_2D":                      # the series finish() prints (mpiTE_UPML.c:795-878)
+                eth = np.zeros((360, steps), dtype=np.complex128)
+                eph = np.zeros((360, steps), dtype=np.complex128)
+                L.mpifdtd_mpi_te_far_series.argtypes = [C.c_void_p, C.c_void_p]
+                assert L.mpifdtd_mpi_te_far_series(eth.ctypes.data, eph.ctypes.data) == 0
+                uw = [eth, eph]
+            gpu.finish()
+        finally:
+            L.mpifdtd_setDevices(0)
+        res[n] = (getters, state, uw)
+    assert np.abs(res[1][0][0]).max() > 0
+    for a, b in zip(res[n_slabs][0] + res[n_slabs][1], res[1][0] + res[1][1]):
+        assert bit_equal(a, b)
+    for a, b in zip(res[n_slabs][2], res[1][2]):
+        assert np.abs(b).max() > 0
+        assert rel_err(a, b) <= 1e-12
+
+
 def test_c_driver_with_devices_from_the_environment(plugin_lib, tmp_path):
     """An unmodified C driver of the plugin surface (tests/c/dropin_driver.c) goes multi-GPU by
     environment alone: same stdout line (cell count, peak of the getter's array, material cells),
