@@ -161,6 +161,17 @@ typedef struct b200fdtd_batch_source {
   double t0[2];
 } b200fdtd_batch_source;
 
+/* Per-simulation part of the continuous-wave source of a batched split-field engine (kinds 0, 1,
+ * 6, 7): what of b200fdtd_cw depends on the incidence angle.  step_args.cw[m] then carries what the
+ * simulations share -- gaps, phases, two_term, and scale = ray_coef WITHOUT the polarisation
+ * factor; the kernels form scale * dot[m] (the host's own multiplication, field.c:160) and take
+ * enabled[m], ks_cos, ks_sin from here.  Uploaded once per sweep with b200fdtd_set_batch_cw. */
+typedef struct b200fdtd_batch_cw {
+  double ks_cos, ks_sin;           /* cos(rad)*k_s, sin(rad)*k_s from host libm        */
+  double dot[2];                   /* 1.0, or cos / sin(angle + 90 deg) for kind 7     */
+  int32_t enabled[2];
+} b200fdtd_batch_cw;
+
 /* Opt-in soft-started point source for the NoModel configuration:
  * value field_pointLight() (field.c:145-152) added to E-slot 0 at (i, j). */
 typedef struct b200fdtd_point_source {
@@ -290,6 +301,8 @@ int b200fdtd_set_eps_palette(b200fdtd_engine *e, int32_t eps_slot, const uint16_
 int b200fdtd_set_ntff_plan(b200fdtd_engine *e, const b200fdtd_ntff_plan *plan);   /* ntffTM_init */
 /* batched engines: the n_batch per-simulation sources (host array) */
 int b200fdtd_set_batch_sources(b200fdtd_engine *e, const b200fdtd_batch_source *sources);
+/* batched split-field engines: the n_batch per-simulation CW records (host array) */
+int b200fdtd_set_batch_cw(b200fdtd_engine *e, const b200fdtd_batch_cw *sources);
 /* batched engines: the simulation the state-access and NTFF read-out calls below refer to
  * (get/set_field*, ntff_get_uw, ntff_spectrum, ntff_frequency); default 0 */
 int b200fdtd_select_batch(b200fdtd_engine *e, int32_t index);

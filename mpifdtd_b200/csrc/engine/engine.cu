@@ -129,6 +129,7 @@ int b200fdtd_struct_size(int32_t which)
   case 3: return (int)sizeof(b200fdtd_spectrum_args);
   case 4: return (int)sizeof(b200fdtd_freq_args);
   case 5: return (int)sizeof(b200fdtd_batch_source);
+  case 6: return (int)sizeof(b200fdtd_batch_cw);
   default: return -1;
   }
 }
@@ -237,10 +238,10 @@ int b200fdtd_create(const b200fdtd_grid *grid, b200fdtd_engine **out)
   if (grid->precision == B200FDTD_F32 && !kind_is_upml(grid->kind))
     return b200_fail(B200FDTD_ERR_ARG, "the single-precision path serves the UPML kinds (2-5)");
   const int n_batch = grid->n_batch > 1 ? grid->n_batch : 1;
-  if (n_batch > 1 && ((grid->kind != B200FDTD_TM_UPML && grid->kind != B200FDTD_TE_UPML) ||
+  if (n_batch > 1 && ((grid->kind != B200FDTD_TM_UPML && grid->kind != B200FDTD_TE_UPML && !kind_is_split(grid->kind)) ||
                       grid->j0 != 0 || grid->nj != grid->n_py || n_batch > 65535))
-    return b200_fail(B200FDTD_ERR_ARG, "batched engines serve the serial UPML kinds (2, 3) with the whole "
-                                       "grid on one engine, n_batch <= 65535");
+    return b200_fail(B200FDTD_ERR_ARG, "batched engines serve the serial UPML kinds (2, 3) and the split-field "
+                                       "kinds (0, 1, 6, 7) with the whole grid on one engine, n_batch <= 65535");
 
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
@@ -312,6 +313,7 @@ int b200fdtd_create(const b200fdtd_grid *grid, b200fdtd_engine **out)
     // call for their slot: the lean form needs only a few of them
     rc = dev_alloc_zero(e, (void **)&e->tab_i, sizeof(double) * B200FDTD_SPLIT_TABS * e->rows);
     if (!rc) rc = dev_alloc_zero(e, (void **)&e->tab_j, sizeof(double) * B200FDTD_SPLIT_TABS * e->pitch);
+    if (!rc && n_batch > 1) rc = dev_alloc_zero(e, (void **)&e->batch_cw, sizeof(b200fdtd_batch_cw) * (size_t)n_batch);
   } else {
     const int n_eps = (grid->kind == B200FDTD_TM_UPML || grid->kind == B200FDTD_MPI_TM_UPML) ? 1 : 2;
     for (int s = 0; s < n_eps && !rc; s++)
@@ -358,7 +360,7 @@ int b200fdtd_destroy(b200fdtd_engine *e)
   if (e->stream) cudaStreamSynchronize(e->stream);
   for (int s = 0; s < B200FDTD_MAX_FIELDS; s++) cudaFree(e->field[s]);
   cudaFree(e->eps[0]); cudaFree(e->eps[1]);
-  cudaFree(e->tab_i); cudaFree(e->tab_j); cudaFree(e->batch_src); cudaFree(e->clock_dev);
+  cudaFree(e->tab_i); cudaFree(e->tab_j); cudaFree(e->batch_src); cudaFree(e->batch_cw); cudaFree(e->clock_dev);
   if (e->graph_exec) cudaGraphExecDestroy((cudaGraphExec_t)e->graph_exec);
   for (int s = 0; s < B200FDTD_MAX_DENSE; s++) cudaFree(e->dense[s]);
   free_ntff(e);
@@ -797,6 +799,18 @@ int b200fdtd_set_batch_sources(b200fdtd_engine *e, const b200fdtd_batch_source *
   return B200FDTD_OK;
 }
 
+int b200fdtd_set_batch_cw(b200fdtd_engine *e, const b200fdtd_batch_cw *sources)
+{
+  if (!e || !sources) return b200_fail(B200FDTD_ERR_ARG, "NULL argument");
+  if (!e->batch_cw) return b200_fail(B200FDTD_ERR_ARG, "batch CW records serve batched split-field engines");
+  int rc = select_device(e); if (rc) return rc;
+  B200_CUDA(cudaMemcpyAsync(e->batch_cw, sources, sizeof(b200fdtd_batch_cw) * (size_t)e->n_batch,
+                            cudaMemcpyHostToDevice, e->stream));
+  B200_CUDA(cudaStreamSynchronize(e->stream));
+  e->have_batch_cw = true;
+  return B200FDTD_OK;
+}
+
 int b200fdtd_select_batch(b200fdtd_engine *e, int32_t index)
 {
   if (!e || index < 0 || index >= e->n_batch) return b200_fail(B200FDTD_ERR_ARG, "batch index %d out of range", index);
@@ -877,6 +891,8 @@ static int check_ready(b200fdtd_engine *e, const b200fdtd_step_args *a)
   if (!e || !a) return b200_fail(B200FDTD_ERR_ARG, "NULL argument");
   if (e->n_fields == 0) return b200_fail(B200FDTD_ERR_STATE, "an NTFF-only engine has no fields to step");
   if (kind_is_split(e->g.kind)) {
+    if (e->n_batch > 1 && !e->have_batch_cw)
+      return b200_fail(B200FDTD_ERR_STATE, "step of a batched engine before set_batch_cw");
     if (e->split_lean) {            // 1-D tables + eps (kinds 0, 1) or G arrays + source factor (kind 6)
       const int k = e->g.kind;
       if (k == B200FDTD_NS_TM) {

@@ -76,6 +76,8 @@ struct b200fdtd_engine {
   int sel;                  // simulation the getters / NTFF read-out refer to
   b200fdtd_batch_source *batch_src;   // device [n_batch], or nullptr
   bool have_batch_src;
+  b200fdtd_batch_cw *batch_cw;        // device [n_batch]: batched split-field engines, or nullptr
+  bool have_batch_cw;
   int n_fields;
   bool fp32;                // optional single-precision path: the arrays below then hold
   size_t csize, rsize;      //   float2 / float elements (csize = 8, rsize = 4) behind the same pointers

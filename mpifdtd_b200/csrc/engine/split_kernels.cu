@@ -35,6 +35,8 @@ struct SplitView {
   int j_base;
   b200fdtd_cw cw[2];
   double ns_r2;
+  size_t plane;                         // batched engines: elements per simulation (blockIdx.y selects it)
+  const b200fdtd_batch_cw *batch;       // batched engines: per-simulation part of the CW source
 };
 
 __device__ __forceinline__ bool locate(const SplitView &v, int &r, int &c, size_t &k)
@@ -72,6 +74,26 @@ __device__ __forceinline__ double2 cw_term(const b200fdtd_cw &s, int i, int j, d
   return make_double2(amp * wave.x, amp * wave.y);
 }
 
+// The CW record of this thread block's simulation.  Batched engines (BATCH): the angle-dependent
+// members come from the per-simulation record, scale = ray_coef * dot as the host forms it.
+template <bool BATCH>
+__device__ __forceinline__ bool cw_on(const SplitView &v, int m)
+{
+  return BATCH ? v.batch[blockIdx.y].enabled[m] != 0 : v.cw[m].enabled != 0;
+}
+template <bool BATCH>
+__device__ __forceinline__ b200fdtd_cw cw_of(const SplitView &v, int m)
+{
+  b200fdtd_cw s = v.cw[m];
+  if (BATCH) {
+    const b200fdtd_batch_cw b = v.batch[blockIdx.y];
+    s.ks_cos = b.ks_cos;
+    s.ks_sin = b.ks_sin;
+    s.scale = s.scale * b.dot[m];
+  }
+  return s;
+}
+
 __device__ __forceinline__ double2 twice(double2 z) { return make_double2(2 * z.x, 2 * z.y); }
 
 // ---- lean form: coefficients evaluated in the kernel with the reference's operations -------
@@ -98,18 +120,21 @@ __device__ __forceinline__ double one_over(double eps) { return eps == 1.0 ? 1.0
 __device__ __forceinline__ double over_den(double g, double den) { return den == 1.0 ? g : ieee_div(g, den); }
 
 // ---------------------------------------------------------------- TM family ------
+#define F(SLOT) (v.f[SLOT] + sim)
+
 // slots: 0 Ez 1 Ezx 2 Ezy 3 Hx 4 Hy
 // LEAN: see b200fdtd.h "lean form".  Kind 0 (Berenger): the four H coefficients are 1-D tables.
 // Kind 6 (NS): decay coefficients 1-D, curl coefficients G[k] / DEN (1-D).
-template <bool NS, bool LEAN>
+template <bool NS, bool LEAN, bool BATCH>
 __global__ void __launch_bounds__(kBlock, B200_SPLIT_TM_MIN_BLOCKS(NS)) split_tm_h_kernel(const SplitView v)
 {
   int r, c; size_t k;
   if (!locate(v, r, c, k)) return;
+  const size_t sim = BATCH ? (size_t)blockIdx.y * v.plane : 0;   // field arrays only: coefficients are shared
   const int P = v.pitch;
   double2 dy_term, dx_term;
   if (NS) {                                             // nsFdtdTM.c:127-150
-    const double2 *__restrict__ Ez = v.f[B200FDTD_STM_EZ];
+    const double2 *__restrict__ Ez = F(B200FDTD_STM_EZ);
     const double2 e = Ez[k], e_j = Ez[k + 1], e_i = Ez[k + P], e_ij = Ez[k + 1 + P];
     const double2 e_jm = Ez[k + 1 - P], e_im = Ez[k - P], e_ijm = Ez[k + P - 1], e_jmm = Ez[k - 1];
     const double2 ns_x = v.ns_r2 * (((e_ij + e_jm) - twice(e_j)) - ((e_i + e_im) - twice(e)));
@@ -117,8 +142,8 @@ __global__ void __launch_bounds__(kBlock, B200_SPLIT_TM_MIN_BLOCKS(NS)) split_tm
     dy_term = (e_j - e) + ns_x;
     dx_term = (e_i - e) + ns_y;
   } else {                                              // fdtdTM.c:315-327
-    const double2 *__restrict__ Ezx = v.f[B200FDTD_STM_EZX];
-    const double2 *__restrict__ Ezy = v.f[B200FDTD_STM_EZY];
+    const double2 *__restrict__ Ezx = F(B200FDTD_STM_EZX);
+    const double2 *__restrict__ Ezy = F(B200FDTD_STM_EZY);
     const double2 zx = Ezx[k], zy = Ezy[k];
     dy_term = ((Ezx[k + 1] - zx) + Ezy[k + 1]) - zy;
     dx_term = ((Ezx[k + P] - zx) + Ezy[k + P]) - zy;
@@ -136,17 +161,18 @@ __global__ void __launch_bounds__(kBlock, B200_SPLIT_TM_MIN_BLOCKS(NS)) split_tm
     c_hx = v.tj[B200FDTD_LTM_J_C_HX * v.pitch + c];  c_hxly = v.tj[B200FDTD_LTM_J_C_HXLY * v.pitch + c];
     c_hy = v.ti[B200FDTD_LTM_I_C_HY * v.rows + r];   c_hylx = v.ti[B200FDTD_LTM_I_C_HYLX * v.rows + r];
   }
-  v.f[B200FDTD_STM_HX][k] = c_hx * v.f[B200FDTD_STM_HX][k] - c_hxly * dy_term;
-  v.f[B200FDTD_STM_HY][k] = c_hy * v.f[B200FDTD_STM_HY][k] + c_hylx * dx_term;
+  F(B200FDTD_STM_HX)[k] = c_hx * F(B200FDTD_STM_HX)[k] - c_hxly * dy_term;
+  F(B200FDTD_STM_HY)[k] = c_hy * F(B200FDTD_STM_HY)[k] + c_hylx * dx_term;
 }
 
-template <bool NS, bool LEAN>
+template <bool NS, bool LEAN, bool BATCH>
 __global__ void __launch_bounds__(kBlock, B200_SPLIT_TM_MIN_BLOCKS(NS)) split_tm_e_kernel(const SplitView v)
 {
   int r, c; size_t k;
   if (!locate(v, r, c, k)) return;
-  const double2 *__restrict__ Hx = v.f[B200FDTD_STM_HX];
-  const double2 *__restrict__ Hy = v.f[B200FDTD_STM_HY];
+  const size_t sim = BATCH ? (size_t)blockIdx.y * v.plane : 0;   // field arrays only: coefficients are shared
+  const double2 *__restrict__ Hx = F(B200FDTD_STM_HX);
+  const double2 *__restrict__ Hy = F(B200FDTD_STM_HY);
   double c_ezx, c_ezxlx, c_ezy, c_ezyly, factor;
   if (!LEAN) {
     c_ezx = v.c[B200FDTD_STM_C_EZX][k];  c_ezxlx = v.c[B200FDTD_STM_C_EZXLX][k];
@@ -166,32 +192,33 @@ __global__ void __launch_bounds__(kBlock, B200_SPLIT_TM_MIN_BLOCKS(NS)) split_tm
     factor = inv_eps - 1.0;                        // EPSILON_0_S / eps - 1.0 (field.c:193)
   }
   // fdtdTM.c:302-308 / nsFdtdTM.c:95-108
-  double2 ezx = c_ezx * v.f[B200FDTD_STM_EZX][k] + c_ezxlx * (Hy[k] - Hy[k - v.pitch]);
-  double2 ezy = c_ezy * v.f[B200FDTD_STM_EZY][k] - c_ezyly * (Hx[k] - Hx[k - 1]);
+  double2 ezx = c_ezx * F(B200FDTD_STM_EZX)[k] + c_ezxlx * (Hy[k] - Hy[k - v.pitch]);
+  double2 ezy = c_ezy * F(B200FDTD_STM_EZY)[k] - c_ezyly * (Hx[k] - Hx[k - 1]);
   double2 ez;
   if (NS) {          // source on Ezy, then Ez = Ezx + Ezy (nsFdtdTM.c:73-79)
-    if (v.cw[0].enabled && factor != 0.0) ezy = ezy + cw_term(v.cw[0], r - 1, v.j_base + c, factor);
+    if (cw_on<BATCH>(v, 0) && factor != 0.0) ezy = ezy + cw_term(cw_of<BATCH>(v, 0), r - 1, v.j_base + c, factor);
     ez = ezx + ezy;
   } else {           // Ez = Ezx + Ezy first, then the source on Ezx (fdtdTM.c:290-297,310-312)
     ez = ezx + ezy;
-    if (v.cw[0].enabled && factor != 0.0) ezx = ezx + cw_term(v.cw[0], r - 1, v.j_base + c, factor);
+    if (cw_on<BATCH>(v, 0) && factor != 0.0) ezx = ezx + cw_term(cw_of<BATCH>(v, 0), r - 1, v.j_base + c, factor);
   }
-  v.f[B200FDTD_STM_EZX][k] = ezx;
-  v.f[B200FDTD_STM_EZY][k] = ezy;
-  v.f[B200FDTD_STM_EZ][k] = ez;
+  F(B200FDTD_STM_EZX)[k] = ezx;
+  F(B200FDTD_STM_EZY)[k] = ezy;
+  F(B200FDTD_STM_EZ)[k] = ez;
 }
 
 // ---------------------------------------------------------------- TE family ------
 // slots: 0 Hz 1 Hzx 2 Hzy 3 Ex 4 Ey
-template <bool NS, bool LEAN, bool INTERIOR = false>          // LEAN: kind 1 only (NS TE keeps its dense arrays)
+template <bool NS, bool LEAN, bool INTERIOR, bool BATCH>          // LEAN: kind 1 only (NS TE keeps its dense arrays)
 __global__ void __launch_bounds__(kBlock, B200_SPLIT_TE_MIN_BLOCKS) split_te_e_kernel(const SplitView v)
 {
   int r, c; size_t k;
   if (!locate(v, r, c, k)) return;
+  const size_t sim = BATCH ? (size_t)blockIdx.y * v.plane : 0;   // field arrays only: coefficients are shared
   const int P = v.pitch;
   double2 dy_term, dx_term;
   if (NS) {                                             // nsFdtdTE.c:270-289
-    const double2 *__restrict__ Hz = v.f[B200FDTD_STE_HZ];
+    const double2 *__restrict__ Hz = F(B200FDTD_STE_HZ);
     const double2 h = Hz[k], h_jm = Hz[k - 1], h_im = Hz[k - P];
     const double2 h_i = Hz[k + P], h_j = Hz[k + 1];
     const double2 ns_x = v.ns_r2 * (((h_i + h_im) - twice(h)) - ((Hz[k - 1 + P] + Hz[k - 1 - P]) - twice(h_jm)));
@@ -199,8 +226,8 @@ __global__ void __launch_bounds__(kBlock, B200_SPLIT_TE_MIN_BLOCKS) split_te_e_k
     dy_term = (h - h_jm) + ns_x;
     dx_term = (h - h_im) + ns_y;
   } else {                                              // fdtdTE.c:293-301
-    const double2 *__restrict__ Hzx = v.f[B200FDTD_STE_HZX];
-    const double2 *__restrict__ Hzy = v.f[B200FDTD_STE_HZY];
+    const double2 *__restrict__ Hzx = F(B200FDTD_STE_HZX);
+    const double2 *__restrict__ Hzy = F(B200FDTD_STE_HZY);
     const double2 zx = Hzx[k], zy = Hzy[k];
     dy_term = ((zx - Hzx[k - 1]) + zy) - Hzy[k - 1];
     dx_term = ((zx - Hzx[k - P]) + zy) - Hzy[k - P];
@@ -223,31 +250,32 @@ __global__ void __launch_bounds__(kBlock, B200_SPLIT_TE_MIN_BLOCKS) split_te_e_k
     c_ex = px.c;  c_exly = px.l;  c_ey = py.c;  c_eylx = py.l;
     fx = 0.0;  fy = inv_y - 1.0;
   }
-  double2 ex = (inside ? v.f[B200FDTD_STE_EX][k] : c_ex * v.f[B200FDTD_STE_EX][k]) + c_exly * dy_term;
-  double2 ey = (inside ? v.f[B200FDTD_STE_EY][k] : c_ey * v.f[B200FDTD_STE_EY][k]) - c_eylx * dx_term;
+  double2 ex = (inside ? F(B200FDTD_STE_EX)[k] : c_ex * F(B200FDTD_STE_EX)[k]) + c_exly * dy_term;
+  double2 ey = (inside ? F(B200FDTD_STE_EY)[k] : c_ey * F(B200FDTD_STE_EY)[k]) - c_eylx * dx_term;
   const int i = r - 1, j = v.j_base + c;
-  if (v.cw[0].enabled && fx != 0.0) ex = ex + cw_term(v.cw[0], i, j, fx);     // nsFdtdTE.c:247-248
-  if (v.cw[1].enabled && fy != 0.0) ey = ey + cw_term(v.cw[1], i, j, fy);     // fdtdTE.c:285, nsFdtdTE.c:249-250
-  v.f[B200FDTD_STE_EX][k] = ex;
-  v.f[B200FDTD_STE_EY][k] = ey;
+  if (cw_on<BATCH>(v, 0) && fx != 0.0) ex = ex + cw_term(cw_of<BATCH>(v, 0), i, j, fx);     // nsFdtdTE.c:247-248
+  if (cw_on<BATCH>(v, 1) && fy != 0.0) ey = ey + cw_term(cw_of<BATCH>(v, 1), i, j, fy);     // fdtdTE.c:285, nsFdtdTE.c:249-250
+  F(B200FDTD_STE_EX)[k] = ex;
+  F(B200FDTD_STE_EY)[k] = ey;
 }
 
 // INTERIOR (NS TE, kind 7): thread blocks inside the rectangle of b200fdtd_set_split_interior -- decay
 // coefficients exactly 1.0, the two curl coefficients equal -- read three arrays fewer: same bits
-template <bool LEAN, bool INTERIOR = false>
+template <bool LEAN, bool INTERIOR, bool BATCH>
 __global__ void __launch_bounds__(kBlock, B200_SPLIT_TE_MIN_BLOCKS) split_te_h_kernel(const SplitView v)
 {
   int r, c; size_t k;
   if (!locate(v, r, c, k)) return;
-  const double2 *__restrict__ Ex = v.f[B200FDTD_STE_EX];
-  const double2 *__restrict__ Ey = v.f[B200FDTD_STE_EY];
+  const size_t sim = BATCH ? (size_t)blockIdx.y * v.plane : 0;   // field arrays only: coefficients are shared
+  const double2 *__restrict__ Ex = F(B200FDTD_STE_EX);
+  const double2 *__restrict__ Ey = F(B200FDTD_STE_EY);
   if (INTERIOR && block_in_interior(v, r, c)) {
     const double g = v.c[B200FDTD_STE_C_HZXLX][k];
-    const double2 hzx = v.f[B200FDTD_STE_HZX][k] - g * (Ey[k + v.pitch] - Ey[k]);
-    const double2 hzy = v.f[B200FDTD_STE_HZY][k] + g * (Ex[k + 1] - Ex[k]);
-    v.f[B200FDTD_STE_HZX][k] = hzx;
-    v.f[B200FDTD_STE_HZY][k] = hzy;
-    v.f[B200FDTD_STE_HZ][k] = hzx + hzy;
+    const double2 hzx = F(B200FDTD_STE_HZX)[k] - g * (Ey[k + v.pitch] - Ey[k]);
+    const double2 hzy = F(B200FDTD_STE_HZY)[k] + g * (Ex[k + 1] - Ex[k]);
+    F(B200FDTD_STE_HZX)[k] = hzx;
+    F(B200FDTD_STE_HZY)[k] = hzy;
+    F(B200FDTD_STE_HZ)[k] = hzx + hzy;
     return;
   }
   double c_hzx, c_hzxlx, c_hzy, c_hzyly;
@@ -259,13 +287,14 @@ __global__ void __launch_bounds__(kBlock, B200_SPLIT_TE_MIN_BLOCKS) split_te_h_k
     c_hzy = v.tj[B200FDTD_LTE_J_C_HZY * v.pitch + c];  c_hzyly = v.tj[B200FDTD_LTE_J_C_HZYLY * v.pitch + c];
   }
   // fdtdTE.c:308-320 / nsFdtdTE.c:293-307,237-240
-  const double2 hzx = c_hzx * v.f[B200FDTD_STE_HZX][k] - c_hzxlx * (Ey[k + v.pitch] - Ey[k]);
-  const double2 hzy = c_hzy * v.f[B200FDTD_STE_HZY][k] + c_hzyly * (Ex[k + 1] - Ex[k]);
-  v.f[B200FDTD_STE_HZX][k] = hzx;
-  v.f[B200FDTD_STE_HZY][k] = hzy;
-  v.f[B200FDTD_STE_HZ][k] = hzx + hzy;
+  const double2 hzx = c_hzx * F(B200FDTD_STE_HZX)[k] - c_hzxlx * (Ey[k + v.pitch] - Ey[k]);
+  const double2 hzy = c_hzy * F(B200FDTD_STE_HZY)[k] + c_hzyly * (Ex[k + 1] - Ex[k]);
+  F(B200FDTD_STE_HZX)[k] = hzx;
+  F(B200FDTD_STE_HZY)[k] = hzy;
+  F(B200FDTD_STE_HZ)[k] = hzx + hzy;
 }
 
+#undef F
 }  // namespace
 
 int b200_launch_split_step(b200fdtd_engine *e, const b200fdtd_step_args *a)
@@ -285,34 +314,44 @@ int b200_launch_split_step(b200fdtd_engine *e, const b200fdtd_step_args *a)
   v.rows = e->rows;
   v.in_r_lo = e->split_in_r_lo; v.in_r_hi = e->split_in_r_hi;
   v.in_c_lo = e->split_in_c_lo; v.in_c_hi = e->split_in_c_hi;
-  const unsigned nblk = (unsigned)((long long)v.nbx * (e->r_hi - e->r_lo + 1));
+  v.plane = e->plane;
+  v.batch = e->n_batch > 1 ? e->batch_cw : nullptr;
+  const bool batch = e->n_batch > 1;
+  const dim3 nblk((unsigned)((long long)v.nbx * (e->r_hi - e->r_lo + 1)), (unsigned)e->n_batch);
   cudaStream_t st = e->stream;
   const bool lean = e->split_lean;
+  // KERNEL<..., false> for one simulation, <..., true> for an angle batch (blockIdx.y = simulation)
+#define SPLIT_LAUNCH(KERNEL, ...)                                                             \
+  do {                                                                                        \
+    if (batch) KERNEL<__VA_ARGS__, true><<<nblk, kBlock, 0, st>>>(v);                         \
+    else       KERNEL<__VA_ARGS__, false><<<nblk, kBlock, 0, st>>>(v);                        \
+  } while (0)
   switch (e->g.kind) {
   case B200FDTD_TM:        // fdtdTM.c:290-297: calcH, calcE, source
-    if (lean) { split_tm_h_kernel<false, true><<<nblk, kBlock, 0, st>>>(v);  split_tm_e_kernel<false, true><<<nblk, kBlock, 0, st>>>(v); }
-    else      { split_tm_h_kernel<false, false><<<nblk, kBlock, 0, st>>>(v); split_tm_e_kernel<false, false><<<nblk, kBlock, 0, st>>>(v); }
+    if (lean) { SPLIT_LAUNCH(split_tm_h_kernel, false, true);  SPLIT_LAUNCH(split_tm_e_kernel, false, true); }
+    else      { SPLIT_LAUNCH(split_tm_h_kernel, false, false); SPLIT_LAUNCH(split_tm_e_kernel, false, false); }
     break;
   case B200FDTD_TE:        // fdtdTE.c:283-287: calcE, source, calcH
-    if (lean) { split_te_e_kernel<false, true><<<nblk, kBlock, 0, st>>>(v);  split_te_h_kernel<true><<<nblk, kBlock, 0, st>>>(v); }
-    else      { split_te_e_kernel<false, false><<<nblk, kBlock, 0, st>>>(v); split_te_h_kernel<false><<<nblk, kBlock, 0, st>>>(v); }
+    if (lean) { SPLIT_LAUNCH(split_te_e_kernel, false, true, false);  SPLIT_LAUNCH(split_te_h_kernel, true, false); }
+    else      { SPLIT_LAUNCH(split_te_e_kernel, false, false, false); SPLIT_LAUNCH(split_te_h_kernel, false, false); }
     break;
   case B200FDTD_NS_TM:     // nsFdtdTM.c:68-80: calcH, calcE, source, Ez = Ezx + Ezy
-    if (lean) { split_tm_h_kernel<true, true><<<nblk, kBlock, 0, st>>>(v);  split_tm_e_kernel<true, true><<<nblk, kBlock, 0, st>>>(v); }
-    else      { split_tm_h_kernel<true, false><<<nblk, kBlock, 0, st>>>(v); split_tm_e_kernel<true, false><<<nblk, kBlock, 0, st>>>(v); }
+    if (lean) { SPLIT_LAUNCH(split_tm_h_kernel, true, true);  SPLIT_LAUNCH(split_tm_e_kernel, true, true); }
+    else      { SPLIT_LAUNCH(split_tm_h_kernel, true, false); SPLIT_LAUNCH(split_tm_e_kernel, true, false); }
     break;
   case B200FDTD_NS_TE:     // nsFdtdTE.c:233-251: calcH, Hz = Hzx + Hzy, calcE, sources
     if (v.in_r_hi >= v.in_r_lo && v.in_c_hi >= v.in_c_lo) {      // blocks inside the frame-free rectangle: 3 arrays
-      split_te_h_kernel<false, true><<<nblk, kBlock, 0, st>>>(v);
-      split_te_e_kernel<true, false, true><<<nblk, kBlock, 0, st>>>(v);
+      SPLIT_LAUNCH(split_te_h_kernel, false, true);
+      SPLIT_LAUNCH(split_te_e_kernel, true, false, true);
     } else {
-      split_te_h_kernel<false><<<nblk, kBlock, 0, st>>>(v);
-      split_te_e_kernel<true, false><<<nblk, kBlock, 0, st>>>(v);
+      SPLIT_LAUNCH(split_te_h_kernel, false, false);
+      SPLIT_LAUNCH(split_te_e_kernel, true, false, false);
     }
     break;
   default:
     return b200_fail(B200FDTD_ERR_STATE, "not a split-field kind: %d", e->g.kind);
   }
+#undef SPLIT_LAUNCH
   e->launches += 2;
   B200_CUDA(cudaGetLastError());
   return B200FDTD_OK;

@@ -21,6 +21,8 @@ extern int mpifdtd_eps_palette(const double *map, size_t n, uint16_t *index, dou
 extern int mpifdtd_ntff_point_count(const NTFFInfo *box);
 extern int mpifdtd_ntff_local_count(const NTFFInfo *box, int j0, int nj);
 extern double *mpifdtd_ntff_time_shift(const NTFFInfo *box, int n_angles, double stagger, int j0, int nj);
+extern int mpifdtd_angle_batch_requested(const int **angles_deg);
+extern void mpifdtd_split_select_angle(int index);
 extern int mpifdtd_ntff_local_count_shifted(const NTFFInfo *box, int sample_dj, int j0, int nj);
 extern double *mpifdtd_ntff_time_shift_direct(const NTFFInfo *box, int n_angles, double stagger, int sample_dj, int j0, int nj);
 extern double complex mpifdtd_ntff_translate_coef(double omega);

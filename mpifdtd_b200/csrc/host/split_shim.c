@@ -31,6 +31,8 @@ typedef struct SplitSolver {
   double *src[2];
   dcomplex *mirror[5];            /* host mirrors of the five fields              */
   int mirror_reads[5];            /* refreshes so far; pinned in place at the first */
+  int n_batch;                    /* angles of a batched run (mpifdtd_setAngleBatch), 0 = one simulation */
+  int *batch_angles;
 } SplitSolver;
 
 static SplitSolver tm_plain = { .kind = B200FDTD_TM }, te_plain = { .kind = B200FDTD_TE };
@@ -434,6 +436,7 @@ static void set_ns_te_interior(SplitSolver *s)
   }
 }
 
+static void fill_batch_cw(int kind, int angle_deg, b200fdtd_batch_cw *b);
 static void solver_init(SplitSolver *s)
 {
   FieldInfo_S g = field_getFieldInfo_S();
@@ -449,7 +452,27 @@ static void solver_init(SplitSolver *s)
   grid.j_lo = 1;       grid.j_hi = g.N_PY - 2;
   grid.device = -1;
   grid.mu0 = MU_0_S;
+  /* an angle batch: main.c as shipped sweeps the incidence angle with NS_TE_2D, one
+   * simulation after the other (main.c:152,183-211); the simulations share every coefficient array
+   * and differ in the CW source only, so they run as planes of one engine, advanced together */
+  {
+    const int *req = NULL;
+    const int n_req = mpifdtd_angle_batch_requested(&req);
+    s->n_batch = n_req > 1 ? n_req : 0;
+    free(s->batch_angles);  s->batch_angles = NULL;
+    if (s->n_batch) {
+      s->batch_angles = (int *)malloc(sizeof(int) * (size_t)s->n_batch);
+      memcpy(s->batch_angles, req, sizeof(int) * (size_t)s->n_batch);
+    }
+  }
+  grid.n_batch = s->n_batch;
   die_on(b200fdtd_create(&grid, &s->engine), "b200fdtd_create");
+  if (s->n_batch) {
+    b200fdtd_batch_cw *rec = (b200fdtd_batch_cw *)calloc((size_t)s->n_batch, sizeof *rec);
+    for (int k = 0; k < s->n_batch; k++) fill_batch_cw(s->kind, s->batch_angles[k], &rec[k]);
+    die_on(b200fdtd_set_batch_cw(s->engine, rec), "b200fdtd_set_batch_cw");
+    free(rec);
+  }
   if (lean) {
     double *ti = (double *)malloc(sizeof(double) * B200FDTD_SPLIT_TABS * (size_t)g.N_PX);
     double *tj = (double *)malloc(sizeof(double) * B200FDTD_SPLIT_TABS * (size_t)g.N_PY);
@@ -527,10 +550,44 @@ void mpifdtd_split_step_args(int kind, b200fdtd_step_args *a)
   }
 }
 
+/* Batched engine: step_args carries what the simulations share (gaps, phases, scale = ray_coef);
+ * the angle-dependent rest sits in the per-simulation records below. */
+static void split_step_args_batched(int kind, b200fdtd_step_args *a)
+{
+  mpifdtd_split_step_args(kind, a);
+  memset(a->cw, 0, sizeof a->cw);
+  switch (kind) {
+  case B200FDTD_TM:    fill_cw(&a->cw[0], 0, 0.0, 0.0, 1.0); break;
+  case B200FDTD_TE:    fill_cw(&a->cw[1], 0, 0.0, 0.5, 1.0); break;
+  case B200FDTD_NS_TM: fill_cw(&a->cw[0], 1, 0, 0, 1.0);     break;
+  default:             fill_cw(&a->cw[0], 1, 0, 0.5, 1.0);  fill_cw(&a->cw[1], 1, 0, 0.5, 1.0);  break;
+  }
+}
+
+/* what fill_cw / mpifdtd_split_step_args take from the incidence angle, for one simulation */
+static void fill_batch_cw(int kind, int angle_deg, b200fdtd_batch_cw *b)
+{
+  const double k_s = field_getK();
+  const double rad = angle_deg * M_PI / 180.0;
+  memset(b, 0, sizeof *b);
+  b->ks_cos = cos(rad) * k_s;
+  b->ks_sin = sin(rad) * k_s;
+  b->dot[0] = b->dot[1] = 1.0;
+  if (kind == B200FDTD_NS_TE) {                               /* nsFdtdTE.c:243-250 */
+    double co = cos((angle_deg + 90) * M_PI / 180.0);
+    double si = sin((angle_deg + 90) * M_PI / 180.0);
+    b->dot[0] = co;  b->enabled[0] = co != 0.0;
+    b->dot[1] = si;  b->enabled[1] = si != 0.0;
+  } else {
+    b->enabled[kind == B200FDTD_TE ? 1 : 0] = 1;
+  }
+}
+
 static void solver_update(SplitSolver *s)
 {
   b200fdtd_step_args a;
-  mpifdtd_split_step_args(s->kind, &a);
+  if (s->n_batch) split_step_args_batched(s->kind, &a);
+  else            mpifdtd_split_step_args(s->kind, &a);
   die_on(b200fdtd_step(s->engine, &a), "b200fdtd_step");
 }
 
@@ -556,9 +613,21 @@ static void solver_reset(SplitSolver *s)
   static const char *const stem[] = { "tm_%dnm.txt", "te_%dnm.txt", NULL, NULL, NULL, NULL,
                                       "ns_tm_%dnm.txt", "ns_te_%dnm.txt" };
   FieldInfo phys = field_getFieldInfo();
-  char name[128];
+  char name[128], per_angle[160];
   sprintf(name, stem[s->kind], phys.h_u_nm);
-  field_outputElliptic(name, solver_field(s, is_tm(s) ? B200FDTD_STM_EZ : B200FDTD_STE_EY));
+  const int slot = is_tm(s) ? B200FDTD_STM_EZ : B200FDTD_STE_EY;
+  /* An angle batch writes the dump of every simulation in sweep order under the reference's name
+   * -- which carries no angle, so upstream's sweep keeps the last one, and so does this -- and,
+   * so that nothing is lost, also as "<angle>[deg]_<name>". */
+  for (int k = 0; k < (s->n_batch ? s->n_batch : 1); k++) {
+    if (s->n_batch) {
+      die_on(b200fdtd_select_batch(s->engine, k), "b200fdtd_select_batch");
+      sprintf(per_angle, "%d[deg]_%s", s->batch_angles[k], name);
+      field_outputElliptic(per_angle, solver_field(s, slot));
+    }
+    field_outputElliptic(name, solver_field(s, slot));
+  }
+  if (s->n_batch) die_on(b200fdtd_select_batch(s->engine, 0), "b200fdtd_select_batch");
   die_on(b200fdtd_zero_state(s->engine), "b200fdtd_zero_state");
 }
 
@@ -568,11 +637,21 @@ static void solver_finish(SplitSolver *s)
   solver_reset(s);
   die_on(b200fdtd_destroy(s->engine), "b200fdtd_destroy");
   s->engine = NULL;
+  free(s->batch_angles);  s->batch_angles = NULL;  s->n_batch = 0;
   free_host(s);
   for (int m = 0; m < 5; m++) {
     b200fdtd_mirror_free(s->mirror[m], s->mirror_reads[m] >= 1);
     s->mirror[m] = NULL;  s->mirror_reads[m] = 0;
   }
+}
+
+/* which simulation of an angle batch the getters show (mpifdtd_selectAngle) */
+void mpifdtd_split_select_angle(int index)
+{
+  SplitSolver *all[] = { &tm_plain, &te_plain, &tm_ns, &te_ns };
+  for (int n = 0; n < 4; n++)
+    if (all[n]->engine != NULL && all[n]->n_batch > 1)
+      die_on(b200fdtd_select_batch(all[n]->engine, index), "b200fdtd_select_batch");
 }
 
 /* test hooks: host-built dense arrays and the engine of a split solver */

@@ -185,6 +185,13 @@ void mpifdtd_setAngleBatch(const int *angles_deg, int n)
   for (int k = 0; k < n; k++) batch_angles_requested[k] = angles_deg[k];
 }
 
+/* the batch the next init() takes (split_shim.c reads it for ids 0, 1, 6, 7) */
+int mpifdtd_angle_batch_requested(const int **angles_deg)
+{
+  if (angles_deg != NULL) *angles_deg = batch_angles_requested;
+  return batch_requested;
+}
+
 /* ---- coefficient tables ------------------------------------------------------
  * Same expressions as setCoefficient (fdtdTM_upml.c:230-271, fdtdTE_upml.c:367-409)
  * evaluated once per row / column instead of once per cell.  sigma_z = 0 and
@@ -723,6 +730,7 @@ void mpifdtd_selectAngle(int index)
   for (int m = 0; m < 2; m++)
     if (all[m]->engine != NULL && all[m]->n_batch > 1)
       die_on(b200fdtd_select_batch(all[m]->engine, index), "b200fdtd_select_batch");
+  mpifdtd_split_select_angle(index);
 }
 
 /* ntffOutput + ntffSaveData of the MPI TE solver (mpiTE_UPML.c:795-878): translate the first

@@ -50,6 +50,61 @@ def test_batched_angles_equal_single_runs(plugin_lib, solver, model, precision):
         assert os.path.exists("%d[deg].txt" % ang)
 
 
+SPLIT_NAMES = {0: ("Ez", "Hx", "Hy", "Ezx", "Ezy"), 1: ("Ex", "Ey", "Hz", "Hzx", "Hzy")}
+SPLIT_NAMES[6], SPLIT_NAMES[7] = SPLIT_NAMES[0], SPLIT_NAMES[1]
+SPLIT_DUMP = {0: "tm_20nm.txt", 1: "te_20nm.txt", 6: "ns_tm_20nm.txt", 7: "ns_te_20nm.txt"}
+
+
+@pytest.mark.parametrize("dense", [False, True])
+@pytest.mark.parametrize("solver", [0, 1, 6, 7])
+def test_batched_angles_of_the_split_field_solvers(plugin_lib, monkeypatch, solver, dense):
+    """main.c as shipped sweeps the incidence angle with NS_TE_2D (main.c:152,183-211); ids 0, 1, 6, 7 as
+    one batched engine: every simulation bit-identical to its own single run (CW source with the
+    per-angle wave vector and, for id 7, the polarisation factors and on/off switches of
+    nsFdtdTE.c:243-250), the validation-circle dump of every angle on disk."""
+    if dense:
+        monkeypatch.setenv("MPIFDTD_SPLIT_DENSE", "1")
+    npx, npy, steps, angles = 150, 340, 260, [0, 30, 90, 200]
+    singles = {}
+    for ang in angles:
+        gpu = B.Plugin("MIE_CYLINDER", solver, npx, npy, steps=steps, h_u_nm=20, angle_deg=ang)
+        gpu.run()
+        singles[ang] = {f: gpu.field(f) for f in SPLIT_NAMES[solver]}
+        gpu.finish()
+        singles[ang]["dump"] = open(SPLIT_DUMP[solver]).read()
+    assert np.abs(singles[30][SPLIT_NAMES[solver][0]]).max() > 1e-6
+    assert not np.array_equal(singles[0][SPLIT_NAMES[solver][0]], singles[90][SPLIT_NAMES[solver][0]])
+
+    batch = B.Plugin("MIE_CYLINDER", solver, npx, npy, steps=steps, h_u_nm=20, angle_deg=angles[0], angle_batch=angles)
+    launches0 = batch.launches()
+    batch.run()
+    assert batch.launches() - launches0 == 2 * steps                  # still two kernels per step
+    for k, ang in enumerate(angles):
+        batch.select_angle(k)
+        for f in SPLIT_NAMES[solver]:
+            assert bit_equal(batch.field(f), singles[ang][f]), (ang, f)
+    batch.finish()
+    for ang in angles:
+        assert open("%d[deg]_%s" % (ang, SPLIT_DUMP[solver])).read() == singles[ang]["dump"], ang
+    assert open(SPLIT_DUMP[solver]).read() == singles[angles[-1]]["dump"]       # upstream's name: the last angle
+
+
+def test_angle_sweep_of_the_shipped_default_solver(plugin_lib):
+    """mpifdtd_runAngleSweep with NS_TE_2D: chunks of 3 and the one-at-a-time loop leave the same dump."""
+    L = B.lib()
+    n, steps = 120, 150
+    L.models_setModel(B.MODELS["MIE_CYLINDER"])
+    L.simulator_setSolver(7)
+    info = B.FieldInfo(n * 20, n * 20, 20, 10, 500, 0, steps)
+    assert L.mpifdtd_runAngleSweep(info, 0, 80, 20, 3) == 5
+    swept = {a: open("%d[deg]_ns_te_20nm.txt" % a).read() for a in range(0, 81, 20)}
+    last = open("ns_te_20nm.txt").read()
+    assert last == swept[80] and swept[0] != swept[80]
+    os.remove("ns_te_20nm.txt")
+    assert L.mpifdtd_runAngleSweep(info, 0, 80, 20, 1) == 5
+    assert open("ns_te_20nm.txt").read() == last
+
+
 def test_batch_vs_oracle_directly(plugin_lib, oracle):
     """One angle of a batch against the CPU oracle itself (not only against our own single run)."""
     n, steps, angles = 96, 400, [10, 60]
@@ -112,7 +167,7 @@ def test_run_angle_sweep_chunks_and_names(plugin_lib):
 def test_batch_rejected_where_not_built(plugin_lib):
     import ctypes as C
     h = C.c_void_p()
-    for kind, j0, nj in ((4, 0, 64), (0, 0, 64), (2, 0, 32)):          # MPI variant, split-field, slab
+    for kind, j0, nj in ((4, 0, 64), (2, 0, 32), (7, 0, 32)):          # MPI variant, slabs
         grid = B.Grid(kind, 64, 64, 10, j0, nj, 1, 62, 1, 62, -1, 0, B.MU_0_S, 4, 0)
         assert plugin_lib.b200fdtd_create(C.byref(grid), C.byref(h)) == 1, kind
     grid = B.Grid(2, 64, 64, 10, 0, 64, 1, 62, 1, 62, -1, 0, B.MU_0_S, 3, 0)
