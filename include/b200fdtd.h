@@ -350,6 +350,12 @@ int b200fdtd_sync(b200fdtd_engine *e);
  * pulse sources of b200fdtd_set_batch_sources (also accepted for n_batch = 1); no point / CW /
  * line source, no peer halos.  Bit-identical to n_steps b200fdtd_step calls. */
 int b200fdtd_run_steps(b200fdtd_engine *e, double time0, int32_t n_steps);
+/* The same for the split-field kinds (0, 1, 6, 7), whose CW source changes with the step (phases
+ * w(t +- 1/2) or w(t+1), w t and the ramp ray_coef): args[s] is what b200fdtd_step would have been
+ * given at step s.  The CW records of a chunk go to a device table in one copy and every kernel of
+ * the captured chunk reads its own step's record, so the graph is the same for every chunk.  ns_r2
+ * is taken from args[0].  Bit-identical to n_steps b200fdtd_step calls. */
+int b200fdtd_run_split_steps(b200fdtd_engine *e, const b200fdtd_step_args *args, int32_t n_steps);
 
 /* Halo columns for the y-slab split (replaces Connection_ISend_IRecvH/E,
  * mpiTM_UPML.c:252-296).  which: 0 = after the H phase (TM Hx / TE Hz, my last

@@ -360,7 +360,12 @@ int b200fdtd_destroy(b200fdtd_engine *e)
   if (e->stream) cudaStreamSynchronize(e->stream);
   for (int s = 0; s < B200FDTD_MAX_FIELDS; s++) cudaFree(e->field[s]);
   cudaFree(e->eps[0]); cudaFree(e->eps[1]);
-  cudaFree(e->tab_i); cudaFree(e->tab_j); cudaFree(e->batch_src); cudaFree(e->batch_cw); cudaFree(e->clock_dev);
+  cudaFree(e->tab_i); cudaFree(e->tab_j); cudaFree(e->batch_src); cudaFree(e->batch_cw); cudaFree(e->cw_tab);
+  for (int b = 0; b < 2; b++) {
+    if (e->cw_stage[b]) cudaFreeHost(e->cw_stage[b]);
+    if (e->cw_stage_done[b]) cudaEventDestroy((cudaEvent_t)e->cw_stage_done[b]);
+  }
+  cudaFree(e->clock_dev);
   if (e->graph_exec) cudaGraphExecDestroy((cudaGraphExec_t)e->graph_exec);
   for (int s = 0; s < B200FDTD_MAX_DENSE; s++) cudaFree(e->dense[s]);
   free_ntff(e);
@@ -657,6 +662,7 @@ int b200fdtd_set_split_tables(b200fdtd_engine *e, const double *tab_i, const dou
   B200_CUDA(cudaStreamSynchronize(e->stream));
   e->have_tabs = true;
   e->split_lean = true;
+  e->graph_epoch++;
   return B200FDTD_OK;
 }
 
@@ -764,6 +770,7 @@ int b200fdtd_set_dense(b200fdtd_engine *e, int32_t slot, const double *host_map)
                               cudaMemcpyHostToDevice, e->stream));
   B200_CUDA(cudaStreamSynchronize(e->stream));
   e->have_dense[slot] = true;
+  e->graph_epoch++;                     // the first upload of a slot allocates it: captured pointers are stale
   return B200FDTD_OK;
 }
 
@@ -771,6 +778,7 @@ int b200fdtd_set_split_interior(b200fdtd_engine *e, int32_t i_lo, int32_t i_hi, 
 {
   if (!e) return b200_fail(B200FDTD_ERR_ARG, "NULL engine");
   if (e->g.kind != B200FDTD_NS_TE) return b200_fail(B200FDTD_ERR_ARG, "the interior form serves the NS-FDTD TE kind (7)");
+  e->graph_epoch++;
   e->split_in_r_lo = e->split_in_c_lo = 1;
   e->split_in_r_hi = e->split_in_c_hi = 0;
   if (i_lo > i_hi || j_lo > j_hi) return B200FDTD_OK;             // switched off
@@ -1154,6 +1162,76 @@ int b200fdtd_run_steps(b200fdtd_engine *e, double time0, int32_t n_steps)
   if (!rc) {
     e->h_stale = !e->store_h;
     if (n.ready && (int)time0 + n_steps > n.steps_recorded) n.steps_recorded = (int)time0 + n_steps;
+  }
+  return rc;
+}
+
+// Split-field kinds: a chunk of steps from one graph, each kernel reading its own step's CW records
+// from a device table refreshed by one copy per chunk.
+int b200fdtd_run_split_steps(b200fdtd_engine *e, const b200fdtd_step_args *args, int32_t n_steps)
+{
+  if (!e || !args || n_steps < 0) return b200_fail(B200FDTD_ERR_ARG, "bad argument");
+  if (!kind_is_split(e->g.kind)) return b200_fail(B200FDTD_ERR_ARG, "run_split_steps serves the split-field kinds (0, 1, 6, 7)");
+  int rc = check_ready(e, args); if (rc) return rc;
+  if (n_steps == 0) return B200FDTD_OK;
+  const int kChunk = 128;
+  if (!e->cw_tab) {
+    rc = dev_alloc_zero(e, (void **)&e->cw_tab, sizeof(b200fdtd_cw) * 2 * kChunk);
+    if (rc) return rc;
+    for (int b = 0; b < 2; b++) {
+      B200_CUDA(cudaMallocHost((void **)&e->cw_stage[b], sizeof(b200fdtd_cw) * 2 * kChunk));
+      cudaEvent_t ev;
+      B200_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      e->cw_stage_done[b] = ev;
+    }
+  }
+  int done = 0, turn = 0;
+  while (done < n_steps && !rc) {
+    const int chunk = n_steps - done < kChunk ? n_steps - done : kChunk;
+    if (chunk < 8) {                    // not worth a graph
+      for (int s = 0; s < chunk && !rc; s++) rc = b200_launch_split_step(e, &args[done + s]);
+      done += chunk;
+      continue;
+    }
+    cudaGraphExec_t exec = (cudaGraphExec_t)e->graph_exec;
+    if (exec == nullptr || e->graph_steps != chunk || e->graph_built_epoch != e->graph_epoch) {
+      if (exec) { cudaGraphExecDestroy(exec); e->graph_exec = nullptr; }
+      const uint64_t launches_before = e->launches;
+      cudaGraph_t graph = nullptr;
+      cudaError_t err = cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal);
+      if (err != cudaSuccess) { rc = b200_fail(B200FDTD_ERR_CUDA, "begin capture: %s", cudaGetErrorString(err)); break; }
+      for (int s = 0; s < chunk && !rc; s++) {
+        e->split_cw_step = e->cw_tab + 2 * s;
+        rc = b200_launch_split_step(e, &args[0]);          // ns_r2; the CW records come from the table
+      }
+      e->split_cw_step = nullptr;
+      err = cudaStreamEndCapture(e->stream, &graph);
+      e->graph_launches = e->launches - launches_before;
+      e->launches = launches_before;
+      if (rc) { if (graph) cudaGraphDestroy(graph); break; }
+      if (err != cudaSuccess) { rc = b200_fail(B200FDTD_ERR_CUDA, "end capture: %s", cudaGetErrorString(err)); break; }
+      err = cudaGraphInstantiate(&exec, graph, 0);
+      cudaGraphDestroy(graph);
+      if (err != cudaSuccess) { rc = b200_fail(B200FDTD_ERR_CUDA, "graph instantiate: %s", cudaGetErrorString(err)); break; }
+      e->graph_exec = exec;
+      e->graph_steps = chunk;
+      e->graph_built_epoch = e->graph_epoch;
+    }
+    // this chunk's records: pinned twin (once its previous copy has run) -> device table, in stream order
+    // after the previous chunk's kernels
+    B200_CUDA(cudaEventSynchronize((cudaEvent_t)e->cw_stage_done[turn]));
+    for (int s = 0; s < chunk; s++) {
+      e->cw_stage[turn][2 * s] = args[done + s].cw[0];
+      e->cw_stage[turn][2 * s + 1] = args[done + s].cw[1];
+    }
+    B200_CUDA(cudaMemcpyAsync(e->cw_tab, e->cw_stage[turn], sizeof(b200fdtd_cw) * 2 * (size_t)chunk,
+                              cudaMemcpyHostToDevice, e->stream));
+    B200_CUDA(cudaEventRecord((cudaEvent_t)e->cw_stage_done[turn], e->stream));
+    cudaError_t err = cudaGraphLaunch((cudaGraphExec_t)e->graph_exec, e->stream);
+    if (err != cudaSuccess) { rc = b200_fail(B200FDTD_ERR_CUDA, "graph launch: %s", cudaGetErrorString(err)); break; }
+    e->launches += e->graph_launches;
+    done += chunk;
+    turn ^= 1;
   }
   return rc;
 }

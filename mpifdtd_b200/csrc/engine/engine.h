@@ -101,6 +101,10 @@ struct b200fdtd_engine {
   void *graph_exec;         // cudaGraphExec_t of `graph_steps` steps, or nullptr
   int graph_steps;
   uint64_t graph_launches;  // kernels one replay of the cached graph launches
+  b200fdtd_cw *cw_tab;      // device [kSplitChunk][2]: per-step CW records of a replayed chunk (split kinds)
+  b200fdtd_cw *cw_stage[2]; // pinned host twins, used alternately
+  void *cw_stage_done[2];   // cudaEvent_t: the copy out of cw_stage[b] has run
+  const b200fdtd_cw *split_cw_step;   // while capturing: the record pair of the step being launched
   unsigned graph_epoch, graph_built_epoch;   // bumped by anything that changes what a step launches
   bool f32_pairs;           // single precision: two cells per thread (default on)
   bool use_fused;           // b200fdtd_step runs the one-pass kernel (serial UPML kinds) wherever it can

@@ -37,6 +37,7 @@ struct SplitView {
   double ns_r2;
   size_t plane;                         // batched engines: elements per simulation (blockIdx.y selects it)
   const b200fdtd_batch_cw *batch;       // batched engines: per-simulation part of the CW source
+  const b200fdtd_cw *cw_step;           // replayed chunk (b200fdtd_run_split_steps): this step's two records, else nullptr
 };
 
 __device__ __forceinline__ bool locate(const SplitView &v, int &r, int &c, size_t &k)
@@ -79,12 +80,13 @@ __device__ __forceinline__ double2 cw_term(const b200fdtd_cw &s, int i, int j, d
 template <bool BATCH>
 __device__ __forceinline__ bool cw_on(const SplitView &v, int m)
 {
-  return BATCH ? v.batch[blockIdx.y].enabled[m] != 0 : v.cw[m].enabled != 0;
+  if (BATCH) return v.batch[blockIdx.y].enabled[m] != 0;
+  return (v.cw_step != nullptr ? v.cw_step[m].enabled : v.cw[m].enabled) != 0;
 }
 template <bool BATCH>
 __device__ __forceinline__ b200fdtd_cw cw_of(const SplitView &v, int m)
 {
-  b200fdtd_cw s = v.cw[m];
+  b200fdtd_cw s = v.cw_step != nullptr ? v.cw_step[m] : v.cw[m];
   if (BATCH) {
     const b200fdtd_batch_cw b = v.batch[blockIdx.y];
     s.ks_cos = b.ks_cos;
@@ -196,11 +198,11 @@ __global__ void __launch_bounds__(kBlock, B200_SPLIT_TM_MIN_BLOCKS(NS)) split_tm
   double2 ezy = c_ezy * F(B200FDTD_STM_EZY)[k] - c_ezyly * (Hx[k] - Hx[k - 1]);
   double2 ez;
   if (NS) {          // source on Ezy, then Ez = Ezx + Ezy (nsFdtdTM.c:73-79)
-    if (cw_on<BATCH>(v, 0) && factor != 0.0) ezy = ezy + cw_term(cw_of<BATCH>(v, 0), r - 1, v.j_base + c, factor);
+    if (factor != 0.0 && cw_on<BATCH>(v, 0)) ezy = ezy + cw_term(cw_of<BATCH>(v, 0), r - 1, v.j_base + c, factor);
     ez = ezx + ezy;
   } else {           // Ez = Ezx + Ezy first, then the source on Ezx (fdtdTM.c:290-297,310-312)
     ez = ezx + ezy;
-    if (cw_on<BATCH>(v, 0) && factor != 0.0) ezx = ezx + cw_term(cw_of<BATCH>(v, 0), r - 1, v.j_base + c, factor);
+    if (factor != 0.0 && cw_on<BATCH>(v, 0)) ezx = ezx + cw_term(cw_of<BATCH>(v, 0), r - 1, v.j_base + c, factor);
   }
   F(B200FDTD_STM_EZX)[k] = ezx;
   F(B200FDTD_STM_EZY)[k] = ezy;
@@ -253,8 +255,8 @@ __global__ void __launch_bounds__(kBlock, B200_SPLIT_TE_MIN_BLOCKS) split_te_e_k
   double2 ex = (inside ? F(B200FDTD_STE_EX)[k] : c_ex * F(B200FDTD_STE_EX)[k]) + c_exly * dy_term;
   double2 ey = (inside ? F(B200FDTD_STE_EY)[k] : c_ey * F(B200FDTD_STE_EY)[k]) - c_eylx * dx_term;
   const int i = r - 1, j = v.j_base + c;
-  if (cw_on<BATCH>(v, 0) && fx != 0.0) ex = ex + cw_term(cw_of<BATCH>(v, 0), i, j, fx);     // nsFdtdTE.c:247-248
-  if (cw_on<BATCH>(v, 1) && fy != 0.0) ey = ey + cw_term(cw_of<BATCH>(v, 1), i, j, fy);     // fdtdTE.c:285, nsFdtdTE.c:249-250
+  if (fx != 0.0 && cw_on<BATCH>(v, 0)) ex = ex + cw_term(cw_of<BATCH>(v, 0), i, j, fx);     // nsFdtdTE.c:247-248
+  if (fy != 0.0 && cw_on<BATCH>(v, 1)) ey = ey + cw_term(cw_of<BATCH>(v, 1), i, j, fy);     // fdtdTE.c:285, nsFdtdTE.c:249-250
   F(B200FDTD_STE_EX)[k] = ex;
   F(B200FDTD_STE_EY)[k] = ey;
 }
@@ -316,6 +318,7 @@ int b200_launch_split_step(b200fdtd_engine *e, const b200fdtd_step_args *a)
   v.in_c_lo = e->split_in_c_lo; v.in_c_hi = e->split_in_c_hi;
   v.plane = e->plane;
   v.batch = e->n_batch > 1 ? e->batch_cw : nullptr;
+  v.cw_step = e->split_cw_step;
   const bool batch = e->n_batch > 1;
   const dim3 nblk((unsigned)((long long)v.nbx * (e->r_hi - e->r_lo + 1)), (unsigned)e->n_batch);
   cudaStream_t st = e->stream;

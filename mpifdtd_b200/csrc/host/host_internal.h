@@ -32,6 +32,7 @@ extern double complex *mpifdtd_fft_twiddles(int n);
 /* upml_shim.c */
 /* hands every update() the serial UPML solvers have only counted so far to the engine */
 extern void mpifdtd_flush_pending_steps(void);
+extern void mpifdtd_split_flush_pending_steps(void);
 #include "b200fdtd.h"
 extern void mpifdtd_upml_step_args(int kind, int point_source, b200fdtd_step_args *a);
 extern void mpifdtd_upml_far_field(b200fdtd_engine *engine, int kind, int project, double *table);

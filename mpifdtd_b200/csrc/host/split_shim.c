@@ -33,6 +33,9 @@ typedef struct SplitSolver {
   int mirror_reads[5];            /* refreshes so far; pinned in place at the first */
   int n_batch;                    /* angles of a batched run (mpifdtd_setAngleBatch), 0 = one simulation */
   int *batch_angles;
+  int defer;                      /* update() collects step arguments, the engine replays them in chunks */
+  int pending, pending_cap;
+  b200fdtd_step_args *pending_args;
 } SplitSolver;
 
 static SplitSolver tm_plain = { .kind = B200FDTD_TM }, te_plain = { .kind = B200FDTD_TE };
@@ -466,6 +469,14 @@ static void solver_init(SplitSolver *s)
     }
   }
   grid.n_batch = s->n_batch;
+  {
+    const char *v = getenv("MPIFDTD_DEFER_STEPS"), *c = getenv("MPIFDTD_DEFER_CHUNK");
+    s->defer = !(v != NULL && v[0] == '0');
+    s->pending = 0;
+    s->pending_cap = c != NULL && atoi(c) > 0 ? atoi(c) : 256;
+    free(s->pending_args);
+    s->pending_args = s->defer ? (b200fdtd_step_args *)malloc(sizeof(b200fdtd_step_args) * (size_t)s->pending_cap) : NULL;
+  }
   die_on(b200fdtd_create(&grid, &s->engine), "b200fdtd_create");
   if (s->n_batch) {
     b200fdtd_batch_cw *rec = (b200fdtd_batch_cw *)calloc((size_t)s->n_batch, sizeof *rec);
@@ -583,18 +594,44 @@ static void fill_batch_cw(int kind, int angle_deg, b200fdtd_batch_cw *b)
   }
 }
 
+/* update() is asynchronous anyway, so it only RECORDS the step's arguments (the CW source's phases
+ * and ramp, which the host clock advances between calls); the pending steps go to the engine in
+ * one b200fdtd_run_split_steps call -- a CUDA-graph replay, each kernel reading its own step's
+ * record -- when somebody looks (a getter, reset/finish, the engine handle) or MPIFDTD_DEFER_CHUNK
+ * (256) steps have piled up.  Bit-identical to stepping one by one; on small grids, where a step
+ * is a few microseconds of device work, it removes the per-launch host cost.
+ * MPIFDTD_DEFER_STEPS=0 hands every step over immediately. */
+static void flush_pending(SplitSolver *s)
+{
+  if (s->engine == NULL || s->pending == 0) return;
+  const int n = s->pending;
+  s->pending = 0;
+  die_on(b200fdtd_run_split_steps(s->engine, s->pending_args, n), "b200fdtd_run_split_steps");
+}
+
+void mpifdtd_split_flush_pending_steps(void)
+{
+  flush_pending(&tm_plain);  flush_pending(&te_plain);  flush_pending(&tm_ns);  flush_pending(&te_ns);
+}
+
 static void solver_update(SplitSolver *s)
 {
   b200fdtd_step_args a;
   if (s->n_batch) split_step_args_batched(s->kind, &a);
   else            mpifdtd_split_step_args(s->kind, &a);
-  die_on(b200fdtd_step(s->engine, &a), "b200fdtd_step");
+  if (!s->defer) {
+    die_on(b200fdtd_step(s->engine, &a), "b200fdtd_step");
+    return;
+  }
+  s->pending_args[s->pending++] = a;
+  if (s->pending >= s->pending_cap) flush_pending(s);
 }
 
 /* ---- getters / reset / finish ------------------------------------------------------ */
 static dcomplex *solver_field(SplitSolver *s, int slot)
 {
   if (s->engine == NULL) return NULL;
+  flush_pending(s);
   const size_t mirror_bytes = sizeof(dcomplex) * (size_t)field_getFieldInfo_S().N_CELL;
   if (s->mirror[slot] == NULL) {        /* only if somebody looks */
     die_on(b200fdtd_mirror_alloc((void **)&s->mirror[slot], mirror_bytes), "mirror_alloc");
@@ -608,6 +645,7 @@ static dcomplex *solver_field(SplitSolver *s, int slot)
 static void solver_reset(SplitSolver *s)
 {
   if (s->engine == NULL) return;
+  flush_pending(s);
   /* validation-circle dump of the drawn field (fdtdTM.c:154-160, fdtdTE.c:273-278,
    * nsFdtdTM.c:159-164, nsFdtdTE.c:218-223) */
   static const char *const stem[] = { "tm_%dnm.txt", "te_%dnm.txt", NULL, NULL, NULL, NULL,
@@ -638,6 +676,7 @@ static void solver_finish(SplitSolver *s)
   die_on(b200fdtd_destroy(s->engine), "b200fdtd_destroy");
   s->engine = NULL;
   free(s->batch_angles);  s->batch_angles = NULL;  s->n_batch = 0;
+  free(s->pending_args);  s->pending_args = NULL;  s->pending = 0;
   free_host(s);
   for (int m = 0; m < 5; m++) {
     b200fdtd_mirror_free(s->mirror[m], s->mirror_reads[m] >= 1);
@@ -685,7 +724,7 @@ b200fdtd_engine *mpifdtd_split_engine(int kind)
 {
   SplitSolver *all[] = { &tm_plain, &te_plain, &tm_ns, &te_ns };
   for (int n = 0; n < 4; n++)
-    if (all[n]->kind == kind) return all[n]->engine;
+    if (all[n]->kind == kind) { flush_pending(all[n]); return all[n]->engine; }   /* whoever takes the handle sees every update() */
   return NULL;
 }
 

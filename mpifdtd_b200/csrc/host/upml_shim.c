@@ -631,6 +631,7 @@ void mpifdtd_flush_pending_steps(void)
 {
   flush_pending(&tm_solver);
   flush_pending(&te_solver);
+  mpifdtd_split_flush_pending_steps();
 }
 
 static void solver_update(UpmlSolver *s)

@@ -37,6 +37,7 @@ def main():
             h = gpu.engine_handle()
             B.check(L.b200fdtd_timer_start(h), "timer_start")
             gpu.run()
+            gpu.engine_handle()              # hands the recorded steps to the engine
             ms = C.c_float(0)
             B.check(L.b200fdtd_timer_stop(h, C.byref(ms)), "timer_stop")
             far = np.zeros(360, dtype=np.complex128)

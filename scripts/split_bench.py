@@ -26,16 +26,18 @@ BYTES = {0: 280, 1: 288, 6: 264, 7: 272} if DENSE else {0: 216, 1: 224, 6: 224, 
 
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
-    K, W = 40, 5
+    K, W = int(os.environ.get("SPLIT_BENCH_STEPS", 40)), int(os.environ.get("SPLIT_BENCH_WARMUP", 5))
     L = B.lib()
     kinds = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [0, 1, 6, 7]
     for kind in kinds:
         gpu = B.Plugin("MIE_CYLINDER", kind, n, steps=K + W + 2, lambda_nm=500)
         h = gpu.engine_handle()
         gpu.step(W)
+        h = gpu.engine_handle()              # taking the handle hands the recorded steps to the engine
         B.check(L.b200fdtd_sync(h), "sync")
         B.check(L.b200fdtd_timer_start(h), "timer_start")
         gpu.step(K)
+        gpu.engine_handle()
         ms = C.c_float(0)
         B.check(L.b200fdtd_timer_stop(h, C.byref(ms)), "timer_stop")
         rate = n * n * K / (ms.value * 1e-3) / 1e9

@@ -60,6 +60,42 @@ def test_deferred_stepping_is_bit_identical(plugin_lib, monkeypatch, solver, mod
     assert n_replay >= n_plain                       # same kernels + one clock tick per step
 
 
+SPLIT_FIELDS = {0: ("Ez", "Hx", "Hy", "Ezx", "Ezy"), 1: ("Ex", "Ey", "Hz", "Hzx", "Hzy")}
+SPLIT_FIELDS[6], SPLIT_FIELDS[7] = SPLIT_FIELDS[0], SPLIT_FIELDS[1]
+
+
+@pytest.mark.parametrize("solver,chunk,batch", [(0, None, None), (1, "100", None), (6, "50", None), (7, None, None),
+                                               (7, "5", None), (7, "128", [0, 40, 75]), (0, "64", [10, 100])])
+def test_deferred_stepping_of_the_split_field_solvers(plugin_lib, monkeypatch, solver, chunk, batch):
+    """b200fdtd_run_split_steps: update() records the step's CW arguments, chunks of them replay from
+    one CUDA graph whose kernels read their own step's record.  Bit-identical to one b200fdtd_step
+    per update(), a getter in mid-run included; same number of kernels."""
+    npx, npy, steps, mid = 130, 300, 430, 170
+
+    def once():
+        gpu = B.Plugin("MIE_CYLINDER", solver, npx, npy, steps=steps, h_u_nm=20, angle_deg=35, angle_batch=batch)
+        gpu.step(mid)
+        snaps = {"mid": gpu.field(SPLIT_FIELDS[solver][0])}
+        gpu.step(steps - mid)
+        if batch:
+            gpu.select_angle(len(batch) - 1)
+        snaps.update({f: gpu.field(f) for f in SPLIT_FIELDS[solver]})
+        n_launch = gpu.launches()
+        gpu.finish()
+        return snaps, n_launch
+
+    monkeypatch.setenv("MPIFDTD_DEFER_STEPS", "0")
+    want, n_plain = once()
+    monkeypatch.delenv("MPIFDTD_DEFER_STEPS")
+    if chunk:
+        monkeypatch.setenv("MPIFDTD_DEFER_CHUNK", chunk)
+    got, n_replay = once()
+    assert np.abs(want["mid"]).max() > 1e-6
+    for key in want:
+        assert bit_equal(got[key], want[key]), key
+    assert n_replay == n_plain and 0 <= n_plain - 2 * steps <= 2      # + the fill kernels of init()
+
+
 def test_run_steps_argument_checks(plugin_lib):
     import ctypes as C
     from mpifdtd_b200.slab import SlabRun
@@ -73,5 +109,10 @@ def test_run_steps_argument_checks(plugin_lib):
     assert L.b200fdtd_run_steps(h, 0.0, -1) == 1
     r.close()
     split = B.Plugin("MIE_CYLINDER", 0, 200, steps=4)
-    assert L.b200fdtd_run_steps(split.engine_handle(), 0.0, 2) == 1   # split-field kinds step one by one
+    assert L.b200fdtd_run_steps(split.engine_handle(), 0.0, 2) == 1   # split-field kinds: b200fdtd_run_split_steps
+    L.b200fdtd_run_split_steps.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
+    assert L.b200fdtd_run_split_steps(split.engine_handle(), None, 2) == 1
+    args = (B.StepArgs * 3)()
+    assert L.b200fdtd_run_split_steps(split.engine_handle(), args, -1) == 1
+    assert L.b200fdtd_run_split_steps(split.engine_handle(), args, 3) == 0   # sources disabled: three plain steps
     split.finish()
