@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define B200FDTD_ABI_VERSION 6
+#define B200FDTD_ABI_VERSION 7
 
 enum {
   B200FDTD_OK = 0,

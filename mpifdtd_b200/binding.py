@@ -72,6 +72,10 @@ class CwSource(C.Structure):
                 ("ks_sin", C.c_double), ("phase_a", C.c_double), ("phase_b", C.c_double)]
 
 
+class BatchCw(C.Structure):                         # b200fdtd_batch_cw
+    _fields_ = [("ks_cos", C.c_double), ("ks_sin", C.c_double), ("dot", C.c_double * 2), ("enabled", C.c_int32 * 2)]
+
+
 class LineSource(C.Structure):
     _fields_ = [("enabled", C.c_int32), ("i", C.c_int32), ("j_lo", C.c_int32), ("j_hi", C.c_int32),
                 ("scale", C.c_double), ("ks_cos", C.c_double), ("ks_sin", C.c_double),

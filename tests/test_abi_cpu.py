@@ -27,7 +27,7 @@ def declared_functions(header):
 def test_engine_header_symbols_exported(plugin_lib):
     missing = [n for n in sorted(declared_functions("b200fdtd.h")) if not hasattr(plugin_lib, n)]
     assert not missing, missing
-    assert plugin_lib.b200fdtd_abi_version() == 6
+    assert plugin_lib.b200fdtd_abi_version() == 7
 
 
 def test_ctypes_mirrors_match_the_compiled_structs(plugin_lib):
@@ -35,6 +35,7 @@ def test_ctypes_mirrors_match_the_compiled_structs(plugin_lib):
     include/b200fdtd.h; the library reports its own sizeof() for each."""
     for which, mirror in enumerate([B.Grid, B.StepArgs, B.NtffPlan, B.SpectrumArgs]):
         assert plugin_lib.b200fdtd_struct_size(which) == C.sizeof(mirror), mirror.__name__
+    assert plugin_lib.b200fdtd_struct_size(6) == C.sizeof(B.BatchCw)
     assert plugin_lib.b200fdtd_struct_size(99) == -1
 
 
