@@ -20,6 +20,9 @@ for solver, field in (("TM_UPML_2D", "Ez"), ("TE_UPML_2D", "Hz")):
     f = gpu.field(field)
     table = gpu.finish()
     t3 = time.perf_counter()
+    if os.environ.get("CONFIG2_SAVE"):           # for a bit-compare between step forms
+        np.save(os.environ["CONFIG2_SAVE"] + "_" + solver + "_field.npy", f)
+        np.save(os.environ["CONFIG2_SAVE"] + "_" + solver + "_table.npy", table)
     rec = {"init_s": t1 - t0, "steps_s": t2 - t1, "finish_s": t3 - t2,
            "gcell_per_s_steps": n * n * steps / (t2 - t1) / 1e9,
            "gcell_per_s_with_far_field": n * n * steps / (t3 - t1) / 1e9}
@@ -36,4 +39,5 @@ for solver, field in (("TM_UPML_2D", "Ez"), ("TE_UPML_2D", "Hz")):
     out[solver] = rec
     print(solver, json.dumps(rec), flush=True)
 os.makedirs(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out"), exist_ok=True)
-json.dump(out, open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "config2_full.json"), "w"), indent=1)
+json.dump(out, open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out",
+                           os.environ.get("CONFIG2_OUT", "config2_full.json")), "w"), indent=1)

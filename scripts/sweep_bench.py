@@ -4,7 +4,8 @@ main.c:114-211) run (a) one angle at a time, as the reference does, and (b) as o
 engine.  Wall clock around mpifdtd_runAngleSweep, i.e. including init, eps maps, the deferred
 NTFF projection, FFT and file output for every angle -- what a user of the sweep sees.
 
-  python scripts/sweep_bench.py [N ...]      -> one JSON line per grid size on stdout
+  python scripts/sweep_bench.py [--solver ID] [N ...]      -> one JSON line per grid size on stdout
+(ID 2 = TM_UPML_2D, the default; 7 = NS_TE_2D, the solver main.c ships with)
 """
 import json
 import os
@@ -37,9 +38,15 @@ def sweep(n, steps, start, end, delta, max_batch, solver=2):
 
 
 def main():
-    sizes = [int(a) for a in sys.argv[1:]] or [256, 1024]
+    argv = sys.argv[1:]
+    solver = 2
+    if "--solver" in argv:
+        at = argv.index("--solver")
+        solver = int(argv[at + 1])
+        del argv[at:at + 2]
+    sizes = [int(a) for a in argv] or [256, 1024]
     start, end, delta = 0, 180, 5
-    sweep(128, 50, 0, 10, 5, 0)             # warm-up: context, module load
+    sweep(128, 50, 0, 10, 5, 0, solver)     # warm-up: context, module load
     for n in sizes:
         steps = 2000 if n <= 512 else 1000
         rows = {}
@@ -48,13 +55,14 @@ def main():
             # cores are shared with other jobs, so take the best of three and keep all samples
             samples = []
             for _ in range(3):
-                count, dt = sweep(n, steps, start, end, delta, max_batch)
+                count, dt = sweep(n, steps, start, end, delta, max_batch, solver)
                 samples.append(dt)
             dt = min(samples)
             rows[label] = {"seconds": dt, "samples_s": samples, "simulations": count,
                            "gcell_updates_per_s": count * n * n * steps / dt / 1e9}
-        print(json.dumps({"workload": "MieCylinder TM_UPML %dx%d, %d steps, angles %d..%d step %d, "
-                                      "far-field files for every angle" % (n, n, steps, start, end, delta),
+        names = {0: "TM_2D", 1: "TE_2D", 2: "TM_UPML_2D", 3: "TE_UPML_2D", 6: "NS_TM_2D", 7: "NS_TE_2D"}
+        print(json.dumps({"workload": "MieCylinder %s %dx%d, %d steps, angles %d..%d step %d, "
+                                      "output files for every angle" % (names[solver], n, n, steps, start, end, delta),
                           "speedup_batched": rows["one_angle_at_a_time"]["seconds"] / rows["batched"]["seconds"],
                           **rows}))
 

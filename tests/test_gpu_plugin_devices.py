@@ -59,14 +59,16 @@ def test_plugin_with_several_slabs_matches_single_engine(plugin_lib, in_tmp_cwd,
 
 
 @pytest.mark.parametrize("solver,names", [("MPI_TM_UPML_2D", ("Ez", "Hx", "Hy")), ("MPI_TE_UPML_2D", ("Ex", "Ey", "Hz"))])
-@pytest.mark.parametrize("n_slabs", [2, 5])
-def test_mpi_variant_solvers_with_several_slabs(plugin_lib, in_tmp_cwd, monkeypatch, solver, names, n_slabs):
+@pytest.mark.parametrize("n_slabs,form", [(2, "default"), (5, "default"), (3, "unit")])
+def test_mpi_variant_solvers_with_several_slabs(plugin_lib, in_tmp_cwd, monkeypatch, solver, names, n_slabs, form):
     """Ids 4/5 -- the reference's own domain-decomposed solvers (E phase first, CW source, all N x N cells
     updated, getters with a ghost ring: mpiTM_UPML.c:196-217,674-743) -- over several slabs: the two
     MPI_Sendrecv exchanges become peer stores.  Fields, state arrays and the projected U/W partial
     sums must reproduce the single-engine run (fields bit for bit, U/W to summation order)."""
     monkeypatch.setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32")
     monkeypatch.setenv("MPIFDTD_NTFF_FULL_BINS", "1")
+    if form == "unit":                              # frame-free rectangle through the unit-coefficient kernels
+        monkeypatch.setenv("B200FDTD_UNIT_SPLIT", "1")
     npx, npy, steps = 110, 230, 300
     L = plugin_lib
     res = {}
