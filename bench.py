@@ -499,6 +499,8 @@ def gpu_arm(args):
         ms_max, launches = timed_steps()
         clocks = sampler.stop() if rank == 0 else None
         value = cells * K / (ms_max * 1e-3) / 1e9
+        # cells of this rank in vacuum row-strips, where the one-pass step keeps no E arrays (B200FDTD_OPT_DERIVED_E)
+        vac_cells = float(run.engine.vacuum_cells()) if form in (3, 4) else 0.0
 
         # ---- per-kernel timing for the roofline (rank-local, same state, CUDA events) -------
         def time_phase(fn, reps):
@@ -543,8 +545,9 @@ def gpu_arm(args):
             del d_eps
             ms_dense, _ = timed_steps()
             ms_dense_kernel = time_phase(run.engine.phase_fused, reps) if form in (3, 4) else None
+            vac_dense = float(run.engine.vacuum_cells()) if form in (3, 4) else 0.0
             B.check(run.L.b200fdtd_set_eps_slab(run.engine.h, 0, run.eps_host[0].ctypes.data), "set_eps_slab")
-            dense = (ms_dense, ms_dense_kernel, frac)
+            dense = (ms_dense, ms_dense_kernel, frac, vac_dense)
 
         # ---- e2e: host buffers inside the timed region ------------------------------------------
         # What simulator_init / K x simulator_calc / simulator_finish move between host and device for a
@@ -637,24 +640,32 @@ def gpu_arm(args):
                            "achieved": by["e"] * scale * cells_rank / (ms_e * 1e-3) / 1e9}}
         for ph in two.values():
             ph["frac"] = ph["achieved"] / peak
+        # a vacuum row-strip moves no E (read + write) and no eps: TM 40 B, TE 80 B per cell less, exact and lean alike
+        vac_saved = 40 if tm else 80
         if one_pass:
             b_one = by["one_pass_lean" if form == 4 else "one_pass"]
-            ach = b_one * cells_rank / (ms_one * 1e-3) / 1e9
+            launch_bytes = b_one * cells_rank - vac_saved * vac_cells
+            ach = launch_bytes / (ms_one * 1e-3) / 1e9
             traffic, traffic_src = ncu_traffic(kname + "_onepass_kernel<%d,0" % (1 if form == 4 else 0), cells_rank)
             roof = {"bound": "hbm",
                     "kernel": "%s_onepass_kernel<LEAN=%s, STORE_H=false, 8 warps, 4 row buffers> (+ its edge pre-pass, "
                               "timed together)" % (kname, "true" if form == 4 else "false"),
                     "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": peak_kind,
                     "traffic": traffic, "traffic_source": traffic_src,
-                    "algorithmic_bytes_per_launch": b_one * cells_rank, "ms_per_launch": ms_one,
-                    "algorithmic_bytes_per_cell": b_one,
+                    "algorithmic_bytes_per_launch": launch_bytes, "ms_per_launch": ms_one,
+                    "algorithmic_bytes_per_cell": launch_bytes / cells_rank,
+                    "algorithmic_bytes_per_cell_by_region": {"vacuum_row_strips": b_one - vac_saved, "elsewhere": b_one,
+                                                             "vacuum_row_strip_cells": vac_cells, "cells": cells_rank},
                     "note": ("one pass reads Ez,Mx,Bx,My,By,Jz,Dz + eps (120 B) and writes Mx,Bx,My,By,Jz,Dz,Ez (112 B): "
-                             "232 B per cell-update against SURVEY 8(d)'s 264 B contract figure for two passes"
+                             "232 B per cell-update against SURVEY 8(d)'s 264 B contract figure for two passes; in "
+                             "vacuum row-strips (every cell of a tile row has eps == 1, so Ez holds the bits of Dz) "
+                             "neither Ez nor eps moves: 192 B"
                              if tm and form == 3 else "see DESIGN.md section 4 for the byte count of this form"),
                     "step": {"algorithmic_bytes_per_cell_update": by["contract"], "achieved": step_gbs,
                              "frac": step_gbs / peak, "frac_of_nominal_8TBs": step_gbs / 8000.0,
-                             "moved_bytes_per_cell_update": b_one, "moved": b_one * (value / world),
-                             "moved_frac": b_one * (value / world) / peak},
+                             "moved_bytes_per_cell_update": launch_bytes / cells_rank,
+                             "moved": launch_bytes / cells_rank * (value / world),
+                             "moved_frac": launch_bytes / cells_rank * (value / world) / peak},
                     "two_kernel_form": two}
         else:
             bh = (by["lean_h"] if form == 2 else by["h"]) * scale
@@ -717,6 +728,8 @@ def gpu_arm(args):
             ms_lean, ms_lean_kernel, lean_form = lean
             v_lean = cells * K / (ms_lean * 1e-3) / 1e9
             b_lean = by["one_pass_lean"] if lean_form == 4 else by["lean_h"] + by["lean_e"]
+            if lean_form == 4:
+                b_lean -= vac_saved * vac_cells / cells_rank
             line["lean_interior"] = {
                 "value": v_lean, "unit": "Gcell-updates/s", "ms_per_step": ms_lean / K,
                 "speedup_vs_value": v_lean / value, "step_form": forms[lean_form],
@@ -729,7 +742,7 @@ def gpu_arm(args):
                 ach = b_lean * cells_rank / (ms_lean_kernel * 1e-3) / 1e9
                 line["lean_interior"]["kernel"] = {"ms_per_launch": ms_lean_kernel, "achieved": ach, "frac": ach / peak}
         if dense is not None:
-            ms_dense, ms_dense_kernel, frac = dense
+            ms_dense, ms_dense_kernel, frac, vac_dense = dense
             v_dense = cells * K / (ms_dense * 1e-3) / 1e9
             line["dense"] = {"value": v_dense, "unit": "Gcell-updates/s", "ms_per_step": ms_dense / K,
                              "material_cell_fraction": frac, "ratio_to_value": v_dense / value,
@@ -737,9 +750,10 @@ def gpu_arm(args):
                                           "material cell divides by eps and evaluates the pulse's exp / sincos each "
                                           "step (field.c:224-256)" % (100 * frac)}
             if ms_dense_kernel:
-                ach = by["one_pass"] * cells_rank / (ms_dense_kernel * 1e-3) / 1e9
+                b_dense = by["one_pass"] - vac_saved * vac_dense / cells_rank
+                ach = b_dense * cells_rank / (ms_dense_kernel * 1e-3) / 1e9
                 line["dense"]["roofline"] = {"ms_per_launch": ms_dense_kernel, "achieved": ach, "frac": ach / peak,
-                                             "algorithmic_bytes_per_cell": by["one_pass"]}
+                                             "algorithmic_bytes_per_cell": b_dense, "vacuum_row_strip_cells": vac_dense}
         emit(json.dumps(line))
     if run is not None:
         run.close()

@@ -458,6 +458,13 @@ enum {
                                   the full kernels.  0: one kernel per phase over the whole grid,
                                   1: split whenever the rectangle exists, 2 (default): split when the
                                   rectangle holds >= 2^20 cells and >= 3/4 of the updated cells.     */
+  B200FDTD_OPT_DERIVED_E = 10,  /* one-pass step.  1 (default): in "vacuum row-strips" -- a row of a CTA tile
+                                  whose cells all have eps == 1 (and none is an NTFF sample cell) -- the E
+                                  arrays are derived state: E = D/1.0 holds the bits of D, so the pass takes
+                                  the old E from D, stores no E and stages no eps there: TM 232 -> 192 B per
+                                  cell-update, TE 272 -> 192, lean 136 / 176 -> 96.  Bit-identical; the E
+                                  arrays are brought up to date whenever something outside the pass reads
+                                  them.  0: E read and written everywhere.                            */
   B200FDTD_OPT_LEAN_INTERIOR = 8 /* UPML kinds, two-kernel step.  1: cells outside the absorbing frame
                                   -- where every UPML coefficient of fdtdTM_upml.c:253-271 /
                                   fdtdTE_upml.c:384-403 is exactly 1 -- advance B and D directly
@@ -470,6 +477,9 @@ enum {
                                   reference's arithmetic in every cell.                            */
 };
 int b200fdtd_set_option(b200fdtd_engine *e, int32_t option, int32_t value);
+/* cells per step that lie in vacuum row-strips of the one-pass step (B200FDTD_OPT_DERIVED_E) with the
+ * current launch shape, permittivity maps and NTFF plan; 0 when the step does not use them */
+int b200fdtd_onepass_vacuum_cells(b200fdtd_engine *e, uint64_t *cells);
 
 /* The region OPT_LEAN_INTERIOR may treat as frame-free, from the 1-D coefficient tables alone
  * (host arithmetic, no device needed): the longest run of i (rows) and of j (columns) around the

@@ -26,6 +26,7 @@ SOLVERS = dict(TM_2D=0, TE_2D=1, TM_UPML_2D=2, TE_UPML_2D=3,
 D_X, D_Y, D_XY = 0, 1, 2
 UPML_TABS = 6
 OPT_FUSED, OPT_STORE_H, OPT_BAND_ROWS, OPT_FUSED_SHAPE, OPT_F32_PAIRS = 1, 2, 3, 4, 7
+OPT_DERIVED_E = 10
 OPT_LEAN_INTERIOR = 8
 OPT_UNIT_SPLIT = 9
 
@@ -163,6 +164,7 @@ def lib():
     L.b200fdtd_ntff_uw_device.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_uint64)]
     L.b200fdtd_ntff_spectrum.argtypes = [vp, C.POINTER(SpectrumArgs), vp]
     L.b200fdtd_launch_count.argtypes = [vp, C.POINTER(C.c_uint64)]
+    L.b200fdtd_onepass_vacuum_cells.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.b200fdtd_device_bytes.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.b200fdtd_timer_start.argtypes = [vp]
     L.b200fdtd_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
@@ -505,6 +507,12 @@ class Engine:
 
     def set_option(self, option, value):
         check(self.L.b200fdtd_set_option(self.h, option, value), "set_option")
+
+    def vacuum_cells(self):
+        """cells per step in vacuum row-strips of the one-pass step (no E arrays kept there)"""
+        n = C.c_uint64(0)
+        check(self.L.b200fdtd_onepass_vacuum_cells(self.h, C.byref(n)), "onepass_vacuum_cells")
+        return n.value
 
     def step_form(self):
         """0 one full kernel per phase, 1 unit-coefficient interior + frame, 2 lean interior + frame,

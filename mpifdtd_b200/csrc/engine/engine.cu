@@ -277,6 +277,10 @@ int b200fdtd_create(const b200fdtd_grid *grid, b200fdtd_engine **out)
   e->fused_variant = 20;    // 8 consumer warps (256 columns) x 4 row buffers
   e->store_h = false;
   e->h_stale = false;
+  e->derived_e = true;      // the one-pass step keeps no E arrays in vacuum row-strips (fused_kernels.cu)
+  if (const char *v = getenv("B200FDTD_DERIVED_E")) e->derived_e = atoi(v) != 0;
+  e->e_consistent = true;   // at rest E == D == 0
+  e->e_stale = false;
   if (const char *v = getenv("B200FDTD_FUSED")) {
     e->use_fused = atoi(v) == 1 && (grid->kind == B200FDTD_TM_UPML || grid->kind == B200FDTD_TE_UPML) && !e->fp32 &&
                    n_batch == 1;
@@ -702,7 +706,7 @@ static int upload_eps(b200fdtd_engine *e, int32_t slot, const double *src, size_
     if (!rc) rc = b200_narrow_real_region(e, stage, (size_t)g.nj, (float *)e->eps[slot]);
     cudaStreamSynchronize(e->stream);
     cudaFree(stage);
-    if (!rc) e->have_eps[slot] = true;
+    if (!rc) { e->have_eps[slot] = true; e->eps_epoch++; }
     return rc;
   }
   // ghosts and row padding hold vacuum (1.0) so no kernel can ever divide by zero there
@@ -714,6 +718,7 @@ static int upload_eps(b200fdtd_engine *e, int32_t slot, const double *src, size_
                               cudaMemcpyHostToDevice, e->stream));
   B200_CUDA(cudaStreamSynchronize(e->stream));
   e->have_eps[slot] = true;
+  e->eps_epoch++;
   return B200FDTD_OK;
 }
 
@@ -754,7 +759,7 @@ int b200fdtd_set_eps_palette(b200fdtd_engine *e, int32_t slot, const uint16_t *i
     if (err != cudaSuccess) rc = b200_fail(B200FDTD_ERR_CUDA, "palette upload: %s", cudaGetErrorString(err));
   }
   cudaFree(d_index); cudaFree(d_table);
-  if (!rc) e->have_eps[slot] = true;
+  if (!rc) { e->have_eps[slot] = true; e->eps_epoch++; }
   return rc;
 }
 
@@ -891,6 +896,7 @@ int b200fdtd_set_ntff_plan(b200fdtd_engine *e, const b200fdtd_ntff_plan *p)
   n.ready = true;
   n.steps_recorded = 0;
   e->graph_epoch++;
+  e->ntff_epoch++;
   return B200FDTD_OK;
 }
 
@@ -991,6 +997,12 @@ int b200fdtd_set_option(b200fdtd_engine *e, int32_t option, int32_t value)
   case B200FDTD_OPT_UNIT_SPLIT:
     if (value < 0 || value > 2) return b200_fail(B200FDTD_ERR_ARG, "unit split: 0 off, 1 on, 2 auto");
     e->unit_split = value;
+    return B200FDTD_OK;
+  case B200FDTD_OPT_DERIVED_E:
+    rc = b200_refresh_e(e); if (rc) return rc;
+    B200_CUDA(cudaStreamSynchronize(e->stream));
+    e->derived_e = value != 0;
+    e->fused.vac_built = false;
     return B200FDTD_OK;
   case B200FDTD_OPT_LEAN_INTERIOR:
     if (value && !kind_is_upml(e->g.kind))
@@ -1126,6 +1138,13 @@ int b200fdtd_run_steps(b200fdtd_engine *e, double time0, int32_t n_steps)
   e->clock_mode = true;
   int done = 0;
   while (done < n_steps && !rc) {
+    if (!e->e_consistent) {
+      // after b200fdtd_set_field: one step outside any graph restores E == D/eps, which decides what the
+      // one-pass kernels of the captured steps read (fused_kernels.cu, vacuum row-strips)
+      rc = launch_clocked_step(e, &a);
+      done++;
+      continue;
+    }
     const int chunk = n_steps - done < kChunk ? n_steps - done : kChunk;
     cudaGraphExec_t exec = (cudaGraphExec_t)e->graph_exec;
     if (exec == nullptr || e->graph_steps != chunk || e->graph_built_epoch != e->graph_epoch) {
@@ -1276,6 +1295,7 @@ static int field_plane_f64(b200fdtd_engine *e, int slot, const double2 **plane, 
 static int copy_field_out(b200fdtd_engine *e, int slot, double *host_first, size_t host_ld_complex)
 {
   int rc = b200_refresh_h(e); if (rc) return rc;
+  rc = b200_refresh_e(e); if (rc) return rc;
   const double2 *plane; double2 *temp;
   rc = field_plane_f64(e, slot, &plane, &temp); if (rc) return rc;
   const b200fdtd_grid &g = e->g;
@@ -1315,6 +1335,9 @@ int b200fdtd_set_field(b200fdtd_engine *e, int32_t slot, const double *host)
   if (!e || !host || slot < 0 || slot >= e->n_fields) return b200_fail(B200FDTD_ERR_ARG, "bad field slot %d", slot);
   int rc = select_device(e); if (rc) return rc;
   const b200fdtd_grid &g = e->g;
+  rc = b200_refresh_e(e); if (rc) return rc;
+  e->e_consistent = false;        // an arbitrary state: E == D/eps is not given (until the next full step)
+  e->graph_epoch++;
   double2 *dst = e->field[slot] + (size_t)e->sel * e->plane, *temp = nullptr;
   if (e->fp32) {
     cudaError_t err = cudaMalloc(&temp, e->plane * sizeof(double2));
@@ -1337,6 +1360,7 @@ int b200fdtd_field_digest(b200fdtd_engine *e, int32_t slot, uint64_t *digest)
   if (!e || !digest || slot < 0 || slot >= e->n_fields) return b200_fail(B200FDTD_ERR_ARG, "bad field slot %d", slot);
   int rc = select_device(e); if (rc) return rc;
   rc = b200_refresh_h(e); if (rc) return rc;
+  rc = b200_refresh_e(e); if (rc) return rc;
   unsigned long long *acc = nullptr;
   cudaError_t err = cudaMalloc((void **)&acc, sizeof *acc);
   if (err != cudaSuccess) return b200_fail(B200FDTD_ERR_NOMEM, "digest accumulator: %s", cudaGetErrorString(err));
@@ -1362,6 +1386,8 @@ int b200fdtd_zero_state(b200fdtd_engine *e)
   for (int s = 0; s < e->n_fields; s++)
     B200_CUDA(cudaMemsetAsync(e->field[s], 0, e->plane * e->csize * (size_t)e->n_batch, e->stream));
   e->h_stale = false;
+  e->e_stale = false;
+  e->e_consistent = true;
   // peer-halo flags restart with the step counter; a multi-rank reset must be bracketed by
   // the driver's own barrier (no rank may be mid-step while another zeroes)
   if (e->peer.flags) B200_CUDA(cudaMemsetAsync(e->peer.flags, 0, 2 * sizeof(unsigned long long), e->stream));

@@ -48,6 +48,13 @@ struct FusedState {          // side buffers of the one-pass step (fused_kernels
   int n_strips, n_bands, band_h;
   double2 *col_e, *col_h, *row_e, *row_h;   // old E / new B at strip and band edges
   double2 *ghost_e;          // y-slab with an upper neighbour: old Ez of the high ghost column (see fused_kernels.cu)
+  // "vacuum row-strips" (fused_kernels.cu): bit i of vac[band][cta strip] = every cell of row r0+i of that tile
+  // has eps == 1, is updated, and is not an NTFF sample cell -> E == D there and the E arrays are not kept
+  unsigned long long *vac;
+  int vac_strip_w, vac_band_h, vac_edges;   // geometry the masks were built for
+  unsigned vac_eps_epoch, vac_ntff_epoch;   // ... and the uploads they reflect
+  bool vac_built;
+  unsigned long long vac_cells;             // cells in flagged row-strips
 };
 
 // Peer (NVLink) halo state of a y-slab engine: the neighbours' field arrays and flag words,
@@ -111,6 +118,11 @@ struct b200fdtd_engine {
   bool fused_auto;          // ... or on large grids only (default)
   bool store_h;             // the fused kernel also writes Hx/Hy (264 instead of 232 B/cell)
   bool h_stale;             // Hx/Hy arrays lag Bx/By (fused step without store_h)
+  bool derived_e;           // option: the one-pass step may skip the E arrays in vacuum row-strips
+  bool e_consistent;        // E == D/eps (+ pulse) in every updated cell: true from rest and after any full step
+                            //   without point / line source; false after b200fdtd_set_field
+  bool e_stale;             // the E arrays lag D in the flagged row-strips (b200_refresh_e brings them up to date)
+  unsigned eps_epoch, ntff_epoch;   // bumped by eps uploads / NTFF plans
   int fused_variant;        // launch shape of the fused kernel (tuning)
   int unit_split;           // frame-free rectangle through the unit-coefficient kernels: 0 off, 1 on, 2 auto
   bool lean_interior;       // opt-in: cells outside the absorbing frame skip the M / J recurrences
@@ -158,6 +170,7 @@ int b200_launch_upml_fused(b200fdtd_engine *e, const b200fdtd_step_args *a);
 bool b200_want_fused(const b200fdtd_engine *e, const b200fdtd_step_args *a);
 int b200_launch_fused_edge(b200fdtd_engine *e, const b200fdtd_step_args *a);
 int b200_refresh_h(b200fdtd_engine *e);
+int b200_refresh_e(b200fdtd_engine *e);
 int b200_fused_prepare(b200fdtd_engine *e);
 void b200_fused_release(b200fdtd_engine *e);
 

@@ -57,7 +57,33 @@ struct OnePassView {
   int lean;                     // cells of that rectangle advance B / D directly (tolerance form)
   double2 *ghost_e;             // [rows]: y-slab with an upper neighbour: the OLD E of my high ghost column,
                                 //   captured by the edge kernel before the neighbour may overwrite it; else nullptr
+  const unsigned long long *vac;  // [n_bands][n_edges] row masks of the vacuum row-strips (below), or nullptr
 };
+
+// ---- vacuum row-strips: the E arrays are derived state there ------------------------------------------
+// E = D/eps (+ the pulse, in material cells only: field.c:243) is formed from D every step, so in a cell
+// with eps == 1 the E array holds the bits of D: x/1.0 == x.  A "vacuum row-strip" is one row of a CTA
+// tile all of whose cells are updated cells with eps == 1 (and none an NTFF sample cell, so the sample
+// kernel can keep reading the E arrays).  There the pass takes the old E from D -- the producer copies
+// the D row where it would have copied the E row -- and does not store E nor stage eps: TM 232 -> 192 B
+// per cell-update, TE 272 -> 192, lean 136 / 176 -> 96 (three complex fields in, three out).  Same
+// bits: nothing is computed differently.  Whoever reads an E array outside the pass (getters, digests,
+// the two-kernel forms, halo packing) calls b200_refresh_e first, which copies D over E in the
+// flagged row-strips.  Only while E == D/eps actually holds (engine.h: e_consistent).
+__device__ __forceinline__ bool vac_cell(const OnePassView &f, int r, int c)
+{
+  const UpmlView &v = f.u;
+  if (f.vac == nullptr || r < v.r_lo || r > v.r_hi || c < v.c_lo || c > v.c_hi) return false;
+  const int rr = r - v.r_lo;
+  const unsigned long long m = f.vac[(size_t)(rr / f.band_h) * f.n_edges + (c - v.c_lo) / f.strip_w];
+  return (m >> (rr % f.band_h)) & 1ull;
+}
+// the OLD value of an E component at (r, c): from its D array inside a vacuum row-strip
+__device__ __forceinline__ double2 e_old_at(const OnePassView &f, int e_slot, int d_slot, int r, int c)
+{
+  const size_t k = (size_t)r * f.u.pitch + c;
+  return vac_cell(f, r, c) ? f.u.f[d_slot][k] : f.u.f[e_slot][k];
+}
 
 __device__ __forceinline__ bool in_rect(const OnePassView &f, int r, int c)
 {
@@ -132,9 +158,10 @@ __global__ void onepass_prepass_cols_kernel(const OnePassView f)
   if (c0 > v.c_hi + 1) return;                          // past the ragged end: nobody reads it
   const size_t out = (size_t)s * v.rows + r;
   const size_t k0 = (size_t)r * v.pitch + c0;
-  const double2 *Ej = v.f[TM ? (int)B200FDTD_TM_EZ : (int)B200FDTD_TE_EX];     // the E component differenced along j
+  constexpr int EJ = TM ? (int)B200FDTD_TM_EZ : (int)B200FDTD_TE_EX;           // the E component differenced along j
+  constexpr int DJ = TM ? (int)B200FDTD_TM_DZ : (int)B200FDTD_TE_DX;           // ... and the D it is formed from
   // (a slab with an upper neighbour: the live ghost column may already hold the NEXT step's values)
-  const double2 e0 = (f.ghost_e != nullptr && c0 == v.c_hi + 1) ? f.ghost_e[r] : Ej[k0];
+  const double2 e0 = (f.ghost_e != nullptr && c0 == v.c_hi + 1) ? f.ghost_e[r] : e_old_at(f, EJ, DJ, r, c0);
   f.col_e[out] = e0;                                    // old E(r, c0) for strip s-1's last lane
   if (s == 0) {
     // column c_lo-1 is never updated by this engine: the ring (H == 0), or the low ghost column a
@@ -146,12 +173,13 @@ __global__ void onepass_prepass_cols_kernel(const OnePassView f)
   const bool lean = f.lean && in_rect(f, r, c0 - 1);
   double2 m_unused;
   if (TM) {
-    const double2 ez = Ej[k], bx_old = v.f[B200FDTD_TM_BX][k];
+    const double2 ez = e_old_at(f, EJ, DJ, r, c0 - 1), bx_old = v.f[B200FDTD_TM_BX][k];
     f.col_b[out] = lean ? bx_old - (e0 - ez)
                         : tm_bx_full(v, r, c0 - 1, ez, e0, v.f[B200FDTD_TM_MX][k], bx_old, &m_unused);
   } else {
-    const double2 *Ey = v.f[B200FDTD_TE_EY];
-    const double2 ey_i1 = Ey[k + v.pitch], ey = Ey[k], ex = Ej[k], bz_old = v.f[B200FDTD_TE_BZ][k];
+    const double2 ey_i1 = e_old_at(f, B200FDTD_TE_EY, B200FDTD_TE_DY, r + 1, c0 - 1);
+    const double2 ey = e_old_at(f, B200FDTD_TE_EY, B200FDTD_TE_DY, r, c0 - 1);
+    const double2 ex = e_old_at(f, EJ, DJ, r, c0 - 1), bz_old = v.f[B200FDTD_TE_BZ][k];
     f.col_b[out] = lean ? bz_old - (((ey_i1 - ey) - e0) + ex)
                         : te_bz_full(v, r, c0 - 1, ey_i1, ey, e0, ex, v.f[B200FDTD_TE_MZ][k], bz_old, &m_unused);
   }
@@ -171,8 +199,9 @@ __global__ void onepass_prepass_rows_kernel(const OnePassView f)
   if (r0 > v.r_hi + 1) r0 = v.r_hi + 1;
   const size_t out = (size_t)b * v.pitch + c;
   const size_t k0 = (size_t)r0 * v.pitch + c;
-  const double2 *Ei = v.f[TM ? (int)B200FDTD_TM_EZ : (int)B200FDTD_TE_EY];     // the E component differenced along i
-  const double2 e0 = Ei[k0];
+  constexpr int EI = TM ? (int)B200FDTD_TM_EZ : (int)B200FDTD_TE_EY;           // the E component differenced along i
+  constexpr int DI = TM ? (int)B200FDTD_TM_DZ : (int)B200FDTD_TE_DY;
+  const double2 e0 = e_old_at(f, EI, DI, r0, c);
   f.row_e[out] = e0;                                    // old E(r0, c) for band b-1's last row
   if (b == 0) {
     f.row_b[out] = v.f[TM ? (int)B200FDTD_TM_HY : (int)B200FDTD_TE_HZ][k0 - v.pitch];   // row r_lo-1: ring / ghost row
@@ -182,13 +211,14 @@ __global__ void onepass_prepass_rows_kernel(const OnePassView f)
   const bool lean = f.lean && in_rect(f, r0 - 1, c);
   double2 m_unused;
   if (TM) {
-    const double2 ez = Ei[k], by_old = v.f[B200FDTD_TM_BY][k];
+    const double2 ez = e_old_at(f, EI, DI, r0 - 1, c), by_old = v.f[B200FDTD_TM_BY][k];
     f.row_b[out] = lean ? by_old - ((-e0) + ez)
                         : tm_by_full(v, r0 - 1, c, ez, e0, v.f[B200FDTD_TM_MY][k], by_old, &m_unused);
   } else {
-    const double2 *Ex = v.f[B200FDTD_TE_EX];
-    const double2 ex_j1 = (f.ghost_e != nullptr && c == v.c_hi) ? f.ghost_e[r0 - 1] : Ex[k + 1];
-    const double2 ey = Ei[k], ex = Ex[k], bz_old = v.f[B200FDTD_TE_BZ][k];
+    const double2 ex_j1 = (f.ghost_e != nullptr && c == v.c_hi) ? f.ghost_e[r0 - 1]
+                                                                : e_old_at(f, B200FDTD_TE_EX, B200FDTD_TE_DX, r0 - 1, c + 1);
+    const double2 ey = e_old_at(f, EI, DI, r0 - 1, c);
+    const double2 ex = e_old_at(f, B200FDTD_TE_EX, B200FDTD_TE_DX, r0 - 1, c), bz_old = v.f[B200FDTD_TE_BZ][k];
     f.row_b[out] = lean ? bz_old - (((e0 - ey) - ex_j1) + ex)
                         : te_bz_full(v, r0 - 1, c, e0, ey, ex_j1, ex, v.f[B200FDTD_TE_MZ][k], bz_old, &m_unused);
   }
@@ -211,16 +241,17 @@ __global__ void onepass_edge_kernel(const OnePassView f)
   if (r > v.r_hi) return;
   const int c = v.c_hi;                                   // == c_last: the slab has an upper neighbour
   const size_t k = (size_t)r * v.pitch + c;
-  const double2 *Ej = v.f[TM ? (int)B200FDTD_TM_EZ : (int)B200FDTD_TE_EX];
-  const double2 e = Ej[k], e_ghost = Ej[k + 1];
+  constexpr int EJ = TM ? (int)B200FDTD_TM_EZ : (int)B200FDTD_TE_EX;
+  constexpr int DJ = TM ? (int)B200FDTD_TM_DZ : (int)B200FDTD_TE_DX;
+  const double2 e = e_old_at(f, EJ, DJ, r, c), e_ghost = v.f[EJ][k + 1];      // the ghost column is never derived
   const bool lean = f.lean && in_rect(f, r, c);
   double2 m_unused, b;
   if (TM) {
     const double2 bx_old = v.f[B200FDTD_TM_BX][k];
     b = lean ? bx_old - (e_ghost - e) : tm_bx_full(v, r, c, e, e_ghost, v.f[B200FDTD_TM_MX][k], bx_old, &m_unused);
   } else {
-    const double2 *Ey = v.f[B200FDTD_TE_EY];
-    const double2 ey_i1 = Ey[k + v.pitch], ey = Ey[k], bz_old = v.f[B200FDTD_TE_BZ][k];
+    const double2 ey_i1 = e_old_at(f, B200FDTD_TE_EY, B200FDTD_TE_DY, r + 1, c);
+    const double2 ey = e_old_at(f, B200FDTD_TE_EY, B200FDTD_TE_DY, r, c), bz_old = v.f[B200FDTD_TE_BZ][k];
     b = lean ? bz_old - (((ey_i1 - ey) - e_ghost) + e)
              : te_bz_full(v, r, c, ey_i1, ey, e_ghost, e, v.f[B200FDTD_TE_MZ][k], bz_old, &m_unused);
   }
@@ -294,6 +325,7 @@ struct __align__(128) TeRow {
 struct Tile {
   int lane, warp, c0, r0, r1, live_warps, eps_off, wcopy, n_eps;
   bool lean_tile;
+  unsigned long long vac;       // bit i: row r0 + i of this tile is a vacuum row-strip
 };
 template <bool LEAN, int WARPS>
 __device__ __forceinline__ Tile make_tile(const OnePassView &f)
@@ -316,6 +348,7 @@ __device__ __forceinline__ Tile make_tile(const OnePassView &f)
   int c_end = t.c0 + W - 1;
   if (c_end > v.c_hi) c_end = v.c_hi;
   t.lean_tile = LEAN && t.r0 >= f.in_r_lo && t.r1 - 1 <= f.in_r_hi && t.c0 >= f.in_c_lo && c_end <= f.in_c_hi;
+  t.vac = f.vac != nullptr ? f.vac[(size_t)blockIdx.y * f.n_edges + blockIdx.x] : 0ull;
   return t;
 }
 
@@ -433,6 +466,7 @@ __device__ __forceinline__ void tm_consume(const OnePassView &f, const Tile &T, 
       if (cta_right) edge_e_nxt = col_e_next[r + 1];
       if (cta_left) edge_b_nxt = col_b_mine[r + 1];
     }
+    const bool vac_row = (T.vac >> (r - r0)) & 1ull;      // E == D in this row of the tile: E is not kept
     mbar_wait(&full[s], ph);                              // this row's operands have landed
     const TmRow<W> &st = ring[s];
     const double2 ez_below = (sees_e && t < wcopy) ? st.ez[t] : zero;
@@ -444,7 +478,7 @@ __device__ __forceinline__ void tm_consume(const OnePassView &f, const Tile &T, 
     if (active) {
       bx_old = st.bx[t]; by_old = st.by[t]; dz_old = st.dz[t];
       if (!lean_tile) { mx_old = st.mx[t]; my_old = st.my[t]; jz_old = st.jz[t]; }
-      eps = st.eps[t + T.eps_off];
+      if (!vac_row) eps = st.eps[t + T.eps_off];          // not staged for a vacuum row-strip: eps == 1
     }
     if (inner_left) {
       ez_nb_nxt = st.ez[t - 1]; l_bx = st.bx[t - 1];
@@ -532,7 +566,7 @@ __device__ __forceinline__ void tm_consume(const OnePassView &f, const Tile &T, 
       v.f[B200FDTD_TM_BX][k] = bx;
       v.f[B200FDTD_TM_BY][k] = by;
       v.f[B200FDTD_TM_DZ][k] = dz;
-      Ez[k] = ez;
+      if (!vac_row) Ez[k] = ez;
       // y-slab halo: my first owned column of Ez is the lower neighbour's high ghost column
       if (v.peer_down_e != nullptr && c == v.c_first)
         v.peer_down_e[(size_t)r * v.peer_down_pitch + v.peer_down_col] = ez;
@@ -579,19 +613,23 @@ __global__ void __launch_bounds__(32 * (WARPS + 1), 1) tm_onepass_kernel(const _
     // ---- producer: one lane streams the band, STAGES rows ahead of the slowest consumer ----
     if (lane != 0) return;
     const unsigned seg = (unsigned)(wcopy * sizeof(double2));
-    const unsigned tx = (lean_tile ? 4u : 7u) * seg + (unsigned)(T.n_eps * sizeof(double));
+    const unsigned eps_bytes = (unsigned)(T.n_eps * sizeof(double));
+    const unsigned tx = (lean_tile ? 4u : 7u) * seg;
     const double2 *row_e_next = f.row_e + (size_t)(blockIdx.y + 1) * v.pitch;
+    const double2 *Dz = v.f[B200FDTD_TM_DZ];
     // the band's first Ez row: nobody has written it yet (only this CTA's consumers will, and they
     // wait for this copy), so every consumer sees the OLD values of its own and its neighbours' cells
+    // (a vacuum row-strip: the old Ez IS the old Dz, and only Dz is kept)
     mbar_expect_tx(first_bar, seg);
-    bulk_g2s(ez_first, &Ez[(size_t)r0 * v.pitch + c0], seg, first_bar);
+    bulk_g2s(ez_first, ((T.vac & 1ull) ? Dz : Ez) + (size_t)r0 * v.pitch + c0, seg, first_bar);
     int s = 0; unsigned ph = 0;
     for (int r = r0; r < r1; r++) {
       if (r - r0 >= STAGES) mbar_wait(&empty[s], ph ^ 1u);   // every consumer has handed the slot back
       TmRow<W> &st = ring[s];
       const size_t k = (size_t)r * v.pitch + c0;
-      mbar_expect_tx(&full[s], tx);
-      bulk_g2s(st.ez, (r + 1 < r1) ? &Ez[k + v.pitch] : &row_e_next[c0], seg, &full[s]);
+      const bool vac_row = (T.vac >> (r - r0)) & 1ull, vac_below = (T.vac >> (r + 1 - r0)) & 1ull;
+      mbar_expect_tx(&full[s], tx + (vac_row ? 0u : eps_bytes));
+      bulk_g2s(st.ez, (r + 1 < r1) ? (vac_below ? Dz : Ez) + k + v.pitch : &row_e_next[c0], seg, &full[s]);
       bulk_g2s(st.bx, &v.f[B200FDTD_TM_BX][k], seg, &full[s]);
       bulk_g2s(st.by, &v.f[B200FDTD_TM_BY][k], seg, &full[s]);
       bulk_g2s(st.dz, &v.f[B200FDTD_TM_DZ][k], seg, &full[s]);
@@ -600,7 +638,7 @@ __global__ void __launch_bounds__(32 * (WARPS + 1), 1) tm_onepass_kernel(const _
         bulk_g2s(st.my, &v.f[B200FDTD_TM_MY][k], seg, &full[s]);
         bulk_g2s(st.jz, &v.f[B200FDTD_TM_JZ][k], seg, &full[s]);
       }
-      bulk_g2s(st.eps, &v.eps0[k - T.eps_off], (unsigned)(T.n_eps * sizeof(double)), &full[s]);
+      if (!vac_row) bulk_g2s(st.eps, &v.eps0[k - T.eps_off], eps_bytes, &full[s]);
       if (++s == STAGES) { s = 0; ph ^= 1u; }
     }
     return;
@@ -707,6 +745,7 @@ __device__ __forceinline__ void te_consume(const OnePassView &f, const Tile &T, 
       if (cta_right) edge_e_nxt = col_e_next[r + 1];
       if (cta_left) edge_b_nxt = col_b_mine[r + 1];
     }
+    const bool vac_row = (T.vac >> (r - r0)) & 1ull;      // Ex == Dx, Ey == Dy in this row of the tile: E is not kept
     mbar_wait(&full[s], ph);
     const TeRow<W> &st = ring[s];
     double2 ey_below = zero, ex_old = zero, ex_nb = zero;
@@ -719,7 +758,7 @@ __device__ __forceinline__ void te_consume(const OnePassView &f, const Tile &T, 
     if (active) {
       bz_old = st.bz[t]; dx_old = st.dx[t]; dy_old = st.dy[t];
       if (!lean_tile) { mz_old = st.mz[t]; jx_old = st.jx[t]; jy_old = st.jy[t]; }
-      eps_x = st.epx[t + T.eps_off]; eps_y = st.epy[t + T.eps_off];
+      if (!vac_row) { eps_x = st.epx[t + T.eps_off]; eps_y = st.epy[t + T.eps_off]; }
     }
     if (inner_left) {
       l_ey_below = st.ey[t - 1]; l_ex = st.ex[t - 1]; l_bz = st.bz[t - 1];
@@ -803,8 +842,10 @@ __device__ __forceinline__ void te_consume(const OnePassView &f, const Tile &T, 
       v.f[B200FDTD_TE_BZ][k] = bz;
       v.f[B200FDTD_TE_DX][k] = dx;
       v.f[B200FDTD_TE_DY][k] = dy;
-      Ex[k] = ex;
-      Ey[k] = ey;
+      if (!vac_row) {
+        Ex[k] = ex;
+        Ey[k] = ey;
+      }
       if (v.peer_down_e != nullptr && c == v.c_first)
         v.peer_down_e[(size_t)r * v.peer_down_pitch + v.peer_down_col] = ex;
       if (STORE_H) v.f[B200FDTD_TE_HZ][k] = hz;
@@ -846,18 +887,21 @@ __global__ void __launch_bounds__(32 * (WARPS + 1), 1) te_onepass_kernel(const _
     if (lane != 0) return;
     const unsigned seg = (unsigned)(wcopy * sizeof(double2));
     const unsigned eps_bytes = (unsigned)(T.n_eps * sizeof(double));
-    const unsigned tx = (lean_tile ? 5u : 8u) * seg + 2u * eps_bytes;
+    const unsigned tx = (lean_tile ? 5u : 8u) * seg;
     const double2 *row_e_next = f.row_e + (size_t)(blockIdx.y + 1) * v.pitch;
+    const double2 *Dx = v.f[B200FDTD_TE_DX], *Dy = v.f[B200FDTD_TE_DY];
     mbar_expect_tx(first_bar, seg);
-    bulk_g2s(ey_first, &Ey[(size_t)r0 * v.pitch + c0], seg, first_bar);
+    bulk_g2s(ey_first, ((T.vac & 1ull) ? Dy : Ey) + (size_t)r0 * v.pitch + c0, seg, first_bar);
     int s = 0; unsigned ph = 0;
     for (int r = r0; r < r1; r++) {
       if (r - r0 >= STAGES) mbar_wait(&empty[s], ph ^ 1u);
       TeRow<W> &st = ring[s];
       const size_t k = (size_t)r * v.pitch + c0;
-      mbar_expect_tx(&full[s], tx);
-      bulk_g2s(st.ey, (r + 1 < r1) ? &Ey[k + v.pitch] : &row_e_next[c0], seg, &full[s]);
-      bulk_g2s(st.ex, &Ex[k], seg, &full[s]);
+      // a vacuum row-strip keeps no E: the old Ex / Ey are the old Dx / Dy, and eps is not staged
+      const bool vac_row = (T.vac >> (r - r0)) & 1ull, vac_below = (T.vac >> (r + 1 - r0)) & 1ull;
+      mbar_expect_tx(&full[s], tx + (vac_row ? 0u : 2u * eps_bytes));
+      bulk_g2s(st.ey, (r + 1 < r1) ? (vac_below ? Dy : Ey) + k + v.pitch : &row_e_next[c0], seg, &full[s]);
+      bulk_g2s(st.ex, (vac_row ? Dx : Ex) + k, seg, &full[s]);
       bulk_g2s(st.bz, &v.f[B200FDTD_TE_BZ][k], seg, &full[s]);
       bulk_g2s(st.dx, &v.f[B200FDTD_TE_DX][k], seg, &full[s]);
       bulk_g2s(st.dy, &v.f[B200FDTD_TE_DY][k], seg, &full[s]);
@@ -866,8 +910,10 @@ __global__ void __launch_bounds__(32 * (WARPS + 1), 1) te_onepass_kernel(const _
         bulk_g2s(st.jx, &v.f[B200FDTD_TE_JX][k], seg, &full[s]);
         bulk_g2s(st.jy, &v.f[B200FDTD_TE_JY][k], seg, &full[s]);
       }
-      bulk_g2s(st.epx, &v.eps0[k - T.eps_off], eps_bytes, &full[s]);
-      bulk_g2s(st.epy, &v.eps1[k - T.eps_off], eps_bytes, &full[s]);
+      if (!vac_row) {
+        bulk_g2s(st.epx, &v.eps0[k - T.eps_off], eps_bytes, &full[s]);
+        bulk_g2s(st.epy, &v.eps1[k - T.eps_off], eps_bytes, &full[s]);
+      }
       if (++s == STAGES) { s = 0; ph ^= 1u; }
     }
     return;
@@ -895,6 +941,56 @@ __global__ void derive_h_kernel(const double2 *__restrict__ b, double2 *h, int p
   for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) {
     const size_t k = (size_t)(r_lo + t / n_cols) * pitch + c_lo + t % n_cols;
     h[k] = b[k] / mu0;
+  }
+}
+
+// ---- vacuum row-strip masks (see the top of the file) ---------------------------------------------------
+// one warp per (updated row, CTA strip): the strip must be a full one of updated columns and every eps 1.0
+__global__ void vac_build_kernel(unsigned long long *mask, const double *__restrict__ eps0, const double *__restrict__ eps1,
+                                 int pitch, int r_lo, int n_rows, int c_lo, int c_hi, int strip_w, int n_edges, int band_h)
+{
+  const long long w = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= (long long)n_rows * n_edges) return;
+  const int rr = (int)(w / n_edges), s = (int)(w - (long long)rr * n_edges);
+  const int c0 = c_lo + s * strip_w;
+  bool ok = c0 + strip_w - 1 <= c_hi;
+  if (ok) {
+    const size_t k = (size_t)(r_lo + rr) * pitch + c0;
+    for (int t = lane; t < strip_w; t += 32)
+      if (eps0[k + t] != 1.0 || (eps1 != nullptr && eps1[k + t] != 1.0)) ok = false;
+  }
+  ok = __all_sync(0xffffffffu, ok);
+  if (ok && lane == 0) atomicOr(&mask[(size_t)(rr / band_h) * n_edges + s], 1ull << (rr % band_h));
+}
+// the rows the NTFF sample kernel reads E from keep their E arrays
+__global__ void vac_clear_samples_kernel(unsigned long long *mask, const NtffPoint *__restrict__ pts, int n_local, int pitch,
+                                         int r_lo, int r_hi, int c_lo, int c_hi, int strip_w, int n_edges, int band_h)
+{
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_local) return;
+  const int r = (int)(pts[p].k / pitch), c = (int)(pts[p].k % pitch);
+  if (r < r_lo || r > r_hi || c < c_lo || c > c_hi) return;
+  const int rr = r - r_lo;
+  atomicAnd(&mask[(size_t)(rr / band_h) * n_edges + (c - c_lo) / strip_w], ~(1ull << (rr % band_h)));
+}
+__global__ void vac_count_kernel(const unsigned long long *mask, int n, unsigned long long *rows)
+{
+  unsigned long long mine = 0;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) mine += __popcll(mask[t]);
+  if (mine) atomicAdd(rows, mine);
+}
+// E := D in the flagged row-strips (the identity the pass relied on)
+__global__ void derive_e_kernel(const unsigned long long *__restrict__ mask, const double2 *__restrict__ d, double2 *e,
+                                int pitch, int r_lo, int n_rows, int c_lo, int strip_w, int n_edges, int band_h)
+{
+  const size_t n = (size_t)n_rows * n_edges * strip_w;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) {
+    const int rr = (int)(t / ((size_t)n_edges * strip_w));
+    const int cc = (int)(t - (size_t)rr * n_edges * strip_w);
+    if (!((mask[(size_t)(rr / band_h) * n_edges + cc / strip_w] >> (rr % band_h)) & 1ull)) continue;
+    const size_t k = (size_t)(r_lo + rr) * pitch + c_lo + cc;       // a flagged strip is a full one: in range
+    e[k] = d[k];
   }
 }
 
@@ -962,6 +1058,14 @@ bool lean_form(const b200fdtd_engine *e)
   return e->lean_interior && e->lean_r_hi >= e->lean_r_lo && e->lean_c_hi >= e->lean_c_lo;
 }
 
+// may this step treat the E arrays as derived state in the vacuum row-strips?
+bool use_vac(const b200fdtd_engine *e, const b200fdtd_step_args *a)
+{
+  const FusedState &fs = e->fused;
+  return e->derived_e && e->e_consistent && fs.vac_built && fs.vac != nullptr && fs.vac_cells > 0 &&
+         !(a != nullptr && a->point.enabled);
+}
+
 void fill_view(const b200fdtd_engine *e, const b200fdtd_step_args *a, OnePassView &f)
 {
   const FusedState &fs = e->fused;
@@ -975,6 +1079,7 @@ void fill_view(const b200fdtd_engine *e, const b200fdtd_step_args *a, OnePassVie
   f.in_c_lo = e->lean_c_lo; f.in_c_hi = e->lean_c_hi;
   f.lean = lean_form(e) ? 1 : 0;
   f.ghost_e = fs.ghost_e;
+  f.vac = use_vac(e, a) ? fs.vac : nullptr;
 }
 
 }  // namespace
@@ -992,6 +1097,52 @@ bool b200_want_fused(const b200fdtd_engine *e, const b200fdtd_step_args *a)
   return (double)(e->r_hi - e->r_lo + 1) * (double)(e->c_hi - e->c_lo + 1) >= 4194304.0;
 }
 
+// Row masks of the vacuum row-strips for the current launch shape, eps maps and NTFF plan.  Not while a
+// stream capture is running (b200fdtd_run_steps prepares before it captures): the keys cannot change there.
+static int build_vac(b200fdtd_engine *e)
+{
+  FusedState &fs = e->fused;
+  const int strip_w = 32 * shape_of(e->fused_variant).warps;
+  const int n_cols = e->c_hi - e->c_lo + 1, n_rows = e->r_hi - e->r_lo + 1;
+  const int n_edges = (n_cols + strip_w - 1) / strip_w;
+  if (fs.vac_built && fs.vac_strip_w == strip_w && fs.vac_band_h == fs.band_h && fs.vac_edges == n_edges &&
+      fs.vac_eps_epoch == e->eps_epoch && fs.vac_ntff_epoch == e->ntff_epoch)
+    return B200FDTD_OK;
+  cudaStreamCaptureStatus capturing = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(e->stream, &capturing);
+  if (capturing != cudaStreamCaptureStatusNone) return B200FDTD_OK;      // keep what there is
+  // whatever the old masks let the pass skip is brought up to date first
+  int rc = b200_refresh_e(e); if (rc) return rc;
+  cudaFree(fs.vac); fs.vac = nullptr;
+  fs.vac_built = true;
+  fs.vac_strip_w = strip_w; fs.vac_band_h = fs.band_h; fs.vac_edges = n_edges;
+  fs.vac_eps_epoch = e->eps_epoch; fs.vac_ntff_epoch = e->ntff_epoch;
+  fs.vac_cells = 0;
+  const bool tm = is_tm(e->g.kind);
+  if (!e->derived_e || fs.band_h > 63 || n_edges < 1 || fs.n_bands < 1 || !e->have_eps[0] || (!tm && !e->have_eps[1]))
+    return B200FDTD_OK;
+  const size_t n_masks = (size_t)fs.n_bands * n_edges;
+  unsigned long long *count = nullptr;
+  cudaError_t err = cudaMalloc((void **)&fs.vac, (n_masks + 1) * sizeof(unsigned long long));
+  if (err != cudaSuccess) return b200_fail(B200FDTD_ERR_NOMEM, "one-pass row masks: %s", cudaGetErrorString(err));
+  count = fs.vac + n_masks;
+  B200_CUDA(cudaMemsetAsync(fs.vac, 0, (n_masks + 1) * sizeof(unsigned long long), e->stream));
+  const long long n_warps = (long long)n_rows * n_edges;
+  vac_build_kernel<<<(unsigned)((n_warps * 32 + 255) / 256), 256, 0, e->stream>>>(
+      fs.vac, e->eps[0], tm ? nullptr : e->eps[1], e->pitch, e->r_lo, n_rows, e->c_lo, e->c_hi, strip_w, n_edges, fs.band_h);
+  if (e->ntff.ready && e->ntff.n_local > 0)
+    vac_clear_samples_kernel<<<(e->ntff.n_local + 127) / 128, 128, 0, e->stream>>>(
+        fs.vac, e->ntff.pts, e->ntff.n_local, e->pitch, e->r_lo, e->r_hi, e->c_lo, e->c_hi, strip_w, n_edges, fs.band_h);
+  vac_count_kernel<<<148, 256, 0, e->stream>>>(fs.vac, (int)n_masks, count);
+  e->launches += 3;
+  unsigned long long rows = 0;
+  B200_CUDA(cudaMemcpyAsync(&rows, count, sizeof rows, cudaMemcpyDeviceToHost, e->stream));
+  B200_CUDA(cudaStreamSynchronize(e->stream));
+  fs.vac_cells = rows * (unsigned long long)strip_w;
+  e->graph_epoch++;
+  return B200FDTD_OK;
+}
+
 int b200_fused_prepare(b200fdtd_engine *e)
 {
   FusedState &fs = e->fused;
@@ -1001,7 +1152,7 @@ int b200_fused_prepare(b200fdtd_engine *e)
     B200_CUDA(cudaMemsetAsync(fs.ghost_e, 0, (size_t)e->rows * sizeof(double2), e->stream));
     e->dev_bytes += (size_t)e->rows * sizeof(double2);
   }
-  if (fs.ready) return B200FDTD_OK;
+  if (fs.ready) return build_vac(e);
   const int n_cols = e->c_hi - e->c_lo + 1, n_rows = e->r_hi - e->r_lo + 1;
   if (n_cols < 1 || n_rows < 1) { fs.ready = true; fs.n_strips = fs.n_bands = 0; return B200FDTD_OK; }
   fs.n_strips = (n_cols + 31) / 32;
@@ -1017,13 +1168,25 @@ int b200_fused_prepare(b200fdtd_engine *e)
     e->dev_bytes += sizes[n] * sizeof(double2);
   }
   fs.ready = true;
+  return build_vac(e);
+}
+
+int b200fdtd_onepass_vacuum_cells(b200fdtd_engine *e, uint64_t *cells)
+{
+  if (!e || !cells) return b200_fail(B200FDTD_ERR_ARG, "NULL argument");
+  *cells = 0;
+  if (!b200_want_fused(e, nullptr)) return B200FDTD_OK;
+  cudaSetDevice(e->device);
+  int rc = b200_fused_prepare(e); if (rc) return rc;
+  if (e->derived_e && e->fused.vac != nullptr) *cells = e->fused.vac_cells;
   return B200FDTD_OK;
 }
 
 void b200_fused_release(b200fdtd_engine *e)
 {
   FusedState &fs = e->fused;
-  cudaFree(fs.col_e); cudaFree(fs.col_h); cudaFree(fs.row_e); cudaFree(fs.row_h); cudaFree(fs.ghost_e);
+  b200_refresh_e(e);            // the masks go away: nothing may stay derived
+  cudaFree(fs.col_e); cudaFree(fs.col_h); cudaFree(fs.row_e); cudaFree(fs.row_h); cudaFree(fs.ghost_e); cudaFree(fs.vac);
   const int keep_band = fs.band_h;
   memset(&fs, 0, sizeof fs);
   fs.band_h = keep_band;
@@ -1040,6 +1203,7 @@ int b200_launch_upml_fused(b200fdtd_engine *e, const b200fdtd_step_args *a)
   FusedState &fs = e->fused;
   if (fs.n_strips == 0) return B200FDTD_OK;
   const bool tm = is_tm(e->g.kind);
+  if (!use_vac(e, a)) { rc = b200_refresh_e(e); if (rc) return rc; }    // this pass reads the E arrays everywhere
   OnePassView f;
   fill_view(e, a, f);
   const Shape sh = shape_of(e->fused_variant);
@@ -1064,6 +1228,9 @@ int b200_launch_upml_fused(b200fdtd_engine *e, const b200fdtd_step_args *a)
     return b200_fail(B200FDTD_ERR_CUDA, "one-pass kernel (shape %d): %s", e->fused_variant, cudaGetErrorString(err));
   e->launches += 3;
   e->h_stale = !e->store_h;
+  if (f.vac != nullptr) e->e_stale = true;
+  // E == D/eps (+ pulse) holds again in every updated cell, unless the point source touched one
+  e->e_consistent = !a->point.enabled;
   return B200FDTD_OK;
 }
 
@@ -1080,6 +1247,24 @@ int b200_launch_fused_edge(b200fdtd_engine *e, const b200fdtd_step_args *a)
   if (is_tm(e->g.kind)) onepass_edge_kernel<true><<<(n_rows + 127) / 128, 128, 0, e->stream>>>(f);
   else                  onepass_edge_kernel<false><<<(n_rows + 127) / 128, 128, 0, e->stream>>>(f);
   e->launches++;
+  B200_CUDA(cudaGetLastError());
+  return B200FDTD_OK;
+}
+
+// Bring the E arrays up to date in the vacuum row-strips, where the one-pass step does not store them.
+int b200_refresh_e(b200fdtd_engine *e)
+{
+  if (!e->e_stale) return B200FDTD_OK;
+  const FusedState &fs = e->fused;
+  if (fs.vac == nullptr) { e->e_stale = false; return B200FDTD_OK; }
+  const int n_rows = e->r_hi - e->r_lo + 1;
+  const int pairs[3][2] = { { B200FDTD_TM_DZ, B200FDTD_TM_EZ }, { B200FDTD_TE_DX, B200FDTD_TE_EX }, { B200FDTD_TE_DY, B200FDTD_TE_EY } };
+  for (int n = is_tm(e->g.kind) ? 0 : 1; n < (is_tm(e->g.kind) ? 1 : 3); n++) {
+    derive_e_kernel<<<1184, 256, 0, e->stream>>>(fs.vac, e->field[pairs[n][0]], e->field[pairs[n][1]], e->pitch, e->r_lo,
+                                                 n_rows, e->c_lo, fs.vac_strip_w, fs.vac_edges, fs.vac_band_h);
+    e->launches++;
+  }
+  e->e_stale = false;
   B200_CUDA(cudaGetLastError());
   return B200FDTD_OK;
 }

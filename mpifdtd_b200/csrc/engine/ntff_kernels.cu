@@ -472,6 +472,8 @@ int b200_run_ntff_frequency(b200fdtd_engine *e, const b200fdtd_freq_args *a, dou
     return b200_fail(B200FDTD_ERR_ARG, "bad NTFF box");
   int rc = b200_refresh_h(e);
   if (rc) return rc;
+  rc = b200_refresh_e(e);
+  if (rc) return rc;
   const bool upml = (e->g.kind == B200FDTD_TM_UPML || e->g.kind == B200FDTD_MPI_TM_UPML);
   const size_t sel = (size_t)e->sel * e->plane;
   const double2 *Ez = e->field[0] + sel;

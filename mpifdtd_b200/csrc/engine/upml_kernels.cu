@@ -1026,13 +1026,19 @@ int b200_step_form(const b200fdtd_engine *e)
 int b200_launch_upml_h(b200fdtd_engine *e, const b200fdtd_step_args *a)
 {
   if (e->r_hi < e->r_lo || e->c_hi < e->c_lo) return B200FDTD_OK;   // slab owns no updated cell
+  { int rc = b200_refresh_e(e); if (rc) return rc; }                // a one-pass step may have left E derived
   return e->fp32 ? launch_h<float>(e, a) : launch_h<double>(e, a);
 }
 
 int b200_launch_upml_e(b200fdtd_engine *e, const b200fdtd_step_args *a)
 {
   if (e->r_hi < e->r_lo || e->c_hi < e->c_lo) return B200FDTD_OK;
-  return e->fp32 ? launch_e<float>(e, a) : launch_e<double>(e, a);
+  int rc = b200_refresh_e(e); if (rc) return rc;
+  rc = e->fp32 ? launch_e<float>(e, a) : launch_e<double>(e, a);
+  // every updated cell now holds E = D/eps + the pulse (material cells only); the opt-in sources also act in
+  // vacuum cells (point, line) or add a signed zero there (CW), after which E == D is not given
+  if (!rc) e->e_consistent = !(a->line.enabled || a->point.enabled || a->cw[0].enabled || a->cw[1].enabled);
+  return rc;
 }
 
 template <typename T>
@@ -1054,6 +1060,7 @@ int b200_launch_halo(b200fdtd_engine *e, int which, void *buf, bool pack)
     slot = is_tm(e->g.kind) ? (int)B200FDTD_TM_EZ : (int)B200FDTD_TE_EX;
     col = pack ? B200_JOFF : B200_JOFF + e->g.nj;
   }
+  if (which == 1 && pack) { int rc = b200_refresh_e(e); if (rc) return rc; }   // the E arrays themselves, not D
   bool derive = false;
   if (which == 0 && pack && e->h_stale) {     // H column = B column / mu0 (H arrays not kept)
     slot = is_tm(e->g.kind) ? (int)B200FDTD_TM_BX : (int)B200FDTD_TE_BZ;

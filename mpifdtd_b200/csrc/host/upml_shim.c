@@ -527,6 +527,12 @@ static void fill_batch_source(int kind, double angle_deg, b200fdtd_batch_source 
   }
 }
 
+/* test hook: the per-simulation pulse record of one incidence angle (b200fdtd_set_batch_sources) */
+void mpifdtd_upml_batch_source(int kind, double angle_deg, b200fdtd_batch_source *out)
+{
+  fill_batch_source(kind, angle_deg, out);
+}
+
 /* Everything update() reads from the host's grid/time state, packed for the
  * engine.  Also used by slab (multi-GPU) drivers, which call the engine phases
  * themselves and then field_nextStep(). */

@@ -140,6 +140,133 @@ def test_lean_one_pass_is_bit_identical_to_lean_two_kernel_step(plugin_lib, npx,
     run_and_compare(L, kind, engines, state, steps)
 
 
+def structured_case(npx, npy, kind):
+    """vacuum with a dielectric block and a few single cells: most rows of most strips have eps == 1
+    everywhere, some do not; random state"""
+    rng = np.random.default_rng(7 * npx + npy + kind)
+    eps = []
+    for m in range(1 if kind == 2 else 2):
+        e = np.ones((npx, npy))
+        e[npx // 3:npx // 3 + 9, npy // 2 - 40:npy // 2 + 200 + 30 * m] = 2.56
+        for _ in range(6):
+            e[rng.integers(12, npx - 12), rng.integers(12, npy - 12)] = 1.0 + rng.random()
+        eps.append(e)
+    state = [rng.standard_normal((npx, npy)) + 1j * rng.standard_normal((npx, npy)) for _ in range(9)]
+    mu0 = B.MU_0_S
+    for h, b in H_OF_B[kind]:
+        state[h] = (state[b].real / mu0) + 1j * (state[b].imag / mu0)
+    return eps, state
+
+
+@pytest.mark.parametrize("lean", [0, 1])
+@pytest.mark.parametrize("kind", [2, 3])
+@pytest.mark.parametrize("npx,npy,band", [(150, 1100, 32), (97, 790, 7), (140, 1560, 63), (60, 530, 64)])
+def test_vacuum_row_strips_keep_no_e_arrays_and_change_no_bit(plugin_lib, npx, npy, band, kind, lean):
+    """B200FDTD_OPT_DERIVED_E: in a row of a CTA tile whose cells all have eps == 1 the E arrays hold the
+    bits of D (E = D/1.0), so the pass reads D for the old E, stores no E and stages no eps there.
+    From a random state (first step: E arrays everywhere, since E == D/eps is not given yet), with a
+    getter in mid-run (refresh of the E arrays, then derived again), a changed permittivity map and a
+    restart: all nine arrays and the NTFF history bit-identical to the two-kernel step and to the pass
+    with the option off.  band 64 does not fit the 64-bit row masks: the option is then inert."""
+    L = plugin_lib
+    steps = 14
+    L.models_setModel(B.MODELS["NO_MODEL"])
+    L.field_init(B.FieldInfo(npx * 10, npy * 10, 10, 10, 500, 30, steps))
+    eps, state = structured_case(npx, npy, kind)
+    mk = lambda *a, **kw: make_engine(L, npx, npy, steps, eps, *a, kind=kind, lean=lean, **kw)
+    engines = [mk(0), mk(1, band=band, shape=20), mk(1, band=band, shape=20), mk(1, band=band, shape=23),
+               mk(1, band=band, shape=22 if kind == 2 else 21)]
+    engines[1].set_option(B.OPT_DERIVED_E, 0)
+    assert engines[1].vacuum_cells() == 0
+    for eng in engines[2:]:
+        n_vac = eng.vacuum_cells()
+        assert (n_vac == 0) if band > 63 else (0 < n_vac < npx * npy), n_vac
+
+    def compare(what):
+        ref = [engines[0].get_field(s) for s in range(9)]
+        assert np.abs(ref[0]).max() > 0 and np.all(np.isfinite(ref[0].view(np.float64)))
+        for which, eng in enumerate(engines[1:], 1):
+            for slot in range(9):
+                got = eng.get_field(slot)
+                if not bit_equal(got.view(np.float64), ref[slot].view(np.float64)):
+                    ii, jj = np.nonzero(got != ref[slot])
+                    raise AssertionError("%s: engine %d slot %d: %d cells differ, rows %d..%d, columns %d..%d"
+                                         % (what, which, slot, len(ii), ii.min(), ii.max(), jj.min(), jj.max()))
+
+    def advance(n):
+        args = B.StepArgs()
+        for _ in range(n):
+            L.mpifdtd_upml_step_args(kind, 0, C.byref(args))       # the pulse only
+            for eng in engines:
+                eng.step(args)
+            L.field_nextStep()
+
+    for eng in engines:
+        for slot in range(9):
+            eng.set_field(slot, state[slot])
+    L.field_reset()
+    advance(5)
+    compare("after 5 steps")
+    advance(4)
+    compare("after 9 steps")
+    eps2 = [e.copy() for e in eps]                              # material where there was vacuum: new masks
+    for e in eps2:
+        e[npx // 2, 20:npy - 20:37] = 1.44
+    for eng in engines:
+        for slot, e in enumerate(eps2):
+            eng.set_eps(slot, e)
+    advance(5)
+    compare("after 14 steps, new permittivity")
+    for eng in engines:
+        eng.project()
+    for slot in range(3):
+        want = engines[0].uw(slot)
+        for eng in engines[1:]:
+            assert bit_equal(eng.uw(slot).view(np.float64), want.view(np.float64)), slot
+    for eng in engines:                                         # from rest: E == D == 0 is consistent at once
+        eng.zero()
+        eng.set_field(1 if kind == 2 else 4, state[1])          # ... but a setter call is not
+    L.field_reset()
+    advance(3)
+    compare("after a restart")
+    for eng in engines:
+        eng.close()
+
+
+def test_one_pass_replay_from_a_set_state(plugin_lib):
+    """b200fdtd_run_steps with the one-pass step after b200fdtd_set_field: the first step runs outside the
+    graph (E arrays everywhere), the captured ones keep no E in the vacuum row-strips; same bits as
+    stepping one by one with the option off."""
+    L = plugin_lib
+    npx, npy, steps, kind = 120, 800, 40, 2
+    L.models_setModel(B.MODELS["NO_MODEL"])
+    L.field_init(B.FieldInfo(npx * 10, npy * 10, 10, 10, 500, 30, steps))
+    eps, state = structured_case(npx, npy, kind)
+    plain = make_engine(L, npx, npy, steps, eps, 1, kind=kind)
+    plain.set_option(B.OPT_DERIVED_E, 0)
+    replay = make_engine(L, npx, npy, steps, eps, 1, kind=kind)
+    for eng in (plain, replay):
+        for slot in range(9):
+            eng.set_field(slot, state[slot])
+    L.field_reset()
+    args = B.StepArgs()
+    for _ in range(steps):
+        L.mpifdtd_upml_step_args(kind, 0, C.byref(args))
+        plain.step(args)
+        L.field_nextStep()
+    src = (C.c_char * L.b200fdtd_struct_size(5))()
+    L.field_reset()
+    L.mpifdtd_upml_batch_source.argtypes = [C.c_int, C.c_double, C.c_void_p]
+    L.mpifdtd_upml_batch_source(kind, 30.0, src)
+    B.check(L.b200fdtd_set_batch_sources(replay.h, src), "set_batch_sources")
+    L.b200fdtd_run_steps.argtypes = [C.c_void_p, C.c_double, C.c_int32]
+    B.check(L.b200fdtd_run_steps(replay.h, 0.0, steps), "run_steps")
+    assert replay.vacuum_cells() > 0
+    for slot in range(9):
+        assert bit_equal(replay.get_field(slot).view(np.float64), plain.get_field(slot).view(np.float64)), slot
+    plain.close(); replay.close()
+
+
 def test_launches_per_step(plugin_lib, in_tmp_cwd, monkeypatch):
     gpu = B.Plugin("MIE_CYLINDER", "TM_UPML_2D", 96, steps=10, h_u_nm=20)
     n0 = gpu.launches()
@@ -188,7 +315,9 @@ def test_one_pass_step_is_the_default_on_large_grids(plugin_lib, in_tmp_cwd, mon
         gpu.run()
         gpu.sync()
         per_step = (gpu.launches() - n0) / steps
-        assert per_step == (5 if mode == "2" else 6)     # pre-pass x2 + one pass | (interior + frame) x2; + sample + clock
+        # pre-pass x2 + one pass | (interior + frame) x2; + sample + clock (+ once, the three kernels that build the
+        # row masks of the vacuum row-strips)
+        assert per_step == (5 + 3 / steps if mode == "2" else 6)
         res[mode] = [gpu.any_field(s) for s in range(9)] + [gpu.ntff_uw(s, project=(s == 0)) for s in range(3)]
         gpu.finish()
     assert np.abs(res["0"][0]).max() > 0
