@@ -16,7 +16,9 @@ larger than the 126 MB L2, so no flush is needed between iterations.
   value      whole-job Gcell-updates/s, state resident in HBM, CUDA-event timed on
              the engine's stream, max over ranks.
   roofline   the one-pass kernel (+ its edge pre-pass, timed together, live, CUDA
-             events): algorithmic bytes per launch (TM 232 B per cell-update: reads
+             events): algorithmic bytes per launch (192 B per cell-update in vacuum row-strips -- rows of a tile
+             whose cells all have eps == 1, where E holds the bits of D and does not move; the engine reports
+             how many cells those are -- and elsewhere TM 232 B per cell-update: reads
              Ez,Mx,Bx,My,By,Jz,Dz + eps, writes Mx,Bx,My,By,Jz,Dz,Ez; TE 272) over its
              mean duration, against MEASURED_PEAKS.json hbm_gbs.  `step` carries SURVEY
              8(d)'s contract figure (264 / 288 B) for comparison; `two_kernel_form` the two

@@ -8,6 +8,7 @@
 //              = 272 B (two kernels: 288)
 //   TM lean    reads Ez,Bx,By,Dz + eps (72 B), writes Bx,By,Dz,Ez (64 B) = 136 B   (two kernels: 168)
 //   TE lean    reads Ex,Ey,Bz,Dx,Dy + 2 eps (96 B), writes Bz,Dx,Dy,Ex,Ey (80 B) = 176 B (two: 192)
+//   (in vacuum row-strips -- see below -- the E arrays and eps do not move: 192 B exact, 96 B lean, TM and TE)
 // "exact" evaluates the reference's expressions operation for operation (-fmad=false) and is
 // bit-identical to the two-kernel step; "lean" (B200FDTD_OPT_LEAN_INTERIOR) is the tolerance form
 // of upml_kernels.cu -- cells outside the absorbing frame advance B and D directly -- and is
