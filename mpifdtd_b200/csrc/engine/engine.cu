@@ -362,6 +362,7 @@ int b200fdtd_destroy(b200fdtd_engine *e)
   if (!e) return B200FDTD_OK;
   cudaSetDevice(e->device);
   if (e->stream) cudaStreamSynchronize(e->stream);
+  e->e_stale = false;               // nobody will read the E arrays again: nothing to bring up to date
   for (int s = 0; s < B200FDTD_MAX_FIELDS; s++) cudaFree(e->field[s]);
   cudaFree(e->eps[0]); cudaFree(e->eps[1]);
   cudaFree(e->tab_i); cudaFree(e->tab_j); cudaFree(e->batch_src); cudaFree(e->batch_cw); cudaFree(e->cw_tab);

@@ -1242,6 +1242,7 @@ int b200_launch_fused_edge(b200fdtd_engine *e, const b200fdtd_step_args *a)
   if (rc) return rc;
   if (e->fused.ghost_e == nullptr || e->peer.up_h == nullptr)
     return b200_fail(B200FDTD_ERR_STATE, "one-pass edge kernel without an upper neighbour");
+  if (!use_vac(e, a)) { rc = b200_refresh_e(e); if (rc) return rc; }    // this step reads the E arrays everywhere
   OnePassView f;
   fill_view(e, a, f);
   const int n_rows = e->r_hi - e->r_lo + 1;

@@ -67,6 +67,45 @@ def test_slab_time_shift_tables_tile_the_global_table(plugin_lib, stagger):
     assert total == P
 
 
+@pytest.mark.parametrize("stagger", [0.0, 0.5])
+def test_direct_time_shift_tables_of_the_mpi_variant_solvers_tile_too(plugin_lib, stagger):
+    """Ids 4/5 over several slabs: the direct-formula table (mpiTM_UPML.c:849-1037) of every slab keeps the
+    points whose SAMPLED cell -- one column below the nominal one -- it owns; together they are the
+    single-engine table."""
+    L = plugin_lib
+    L.field_init(B.FieldInfo(900, 2600, 10, 10, 500, 0, 50))
+    box = L.field_getNTFFInfo()
+    P = L.mpifdtd_ntff_point_count(C.byref(box))
+    n_ang, dj = 360, -1
+    L.mpifdtd_ntff_time_shift_direct.restype = C.c_void_p
+    L.mpifdtd_ntff_time_shift_direct.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int]
+    L.mpifdtd_ntff_local_count_shifted.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+
+    def table(j0, nj):
+        n = L.mpifdtd_ntff_local_count_shifted(C.byref(box), dj, j0, nj)
+        ptr = L.mpifdtd_ntff_time_shift_direct(C.byref(box), n_ang, stagger, dj, j0, nj)
+        arr = np.ctypeslib.as_array((C.c_double * (n_ang * max(n, 1))).from_address(ptr)).copy()
+        L.free(C.c_void_p(ptr))
+        return arr[:n_ang * n].reshape(n_ang, n), n
+
+    full, n_full = table(0, 260)
+    assert n_full == P
+    nx = box.right - box.left
+    j_of = np.concatenate([np.full(nx, box.bottom), np.arange(box.bottom, box.top),
+                           np.full(nx, box.top), np.arange(box.bottom, box.top)]) + dj
+    total = 0
+    for world in (2, 5):
+        total = 0
+        for r in range(world):
+            j0, nj = split_columns(260, world, r)
+            local, n = table(j0, nj)
+            mask = (j_of >= j0) & (j_of < j0 + nj)
+            assert n == int(mask.sum())
+            assert np.array_equal(local.view(np.uint64), full[:, mask].view(np.uint64))
+            total += n
+        assert total == P
+
+
 WORKER = r"""
 import os, sys, ctypes as C
 sys.path.insert(0, %(root)r)
