@@ -34,3 +34,18 @@ def test_slabs_from_a_random_state(solver, world, form):
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
     assert "PEER_LOCAL_CHECK %s %s world %d spread random OK" % (solver, form, world) in p.stdout
+
+
+@pytest.mark.parametrize("solver,world,form,start", [("TM_UPML_2D", 3, "fused", "model"), ("TE_UPML_2D", 3, "fused", "random"),
+                                                     ("TM_UPML_2D", 2, "leanfused", "random"),
+                                                     ("TE_UPML_2D", 3, "leanfused", "model")])
+def test_slabs_whose_strips_are_vacuum_row_strips(solver, world, form, start):
+    """1536 columns: every slab is a whole number of 256-column strips, so its first and last columns lie in
+    tile rows where the one-pass step keeps no E arrays (B200FDTD_OPT_DERIVED_E) -- the halo column stored
+    downward comes out of registers, the edge kernel takes the old E from D -- and the fields must still be
+    the single engine's bit for bit."""
+    cmd = [sys.executable, os.path.join(ROOT, "scripts", "peer_local_check.py"), solver, "96", "1536",
+           "420" if start == "model" else "40", str(world), form, "spread", start]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
+    assert "PEER_LOCAL_CHECK %s %s world %d spread %s OK" % (solver, form, world, start) in p.stdout
