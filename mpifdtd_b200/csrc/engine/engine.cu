@@ -1179,6 +1179,9 @@ int b200fdtd_run_steps(b200fdtd_engine *e, double time0, int32_t n_steps)
     done += chunk;
   }
   e->clock_mode = false;
+  // a replayed graph runs none of the launch functions that keep these flags: a getter between two replays
+  // of the same graph has refreshed the E arrays, and the second replay leaves them behind again
+  if (done > 0 && b200_fused_derives_e(e)) e->e_stale = true;
   if (!rc) {
     e->h_stale = !e->store_h;
     if (n.ready && (int)time0 + n_steps > n.steps_recorded) n.steps_recorded = (int)time0 + n_steps;

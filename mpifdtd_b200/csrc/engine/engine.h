@@ -171,6 +171,7 @@ bool b200_want_fused(const b200fdtd_engine *e, const b200fdtd_step_args *a);
 int b200_launch_fused_edge(b200fdtd_engine *e, const b200fdtd_step_args *a);
 int b200_refresh_h(b200fdtd_engine *e);
 int b200_refresh_e(b200fdtd_engine *e);
+bool b200_fused_derives_e(const b200fdtd_engine *e);
 int b200_fused_prepare(b200fdtd_engine *e);
 void b200_fused_release(b200fdtd_engine *e);
 

@@ -1172,6 +1172,13 @@ int b200_fused_prepare(b200fdtd_engine *e)
   return build_vac(e);
 }
 
+// Does a step of this engine (pulse sources) leave the E arrays behind D in the vacuum row-strips?  For callers
+// that replay captured steps, where the launch functions -- which keep e_stale -- do not run.
+bool b200_fused_derives_e(const b200fdtd_engine *e)
+{
+  return b200_want_fused(e, nullptr) && use_vac(e, nullptr);
+}
+
 int b200fdtd_onepass_vacuum_cells(b200fdtd_engine *e, uint64_t *cells)
 {
   if (!e || !cells) return b200_fail(B200FDTD_ERR_ARG, "NULL argument");

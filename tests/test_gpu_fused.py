@@ -267,6 +267,28 @@ def test_one_pass_replay_from_a_set_state(plugin_lib):
     plain.close(); replay.close()
 
 
+def test_getter_between_two_replays_of_the_same_graph(plugin_lib, in_tmp_cwd, monkeypatch):
+    """The plugin on a grid of >= 2^22 cells: one-pass step, update() calls replayed from a 128-step CUDA graph.
+    A getter after the first replay brings the E arrays up to date; the second replay of the SAME graph (no
+    launch function runs) leaves them behind D again in the vacuum row-strips, and the next getter must know."""
+    npx, npy, steps = 2048, 2100, 300
+    monkeypatch.setenv("MPIFDTD_DEFER_CHUNK", "128")
+    res = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("B200FDTD_DERIVED_E", mode)
+        gpu = B.Plugin("MIE_CYLINDER", "TM_UPML_2D", npx, npy, steps=steps, h_u_nm=10, angle_deg=20)
+        snaps = []
+        for n in (128, 128, 44):
+            gpu.step(n)
+            snaps.append(gpu.field("Ez"))
+        snaps += [gpu.any_field(s) for s in range(9)]
+        res[mode] = snaps
+        gpu.finish()
+    assert np.abs(res["0"][1]).max() > 0 and not np.array_equal(res["0"][0], res["0"][1])
+    for n, (a, b) in enumerate(zip(res["1"], res["0"])):
+        assert bit_equal(a, b), n
+
+
 def test_launches_per_step(plugin_lib, in_tmp_cwd, monkeypatch):
     gpu = B.Plugin("MIE_CYLINDER", "TM_UPML_2D", 96, steps=10, h_u_nm=20)
     n0 = gpu.launches()
