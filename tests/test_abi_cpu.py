@@ -101,3 +101,14 @@ def test_product_never_imports_the_oracle():
             if fn.endswith((".py", ".c", ".cu", ".h")):
                 text = open(os.path.join(dirpath, fn), errors="ignore").read()
                 assert "oraclelib" not in text and "reflib" not in text and "liboracle" not in text, fn
+
+
+def test_option_numbers_of_the_binding_match_the_header():
+    """B200FDTD_OPT_* in include/b200fdtd.h are what mpifdtd_b200/binding.py passes to b200fdtd_set_option."""
+    text = open(os.path.join(ROOT, "include", "b200fdtd.h")).read()
+    header = {name: int(value) for name, value in re.findall(r"\bB200FDTD_OPT_([A-Z0-9_]+)\s*=\s*(\d+)", text)}
+    mine = {name[4:]: getattr(B, name) for name in dir(B) if name.startswith("OPT_")}
+    assert mine and set(mine) <= set(header)
+    for name, value in mine.items():
+        assert header[name] == value, name
+    assert len(set(header.values())) == len(header)          # no two options share a number
